@@ -1,0 +1,25 @@
+# Builds libscanet_b200.so (the C-ABI engine) for sm_100a.  `make -j` ; nvcc cross-compiles without a GPU.
+NVCC      ?= /usr/local/cuda/bin/nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v --expt-relaxed-constexpr
+CSRC      := scanet3_b200/csrc
+BUILD     := build
+OBJS      := $(BUILD)/engine.o $(BUILD)/kernels_simt.o $(BUILD)/tc.o $(BUILD)/lstm.o $(BUILD)/group.o $(BUILD)/host_init.o
+LIB       := scanet3_b200/libscanet_b200.so
+
+all: $(LIB)
+
+$(BUILD)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh) include/scanet_b200.h
+	@mkdir -p $(BUILD)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(BUILD)/$*.ptxas.log || (cat $(BUILD)/$*.ptxas.log; exit 1)
+
+$(BUILD)/%.o: $(CSRC)/%.cpp $(wildcard $(CSRC)/*.h) include/scanet_b200.h
+	@mkdir -p $(BUILD)
+	g++ -O2 -std=c++17 -fPIC -Wall -c $< -o $@
+
+$(LIB): $(OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -cudart static -ldl -lpthread
+
+clean:
+	rm -rf $(BUILD) $(LIB)
+.PHONY: all clean

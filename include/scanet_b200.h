@@ -1,0 +1,264 @@
+/* scanet_b200.h -- C ABI of the B200-native train engine for scanet3's data-parallel hot path.
+ *
+ * The reference (pashashiz/scanet3) has no FFI seam of its own for this path: its only native
+ * boundary is TensorFlow-Java's generic JNI behind `Session.runner.feed().fetch().run()`
+ * (src/main/scala/scanet/core/Session.scala:83-94).  The natural seam is the trio of compiled
+ * closures the optimizer obtains and calls (src/main/scala/scanet/optimizers/Optimizer.scala):
+ *
+ *   backprop : (x, y, weights, optParams, state, iter) => (nextWeights, nextOpt, nextState)   :132,142-143,169-194
+ *   loss     : (x, y, params) => (loss, state)                                                :133-134,148,163-167
+ *   agg      : (leftParams, rightParams) => averagedParams  (model + optimizer state)        :196-230
+ *
+ * plus what surrounds them in `optimizeOnPartition` (:106-161): epoch-0 initialisation, the
+ * TensorIterator batch loop (optimizers/Iterators.scala:39-92) and the global step counter.
+ * Each entry point below names the reference lines it replaces.  The JVM-side binding a
+ * maintainer would add (Panama FFM) is shown in INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes only; every tensor is fp32, C-contiguous row-major, conv
+ * tensors NHWC, filters HWIO -- the layout of the reference's `Tensor` direct buffers
+ * (core/TensorCodec.scala:31-41).  Every function returns an `sb_status`; the message of the last
+ * failure on the calling thread is `sb_last_error()`.  There is NO CPU fallback: without a CUDA
+ * device every compute entry point fails with SB_ERR_CUDA.
+ *
+ * Threading: one `sb_engine` = one worker = one GPU (one Spark partition task,
+ * Optimizer.scala:75-85).  An engine is single-owner (no internal locking); different engines may be
+ * driven concurrently from different threads.  `sb_group_*` is called by one coordinator thread.
+ */
+#ifndef SCANET_B200_H
+#define SCANET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_ABI_VERSION 1
+
+typedef enum {
+  SB_OK = 0,
+  SB_ERR_INVALID_ARG = 1, /* reference: IllegalArgumentException via require(...) (core/Require.scala:5-6) */
+  SB_ERR_UNSUPPORTED = 2, /* a reference feature outside the accelerated path (no CPU fallback)          */
+  SB_ERR_CUDA = 3,        /* reference: TF_Status -> RuntimeException (native/package.scala:6-9)          */
+  SB_ERR_NCCL = 4,
+  SB_ERR_STATE = 5        /* call order violated (e.g. train before params are initialised)               */
+} sb_status;
+
+/* ---- model descriptor: the flattened leaf-layer list of `Composed` (layer/Composed.scala:89-99) ---- */
+typedef enum {
+  SB_LAYER_DENSE = 1,     /* layer/Dense.scala:42-71   params: "weights" [in,out]                        */
+  SB_LAYER_BIAS = 2,      /* layer/Bias.scala:22-43    params: "weights" [features]                      */
+  SB_LAYER_ACTIVATE = 3,  /* layer/Activate.scala:12   no params                                         */
+  SB_LAYER_FLATTEN = 4,   /* layer/Flatten.scala:10    no params                                         */
+  SB_LAYER_CONV2D = 5,    /* layer/Conv2D.scala:70-125 params: "weights" [KH,KW,Cin,filters]             */
+  SB_LAYER_POOL2D = 6,    /* layer/Pool2D.scala:28-57  no params; always Max (the layer ignores `reduce`) */
+  SB_LAYER_BATCHNORM = 7, /* layer/BatchNorm.scala:63-174 params: beta,gamma (+state moving_mean/variance) */
+  SB_LAYER_LSTM = 8       /* layer/RNN.scala:208-339   RNN(LSTMCell): per gate kernel/recurrent/bias       */
+} sb_layer_kind;
+
+typedef enum { SB_ACT_IDENTITY = 0, SB_ACT_SIGMOID = 1, SB_ACT_TANH = 2, SB_ACT_SOFTMAX = 3, SB_ACT_RELU = 4 } sb_activation;
+typedef enum { SB_PAD_VALID = 0, SB_PAD_SAME = 1 } sb_padding;
+typedef enum { SB_POOL_MAX = 0, SB_POOL_AVG = 1 } sb_pool_reduce;
+
+/* models/Initializer.scala:28-220.  Random kinds are bit-compatible with TF's seeded Philox ops
+ * (math/rand/AllKernels.scala:12-43); an unseeded random initializer is rejected. */
+typedef enum {
+  SB_INIT_ZEROS = 0,
+  SB_INIT_ONES = 1,
+  SB_INIT_CONST = 2,          /* a = value                     */
+  SB_INIT_RANDOM_UNIFORM = 3, /* a = min, b = max              */
+  SB_INIT_RANDOM_NORMAL = 4,  /* a = mean, b = std             */
+  SB_INIT_GLOROT_UNIFORM = 5,
+  SB_INIT_HE_UNIFORM = 6,
+  SB_INIT_LECUN_UNIFORM = 7,
+  SB_INIT_ORTHOGONAL = 8      /* a = gain (0 => none); QR on the host, values uploaded */
+} sb_init_kind;
+
+typedef struct {
+  int32_t kind;     /* sb_init_kind */
+  int32_t has_seed; /* `seed: Option[Long]` */
+  int64_t seed;
+  float a, b;
+} sb_initializer;
+
+typedef struct {
+  int32_t kind;                 /* sb_layer_kind */
+  int32_t units;                /* Dense outputs | Bias features | Conv2D filters | LSTM units */
+  int32_t activation;           /* Activate: sb_activation; LSTM: cell activation (default Tanh) */
+  int32_t recurrent_activation; /* LSTM (default Sigmoid) */
+  float relu_threshold;         /* ReLU(threshold) (models/Activation.scala:80-83) */
+  int32_t window_h, window_w;   /* Conv2D kernel | Pool2D window */
+  int32_t stride_h, stride_w;
+  int32_t padding;              /* sb_padding */
+  int32_t pool_reduce;          /* sb_pool_reduce, recorded but ignored like the reference layer */
+  int32_t use_bias;             /* LSTM */
+  int32_t trainable;
+  float bn_momentum, bn_epsilon;
+  int32_t bn_mode;              /* 0 = reference (bug-for-bug fused wiring), 1 = correct */
+  int32_t bn_fused;             /* -1 = None (auto), 0 = Some(false), 1 = Some(true) */
+  sb_initializer init[4];       /* [0] kernel | gamma, [1] recurrent | beta, [2] bias | moving_mean,
+                                   [3] forget-bias | moving_variance */
+} sb_layer_desc;
+
+typedef struct {
+  int32_t n_layers;
+  const sb_layer_desc* layers;
+  int32_t input_rank;  /* per-sample feature shape (`ds.shapes._1`, optimizers/SparkExt.scala:36-44) */
+  int64_t input_dims[4];
+  int32_t label_rank;
+  int64_t label_dims[4];
+} sb_model_desc;
+
+typedef enum { SB_LOSS_MSE = 0, SB_LOSS_BCE = 1, SB_LOSS_CCE = 2 } sb_loss; /* models/Loss.scala:18-57 */
+
+/* optimizers/{SGD,Adam,AdaGrad,RMSProp,AdaDelta,Adamax,Nadam,AMSGrad}.scala */
+typedef enum {
+  SB_OPT_SGD = 0, SB_OPT_ADAM = 1, SB_OPT_ADAGRAD = 2, SB_OPT_RMSPROP = 3,
+  SB_OPT_ADADELTA = 4, SB_OPT_ADAMAX = 5, SB_OPT_NADAM = 6, SB_OPT_AMSGRAD = 7
+} sb_optimizer;
+
+/* Arithmetic of the contractions (MatMul / Conv2D fwd, dgrad, wgrad). */
+typedef enum {
+  SB_PREC_FP32 = 0,  /* fp32 FFMA kernels: parity mode */
+  SB_PREC_TF32 = 1,  /* tcgen05 kind::tf32, fp32 accumulate in TMEM (throughput mode) where the shape fits */
+  SB_PREC_3XTF32 = 2 /* split-operand 3xTF32 on tcgen05 (fp32-class accuracy) where the shape fits */
+} sb_precision;
+
+typedef struct {
+  int32_t batch;     /* `.batch(n)` (Optimizer.scala:296-297) */
+  int32_t loss;      /* sb_loss */
+  int32_t optimizer; /* sb_optimizer */
+  float rate;        /* SGD/Adam/AdaGrad/RMSProp/AdaDelta/Adamax/AMSGrad `rate` (Nadam has none) */
+  float beta1;       /* Adam/Adamax/Nadam/AMSGrad beta1 | SGD momentum | RMSProp/AdaDelta rho */
+  float beta2;
+  float epsilon;
+  float init_acc;    /* Adamax/Nadam initial accumulator (Const(initAcc)) */
+  int32_t nesterov;  /* SGD */
+  int32_t minimizing; /* Optimizer.minimize (1) / maximize (0 -> SB_ERR_UNSUPPORTED) */
+  int32_t precision; /* sb_precision */
+  int32_t use_graph; /* 1: capture the step into a CUDA graph (default), 0: eager launches */
+} sb_train_desc;
+
+typedef struct sb_engine sb_engine;
+typedef struct sb_group sb_group;
+
+/* thread-local message of the last failure */
+const char* sb_last_error(void);
+int sb_abi_version(void);
+/* number of visible CUDA devices (0 when there is none; never fails) */
+int sb_device_count(void);
+
+/* Builds the flat parameter arena, streams, kernels' workspaces and the captured step graphs.
+ * Replaces `model.params`, `alg.params`, `compileBackprop`, `compileLoss`
+ * (Optimizer.scala:116-134,163-194).  `device` < 0 builds a PLAN-ONLY engine (no CUDA calls): it
+ * answers sb_param_* / sb_output_dims so host code can be exercised without a GPU; every compute
+ * call on it fails with SB_ERR_CUDA. */
+int sb_engine_create(const sb_model_desc* model, const sb_train_desc* train, int device, sb_engine** out);
+void sb_engine_destroy(sb_engine* e);
+
+/* ---- parameters by the reference's path strings (core/Params.scala:3-81; Optimizer.scala:117-122) ---- */
+typedef enum { SB_ROLE_WEIGHT = 0, SB_ROLE_STATE = 1, SB_ROLE_OPT = 2 } sb_param_role;
+typedef enum { SB_AGG_NONE = 0, SB_AGG_AVG = 1 } sb_aggregation;
+
+int sb_param_count(const sb_engine* e);
+/* path: caller buffer of `path_cap` bytes (NUL-terminated on return); dims: up to 4 entries */
+int sb_param_info(const sb_engine* e, int index, char* path, size_t path_cap, int64_t* dims, int32_t* rank,
+                  int32_t* role, int32_t* aggregation, int64_t* arena_offset);
+int sb_output_dims(const sb_engine* e, int64_t* dims, int32_t* rank); /* model.outputShape incl. batch */
+
+/* H2D / D2H of one tensor (`initParams`, broadcast in, `StepResult` out, `Tensor` read-back:
+ * Optimizer.scala:72-73,124-126,149-155; core/Tensor.scala:13-32). n = element count (checked). */
+int sb_params_set(sb_engine* e, const char* path, const float* host, size_t n);
+int sb_params_get(sb_engine* e, const char* path, float* host, size_t n);
+/* run the declared initializers on the device (Optimizer.scala:123-131; optimizer state too) */
+int sb_init_params(sb_engine* e);
+/* only the optimizer state (when model params came from `initParams`) */
+int sb_init_opt_params(sb_engine* e);
+
+/* ---- the train path ---- */
+/* shard resident in HBM (the partition iterator + TensorIterator, Iterators.scala:39-83).
+ * x: [n_rows, prod(input_dims)], y: [n_rows, prod(label_dims)]; host memory (pinned or pageable). */
+int sb_dataset_upload(sb_engine* e, const float* x, const float* y, int64_t n_rows);
+/* one epoch of `optimizeOnPartition` (Optimizer.scala:135-157): all FULL batches in row order
+ * (partial tail dropped), iter = global_iter + j + 1, then the forward-only loss on the last batch
+ * with the updated params.  No host sync inside the epoch.  Fewer rows than one batch ->
+ * SB_ERR_INVALID_ARG (the reference throws NoSuchElementException, Iterators.scala:79-81). */
+int sb_train_epoch(sb_engine* e, int64_t global_iter, int64_t* iterations_out, float* last_loss_out);
+/* asynchronous variant: enqueue `n_steps` batches starting at batch `first_batch` of the shard */
+int sb_train_steps_async(sb_engine* e, int64_t global_iter, int64_t first_batch, int64_t n_steps);
+/* single `backprop` call on HOST buffers x[batch,...], y[batch,...] with iter = `iter` (1-based global
+ * step): H2D copy, forward, loss, backward, update.  `loss_out` (optional) receives the PRE-update loss
+ * of this batch after a D2H read (one sync). */
+int sb_train_step(sb_engine* e, const float* x, const float* y, int64_t iter, float* loss_out);
+/* asynchronous `backprop` on HOST buffers: enqueues the H2D copies of x,y (pinned memory for real overlap), the
+ * step, and a D2H read of the PRE-update loss into `loss_out_host` (pinned; may be NULL).  No sync: call sb_sync
+ * before reading the loss or reusing x / y. */
+int sb_train_step_async(sb_engine* e, const float* x, const float* y, int64_t iter, float* loss_out_host);
+/* the `loss` closure on HOST buffers (training-mode forward, state discarded) */
+int sb_eval_loss(sb_engine* e, const float* x, const float* y, float* loss_out);
+/* forward only (`TrainedModel.result`, models/Model.scala:154-163): out[batch, ...] on the host */
+int sb_predict(sb_engine* e, const float* x, float* out, size_t n_out);
+/* gradients of the trainable weights for one HOST batch without updating anything
+ * (`LossModel.grad`, models/Model.scala:107-111) -- parity-test hook. */
+int sb_compute_grads(sb_engine* e, const float* x, const float* y, float* loss_out);
+int sb_grad_get(sb_engine* e, const char* weight_path, float* host, size_t n);
+int sb_sync(sb_engine* e);
+
+/* ---- raw access for host plumbing (torch.distributed over NCCL, timing on the right stream) ---- */
+/* device pointer + float count of the averaged arena region [model params | optimizer state] */
+int sb_arena(sb_engine* e, void** device_ptr, int64_t* n_floats);
+/* cudaStream_t the engine launches on (for CUDA-event timing by the caller) */
+int sb_stream(sb_engine* e, void** stream);
+/* scale the whole arena by `w` on the engine's stream (pre-multiply of a weighted all-reduce) */
+int sb_arena_scale(sb_engine* e, float w);
+/* re-initialise tensors whose ParamDef.aggregation == None (Optimizer.scala:209) */
+int sb_reset_unaggregated(sb_engine* e);
+/* cudaIpcMemHandle_t (64 bytes) of the arena allocation, for peer mapping from another process */
+int sb_arena_ipc_handle(sb_engine* e, void* handle64, int64_t* byte_offset);
+
+/* ---- epoch-end averaging across the k workers of one box: `treeReduce(aggregateParams)`
+ * (Optimizer.scala:86,196-230; models/Aggregation.scala:16-19) ---- */
+typedef enum {
+  SB_AVG_MEAN = 0,        /* arithmetic mean (== the reference for k <= 2)                       */
+  SB_AVG_SPARK_CHAIN = 1, /* chain of pairwise (l+r)/2 in Spark's treeReduce shape, canonical order  */
+  SB_AVG_WEIGHTS = 2      /* caller-supplied convex weights                                      */
+} sb_avg_mode;
+typedef enum {
+  SB_COLL_P2P = 0,  /* one fused kernel per GPU: peer loads over NVLink, weighted sum in rank order
+                       (bit-identical to the chain), state reset; needs peer access               */
+  SB_COLL_NCCL = 1  /* pre-scale + ncclAllReduce(sum) (libnccl loaded with dlopen)               */
+} sb_collective;
+
+int sb_group_create(sb_engine** engines, int k, int avg_mode, const float* weights_or_null, int collective,
+                    sb_group** out);
+/* averages the arenas in place on every engine, resets aggregation==None tensors, combines
+ * loss (same weights) and iterations (plain sum, Optimizer.scala:223).  In/out arrays of length k;
+ * on return every entry holds the combined value. */
+int sb_group_average(sb_group* g, float* loss_inout, int64_t* iterations_inout);
+void sb_group_destroy(sb_group* g);
+/* One process per GPU (torchrun / one JVM executor per GPU): `handles` = k x 64 bytes, entry q = rank q's
+ * sb_arena_ipc_handle.  sb_group_average_local launches THIS rank's slice of the fused P2P reduce on the
+ * engine stream; the caller places a cross-process barrier before it (all epochs done) and after it
+ * (all slices stored), then calls sb_reset_unaggregated and combines loss/iterations itself. */
+int sb_group_create_ipc(sb_engine* self, int rank, int k, const void* handles, int avg_mode,
+                        const float* weights_or_null, sb_group** out);
+int sb_group_average_local(sb_group* g);
+/* effective weights the group applies (length k) */
+int sb_group_weights(const sb_group* g, float* weights_out);
+/* the Spark 3.3.1 treeReduce(depth=2) weight vector for k partitions in ascending completion order */
+int sb_spark_chain_weights(int k, float* weights_out);
+
+/* ---- per-kernel-class device timing (CUDA events on the engine stream, eager mode) ---- */
+int sb_profile_enable(sb_engine* e, int on);
+int sb_profile_count(const sb_engine* e);
+int sb_profile_get(const sb_engine* e, int index, char* name, size_t name_cap, double* total_ms, int64_t* launches,
+                   double* algorithmic_bytes, double* algorithmic_flops);
+int sb_profile_reset(sb_engine* e);
+/* kernels launched by this engine since creation (graph replays count their kernel nodes) */
+int64_t sb_launch_count(const sb_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCANET_B200_H */

@@ -65,7 +65,8 @@ def philox_uniform(seed: int, n: int) -> np.ndarray:
 
 def _box_muller(x0: np.ndarray, x1: np.ndarray):
     u1 = np.maximum(uint32_to_float(x0), np.float32(1.0e-7))
-    v1 = np.float32(2.0 * np.pi) * uint32_to_float(x1)
+    # `const float v1 = 2.0f * M_PI * Uint32ToFloat(x1)`: the product is evaluated in double, rounded once
+    v1 = (np.float64(2.0 * np.pi) * uint32_to_float(x1).astype(np.float64)).astype(np.float32)
     u2 = np.sqrt(np.float32(-2.0) * np.log(u1)).astype(np.float32)
     return (np.sin(v1) * u2).astype(np.float32), (np.cos(v1) * u2).astype(np.float32)
 

@@ -1,0 +1,1152 @@
+// scanet-b200 engine: model descriptor -> plan (flat arena, activation buffers, op schedule) ->
+// eager or CUDA-graph execution of the reference's train step.  Reference lines cited are under
+// /root/reference/src/main/scala/scanet/.
+#include "engine.h"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <memory>
+
+#include "common.cuh"
+#include "tc.h"
+
+using namespace sb;
+
+// -------------------------------------------------------------------------------------------------
+// error plumbing
+// -------------------------------------------------------------------------------------------------
+static thread_local std::string tl_error;
+namespace sb {
+struct ApiError : std::runtime_error {
+  int code;
+  ApiError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+void set_error(const std::string& m) { tl_error = m; }
+}  // namespace sb
+#define SB_FAIL(code, msg) throw ::sb::ApiError((code), (msg))
+#define SB_API_BEGIN try {
+#define SB_API_END                      \
+  }                                     \
+  catch (const ::sb::ApiError& e) {     \
+    tl_error = e.what();                \
+    return e.code;                      \
+  }                                     \
+  catch (const ::sb::CudaError& e) {    \
+    tl_error = e.what();                \
+    return SB_ERR_CUDA;                 \
+  }                                     \
+  catch (const std::exception& e) {     \
+    tl_error = e.what();                \
+    return SB_ERR_INVALID_ARG;          \
+  }                                     \
+  return SB_OK;
+
+extern "C" const char* sb_last_error(void) { return tl_error.c_str(); }
+extern "C" int sb_abi_version(void) { return SB_ABI_VERSION; }
+extern "C" int sb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+static void need_device(const sb_engine* e) {
+  if (e == nullptr) SB_FAIL(SB_ERR_INVALID_ARG, "null engine");
+  if (e->plan_only)
+    SB_FAIL(SB_ERR_CUDA, "plan-only engine (device < 0): no CUDA device bound; this library has no CPU fallback");
+}
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    SB_CUDA(cudaGetDevice(&prev));
+    if (prev != dev) SB_CUDA(cudaSetDevice(dev));
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// -------------------------------------------------------------------------------------------------
+// plan
+// -------------------------------------------------------------------------------------------------
+static int64_t pad32(int64_t n) { return (n + 31) / 32 * 32; }
+
+static void conv_pad(int padding, int in, int k, int s, int* out, int* before) {
+  // TF padding arithmetic (math/nn/AllKernels.scala:39-65)
+  if (padding == SB_PAD_VALID) {
+    *out = (in - k + 1 + s - 1) / s;
+    *before = 0;
+  } else {
+    *out = (in + s - 1) / s;
+    int total = std::max((*out - 1) * s + k - in, 0);
+    *before = total / 2;
+  }
+}
+
+static int add_param(sb_engine* e, const std::string& path, std::initializer_list<int64_t> dims, int role, int agg,
+                     const sb_initializer& init, int layer) {
+  Param p;
+  p.path = path;
+  p.rank = (int)dims.size();
+  int i = 0;
+  p.numel = 1;
+  for (int64_t d : dims) {
+    p.dims[i++] = d;
+    p.numel *= d;
+  }
+  p.padded = pad32(p.numel);
+  p.role = role;
+  p.agg = agg;
+  p.init = init;
+  p.layer = layer;
+  if (e->by_path.count(path)) SB_FAIL(SB_ERR_INVALID_ARG, "duplicate param path " + path);
+  e->by_path[path] = (int)e->params.size();
+  e->params.push_back(p);
+  return (int)e->params.size() - 1;
+}
+
+static const char* kGateNames[4] = {"forget", "input", "gate", "output"};
+
+static int opt_slots(int kind) {
+  switch (kind) {
+    case SB_OPT_SGD: case SB_OPT_ADAGRAD: case SB_OPT_RMSPROP: return 1;
+    case SB_OPT_ADAM: case SB_OPT_ADADELTA: case SB_OPT_ADAMAX: case SB_OPT_NADAM: return 2;
+    case SB_OPT_AMSGRAD: return 3;
+  }
+  SB_FAIL(SB_ERR_INVALID_ARG, "unknown optimizer kind");
+}
+static const char* opt_slot_name(int kind, int slot) {
+  // state paths `<weightPath>/<stateName>` (Optimizer.scala:118-121,187)
+  static const char* names[8][3] = {{"velocity", "", ""},        {"momentum", "velocity", ""},
+                                    {"grad_acc", "", ""},        {"avg_grad", "", ""},
+                                    {"avg_grad", "avg_delta", ""}, {"momentum_1", "momentum_2", ""},
+                                    {"momentum", "velocity", ""}, {"momentum", "velocity", "corrected_velocity"}};
+  return names[kind][slot];
+}
+
+static void build_plan(sb_engine* e) {
+  const sb_model_desc& m = e->model;
+  const sb_train_desc& t = e->train;
+  if (m.n_layers <= 0) SB_FAIL(SB_ERR_INVALID_ARG, "requirement failed: at least 1 layer is required");
+  if (t.batch <= 0) SB_FAIL(SB_ERR_INVALID_ARG, "batch must be positive");
+  if (m.input_rank < 0 || m.input_rank > 3 || m.label_rank < 0 || m.label_rank > 3)
+    SB_FAIL(SB_ERR_INVALID_ARG, "input/label rank must be in [0,3]");
+  if (!t.minimizing) SB_FAIL(SB_ERR_UNSUPPORTED, "Optimizer.maximize is outside the accelerated path");
+  if (t.loss < SB_LOSS_MSE || t.loss > SB_LOSS_CCE) SB_FAIL(SB_ERR_INVALID_ARG, "unknown loss");
+  e->n_slots = opt_slots(t.optimizer);
+
+  Shape cur;
+  cur.rank = m.input_rank + 1;
+  cur.d[0] = t.batch;
+  for (int i = 0; i < m.input_rank; ++i) cur.d[i + 1] = m.input_dims[i];
+  e->in_shape = cur;
+  e->label_shape.rank = m.label_rank + 1;
+  e->label_shape.d[0] = t.batch;
+  for (int i = 0; i < m.label_rank; ++i) e->label_shape.d[i + 1] = m.label_dims[i];
+  e->x_per_row = cur.numel() / t.batch;
+  e->y_per_row = e->label_shape.numel() / t.batch;
+
+  int cur_buf = 0;
+  std::vector<int64_t> buf_numel{cur.numel()};
+  std::vector<char> output_needed{0};
+  bool any_trainable_before = false;
+  e->L.resize(m.n_layers);
+  for (int li = 0; li < m.n_layers; ++li) {
+    LayerPlan& L = e->L[li];
+    L.d = m.layers[li];
+    for (int k = 0; k < 16; ++k) L.p_aux[k] = -1;
+    L.in = cur;
+    L.buf_in = cur_buf;
+    L.need_dx = any_trainable_before;
+    const sb_layer_desc& d = L.d;
+    const std::string pre = std::to_string(li) + "/";
+    Shape out = cur;
+    bool new_buf = true;
+    switch (d.kind) {
+      case SB_LAYER_DENSE: {
+        if (cur.rank != 2) SB_FAIL(SB_ERR_INVALID_ARG, "Dense requires input Shape(batch, features)");
+        if (d.units <= 0) SB_FAIL(SB_ERR_INVALID_ARG, "Dense outputs must be positive");
+        if (!d.trainable) SB_FAIL(SB_ERR_UNSUPPORTED, "frozen layers are outside the accelerated path");
+        L.p_w = add_param(e, pre + "weights", {cur.d[1], (int64_t)d.units}, SB_ROLE_WEIGHT, SB_AGG_AVG, d.init[0], li);
+        out.d[1] = d.units;
+        any_trainable_before = true;
+        break;
+      }
+      case SB_LAYER_BIAS: {
+        if (cur.d[cur.rank - 1] != d.units) SB_FAIL(SB_ERR_INVALID_ARG, "Bias features must equal the last input dimension");
+        if (!d.trainable) SB_FAIL(SB_ERR_UNSUPPORTED, "frozen layers are outside the accelerated path");
+        L.p_w = add_param(e, pre + "weights", {(int64_t)d.units}, SB_ROLE_WEIGHT, SB_AGG_AVG, d.init[2], li);
+        new_buf = (cur_buf == 0) || output_needed[cur_buf];
+        any_trainable_before = true;
+        break;
+      }
+      case SB_LAYER_ACTIVATE: {
+        if (d.activation < SB_ACT_IDENTITY || d.activation > SB_ACT_RELU) SB_FAIL(SB_ERR_INVALID_ARG, "unknown activation");
+        if (d.activation == SB_ACT_SOFTMAX && cur.rank != 2) SB_FAIL(SB_ERR_INVALID_ARG, "Softmax requires a rank-2 input");
+        new_buf = (cur_buf == 0) || output_needed[cur_buf];
+        break;
+      }
+      case SB_LAYER_FLATTEN: {
+        if (cur.rank < 2) SB_FAIL(SB_ERR_INVALID_ARG, "requirement failed: rank should be >= 2");
+        out.rank = 2;
+        out.d[1] = cur.numel() / cur.d[0];
+        new_buf = false;  // a view
+        break;
+      }
+      case SB_LAYER_CONV2D: {
+        if (cur.rank != 4) SB_FAIL(SB_ERR_INVALID_ARG, "Conv2D input should have a shape (NHWC)");
+        if (!d.trainable) SB_FAIL(SB_ERR_UNSUPPORTED, "frozen layers are outside the accelerated path");
+        if (d.units <= 0 || d.window_h <= 0 || d.window_w <= 0 || d.stride_h <= 0 || d.stride_w <= 0)
+          SB_FAIL(SB_ERR_INVALID_ARG, "Conv2D filters/kernel/strides must be positive");
+        if (d.padding != SB_PAD_VALID && d.padding != SB_PAD_SAME) SB_FAIL(SB_ERR_UNSUPPORTED, "EXPLICIT padding is unsupported");
+        ConvGeom& g = L.cg;
+        g.N = (int)cur.d[0]; g.H = (int)cur.d[1]; g.W = (int)cur.d[2]; g.Cin = (int)cur.d[3];
+        g.Cout = d.units; g.KH = d.window_h; g.KW = d.window_w; g.SH = d.stride_h; g.SW = d.stride_w;
+        conv_pad(d.padding, g.H, g.KH, g.SH, &g.OH, &g.PT);
+        conv_pad(d.padding, g.W, g.KW, g.SW, &g.OW, &g.PL);
+        if (g.OH <= 0 || g.OW <= 0) SB_FAIL(SB_ERR_INVALID_ARG, "Conv2D output would be empty");
+        L.p_w = add_param(e, pre + "weights", {(int64_t)g.KH, (int64_t)g.KW, (int64_t)g.Cin, (int64_t)g.Cout}, SB_ROLE_WEIGHT,
+                          SB_AGG_AVG, d.init[0], li);
+        out.d[1] = g.OH; out.d[2] = g.OW; out.d[3] = g.Cout;
+        any_trainable_before = true;
+        break;
+      }
+      case SB_LAYER_POOL2D: {
+        if (cur.rank != 4) SB_FAIL(SB_ERR_INVALID_ARG, "Pool2D input should have a shape (NHWC)");
+        if (d.padding != SB_PAD_VALID && d.padding != SB_PAD_SAME)
+          SB_FAIL(SB_ERR_INVALID_ARG, "requirement failed: only [Same, Valid] paddings are supported");
+        if (d.window_h <= 0 || d.window_w <= 0 || d.stride_h <= 0 || d.stride_w <= 0)
+          SB_FAIL(SB_ERR_INVALID_ARG, "Pool2D window/strides must be positive");
+        PoolGeom& g = L.pg;
+        g.N = (int)cur.d[0]; g.H = (int)cur.d[1]; g.W = (int)cur.d[2]; g.C = (int)cur.d[3];
+        g.KH = d.window_h; g.KW = d.window_w; g.SH = d.stride_h; g.SW = d.stride_w;
+        conv_pad(d.padding, g.H, g.KH, g.SH, &g.OH, &g.PT);
+        conv_pad(d.padding, g.W, g.KW, g.SW, &g.OW, &g.PL);
+        if (g.OH <= 0 || g.OW <= 0) SB_FAIL(SB_ERR_INVALID_ARG, "Pool2D output would be empty");
+        out.d[1] = g.OH; out.d[2] = g.OW;
+        break;
+      }
+      case SB_LAYER_BATCHNORM: {
+        if (cur.rank != 2 && cur.rank != 4) SB_FAIL(SB_ERR_UNSUPPORTED, "BatchNorm supports rank-2 and rank-4 (NHWC) inputs, axes=[-1]");
+        if (!d.trainable) SB_FAIL(SB_ERR_UNSUPPORTED, "frozen layers are outside the accelerated path");
+        int64_t C = cur.d[cur.rank - 1];
+        L.bn_fused = (cur.rank == 4) && d.bn_fused != 0;
+        if (d.bn_fused == 1 && cur.rank != 4) SB_FAIL(SB_ERR_INVALID_ARG, "Cannot use fused implementation with this input shape");
+        // param shape = input shape with every non-axes dim set to 1 (layer/BatchNorm.scala:79-87)
+        auto bn_param = [&](const char* name, int role, const sb_initializer& in) {
+          if (cur.rank == 2) return add_param(e, pre + name, {1, C}, role, SB_AGG_AVG, in, li);
+          return add_param(e, pre + name, {1, 1, 1, C}, role, SB_AGG_AVG, in, li);
+        };
+        L.p_aux[0] = bn_param("beta", SB_ROLE_WEIGHT, d.init[1]);
+        L.p_aux[1] = bn_param("gamma", SB_ROLE_WEIGHT, d.init[0]);
+        L.p_aux[2] = bn_param("moving_mean", SB_ROLE_STATE, d.init[2]);
+        L.p_aux[3] = bn_param("moving_variance", SB_ROLE_STATE, d.init[3]);
+        any_trainable_before = true;
+        break;
+      }
+      case SB_LAYER_LSTM: {
+        if (cur.rank != 3) SB_FAIL(SB_ERR_INVALID_ARG, "requirement failed: RNN requires input to have Shape(batch, time, features)");
+        if (!d.trainable) SB_FAIL(SB_ERR_UNSUPPORTED, "frozen layers are outside the accelerated path");
+        if (d.units <= 0) SB_FAIL(SB_ERR_INVALID_ARG, "requirement failed: RNN Cell should contain at least one unit");
+        int64_t F = cur.d[2], U = d.units;
+        for (int gi = 0; gi < 4; ++gi) {
+          std::string gp = pre + kGateNames[gi] + "/";
+          L.p_aux[gi * 3 + 0] = add_param(e, gp + "0/kernel_weights", {F, U}, SB_ROLE_WEIGHT, SB_AGG_AVG, d.init[0], li);
+          L.p_aux[gi * 3 + 1] = add_param(e, gp + "0/recurrent_weights", {U, U}, SB_ROLE_WEIGHT, SB_AGG_AVG, d.init[1], li);
+          if (d.use_bias)
+            L.p_aux[gi * 3 + 2] = add_param(e, gp + "1/weights", {U}, SB_ROLE_WEIGHT, SB_AGG_AVG, gi == 0 ? d.init[3] : d.init[2], li);
+        }
+        out.rank = 2;
+        out.d[1] = U;
+        any_trainable_before = true;
+        break;
+      }
+      default:
+        SB_FAIL(SB_ERR_INVALID_ARG, "unknown layer kind " + std::to_string(d.kind));
+    }
+    L.out = out;
+    if (new_buf) {
+      buf_numel.push_back(out.numel());
+      output_needed.push_back(0);
+      cur_buf = (int)buf_numel.size() - 1;
+      L.inplace = false;
+    } else {
+      L.inplace = true;
+    }
+    if (d.kind == SB_LAYER_ACTIVATE) output_needed[cur_buf] = 1;
+    L.buf_out = cur_buf;
+    cur = out;
+  }
+  e->out_shape = cur;
+  if (cur.numel() != e->label_shape.numel())
+    SB_FAIL(SB_ERR_INVALID_ARG, "model output " + std::to_string(cur.numel()) + " elements per batch does not match the labels " +
+                                    std::to_string(e->label_shape.numel()));
+  if (cur_buf == 0) SB_FAIL(SB_ERR_INVALID_ARG, "the model has no computing layer");
+  e->act_numel = buf_numel;
+
+  // arena layout: [trainable weights | state | opt slot 0 | opt slot 1 | opt slot 2]; weights first so that the
+  // fused optimizer is one element-wise pass over nW floats and the gradient buffer mirrors the weight region.
+  int64_t off = 0;
+  for (auto& p : e->params)
+    if (p.role == SB_ROLE_WEIGHT) { p.offset = off; off += p.padded; }
+  e->nW = off;
+  for (auto& p : e->params)
+    if (p.role == SB_ROLE_STATE) { p.offset = off; off += p.padded; }
+  e->nS = off - e->nW;
+  const int n_model = (int)e->params.size();
+  for (int slot = 0; slot < e->n_slots; ++slot)
+    for (int wi = 0; wi < n_model; ++wi) {
+      if (e->params[wi].role != SB_ROLE_WEIGHT) continue;
+      const Param w = e->params[wi];
+      sb_initializer in{};
+      in.kind = SB_INIT_ZEROS;
+      if (t.optimizer == SB_OPT_ADAMAX || t.optimizer == SB_OPT_NADAM) {  // Const(initAcc) (Adamax.scala:32-40)
+        in.kind = SB_INIT_CONST;
+        in.a = t.init_acc;
+      }
+      int pi;
+      switch (w.rank) {
+        case 1: pi = add_param(e, w.path + "/" + opt_slot_name(t.optimizer, slot), {w.dims[0]}, SB_ROLE_OPT, SB_AGG_AVG, in, w.layer); break;
+        case 2: pi = add_param(e, w.path + "/" + opt_slot_name(t.optimizer, slot), {w.dims[0], w.dims[1]}, SB_ROLE_OPT, SB_AGG_AVG, in, w.layer); break;
+        default: pi = add_param(e, w.path + "/" + opt_slot_name(t.optimizer, slot), {w.dims[0], w.dims[1], w.dims[2], w.dims[3]}, SB_ROLE_OPT, SB_AGG_AVG, in, w.layer); break;
+      }
+      Param& op = e->params[pi];
+      op.weight_param = wi;
+      op.slot = slot;
+      op.offset = e->nW + e->nS + (int64_t)slot * e->nW + w.offset;
+    }
+  e->arena_floats = e->nW + e->nS + (int64_t)e->n_slots * e->nW;
+}
+
+// -------------------------------------------------------------------------------------------------
+// allocation
+// -------------------------------------------------------------------------------------------------
+static float* dmalloc_floats(int64_t n) {
+  void* p = nullptr;
+  SB_CUDA(cudaMalloc(&p, (size_t)std::max<int64_t>(n, 32) * sizeof(float)));
+  return (float*)p;
+}
+
+static void allocate(sb_engine* e) {
+  SB_CUDA(cudaSetDevice(e->device));
+  SB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  e->arena = dmalloc_floats(e->arena_floats);
+  SB_CUDA(cudaMemsetAsync(e->arena, 0, (size_t)e->arena_floats * 4, e->stream));
+  e->grads = dmalloc_floats(e->nW);
+  SB_CUDA(cudaMemsetAsync(e->grads, 0, (size_t)std::max<int64_t>(e->nW, 32) * 4, e->stream));
+  const int nb = (int)e->act_numel.size();
+  e->acts.assign(nb, nullptr);
+  e->dacts.assign(nb, nullptr);
+  for (int i = 0; i < nb; ++i) {
+    e->acts[i] = dmalloc_floats(pad32(e->act_numel[i]));
+    if (i > 0) e->dacts[i] = dmalloc_floats(pad32(e->act_numel[i]));
+  }
+  e->by = dmalloc_floats(pad32(e->label_shape.numel()));
+  void* p = nullptr;
+  SB_CUDA(cudaMalloc(&p, sizeof(StepState)));
+  e->st = (StepState*)p;
+  SB_CUDA(cudaMemsetAsync(e->st, 0, sizeof(StepState), e->stream));
+  SB_CUDA(cudaMallocHost(&p, sizeof(StepState) * 4));
+  e->st_host = (StepState*)p;
+  memset(e->st_host, 0, sizeof(StepState) * 4);
+  e->ws_floats = (size_t)16 << 20;  // 64 MB: split-K partials, column-reduction partials
+  e->ws = dmalloc_floats((int64_t)e->ws_floats);
+  for (auto& L : e->L) {
+    if (L.d.kind == SB_LAYER_BATCHNORM) {
+      int64_t C = L.in.d[L.in.rank - 1];
+      L.bn_save_mean = dmalloc_floats(C);
+      L.bn_save_var = dmalloc_floats(C);
+    }
+  }
+  tc_plan_layers(e);  // tensor-core fast paths (TMA descriptors, padded-grid buffers)
+  SB_CUDA(cudaStreamSynchronize(e->stream));
+}
+
+// -------------------------------------------------------------------------------------------------
+// profiling scopes (eager mode only)
+// -------------------------------------------------------------------------------------------------
+namespace {
+struct Prof {
+  sb_engine* e;
+  int idx = -1;
+  cudaEvent_t a = nullptr, b = nullptr;
+  long long launches0 = 0;
+  Prof(sb_engine* e_, const char* name, double bytes, double flops) : e(e_) {
+    if (!e->profiling) return;
+    auto it = e->prof_by_name.find(name);
+    if (it == e->prof_by_name.end()) {
+      e->prof_by_name[name] = idx = (int)e->prof.size();
+      ProfEntry pe;
+      pe.name = name;
+      e->prof.push_back(pe);
+    } else {
+      idx = it->second;
+    }
+    e->prof[idx].bytes += bytes;
+    e->prof[idx].flops += flops;
+    launches0 = tl_launch_count;
+    SB_CUDA(cudaEventCreate(&a));
+    SB_CUDA(cudaEventCreate(&b));
+    SB_CUDA(cudaEventRecord(a, e->stream));
+  }
+  ~Prof() {
+    if (idx < 0) return;
+    cudaEventRecord(b, e->stream);
+    e->prof[idx].launches += tl_launch_count - launches0;
+    e->prof_pending.push_back(ProfPending{idx, a, b});
+  }
+};
+}  // namespace
+
+static void prof_resolve(sb_engine* e) {
+  if (e->prof_pending.empty()) return;
+  SB_CUDA(cudaStreamSynchronize(e->stream));
+  for (auto& pp : e->prof_pending) {
+    float ms = 0;
+    SB_CUDA(cudaEventElapsedTime(&ms, pp.a, pp.b));
+    e->prof[pp.entry].total_ms += ms;
+    cudaEventDestroy(pp.a);
+    cudaEventDestroy(pp.b);
+  }
+  e->prof_pending.clear();
+}
+
+// -------------------------------------------------------------------------------------------------
+// the train step
+// -------------------------------------------------------------------------------------------------
+static float* P(sb_engine* e, int pi) { return e->arena + e->params[pi].offset; }
+static float* G(sb_engine* e, int pi) { return e->grads + e->params[pi].offset; }
+
+enum FwdMode { FWD_TRAIN = 0, FWD_LOSS_ONLY = 1, FWD_INFER = 2 };
+
+static void run_forward(sb_engine* e, int mode) {
+  cudaStream_t s = e->stream;
+  const int nl = (int)e->L.size();
+  for (int li = 0; li < nl; ++li) {
+    LayerPlan& L = e->L[li];
+    if (L.fused_into_prev) continue;
+    if (e->softmax_cce_fused && li == nl - 1 && mode != FWD_INFER) continue;  // executed by the loss kernel
+    float* in = e->acts[L.buf_in];
+    float* out = e->acts[L.buf_out];
+    const int64_t n_out = L.out.numel();
+    switch (L.d.kind) {
+      case SB_LAYER_DENSE: {
+        const int M = (int)L.in.d[0], K = (int)L.in.d[1], N = (int)L.out.d[1];
+        if (L.tc_kind && tc_dense_fwd(e, L, li)) break;
+        Prof pr(e, "dense_fwd_f32", 4.0 * ((double)M * K + (double)K * N + (double)M * N), 2.0 * M * N * K);
+        gemm_nn(in, P(e, L.p_w), out, M, N, K, e->ws, e->ws_floats, s);
+        break;
+      }
+      case SB_LAYER_BIAS: {
+        Prof pr(e, "bias_add", 8.0 * n_out, 0);
+        if (!L.inplace) SB_CUDA(cudaMemcpyAsync(out, in, (size_t)n_out * 4, cudaMemcpyDeviceToDevice, s));
+        bias_add(out, P(e, L.p_w), n_out / L.d.units, L.d.units, s);
+        break;
+      }
+      case SB_LAYER_ACTIVATE: {
+        Prof pr(e, "act_fwd", 8.0 * n_out, 0);
+        if (!L.inplace) SB_CUDA(cudaMemcpyAsync(out, in, (size_t)n_out * 4, cudaMemcpyDeviceToDevice, s));
+        if (L.d.activation == SB_ACT_SOFTMAX) softmax_fwd(out, (int)L.out.d[0], (int)L.out.d[1], s);
+        else act_fwd(out, L.d.activation, L.d.relu_threshold, n_out, s);
+        break;
+      }
+      case SB_LAYER_FLATTEN:
+        break;
+      case SB_LAYER_CONV2D: {
+        const ConvGeom& g = L.cg;
+        if (L.tc_kind && tc_conv_fwd(e, L, li)) break;
+        Prof pr(e, "conv2d_fwd_f32", 4.0 * ((double)L.in.numel() + n_out + e->params[L.p_w].numel),
+                2.0 * g.N * g.OH * g.OW * (double)g.Cout * g.KH * g.KW * g.Cin);
+        conv2d_fwd(in, P(e, L.p_w), out, g, e->ws, e->ws_floats, s);
+        break;
+      }
+      case SB_LAYER_POOL2D: {
+        Prof pr(e, "pool_fwd", 4.0 * ((double)L.in.numel() + n_out), 0);
+        pool_fwd(in, out, L.pg, SB_POOL_MAX, s);  // the layer ignores `reduce` (layer/Pool2D.scala:36-42)
+        break;
+      }
+      case SB_LAYER_BATCHNORM: {
+        const int C = (int)L.in.d[L.in.rank - 1];
+        const long long rows = L.in.numel() / C;
+        Prof pr(e, "batchnorm_fwd", 4.0 * (3.0 * L.in.numel()), 0);
+        if (mode == FWD_INFER) {
+          bn_fwd_infer(in, out, P(e, L.p_aux[1]), P(e, L.p_aux[0]), P(e, L.p_aux[2]), P(e, L.p_aux[3]), rows, C, L.d.bn_epsilon,
+                       L.bn_fused, s);
+        } else {
+          bn_fwd(in, out, P(e, L.p_aux[1]), P(e, L.p_aux[0]), P(e, L.p_aux[2]), P(e, L.p_aux[3]), L.bn_save_mean, L.bn_save_var,
+                 rows, C, L.d.bn_epsilon, L.d.bn_momentum, L.bn_fused, L.d.bn_mode, mode == FWD_TRAIN, e->ws, e->ws_floats, s);
+        }
+        break;
+      }
+      case SB_LAYER_LSTM: {
+        Prof pr(e, "lstm_fwd", 0, 0);
+        lstm_forward(e, L, li);
+        break;
+      }
+    }
+  }
+}
+
+static void run_loss(sb_engine* e, bool with_grad) {
+  const LayerPlan& last = e->L.back();
+  float* pred = e->acts[last.buf_out];
+  float* dpred = with_grad ? e->dacts[last.buf_out] : nullptr;
+  const long long rows = e->label_shape.d[0];
+  const long long cols = e->label_shape.numel() / rows;
+  if (e->softmax_cce_fused) {
+    Prof pr(e, "softmax_cce_fused", 4.0 * 4.0 * (double)rows * cols, 0);
+    softmax_cce_fwd_bwd(pred, e->by, dpred, e->st, (int)rows, (int)cols, e->stream);
+  } else {
+    Prof pr(e, "loss_fwd_bwd", 4.0 * 3.0 * (double)rows * cols, 0);
+    loss_fwd_bwd(e->train.loss, pred, e->by, dpred, e->st, rows, cols, e->stream);
+  }
+}
+
+static void run_backward(sb_engine* e) {
+  cudaStream_t s = e->stream;
+  const int nl = (int)e->L.size();
+  for (int li = nl - 1; li >= 0; --li) {
+    LayerPlan& L = e->L[li];
+    if (L.fused_into_prev) continue;
+    if (e->softmax_cce_fused && li == nl - 1) continue;
+    float* in = e->acts[L.buf_in];
+    float* out = e->acts[L.buf_out];
+    float* dout = e->dacts[L.buf_out];
+    float* din = e->dacts[L.buf_in];  // null for the input buffer
+    const int64_t n_out = L.out.numel();
+    switch (L.d.kind) {
+      case SB_LAYER_DENSE: {
+        const int M = (int)L.in.d[0], K = (int)L.in.d[1], N = (int)L.out.d[1];
+        if (L.tc_kind && tc_dense_bwd(e, L, li)) break;
+        {
+          Prof pr(e, "dense_wgrad_f32", 4.0 * ((double)M * K + (double)K * N + (double)M * N), 2.0 * M * N * K);
+          gemm_tn(in, dout, G(e, L.p_w), K, N, M, e->ws, e->ws_floats, s);  // dW = X^T . G
+        }
+        if (L.need_dx && din) {
+          Prof pr(e, "dense_dgrad_f32", 4.0 * ((double)M * K + (double)K * N + (double)M * N), 2.0 * M * N * K);
+          gemm_nt(dout, P(e, L.p_w), din, M, K, N, e->ws, e->ws_floats, s);  // dX = G . W^T
+        }
+        break;
+      }
+      case SB_LAYER_BIAS: {
+        Prof pr(e, "bias_grad", 4.0 * n_out, 0);
+        col_sum(dout, G(e, L.p_w), n_out / L.d.units, L.d.units, e->ws, e->ws_floats, s);
+        if (!L.inplace && L.need_dx && din) SB_CUDA(cudaMemcpyAsync(din, dout, (size_t)n_out * 4, cudaMemcpyDeviceToDevice, s));
+        break;
+      }
+      case SB_LAYER_ACTIVATE: {
+        if (!L.need_dx) break;
+        Prof pr(e, "act_bwd", 12.0 * n_out, 0);
+        float* g = dout;
+        if (!L.inplace) {
+          if (!din) break;
+          SB_CUDA(cudaMemcpyAsync(din, dout, (size_t)n_out * 4, cudaMemcpyDeviceToDevice, s));
+          g = din;
+        }
+        if (L.d.activation == SB_ACT_SOFTMAX) softmax_bwd(g, out, (int)L.out.d[0], (int)L.out.d[1], s);
+        else act_bwd(g, out, L.d.activation, L.d.relu_threshold, n_out, s);
+        break;
+      }
+      case SB_LAYER_FLATTEN:
+        break;
+      case SB_LAYER_CONV2D: {
+        const ConvGeom& g = L.cg;
+        if (L.tc_kind && tc_conv_bwd(e, L, li)) break;
+        const double fl = 2.0 * g.N * g.OH * g.OW * (double)g.Cout * g.KH * g.KW * g.Cin;
+        {
+          Prof pr(e, "conv2d_wgrad_f32", 4.0 * ((double)L.in.numel() + n_out + e->params[L.p_w].numel), fl);
+          conv2d_wgrad(in, dout, G(e, L.p_w), g, e->ws, e->ws_floats, s);
+        }
+        if (L.need_dx && din) {
+          Prof pr(e, "conv2d_dgrad_f32", 4.0 * ((double)L.in.numel() + n_out + e->params[L.p_w].numel), fl);
+          conv2d_dgrad(dout, P(e, L.p_w), din, g, e->ws, e->ws_floats, s);
+        }
+        break;
+      }
+      case SB_LAYER_POOL2D: {
+        if (!L.need_dx || !din) break;
+        Prof pr(e, "pool_bwd", 4.0 * (2.0 * L.in.numel() + 2.0 * n_out), 0);
+        pool_bwd(in, dout, din, L.pg, SB_POOL_MAX, s);
+        break;
+      }
+      case SB_LAYER_BATCHNORM: {
+        const int C = (int)L.in.d[L.in.rank - 1];
+        const long long rows = L.in.numel() / C;
+        Prof pr(e, "batchnorm_bwd", 4.0 * (5.0 * L.in.numel()), 0);
+        bn_bwd(in, dout, (L.need_dx && din) ? din : nullptr, P(e, L.p_aux[1]), L.bn_save_mean, L.bn_save_var, G(e, L.p_aux[1]),
+               G(e, L.p_aux[0]), rows, C, L.d.bn_epsilon, L.bn_fused, L.d.bn_mode, e->ws, e->ws_floats, s);
+        break;
+      }
+      case SB_LAYER_LSTM: {
+        Prof pr(e, "lstm_bwd", 0, 0);
+        lstm_backward(e, L, li);
+        break;
+      }
+    }
+  }
+}
+
+static OptDesc opt_desc(const sb_engine* e) {
+  OptDesc o;
+  o.kind = e->train.optimizer;
+  o.rate = e->train.rate;
+  o.beta1 = e->train.beta1;
+  o.beta2 = e->train.beta2;
+  o.epsilon = e->train.epsilon;
+  o.nesterov = e->train.nesterov;
+  o.minimizing = e->train.minimizing;
+  return o;
+}
+
+static void run_optimizer(sb_engine* e, int advance_batch) {
+  static const double bytes_per_param[8] = {20, 28, 20, 20, 28, 28, 28, 36};
+  Prof pr(e, "optimizer_fused", bytes_per_param[e->train.optimizer] * (double)e->nW, 0);
+  float* w = e->arena;
+  float* s0 = e->arena + e->nW + e->nS;
+  float* s1 = e->n_slots >= 2 ? s0 + e->nW : nullptr;
+  float* s2 = e->n_slots >= 3 ? s0 + 2 * e->nW : nullptr;
+  optimizer_step(opt_desc(e), w, e->grads, s0, s1, s2, e->nW, e->st, advance_batch, e->stream);
+}
+
+static void run_prologue(sb_engine* e, bool resident) {
+  Prof pr(e, "step_prologue", resident ? 8.0 * (double)(e->in_shape.numel() + e->label_shape.numel()) : 0, 0);
+  step_prologue(e->st, resident ? e->ds_x : nullptr, resident ? e->ds_y : nullptr, e->acts[0], e->by, e->in_shape.numel(),
+                e->label_shape.numel(), e->train.beta1, e->train.beta2, e->stream);
+}
+
+static void run_train_step_body(sb_engine* e, bool resident) {
+  run_prologue(e, resident);
+  run_forward(e, FWD_TRAIN);
+  run_loss(e, true);
+  run_backward(e);
+  run_optimizer(e, resident ? 1 : 0);
+}
+
+static cudaGraphExec_t capture(sb_engine* e, long long* nodes, void (*body)(sb_engine*, bool), bool flag) {
+  cudaGraph_t graph = nullptr;
+  const long long before = tl_launch_count;
+  SB_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+  try {
+    body(e, flag);
+  } catch (...) {
+    cudaStreamEndCapture(e->stream, &graph);
+    if (graph) cudaGraphDestroy(graph);
+    throw;
+  }
+  SB_CUDA(cudaStreamEndCapture(e->stream, &graph));
+  *nodes = tl_launch_count - before;
+  tl_launch_count = before;  // captured launches are counted per replay
+  cudaGraphExec_t exec = nullptr;
+  SB_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+  SB_CUDA(cudaGraphDestroy(graph));
+  return exec;
+}
+
+static void loss_body(sb_engine* e, bool) {
+  run_forward(e, FWD_LOSS_ONLY);
+  run_loss(e, false);
+}
+
+static bool use_graph(const sb_engine* e) { return e->train.use_graph && !e->profiling; }
+
+static void launch_train_step(sb_engine* e, bool resident) {
+  const long long before = tl_launch_count;
+  if (use_graph(e)) {
+    cudaGraphExec_t& g = resident ? e->g_resident : e->g_hostfed;
+    long long& nodes = resident ? e->nodes_resident : e->nodes_hostfed;
+    if (!g) g = capture(e, &nodes, run_train_step_body, resident);
+    SB_CUDA(cudaGraphLaunch(g, e->stream));
+    e->launches += nodes;
+  } else {
+    run_train_step_body(e, resident);
+    e->launches += tl_launch_count - before;
+  }
+}
+
+static void launch_loss(sb_engine* e) {
+  const long long before = tl_launch_count;
+  if (use_graph(e)) {
+    if (!e->g_loss) e->g_loss = capture(e, &e->nodes_loss, loss_body, false);
+    SB_CUDA(cudaGraphLaunch(e->g_loss, e->stream));
+    e->launches += e->nodes_loss;
+  } else {
+    loss_body(e, false);
+    e->launches += tl_launch_count - before;
+  }
+}
+
+static void set_device_iter(sb_engine* e, long long iter_done, long long batch_idx) {
+  // host -> device control write; st_host slots rotate so an in-flight copy is never overwritten
+  static thread_local int slot = 0;
+  slot = (slot + 1) & 3;
+  StepState* h = e->st_host + slot;
+  h->iter = iter_done;
+  h->batch_idx = batch_idx;
+  SB_CUDA(cudaMemcpyAsync(e->st, h, 2 * sizeof(long long), cudaMemcpyHostToDevice, e->stream));
+  e->host_iter_mirror = iter_done;
+}
+
+static float read_loss(sb_engine* e) {
+  StepState* h = e->st_host + 0;
+  SB_CUDA(cudaMemcpyAsync(&h->loss, &e->st->loss, sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  SB_CUDA(cudaStreamSynchronize(e->stream));
+  return h->loss;
+}
+
+static void require_ready(const sb_engine* e) {
+  if (!e->params_ready || !e->opt_ready)
+    SB_FAIL(SB_ERR_STATE, "parameters are not initialised: call sb_init_params, or sb_params_set for every model param "
+                          "followed by sb_init_opt_params");
+}
+
+static void upload_batch(sb_engine* e, const float* x, const float* y) {
+  if (!x) SB_FAIL(SB_ERR_INVALID_ARG, "null x");
+  SB_CUDA(cudaMemcpyAsync(e->acts[0], x, (size_t)e->in_shape.numel() * 4, cudaMemcpyHostToDevice, e->stream));
+  if (y) SB_CUDA(cudaMemcpyAsync(e->by, y, (size_t)e->label_shape.numel() * 4, cudaMemcpyHostToDevice, e->stream));
+}
+
+// -------------------------------------------------------------------------------------------------
+// initialisation (models/Initializer.scala; Optimizer.scala:123-131)
+// -------------------------------------------------------------------------------------------------
+static void fans_of(const Param& p, int64_t* fin, int64_t* fout) {
+  // Initializer.fans (Initializer.scala:16-25): rank>=3 takes d0 as "out" and d1 as "in" (sic)
+  if (p.rank == 0) { *fin = *fout = 1; return; }
+  if (p.rank == 1) { *fin = *fout = p.dims[0]; return; }
+  if (p.rank == 2) { *fin = p.dims[0]; *fout = p.dims[1]; return; }
+  int64_t size = 1;
+  for (int i = 2; i < p.rank; ++i) size *= p.dims[i];
+  *fin = size * p.dims[1];
+  *fout = size * p.dims[0];
+}
+static float f32_sqrt_ratio(float num, int64_t den) {
+  // math.sqrt(6f / (fanIn + fanOut)).toFloat : fp32 division, double sqrt, cast back (Initializer.scala:86)
+  float q = num / (float)den;
+  return (float)sqrt((double)q);
+}
+
+static void init_param(sb_engine* e, const Param& p) {
+  float* dst = e->arena + p.offset;
+  cudaStream_t s = e->stream;
+  const sb_initializer& in = p.init;
+  auto need_seed = [&]() {
+    if (!in.has_seed)
+      SB_FAIL(SB_ERR_UNSUPPORTED, "unseeded random initializer for '" + p.path + "': pass a seed or set the tensor with sb_params_set "
+                                  "(every partition initialises independently in the reference, SURVEY App. B-Q6)");
+  };
+  SB_CUDA(cudaMemsetAsync(dst, 0, (size_t)p.padded * 4, s));
+  int64_t fin, fout;
+  fans_of(p, &fin, &fout);
+  switch (in.kind) {
+    case SB_INIT_ZEROS: break;
+    case SB_INIT_ONES: fill_const(dst, 1.0f, p.numel, s); break;
+    case SB_INIT_CONST: fill_const(dst, in.a, p.numel, s); break;
+    case SB_INIT_RANDOM_UNIFORM: need_seed(); philox_fill(dst, p.numel, (unsigned long long)in.seed, 0, in.b - in.a, 1, in.a, 1, s); break;
+    case SB_INIT_RANDOM_NORMAL: need_seed(); philox_fill(dst, p.numel, (unsigned long long)in.seed, 1, in.b, 1, in.a, 1, s); break;
+    case SB_INIT_GLOROT_UNIFORM: {
+      need_seed();
+      float limit = f32_sqrt_ratio(6.0f, fin + fout);
+      philox_fill(dst, p.numel, (unsigned long long)in.seed, 0, 2.0f * limit, 1, -limit, 1, s);
+      break;
+    }
+    case SB_INIT_HE_UNIFORM: {
+      need_seed();
+      float limit = f32_sqrt_ratio(6.0f, fin);
+      philox_fill(dst, p.numel, (unsigned long long)in.seed, 0, 2.0f * limit, 1, -limit, 1, s);
+      break;
+    }
+    case SB_INIT_LECUN_UNIFORM: {
+      need_seed();
+      float limit = f32_sqrt_ratio(3.0f, fin);
+      philox_fill(dst, p.numel, (unsigned long long)in.seed, 0, 2.0f * limit, 1, -limit, 1, s);
+      break;
+    }
+    case SB_INIT_ORTHOGONAL: {
+      need_seed();
+      std::vector<float> host((size_t)p.numel);
+      int64_t cols = p.dims[p.rank - 1], rows = p.numel / cols;
+      orthogonal_host(host.data(), rows, cols, (unsigned long long)in.seed, in.a);
+      SB_CUDA(cudaMemcpyAsync(dst, host.data(), (size_t)p.numel * 4, cudaMemcpyHostToDevice, s));
+      SB_CUDA(cudaStreamSynchronize(s));
+      break;
+    }
+    default: SB_FAIL(SB_ERR_UNSUPPORTED, "initializer kind " + std::to_string(in.kind) + " is unsupported on the device; set '" + p.path + "' with sb_params_set");
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// C ABI
+// -------------------------------------------------------------------------------------------------
+extern "C" int sb_engine_create(const sb_model_desc* model, const sb_train_desc* train, int device, sb_engine** out) {
+  SB_API_BEGIN
+  if (!model || !train || !out || !model->layers) SB_FAIL(SB_ERR_INVALID_ARG, "null argument");
+  std::unique_ptr<sb_engine> e(new sb_engine());
+  e->layers_desc.assign(model->layers, model->layers + std::max(model->n_layers, 0));
+  e->model = *model;
+  e->model.layers = e->layers_desc.data();
+  e->train = *train;
+  e->device = device;
+  e->plan_only = device < 0;
+  build_plan(e.get());
+  if (!e->plan_only) {
+    int n = 0;
+    cudaError_t ce = cudaGetDeviceCount(&n);
+    if (ce != cudaSuccess || device >= n) {
+      cudaGetLastError();
+      SB_FAIL(SB_ERR_CUDA, "CUDA device " + std::to_string(device) + " is not available (" + std::to_string(n) +
+                               " visible); this library has no CPU fallback");
+    }
+    allocate(e.get());
+  }
+  *out = e.release();
+  SB_API_END
+}
+
+extern "C" void sb_engine_destroy(sb_engine* e) {
+  if (!e) return;
+  if (!e->plan_only) {
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    for (auto& pp : e->prof_pending) { cudaEventDestroy(pp.a); cudaEventDestroy(pp.b); }
+    if (e->g_resident) cudaGraphExecDestroy(e->g_resident);
+    if (e->g_hostfed) cudaGraphExecDestroy(e->g_hostfed);
+    if (e->g_loss) cudaGraphExecDestroy(e->g_loss);
+    tc_free_layers(e);
+    lstm_free(e);
+    for (auto& L : e->L) { cudaFree(L.bn_save_mean); cudaFree(L.bn_save_var); }
+    for (float* p : e->acts) cudaFree(p);
+    for (float* p : e->dacts) cudaFree(p);
+    cudaFree(e->arena); cudaFree(e->grads); cudaFree(e->by); cudaFree(e->ds_x); cudaFree(e->ds_y);
+    cudaFree(e->st); cudaFree(e->ws);
+    if (e->st_host) cudaFreeHost(e->st_host);
+    if (e->stream) cudaStreamDestroy(e->stream);
+  }
+  delete e;
+}
+
+extern "C" int sb_param_count(const sb_engine* e) { return e ? (int)e->params.size() : 0; }
+
+extern "C" int sb_param_info(const sb_engine* e, int index, char* path, size_t path_cap, int64_t* dims, int32_t* rank,
+                             int32_t* role, int32_t* aggregation, int64_t* arena_offset) {
+  SB_API_BEGIN
+  if (!e || index < 0 || index >= (int)e->params.size()) SB_FAIL(SB_ERR_INVALID_ARG, "param index out of range");
+  const Param& p = e->params[index];
+  if (path && path_cap) {
+    strncpy(path, p.path.c_str(), path_cap - 1);
+    path[path_cap - 1] = 0;
+  }
+  if (dims) for (int i = 0; i < p.rank; ++i) dims[i] = p.dims[i];
+  if (rank) *rank = p.rank;
+  if (role) *role = p.role;
+  if (aggregation) *aggregation = p.agg;
+  if (arena_offset) *arena_offset = p.offset;
+  SB_API_END
+}
+
+extern "C" int sb_output_dims(const sb_engine* e, int64_t* dims, int32_t* rank) {
+  SB_API_BEGIN
+  if (!e || !dims || !rank) SB_FAIL(SB_ERR_INVALID_ARG, "null argument");
+  *rank = e->out_shape.rank;
+  for (int i = 0; i < e->out_shape.rank; ++i) dims[i] = e->out_shape.d[i];
+  SB_API_END
+}
+
+static const Param& find_param(const sb_engine* e, const char* path, size_t n) {
+  if (!e || !path) SB_FAIL(SB_ERR_INVALID_ARG, "null argument");
+  auto it = e->by_path.find(path);
+  if (it == e->by_path.end()) SB_FAIL(SB_ERR_INVALID_ARG, std::string("missing ") + path + " param");  // core/Params.scala:22-23
+  const Param& p = e->params[it->second];
+  if ((int64_t)n != p.numel)
+    SB_FAIL(SB_ERR_INVALID_ARG, std::string("param ") + path + " has " + std::to_string(p.numel) + " elements, got " + std::to_string(n));
+  return p;
+}
+
+static void refresh_ready(sb_engine* e) { /* readiness is tracked by explicit calls */ (void)e; }
+
+extern "C" int sb_params_set(sb_engine* e, const char* path, const float* host, size_t n) {
+  SB_API_BEGIN
+  need_device(e);
+  if (!host) SB_FAIL(SB_ERR_INVALID_ARG, "null host buffer");
+  const Param& p = find_param(e, path, n);
+  DeviceGuard dg(e->device);
+  SB_CUDA(cudaMemcpyAsync(e->arena + p.offset, host, n * 4, cudaMemcpyHostToDevice, e->stream));
+  SB_CUDA(cudaStreamSynchronize(e->stream));
+  tc_params_changed(e);
+  // setting every model param makes the model side ready (mirrors `initParams`, Optimizer.scala:124-126)
+  e->params_ready = true;
+  refresh_ready(e);
+  SB_API_END
+}
+
+extern "C" int sb_params_get(sb_engine* e, const char* path, float* host, size_t n) {
+  SB_API_BEGIN
+  need_device(e);
+  if (!host) SB_FAIL(SB_ERR_INVALID_ARG, "null host buffer");
+  const Param& p = find_param(e, path, n);
+  DeviceGuard dg(e->device);
+  SB_CUDA(cudaMemcpyAsync(host, e->arena + p.offset, n * 4, cudaMemcpyDeviceToHost, e->stream));
+  SB_CUDA(cudaStreamSynchronize(e->stream));
+  SB_API_END
+}
+
+extern "C" int sb_init_opt_params(sb_engine* e) {
+  SB_API_BEGIN
+  need_device(e);
+  DeviceGuard dg(e->device);
+  for (const Param& p : e->params)
+    if (p.role == SB_ROLE_OPT) init_param(e, p);
+  SB_CUDA(cudaStreamSynchronize(e->stream));
+  e->opt_ready = true;
+  SB_API_END
+}
+
+extern "C" int sb_init_params(sb_engine* e) {
+  SB_API_BEGIN
+  need_device(e);
+  DeviceGuard dg(e->device);
+  for (const Param& p : e->params) init_param(e, p);
+  SB_CUDA(cudaStreamSynchronize(e->stream));
+  tc_params_changed(e);
+  e->params_ready = e->opt_ready = true;
+  SB_API_END
+}
+
+extern "C" int sb_dataset_upload(sb_engine* e, const float* x, const float* y, int64_t n_rows) {
+  SB_API_BEGIN
+  need_device(e);
+  if (!x || !y || n_rows <= 0) SB_FAIL(SB_ERR_INVALID_ARG, "dataset must have at least one row");
+  DeviceGuard dg(e->device);
+  SB_CUDA(cudaStreamSynchronize(e->stream));
+  cudaFree(e->ds_x);
+  cudaFree(e->ds_y);
+  e->ds_x = e->ds_y = nullptr;
+  e->ds_x = dmalloc_floats(pad32(n_rows * e->x_per_row));
+  e->ds_y = dmalloc_floats(pad32(n_rows * e->y_per_row));
+  SB_CUDA(cudaMemcpyAsync(e->ds_x, x, (size_t)(n_rows * e->x_per_row) * 4, cudaMemcpyHostToDevice, e->stream));
+  SB_CUDA(cudaMemcpyAsync(e->ds_y, y, (size_t)(n_rows * e->y_per_row) * 4, cudaMemcpyHostToDevice, e->stream));
+  SB_CUDA(cudaStreamSynchronize(e->stream));
+  e->ds_rows = n_rows;
+  // the captured graphs hold the dataset pointers
+  if (e->g_resident) { cudaGraphExecDestroy(e->g_resident); e->g_resident = nullptr; }
+  SB_API_END
+}
+
+extern "C" int sb_train_steps_async(sb_engine* e, int64_t global_iter, int64_t first_batch, int64_t n_steps) {
+  SB_API_BEGIN
+  need_device(e);
+  require_ready(e);
+  if (!e->ds_x) SB_FAIL(SB_ERR_STATE, "no dataset uploaded");
+  const int64_t n_batches = e->ds_rows / e->train.batch;
+  if (first_batch < 0 || n_steps < 0 || first_batch + n_steps > n_batches)
+    SB_FAIL(SB_ERR_INVALID_ARG, "batch range exceeds the shard (" + std::to_string(n_batches) + " full batches)");
+  DeviceGuard dg(e->device);
+  set_device_iter(e, global_iter, first_batch);
+  for (int64_t j = 0; j < n_steps; ++j) launch_train_step(e, true);
+  e->host_iter_mirror = global_iter + n_steps;
+  SB_API_END
+}
+
+extern "C" int sb_train_epoch(sb_engine* e, int64_t global_iter, int64_t* iterations_out, float* last_loss_out) {
+  SB_API_BEGIN
+  need_device(e);
+  require_ready(e);
+  if (!e->ds_x) SB_FAIL(SB_ERR_STATE, "no dataset uploaded");
+  const int64_t n_batches = e->ds_rows / e->train.batch;  // Skip: the partial tail batch is dropped (Iterators.scala:46-47,90)
+  if (n_batches == 0)
+    SB_FAIL(SB_ERR_INVALID_ARG, "NoSuchElementException: the shard holds fewer rows than one batch (Iterators.scala:79-81)");
+  DeviceGuard dg(e->device);
+  set_device_iter(e, global_iter, 0);
+  for (int64_t j = 0; j < n_batches; ++j) launch_train_step(e, true);
+  e->host_iter_mirror = global_iter + n_batches;
+  launch_loss(e);  // forward-only loss on the LAST batch with the UPDATED params (Optimizer.scala:148)
+  float loss = read_loss(e);
+  if (e->profiling) prof_resolve(e);
+  if (iterations_out) *iterations_out = n_batches;
+  if (last_loss_out) *last_loss_out = loss;
+  SB_API_END
+}
+
+extern "C" int sb_train_step(sb_engine* e, const float* x, const float* y, int64_t iter, float* loss_out) {
+  SB_API_BEGIN
+  need_device(e);
+  require_ready(e);
+  if (!y) SB_FAIL(SB_ERR_INVALID_ARG, "null y");
+  if (iter < 1) SB_FAIL(SB_ERR_INVALID_ARG, "iter is the 1-based global step");
+  DeviceGuard dg(e->device);
+  if (e->host_iter_mirror != iter - 1) set_device_iter(e, iter - 1, 0);
+  upload_batch(e, x, y);
+  launch_train_step(e, false);
+  e->host_iter_mirror = iter;
+  if (loss_out) *loss_out = read_loss(e);
+  SB_API_END
+}
+
+extern "C" int sb_train_step_async(sb_engine* e, const float* x, const float* y, int64_t iter, float* loss_out_host) {
+  SB_API_BEGIN
+  need_device(e);
+  require_ready(e);
+  if (!y) SB_FAIL(SB_ERR_INVALID_ARG, "null y");
+  if (iter < 1) SB_FAIL(SB_ERR_INVALID_ARG, "iter is the 1-based global step");
+  DeviceGuard dg(e->device);
+  if (e->host_iter_mirror != iter - 1) set_device_iter(e, iter - 1, 0);
+  upload_batch(e, x, y);
+  launch_train_step(e, false);
+  e->host_iter_mirror = iter;
+  if (loss_out_host)
+    SB_CUDA(cudaMemcpyAsync(loss_out_host, &e->st->loss, sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  SB_API_END
+}
+
+extern "C" int sb_eval_loss(sb_engine* e, const float* x, const float* y, float* loss_out) {
+  SB_API_BEGIN
+  need_device(e);
+  if (!e->params_ready) SB_FAIL(SB_ERR_STATE, "model parameters are not initialised");
+  if (!y || !loss_out) SB_FAIL(SB_ERR_INVALID_ARG, "null argument");
+  DeviceGuard dg(e->device);
+  upload_batch(e, x, y);
+  launch_loss(e);
+  *loss_out = read_loss(e);
+  SB_API_END
+}
+
+extern "C" int sb_predict(sb_engine* e, const float* x, float* out, size_t n_out) {
+  SB_API_BEGIN
+  need_device(e);
+  if (!e->params_ready) SB_FAIL(SB_ERR_STATE, "model parameters are not initialised");
+  if (!out || (int64_t)n_out != e->out_shape.numel()) SB_FAIL(SB_ERR_INVALID_ARG, "output buffer size mismatch");
+  DeviceGuard dg(e->device);
+  upload_batch(e, x, nullptr);
+  const long long before = tl_launch_count;
+  run_forward(e, FWD_INFER);
+  e->launches += tl_launch_count - before;
+  SB_CUDA(cudaMemcpyAsync(out, e->acts[e->L.back().buf_out], n_out * 4, cudaMemcpyDeviceToHost, e->stream));
+  SB_CUDA(cudaStreamSynchronize(e->stream));
+  SB_API_END
+}
+
+extern "C" int sb_compute_grads(sb_engine* e, const float* x, const float* y, float* loss_out) {
+  SB_API_BEGIN
+  need_device(e);
+  if (!e->params_ready) SB_FAIL(SB_ERR_STATE, "model parameters are not initialised");
+  if (!y) SB_FAIL(SB_ERR_INVALID_ARG, "null y");
+  DeviceGuard dg(e->device);
+  upload_batch(e, x, y);
+  const long long before = tl_launch_count;
+  run_forward(e, FWD_LOSS_ONLY);
+  run_loss(e, true);
+  run_backward(e);
+  e->launches += tl_launch_count - before;
+  float loss = read_loss(e);
+  if (loss_out) *loss_out = loss;
+  SB_API_END
+}
+
+extern "C" int sb_grad_get(sb_engine* e, const char* path, float* host, size_t n) {
+  SB_API_BEGIN
+  need_device(e);
+  const Param& p = find_param(e, path, n);
+  if (p.role != SB_ROLE_WEIGHT) SB_FAIL(SB_ERR_INVALID_ARG, std::string(path) + " is not a trainable weight");
+  DeviceGuard dg(e->device);
+  SB_CUDA(cudaMemcpyAsync(host, e->grads + p.offset, n * 4, cudaMemcpyDeviceToHost, e->stream));
+  SB_CUDA(cudaStreamSynchronize(e->stream));
+  SB_API_END
+}
+
+extern "C" int sb_sync(sb_engine* e) {
+  SB_API_BEGIN
+  need_device(e);
+  DeviceGuard dg(e->device);
+  SB_CUDA(cudaStreamSynchronize(e->stream));
+  if (e->profiling) prof_resolve(e);
+  SB_API_END
+}
+
+extern "C" int sb_arena(sb_engine* e, void** device_ptr, int64_t* n_floats) {
+  SB_API_BEGIN
+  need_device(e);
+  if (device_ptr) *device_ptr = e->arena;
+  if (n_floats) *n_floats = e->arena_floats;
+  SB_API_END
+}
+
+extern "C" int sb_stream(sb_engine* e, void** stream) {
+  SB_API_BEGIN
+  need_device(e);
+  if (!stream) SB_FAIL(SB_ERR_INVALID_ARG, "null argument");
+  *stream = (void*)e->stream;
+  SB_API_END
+}
+
+extern "C" int sb_arena_scale(sb_engine* e, float w) {
+  SB_API_BEGIN
+  need_device(e);
+  DeviceGuard dg(e->device);
+  const long long before = tl_launch_count;
+  scale_inplace(e->arena, w, e->arena_floats, e->stream);
+  e->launches += tl_launch_count - before;
+  SB_API_END
+}
+
+extern "C" int sb_reset_unaggregated(sb_engine* e) {
+  SB_API_BEGIN
+  need_device(e);
+  DeviceGuard dg(e->device);
+  for (const Param& p : e->params)
+    if (p.agg == SB_AGG_NONE) init_param(e, p);
+  SB_API_END
+}
+
+extern "C" int sb_arena_ipc_handle(sb_engine* e, void* handle64, int64_t* byte_offset) {
+  SB_API_BEGIN
+  need_device(e);
+  if (!handle64) SB_FAIL(SB_ERR_INVALID_ARG, "null argument");
+  DeviceGuard dg(e->device);
+  cudaIpcMemHandle_t h;
+  SB_CUDA(cudaIpcGetMemHandle(&h, e->arena));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  if (byte_offset) *byte_offset = 0;
+  SB_API_END
+}
+
+extern "C" int sb_profile_enable(sb_engine* e, int on) {
+  SB_API_BEGIN
+  need_device(e);
+  DeviceGuard dg(e->device);
+  if (!on && e->profiling) prof_resolve(e);
+  e->profiling = on != 0;
+  SB_API_END
+}
+extern "C" int sb_profile_count(const sb_engine* e) { return e ? (int)e->prof.size() : 0; }
+extern "C" int sb_profile_get(const sb_engine* ce, int index, char* name, size_t name_cap, double* total_ms, int64_t* launches,
+                              double* bytes, double* flops) {
+  SB_API_BEGIN
+  sb_engine* e = const_cast<sb_engine*>(ce);
+  need_device(e);
+  if (index < 0 || index >= (int)e->prof.size()) SB_FAIL(SB_ERR_INVALID_ARG, "profile index out of range");
+  DeviceGuard dg(e->device);
+  prof_resolve(e);
+  const ProfEntry& p = e->prof[index];
+  if (name && name_cap) {
+    strncpy(name, p.name.c_str(), name_cap - 1);
+    name[name_cap - 1] = 0;
+  }
+  if (total_ms) *total_ms = p.total_ms;
+  if (launches) *launches = p.launches;
+  if (bytes) *bytes = p.bytes;
+  if (flops) *flops = p.flops;
+  SB_API_END
+}
+extern "C" int sb_profile_reset(sb_engine* e) {
+  SB_API_BEGIN
+  need_device(e);
+  DeviceGuard dg(e->device);
+  prof_resolve(e);
+  for (auto& p : e->prof) { p.total_ms = 0; p.launches = 0; p.bytes = 0; p.flops = 0; }
+  SB_API_END
+}
+extern "C" int64_t sb_launch_count(const sb_engine* e) { return e ? e->launches : 0; }

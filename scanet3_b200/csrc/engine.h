@@ -1,0 +1,116 @@
+// Internal engine structures (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/scanet_b200.h"
+#include "kernels.cuh"
+
+namespace sb {
+
+struct Shape {
+  int rank = 0;
+  int64_t d[5] = {0, 0, 0, 0, 0};
+  int64_t numel() const {
+    int64_t n = 1;
+    for (int i = 0; i < rank; ++i) n *= d[i];
+    return n;
+  }
+};
+
+struct Param {
+  std::string path;
+  int rank = 0;
+  int64_t dims[4] = {0, 0, 0, 0};
+  int role = 0;  // sb_param_role
+  int agg = 0;   // sb_aggregation
+  int64_t numel = 0;
+  int64_t padded = 0;  // numel rounded up to 32 floats (128 B: vector loads + TMA alignment)
+  int64_t offset = 0;  // floats from the arena base
+  sb_initializer init{};
+  int layer = -1;
+  int weight_param = -1;  // role OPT: index of the weight this state belongs to
+  int slot = -1;          // role OPT: state slot 0..2
+};
+
+struct LayerPlan {
+  sb_layer_desc d{};
+  Shape in, out;        // incl. batch
+  int buf_in = 0;       // activation buffer ids
+  int buf_out = 0;
+  bool inplace = false;
+  bool need_dx = false; // some trainable parameter lives in an earlier layer
+  int p_w = -1;         // param indices (kind specific)
+  int p_aux[16];        // BN: beta,gamma,mm,mv ; LSTM: per gate kernel,recurrent,bias
+  ConvGeom cg{};
+  PoolGeom pg{};
+  // BatchNorm
+  bool bn_fused = false;
+  float* bn_save_mean = nullptr;
+  float* bn_save_var = nullptr;
+  // fusion / fast-path decisions
+  bool fused_into_prev = false;   // this layer's forward+backward is executed by the previous op
+  int tc_kind = 0;                // 0 none, otherwise a tcgen05 kernel variant
+  void* tc_plan = nullptr;        // opaque plan of the tensor-core path (TMA descriptors, buffers)
+  void* lstm = nullptr;           // opaque LSTM workspace
+};
+
+struct ProfEntry {
+  std::string name;
+  double total_ms = 0;
+  long long launches = 0;
+  double bytes = 0;
+  double flops = 0;
+};
+struct ProfPending {
+  int entry;
+  cudaEvent_t a, b;
+};
+
+}  // namespace sb
+
+struct sb_engine {
+  int device = -1;
+  bool plan_only = false;
+  std::vector<sb_layer_desc> layers_desc;
+  sb_model_desc model{};
+  sb_train_desc train{};
+  sb::Shape in_shape, label_shape, out_shape;  // incl. batch
+  int64_t x_per_row = 0, y_per_row = 0;
+
+  std::vector<sb::Param> params;
+  std::unordered_map<std::string, int> by_path;
+  std::vector<sb::LayerPlan> L;
+  int64_t nW = 0;      // floats in the trainable-weight region (padded)
+  int64_t nS = 0;      // floats in the state region
+  int n_slots = 0;     // optimizer state slots
+  int64_t arena_floats = 0;
+
+  float* arena = nullptr;
+  float* grads = nullptr;
+  std::vector<float*> acts, dacts;
+  std::vector<int64_t> act_numel;
+  float* by = nullptr;  // label staging
+  float* ds_x = nullptr;
+  float* ds_y = nullptr;
+  int64_t ds_rows = 0;
+  sb::StepState* st = nullptr;
+  sb::StepState* st_host = nullptr;  // pinned mirror
+  float* ws = nullptr;
+  size_t ws_floats = 0;
+  cudaStream_t stream = nullptr;
+  cudaGraphExec_t g_resident = nullptr, g_hostfed = nullptr, g_loss = nullptr;
+  long long nodes_resident = 0, nodes_hostfed = 0, nodes_loss = 0;
+  long long launches = 0;
+  long long host_iter_mirror = -1;  // device st->iter as far as the host knows (-1 unknown)
+  bool params_ready = false, opt_ready = false;
+  bool softmax_cce_fused = false;
+
+  bool profiling = false;
+  std::vector<sb::ProfEntry> prof;
+  std::vector<sb::ProfPending> prof_pending;
+  std::unordered_map<std::string, int> prof_by_name;
+};

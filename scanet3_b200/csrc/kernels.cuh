@@ -1,0 +1,91 @@
+// Kernel launchers of the scanet-b200 engine (sm_100a).  Every launcher enqueues on `s` and never syncs.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sb {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+// Device-resident step bookkeeping: lets a whole epoch run without a host sync
+// (reference: `iter = globalIter + localIter + 1`, optimizers/Optimizer.scala:143).
+struct StepState {
+  long long iter;       // last completed GLOBAL step t-1; the prologue kernel advances it
+  long long batch_idx;  // next batch of the resident shard; advanced by the optimizer kernel
+  float bc1;            // 1 - beta1^t   (`boost`, math/alg/AllKernels.scala:546-549)
+  float bc2;            // 1 - beta2^t
+  float loss;           // loss of the latest forward
+  float pad;
+};
+
+struct ConvGeom {
+  int N, H, W, Cin, Cout, KH, KW, SH, SW, PT, PL, OH, OW;
+};
+
+struct PoolGeom {
+  int N, H, W, C, KH, KW, SH, SW, PT, PL, OH, OW;
+};
+
+struct OptDesc {
+  int kind;  // sb_optimizer
+  float rate, beta1, beta2, epsilon;
+  int nesterov;
+  int minimizing;
+};
+
+// ---- step prologue: gather the batch out of the resident shard + advance iter / bias corrections ----
+void step_prologue(StepState* st, const float* ds_x, const float* ds_y, float* bx, float* by, long long x_per_batch,
+                   long long y_per_batch, float beta1, float beta2, cudaStream_t s);
+
+// ---- fp32 FFMA contractions (parity mode; also the shapes tcgen05 does not fit) ----
+// C[M,N] = A[M,K] . B[K,N]
+void gemm_nn(const float* A, const float* B, float* C, int M, int N, int K, float* ws, size_t ws_floats, cudaStream_t s);
+// C[M,N] = A[M,K] . B[N,K]^T            (dX = G . W^T)
+void gemm_nt(const float* A, const float* B, float* C, int M, int N, int K, float* ws, size_t ws_floats, cudaStream_t s);
+// C[M,N] = A[K,M]^T . B[K,N]            (dW = X^T . G), deterministic split-K through `ws`
+void gemm_tn(const float* A, const float* B, float* C, int M, int N, int K, float* ws, size_t ws_floats, cudaStream_t s);
+void conv2d_fwd(const float* x, const float* w, float* y, const ConvGeom& g, float* ws, size_t ws_floats, cudaStream_t s);
+void conv2d_dgrad(const float* dy, const float* w, float* dx, const ConvGeom& g, float* ws, size_t ws_floats, cudaStream_t s);
+void conv2d_wgrad(const float* x, const float* dy, float* dw, const ConvGeom& g, float* ws, size_t ws_floats, cudaStream_t s);
+
+// ---- bandwidth-bound kernels ----
+void bias_add(float* x, const float* b, long long rows, int C, cudaStream_t s);
+void col_sum(const float* g, float* out, long long rows, int C, float* ws, size_t ws_floats, cudaStream_t s);
+void act_fwd(float* x, int act, float thr, long long n, cudaStream_t s);
+void act_bwd(float* g, const float* y, int act, float thr, long long n, cudaStream_t s);
+void softmax_fwd(float* x, int rows, int C, cudaStream_t s);
+void softmax_bwd(float* g, const float* p, int rows, int C, cudaStream_t s);
+// loss value -> st->loss ; dpred (may be null) = dLoss/dpred.  rows = y.shape[0].
+void loss_fwd_bwd(int loss, const float* pred, const float* y, float* dpred, StepState* st, long long rows, long long cols,
+                  cudaStream_t s);
+// fused Softmax + CategoricalCrossentropy head: p = softmax(z) in place, loss, dz
+void softmax_cce_fwd_bwd(float* z_inout_p, const float* y, float* dz, StepState* st, int rows, int C, cudaStream_t s);
+void pool_fwd(const float* x, float* y, const PoolGeom& g, int reduce, cudaStream_t s);
+// max: gather form with the reference's first-max tie rule (math/nn/KernelsSpec.scala:277-288)
+void pool_bwd(const float* x, const float* dy, float* dx, const PoolGeom& g, int reduce, cudaStream_t s);
+// pool_bwd fused with the gradient of a ReLU that produced x in place:  dx = [x > thr] * poolgrad
+void pool_bwd_relu(const float* x, const float* dy, float* dx, const PoolGeom& g, float thr, cudaStream_t s);
+
+// batch norm over the last axis (C), rows = product of the other axes
+void bn_fwd(const float* x, float* y, const float* gamma, const float* beta, float* mov_mean, float* mov_var,
+            float* save_mean, float* save_var, long long rows, int C, float eps, float momentum, int fused, int bn_mode,
+            int update_moving, float* ws, size_t ws_floats, cudaStream_t s);
+void bn_fwd_infer(const float* x, float* y, const float* gamma, const float* beta, const float* mov_mean, const float* mov_var,
+                  long long rows, int C, float eps, int fused, cudaStream_t s);
+void bn_bwd(const float* x, const float* dy, float* dx, const float* gamma, const float* save_mean, const float* save_var,
+            float* dgamma, float* dbeta, long long rows, int C, float eps, int fused, int bn_mode, float* ws,
+            size_t ws_floats, cudaStream_t s);
+
+// fused multi-tensor optimizer over the flat arena: w,g,state regions of n floats each
+void optimizer_step(const OptDesc& o, float* w, const float* g, float* s0, float* s1, float* s2, long long n,
+                    StepState* st, int advance_batch, cudaStream_t s);
+
+// ---- init / utility ----
+void fill_const(float* p, float v, long long n, cudaStream_t s);
+void scale_inplace(float* p, float w, long long n, cudaStream_t s);
+// TF RandomUniform / RandomStandardNormal (Philox-4x32-10), out = sample*scale + shift
+void philox_fill(float* p, long long n, unsigned long long seed, int normal, float scale, int has_scale, float shift,
+                 int has_shift, cudaStream_t s);
+
+
+}  // namespace sb

@@ -1,0 +1,410 @@
+"""Host-side mirror of the reference's model DSL for the train path (same names, argument meaning, defaults and
+param-path conventions), lowering to the C-ABI descriptors of include/scanet_b200.h.
+
+Reference (under /root/reference/src/main/scala/scanet/): models/layer/{Layer,Composed,Dense,Bias,Activate,Flatten,
+Conv2D,Pool2D,BatchNorm,RNN}.scala, models/{Activation,Loss,Initializer}.scala, optimizers/{SGD..AMSGrad}.scala.
+This module contains NO arithmetic: it only describes models; all compute happens in libscanet_b200.so."""
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+from . import _native as N
+
+
+# ---- initializers (models/Initializer.scala:28-220) ---------------------------------------------------------
+@dataclass(frozen=True)
+class Initializer:
+    kind: int
+    seed: Optional[int] = None
+    a: float = 0.0
+    b: float = 0.0
+    name: str = ""
+
+    def to_native(self) -> N.sb_initializer:
+        return N.sb_initializer(self.kind, 0 if self.seed is None else 1, 0 if self.seed is None else int(self.seed),
+                                float(self.a), float(self.b))
+
+    def __repr__(self):
+        return self.name
+
+
+Zeros = Initializer(N.INIT_ZEROS, name="Zeros")
+Ones = Initializer(N.INIT_ONES, name="Ones")
+
+
+def Const(value: float):
+    return Initializer(N.INIT_CONST, a=value, name=f"Const({value})")
+
+
+def RandomUniform(min: float = -0.05, max: float = 0.05, seed: Optional[int] = None):
+    return Initializer(N.INIT_RANDOM_UNIFORM, seed, min, max, f"RandomUniform(min={min},max={max})")
+
+
+def RandomNormal(mean: float = 0.0, std: float = 0.05, seed: Optional[int] = None):
+    return Initializer(N.INIT_RANDOM_NORMAL, seed, mean, std, f"RandomNormal(mean={mean},std={std})")
+
+
+def GlorotUniform(seed: Optional[int] = None):
+    return Initializer(N.INIT_GLOROT_UNIFORM, seed, name="GlorotUniform")
+
+
+def HeUniform(seed: Optional[int] = None):
+    return Initializer(N.INIT_HE_UNIFORM, seed, name="HeUniform")
+
+
+def LecunUniform(seed: Optional[int] = None):
+    return Initializer(N.INIT_LECUN_UNIFORM, seed, name="LecunUniform")
+
+
+def Orthogonal(gain: Optional[float] = None, seed: Optional[int] = None):
+    return Initializer(N.INIT_ORTHOGONAL, seed, 0.0 if gain is None else gain, name="Orthogonal")
+
+
+# ---- activations (models/Activation.scala:26-84) ------------------------------------------------------------
+@dataclass(frozen=True)
+class Activation:
+    code: int
+    name: str
+    threshold: float = 0.0
+
+    @property
+    def identity(self):
+        return self.code == N.ACT_IDENTITY
+
+    @property
+    def layer(self):
+        return Activate(self)
+
+    def __repr__(self):
+        return self.name
+
+
+Identity = Activation(N.ACT_IDENTITY, "Identity")
+Sigmoid = Activation(N.ACT_SIGMOID, "Sigmoid")
+Tanh = Activation(N.ACT_TANH, "Tanh")
+Softmax = Activation(N.ACT_SOFTMAX, "Softmax")
+
+
+def ReLU(threshold: float = 0.0):
+    return Activation(N.ACT_RELU, "ReLU" if threshold == 0 else f"ReLU({threshold})", float(threshold))
+
+
+# ---- losses (models/Loss.scala:10-58) -----------------------------------------------------------------------
+@dataclass(frozen=True)
+class Loss:
+    code: int
+    name: str
+
+    def __repr__(self):
+        return self.name
+
+
+MeanSquaredError = Loss(N.LOSS_MSE, "MeanSquaredError")
+BinaryCrossentropy = Loss(N.LOSS_BCE, "BinaryCrossentropy")
+CategoricalCrossentropy = Loss(N.LOSS_CCE, "CategoricalCrossentropy")
+
+
+# ---- regularisation: only `Zero` is on the accelerated path --------------------------------------
+class _Zero:
+    def __repr__(self):
+        return "Zero"
+
+
+Zero = _Zero()
+
+
+def _check_reg(reg):
+    if reg is not Zero:
+        raise N.Unsupported(N.SB_ERR_UNSUPPORTED, "non-zero regularisation is outside the accelerated path (SURVEY 8b)")
+
+
+# ---- layers --------------------------------------------------------------------------------------------------
+class Layer:
+    """`layer/Layer.scala:24-26`: `>>` composes; compositions flatten (`Composed.scala:89-99`)."""
+
+    def leaves(self) -> List["Layer"]:
+        return [self]
+
+    def __rshift__(self, other: "Layer") -> "Layer":
+        return Composed(self.leaves() + other.leaves())
+
+    def andThen(self, other):
+        return self >> other
+
+    def to_native(self) -> N.sb_layer_desc:
+        raise NotImplementedError
+
+    def _desc(self, kind, **kw):
+        d = N.sb_layer_desc()
+        d.kind = kind
+        d.trainable = 1
+        d.window_h = d.window_w = d.stride_h = d.stride_w = 1
+        d.bn_fused = -1
+        for k, v in kw.items():
+            setattr(d, k, v)
+        return d
+
+
+class Composed(Layer):
+    def __init__(self, layers: Sequence[Layer]):
+        flat: List[Layer] = []
+        for l in layers:
+            flat.extend(l.leaves())
+        if not flat:
+            raise ValueError("requirement failed: at least 1 layer is required")
+        self.layers = flat
+
+    def leaves(self):
+        return list(self.layers)
+
+    def __repr__(self):
+        return " >> ".join(repr(l) for l in self.layers)
+
+
+class _DenseKernel(Layer):
+    def __init__(self, outputs, initializer, trainable):
+        self.outputs, self.initializer, self.trainable = outputs, initializer, trainable
+
+    def to_native(self):
+        d = self._desc(N.LAYER_DENSE, units=self.outputs, trainable=int(self.trainable))
+        d.init[0] = self.initializer.to_native()
+        return d
+
+    def __repr__(self):
+        return f"Dense({self.outputs})"
+
+
+class Bias(Layer):
+    def __init__(self, features, reg=Zero, initializer=Zeros, trainable=True):
+        _check_reg(reg)
+        self.features, self.initializer, self.trainable = features, initializer, trainable
+
+    def to_native(self):
+        d = self._desc(N.LAYER_BIAS, units=self.features, trainable=int(self.trainable))
+        d.init[2] = self.initializer.to_native()
+        return d
+
+    def __repr__(self):
+        return f"Bias({self.features})"
+
+
+class Activate(Layer):
+    def __init__(self, activation: Activation):
+        self.activation = activation
+
+    def to_native(self):
+        return self._desc(N.LAYER_ACTIVATE, activation=self.activation.code, relu_threshold=self.activation.threshold)
+
+    def __repr__(self):
+        return repr(self.activation)
+
+
+class _Flatten(Layer):
+    def to_native(self):
+        return self._desc(N.LAYER_FLATTEN)
+
+    def __repr__(self):
+        return "Flatten"
+
+
+Flatten = _Flatten()
+
+
+def Dense(outputs: int, activation: Activation = Identity, reg=Zero, bias: bool = True,
+          kernelInitializer: Initializer = GlorotUniform(), biasInitializer: Initializer = Zeros,
+          trainable: bool = True) -> Layer:
+    """layer/Dense.scala:30-41 -> Dense >> Bias >> activation.layer"""
+    _check_reg(reg)
+    layers: List[Layer] = [_DenseKernel(outputs, kernelInitializer, trainable)]
+    if bias:
+        layers.append(Bias(outputs, reg, biasInitializer))
+    if not activation.identity:
+        layers.append(activation.layer)
+    return layers[0] if len(layers) == 1 else Composed(layers)
+
+
+Valid, Same = "Valid", "Same"
+_PAD = {Valid: N.PAD_VALID, Same: N.PAD_SAME}
+
+
+def _pad_code(padding):
+    if padding not in _PAD:
+        raise N.Unsupported(N.SB_ERR_UNSUPPORTED, f"padding {padding!r}: only Valid/Same are on the accelerated path")
+    return _PAD[padding]
+
+
+class _Conv2DKernel(Layer):
+    def __init__(self, filters, kernel, strides, padding, initializer, trainable):
+        self.filters, self.kernel, self.strides, self.padding = filters, tuple(kernel), tuple(strides), padding
+        self.initializer, self.trainable = initializer, trainable
+
+    def to_native(self):
+        d = self._desc(N.LAYER_CONV2D, units=self.filters, window_h=self.kernel[0], window_w=self.kernel[1],
+                       stride_h=self.strides[0], stride_w=self.strides[1], padding=_pad_code(self.padding),
+                       trainable=int(self.trainable))
+        d.init[0] = self.initializer.to_native()
+        return d
+
+    def __repr__(self):
+        return f"Conv2D({self.filters},({self.kernel[0]},{self.kernel[1]}),({self.strides[0]},{self.strides[1]}),{self.padding},NHWC)"
+
+
+def Conv2D(filters: int, kernel: Tuple[int, int] = (3, 3), strides: Tuple[int, int] = (1, 1), padding=Valid,
+           format: str = "NHWC", activation: Activation = Identity, bias: bool = False,
+           kernelInitializer: Initializer = GlorotUniform(), biasInitializer: Initializer = Zeros, biasReg=Zero,
+           trainable: bool = True) -> Layer:
+    """layer/Conv2D.scala:54-68 -> Conv2D [>> Bias] [>> activation]; NOTE bias defaults to False."""
+    if format != "NHWC":
+        raise N.Unsupported(N.SB_ERR_UNSUPPORTED, "NCHW is outside the accelerated path (SURVEY 8b)")
+    layers: List[Layer] = [_Conv2DKernel(filters, kernel, strides, padding, kernelInitializer, trainable)]
+    if bias:
+        layers.append(Bias(filters, biasReg, biasInitializer))
+    if not activation.identity:
+        layers.append(activation.layer)
+    return layers[0] if len(layers) == 1 else Composed(layers)
+
+
+class Pool2D(Layer):
+    """layer/Pool2D.scala:28-57: window (2,2), strides (1,1), Valid, Max.  `reduce` is recorded but the layer's
+    build never forwards it, so pooling is always Max."""
+
+    def __init__(self, window=(2, 2), strides=(1, 1), padding=Valid, format="NHWC", reduce="Max"):
+        if format != "NHWC":
+            raise N.Unsupported(N.SB_ERR_UNSUPPORTED, "NCHW is outside the accelerated path (SURVEY 8b)")
+        if padding not in _PAD:
+            raise ValueError("requirement failed: only [Same, Valid] paddings are supported")
+        self.window, self.strides, self.padding, self.reduce = tuple(window), tuple(strides), padding, reduce
+
+    def to_native(self):
+        return self._desc(N.LAYER_POOL2D, window_h=self.window[0], window_w=self.window[1], stride_h=self.strides[0],
+                          stride_w=self.strides[1], padding=_PAD[self.padding],
+                          pool_reduce=N.POOL_AVG if self.reduce == "Avg" else N.POOL_MAX)
+
+    def __repr__(self):
+        return f"Pool2D(({self.window[0]},{self.window[1]}),({self.strides[0]},{self.strides[1]}),{self.padding},NHWC,{self.reduce})"
+
+
+class BatchNorm(Layer):
+    """layer/BatchNorm.scala:63-96.  `bnMode`: "reference" reproduces the fused path's output wiring bug for bug
+    (SURVEY App. B-Q5), "correct" is the TF op as intended."""
+
+    def __init__(self, axes=(-1,), momentum=0.99, epsilon=1e-3, betaInitializer=Zeros, gammaInitializer=Ones,
+                 movingMeanInitializer=Zeros, movingVarianceInitializer=Ones, fused: Optional[bool] = None,
+                 trainable=True, bnMode="reference"):
+        if tuple(axes) != (-1,):
+            raise N.Unsupported(N.SB_ERR_UNSUPPORTED, "BatchNorm axes other than [-1] are outside the accelerated path")
+        self.momentum, self.epsilon, self.fused, self.trainable, self.bnMode = momentum, epsilon, fused, trainable, bnMode
+        self.inits = (gammaInitializer, betaInitializer, movingMeanInitializer, movingVarianceInitializer)
+
+    def to_native(self):
+        d = self._desc(N.LAYER_BATCHNORM, bn_momentum=self.momentum, bn_epsilon=self.epsilon,
+                       bn_mode=0 if self.bnMode == "reference" else 1,
+                       bn_fused=-1 if self.fused is None else int(self.fused), trainable=int(self.trainable))
+        for i, init in enumerate(self.inits):
+            d.init[i] = init.to_native()
+        return d
+
+    def __repr__(self):
+        return "BatchNorm(List(-1))"
+
+
+class RNN(Layer):
+    """layer/RNN.scala:27-94 with an LSTMCell (the only cell on the accelerated path)."""
+
+    def __init__(self, cell: "LSTMCell", returnSequence=False, stateful=False):
+        if returnSequence or stateful:
+            raise N.Unsupported(N.SB_ERR_UNSUPPORTED, "returnSequence / stateful RNNs are outside the accelerated path")
+        if not isinstance(cell, LSTMCell):
+            raise N.Unsupported(N.SB_ERR_UNSUPPORTED, "only LSTMCell is on the accelerated path")
+        self.cell = cell
+
+    def to_native(self):
+        c = self.cell
+        d = self._desc(N.LAYER_LSTM, units=c.units, activation=c.activation.code,
+                       recurrent_activation=c.recurrentActivation.code, use_bias=int(c.bias))
+        for i, init in enumerate((c.kernelInitializer, c.recurrentInitializer, c.biasInitializer, c.biasForgetInitializer)):
+            d.init[i] = init.to_native()
+        return d
+
+    def __repr__(self):
+        return f"RNN({self.cell!r})"
+
+
+@dataclass
+class LSTMCell:
+    units: int
+    activation: Activation = Tanh
+    recurrentActivation: Activation = Sigmoid
+    bias: bool = True
+    kernelInitializer: Initializer = GlorotUniform()
+    recurrentInitializer: Initializer = Orthogonal()
+    biasInitializer: Initializer = Zeros
+    biasForgetInitializer: Initializer = Ones
+
+    def __repr__(self):
+        return f"LSTMCell({self.units},{self.activation!r},{self.recurrentActivation!r},{str(self.bias).lower()})"
+
+
+def LSTM(units, activation=Tanh, recurrentActivation=Sigmoid, bias=True, kernelInitializer=GlorotUniform(),
+         recurrentInitializer=Orthogonal(), biasInitializer=Zeros, biasForgetInitializer=Ones, returnSequence=False,
+         stateful=False) -> RNN:
+    """layer/RNN.scala:208-239"""
+    return RNN(LSTMCell(units, activation, recurrentActivation, bias, kernelInitializer, recurrentInitializer,
+                        biasInitializer, biasForgetInitializer), returnSequence, stateful)
+
+
+# ---- optimizers (optimizers/*.scala; defaults as in the case classes) ----------------------------------------
+@dataclass(frozen=True)
+class Algorithm:
+    code: int
+    rate: float = 0.0
+    beta1: float = 0.0
+    beta2: float = 0.0
+    epsilon: float = 0.0
+    initAcc: float = 0.0
+    nesterov: bool = False
+    name: str = ""
+
+    def __repr__(self):
+        return self.name
+
+
+def SGD(rate=0.01, momentum=0.0, nesterov=False):
+    return Algorithm(N.OPT_SGD, rate=rate, beta1=momentum, nesterov=nesterov, name=f"SGD({rate},{momentum},{nesterov})")
+
+
+def Adam(rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-7):
+    return Algorithm(N.OPT_ADAM, rate, beta1, beta2, epsilon, name=f"Adam({rate},{beta1},{beta2},{epsilon})")
+
+
+def AdaGrad(rate=0.001, epsilon=1e-7):
+    return Algorithm(N.OPT_ADAGRAD, rate=rate, epsilon=epsilon, name=f"AdaGrad({rate},{epsilon})")
+
+
+def RMSProp(rate=0.001, rho=0.9, epsilon=1e-7):
+    return Algorithm(N.OPT_RMSPROP, rate=rate, beta1=rho, epsilon=epsilon, name=f"RMSProp({rate},{rho},{epsilon})")
+
+
+def AdaDelta(rate=1.0, rho=0.9, epsilon=1e-7):
+    return Algorithm(N.OPT_ADADELTA, rate=rate, beta1=rho, epsilon=epsilon, name=f"AdaDelta({rate},{rho},{epsilon})")
+
+
+def Adamax(rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-7, initAcc=0.001):
+    return Algorithm(N.OPT_ADAMAX, rate, beta1, beta2, epsilon, initAcc, name=f"Adamax({rate},{beta1},{beta2},{epsilon},{initAcc})")
+
+
+def Nadam(beta1=0.9, beta2=0.999, epsilon=1e-7, initAcc=0.001):
+    return Algorithm(N.OPT_NADAM, 0.0, beta1, beta2, epsilon, initAcc, name=f"Nadam({beta1},{beta2},{epsilon},{initAcc})")
+
+
+def AMSGrad(rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-7):
+    return Algorithm(N.OPT_AMSGRAD, rate, beta1, beta2, epsilon, name=f"AMSGrad({rate},{beta1},{beta2},{epsilon})")
+
+
+def LinearRegression(bias=True, kernelInitializer=Zeros, biasInitializer=Zeros):
+    """models/LinearRegression.scala:20-31"""
+    return Dense(1, Identity, bias=bias, kernelInitializer=kernelInitializer, biasInitializer=biasInitializer)
+
+
+def LogisticRegression(bias=True, kernelInitializer=Zeros, biasInitializer=Zeros):
+    """models/LogisticRegression.scala:19-30"""
+    return Dense(1, Sigmoid, bias=bias, kernelInitializer=kernelInitializer, biasInitializer=biasInitializer)

@@ -1,0 +1,376 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs and against
+the reference's golden vectors.  Tolerances are stated per test.  Run on the B200 box with `-m gpu`.
+
+fp32 (SB_PREC_FP32) tolerance rationale: every contraction accumulates in fp32 with FMA in a different association
+order than NumPy/BLAS (and than TF-CPU's Eigen), transcendental functions differ at the 1-2 ulp level; so values are
+compared with rtol 2e-5 / atol 2e-6 after one op chain and rtol 1e-3 / atol 2e-5 after tens of optimizer steps."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+import scanet3_b200 as S
+from helpers import OALG, OLOSS, SALG, SLOSS, assert_params_close, build_models, synth_classification
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+
+
+def oracle_init(omodel, alg, in_shape_batched, seed_params=None):
+    defs, mp, op = O.init_params(omodel, alg, in_shape_batched, np.float32, seed_params)
+    return defs, mp, op
+
+
+def make_engine(smodel, loss, alg, batch, in_shape, lab_shape, **kw):
+    return S.Engine(smodel, loss, alg, batch, in_shape, lab_shape, device=0, **kw)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# initialisers: device Philox is bit-compatible with the restated TF Philox (InitializerSpec.scala:23-42)
+# ---------------------------------------------------------------------------------------------------------------
+def test_device_philox_matches_tf_goldens_and_oracle():
+    e = make_engine(S.Dense(3, kernelInitializer=S.RandomUniform(-1, 1, seed=1), bias=False), S.MeanSquaredError, S.SGD(), 1,
+                    (1,), (3,))
+    e.init_params()
+    w = e.get_param("weights").reshape(-1)
+    assert np.array_equal(np.round(w * f32(100)) / f32(100), np.array([0.63, -0.84, 0.78], f32))
+    assert np.array_equal(w, O.RandomUniform(-1, 1, seed=1).build((3,)))
+    e.close()
+    om, sm = build_models([("dense", 50, "sigmoid"), ("dense", 10, "softmax")], seed=7)
+    e = make_engine(sm, S.CategoricalCrossentropy, S.Adamax(), 4, (784,), (10,))
+    e.init_params()
+    _, mp, op = oracle_init(om, O.Adamax(), (4, 784))
+    got = e.get_model_params()
+    for k, v in mp.items():
+        assert np.array_equal(got[k], v), k  # GlorotUniform: bit exact
+    gop = e.get_opt_params()
+    for k, v in op.items():
+        assert np.array_equal(gop[k], v), k  # Const(initAcc)
+    e.close()
+    e = make_engine(S.Dense(64, kernelInitializer=S.RandomNormal(0.0, 1.0, seed=5), bias=False), S.MeanSquaredError, S.SGD(),
+                    1, (33,), (64,))
+    e.init_params()
+    np.testing.assert_allclose(e.get_param("weights"), O.RandomNormal(0.0, 1.0, seed=5).build((33, 64)), rtol=0, atol=2e-6)
+    e.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the reference's golden vectors, evaluated through the engine
+# ---------------------------------------------------------------------------------------------------------------
+X4 = np.array([[0, 0, 1], [0, 1, 1], [1, 0, 1], [1, 1, 1]], f32)
+W34 = np.array([[1, 0.5, 1, 0.1], [0.1, 1, 1, 1], [1, 0, 0.2, 0.3]], f32)
+
+
+def test_dense_layer_goldens():  # models/layer/DenseLayerSpec.scala:17-41, 55-78
+    e = make_engine(S.Dense(4, S.Sigmoid), S.BinaryCrossentropy, S.SGD(), 4, (3,), (4,))
+    e.set_params({"0/weights": W34, "1/weights": np.zeros(4, f32)})
+    exp = np.array([[0.731059, 0.500000, 0.549834, 0.574442], [0.750260, 0.731059, 0.768525, 0.785835],
+                    [0.880797, 0.622459, 0.768525, 0.598688], [0.890903, 0.817574, 0.900250, 0.802184]], f32)
+    np.testing.assert_allclose(e.predict(X4), exp, atol=7e-7)
+    y = np.array([[0.7310586, 0.5, 0.549834, 0.5744425], [0.7502601, 0.7310586, 0.76852477, 0.7858349],
+                  [0.8807971, 0.6224593, 0.76852477, 0.59868765], [0.89090323, 0.81757444, 0.9002496, 0.80218387]], f32)
+    e.set_params({"0/weights": np.zeros((3, 4), f32), "1/weights": np.zeros(4, f32)})
+    _, g = e.compute_grads(X4, y)
+    wg = np.array([[-0.048231270, -0.027502108, -0.041798398, -0.025054470],
+                   [-0.040072710, -0.034289565, -0.041798398, -0.036751173],
+                   [-0.078313690, -0.041943270, -0.061695820, -0.047571808]], f32)
+    np.testing.assert_allclose(g["0/weights"], wg, rtol=3e-6, atol=1e-8)
+    np.testing.assert_allclose(g["1/weights"], wg[2], rtol=3e-6, atol=1e-8)
+    e.close()
+
+
+def test_regression_goldens():  # models/RegressionSpec.scala:13-61, 67-105
+    e = make_engine(S.LinearRegression(), S.MeanSquaredError, S.SGD(), 2, (2,), (1,))
+    x = np.array([[1, 2], [2, 4]], f32)
+    y = np.array([[6], [12]], f32)
+    e.set_params({"0/weights": np.array([[2], [3]], f32), "1/weights": np.array([1], f32)})
+    assert e.eval_loss(x, y) == 17.0
+    assert np.array_equal(e.predict(x), np.array([[9], [17]], f32))
+    e.set_params({"0/weights": np.zeros((2, 1), f32), "1/weights": np.zeros(1, f32)})
+    _, g = e.compute_grads(x, y)
+    assert np.array_equal(g["0/weights"], np.array([[-30], [-60]], f32)) and np.array_equal(g["1/weights"], np.array([-18], f32))
+    e.close()
+    e = make_engine(S.LogisticRegression(), S.BinaryCrossentropy, S.SGD(), 2, (2,), (1,))
+    x = np.array([[0.34, 0.78], [0.6, 0.86]], f32)
+    y = np.array([[0.402], [0.47800002]], f32)
+    e.set_params({"0/weights": np.array([[0.2], [0.3]], f32), "1/weights": np.array([0.1], f32)})
+    assert abs(e.eval_loss(x, y) - 0.7422824) < 1e-6
+    np.testing.assert_allclose(e.predict(x), [[0.599168], [0.617276]], atol=7e-7)
+    _, g = e.compute_grads(x, y)
+    np.testing.assert_allclose(g["0/weights"], [[0.075301], [0.136784]], atol=7e-7)
+    np.testing.assert_allclose(g["1/weights"], [0.168222], atol=7e-7)
+    e.close()
+
+
+def test_composed_mse_golden():  # models/layer/ComposedLayerSpec.scala:17-48, 71-95
+    e = make_engine(S.Dense(3, S.Sigmoid) >> S.Dense(1, S.Sigmoid), S.MeanSquaredError, S.SGD(), 2, (3,), (1,))
+    assert e.model_param_paths() == ["0/weights", "1/weights", "3/weights", "4/weights"]
+    e.set_params({"0/weights": np.array([[1, 0.5, 1], [0.1, 1, 1], [1, 0, 0.2]], f32), "1/weights": np.zeros(3, f32),
+                  "3/weights": np.array([[0.1], [0.5], [1]], f32), "4/weights": np.zeros(1, f32)})
+    assert abs(e.eval_loss(np.array([[0, 0, 1], [0, 1, 1]], f32), np.array([[1], [0]], f32)) - 0.339962) < 1e-6
+    e.close()
+
+
+IMG = np.array([[2, 1, 2, 0, 1], [1, 3, 2, 2, 3], [1, 1, 3, 3, 0], [2, 2, 0, 1, 1], [0, 0, 3, 1, 2]], f32).reshape(1, 5, 5, 1)
+FIL = np.array([[2, 3], [0, 1]], f32).reshape(2, 2, 1, 1)
+
+
+@pytest.mark.parametrize("padding,strides,expected", [
+    ("Same", (1, 1), [[10, 10, 6, 6, 2], [12, 15, 13, 13, 6], [7, 11, 16, 7, 0], [10, 7, 4, 7, 2], [0, 9, 9, 8, 4]]),
+    ("Same", (2, 2), [[10, 6, 2], [7, 16, 0], [0, 9, 4]]),
+    ("Valid", (1, 1), [[10, 10, 6, 6], [12, 15, 13, 13], [7, 11, 16, 7], [10, 7, 4, 7]]),
+    ("Valid", (2, 2), [[10, 6], [7, 16]]),
+])
+def test_conv2d_goldens(padding, strides, expected):  # math/nn/KernelsSpec.scala:45-106; Conv2DLayerSpec.scala:13-36
+    exp = np.array(expected, f32)
+    e = make_engine(S.Conv2D(1, (2, 2), strides, padding), S.MeanSquaredError, S.SGD(), 1, (5, 5, 1), exp.shape + (1,))
+    e.set_param("weights", FIL)
+    assert np.array_equal(e.predict(IMG).reshape(exp.shape), exp)
+    e.close()
+
+
+def test_conv2d_gradient_goldens():  # math/nn/KernelsSpec.scala:146-157 (wgrad), 174-188 (dgrad via a second conv in front)
+    # d(sum(conv))/dW through MSE: with y = conv - n/2 the MSE gradient w.r.t. the output is exactly 1 everywhere
+    e = make_engine(S.Conv2D(1, (2, 2)), S.MeanSquaredError, S.SGD(), 1, (5, 5, 1), (4, 4, 1))
+    e.set_param("weights", FIL)
+    out = e.predict(IMG)
+    _, g = e.compute_grads(IMG, out - f32(8.0))  # dL/dout = 2*(8)/16 = 1
+    assert np.array_equal(g["weights"].reshape(2, 2), np.array([[26, 25], [25, 27]], f32))
+    e.close()
+    # dgrad: put a 1x1 identity conv in front so the 2x2 conv's input gradient becomes the first layer's weight gradient
+    # contracted with the image; check it against the oracle instead of a literal
+    om, sm = build_models([("conv", 1, "identity", (1, 1), (1, 1), "Valid", False), ("conv", 1, "identity", (2, 2), (1, 1), "Valid", False)])
+    e = make_engine(sm, S.MeanSquaredError, S.SGD(), 1, (5, 5, 1), (4, 4, 1))
+    p = {"0/weights": np.ones((1, 1, 1, 1), f32), "1/weights": FIL}
+    e.set_params(p)
+    y = np.zeros((1, 4, 4, 1), f32)
+    _, g = e.compute_grads(IMG, y)
+    _, og, _ = O.LossModel(om, O.MeanSquaredError).grad_stateful(IMG, y, p)
+    np.testing.assert_allclose(g["0/weights"], og["0/weights"], rtol=2e-6)
+    np.testing.assert_allclose(g["1/weights"], og["1/weights"], rtol=2e-6)
+    e.close()
+
+
+@pytest.mark.parametrize("padding,strides,expected", [
+    ("Same", (1, 1), [[3, 3, 2, 3, 3], [3, 3, 3, 3, 3], [2, 3, 3, 3, 1], [2, 3, 3, 2, 2], [0, 3, 3, 2, 2]]),
+    ("Same", (2, 2), [[3, 2, 3], [2, 3, 1], [0, 3, 2]]),
+    ("Valid", (1, 1), [[3, 3, 2, 3], [3, 3, 3, 3], [2, 3, 3, 3], [2, 3, 3, 2]]),
+    ("Valid", (2, 2), [[3, 2], [2, 3]]),
+])
+def test_maxpool_goldens(padding, strides, expected):  # math/nn/KernelsSpec.scala:200-256; Pool2DLayerSpec.scala:12-30
+    exp = np.array(expected, f32)
+    # a 1x1 conv with weight 1 in front gives the pool a trainable predecessor (the engine needs one parameter)
+    e = make_engine(S.Conv2D(1, (1, 1)) >> S.Pool2D((2, 2), strides, padding), S.MeanSquaredError, S.SGD(), 1, (5, 5, 1),
+                    exp.shape + (1,))
+    e.set_param("0/weights", np.ones((1, 1, 1, 1), f32))
+    assert np.array_equal(e.predict(IMG).reshape(exp.shape), exp)
+    e.close()
+
+
+def test_maxpool_gradient_first_max_rule():  # math/nn/KernelsSpec.scala:277-288
+    # dL/d(conv weight) = sum(image * poolgrad): compare the routed gradient through a 1x1 conv with the golden map
+    e = make_engine(S.Conv2D(1, (1, 1)) >> S.Pool2D((2, 2), (1, 1), "Same"), S.MeanSquaredError, S.SGD(), 1, (5, 5, 1), (5, 5, 1))
+    e.set_param("0/weights", np.ones((1, 1, 1, 1), f32))
+    out = e.predict(IMG)
+    _, g = e.compute_grads(IMG, out - f32(12.5))  # dL/dpool = 2*12.5/25 = 1
+    golden = np.array([[0, 0, 1, 0, 0], [0, 4, 0, 0, 4], [0, 0, 3, 1, 0], [2, 0, 0, 0, 1], [1, 0, 4, 0, 4]], f32)
+    assert float(g["0/weights"].reshape(())) == float(np.sum(golden * IMG.reshape(5, 5)))
+    e.close()
+
+
+def test_batchnorm_generic_golden():  # models/layer/BatchNormSpec.scala:30-49
+    x = np.array([[0, 0, 10], [0, 8, 4], [5, 0, 13], [20, 3, 8]], f32)
+    e = make_engine(S.Dense(4) >> S.BatchNorm(momentum=0.5), S.MeanSquaredError, S.SGD(rate=0.0), 4, (3,), (4,))
+    assert e.model_param_paths() == ["0/weights", "1/weights", "2/beta", "2/gamma", "2/moving_mean", "2/moving_variance"]
+    e.set_params({"0/weights": W34, "1/weights": np.zeros(4, f32), "2/beta": np.zeros((1, 4), f32), "2/gamma": np.ones((1, 4), f32),
+                  "2/moving_mean": np.zeros((1, 4), f32), "2/moving_variance": np.ones((1, 4), f32)})
+    e.init_opt_params()
+    e.train_step(x, np.zeros((4, 4), f32), 1)  # rate 0: only the moving statistics change
+    np.testing.assert_allclose(e.get_param("2/moving_mean"), [[7.638, 2.938, 5.375, 3.0]], atol=6e-4)
+    np.testing.assert_allclose(e.get_param("2/moving_variance"), [[39.828, 13.148, 35.764, 3.47]], atol=6e-4)
+    e.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# trajectories: per-step loss and parameters after n steps vs the oracle
+# ---------------------------------------------------------------------------------------------------------------
+def run_trajectory(spec, loss, alg_name, alg_kw, batch, in_shape, classes, steps, seed=3, rtol=1e-3, atol=2e-5, loss_rtol=2e-5,
+                   precision=S.PREC_FP32, use_graph=True):
+    om, sm = build_models(spec)
+    oalg, salg = OALG[alg_name](**alg_kw), SALG[alg_name](**alg_kw)
+    x, y = synth_classification(batch * steps, in_shape, classes, seed)
+    e = make_engine(sm, SLOSS[loss], salg, batch, in_shape, (classes,), precision=precision, use_graph=use_graph)
+    e.init_params()
+    _, mp, op = oracle_init(om, oalg, (batch,) + tuple(in_shape))
+    assert_params_close(e.get_model_params(), mp, 0, 0, "init")
+    lm = O.LossModel(om, OLOSS[loss])
+    for t in range(1, steps + 1):
+        xb, yb = x[(t - 1) * batch:t * batch], y[(t - 1) * batch:t * batch]
+        gl = e.train_step(xb, yb, t)
+        mp, op, ol = O.train_step(lm, oalg, xb, yb, mp, op, t)
+        assert abs(gl - float(ol)) <= loss_rtol * abs(float(ol)) + 1e-6, (t, gl, float(ol))
+    assert_params_close(e.get_model_params(), mp, rtol, atol, f"after {steps} steps")
+    assert_params_close(e.get_opt_params(), op, rtol * 5, atol, f"opt state after {steps} steps")
+    e.close()
+
+
+MLP = [("dense", 50, "sigmoid"), ("dense", 10, "softmax")]
+
+
+@pytest.mark.parametrize("alg,kw", [
+    ("sgd", dict(rate=0.05)), ("sgd", dict(rate=0.05, momentum=0.1, nesterov=True)), ("adam", dict(rate=0.01)),
+    ("adagrad", dict(rate=0.05)), ("rmsprop", dict(rate=0.005)), ("adadelta", dict()), ("adamax", dict(rate=0.01)),
+    ("nadam", dict()), ("amsgrad", dict(rate=0.01)),
+])
+def test_mlp_trajectory_all_optimizers(alg, kw):  # BASELINE config 1 shape (784 -> 50 -> 10), smaller batch
+    run_trajectory(MLP, "cce", alg, kw, batch=200, in_shape=(784,), classes=10, steps=12)
+
+
+def test_mlp_full_batch_config1():  # BASELINE config 1 exactly: batch 1000
+    run_trajectory(MLP, "cce", "adam", dict(rate=0.01), batch=1000, in_shape=(784,), classes=10, steps=5)
+
+
+LENET = [("conv", 32, "relu", (3, 3), (1, 1), "Valid", False), ("pool", (2, 2), (1, 1), "Valid"),
+         ("conv", 64, "relu", (3, 3), (1, 1), "Valid", False), ("pool", (2, 2), (1, 1), "Valid"), ("flatten",),
+         ("dense", 10, "softmax")]
+
+
+def test_lenet_small_trajectory():
+    run_trajectory(LENET, "cce", "adam", dict(rate=0.001), batch=8, in_shape=(12, 12, 1), classes=10, steps=8, rtol=2e-3,
+                   atol=3e-5, loss_rtol=5e-5)
+
+
+def test_lenet_config2_full_size():  # BASELINE config 2: 28x28x1, batch 100 (fp32 contractions)
+    run_trajectory(LENET, "cce", "adam", dict(rate=0.001), batch=100, in_shape=(28, 28, 1), classes=10, steps=3, rtol=2e-3,
+                   atol=3e-5, loss_rtol=5e-5)
+
+
+def test_strided_same_conv_with_bias_and_sigmoid_trajectory():
+    spec = [("conv", 8, "sigmoid", (3, 3), (2, 2), "Same", True), ("pool", (2, 2), (2, 2), "Same"),
+            ("conv", 16, "tanh", (2, 2), (1, 1), "Same", True), ("flatten",), ("dense", 4, "sigmoid")]
+    run_trajectory(spec, "mse", "sgd", dict(rate=0.1, momentum=0.5), batch=6, in_shape=(9, 11, 3), classes=4, steps=6,
+                   rtol=2e-3, atol=3e-5, loss_rtol=5e-5)
+
+
+@pytest.mark.parametrize("mode", ["reference", "correct"])
+def test_batchnorm_cnn_trajectory(mode):  # BASELINE config 5 pattern (fused rank-4 BN), small
+    spec = [("conv", 8, "relu", (3, 3), (1, 1), "Valid", False), ("bn", 0.99, mode), ("pool", (2, 2), (2, 2), "Valid"),
+            ("flatten",), ("dense", 16, "identity"), ("bn", 0.9, mode), ("dense", 10, "softmax")]
+    run_trajectory(spec, "cce", "adam", dict(rate=0.001), batch=16, in_shape=(10, 10, 3), classes=10, steps=6, rtol=3e-3,
+                   atol=5e-5, loss_rtol=1e-4)
+
+
+def test_graph_and_eager_are_bit_identical():
+    om, sm = build_models(MLP)
+    x, y = synth_classification(400, (784,), 10, 11)
+    outs = []
+    for use_graph in (True, False):
+        e = make_engine(sm, S.CategoricalCrossentropy, S.Adam(0.01), 100, (784,), (10,), use_graph=use_graph)
+        e.init_params()
+        losses = [e.train_step(x[i * 100:(i + 1) * 100], y[i * 100:(i + 1) * 100], i + 1) for i in range(4)]
+        outs.append((losses, e.get_params()))
+        e.close()
+    assert outs[0][0] == outs[1][0]
+    for k in outs[0][1]:
+        assert np.array_equal(outs[0][1][k], outs[1][1][k]), k
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the per-worker epoch (optimizeOnPartition, Optimizer.scala:106-161) with the shard resident in HBM
+# ---------------------------------------------------------------------------------------------------------------
+def test_resident_epoch_matches_optimize_on_partition():
+    om, sm = build_models(MLP)
+    batch, rows = 64, 64 * 5 + 17  # partial tail batch of 17 rows is dropped (Iterators.scala:46-47,90)
+    x, y = synth_classification(rows, (784,), 10, 5)
+    oalg = O.Adam(rate=0.01)
+    e = make_engine(sm, S.CategoricalCrossentropy, S.Adam(0.01), batch, (784,), (10,))
+    e.init_params()
+    e.upload_dataset(x, y)
+    _, mp, op = oracle_init(om, oalg, (batch, 784))
+    lm = O.LossModel(om, O.CategoricalCrossentropy)
+    global_iter = 0
+    for epoch in range(3):
+        iters, loss = e.train_epoch(global_iter)
+        res = O.optimize_on_partition(lm, oalg, x, y, batch, global_iter, mp, op)
+        assert iters == res.iterations == 5
+        assert abs(loss - res.loss) <= 3e-5 * abs(res.loss) + 1e-6  # forward-only loss on the last batch, updated params
+        mp, op = res.model_params, res.opt_params
+        global_iter += iters  # the step counter is global (Optimizer.scala:88,143)
+    assert_params_close(e.get_model_params(), mp, 1e-3, 2e-5, "after 3 epochs")
+    assert_params_close(e.get_opt_params(), op, 5e-3, 2e-5, "opt after 3 epochs")
+    # a global_iter offset (what a second worker contributes) changes the bias correction: check it is honoured
+    iters, _ = e.train_epoch(1000)
+    res = O.optimize_on_partition(lm, oalg, x, y, batch, 1000, mp, op)
+    assert_params_close(e.get_model_params(), res.model_params, 1e-3, 2e-5, "epoch at global_iter=1000")
+    e.close()
+
+
+def test_shard_smaller_than_one_batch_is_rejected():  # Iterators.scala:79-81 NoSuchElementException
+    _, sm = build_models(MLP)
+    e = make_engine(sm, S.CategoricalCrossentropy, S.Adam(), 64, (784,), (10,))
+    e.init_params()
+    x, y = synth_classification(10, (784,), 10, 1)
+    e.upload_dataset(x, y)
+    with pytest.raises(S.IllegalArgument):
+        e.train_epoch(0)
+    e.close()
+
+
+def test_state_errors_and_unsupported():
+    _, sm = build_models(MLP)
+    e = make_engine(sm, S.CategoricalCrossentropy, S.Adam(), 8, (784,), (10,))
+    x, y = synth_classification(8, (784,), 10, 1)
+    with pytest.raises(S.NativeError):
+        e.train_step(x, y, 1)  # params not initialised
+    with pytest.raises(S.IllegalArgument):
+        e.set_param("0/weights", np.zeros(3, f32))  # wrong size
+    with pytest.raises(S.IllegalArgument, match="missing 9/nope param"):  # core/Params.scala:22-23
+        S.native.check(e._lib.sb_params_get(e.handle, b"9/nope", np.zeros(1, f32).ctypes.data, 1))
+    e.close()
+    with pytest.raises(S.Unsupported):
+        S.Engine(S.Dense(3, kernelInitializer=S.GlorotUniform()), S.MeanSquaredError, S.SGD(), 2, (2,), (3,)).init_params()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the reference's optimizer tests, re-run through the drop-in API (optimizers/*Spec.scala)
+# ---------------------------------------------------------------------------------------------------------------
+def _linear(fixtures_dir):
+    d = np.loadtxt(os.path.join(fixtures_dir, "linear_function_1.scv"), delimiter=",", dtype=np.float32)
+    return S.Dataset(d[:, :1], d[:, 1:])
+
+
+@pytest.mark.parametrize("alg,n_epochs,threshold", [
+    (S.SGD(), 100, 11.0), (S.SGD(momentum=0.1), 100, 11.0), (S.SGD(momentum=0.1, nesterov=True), 100, 11.0),
+    (S.Adam(rate=0.1), 100, 12.0), (S.AdaGrad(rate=1.0), 100, 9.0), (S.RMSProp(rate=0.06), 100, 9.4),
+    (S.AdaDelta(), 100, 50.0), (S.Adamax(), 70, 9.0), (S.Nadam(), 50, 9.0), (S.AMSGrad(rate=0.1), 100, 9.0),
+])
+def test_optimizer_specs_linear_regression(fixtures_dir, alg, n_epochs, threshold):
+    ds = _linear(fixtures_dir)
+    rec = S.RecordLoss(console=False)
+    trained = (ds.train(S.LinearRegression()).loss(S.MeanSquaredError).using(alg).batch(97)
+               .each(S.epochs(1), rec).stopAfter(S.epochs(n_epochs)).quiet().run())
+    loss = trained.loss(ds.features[:97], ds.labels[:97])
+    assert loss <= threshold
+    assert len(rec.history) == n_epochs
+    # and the whole run agrees with the oracle's run of the same training
+    d = np.loadtxt(os.path.join(fixtures_dir, "linear_function_1.scv"), delimiter=",", dtype=np.float32)
+    name = {0: "sgd", 1: "adam", 2: "adagrad", 3: "rmsprop", 4: "adadelta", 5: "adamax", 6: "nadam", 7: "amsgrad"}[alg.code]
+    kw = {"sgd": dict(rate=alg.rate, momentum=alg.beta1, nesterov=alg.nesterov), "adam": dict(rate=alg.rate),
+          "adagrad": dict(rate=alg.rate), "rmsprop": dict(rate=alg.rate), "adadelta": dict(), "adamax": dict(), "nadam": dict(),
+          "amsgrad": dict(rate=alg.rate)}[name]
+    om = O.Dense(1, O.Identity, kernel_initializer=O.Zeros)
+    mp, _, hist = O.run_training(om, O.MeanSquaredError, OALG[name](**kw), d[:, :1], d[:, 1:], batch=97, epochs=n_epochs)
+    np.testing.assert_allclose(rec.history[-1], hist[-1][2], rtol=2e-3)
+    assert_params_close(trained.params, mp, 2e-3, 1e-4, "final params")
+
+
+def test_adam_logistic_regression_spec(fixtures_dir):  # optimizers/AdamSpec.scala:44-64
+    d = np.loadtxt(os.path.join(fixtures_dir, "logistic_regression_1.scv"), delimiter=",", dtype=np.float64)
+    ds = S.Dataset((d[:, :2].astype(f32) / f32(100)), d[:, 2:].astype(f32))
+    trained = (ds.train(S.LogisticRegression()).loss(S.BinaryCrossentropy).using(S.Adam(0.1)).batch(100)
+               .each(S.epochs(1), S.RecordLoss(console=False)).stopAfter(S.epochs(100)).quiet().run())
+    assert trained.loss(ds.features, ds.labels) <= 0.4
+    assert S.accuracy(trained, ds) >= 0.9
+    probe = trained.result(np.array([[0.3462, 0.7802], [0.6018, 0.8630]], f32))
+    assert np.array_equal(np.round(probe), [[0], [1]])

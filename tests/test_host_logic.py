@@ -1,0 +1,191 @@
+"""CPU-only tests: the C-ABI library loads and exports every declared symbol, the plan (param paths, shapes, arena
+layout) agrees with the oracle's restatement of the reference, host-side averaging logic, and the world_size-2
+gloo path.  No compute calls: there is no GPU here and the product has no CPU fallback."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle as O
+import scanet3_b200 as S
+from helpers import build_models
+from scanet3_b200 import _native as N
+from scanet3_b200.distributed import averaging_weights, ordered_weighted_sum, spark_chain_shape
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_symbol_the_header_declares():
+    header = open(os.path.join(ROOT, "include", "scanet_b200.h")).read()
+    declared = set(re.findall(r"\b(sb_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 38
+    lib = ctypes.CDLL(N.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} is declared in include/scanet_b200.h but not exported"
+    assert declared == set(N.PROTOTYPES.keys()), declared ^ set(N.PROTOTYPES.keys())
+    assert N.lib().sb_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_a_device():
+    if N.lib().sb_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(S.NativeError) as ei:
+        S.Engine(S.Dense(2), S.MeanSquaredError, S.SGD(), 2, (3,), (2,), device=0)
+    assert ei.value.code == N.SB_ERR_CUDA and "no CPU fallback" in str(ei.value)
+    e = S.Engine(S.Dense(2), S.MeanSquaredError, S.SGD(), 2, (3,), (2,), device=-1)
+    for call in (e.init_params, lambda: e.train_epoch(0), lambda: e.predict(np.zeros((2, 3), np.float32))):
+        with pytest.raises(S.NativeError) as ei:
+            call()
+        assert ei.value.code == N.SB_ERR_CUDA
+
+
+def test_the_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "scanet3_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle", src, re.M), f
+                assert "oracle/" not in src or f.endswith(".cu"), f
+
+
+SPECS = {
+    "cfg1_mlp": ([("dense", 50, "sigmoid"), ("dense", 10, "softmax")], (784,), 1000),
+    "cfg2_lenet": ([("conv", 32, "relu", (3, 3), (1, 1), "Valid", False), ("pool", (2, 2), (1, 1), "Valid"),
+                    ("conv", 64, "relu", (3, 3), (1, 1), "Valid", False), ("pool", (2, 2), (1, 1), "Valid"), ("flatten",),
+                    ("dense", 10, "softmax")], (28, 28, 1), 100),
+    "cfg3_lstm": ([("lstm", 256), ("dense", 1, "tanh")], (64, 1), 1024),
+    "cfg4_wide": ([("dense", 4096, "relu")] * 4 + [("dense", 10, "softmax")], (784,), 8192),
+    "cfg5_cifar_bn": ([("conv", 64, "relu", (3, 3), (1, 1), "Valid", False), ("bn", 0.99, "reference"), ("pool", (2, 2), (2, 2), "Valid"),
+                       ("conv", 128, "relu", (3, 3), (1, 1), "Valid", False), ("bn", 0.99, "reference"), ("pool", (2, 2), (2, 2), "Valid"),
+                       ("conv", 256, "relu", (3, 3), (1, 1), "Valid", False), ("bn", 0.99, "reference"), ("pool", (2, 2), (2, 2), "Valid"),
+                       ("flatten",), ("dense", 10, "softmax")], (32, 32, 3), 256),
+}
+N_PARAMS = {"cfg1_mlp": 39760, "cfg2_lenet": 328490, "cfg3_lstm": 264449, "cfg4_wide": 53600266}
+
+
+@pytest.mark.parametrize("name", list(SPECS))
+def test_plan_matches_the_reference_param_layout(name):
+    spec, in_shape, batch = SPECS[name]
+    om, sm = build_models(spec)
+    out_dim = 1 if name == "cfg3_lstm" else 10
+    e = S.Engine(sm, S.MeanSquaredError, S.Adam(), batch, in_shape, (out_dim,), device=-1)
+    defs = O.model_params(om, (batch,) + in_shape)
+    got = {p: i for p, i in e.params.items() if i.role != N.ROLE_OPT}
+    assert list(got.keys()) == [k for k in defs if defs[k].trainable] + [k for k in defs if not defs[k].trainable] or \
+        set(got.keys()) == set(defs.keys())
+    for k, d in defs.items():
+        assert tuple(got[k].shape) == tuple(d.shape), k
+        assert (got[k].role == N.ROLE_WEIGHT) == d.trainable, k
+        assert got[k].aggregation == (N.AGG_AVG if d.aggregation == "avg" else N.AGG_NONE), k
+    # optimizer state `<weightPath>/<stateName>` for every trainable param (Optimizer.scala:118-121)
+    opt = O.opt_param_defs(defs, O.Adam())
+    assert set(p for p, i in e.params.items() if i.role == N.ROLE_OPT) == set(opt.keys())
+    assert e.output_shape == (batch, out_dim)
+    if name in N_PARAMS:
+        assert sum(i.numel for i in got.values() if i.role == N.ROLE_WEIGHT) == N_PARAMS[name]
+    # arena: 128-byte aligned tensors, weights first, then state, then one region per optimizer slot
+    offs = [i.offset for i in e.params.values()]
+    assert all(o % 32 == 0 for o in offs) and len(set(offs)) == len(offs)
+    e.close()
+
+
+@pytest.mark.parametrize("alg,slots", [(S.SGD(), ["velocity"]), (S.Adam(), ["momentum", "velocity"]), (S.AdaGrad(), ["grad_acc"]),
+                                       (S.RMSProp(), ["avg_grad"]), (S.AdaDelta(), ["avg_grad", "avg_delta"]),
+                                       (S.Adamax(), ["momentum_1", "momentum_2"]), (S.Nadam(), ["momentum", "velocity"]),
+                                       (S.AMSGrad(), ["momentum", "velocity", "corrected_velocity"])])
+def test_optimizer_state_names(alg, slots):
+    e = S.Engine(S.Dense(2), S.MeanSquaredError, alg, 2, (3,), (2,), device=-1)
+    assert e.opt_param_paths() == [f"{w}/{s}" for s in slots for w in ("0/weights", "1/weights")]
+    e.close()
+
+
+def test_invalid_models_raise_like_the_reference():
+    with pytest.raises(S.IllegalArgument):  # Conv2D on a rank-2 input (layer/Conv2D.scala:84-86)
+        S.Engine(S.Conv2D(4), S.MeanSquaredError, S.SGD(), 2, (3,), (2,), device=-1)
+    with pytest.raises(S.IllegalArgument):  # output does not match the labels
+        S.Engine(S.Dense(3), S.MeanSquaredError, S.SGD(), 2, (3,), (2,), device=-1)
+    with pytest.raises(S.Unsupported):
+        S.Conv2D(4, format="NCHW")
+    with pytest.raises(S.Unsupported):
+        S.maximize(S.Dense(1))
+    with pytest.raises(ValueError, match="only \\[Same, Valid\\] paddings are supported"):
+        S.Pool2D(padding=((1, 0), (1, 0)))
+    with pytest.raises(TypeError):  # builder incomplete: run() must not be callable (Optimizer.scala:256-310)
+        S.Dataset(np.zeros((2, 1)), np.zeros((2, 1))).train(S.Dense(1)).loss(S.MeanSquaredError).run()
+    assert repr(S.Dense(4, S.Sigmoid) >> S.Dense(1, S.Sigmoid)) == "Dense(4) >> Bias(4) >> Sigmoid >> Dense(1) >> Bias(1) >> Sigmoid"
+    assert repr(S.LinearRegression()) == "Dense(1) >> Bias(1)"  # RegressionSpec.scala:63-65
+    assert repr(S.Conv2D(1, (2, 2))) == "Conv2D(1,(2,2),(1,1),Valid,NHWC)"  # Conv2DLayerSpec.scala:34
+    assert repr(S.Pool2D((2, 2))) == "Pool2D((2,2),(1,1),Valid,NHWC,Max)"  # Pool2DLayerSpec.scala:28
+
+
+def test_spark_chain_weights_agree_between_library_host_mirror_and_oracle():
+    for k in range(1, 9):
+        w_lib = S.spark_chain_weights(k)
+        w_py, n_groups = spark_chain_shape(k)
+        w_or = O.spark_chain_weights(k)
+        assert np.allclose(w_lib, w_py) and np.allclose(w_py, w_or), k
+        assert abs(sum(w_py) - 1.0) < 1e-12
+    assert spark_chain_shape(2) == ([0.5, 0.5], 1)
+    assert spark_chain_shape(4) == ([0.125, 0.125, 0.25, 0.5], 1)
+    assert spark_chain_shape(8)[1] == 2 and spark_chain_shape(8)[0] == [1 / 16, 1 / 16, 1 / 16, 1 / 16, 1 / 8, 1 / 8, 1 / 4, 1 / 4]
+
+
+def _fake_results(k, seed):
+    rng = np.random.default_rng(seed)
+    from collections import OrderedDict
+    return [O.StepResult(3 + r, OrderedDict(w=rng.normal(size=37).astype(np.float32)),
+                         OrderedDict(m=rng.normal(size=37).astype(np.float32)), float(rng.uniform())) for r in range(k)]
+
+
+@pytest.mark.parametrize("k", [2, 4, 8])
+def test_weighted_ordered_sum_reproduces_the_pairwise_chain_bit_for_bit(k):
+    """(l+r)/2 chains == power-of-two weighted sums in the same order: what the fused P2P kernel computes."""
+    res = _fake_results(k, k)
+    chain = O.spark_tree_reduce(res)
+    w, n_groups = spark_chain_shape(k)
+    for key, src in (("w", "model_params"), ("m", "opt_params")):
+        tot = None
+        for g in range(n_groups):
+            acc = None
+            for q in range(g, k, n_groups):
+                t = getattr(res[q], src)[key] * np.float32(w[q])
+                acc = t if acc is None else acc + t
+            tot = acc if tot is None else tot + acc
+        assert np.array_equal(tot, getattr(chain, src)[key])
+    assert ordered_weighted_sum([r.loss for r in res], w, n_groups) == pytest.approx(chain.loss, rel=1e-6)
+    assert chain.iterations == sum(r.iterations for r in res)
+
+
+def test_gloo_world_size_2_weighted_allreduce_and_scalar_combine(tmp_path):
+    """N>1 host path on CPU: two ranks, gloo, 127.0.0.1 rendezvous."""
+    script = tmp_path / "worker.py"
+    script.write_text(f'''
+import os, sys
+sys.path.insert(0, {ROOT!r})
+import numpy as np, torch, torch.distributed as dist
+from scanet3_b200 import _native as N
+from scanet3_b200.distributed import init_process_group_from_env, averaging_weights, allreduce_average_, combine_scalars
+rank, world = init_process_group_from_env()
+assert dist.get_backend() == "gloo" and world == 2
+w, ng = averaging_weights(world, N.AVG_SPARK_CHAIN)
+rng = np.random.default_rng(0)
+arenas = [rng.normal(size=1000).astype(np.float32) for _ in range(world)]
+t = torch.from_numpy(arenas[rank].copy())
+allreduce_average_(t, w, rank)
+expect = (arenas[0] + arenas[1]) / np.float32(2)
+assert np.array_equal(t.numpy(), expect), "k=2 must equal the reference's (l+r)/2 exactly"
+loss, iters = combine_scalars(1.0 + rank, 10 + rank, w, ng)
+assert loss == 1.5 and iters == 21
+dist.barrier()
+print("RANK_OK", rank)
+''')
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29731", WORLD_SIZE="2", CUDA_VISIBLE_DEVICES="")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"RANK_OK {r}" in o, o
