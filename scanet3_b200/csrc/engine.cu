@@ -429,7 +429,7 @@ static void run_forward(sb_engine* e, int mode) {
   const int nl = (int)e->L.size();
   for (int li = 0; li < nl; ++li) {
     LayerPlan& L = e->L[li];
-    if (L.fused_into_prev) continue;
+    if (L.fused_into_prev || L.skip_fwd) continue;
     if (e->softmax_cce_fused && li == nl - 1 && mode != FWD_INFER) continue;  // executed by the loss kernel
     float* in = e->acts[L.buf_in];
     float* out = e->acts[L.buf_out];
@@ -459,7 +459,12 @@ static void run_forward(sb_engine* e, int mode) {
         break;
       case SB_LAYER_CONV2D: {
         const ConvGeom& g = L.cg;
-        if (L.tc_kind && tc_conv_fwd(e, L, li)) break;
+        const double cbytes = 4.0 * ((double)L.in.numel() + n_out + e->params[L.p_w].numel);
+        const double cflops = 2.0 * g.N * g.OH * g.OW * (double)g.Cout * g.KH * g.KW * g.Cin;
+        if (L.tc_kind) {
+          Prof pr(e, "conv2d_fwd_tf32_tcgen05", cbytes, cflops);
+          if (tc_conv_fwd(e, L, li)) break;
+        }
         Prof pr(e, "conv2d_fwd_f32", 4.0 * ((double)L.in.numel() + n_out + e->params[L.p_w].numel),
                 2.0 * g.N * g.OH * g.OW * (double)g.Cout * g.KH * g.KW * g.Cin);
         conv2d_fwd(in, P(e, L.p_w), out, g, e->ws, e->ws_floats, s);
@@ -556,14 +561,25 @@ static void run_backward(sb_engine* e) {
         break;
       case SB_LAYER_CONV2D: {
         const ConvGeom& g = L.cg;
-        if (L.tc_kind && tc_conv_bwd(e, L, li)) break;
         const double fl = 2.0 * g.N * g.OH * g.OW * (double)g.Cout * g.KH * g.KW * g.Cin;
-        {
-          Prof pr(e, "conv2d_wgrad_f32", 4.0 * ((double)L.in.numel() + n_out + e->params[L.p_w].numel), fl);
+        const double cb = 4.0 * ((double)L.in.numel() + n_out + e->params[L.p_w].numel);
+        bool wdone = false, ddone = false;
+        if (L.tc_kind) {
+          {
+            Prof pr(e, "conv2d_wgrad_tf32_tcgen05", cb, fl);
+            wdone = tc_conv_wgrad(e, L, li);
+          }
+          if (L.need_dx && din) {
+            Prof pr(e, "conv2d_dgrad_tf32_tcgen05", cb, fl);
+            ddone = tc_conv_dgrad(e, L, li);
+          }
+        }
+        if (!wdone) {
+          Prof pr(e, "conv2d_wgrad_f32", cb, fl);
           conv2d_wgrad(in, dout, G(e, L.p_w), g, e->ws, e->ws_floats, s);
         }
-        if (L.need_dx && din) {
-          Prof pr(e, "conv2d_dgrad_f32", 4.0 * ((double)L.in.numel() + n_out + e->params[L.p_w].numel), fl);
+        if (!ddone && L.need_dx && din) {
+          Prof pr(e, "conv2d_dgrad_f32", cb, fl);
           conv2d_dgrad(dout, P(e, L.p_w), din, g, e->ws, e->ws_floats, s);
         }
         break;

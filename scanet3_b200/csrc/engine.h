@@ -53,6 +53,7 @@ struct LayerPlan {
   float* bn_save_var = nullptr;
   // fusion / fast-path decisions
   bool fused_into_prev = false;   // this layer's forward+backward is executed by the previous op
+  bool skip_fwd = false;          // forward only is executed by the previous op's epilogue (ReLU after a tensor-core conv)
   int tc_kind = 0;                // 0 none, otherwise a tcgen05 kernel variant
   void* tc_plan = nullptr;        // opaque plan of the tensor-core path (TMA descriptors, buffers)
   void* lstm = nullptr;           // opaque LSTM workspace

@@ -1,12 +1,533 @@
-// placeholder until the tcgen05 kernels land (replaced below in this round)
+// tcgen05 / TMEM / TMA kernels of the scanet-b200 engine (sm_100a): the true dense contractions of the train step.
+//
+//  * conv_igemm_kernel  -- Conv2D fprop and dgrad (stride 1, VALID) as implicit GEMMs (math/nn/AllKernels.scala:143-261):
+//      an M-tile is BH full rows of one image's output grid (<= 128 pixels); for every filter tap the A operand is ONE
+//      4-D TMA box over the NHWC source shifted by the tap (out-of-bounds pixels are zero-filled by TMA, which is exactly
+//      the zero padding dgrad needs), the B operand is a slice of the HWIO filter; fp32 accumulators live in TMEM
+//      (double-buffered) and a 4-warp epilogue applies ReLU and stores NHWC rows.
+//  * conv_wgrad_kernel  -- Conv2DBackpropFilter: D[Cout, Cin] per tap, K = pixels; both operands MN-major straight out
+//      of NHWC memory; per-CTA partial sums are reduced in a fixed order (deterministic).
+// Arithmetic: kind::tf32 (operands are fp32 words, the low 13 mantissa bits are ignored), fp32 accumulation.
+#include <cuda.h>
+#include <stdio.h>
+
+#include <algorithm>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
 #include "engine.h"
 #include "tc.h"
+#include "tc_sm100.cuh"
+
 namespace sb {
-void tc_plan_layers(sb_engine*) {}
-void tc_free_layers(sb_engine*) {}
-void tc_params_changed(sb_engine*) {}
+
+using namespace tc;
+
+// =====================================================================================================================
+// TMA descriptors
+// =====================================================================================================================
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    SB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    if (!p || qres != cudaDriverEntryPointSuccess) throw std::runtime_error("cuTensorMapEncodeTiled is not available");
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+// fp32 tensor, dims innermost first, 128-byte swizzle, zero fill for out-of-bounds elements
+static CUtensorMap make_map(const float* base, int rank, const uint64_t* dims, const uint32_t* box, bool mn_major = false) {
+  CUtensorMap m;
+  cuuint64_t gdim[5], gstride[4];
+  cuuint32_t bdim[5], estr[5];
+  uint64_t stride = sizeof(float);
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    stride *= dims[i];
+    if (i < rank - 1) gstride[i] = stride;
+  }
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)base, gdim, gstride, bdim, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  return m;
+}
+
+// =====================================================================================================================
+// implicit-GEMM Conv2D fprop / dgrad
+// =====================================================================================================================
+struct IgemmParams {
+  int n_tiles, tiles_per_img;
+  int Hg, Wg, BH;     // output grid of the tile space; tile = BH grid rows (BH*Wg <= 128 pixels)
+  int KH, KW;
+  int kchunks;        // 32-channel K chunks per tap
+  int sign;           // +1 fprop: source pixel = (h+kh, w+kw) ; -1 dgrad: (h-kh, w-kw)
+  int N;              // accumulator columns (fprop: Cout, dgrad: Cin), multiple of 32
+  int b_mn_major;     // fprop 1: B = N/32 boxes [32 n x 32 k] ; dgrad 0: B = one box [32 k x N rows]
+  int b_rows_per_tap; // row offset between taps in the 2-D filter view
+  int stages;
+  int relu;
+  float thr;
+  float* out;         // [n_img*Hg*Wg, N]
+};
+
+constexpr int kIgemmThreads = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..5: epilogue
+constexpr int kATileBytes = 128 * 128;
+
+__global__ void __launch_bounds__(kIgemmThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const IgemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages x (A 16 KB | B N*128 B)] then barriers
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int b_tile_bytes = p.N * 128;
+  const int stage_bytes = kATileBytes + b_tile_bytes;
+  uint64_t* full_bar = (uint64_t*)(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tmem_full = empty_bar + p.stages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int a_box_bytes = p.BH * p.Wg * 128;
+  const int kblocks = p.KH * p.KW * p.kchunks;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < 2 * p.N) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int img = tile / p.tiles_per_img, h0 = (tile % p.tiles_per_img) * p.BH;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          const int tap = kb / p.kchunks, kc = kb % p.kchunks;
+          const int kh = tap / p.KW, kw = tap % p.KW;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          uint8_t* sb = sa + kATileBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(a_box_bytes + b_tile_bytes));
+          tma_load_4d(sa, &map_a, &full_bar[stage], kc * 32, p.sign * kw, h0 + p.sign * kh, img);
+          if (p.b_mn_major) {
+            for (int j = 0; j < p.N / 32; ++j)
+              tma_load_2d(sb + j * 4096, &map_b, &full_bar[stage], j * 32, tap * p.b_rows_per_tap + kc * 32);
+          } else {
+            tma_load_2d(sb, &map_b, &full_bar[stage], kc * 32, tap * p.b_rows_per_tap);
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (one thread) =================
+    if (lane == 0) {
+      const uint32_t idesc = idesc_tf32(128, p.N, 0, p.b_mn_major);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.N);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t sb = sa + kATileBytes;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {  // 4 x (K = 8 tf32) per 32-channel chunk
+            const uint64_t da = smem_desc_sw128(sa + ks * 32, 16, 1024);
+            const uint64_t db = p.b_mn_major ? smem_desc(sb + ks * 1024, 4096, 512, 1) : smem_desc_sw128(sb + ks * 32, 16, 1024);
+            umma_tf32(d_tmem, da, db, idesc, (kb | ks) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs have read it
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ================= epilogue: TMEM -> registers -> (ReLU) -> NHWC rows =================
+    const int sub = warp & 3;  // TMEM sub-partition this warp may read: lanes [32*sub, 32*sub+32)
+    const int row = sub * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      const int img = tile / p.tiles_per_img, h0 = (tile % p.tiles_per_img) * p.BH;
+      const int rows_valid = min(p.BH, p.Hg - h0) * p.Wg;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      float* orow = p.out + ((size_t)(img * p.Hg + h0) * p.Wg + row) * p.N;
+      for (int c0 = 0; c0 < p.N; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * p.N + c0), v);
+        tmem_ld_wait();
+        if (row < rows_valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (p.relu) {
+              o.x = fmaxf(p.thr, o.x); o.y = fmaxf(p.thr, o.y); o.z = fmaxf(p.thr, o.z); o.w = fmaxf(p.thr, o.w);
+            }
+            *reinterpret_cast<float4*>(orow + c0 + j) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// =====================================================================================================================
+// Conv2D wgrad:  dW[tap][ci][co] = sum_pixels X[n, oh+kh, ow+kw, ci] * dY[n, oh, ow, co]
+//   D_tap[M = co, N = ci] += A[M, K] . B_tap[K, N],  K = pixels.  A = dY rows (MN-major, M = Cout contiguous),
+//   B_tap = X rows shifted by the tap (MN-major, N = Cin contiguous).  K-chunk = BH grid rows x WK pixels (WK = OW rounded up
+//   to 8; the extra columns of dY are TMA zero fill, so they add nothing).  One CTA accumulates its chunks for ALL taps in
+//   TMEM (taps*Cin columns), then writes one partial filter gradient; partials are reduced in CTA order.
+// =====================================================================================================================
+struct WgradParams {
+  int n_chunks, chunks_per_img;
+  int BH, WK;
+  int KH, KW, Cin, Cout;
+  int stages;
+  float* partial;  // [gridDim.x][taps*Cin*Cout]
+};
+constexpr int kWgradThreads = 192;
+
+__global__ void __launch_bounds__(kWgradThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, const WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int taps = p.KH * p.KW;
+  const int krows = p.BH * p.WK;            // K rows per chunk (multiple of 8)
+  const int box_bytes = krows * 128;        // one 32-channel box
+  const int a_bytes = (p.Cout / 32) * box_bytes;
+  const int b_bytes = taps * (p.Cin / 32) * box_bytes;
+  const int stage_bytes = ((a_bytes + b_bytes + 1023) / 1024) * 1024;
+  uint64_t* full_bar = (uint64_t*)(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* done_bar = empty_bar + p.stages;
+  uint32_t* tmem_slot = (uint32_t*)(done_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ncols = taps * p.Cin;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < ncols) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_dy);
+    tma_prefetch_desc(&map_x);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const bool has_work = (int)blockIdx.x < p.n_chunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int ch = blockIdx.x; ch < p.n_chunks; ch += gridDim.x) {
+        const int img = ch / p.chunks_per_img, h0 = (ch % p.chunks_per_img) * p.BH;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + (size_t)stage * stage_bytes;
+        uint8_t* sb = sa + a_bytes;
+        mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(a_bytes + b_bytes));
+        for (int j = 0; j < p.Cout / 32; ++j) tma_load_4d(sa + j * box_bytes, &map_dy, &full_bar[stage], j * 32, 0, h0, img);
+        for (int t = 0; t < taps; ++t)
+          for (int j = 0; j < p.Cin / 32; ++j)
+            tma_load_4d(sb + (t * (p.Cin / 32) + j) * box_bytes, &map_x, &full_bar[stage], j * 32, t % p.KW, h0 + t / p.KW, img);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && has_work) {
+      const uint32_t idesc = idesc_tf32(p.Cout, p.Cin, 1, 1);  // M = Cout (64 or 128), N = Cin, both MN-major
+      int stage = 0;
+      uint32_t phase = 0;
+      bool first = true;
+      for (int ch = blockIdx.x; ch < p.n_chunks; ch += gridDim.x) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+        const uint32_t sb = sa + a_bytes;
+        for (int t = 0; t < taps; ++t) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)(t * p.Cin);
+          for (int ks = 0; ks < krows / 8; ++ks) {
+            // MN-major SW128: 8 K-rows per instruction (one swizzle atom deep), 32-element groups along M/N LBO apart
+            const uint64_t da = smem_desc(sa + ks * 1024, (uint32_t)box_bytes, 512, 1);
+            const uint64_t db = smem_desc(sb + t * (p.Cin / 32) * box_bytes + ks * 1024, (uint32_t)box_bytes, 512, 1);
+            umma_tf32(d_tmem, da, db, idesc, (first && ks == 0) ? 0u : 1u);
+          }
+        }
+        first = false;
+        umma_commit(&empty_bar[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(done_bar);
+    }
+  } else {
+    // epilogue: partial[cta][(t*Cin + ci)*Cout + co] = D_t[co][ci]
+    const int sub = warp & 3;
+    float* part = p.partial + (size_t)blockIdx.x * taps * p.Cin * p.Cout;
+    int co = -1;
+    if (p.Cout == 128) co = sub * 32 + lane;                  // M = 128: TMEM lane == row
+    else if (lane < 16) co = sub * 16 + lane;                 // M = 64: row m sits in lane (m % 16) + 32 * (m / 16)
+    if (has_work) {
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
+    }
+    for (int c0 = 0; c0 < ncols; c0 += 32) {
+      float v[32];
+      if (has_work) {
+        tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      if (co >= 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) part[(size_t)(c0 + j) * p.Cout + co] = v[j];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int n, int parts) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float acc = partial[i];
+  for (int c = 1; c < parts; ++c) acc = __fadd_rn(acc, partial[(size_t)c * n + i]);
+  out[i] = acc;
+}
+
+// =====================================================================================================================
+// per-layer plans
+// =====================================================================================================================
+struct ConvTcPlan {
+  CUtensorMap map_x_fwd, map_w_fwd;    // fprop: A = X boxes, B = filter (MN-major)
+  CUtensorMap map_dy_dg, map_w_dg;     // dgrad: A = dY boxes, B = filter (K-major)
+  CUtensorMap map_dy_wg, map_x_wg;     // wgrad
+  IgemmParams fwd{}, dg{};
+  WgradParams wg{};
+  int fwd_smem = 0, dg_smem = 0, wg_smem = 0;
+  int fwd_grid = 0, dg_grid = 0, wg_grid = 0;
+  float* wg_partial = nullptr;
+  bool relu_fused = false;
+  bool has_dgrad = false;
+};
+
+static bool conv_fits(const ConvGeom& g) {
+  // stride 1, VALID, channel counts that tile into 32-float (128 B) swizzle rows and legal UMMA shapes
+  if (g.SH != 1 || g.SW != 1 || g.PT != 0 || g.PL != 0) return false;
+  if (g.Cin % 32 || g.Cout % 32 || g.Cin > 256 || g.Cout > 256) return false;
+  if (g.OW > 128 || g.W > 128) return false;
+  if (g.Cout != 64 && g.Cout != 128) return false;          // wgrad: UMMA M = Cout
+  if (g.KH * g.KW * g.Cin > 512) return false;               // wgrad: taps*Cin TMEM columns
+  return true;
+}
+
+static int igemm_smem(const IgemmParams& p) { return p.stages * (kATileBytes + p.N * 128) + 16 * (2 * p.stages + 4) + 16 + 1024; }
+
+void tc_plan_layers(sb_engine* e) {
+  if (e->train.precision == SB_PREC_FP32) return;
+  if (e->train.precision == SB_PREC_3XTF32) return;  // TODO(round 2): split-operand 3xTF32; fp32 FFMA kernels serve it for now
+  int dev_smem = 0;
+  SB_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device));
+  for (size_t li = 0; li < e->L.size(); ++li) {
+    LayerPlan& L = e->L[li];
+    if (L.d.kind != SB_LAYER_CONV2D || !conv_fits(L.cg)) continue;
+    const ConvGeom& g = L.cg;
+    ConvTcPlan* P = new ConvTcPlan();
+    float* x = e->acts[L.buf_in];
+    float* y = e->acts[L.buf_out];
+    float* dy = e->dacts[L.buf_out];
+    float* dx = e->dacts[L.buf_in];
+    float* w = e->arena + e->params[L.p_w].offset;
+    const int taps = g.KH * g.KW;
+    // a following in-place ReLU is applied in the fprop epilogue
+    if (li + 1 < e->L.size() && e->L[li + 1].d.kind == SB_LAYER_ACTIVATE && e->L[li + 1].d.activation == SB_ACT_RELU &&
+        e->L[li + 1].inplace) {
+      P->relu_fused = true;
+    }
+    // ---- fprop: tile = BH rows of the OH x OW output grid ----
+    {
+      IgemmParams& p = P->fwd;
+      p.Hg = g.OH; p.Wg = g.OW; p.BH = std::max(1, std::min(128 / g.OW, g.OH));
+      p.tiles_per_img = (g.OH + p.BH - 1) / p.BH;
+      p.n_tiles = g.N * p.tiles_per_img;
+      p.KH = g.KH; p.KW = g.KW; p.kchunks = g.Cin / 32; p.sign = +1; p.N = g.Cout; p.b_mn_major = 1;
+      p.b_rows_per_tap = g.Cin;
+      p.relu = P->relu_fused ? 1 : 0;
+      p.thr = P->relu_fused ? e->L[li + 1].d.relu_threshold : 0.f;
+      p.out = y;
+      p.stages = std::max(2, std::min(8, (dev_smem - 2048) / (kATileBytes + p.N * 128)));
+      uint64_t xd[4] = {(uint64_t)g.Cin, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.N};
+      uint32_t xb[4] = {32, (uint32_t)p.Wg, (uint32_t)p.BH, 1};
+      P->map_x_fwd = make_map(x, 4, xd, xb);
+      uint64_t wd[2] = {(uint64_t)g.Cout, (uint64_t)taps * g.Cin};
+      uint32_t wb[2] = {32, 32};
+      P->map_w_fwd = make_map(w, 2, wd, wb, true);
+      P->fwd_smem = igemm_smem(p);
+      P->fwd_grid = std::min(p.n_tiles, kNumSMs);
+    }
+    // ---- dgrad: tile = BH rows of the H x W input grid; source dY shifted by -tap with zero fill ----
+    P->has_dgrad = L.need_dx && dx != nullptr;
+    if (P->has_dgrad) {
+      IgemmParams& p = P->dg;
+      p.Hg = g.H; p.Wg = g.W; p.BH = std::max(1, std::min(128 / g.W, g.H));
+      p.tiles_per_img = (g.H + p.BH - 1) / p.BH;
+      p.n_tiles = g.N * p.tiles_per_img;
+      p.KH = g.KH; p.KW = g.KW; p.kchunks = g.Cout / 32; p.sign = -1; p.N = g.Cin; p.b_mn_major = 0;
+      p.b_rows_per_tap = g.Cin;
+      p.relu = 0; p.thr = 0.f;
+      p.out = dx;
+      p.stages = std::max(2, std::min(8, (dev_smem - 2048) / (kATileBytes + p.N * 128)));
+      uint64_t yd[4] = {(uint64_t)g.Cout, (uint64_t)g.OW, (uint64_t)g.OH, (uint64_t)g.N};
+      uint32_t yb[4] = {32, (uint32_t)p.Wg, (uint32_t)p.BH, 1};
+      P->map_dy_dg = make_map(dy, 4, yd, yb);
+      uint64_t wd[2] = {(uint64_t)g.Cout, (uint64_t)taps * g.Cin};
+      uint32_t wb[2] = {32, (uint32_t)g.Cin};
+      P->map_w_dg = make_map(w, 2, wd, wb);
+      P->dg_smem = igemm_smem(p);
+      P->dg_grid = std::min(p.n_tiles, kNumSMs);
+    }
+    // ---- wgrad ----
+    {
+      WgradParams& p = P->wg;
+      p.KH = g.KH; p.KW = g.KW; p.Cin = g.Cin; p.Cout = g.Cout;
+      p.WK = (g.OW + 7) / 8 * 8;
+      const int box_row_bytes = p.WK * 128;  // one grid row of one 32-channel box
+      const int per_bh = (g.Cout / 32 + taps * (g.Cin / 32)) * box_row_bytes;
+      // deepest chunk that still leaves >= 2 pipeline stages
+      p.BH = std::max(1, std::min(g.OH, (dev_smem - 4096) / 2 / per_bh));
+      while (p.BH > 1 && 256 / p.WK < p.BH) --p.BH;  // TMA box dims <= 256
+      const int stage_bytes = ((p.BH * per_bh + 1023) / 1024) * 1024;
+      p.stages = std::max(1, std::min(4, (dev_smem - 4096) / stage_bytes));
+      p.chunks_per_img = (g.OH + p.BH - 1) / p.BH;
+      p.n_chunks = g.N * p.chunks_per_img;
+      P->wg_grid = std::min(p.n_chunks, kNumSMs);
+      P->wg_smem = p.stages * stage_bytes + 16 * (2 * p.stages + 2) + 16 + 1024;
+      SB_CUDA(cudaMalloc((void**)&P->wg_partial, (size_t)P->wg_grid * taps * g.Cin * g.Cout * sizeof(float)));
+      p.partial = P->wg_partial;
+      uint64_t yd[4] = {(uint64_t)g.Cout, (uint64_t)g.OW, (uint64_t)g.OH, (uint64_t)g.N};
+      uint32_t yb[4] = {32, (uint32_t)p.WK, (uint32_t)p.BH, 1};
+      P->map_dy_wg = make_map(dy, 4, yd, yb, true);
+      uint64_t xd[4] = {(uint64_t)g.Cin, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.N};
+      P->map_x_wg = make_map(x, 4, xd, yb, true);
+    }
+    if (P->fwd_smem > dev_smem || P->dg_smem > dev_smem || P->wg_smem > dev_smem) {
+      cudaFree(P->wg_partial);
+      delete P;
+      continue;
+    }
+    L.tc_kind = 1;
+    L.tc_plan = P;
+    if (P->relu_fused) e->L[li + 1].skip_fwd = true;  // forward only; the backward of ReLU still runs
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    SB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
+    SB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
+    attr_set = true;
+  }
+}
+
+void tc_free_layers(sb_engine* e) {
+  for (auto& L : e->L) {
+    if (L.tc_plan) {
+      ConvTcPlan* P = (ConvTcPlan*)L.tc_plan;
+      cudaFree(P->wg_partial);
+      delete P;
+      L.tc_plan = nullptr;
+    }
+  }
+}
+
+void tc_params_changed(sb_engine*) {}  // the kernels read the filter straight from the arena
+
 bool tc_dense_fwd(sb_engine*, LayerPlan&, int) { return false; }
 bool tc_dense_bwd(sb_engine*, LayerPlan&, int) { return false; }
-bool tc_conv_fwd(sb_engine*, LayerPlan&, int) { return false; }
-bool tc_conv_bwd(sb_engine*, LayerPlan&, int) { return false; }
+
+bool tc_conv_fwd(sb_engine* e, LayerPlan& L, int) {
+  ConvTcPlan* P = (ConvTcPlan*)L.tc_plan;
+  if (!P) return false;
+  conv_igemm_kernel<<<P->fwd_grid, kIgemmThreads, P->fwd_smem, e->stream>>>(P->map_x_fwd, P->map_w_fwd, P->fwd);
+  SB_LAUNCHED();
+  return true;
 }
+
+bool tc_conv_wgrad(sb_engine* e, LayerPlan& L, int) {
+  ConvTcPlan* P = (ConvTcPlan*)L.tc_plan;
+  if (!P) return false;
+  const ConvGeom& g = L.cg;
+  const int n = g.KH * g.KW * g.Cin * g.Cout;
+  conv_wgrad_kernel<<<P->wg_grid, kWgradThreads, P->wg_smem, e->stream>>>(P->map_dy_wg, P->map_x_wg, P->wg);
+  SB_LAUNCHED();
+  wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(P->wg_partial, e->grads + e->params[L.p_w].offset, n, P->wg_grid);
+  SB_LAUNCHED();
+  return true;
+}
+
+bool tc_conv_dgrad(sb_engine* e, LayerPlan& L, int) {
+  ConvTcPlan* P = (ConvTcPlan*)L.tc_plan;
+  if (!P || !P->has_dgrad) return false;
+  conv_igemm_kernel<<<P->dg_grid, kIgemmThreads, P->dg_smem, e->stream>>>(P->map_dy_dg, P->map_w_dg, P->dg);
+  SB_LAUNCHED();
+  return true;
+}
+
+}  // namespace sb

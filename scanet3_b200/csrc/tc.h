@@ -12,7 +12,8 @@ void tc_params_changed(sb_engine* e);
 bool tc_dense_fwd(sb_engine* e, LayerPlan& L, int li);
 bool tc_dense_bwd(sb_engine* e, LayerPlan& L, int li);
 bool tc_conv_fwd(sb_engine* e, LayerPlan& L, int li);
-bool tc_conv_bwd(sb_engine* e, LayerPlan& L, int li);
+bool tc_conv_wgrad(sb_engine* e, LayerPlan& L, int li);
+bool tc_conv_dgrad(sb_engine* e, LayerPlan& L, int li);
 
 void lstm_plan(sb_engine* e);
 void lstm_forward(sb_engine* e, LayerPlan& L, int li);
