@@ -4,6 +4,7 @@
 #include "engine.h"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -332,6 +333,61 @@ static float* dmalloc_floats(int64_t n) {
   return (float*)p;
 }
 
+// Decide which layers run on the vectorised / fused kernels of kernels_fast.cu.  Runs after tc_plan_layers, which owns
+// the contractions that fit tcgen05 (and already folded the ReLU that follows them into its epilogue).
+static void plan_fusions(sb_engine* e) {
+  const char* off = getenv("SB_DISABLE_FAST");
+  e->fast = !(off && off[0] == '1');
+  const int nl = (int)e->L.size();
+  auto inplace_relu = [&](int li) {
+    return li >= 0 && li < nl && e->L[li].d.kind == SB_LAYER_ACTIVATE && e->L[li].d.activation == SB_ACT_RELU && e->L[li].inplace;
+  };
+  // the classifier head  Dense >> Bias >> Softmax  under CategoricalCrossentropy (every BASELINE classifier ends so)
+  const LayerPlan& last = e->L[nl - 1];
+  if (e->train.loss == SB_LOSS_CCE && last.d.kind == SB_LAYER_ACTIVATE && last.d.activation == SB_ACT_SOFTMAX && last.inplace &&
+      last.out.rank == 2) {
+    e->softmax_cce_fused = true;
+    if (e->fast && nl >= 2 && e->L[nl - 2].d.kind == SB_LAYER_BIAS && e->L[nl - 2].inplace && last.out.d[1] <= 32) {
+      e->head_fused = true;
+      e->L[nl - 2].head_skip = true;
+    }
+    e->L[nl - 1].head_skip = true;
+  }
+  if (!e->fast) return;
+  for (int li = 0; li < nl; ++li) {
+    LayerPlan& L = e->L[li];
+    switch (L.d.kind) {
+      case SB_LAYER_CONV2D: {
+        const ConvGeom& g = L.cg;
+        if (!L.tc_kind && g.KH * g.KW * g.Cin <= 32 && g.Cout % 4 == 0 && g.Cout <= 256) {
+          L.fast_smallk = true;
+          if (inplace_relu(li + 1) && !e->L[li + 1].skip_fwd) {
+            L.fuse_relu_fwd = true;
+            L.fused_thr = e->L[li + 1].d.relu_threshold;
+            e->L[li + 1].skip_fwd = true;
+          }
+        }
+        break;
+      }
+      case SB_LAYER_POOL2D: {
+        L.fast_pool = L.pg.C % 4 == 0;
+        // dx = [x > thr] * maxpool_grad: the mask of the in-place ReLU that produced this layer's input
+        if (L.need_dx && inplace_relu(li - 1) && e->L[li - 1].buf_out == L.buf_in) {
+          L.pool_relu_bwd = true;
+          L.fused_thr = e->L[li - 1].d.relu_threshold;
+          e->L[li - 1].skip_bwd = true;
+        }
+        break;
+      }
+      case SB_LAYER_DENSE:
+        L.fast_skinny = L.out.d[1] <= 16 && L.in.d[1] >= 2048 && L.in.d[0] * L.out.d[1] * 4 <= 40000;
+        break;
+      default:
+        break;
+    }
+  }
+}
+
 static void allocate(sb_engine* e) {
   SB_CUDA(cudaSetDevice(e->device));
   SB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
@@ -364,6 +420,7 @@ static void allocate(sb_engine* e) {
     }
   }
   tc_plan_layers(e);  // tensor-core fast paths (TMA descriptors, padded-grid buffers)
+  plan_fusions(e);    // vectorised / fused bandwidth kernels
   SB_CUDA(cudaStreamSynchronize(e->stream));
 }
 
@@ -430,7 +487,7 @@ static void run_forward(sb_engine* e, int mode) {
   for (int li = 0; li < nl; ++li) {
     LayerPlan& L = e->L[li];
     if (L.fused_into_prev || L.skip_fwd) continue;
-    if (e->softmax_cce_fused && li == nl - 1 && mode != FWD_INFER) continue;  // executed by the loss kernel
+    if (L.head_skip && mode != FWD_INFER) continue;  // executed by the loss kernel
     float* in = e->acts[L.buf_in];
     float* out = e->acts[L.buf_out];
     const int64_t n_out = L.out.numel();
@@ -438,7 +495,12 @@ static void run_forward(sb_engine* e, int mode) {
       case SB_LAYER_DENSE: {
         const int M = (int)L.in.d[0], K = (int)L.in.d[1], N = (int)L.out.d[1];
         if (L.tc_kind && tc_dense_fwd(e, L, li)) break;
-        Prof pr(e, "dense_fwd_f32", 4.0 * ((double)M * K + (double)K * N + (double)M * N), 2.0 * M * N * K);
+        const double db = 4.0 * ((double)M * K + (double)K * N + (double)M * N);
+        if (L.fast_skinny) {
+          Prof pr(e, "dense_skinny_fwd", db, 2.0 * M * N * K);
+          if (dense_skinny_fwd(in, P(e, L.p_w), out, M, N, K, e->ws, e->ws_floats, s)) break;
+        }
+        Prof pr(e, "dense_fwd_f32", db, 2.0 * M * N * K);
         gemm_nn(in, P(e, L.p_w), out, M, N, K, e->ws, e->ws_floats, s);
         break;
       }
@@ -465,14 +527,20 @@ static void run_forward(sb_engine* e, int mode) {
           Prof pr(e, "conv2d_fwd_tf32_tcgen05", cbytes, cflops);
           if (tc_conv_fwd(e, L, li)) break;
         }
-        Prof pr(e, "conv2d_fwd_f32", 4.0 * ((double)L.in.numel() + n_out + e->params[L.p_w].numel),
-                2.0 * g.N * g.OH * g.OW * (double)g.Cout * g.KH * g.KW * g.Cin);
+        if (L.fast_smallk) {
+          Prof pr(e, "conv2d_smallk_fwd", cbytes, cflops);
+          conv_smallk_fwd(in, P(e, L.p_w), out, g, L.fuse_relu_fwd, L.fused_thr, s);
+          break;
+        }
+        Prof pr(e, "conv2d_fwd_f32", cbytes, cflops);
         conv2d_fwd(in, P(e, L.p_w), out, g, e->ws, e->ws_floats, s);
         break;
       }
       case SB_LAYER_POOL2D: {
         Prof pr(e, "pool_fwd", 4.0 * ((double)L.in.numel() + n_out), 0);
-        pool_fwd(in, out, L.pg, SB_POOL_MAX, s);  // the layer ignores `reduce` (layer/Pool2D.scala:36-42)
+        // the layer ignores `reduce` (layer/Pool2D.scala:36-42): always max
+        if (L.fast_pool) pool_max_fwd_v4(in, out, L.pg, s);
+        else pool_fwd(in, out, L.pg, SB_POOL_MAX, s);
         break;
       }
       case SB_LAYER_BATCHNORM: {
@@ -503,7 +571,12 @@ static void run_loss(sb_engine* e, bool with_grad) {
   float* dpred = with_grad ? e->dacts[last.buf_out] : nullptr;
   const long long rows = e->label_shape.d[0];
   const long long cols = e->label_shape.numel() / rows;
-  if (e->softmax_cce_fused) {
+  if (e->head_fused) {
+    const LayerPlan& bias = e->L[e->L.size() - 2];
+    Prof pr(e, "head_bias_softmax_cce", 4.0 * 4.0 * (double)rows * cols, 0);
+    head_bias_softmax_cce(pred, P(e, bias.p_w), e->by, dpred, with_grad ? G(e, bias.p_w) : nullptr, e->st, (int)rows, (int)cols,
+                          e->stream);
+  } else if (e->softmax_cce_fused) {
     Prof pr(e, "softmax_cce_fused", 4.0 * 4.0 * (double)rows * cols, 0);
     softmax_cce_fwd_bwd(pred, e->by, dpred, e->st, (int)rows, (int)cols, e->stream);
   } else {
@@ -517,8 +590,7 @@ static void run_backward(sb_engine* e) {
   const int nl = (int)e->L.size();
   for (int li = nl - 1; li >= 0; --li) {
     LayerPlan& L = e->L[li];
-    if (L.fused_into_prev) continue;
-    if (e->softmax_cce_fused && li == nl - 1) continue;
+    if (L.fused_into_prev || L.head_skip || L.skip_bwd) continue;
     float* in = e->acts[L.buf_in];
     float* out = e->acts[L.buf_out];
     float* dout = e->dacts[L.buf_out];
@@ -528,12 +600,24 @@ static void run_backward(sb_engine* e) {
       case SB_LAYER_DENSE: {
         const int M = (int)L.in.d[0], K = (int)L.in.d[1], N = (int)L.out.d[1];
         if (L.tc_kind && tc_dense_bwd(e, L, li)) break;
-        {
-          Prof pr(e, "dense_wgrad_f32", 4.0 * ((double)M * K + (double)K * N + (double)M * N), 2.0 * M * N * K);
+        const double db = 4.0 * ((double)M * K + (double)K * N + (double)M * N);
+        bool wdone = false, ddone = false;
+        if (L.fast_skinny) {
+          {
+            Prof pr(e, "dense_skinny_wgrad", db, 2.0 * M * N * K);
+            wdone = dense_skinny_wgrad(in, dout, G(e, L.p_w), M, N, K, s);
+          }
+          if (L.need_dx && din) {
+            Prof pr(e, "dense_skinny_dgrad", db, 2.0 * M * N * K);
+            ddone = dense_skinny_dgrad(dout, P(e, L.p_w), din, M, N, K, s);
+          }
+        }
+        if (!wdone) {
+          Prof pr(e, "dense_wgrad_f32", db, 2.0 * M * N * K);
           gemm_tn(in, dout, G(e, L.p_w), K, N, M, e->ws, e->ws_floats, s);  // dW = X^T . G
         }
-        if (L.need_dx && din) {
-          Prof pr(e, "dense_dgrad_f32", 4.0 * ((double)M * K + (double)K * N + (double)M * N), 2.0 * M * N * K);
+        if (!ddone && L.need_dx && din) {
+          Prof pr(e, "dense_dgrad_f32", db, 2.0 * M * N * K);
           gemm_nt(dout, P(e, L.p_w), din, M, K, N, e->ws, e->ws_floats, s);  // dX = G . W^T
         }
         break;
@@ -574,6 +658,10 @@ static void run_backward(sb_engine* e) {
             ddone = tc_conv_dgrad(e, L, li);
           }
         }
+        if (!wdone && L.fast_smallk) {
+          Prof pr(e, "conv2d_smallk_wgrad", cb, fl);
+          wdone = conv_smallk_wgrad(in, dout, G(e, L.p_w), g, e->ws, e->ws_floats, s);
+        }
         if (!wdone) {
           Prof pr(e, "conv2d_wgrad_f32", cb, fl);
           conv2d_wgrad(in, dout, G(e, L.p_w), g, e->ws, e->ws_floats, s);
@@ -586,8 +674,10 @@ static void run_backward(sb_engine* e) {
       }
       case SB_LAYER_POOL2D: {
         if (!L.need_dx || !din) break;
-        Prof pr(e, "pool_bwd", 4.0 * (2.0 * L.in.numel() + 2.0 * n_out), 0);
-        pool_bwd(in, dout, din, L.pg, SB_POOL_MAX, s);
+        Prof pr(e, L.pool_relu_bwd ? "pool_relu_bwd" : "pool_bwd", 4.0 * (2.0 * L.in.numel() + 2.0 * n_out), 0);
+        if (L.fast_pool) pool_max_bwd_v4(in, dout, din, L.pg, L.pool_relu_bwd, L.fused_thr, s);
+        else if (L.pool_relu_bwd) pool_bwd_relu(in, dout, din, L.pg, L.fused_thr, s);
+        else pool_bwd(in, dout, din, L.pg, SB_POOL_MAX, s);
         break;
       }
       case SB_LAYER_BATCHNORM: {

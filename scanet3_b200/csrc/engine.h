@@ -54,6 +54,14 @@ struct LayerPlan {
   // fusion / fast-path decisions
   bool fused_into_prev = false;   // this layer's forward+backward is executed by the previous op
   bool skip_fwd = false;          // forward only is executed by the previous op's epilogue (ReLU after a tensor-core conv)
+  bool skip_bwd = false;          // backward is folded into a neighbour (ReLU into the max-pool backward, head layers)
+  bool fuse_relu_fwd = false;     // small-K conv: apply the following in-place ReLU in the store
+  bool pool_relu_bwd = false;     // max-pool backward also applies the mask of the in-place ReLU that produced its input
+  float fused_thr = 0.f;
+  bool head_skip = false;         // Bias / Softmax of the fused classifier head: executed by the head kernel when training
+  bool fast_smallk = false;       // Conv2D with KH*KW*Cin <= 32: register-tiled direct kernel instead of the implicit GEMM
+  bool fast_pool = false;         // 128-bit max-pool kernels (C % 4 == 0)
+  bool fast_skinny = false;       // Dense with <= 16 outputs and a long reduction: split-K skinny kernels
   int tc_kind = 0;                // 0 none, otherwise a tcgen05 kernel variant
   void* tc_plan = nullptr;        // opaque plan of the tensor-core path (TMA descriptors, buffers)
   void* lstm = nullptr;           // opaque LSTM workspace
@@ -109,6 +117,8 @@ struct sb_engine {
   long long host_iter_mirror = -1;  // device st->iter as far as the host knows (-1 unknown)
   bool params_ready = false, opt_ready = false;
   bool softmax_cce_fused = false;
+  bool head_fused = false;   // last layers Dense >> Bias >> Softmax with CCE: one fused bias+softmax+loss+dz+dbias kernel
+  bool fast = true;          // vectorised / fused bandwidth kernels (SB_DISABLE_FAST=1 turns them off for debugging)
 
   bool profiling = false;
   std::vector<sb::ProfEntry> prof;

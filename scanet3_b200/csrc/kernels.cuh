@@ -89,3 +89,16 @@ void philox_fill(float* p, long long n, unsigned long long seed, int normal, flo
 
 
 }  // namespace sb
+
+namespace sb {
+// ---- kernels_fast.cu: vectorised / fused variants (return false when the shape is not covered) ----
+void pool_max_fwd_v4(const float* x, float* y, const PoolGeom& g, cudaStream_t s);
+void pool_max_bwd_v4(const float* x, const float* dy, float* dx, const PoolGeom& g, int relu, float thr, cudaStream_t s);
+void conv_smallk_fwd(const float* x, const float* w, float* y, const ConvGeom& g, int relu, float thr, cudaStream_t s);
+bool conv_smallk_wgrad(const float* x, const float* dy, float* dw, const ConvGeom& g, float* ws, size_t ws_floats, cudaStream_t s);
+bool dense_skinny_fwd(const float* x, const float* w, float* z, int M, int N, int K, float* ws, size_t ws_floats, cudaStream_t s);
+bool dense_skinny_wgrad(const float* x, const float* g, float* dw, int M, int N, int K, cudaStream_t s);
+bool dense_skinny_dgrad(const float* g, const float* w, float* dx, int M, int N, int K, cudaStream_t s);
+bool head_bias_softmax_cce(float* z, const float* bias, const float* y, float* dz, float* dbias, StepState* st, int rows, int C,
+                           cudaStream_t s);
+}  // namespace sb
