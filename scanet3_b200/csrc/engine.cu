@@ -380,7 +380,7 @@ static void plan_fusions(sb_engine* e) {
         break;
       }
       case SB_LAYER_DENSE:
-        L.fast_skinny = L.out.d[1] <= 16 && L.in.d[1] >= 2048 && L.in.d[0] * L.out.d[1] * 4 <= 40000;
+        L.fast_skinny = L.out.d[1] <= 16 && L.in.d[1] >= 2048 && L.in.d[1] % 4 == 0 && L.in.d[0] <= 128;
         break;
       default:
         break;
@@ -412,6 +412,8 @@ static void allocate(sb_engine* e) {
   memset(e->st_host, 0, sizeof(StepState) * 4);
   e->ws_floats = (size_t)16 << 20;  // 64 MB: split-K partials, column-reduction partials
   e->ws = dmalloc_floats((int64_t)e->ws_floats);
+  e->head_scratch = dmalloc_floats((int64_t)kHeadScratchFloats);
+  SB_CUDA(cudaMemsetAsync(e->head_scratch, 0, kHeadScratchFloats * 4, e->stream));
   for (auto& L : e->L) {
     if (L.d.kind == SB_LAYER_BATCHNORM) {
       int64_t C = L.in.d[L.in.rank - 1];
@@ -497,8 +499,14 @@ static void run_forward(sb_engine* e, int mode) {
         if (L.tc_kind && tc_dense_fwd(e, L, li)) break;
         const double db = 4.0 * ((double)M * K + (double)K * N + (double)M * N);
         if (L.fast_skinny) {
-          Prof pr(e, "dense_skinny_fwd", db, 2.0 * M * N * K);
-          if (dense_skinny_fwd(in, P(e, L.p_w), out, M, N, K, e->ws, e->ws_floats, s)) break;
+          Prof pr(e, "dense_head_fwd", db, 2.0 * M * N * K);
+          e->head_chunks = 0;
+          if (e->head_fused && li == nl - 3 && mode != FWD_INFER) {
+            // split-K partials stay in the workspace: the head kernel (next launch) sums them in chunk order
+            if (dense_head_fwd(in, P(e, L.p_w), e->ws, &e->head_chunks, M, N, K, e->ws_floats, s)) break;
+          } else if (dense_skinny_fwd(in, P(e, L.p_w), out, M, N, K, e->ws, e->ws_floats, s)) {
+            break;
+          }
         }
         Prof pr(e, "dense_fwd_f32", db, 2.0 * M * N * K);
         gemm_nn(in, P(e, L.p_w), out, M, N, K, e->ws, e->ws_floats, s);
@@ -574,8 +582,8 @@ static void run_loss(sb_engine* e, bool with_grad) {
   if (e->head_fused) {
     const LayerPlan& bias = e->L[e->L.size() - 2];
     Prof pr(e, "head_bias_softmax_cce", 4.0 * 4.0 * (double)rows * cols, 0);
-    head_bias_softmax_cce(pred, P(e, bias.p_w), e->by, dpred, with_grad ? G(e, bias.p_w) : nullptr, e->st, (int)rows, (int)cols,
-                          e->stream);
+    head_bias_softmax_cce(pred, e->head_chunks > 0 ? e->ws : nullptr, e->head_chunks, P(e, bias.p_w), e->by, dpred,
+                          with_grad ? G(e, bias.p_w) : nullptr, e->st, (int)rows, (int)cols, e->head_scratch, e->stream);
   } else if (e->softmax_cce_fused) {
     Prof pr(e, "softmax_cce_fused", 4.0 * 4.0 * (double)rows * cols, 0);
     softmax_cce_fwd_bwd(pred, e->by, dpred, e->st, (int)rows, (int)cols, e->stream);
@@ -603,14 +611,9 @@ static void run_backward(sb_engine* e) {
         const double db = 4.0 * ((double)M * K + (double)K * N + (double)M * N);
         bool wdone = false, ddone = false;
         if (L.fast_skinny) {
-          {
-            Prof pr(e, "dense_skinny_wgrad", db, 2.0 * M * N * K);
-            wdone = dense_skinny_wgrad(in, dout, G(e, L.p_w), M, N, K, s);
-          }
-          if (L.need_dx && din) {
-            Prof pr(e, "dense_skinny_dgrad", db, 2.0 * M * N * K);
-            ddone = dense_skinny_dgrad(dout, P(e, L.p_w), din, M, N, K, s);
-          }
+          const bool dg = L.need_dx && din;
+          Prof pr(e, "dense_head_bwd", db + (dg ? 4.0 * M * K : 0.0), (dg ? 4.0 : 2.0) * M * N * K);
+          wdone = ddone = dense_head_bwd(in, dout, P(e, L.p_w), G(e, L.p_w), dg ? din : nullptr, M, N, K, s);
         }
         if (!wdone) {
           Prof pr(e, "dense_wgrad_f32", db, 2.0 * M * N * K);
@@ -927,7 +930,7 @@ extern "C" void sb_engine_destroy(sb_engine* e) {
     for (float* p : e->acts) cudaFree(p);
     for (float* p : e->dacts) cudaFree(p);
     cudaFree(e->arena); cudaFree(e->grads); cudaFree(e->by); cudaFree(e->ds_x); cudaFree(e->ds_y);
-    cudaFree(e->st); cudaFree(e->ws);
+    cudaFree(e->st); cudaFree(e->ws); cudaFree(e->head_scratch);
     if (e->st_host) cudaFreeHost(e->st_host);
     if (e->stream) cudaStreamDestroy(e->stream);
   }
@@ -1051,6 +1054,9 @@ extern "C" int sb_train_steps_async(sb_engine* e, int64_t global_iter, int64_t f
     SB_FAIL(SB_ERR_INVALID_ARG, "batch range exceeds the shard (" + std::to_string(n_batches) + " full batches)");
   DeviceGuard dg(e->device);
   set_device_iter(e, global_iter, first_batch);
+  // profiling: hold the device back while the host enqueues the event-bracketed launches (~3 API calls per kernel), so
+  // the events time kernels back to back instead of launch gaps
+  if (e->profiling) device_delay(std::min<long long>(400000000LL, 2000000LL + n_steps * 600000LL), e->stream);
   for (int64_t j = 0; j < n_steps; ++j) launch_train_step(e, true);
   e->host_iter_mirror = global_iter + n_steps;
   SB_API_END

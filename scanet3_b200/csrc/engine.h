@@ -109,6 +109,7 @@ struct sb_engine {
   sb::StepState* st = nullptr;
   sb::StepState* st_host = nullptr;  // pinned mirror
   float* ws = nullptr;
+  float* head_scratch = nullptr;  // per-CTA partials + completion ticket of the fused classifier-head kernel
   size_t ws_floats = 0;
   cudaStream_t stream = nullptr;
   cudaGraphExec_t g_resident = nullptr, g_hostfed = nullptr, g_loss = nullptr;
@@ -118,6 +119,7 @@ struct sb_engine {
   bool params_ready = false, opt_ready = false;
   bool softmax_cce_fused = false;
   bool head_fused = false;   // last layers Dense >> Bias >> Softmax with CCE: one fused bias+softmax+loss+dz+dbias kernel
+  int head_chunks = 0;       // split-K partials of the head's Dense waiting in `ws` for the head kernel (0: none)
   bool fast = true;          // vectorised / fused bandwidth kernels (SB_DISABLE_FAST=1 turns them off for debugging)
 
   bool profiling = false;

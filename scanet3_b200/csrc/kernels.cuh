@@ -82,6 +82,7 @@ void optimizer_step(const OptDesc& o, float* w, const float* g, float* s0, float
 
 // ---- init / utility ----
 void fill_const(float* p, float v, long long n, cudaStream_t s);
+void device_delay(long long ns, cudaStream_t s);  // profiling aid (not counted as a launch)
 void scale_inplace(float* p, float w, long long n, cudaStream_t s);
 // TF RandomUniform / RandomStandardNormal (Philox-4x32-10), out = sample*scale + shift
 void philox_fill(float* p, long long n, unsigned long long seed, int normal, float scale, int has_scale, float shift,
@@ -97,8 +98,16 @@ void pool_max_bwd_v4(const float* x, const float* dy, float* dx, const PoolGeom&
 void conv_smallk_fwd(const float* x, const float* w, float* y, const ConvGeom& g, int relu, float thr, cudaStream_t s);
 bool conv_smallk_wgrad(const float* x, const float* dy, float* dw, const ConvGeom& g, float* ws, size_t ws_floats, cudaStream_t s);
 bool dense_skinny_fwd(const float* x, const float* w, float* z, int M, int N, int K, float* ws, size_t ws_floats, cudaStream_t s);
-bool dense_skinny_wgrad(const float* x, const float* g, float* dw, int M, int N, int K, cudaStream_t s);
-bool dense_skinny_dgrad(const float* g, const float* w, float* dx, int M, int N, int K, cudaStream_t s);
-bool head_bias_softmax_cce(float* z, const float* bias, const float* y, float* dz, float* dbias, StepState* st, int rows, int C,
-                           cudaStream_t s);
+// split-K partials only (partial[chunks][M][N]); the consumer (head kernel or partial_reduce) sums them in chunk order
+bool dense_head_fwd(const float* x, const float* w, float* partial, int* chunks_out, int M, int N, int K, size_t ws_floats,
+                    cudaStream_t s);
+// wgrad and (dx != null) dgrad in one pass
+bool dense_head_bwd(const float* x, const float* g, const float* w, float* dw, float* dx, int M, int N, int K, cudaStream_t s);
+// z (or the sum of `chunks` split-K partials when partial != null) + bias -> softmax -> CCE loss, dz, dbias
+// scratch: kHeadScratchFloats floats, zero-initialised once (per-CTA partials + the completion ticket)
+constexpr size_t kHeadScratchFloats = 1024 * 40 + 32;
+bool head_bias_softmax_cce(float* z, const float* partial, int chunks, const float* bias, const float* y, float* dz, float* dbias,
+                           StepState* st, int rows, int C, float* scratch, cudaStream_t s);
+// out[i] = sum_c partial[c*n + i], fixed order
+void partial_reduce(const float* partial, float* out, int n, int parts, cudaStream_t s);
 }  // namespace sb

@@ -5,6 +5,7 @@
 // All reductions use fixed orders (no atomics), so results are run-to-run deterministic.
 #include "common.cuh"
 #include "kernels.cuh"
+#include "tc_sm100.cuh"
 
 namespace sb {
 
@@ -43,7 +44,46 @@ __global__ void __launch_bounds__(256) pool_max_fwd_v4_kernel(const float* __res
     st4(y + i * 4, m);
   }
 }
+
+// ---- 2x2 window, stride 1, VALID (the layer default, layer/Pool2D.scala:29-31): strip kernels ----
+// A thread owns (image, output row, channel quad) and walks a segment of the row keeping the previous column's vertical
+// maximum in registers: 2 loads per output instead of 4.
+constexpr int kPoolSegs = 4;
+__global__ void __launch_bounds__(256) pool22_fwd_strip_kernel(const float* __restrict__ x, float* __restrict__ y, PoolGeom g,
+                                                               int seg_len, long long n_threads) {
+  const int C4 = g.C >> 2;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_threads) return;
+  const int c4 = (int)(i % C4);
+  long long t = i / C4;
+  const int seg = (int)(t % kPoolSegs); t /= kPoolSegs;
+  const int oh = (int)(t % g.OH);
+  const int b = (int)(t / g.OH);
+  const int w0 = seg * seg_len;
+  const int w1 = min(w0 + seg_len, g.OW);
+  if (w0 >= w1) return;
+  const float* r0 = x + (((long long)b * g.H + oh) * g.W) * g.C + c4 * 4;
+  const float* r1 = r0 + (long long)g.W * g.C;
+  float* yo = y + (((long long)b * g.OH + oh) * g.OW) * g.C + c4 * 4;
+  float4 prev = max4(ld4(r0 + (long long)w0 * g.C), ld4(r1 + (long long)w0 * g.C));
+#pragma unroll 4
+  for (int w = w0; w < w1; ++w) {
+    const float4 next = max4(ld4(r0 + (long long)(w + 1) * g.C), ld4(r1 + (long long)(w + 1) * g.C));
+    st4(yo + (long long)w * g.C, max4(prev, next));
+    prev = next;
+  }
+}
+static bool pool_is_22s1(const PoolGeom& g) {
+  return g.KH == 2 && g.KW == 2 && g.SH == 1 && g.SW == 1 && g.PT == 0 && g.PL == 0 && g.OH == g.H - 1 && g.OW == g.W - 1;
+}
 void pool_max_fwd_v4(const float* x, float* y, const PoolGeom& g, cudaStream_t s) {
+  if (pool_is_22s1(g)) {
+    const long long nt = (long long)g.N * g.OH * kPoolSegs * (g.C / 4);
+    const int seg_len = (g.OW + kPoolSegs - 1) / kPoolSegs;
+    pool22_fwd_strip_kernel<<<(int)((nt + 255) / 256), 256, 0, s>>>(x, y, g, seg_len, nt);
+    SB_LAUNCHED();
+    return;
+  }
   const long long n4 = (long long)g.N * g.OH * g.OW * (g.C / 4);
   pool_max_fwd_v4_kernel<<<grid_for(n4, 256), 256, 0, s>>>(x, y, g, n4);
   SB_LAUNCHED();
@@ -103,7 +143,109 @@ __global__ void __launch_bounds__(256) pool_max_bwd_v4_kernel(const float* __res
     st4(dx + i * 4, acc);
   }
 }
+
+// first maximum of a 2x2 window in row-major order (strict > keeps the earlier element): 0..3
+__device__ __forceinline__ int argmax22(float p0, float p1, float p2, float p3) {
+  int k = 0;
+  float best = p0;
+  if (p1 > best) { best = p1; k = 1; }
+  if (p2 > best) { best = p2; k = 2; }
+  if (p3 > best) { k = 3; }
+  return k;
+}
+struct Idx4 { int x, y, z, w; };
+__device__ __forceinline__ Idx4 argmax22_4(float4 p0, float4 p1, float4 p2, float4 p3) {
+  Idx4 r;
+  r.x = argmax22(p0.x, p1.x, p2.x, p3.x); r.y = argmax22(p0.y, p1.y, p2.y, p3.y);
+  r.z = argmax22(p0.z, p1.z, p2.z, p3.z); r.w = argmax22(p0.w, p1.w, p2.w, p3.w);
+  return r;
+}
+__device__ __forceinline__ void acc_if(float4& acc, const Idx4& k, int pos, const float4& gy) {
+  if (k.x == pos) acc.x = __fadd_rn(acc.x, gy.x);
+  if (k.y == pos) acc.y = __fadd_rn(acc.y, gy.y);
+  if (k.z == pos) acc.z = __fadd_rn(acc.z, gy.z);
+  if (k.w == pos) acc.w = __fadd_rn(acc.w, gy.w);
+}
+// Backward strip: a thread owns (image, INPUT row h, channel quad) and walks a segment of the row.  Column w of the walk
+// evaluates the two windows whose top-left corner is in column w (rows h-1 and h) once -- 3 x loads + 2 dy loads -- and
+// keeps them for column w+1, where the element is their right-hand member.  Summation order per element: windows
+// (h-1,w-1), (h-1,w), (h,w-1), (h,w) -- the same as the generic gather kernel.
+template <bool RELU>
+__global__ void __launch_bounds__(256) pool22_bwd_strip_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                               float* __restrict__ dx, PoolGeom g, float thr, int seg_len,
+                                                               long long n_threads) {
+  const int C4 = g.C >> 2;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_threads) return;
+  const int c4 = (int)(i % C4);
+  long long t = i / C4;
+  const int seg = (int)(t % kPoolSegs); t /= kPoolSegs;
+  const int h = (int)(t % g.H);
+  const int b = (int)(t / g.H);
+  const int w0 = seg * seg_len;
+  const int w1 = min(w0 + seg_len, g.W);
+  if (w0 >= w1) return;
+  const bool top_ok = h >= 1, bot_ok = h <= g.H - 2;  // window rows h-1 and h exist
+  const long long rs = (long long)g.W * g.C;
+  const float* xm = x + (((long long)b * g.H + h) * g.W) * g.C + c4 * 4;  // row h
+  const float* xt = top_ok ? xm - rs : xm;                                 // row h-1 (clamped: its windows then carry dy = 0)
+  const float* xb = bot_ok ? xm + rs : xm;                                 // row h+1
+  const float* dt = dy + (((long long)b * g.OH + (top_ok ? h - 1 : 0)) * g.OW) * g.C + c4 * 4;
+  const float* db = dy + (((long long)b * g.OH + (bot_ok ? h : 0)) * g.OW) * g.C + c4 * 4;
+  float* dxo = dx + (((long long)b * g.H + h) * g.W) * g.C + c4 * 4;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  // state of column w-1: its x values and the two windows anchored there
+  float4 ct, cm, cb;          // x[h-1][w], x[h][w], x[h+1][w] of the CURRENT column
+  Idx4 pkt{-1, -1, -1, -1}, pkb{-1, -1, -1, -1};
+  float4 pgt = zero, pgb = zero;
+  if (w0 >= 1) {
+    const long long o = (long long)(w0 - 1) * g.C;
+    const float4 lt = ld4(xt + o), lm = ld4(xm + o), lb = ld4(xb + o);
+    ct = ld4(xt + o + g.C); cm = ld4(xm + o + g.C); cb = ld4(xb + o + g.C);
+    pkt = argmax22_4(lt, ct, lm, cm);
+    pkb = argmax22_4(lm, cm, lb, cb);
+    pgt = top_ok ? ld4(dt + o) : zero;
+    pgb = bot_ok ? ld4(db + o) : zero;
+  } else {
+    ct = ld4(xt); cm = ld4(xm); cb = ld4(xb);
+  }
+#pragma unroll 2
+  for (int w = w0; w < w1; ++w) {
+    const long long o = (long long)w * g.C;
+    Idx4 kt{-1, -1, -1, -1}, kb{-1, -1, -1, -1};
+    float4 gt = zero, gb = zero, nt = ct, nm = cm, nb = cb;
+    if (w <= g.W - 2) {  // windows anchored in column w exist
+      nt = ld4(xt + o + g.C); nm = ld4(xm + o + g.C); nb = ld4(xb + o + g.C);
+      kt = argmax22_4(ct, nt, cm, nm);
+      kb = argmax22_4(cm, nm, cb, nb);
+      gt = top_ok ? ld4(dt + o) : zero;
+      gb = bot_ok ? ld4(db + o) : zero;
+    }
+    float4 acc = zero;
+    acc_if(acc, pkt, 3, pgt);  // window (h-1, w-1): element is its bottom-right member
+    acc_if(acc, kt, 2, gt);    // window (h-1, w)  : bottom-left
+    acc_if(acc, pkb, 1, pgb);  // window (h,   w-1): top-right
+    acc_if(acc, kb, 0, gb);    // window (h,   w)  : top-left
+    if (RELU) {
+      if (!(cm.x > thr)) acc.x = 0.f;
+      if (!(cm.y > thr)) acc.y = 0.f;
+      if (!(cm.z > thr)) acc.z = 0.f;
+      if (!(cm.w > thr)) acc.w = 0.f;
+    }
+    st4(dxo + o, acc);
+    pkt = kt; pkb = kb; pgt = gt; pgb = gb;
+    ct = nt; cm = nm; cb = nb;
+  }
+}
 void pool_max_bwd_v4(const float* x, const float* dy, float* dx, const PoolGeom& g, int relu, float thr, cudaStream_t s) {
+  if (pool_is_22s1(g)) {
+    const long long nt = (long long)g.N * g.H * kPoolSegs * (g.C / 4);
+    const int seg_len = (g.W + kPoolSegs - 1) / kPoolSegs;
+    if (relu) pool22_bwd_strip_kernel<true><<<(int)((nt + 255) / 256), 256, 0, s>>>(x, dy, dx, g, thr, seg_len, nt);
+    else pool22_bwd_strip_kernel<false><<<(int)((nt + 255) / 256), 256, 0, s>>>(x, dy, dx, g, 0.f, seg_len, nt);
+    SB_LAUNCHED();
+    return;
+  }
   const long long n4 = (long long)g.N * g.H * g.W * (g.C / 4);
   if (relu) pool_max_bwd_v4_kernel<true><<<grid_for(n4, 256), 256, 0, s>>>(x, dy, dx, g, thr, n4);
   else pool_max_bwd_v4_kernel<false><<<grid_for(n4, 256), 256, 0, s>>>(x, dy, dx, g, 0.f, n4);
@@ -209,13 +351,7 @@ __global__ void __launch_bounds__(256) conv_smallk_wgrad_kernel(const float* __r
     __syncthreads();
   }
 }
-__global__ void partial_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int n, int parts) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float acc = partial[i];
-  for (int c = 1; c < parts; ++c) acc = __fadd_rn(acc, partial[(size_t)c * n + i]);
-  out[i] = acc;
-}
+void partial_reduce(const float* partial, float* out, int n, int parts, cudaStream_t s);
 // filter shapes 3x3x1, 3x3x3, 5x5x1 (fully unrolled accumulators); ws must hold blocks*K*Cout floats
 bool conv_smallk_wgrad(const float* x, const float* dy, float* dw, const ConvGeom& g, float* ws, size_t ws_floats, cudaStream_t s) {
   const int K = g.KH * g.KW * g.Cin;
@@ -234,133 +370,277 @@ bool conv_smallk_wgrad(const float* x, const float* dy, float* dw, const ConvGeo
   else conv_smallk_wgrad_kernel<5, 5, 1><<<blocks, 256, 0, s>>>(x, dy, ws, g, pixels, ppb);
   SB_LAUNCHED();
   const int n = K * g.Cout;
-  partial_reduce_kernel<<<(n + 255) / 256, 256, 0, s>>>(ws, dw, n, blocks);
-  SB_LAUNCHED();
+  partial_reduce(ws, dw, n, blocks, s);
   return true;
 }
 
 // =====================================================================================================================
-// skinny dense head: Z[M,N] = X[M,K] . W[K,N], N <= 16 (layer/Dense.scala:57-61 feeding Bias + Softmax + CCE)
+// skinny dense head: Z[M,N] = X[M,K] . W[K,N] with N <= 16 outputs, M <= 128 rows and a long reduction K
+// (layer/Dense.scala:57-61 feeding Bias + Softmax + CategoricalCrossentropy).  Everything here is bound by reading X
+// (forward, wgrad) or writing dX (dgrad) once.
 // =====================================================================================================================
 constexpr int kSkinnyN = 16;
-constexpr int kSkinnyKC = 256;  // K rows per block
-// partial[chunk][m][n]: block = one K chunk; warps stride over rows m; lanes stride over k inside the chunk
-__global__ void __launch_bounds__(256) dense_skinny_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                               float* __restrict__ partial, int M, int K, int N) {
-  __shared__ float sw[kSkinnyKC * kSkinnyN];
-  const int k0 = blockIdx.x * kSkinnyKC;
-  const int kc = min(kSkinnyKC, K - k0);
-  for (int i = threadIdx.x; i < kc * N; i += blockDim.x) sw[i] = w[(size_t)k0 * N + i];
+constexpr int kHeadThreads = 128;
+
+// generic deterministic column reduction  out[i] = sum_c partial[c][i]  (c ascending inside a lane group, then a fixed tree)
+__global__ void __launch_bounds__(256) partial_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int n,
+                                                             int parts) {
+  __shared__ float red[8][33];
+  const int i = blockIdx.x * 32 + threadIdx.x, y = threadIdx.y;
+  float acc = 0.f;
+  if (i < n)
+    for (int c = y; c < parts; c += 8) acc = __fadd_rn(acc, __ldg(partial + (size_t)c * n + i));
+  red[y][threadIdx.x] = acc;
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int m = warp; m < M; m += nw) {
-    float acc[kSkinnyN];
+  if (y == 0 && i < n) {
+    float t = red[0][threadIdx.x];
 #pragma unroll
-    for (int n = 0; n < kSkinnyN; ++n) acc[n] = 0.f;
-    const float* xr = x + (size_t)m * K + k0;
-    for (int k = lane; k < kc; k += 32) {
-      const float xv = __ldg(xr + k);
+    for (int j = 1; j < 8; ++j) t = __fadd_rn(t, red[j][threadIdx.x]);
+    out[i] = t;
+  }
+}
+void partial_reduce(const float* partial, float* out, int n, int parts, cudaStream_t s) {
+  partial_reduce_kernel<<<(n + 31) / 32, dim3(32, 8), 0, s>>>(partial, out, n, parts);
+  SB_LAUNCHED();
+}
+
+// Forward split-K: CTA c owns the K range [c*KC, c*KC+KC).  The X tile [M][KC] arrives through one bulk async copy per row
+// (cp.async.bulk -> mbarrier, all rows in flight at once); the W slab [KC][NT] is staged by the threads meanwhile.  Thread
+// (m, kq) then owns output row m over a quarter of the chunk (no cross-lane reduction): per 4 k one conflict-free LDS.128 of X
+// (row stride KC+4 floats, (KC+4)/4 odd) and NT/4 broadcast LDS.128 of W per k; the four quarters are summed in order through
+// shared memory.  partial[c][m][n].
+constexpr int kHeadKQ = 4;
+template <int NT>
+__global__ void __launch_bounds__(kHeadThreads* kHeadKQ) dense_head_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                               float* __restrict__ partial, int M, int K, int N, int KC) {
+  extern __shared__ __align__(128) float sm[];
+  const int xs_stride = KC + 4;
+  float* xs = sm;                                        // [M][KC+4]
+  float* ws = xs + (size_t)M * xs_stride;                // [KC][NT]
+  float* red = ws + (size_t)KC * NT;                     // [kHeadKQ][M][NT+1]
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x;
+  const int k0 = blockIdx.x * KC;
+  const int kc = min(KC, K - k0);
+  if (tid == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+  if (tid == 0) tc::mbar_arrive_expect_tx(&bar, (uint32_t)(M * kc * 4));
+  if (tid < M) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     tc::smem_u32(xs + (size_t)tid * xs_stride)),
+                 "l"(x + (size_t)tid * K + k0), "r"((uint32_t)(kc * 4)), "r"(tc::smem_u32(&bar))
+                 : "memory");
+  }
+  for (int i = tid; i < KC * NT; i += blockDim.x) {
+    const int k = i / NT, n = i - k * NT;
+    ws[i] = (k < kc && n < N) ? __ldg(w + (size_t)(k0 + k) * N + n) : 0.f;
+  }
+  if (kc < KC) {  // tail chunk: the columns the copy does not write must not hold NaN bit patterns (they meet zero weights)
+    const int pad = KC - kc;
+    for (int i = tid; i < M * pad; i += blockDim.x) xs[(size_t)(i / pad) * xs_stride + kc + i % pad] = 0.f;
+  }
+  __syncthreads();
+  tc::mbar_wait(&bar, 0);
+  const int m = tid & (kHeadThreads - 1), kq = tid / kHeadThreads;
+  const int KQ = KC / kHeadKQ;
+  if (m < M) {
+    float acc[NT];
 #pragma unroll
-      for (int n = 0; n < kSkinnyN; ++n)
-        if (n < N) acc[n] = fmaf(xv, sw[k * N + n], acc[n]);
-    }
+    for (int n = 0; n < NT; ++n) acc[n] = 0.f;
+    const float* xr = xs + (size_t)m * xs_stride + kq * KQ;
+    const float* wr = ws + (size_t)kq * KQ * NT;
+    for (int k = 0; k < KQ; k += 4) {
+      const float4 xv = *reinterpret_cast<const float4*>(xr + k);
+      const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
-    for (int n = 0; n < kSkinnyN; ++n) {
-      if (n < N) {
-        float v = acc[n];
+      for (int j = 0; j < 4; ++j) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
-        if (lane == 0) partial[((size_t)blockIdx.x * M + m) * N + n] = v;
+        for (int n4 = 0; n4 < NT; n4 += 4) {
+          const float4 wv = *reinterpret_cast<const float4*>(wr + (k + j) * NT + n4);
+          acc[n4] = fmaf(xa[j], wv.x, acc[n4]); acc[n4 + 1] = fmaf(xa[j], wv.y, acc[n4 + 1]);
+          acc[n4 + 2] = fmaf(xa[j], wv.z, acc[n4 + 2]); acc[n4 + 3] = fmaf(xa[j], wv.w, acc[n4 + 3]);
+        }
       }
     }
+#pragma unroll
+    for (int n = 0; n < NT; ++n) red[((size_t)kq * M + m) * (NT + 1) + n] = acc[n];
+  }
+  __syncthreads();
+  for (int i = tid; i < M * N; i += blockDim.x) {
+    const int mm = i / N, n = i - mm * N;
+    float t = red[(size_t)mm * (NT + 1) + n];
+#pragma unroll
+    for (int q = 1; q < kHeadKQ; ++q) t = __fadd_rn(t, red[((size_t)q * M + mm) * (NT + 1) + n]);
+    partial[(size_t)blockIdx.x * M * N + i] = t;
   }
 }
-__global__ void skinny_reduce_kernel(const float* __restrict__ partial, float* __restrict__ z, int mn, int chunks) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= mn) return;
-  float acc = partial[i];
-  for (int c = 1; c < chunks; ++c) acc = __fadd_rn(acc, partial[(size_t)c * mn + i]);
-  z[i] = acc;
+static int head_smem_bytes(int M, int KC, int NT) { return (M * (KC + 4) + KC * NT + kHeadKQ * M * (NT + 1)) * 4; }
+// writes partial[chunks][M][N] into `partial`; *chunks_out = number of partials.  K % 4 == 0 (16-byte row alignment).
+bool dense_head_fwd(const float* x, const float* w, float* partial, int* chunks_out, int M, int N, int K, size_t ws_floats,
+                    cudaStream_t s) {
+  if (N > kSkinnyN || M > kHeadThreads || (K & 3) || (((uintptr_t)x) & 15)) return false;
+  const int NT = N <= 12 ? 12 : 16;
+  int KC = ((K + kNumSMs - 1) / kNumSMs + 15) & ~15;  // one wave of CTAs; multiple of 16 (=> (KC+4)/4 is odd)
+  if (KC < 64) KC = 64;
+  while (head_smem_bytes(M, KC, NT) > 200 * 1024 && KC > 64) KC = ((KC / 2) + 15) & ~15;
+  if (head_smem_bytes(M, KC, NT) > 200 * 1024) return false;
+  const int chunks = (K + KC - 1) / KC;
+  if ((size_t)chunks * M * N > ws_floats) return false;
+  const int smem = head_smem_bytes(M, KC, NT);
+  static bool attr = false;
+  if (!attr) {
+    SB_CUDA(cudaFuncSetAttribute(dense_head_fwd_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SB_CUDA(cudaFuncSetAttribute(dense_head_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  if (NT == 12) dense_head_fwd_kernel<12><<<chunks, kHeadThreads * kHeadKQ, smem, s>>>(x, w, partial, M, K, N, KC);
+  else dense_head_fwd_kernel<16><<<chunks, kHeadThreads * kHeadKQ, smem, s>>>(x, w, partial, M, K, N, KC);
+  SB_LAUNCHED();
+  *chunks_out = chunks;
+  return true;
 }
 bool dense_skinny_fwd(const float* x, const float* w, float* z, int M, int N, int K, float* ws, size_t ws_floats, cudaStream_t s) {
-  if (N > kSkinnyN) return false;
-  const int chunks = (K + kSkinnyKC - 1) / kSkinnyKC;
-  if ((size_t)chunks * M * N > ws_floats) return false;
-  dense_skinny_fwd_kernel<<<chunks, 256, 0, s>>>(x, w, ws, M, K, N);
-  SB_LAUNCHED();
-  skinny_reduce_kernel<<<(M * N + 255) / 256, 256, 0, s>>>(ws, z, M * N, chunks);
-  SB_LAUNCHED();
+  int chunks = 0;
+  if (!dense_head_fwd(x, w, ws, &chunks, M, N, K, ws_floats, s)) return false;
+  partial_reduce(ws, z, M * N, chunks, s);
   return true;
 }
-// dW[k][n] = sum_m X[m][k] * G[m][n]: one thread per k, G staged in shared memory
-__global__ void __launch_bounds__(256) dense_skinny_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gmat,
-                                                                 float* __restrict__ dw, int M, int K, int N) {
-  extern __shared__ float sg[];  // [M][N]
-  for (int i = threadIdx.x; i < M * N; i += blockDim.x) sg[i] = gmat[i];
+
+// Backward, wgrad and dgrad in ONE pass over X / dX:  dW[k][n] = sum_m X[m][k] G[m][n] ;  dX[m][k] = sum_n G[m][n] W[k][n].
+// Thread = one k (coalesced along K) x one of 4 row groups; G and the W slab of the CTA are staged in shared memory; the row
+// groups' dW partials are summed in group order through shared memory.
+constexpr int kBwdK = 64, kBwdGroups = 4;
+template <int NT, bool DGRAD>
+__global__ void __launch_bounds__(kBwdK* kBwdGroups) dense_head_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gmat,
+                                                                            const float* __restrict__ w, float* __restrict__ dw,
+                                                                            float* __restrict__ dx, int M, int K, int N) {
+  extern __shared__ __align__(16) float sm[];
+  float* sg = sm;                          // [M][NT]
+  float* sw = sg + (size_t)M * NT;         // [kBwdK][NT+1]
+  float* red = sw + kBwdK * (NT + 1);      // [kBwdGroups][kBwdK][NT+1]
+  const int tid = threadIdx.x, kk = tid % kBwdK, rg = tid / kBwdK;
+  const int k0 = blockIdx.x * kBwdK, k = k0 + kk;
+  for (int i = tid; i < M * NT; i += blockDim.x) {
+    const int m = i / NT, n = i % NT;
+    sg[i] = n < N ? __ldg(gmat + (size_t)m * N + n) : 0.f;
+  }
+  if (DGRAD) {
+    const int kn = min(kBwdK, K - k0) * N;
+    for (int i = tid; i < kn; i += blockDim.x) sw[(i / N) * (NT + 1) + i % N] = __ldg(w + (size_t)k0 * N + i);
+  }
   __syncthreads();
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= K) return;
-  float acc[kSkinnyN];
+  float acc[NT], wr[NT];
 #pragma unroll
-  for (int n = 0; n < kSkinnyN; ++n) acc[n] = 0.f;
-  for (int m = 0; m < M; ++m) {
-    const float xv = __ldg(x + (size_t)m * K + k);
+  for (int n = 0; n < NT; ++n) {
+    acc[n] = 0.f;
+    wr[n] = (DGRAD && n < N) ? sw[kk * (NT + 1) + n] : 0.f;
+  }
+  const int rows_per = (M + kBwdGroups - 1) / kBwdGroups;
+  const int m0 = rg * rows_per, m1 = min(M, m0 + rows_per);
+  if (k < K) {
+#pragma unroll 5
+    for (int m = m0; m < m1; ++m) {
+      const float xv = __ldg(x + (size_t)m * K + k);
+      float d = 0.f;
 #pragma unroll
-    for (int n = 0; n < kSkinnyN; ++n)
-      if (n < N) acc[n] = fmaf(xv, sg[m * N + n], acc[n]);
+      for (int n4 = 0; n4 < NT; n4 += 4) {
+        const float4 gv = *reinterpret_cast<const float4*>(sg + m * NT + n4);
+        acc[n4] = fmaf(xv, gv.x, acc[n4]); acc[n4 + 1] = fmaf(xv, gv.y, acc[n4 + 1]);
+        acc[n4 + 2] = fmaf(xv, gv.z, acc[n4 + 2]); acc[n4 + 3] = fmaf(xv, gv.w, acc[n4 + 3]);
+        if (DGRAD) {
+          d = fmaf(gv.x, wr[n4], d); d = fmaf(gv.y, wr[n4 + 1], d);
+          d = fmaf(gv.z, wr[n4 + 2], d); d = fmaf(gv.w, wr[n4 + 3], d);
+        }
+      }
+      if (DGRAD) dx[(size_t)m * K + k] = d;
+    }
   }
 #pragma unroll
-  for (int n = 0; n < kSkinnyN; ++n)
-    if (n < N) dw[(size_t)k * N + n] = acc[n];
+  for (int n = 0; n < NT; ++n) red[(rg * kBwdK + kk) * (NT + 1) + n] = acc[n];
+  __syncthreads();
+  // dW slab [kBwdK][N] is contiguous in memory: write it coalesced
+  const int kn = min(kBwdK, K - k0) * N;
+  for (int i = tid; i < kn; i += blockDim.x) {
+    const int r = i / N, n = i % N;
+    float t = red[r * (NT + 1) + n];
+#pragma unroll
+    for (int g2 = 1; g2 < kBwdGroups; ++g2) t = __fadd_rn(t, red[(g2 * kBwdK + r) * (NT + 1) + n]);
+    dw[(size_t)k0 * N + i] = t;
+  }
 }
-bool dense_skinny_wgrad(const float* x, const float* g, float* dw, int M, int N, int K, cudaStream_t s) {
-  if (N > kSkinnyN || (size_t)M * N * 4 > 40000) return false;
-  dense_skinny_wgrad_kernel<<<(K + 255) / 256, 256, (size_t)M * N * 4, s>>>(x, g, dw, M, K, N);
-  SB_LAUNCHED();
-  return true;
-}
-// dX[m][k] = sum_n G[m][n] * W[k][n]
-__global__ void __launch_bounds__(256) dense_skinny_dgrad_kernel(const float* __restrict__ gmat, const float* __restrict__ w,
-                                                                 float* __restrict__ dx, int M, int K, int N) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)M * K) return;
-  const int m = (int)(i / K), k = (int)(i % K);
-  float acc = 0.f;
-  for (int n = 0; n < N; ++n) acc = fmaf(__ldg(gmat + m * N + n), __ldg(w + (size_t)k * N + n), acc);
-  dx[i] = acc;
-}
-bool dense_skinny_dgrad(const float* g, const float* w, float* dx, int M, int N, int K, cudaStream_t s) {
+bool dense_head_bwd(const float* x, const float* g, const float* w, float* dw, float* dx, int M, int N, int K, cudaStream_t s) {
   if (N > kSkinnyN) return false;
-  const long long n = (long long)M * K;
-  dense_skinny_dgrad_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(g, w, dx, M, K, N);
+  const int NT = N <= 12 ? 12 : 16;
+  const size_t smem = ((size_t)M * NT + kBwdK * (NT + 1) + (size_t)kBwdGroups * kBwdK * (NT + 1)) * 4;
+  if (smem > 48 * 1024) return false;
+  const int grid = (K + kBwdK - 1) / kBwdK, thr = kBwdK * kBwdGroups;
+  if (NT == 12) {
+    if (dx) dense_head_bwd_kernel<12, true><<<grid, thr, smem, s>>>(x, g, w, dw, dx, M, K, N);
+    else dense_head_bwd_kernel<12, false><<<grid, thr, smem, s>>>(x, g, w, dw, dx, M, K, N);
+  } else {
+    if (dx) dense_head_bwd_kernel<16, true><<<grid, thr, smem, s>>>(x, g, w, dw, dx, M, K, N);
+    else dense_head_bwd_kernel<16, false><<<grid, thr, smem, s>>>(x, g, w, dw, dx, M, K, N);
+  }
   SB_LAUNCHED();
   return true;
 }
 
-// Fused head: z += bias ; p = exp(z)/sum ; loss = -sum(y log(p+eps))/B ; dz = -(p/B)(r - sum r p), r = y/(p+eps) ;
-// db = column sums of dz (fixed row order).  One CTA; rows over warps.  (layer/Bias.scala:32-33, models/Activation.scala:63-69,
+// Fused head: z = (sum of the split-K partials | z) + bias ; p = exp(z)/sum ; loss = -sum(y log(p+eps))/B ;
+// dz = -(p/B)(r - sum r p), r = y/(p+eps) ; db = column sums of dz.  CTA g owns rows [g*R, g*R+R): 8 thread groups sum the
+// partials of every (row, class) (chunk c goes to group c % 8, then the groups in order), one warp per row does the softmax /
+// loss / dz; per-CTA loss and bias-gradient partials go to `scratch` and the LAST CTA to finish (ticket) adds them in CTA order,
+// so the result does not depend on which CTA that is.  (layer/Bias.scala:32-33, models/Activation.scala:63-69,
 // models/Loss.scala:44-57)
-__global__ void __launch_bounds__(1024) head_bias_softmax_cce_kernel(float* __restrict__ z, const float* __restrict__ bias,
+constexpr int kHeadRows = 10;  // rows per CTA
+__global__ void __launch_bounds__(1024) head_bias_softmax_cce_kernel(float* __restrict__ z, const float* __restrict__ partial,
+                                                                     int chunks, const float* __restrict__ bias,
                                                                      const float* __restrict__ y, float* __restrict__ dz,
-                                                                     float* __restrict__ dbias, StepState* st, int rows, int C) {
+                                                                     float* __restrict__ dbias, StepState* st, int rows, int C,
+                                                                     float* __restrict__ scratch, unsigned int* ticket) {
+  __shared__ float zs[8][kHeadRows * 32];
+  __shared__ float sl[kHeadRows];
+  __shared__ float sdb[kHeadRows][33];
+  __shared__ bool last;
   const float eps = 1e-8f, fr = (float)rows;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  __shared__ float sl[32];
-  float acc = 0.f;
-  for (int row = wid; row < rows; row += nw) {
-    float* zr = z + (size_t)row * C;
-    const float* yr = y + (size_t)row * C;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int row0 = blockIdx.x * kHeadRows, nrows = min(kHeadRows, rows - row0);
+  const int mn = rows * C, cnt = nrows * C;
+  // ---- z for this CTA's rows ----
+  {
+    const int grp = tid / 128, i = tid % 128;  // 8 groups x 128 lanes
+    for (int j = i; j < cnt; j += 128) {
+      float v = 0.f;
+      if (partial) {
+        const float* pp = partial + (size_t)row0 * C + j;
+        for (int c = grp; c < chunks; c += 8) v = __fadd_rn(v, __ldg(pp + (size_t)c * mn));
+      } else if (grp == 0) {
+        v = z[(size_t)row0 * C + j];
+      }
+      zs[grp][j] = v;
+    }
+  }
+  __syncthreads();
+  float l = 0.f, d = 0.f;
+  if (wid < nrows) {
+    const int row = row0 + wid;
     float e = 0.f, yv = 0.f;
     if (lane < C) {
-      e = expf(__fadd_rn(zr[lane], bias ? bias[lane] : 0.f));
-      yv = yr[lane];
+      float v = zs[0][wid * C + lane];
+#pragma unroll
+      for (int g2 = 1; g2 < 8; ++g2) v = __fadd_rn(v, zs[g2][wid * C + lane]);
+      if (bias) v = __fadd_rn(v, __ldg(bias + lane));
+      e = expf(v);
+      yv = y[(size_t)row * C + lane];
     }
     float sum = e;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, o));
     const float p = __fdiv_rn(e, sum);
     const float pe = __fadd_rn(p, eps);
-    float l = lane < C ? __fmul_rn(yv, logf(pe)) : 0.f;
+    l = lane < C ? __fmul_rn(yv, logf(pe)) : 0.f;
     const float r = lane < C ? __fdiv_rn(yv, pe) : 0.f;
     float dot = __fmul_rn(r, p);
 #pragma unroll
@@ -368,30 +648,55 @@ __global__ void __launch_bounds__(1024) head_bias_softmax_cce_kernel(float* __re
       l = __fadd_rn(l, __shfl_xor_sync(0xffffffffu, l, o));
       dot = __fadd_rn(dot, __shfl_xor_sync(0xffffffffu, dot, o));
     }
-    acc = __fadd_rn(acc, l);
     if (lane < C) {
-      zr[lane] = p;
-      if (dz) dz[(size_t)row * C + lane] = __fmul_rn(-__fdiv_rn(p, fr), __fsub_rn(r, dot));
+      z[(size_t)row * C + lane] = p;
+      if (dz) {
+        d = __fmul_rn(-__fdiv_rn(p, fr), __fsub_rn(r, dot));
+        dz[(size_t)row * C + lane] = d;
+      }
     }
+    if (lane == 0) sl[wid] = l;
+    sdb[wid][lane] = d;
   }
-  if (lane == 0) sl[wid] = acc;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float tot = 0.f;
-    for (int i = 0; i < nw; ++i) tot = __fadd_rn(tot, sl[i]);
-    st->loss = __fdiv_rn(-tot, fr);
+  // ---- per-CTA partials -> scratch[cta][0] = loss sum, scratch[cta][1 + c] = bias gradient ----
+  float* mine = scratch + (size_t)blockIdx.x * 40;
+  if (tid == 0) {
+    float t = 0.f;
+    for (int i = 0; i < nrows; ++i) t = __fadd_rn(t, sl[i]);
+    mine[0] = t;
   }
-  __syncthreads();  // dz rows of every warp are visible
-  if (dz && dbias && threadIdx.x < C) {
-    float s = 0.f;
-    for (int row = 0; row < rows; ++row) s = __fadd_rn(s, dz[(size_t)row * C + threadIdx.x]);
-    dbias[threadIdx.x] = s;
+  if (tid >= 32 && tid < 32 + C) {
+    float t = 0.f;
+    for (int i = 0; i < nrows; ++i) t = __fadd_rn(t, sdb[i][tid - 32]);
+    mine[1 + tid - 32] = t;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (tid == 0) {
+    float t = 0.f;
+    for (unsigned g2 = 0; g2 < gridDim.x; ++g2) t = __fadd_rn(t, __ldcg(scratch + (size_t)g2 * 40));
+    st->loss = __fdiv_rn(-t, fr);
+    *ticket = 0;  // ready for the next launch
+  }
+  if (dz && dbias && tid >= 32 && tid < 32 + C) {
+    float t = 0.f;
+    for (unsigned g2 = 0; g2 < gridDim.x; ++g2) t = __fadd_rn(t, __ldcg(scratch + (size_t)g2 * 40 + 1 + tid - 32));
+    dbias[tid - 32] = t;
   }
 }
-bool head_bias_softmax_cce(float* z, const float* bias, const float* y, float* dz, float* dbias, StepState* st, int rows, int C,
-                           cudaStream_t s) {
+// scratch: >= ceil(rows/10)*40 floats followed by one zero-initialised 32-bit ticket (the kernel leaves it zero)
+bool head_bias_softmax_cce(float* z, const float* partial, int chunks, const float* bias, const float* y, float* dz, float* dbias,
+                           StepState* st, int rows, int C, float* scratch, cudaStream_t s) {
   if (C > 32) return false;
-  head_bias_softmax_cce_kernel<<<1, 1024, 0, s>>>(z, bias, y, dz, dbias, st, rows, C);
+  const int grid = (rows + kHeadRows - 1) / kHeadRows;
+  if (grid > 1024) return false;
+  head_bias_softmax_cce_kernel<<<grid, 1024, 0, s>>>(z, partial, chunks, bias, y, dz, dbias, st, rows, C, scratch,
+                                                     reinterpret_cast<unsigned int*>(scratch + 1024 * 40));
   SB_LAUNCHED();
   return true;
 }

@@ -898,6 +898,20 @@ __global__ void fill_kernel(float* __restrict__ p, float v, long long n) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) p[i] = v;
 }
+// Busy-wait `ns` nanoseconds on one thread.  Profiling mode enqueues it ahead of a batch of event-bracketed launches so the
+// host runs ahead of the device and the events measure kernel time, not launch gaps.
+__global__ void delay_kernel(long long ns) {
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do {
+    __nanosleep(1000);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  } while ((long long)(t - t0) < ns);
+}
+void device_delay(long long ns, cudaStream_t s) {
+  delay_kernel<<<1, 1, 0, s>>>(ns);
+  SB_CUDA(cudaPeekAtLastError());
+}
 void fill_const(float* p, float v, long long n, cudaStream_t s) {
   if (n <= 0) return;
   int blocks = (int)fmin((double)ceil_div(n, 256), (double)kNumSMs * 16);

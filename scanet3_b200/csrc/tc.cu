@@ -10,6 +10,7 @@
 // Arithmetic: kind::tf32 (operands are fp32 words, the low 13 mantissa bits are ignored), fp32 accumulation.
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <stdexcept>
@@ -217,6 +218,207 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   }
 }
 
+
+// =====================================================================================================================
+// Halo implicit GEMM (fprop and dgrad, stride 1): every source pixel is fetched into shared memory ONCE per tile.
+//   The tile is BH rows of the output grid.  ONE 4-D TMA box per 32-channel chunk brings the (BH+KH-1) x P source rows the
+//   tile needs (P = Wg + KW - 1 pixels per row; pixels outside the source tensor -- dgrad's implicit zero padding, SAME
+//   padding -- are zero-filled by TMA).  With the GEMM row index laid out on the SAME pitch, m = r*P + c, the source pixel
+//   of filter tap (dh,dw) is row m + dh*P + dw of the shared tile: every tap's A operand is the one tile viewed through a
+//   descriptor whose start address is shifted by (dh*P + dw) 128-byte rows (the 128-byte swizzle is a function of the
+//   absolute shared-memory address, so TMA's write pattern and the MMA's read pattern agree for any row shift).
+//   Rows with c >= Wg are computed and dropped by the epilogue (KW-1 of every P).  The whole filter is resident in shared
+//   memory for the life of the CTA.  Per tile: kchunks TMA issues and taps*kchunks*4 MMAs -- no per-tap traffic.
+// =====================================================================================================================
+struct HaloParams {
+  int n_tiles, tiles_per_img;
+  int Hg, Wg, BH, P;
+  int KH, KW, kchunks;
+  int N;               // accumulator columns (fprop: Cout, dgrad: Cin), multiple of 32
+  int b_mn_major;      // fprop 1 (B = N/32 boxes [32 n x 32 k]) ; dgrad 0 (B = one box [32 k x N rows])
+  int b_rows_per_tap;  // rows between taps in the 2-D filter view
+  int flip;            // dgrad: tap (kh,kw) reads source offset (KH-1-kh, KW-1-kw)
+  int ox, oy;          // box origin relative to the tile's first output pixel (fprop: -PL,-PT ; dgrad: -(KW-1-PL), -(KH-1-PT))
+  int a_tile_bytes;    // one 32-channel chunk of the source tile (multiple of 1024)
+  int box_bytes;       // bytes TMA delivers per chunk
+  int stages;
+  int relu;
+  float thr;
+  float* out;          // [n_img, Hg, Wg, N]
+  long long* dbg;      // developer timeline (SB_TC_DEBUG=1): 64 clock64 slots per CTA, null in production
+  int bo_mode;         // debug: 1 = also encode the start row's swizzle phase in the descriptor's base-offset field
+};
+
+__global__ void __launch_bounds__(kIgemmThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const HaloParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int taps = p.KH * p.KW;
+  const int b_tile_bytes = p.N * 128;                         // one (tap, chunk) slice of the filter
+  const int b_bytes = taps * p.kchunks * b_tile_bytes;        // resident filter
+  const int stage_bytes = p.kchunks * p.a_tile_bytes;
+  uint8_t* sm_b = smem;
+  uint8_t* sm_a = smem + b_bytes;
+  uint64_t* full_bar = (uint64_t*)(sm_a + (size_t)p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tmem_full = empty_bar + p.stages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* b_bar = tmem_empty + 2;
+  uint32_t* tmem_slot = (uint32_t*)(b_bar + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // shfl: provably warp-uniform
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < 2 * p.N) tmem_cols <<= 1;
+  long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 64 : nullptr;
+#define HALO_T(slot) do { if (dbg) dbg[slot] = clock64(); } while (0)
+
+  if (threadIdx.x == 0) {
+    HALO_T(0);
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);
+    }
+    mbar_init(b_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) HALO_T(1);
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      // the filter, once
+      mbar_arrive_expect_tx(b_bar, (uint32_t)b_bytes);
+      for (int tap = 0; tap < taps; ++tap)
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          uint8_t* sb = sm_b + (size_t)(tap * p.kchunks + kc) * b_tile_bytes;
+          if (p.b_mn_major) {
+            for (int j = 0; j < p.N / 32; ++j) tma_load_2d(sb + j * 4096, &map_b, b_bar, j * 32, tap * p.b_rows_per_tap + kc * 32);
+          } else {
+            tma_load_2d(sb, &map_b, b_bar, kc * 32, tap * p.b_rows_per_tap);
+          }
+        }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int img = tile / p.tiles_per_img, h0 = (tile - img * p.tiles_per_img) * p.BH;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = sm_a + (size_t)stage * stage_bytes;
+        mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(p.kchunks * p.box_bytes));
+        for (int kc = 0; kc < p.kchunks; ++kc)
+          tma_load_4d(sa + (size_t)kc * p.a_tile_bytes, &map_a, &full_bar[stage], kc * 32, p.ox, h0 + p.oy, img);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer: warp-uniform loop, one elected lane issues =================
+    {
+      const uint32_t idesc = idesc_tf32(128, p.N, 0, p.b_mn_major);
+      // descriptors: the high word is constant, the low word = (LBO >> 4) << 16 | (start address >> 4)
+      const uint64_t a_d = smem_desc_sw128(0, 16, 1024), b_d = p.b_mn_major ? smem_desc(0, 4096, 512, 1) : smem_desc_sw128(0, 16, 1024);
+      const uint32_t a_hi = (uint32_t)(a_d >> 32), a_lo0 = (uint32_t)a_d, b_hi = (uint32_t)(b_d >> 32), b_lo0 = (uint32_t)b_d;
+      const uint32_t b_ks_step = p.b_mn_major ? (1024u >> 4) : (32u >> 4);
+      const uint32_t sb0 = b_lo0 + (smem_u32(sm_b) >> 4);
+      const uint32_t a_chunk = (uint32_t)(p.a_tile_bytes >> 4), b_chunk = (uint32_t)(b_tile_bytes >> 4);
+      const int KH = p.KH, KW = p.KW, kchunks = p.kchunks, P8 = p.P * 8;
+      mbar_wait(b_bar, 0);
+      tc_fence_after();
+      if (lane == 0) HALO_T(2);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      int ti = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0 && ti < 6) HALO_T(8 + ti * 2);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.N);
+        const uint32_t sa0 = a_lo0 + (smem_u32(sm_a + (size_t)stage * stage_bytes) >> 4);
+        uint32_t accumulate = 0;
+        uint32_t bt = sb0;
+        // tap (kh,kw) reads source rows shifted by (dh*P + dw) pixels = 8 descriptor units (128 B >> 4) each
+        uint32_t row_at = sa0 + (p.flip ? (uint32_t)((KH - 1) * P8 + (KW - 1) * 8) : 0u);
+        const int32_t step_w = p.flip ? -8 : 8, step_h = p.flip ? -P8 : P8;
+        for (int kh = 0; kh < KH; ++kh, row_at += step_h) {
+          uint32_t at_tap = row_at;
+          for (int kw = 0; kw < KW; ++kw, at_tap += step_w) {
+            uint32_t at = at_tap;
+            for (int kc = 0; kc < kchunks; ++kc, at += a_chunk, bt += b_chunk) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {  // 4 x (K = 8 tf32) per 32-channel chunk
+                umma_tf32_elect(d_tmem, ((uint64_t)a_hi << 32) | (at + ks * 2), ((uint64_t)b_hi << 32) | (bt + ks * b_ks_step), idesc,
+                                accumulate);
+                accumulate = 1;
+              }
+            }
+          }
+        }
+        umma_commit_elect(&empty_bar[stage]);  // the source tile is free once these MMAs have read it
+        umma_commit_elect(&tmem_full[acc]);
+        if (lane == 0 && ti < 6) HALO_T(9 + ti * 2);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ================= epilogue: TMEM -> registers -> (ReLU) -> NHWC rows =================
+    const int sub = warp & 3;  // TMEM sub-partition this warp may read: lanes [32*sub, 32*sub+32)
+    const int m = sub * 32 + lane;
+    const int r = m / p.P, c = m - r * p.P;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
+      const int img = tile / p.tiles_per_img, h0 = (tile - img * p.tiles_per_img) * p.BH;
+      const bool valid = r < p.BH && c < p.Wg && h0 + r < p.Hg;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      if (threadIdx.x == 64 && ti < 6) HALO_T(24 + ti * 2);
+      float* orow = p.out + ((size_t)(img * p.Hg + h0 + r) * p.Wg + c) * p.N;
+      for (int c0 = 0; c0 < p.N; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * p.N + c0), v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (p.relu) {
+              o.x = fmaxf(p.thr, o.x); o.y = fmaxf(p.thr, o.y); o.z = fmaxf(p.thr, o.z); o.w = fmaxf(p.thr, o.w);
+            }
+            *reinterpret_cast<float4*>(orow + c0 + j) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (threadIdx.x == 64 && ti < 6) HALO_T(25 + ti * 2);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) HALO_T(3);
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+#undef HALO_T
+}
+
 // =====================================================================================================================
 // Conv2D wgrad:  dW[tap][ci][co] = sum_pixels X[n, oh+kh, ow+kw, ci] * dY[n, oh, ow, co]
 //   D_tap[M = co, N = ci] += A[M, K] . B_tap[K, N],  K = pixels.  A = dY rows (MN-major, M = Cout contiguous),
@@ -247,7 +449,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* done_bar = empty_bar + p.stages;
   uint32_t* tmem_slot = (uint32_t*)(done_bar + 1);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // shfl: provably warp-uniform
   const int ncols = taps * p.Cin;
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < ncols) tmem_cols <<= 1;
@@ -287,30 +489,34 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && has_work) {
+    if (has_work) {  // warp-uniform loop, one elected lane issues
       const uint32_t idesc = idesc_tf32(p.Cout, p.Cin, 1, 1);  // M = Cout (64 or 128), N = Cin, both MN-major
+      // MN-major SW128 (32-byte atoms): 8 K-rows per instruction (one swizzle atom deep), 32-element groups along M/N LBO apart
+      const uint64_t tmpl = smem_desc(0, (uint32_t)box_bytes, 512, 1);
+      const uint32_t d_hi = (uint32_t)(tmpl >> 32), d_lo = (uint32_t)tmpl;
+      const uint32_t b_tap = (uint32_t)(((p.Cin / 32) * box_bytes) >> 4);
+      const int nks = krows / 8;
       int stage = 0;
       uint32_t phase = 0;
-      bool first = true;
+      uint32_t accumulate = 0;
       for (int ch = blockIdx.x; ch < p.n_chunks; ch += gridDim.x) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-        const uint32_t sb = sa + a_bytes;
-        for (int t = 0; t < taps; ++t) {
+        const uint32_t sa = d_lo + (smem_u32(smem + (size_t)stage * stage_bytes) >> 4);
+        uint32_t sb = sa + (uint32_t)(a_bytes >> 4);
+        for (int t = 0; t < taps; ++t, sb += b_tap) {
           const uint32_t d_tmem = tmem_base + (uint32_t)(t * p.Cin);
-          for (int ks = 0; ks < krows / 8; ++ks) {
-            // MN-major SW128: 8 K-rows per instruction (one swizzle atom deep), 32-element groups along M/N LBO apart
-            const uint64_t da = smem_desc(sa + ks * 1024, (uint32_t)box_bytes, 512, 1);
-            const uint64_t db = smem_desc(sb + t * (p.Cin / 32) * box_bytes + ks * 1024, (uint32_t)box_bytes, 512, 1);
-            umma_tf32(d_tmem, da, db, idesc, (first && ks == 0) ? 0u : 1u);
+          uint32_t acc_t = accumulate;
+          for (int ks = 0; ks < nks; ++ks) {
+            umma_tf32_elect(d_tmem, ((uint64_t)d_hi << 32) | (sa + ks * 64), ((uint64_t)d_hi << 32) | (sb + ks * 64), idesc, acc_t);
+            acc_t = 1;
           }
         }
-        first = false;
-        umma_commit(&empty_bar[stage]);
+        accumulate = 1;
+        umma_commit_elect(&empty_bar[stage]);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(done_bar);
+      umma_commit_elect(done_bar);
     }
   } else {
     // epilogue: partial[cta][(t*Cin + ci)*Cout + co] = D_t[co][ci]
@@ -362,6 +568,10 @@ struct ConvTcPlan {
   CUtensorMap map_dy_dg, map_w_dg;     // dgrad: A = dY boxes, B = filter (K-major)
   CUtensorMap map_dy_wg, map_x_wg;     // wgrad
   IgemmParams fwd{}, dg{};
+  HaloParams hfwd{}, hdg{};
+  CUtensorMap map_x_h, map_dy_h;       // halo kernels: source boxes [32 ch, P, BH+KH-1, 1]
+  bool halo_fwd = false, halo_dg = false;
+  int hfwd_smem = 0, hdg_smem = 0, hfwd_grid = 0, hdg_grid = 0;
   WgradParams wg{};
   int fwd_smem = 0, dg_smem = 0, wg_smem = 0;
   int fwd_grid = 0, dg_grid = 0, wg_grid = 0;
@@ -377,6 +587,44 @@ static bool conv_fits(const ConvGeom& g) {
   if (g.OW > 128 || g.W > 128) return false;
   if (g.Cout != 64 && g.Cout != 128) return false;          // wgrad: UMMA M = Cout
   if (g.KH * g.KW * g.Cin > 512) return false;               // wgrad: taps*Cin TMEM columns
+  return true;
+}
+
+
+// Fill a HaloParams for an output grid Hg x Wg whose taps read a source tensor [Csrc, Ws, Hs, N] at origin (ox, oy).
+static bool plan_halo(HaloParams& p, CUtensorMap* map, const float* src, int Csrc, int Ws, int Hs, int Nimg, int Hg, int Wg,
+                      int KH, int KW, int Nacc, int b_mn_major, int b_rows_per_tap, int flip, int ox, int oy, float* out,
+                      int dev_smem, int* smem_out) {
+  p.Hg = Hg; p.Wg = Wg; p.KH = KH; p.KW = KW; p.kchunks = Csrc / 32; p.N = Nacc;
+  p.P = Wg + KW - 1;
+  if (p.P > 128) return false;
+  p.BH = std::max(1, std::min(128 / p.P, Hg));
+  const int box_h = p.BH + KH - 1;
+  if (p.P > 256 || box_h > 256) return false;
+  p.tiles_per_img = (Hg + p.BH - 1) / p.BH;
+  p.n_tiles = Nimg * p.tiles_per_img;
+  p.b_mn_major = b_mn_major; p.b_rows_per_tap = b_rows_per_tap; p.flip = flip; p.ox = ox; p.oy = oy;
+  const int rows = std::max(box_h * p.P, 128 + (KH - 1) * p.P + KW - 1);
+  p.a_tile_bytes = ((rows + 7) / 8) * 1024;
+  p.box_bytes = box_h * p.P * 128;
+  p.relu = 0; p.thr = 0.f; p.out = out;
+  p.dbg = nullptr;
+  const char* dbg = getenv("SB_TC_DEBUG");
+  if (dbg && dbg[0] == '1') {
+    SB_CUDA(cudaMalloc((void**)&p.dbg, (size_t)kNumSMs * 64 * sizeof(long long)));
+    SB_CUDA(cudaMemset(p.dbg, 0, (size_t)kNumSMs * 64 * sizeof(long long)));
+  }
+  const char* bo = getenv("SB_TC_BASE_OFFSET");
+  p.bo_mode = (bo && bo[0] == '1') ? 1 : 0;
+  const int b_bytes = KH * KW * p.kchunks * Nacc * 128;
+  const int stage_bytes = p.kchunks * p.a_tile_bytes;
+  const int fixed = b_bytes + 16 * 16 + 1024 + 256;
+  p.stages = std::min(6, (dev_smem - fixed) / stage_bytes);
+  if (p.stages < 2) return false;
+  *smem_out = fixed + p.stages * stage_bytes;
+  uint64_t d[4] = {(uint64_t)Csrc, (uint64_t)Ws, (uint64_t)Hs, (uint64_t)Nimg};
+  uint32_t b[4] = {32, (uint32_t)p.P, (uint32_t)box_h, 1};
+  *map = make_map(src, 4, d, b);
   return true;
 }
 
@@ -423,6 +671,14 @@ void tc_plan_layers(sb_engine* e) {
       P->map_w_fwd = make_map(w, 2, wd, wb, true);
       P->fwd_smem = igemm_smem(p);
       P->fwd_grid = std::min(p.n_tiles, kNumSMs);
+      const char* h = getenv("SB_TC_HALO");
+      const bool halo_on = !(h && h[0] == '0');
+      if (halo_on && plan_halo(P->hfwd, &P->map_x_h, x, g.Cin, g.W, g.H, g.N, g.OH, g.OW, g.KH, g.KW, g.Cout, 1, g.Cin, 0, -g.PL,
+                               -g.PT, y, dev_smem, &P->hfwd_smem)) {
+        P->hfwd.relu = p.relu; P->hfwd.thr = p.thr;
+        P->hfwd_grid = std::min(P->hfwd.n_tiles, kNumSMs);
+        P->halo_fwd = true;
+      }
     }
     // ---- dgrad: tile = BH rows of the H x W input grid; source dY shifted by -tap with zero fill ----
     P->has_dgrad = L.need_dx && dx != nullptr;
@@ -444,6 +700,13 @@ void tc_plan_layers(sb_engine* e) {
       P->map_w_dg = make_map(w, 2, wd, wb);
       P->dg_smem = igemm_smem(p);
       P->dg_grid = std::min(p.n_tiles, kNumSMs);
+      const char* h = getenv("SB_TC_HALO");
+      const bool halo_on = !(h && h[0] == '0');
+      if (halo_on && plan_halo(P->hdg, &P->map_dy_h, dy, g.Cout, g.OW, g.OH, g.N, g.H, g.W, g.KH, g.KW, g.Cin, 0, g.Cin, 1,
+                               -(g.KW - 1 - g.PL), -(g.KH - 1 - g.PT), dx, dev_smem, &P->hdg_smem)) {
+        P->hdg_grid = std::min(P->hdg.n_tiles, kNumSMs);
+        P->halo_dg = true;
+      }
     }
     // ---- wgrad ----
     {
@@ -482,6 +745,7 @@ void tc_plan_layers(sb_engine* e) {
   if (!attr_set) {
     SB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
     SB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
+    SB_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
     attr_set = true;
   }
 }
@@ -490,6 +754,20 @@ void tc_free_layers(sb_engine* e) {
   for (auto& L : e->L) {
     if (L.tc_plan) {
       ConvTcPlan* P = (ConvTcPlan*)L.tc_plan;
+      for (HaloParams* hp : {&P->hfwd, &P->hdg}) {
+        if (!hp->dbg) continue;  // developer timeline of the LAST launch, one line per CTA
+        std::vector<long long> h((size_t)kNumSMs * 64);
+        cudaMemcpy(h.data(), hp->dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        FILE* f = fopen(hp == &P->hfwd ? "gpurun_out/halo_fwd_timeline.txt" : "gpurun_out/halo_dgrad_timeline.txt", "w");
+        if (f) {
+          for (int c = 0; c < kNumSMs; ++c) {
+            for (int j = 0; j < 40; ++j) fprintf(f, "%lld ", h[(size_t)c * 64 + j] ? h[(size_t)c * 64 + j] - h[(size_t)c * 64] : -1);
+            fprintf(f, "\n");
+          }
+          fclose(f);
+        }
+        cudaFree(hp->dbg);
+      }
       cudaFree(P->wg_partial);
       delete P;
       L.tc_plan = nullptr;
@@ -505,6 +783,11 @@ bool tc_dense_bwd(sb_engine*, LayerPlan&, int) { return false; }
 bool tc_conv_fwd(sb_engine* e, LayerPlan& L, int) {
   ConvTcPlan* P = (ConvTcPlan*)L.tc_plan;
   if (!P) return false;
+  if (P->halo_fwd) {
+    conv_halo_kernel<<<P->hfwd_grid, kIgemmThreads, P->hfwd_smem, e->stream>>>(P->map_x_h, P->map_w_fwd, P->hfwd);
+    SB_LAUNCHED();
+    return true;
+  }
   conv_igemm_kernel<<<P->fwd_grid, kIgemmThreads, P->fwd_smem, e->stream>>>(P->map_x_fwd, P->map_w_fwd, P->fwd);
   SB_LAUNCHED();
   return true;
@@ -525,6 +808,11 @@ bool tc_conv_wgrad(sb_engine* e, LayerPlan& L, int) {
 bool tc_conv_dgrad(sb_engine* e, LayerPlan& L, int) {
   ConvTcPlan* P = (ConvTcPlan*)L.tc_plan;
   if (!P || !P->has_dgrad) return false;
+  if (P->halo_dg) {
+    conv_halo_kernel<<<P->hdg_grid, kIgemmThreads, P->hdg_smem, e->stream>>>(P->map_dy_h, P->map_w_dg, P->hdg);
+    SB_LAUNCHED();
+    return true;
+  }
   conv_igemm_kernel<<<P->dg_grid, kIgemmThreads, P->dg_smem, e->stream>>>(P->map_dy_dg, P->map_w_dg, P->dg);
   SB_LAUNCHED();
   return true;
