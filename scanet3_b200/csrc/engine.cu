@@ -423,6 +423,7 @@ static void allocate(sb_engine* e) {
   }
   tc_plan_layers(e);  // tensor-core fast paths (TMA descriptors, padded-grid buffers)
   plan_fusions(e);    // vectorised / fused bandwidth kernels
+  lstm_plan(e);       // LSTM workspaces (saved gate activations for BPTT)
   SB_CUDA(cudaStreamSynchronize(e->stream));
 }
 

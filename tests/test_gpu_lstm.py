@@ -1,0 +1,93 @@
+"""RNN(LSTMCell) on the device against the reference's forward golden (models/layer/RNNLayerSpec.scala:44-79) and against the
+oracle's BPTT (the reference has no LSTM-gradient test; the oracle's BPTT is pinned by finite differences in
+tests/test_oracle_gradcheck.py).  fp32 contractions; tolerances as in test_gpu_parity.py: one op chain rtol 2e-5-class,
+a 64-step recurrence accumulates ~T of them."""
+import numpy as np
+import pytest
+
+import oracle as O
+import scanet3_b200 as S
+from helpers import assert_params_close, build_models
+from test_oracle_goldens import LSTM_GOLD, lstm_gold_params
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+
+
+def synth_series(n, t, f, seed):
+    """min-max scaled series windows like the sunspot data prep (test/Datasets.scala:80-85): features and targets in [0,1]"""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    x = rng.uniform(0.0, 1.0, size=(n, t, f)).astype(f32)
+    y = rng.uniform(0.0, 1.0, size=(n, 1)).astype(f32)
+    return x, y
+
+
+def test_lstm_forward_golden_through_the_engine():
+    e = S.Engine(S.LSTM(2), S.MeanSquaredError, S.SGD(), 1, (3, 1), (2,), device=0)
+    assert set(e.model_param_paths()) == set(lstm_gold_params().keys())
+    e.set_params(lstm_gold_params())
+    y = e.predict(np.array([1, 2, 3], f32).reshape(1, 3, 1))
+    np.testing.assert_allclose(y, np.array([[0.382158, 0.029766]], f32), atol=6e-7)
+    e.close()
+
+
+@pytest.mark.parametrize("units,t,f,batch", [(8, 5, 3, 6), (16, 7, 1, 9), (12, 4, 11, 5), (32, 1, 2, 4)],
+                         ids=["f3", "f1", "f11_gemm_projection", "single_step"])
+def test_lstm_gradients_match_oracle_bptt(units, t, f, batch):
+    om, sm = build_models([("lstm", units), ("dense", 1, "tanh")])
+    x, y = synth_series(batch, t, f, 5)
+    e = S.Engine(sm, S.MeanSquaredError, S.Adam(), batch, (t, f), (1,), device=0)
+    e.init_params()
+    _, mp, _ = O.init_params(om, O.Adam(), (batch, t, f))
+    assert_params_close(e.get_model_params(), mp, 0, 2e-6, "init")  # Orthogonal: host QR, GlorotUniform: bit exact
+    e.set_params(mp)
+    ol, og, _ = O.LossModel(om, O.MeanSquaredError).grad_stateful(x, y, mp)
+    gl, gg = e.compute_grads(x, y)
+    assert abs(gl - float(ol)) <= 2e-5 * abs(float(ol)) + 1e-7
+    for k, v in og.items():
+        np.testing.assert_allclose(gg[k], v, rtol=2e-4, atol=2e-6, err_msg=k)
+    np.testing.assert_allclose(e.predict(x), O.model_forward(om, x, mp)[0], rtol=2e-5, atol=2e-6)
+    e.close()
+
+
+def run_series_trajectory(units, t, f, batch, steps, rate, rtol, atol, loss_rtol, use_graph=True):
+    om, sm = build_models([("lstm", units), ("dense", 1, "tanh")])
+    x, y = synth_series(batch * steps, t, f, 11)
+    e = S.Engine(sm, S.MeanSquaredError, S.Adam(rate), batch, (t, f), (1,), device=0, use_graph=use_graph)
+    e.init_params()
+    oalg = O.Adam(rate)
+    _, mp, op = O.init_params(om, oalg, (batch, t, f))
+    e.set_params(mp)
+    e.init_opt_params()
+    lm = O.LossModel(om, O.MeanSquaredError)
+    for s in range(1, steps + 1):
+        xb, yb = x[(s - 1) * batch:s * batch], y[(s - 1) * batch:s * batch]
+        gl = e.train_step(xb, yb, s)
+        mp, op, ol = O.train_step(lm, oalg, xb, yb, mp, op, s)
+        assert abs(gl - float(ol)) <= loss_rtol * abs(float(ol)) + 1e-7, (s, gl, float(ol))
+    assert_params_close(e.get_model_params(), mp, rtol, atol, f"after {steps} steps")
+    e.close()
+
+
+def test_lstm_small_trajectory_config3_pattern():  # LSTM >> Dense(1, Tanh), MSE, Adam (BASELINE config 3), small
+    run_series_trajectory(units=16, t=10, f=1, batch=32, steps=8, rate=1e-3, rtol=2e-3, atol=3e-5, loss_rtol=1e-4)
+
+
+def test_lstm_config3_full_size_two_steps():  # BASELINE config 3 exactly: LSTM(256), seq len 64, batch 1024, F = 1
+    run_series_trajectory(units=256, t=64, f=1, batch=1024, steps=2, rate=1e-3, rtol=5e-3, atol=1e-4, loss_rtol=5e-4)
+
+
+def test_lstm_resident_epoch_and_graph_determinism():
+    _, sm = build_models([("lstm", 16), ("dense", 1, "tanh")])
+    x, y = synth_series(32 * 3, 6, 2, 2)
+    res = []
+    for use_graph in (True, False):
+        e = S.Engine(sm, S.MeanSquaredError, S.Adam(1e-3), 32, (6, 2), (1,), device=0, use_graph=use_graph)
+        e.init_params()
+        e.upload_dataset(x, y)
+        it, loss = e.train_epoch(0)
+        res.append((it, loss, e.get_model_params()))
+        e.close()
+    assert res[0][:2] == res[1][:2]
+    for k in res[0][2]:
+        assert np.array_equal(res[0][2][k], res[1][2][k]), k
