@@ -497,8 +497,11 @@ static void run_forward(sb_engine* e, int mode) {
     switch (L.d.kind) {
       case SB_LAYER_DENSE: {
         const int M = (int)L.in.d[0], K = (int)L.in.d[1], N = (int)L.out.d[1];
-        if (L.tc_kind && tc_dense_fwd(e, L, li)) break;
         const double db = 4.0 * ((double)M * K + (double)K * N + (double)M * N);
+        if (L.tc_kind) {
+          Prof pr(e, "dense_fwd_tf32_tcgen05", db, 2.0 * M * N * K);
+          if (tc_dense_fwd(e, L, li)) break;
+        }
         if (L.fast_skinny) {
           Prof pr(e, "dense_head_fwd", db, 2.0 * M * N * K);
           e->head_chunks = 0;
@@ -608,10 +611,19 @@ static void run_backward(sb_engine* e) {
     switch (L.d.kind) {
       case SB_LAYER_DENSE: {
         const int M = (int)L.in.d[0], K = (int)L.in.d[1], N = (int)L.out.d[1];
-        if (L.tc_kind && tc_dense_bwd(e, L, li)) break;
         const double db = 4.0 * ((double)M * K + (double)K * N + (double)M * N);
         bool wdone = false, ddone = false;
-        if (L.fast_skinny) {
+        if (L.tc_kind) {
+          {
+            Prof pr(e, "dense_wgrad_tf32_tcgen05", db, 2.0 * M * N * K);
+            wdone = tc_dense_wgrad(e, L, li);
+          }
+          if (L.need_dx && din) {
+            Prof pr(e, "dense_dgrad_tf32_tcgen05", db, 2.0 * M * N * K);
+            ddone = tc_dense_dgrad(e, L, li);
+          }
+        }
+        if (L.fast_skinny && !wdone) {
           const bool dg = L.need_dx && din;
           Prof pr(e, "dense_head_bwd", db + (dg ? 4.0 * M * K : 0.0), (dg ? 4.0 : 2.0) * M * N * K);
           wdone = ddone = dense_head_bwd(in, dout, P(e, L.p_w), G(e, L.p_w), dg ? din : nullptr, M, N, K, s);

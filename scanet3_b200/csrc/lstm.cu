@@ -40,6 +40,10 @@ struct LstmWs {
   float* dwk_cat = nullptr;  // [F, 4U]
   float* db_cat = nullptr;   // [4U]
   float* dx_tm = nullptr;    // [T, B, F] (only when the input gradient is needed)
+  // tcgen05 TF32 plans (SB_PREC_TF32): one plan per contraction serves every time step through the tensor maps' slice coordinate
+  TcGemm* g_fwd = nullptr;   // Z_t = H_{t-1} . Wr_cat           A slice t of h, C slice t of acts
+  TcGemm* g_bwd = nullptr;   // dH_{t-1} = dZ_t . Wr_cat^T       A slice t of acts
+  TcGemm* g_dwr = nullptr;   // dWr_cat = H_prev_all^T . dZ_all  (split-K over T*B)
 };
 
 __device__ __forceinline__ float actf(float x, int act) {
@@ -185,6 +189,12 @@ LstmWs* ws_of(sb_engine* e, LayerPlan& L) {
   w->dwk_cat = dalloc(F * 4 * U);
   w->db_cat = dalloc(4 * U);
   if (L.need_dx) w->dx_tm = dalloc(T * B * F);
+  if (e->train.precision == SB_PREC_TF32 && B * U * 4 * U >= (1 << 22)) {
+    w->g_fwd = tc_gemm_create(0, 1, w->h, (int)T + 1, w->wr_cat, 1, w->acts, (int)T, (int)B, (int)(4 * U), (int)U, 0, nullptr, 0, e->device);
+    w->g_bwd = tc_gemm_create(0, 0, w->acts, (int)T, w->wr_cat, 1, w->dh, 1, (int)B, (int)U, (int)(4 * U), 0, nullptr, 0, e->device);
+    w->g_dwr = tc_gemm_create(1, 1, w->h, 1, w->acts, 1, w->dwr_cat, 1, (int)U, (int)(4 * U), (int)(T * B), 1, e->ws, e->ws_floats,
+                              e->device);
+  }
   L.lstm = w;
   return w;
 }
@@ -238,7 +248,10 @@ void lstm_forward(sb_engine* e, LayerPlan& L, int) {
     float* h_t = w->h + (long long)(t + 1) * BU;
     float* c_t = w->c + (long long)t * BU;
     const float* c_prev = t ? w->c + (long long)(t - 1) * BU : nullptr;
-    if (t > 0) gemm_nn(h_prev, w->wr_cat, z, B, 4 * U, U, e->ws, e->ws_floats, s);  // h_{-1} = 0: no product at t = 0
+    if (t > 0) {  // h_{-1} = 0: no product at t = 0
+      if (w->g_fwd) tc_gemm_run(w->g_fwd, t, 0, t, s);
+      else gemm_nn(h_prev, w->wr_cat, z, B, 4 * U, U, e->ws, e->ws_floats, s);
+    }
     const float* x_t = w->x_tm + (long long)t * B * F;
     const float* xw_t = w->xw ? w->xw + (long long)t * B * 4 * U : nullptr;
     const int first = t == 0;
@@ -272,12 +285,14 @@ void lstm_backward(sb_engine* e, LayerPlan& L, int) {
     lstm_gates_bwd_kernel<<<ew_grid(BU), 256, 0, s>>>(a, c_t, c_prev, dh, w->dc, B, U, t == 0, t == T - 1, act, ract);
     SB_LAUNCHED();
     if (t > 0) {
-      gemm_nt(a, w->wr_cat, w->dh, B, U, 4 * U, e->ws, e->ws_floats, s);  // dH_{t-1} = dZ_t . Wr_cat^T
+      if (w->g_bwd) tc_gemm_run(w->g_bwd, t, 0, 0, s);  // dH_{t-1} = dZ_t . Wr_cat^T
+      else gemm_nt(a, w->wr_cat, w->dh, B, U, 4 * U, e->ws, e->ws_floats, s);
       dh = w->dh;
     }
   }
   // weight gradients over the whole sequence (acts now holds dZ_all[T*B, 4U]; h slots 0..T-1 are H_prev_all[T*B, U])
-  gemm_tn(w->h, w->acts, w->dwr_cat, U, 4 * U, T * B, e->ws, e->ws_floats, s);
+  if (w->g_dwr) tc_gemm_run(w->g_dwr, 0, 0, 0, s);
+  else gemm_tn(w->h, w->acts, w->dwr_cat, U, 4 * U, T * B, e->ws, e->ws_floats, s);
   gemm_tn(w->x_tm, w->acts, w->dwk_cat, F, 4 * U, T * B, e->ws, e->ws_floats, s);
   lstm_unpack_kernel<<<ew_grid((long long)U * 4 * U), 256, 0, s>>>(w->dwr_cat, gate_ptrs(e, L, 1, true), U, U);
   SB_LAUNCHED();
@@ -303,6 +318,7 @@ void lstm_free(sb_engine* e) {
     for (float* p : {w->wr_cat, w->wk_cat, w->b_cat, w->x_tm, w->acts, w->c, w->h, w->xw, w->dh, w->dc, w->dwr_cat, w->dwk_cat,
                      w->db_cat, w->dx_tm})
       cudaFree(p);
+    tc_gemm_destroy(w->g_fwd); tc_gemm_destroy(w->g_bwd); tc_gemm_destroy(w->g_dwr);
     delete w;
     L.lstm = nullptr;
   }

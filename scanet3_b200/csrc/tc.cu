@@ -563,6 +563,12 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
 // =====================================================================================================================
 // per-layer plans
 // =====================================================================================================================
+struct DenseTcPlan {
+  TcGemm* fwd = nullptr;    // Z = X . W (+bias, activation in the epilogue)
+  TcGemm* dgrad = nullptr;  // dX = G . W^T
+  TcGemm* wgrad = nullptr;  // dW = X^T . G
+};
+
 struct ConvTcPlan {
   CUtensorMap map_x_fwd, map_w_fwd;    // fprop: A = X boxes, B = filter (MN-major)
   CUtensorMap map_dy_dg, map_w_dg;     // dgrad: A = dY boxes, B = filter (K-major)
@@ -637,6 +643,47 @@ void tc_plan_layers(sb_engine* e) {
   SB_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device));
   for (size_t li = 0; li < e->L.size(); ++li) {
     LayerPlan& L = e->L[li];
+    if (L.d.kind == SB_LAYER_DENSE) {
+      // MatMul and its gradients on tcgen05 when the GEMM is big enough to matter and the strides are 16-byte multiples
+      const int M = (int)L.in.d[0], K = (int)L.in.d[1], N = (int)L.out.d[1];
+      if (N < 32 || K < 32 || M < 32 || (double)M * N * K < (double)(1 << 22)) continue;
+      float* x = e->acts[L.buf_in];
+      float* z = e->acts[L.buf_out];
+      float* dz = e->dacts[L.buf_out];
+      float* dx = e->dacts[L.buf_in];
+      float* w = e->arena + e->params[L.p_w].offset;
+      float* dw = e->grads + e->params[L.p_w].offset;
+      DenseTcPlan* D = new DenseTcPlan();
+      D->fwd = tc_gemm_create(0, 1, x, 1, w, 1, z, 1, M, N, K, 0, nullptr, 0, e->device);
+      D->wgrad = tc_gemm_create(1, 1, x, 1, dz, 1, dw, 1, K, N, M, 1, e->ws, e->ws_floats, e->device);
+      const bool want_dgrad = L.need_dx && dx != nullptr;
+      if (want_dgrad) D->dgrad = tc_gemm_create(0, 0, dz, 1, w, 1, dx, 1, M, K, N, 1, e->ws, e->ws_floats, e->device);
+      if (!D->fwd || !D->wgrad || (want_dgrad && !D->dgrad)) {
+        tc_gemm_destroy(D->fwd); tc_gemm_destroy(D->wgrad); tc_gemm_destroy(D->dgrad);
+        delete D;
+        continue;
+      }
+      // fold the following in-place Bias and (non-softmax) Activate into the forward epilogue
+      const float* bias = nullptr;
+      int act = 0;
+      float thr = 0.f;
+      size_t nx = li + 1;
+      if (nx < e->L.size() && e->L[nx].d.kind == SB_LAYER_BIAS && e->L[nx].inplace) {
+        bias = e->arena + e->params[e->L[nx].p_w].offset;
+        e->L[nx].skip_fwd = true;
+        ++nx;
+      }
+      if (nx < e->L.size() && e->L[nx].d.kind == SB_LAYER_ACTIVATE && e->L[nx].inplace && e->L[nx].d.activation != SB_ACT_SOFTMAX &&
+          e->L[nx].d.activation != SB_ACT_IDENTITY && (nx == li + 1 || bias)) {
+        act = e->L[nx].d.activation;
+        thr = e->L[nx].d.relu_threshold;
+        e->L[nx].skip_fwd = true;
+      }
+      tc_gemm_set_epilogue(D->fwd, bias, act, thr);
+      L.tc_kind = 2;
+      L.tc_plan = D;
+      continue;
+    }
     if (L.d.kind != SB_LAYER_CONV2D || !conv_fits(L.cg)) continue;
     const ConvGeom& g = L.cg;
     ConvTcPlan* P = new ConvTcPlan();
@@ -752,6 +799,13 @@ void tc_plan_layers(sb_engine* e) {
 
 void tc_free_layers(sb_engine* e) {
   for (auto& L : e->L) {
+    if (L.tc_plan && L.tc_kind == 2) {
+      DenseTcPlan* D = (DenseTcPlan*)L.tc_plan;
+      tc_gemm_destroy(D->fwd); tc_gemm_destroy(D->wgrad); tc_gemm_destroy(D->dgrad);
+      delete D;
+      L.tc_plan = nullptr;
+      continue;
+    }
     if (L.tc_plan) {
       ConvTcPlan* P = (ConvTcPlan*)L.tc_plan;
       for (HaloParams* hp : {&P->hfwd, &P->hdg}) {
@@ -777,12 +831,25 @@ void tc_free_layers(sb_engine* e) {
 
 void tc_params_changed(sb_engine*) {}  // the kernels read the filter straight from the arena
 
-bool tc_dense_fwd(sb_engine*, LayerPlan&, int) { return false; }
-bool tc_dense_bwd(sb_engine*, LayerPlan&, int) { return false; }
+bool tc_dense_fwd(sb_engine* e, LayerPlan& L, int) {
+  if (L.tc_kind != 2) return false;
+  tc_gemm_run(((DenseTcPlan*)L.tc_plan)->fwd, 0, 0, 0, e->stream);
+  return true;
+}
+bool tc_dense_wgrad(sb_engine* e, LayerPlan& L, int) {
+  if (L.tc_kind != 2) return false;
+  tc_gemm_run(((DenseTcPlan*)L.tc_plan)->wgrad, 0, 0, 0, e->stream);
+  return true;
+}
+bool tc_dense_dgrad(sb_engine* e, LayerPlan& L, int) {
+  if (L.tc_kind != 2 || !((DenseTcPlan*)L.tc_plan)->dgrad) return false;
+  tc_gemm_run(((DenseTcPlan*)L.tc_plan)->dgrad, 0, 0, 0, e->stream);
+  return true;
+}
 
 bool tc_conv_fwd(sb_engine* e, LayerPlan& L, int) {
   ConvTcPlan* P = (ConvTcPlan*)L.tc_plan;
-  if (!P) return false;
+  if (!P || L.tc_kind != 1) return false;
   if (P->halo_fwd) {
     conv_halo_kernel<<<P->hfwd_grid, kIgemmThreads, P->hfwd_smem, e->stream>>>(P->map_x_h, P->map_w_fwd, P->hfwd);
     SB_LAUNCHED();

@@ -131,3 +131,85 @@ def test_tf32_resident_epoch_runs_in_a_cuda_graph_and_matches_eager():
     assert res[0][:4] == res[1][:4]  # deterministic: fixed split-K / reduction orders
     for k in res[0][4]:
         assert np.array_equal(res[0][4][k], res[1][4][k]), k
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Dense (MatMul fwd / dgrad / wgrad) and the LSTM contractions on the tcgen05 GEMM
+# ---------------------------------------------------------------------------------------------------------------
+DENSE_STACKS = [
+    # (name, spec, batch, in_features): smooth activations pin the kernels; ragged sizes exercise the TMA-clipped edges
+    ("wide_mlp_small", [("dense", 256, "sigmoid"), ("dense", 128, "tanh"), ("dense", 10, "softmax")], 256, 784),
+    ("ragged", [("dense", 72, "tanh"), ("dense", 200, "sigmoid"), ("dense", 10, "softmax")], 520, 300),
+    ("relu_chain", [("dense", 512, "relu"), ("dense", 512, "relu"), ("dense", 10, "softmax")], 384, 256),
+    ("split_k_wgrad", [("dense", 64, "tanh"), ("dense", 10, "softmax")], 4096, 64),
+]
+
+
+@pytest.mark.parametrize("name,spec,batch,nin", DENSE_STACKS, ids=[c[0] for c in DENSE_STACKS])
+def test_tf32_dense_forward_and_gradients(name, spec, batch, nin):
+    om, e32, etc = engines(spec, "cce", batch, (nin,), 10)
+    x, y = synth_classification(batch, (nin,), 10, 33)
+    x = (x - 0.5).astype(f32)  # centred features: no catastrophic common-mode in the dot products
+    p32, ptc = e32.predict(x), etc.predict(x)
+    assert rel_to_max(ptc, p32) < 4e-3
+    l32, g32 = e32.compute_grads(x, y)
+    ltc, gtc = etc.compute_grads(x, y)
+    assert abs(ltc - l32) <= 2e-3 * abs(l32)
+    relu_net = any(it[0] == "dense" and it[2] == "relu" for it in spec)
+    for k in g32:
+        if relu_net:
+            a, b = gtc[k].astype(np.float64).ravel(), g32[k].astype(np.float64).ravel()
+            cos = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-300))
+            assert cos > 0.995, (k, cos)
+        else:
+            assert rel_to_max(gtc[k], g32[k]) < 6e-3, k
+    etc.profile_enable(True)
+    etc.compute_grads(x, y)
+    names = [r["name"] for r in etc.profile()]
+    etc.profile_enable(False)
+    assert any(n.startswith("dense_") and "tcgen05" in n for n in names), names
+    e32.close()
+    etc.close()
+
+
+def test_tf32_wide_mlp_trajectory_config4_pattern():  # BASELINE config 4 pattern: Dense(ReLU) x n >> Dense(10, Softmax), Adam
+    spec = [("dense", 512, "relu"), ("dense", 512, "relu"), ("dense", 10, "softmax")]
+    om, sm = build_models(spec)
+    batch, steps, rate = 512, 5, 0.001
+    x, y = synth_classification(batch * steps, (784,), 10, 4)
+    e = S.Engine(sm, S.CategoricalCrossentropy, S.Adam(rate), batch, (784,), (10,), device=0, precision=S.PREC_TF32)
+    e.init_params()
+    oalg = O.Adam(rate)
+    _, mp, op = O.init_params(om, oalg, (batch, 784))
+    lm = O.LossModel(om, O.CategoricalCrossentropy)
+    for t in range(1, steps + 1):
+        xb, yb = x[(t - 1) * batch:t * batch], y[(t - 1) * batch:t * batch]
+        gl = e.train_step(xb, yb, t)
+        mp, op, ol = O.train_step(lm, oalg, xb, yb, mp, op, t)
+        assert abs(gl - float(ol)) <= 3e-3 * abs(float(ol)), (t, gl, float(ol))
+    got = e.get_model_params()
+    for k, v in mp.items():
+        err = np.abs(got[k] - v)
+        assert float(np.max(err)) <= 3 * steps * rate, k
+        assert float(np.mean(err)) <= 0.05 * steps * rate, k
+    e.close()
+
+
+def test_tf32_lstm_matches_fp32_engine():
+    spec = [("lstm", 64), ("dense", 1, "tanh")]
+    om, sm = build_models(spec)
+    batch, t, f = 256, 12, 1
+    rng = np.random.Generator(np.random.PCG64(8))
+    x = rng.uniform(0, 1, size=(batch, t, f)).astype(f32)
+    y = rng.uniform(0, 1, size=(batch, 1)).astype(f32)
+    res = []
+    for prec in (S.PREC_FP32, S.PREC_TF32):
+        e = S.Engine(sm, S.MeanSquaredError, S.Adam(1e-3), batch, (t, f), (1,), device=0, precision=prec)
+        e.init_params()
+        res.append((e.predict(x),) + e.compute_grads(x, y))
+        e.close()
+    (p32, l32, g32), (ptc, ltc, gtc) = res
+    assert rel_to_max(ptc, p32) < 4e-3
+    assert abs(ltc - l32) <= 4e-3 * abs(l32)
+    for k in g32:
+        assert rel_to_max(gtc[k], g32[k]) < 1e-2, k
