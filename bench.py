@@ -164,6 +164,13 @@ def run_ours(args):
 
     state = {"iter": 0, "batch": 0}
 
+    def epoch_average():
+        """epoch boundary: the fused P2P kernel synchronises the ranks on the device (flag barriers over NVLink) and combines
+        the losses there, so nothing here blocks the host; the NCCL arm keeps its host-side barriers."""
+        if coll == N.COLL_P2P:
+            return avg.average_async(steps_per_epoch)
+        return avg.average(0.0, steps_per_epoch)[1]
+
     def run_steps(n):
         """n resident steps; epoch boundaries trigger the model averaging (weak scaling: K steps per rank)."""
         done = 0
@@ -176,7 +183,7 @@ def run_ours(args):
             if state["batch"] == steps_per_epoch:
                 state["batch"] = 0
                 if avg is not None:
-                    _, total = avg.average(0.0, steps_per_epoch)
+                    total = epoch_average()
                     state["iter"] += total - steps_per_epoch  # the step counter is global (Optimizer.scala:88)
 
     def barrier():
@@ -221,7 +228,7 @@ def run_ours(args):
             if state["batch"] == steps_per_epoch:
                 state["batch"] = 0
                 if avg is not None:
-                    _, total = avg.average(0.0, steps_per_epoch)
+                    total = epoch_average()
                     state["iter"] += total - steps_per_epoch
     run_steps_e2e(max(args.warmup, 3), 0)
     barrier()

@@ -204,6 +204,8 @@ int sb_predict(sb_engine* e, const float* x, float* out, size_t n_out);
 int sb_compute_grads(sb_engine* e, const float* x, const float* y, float* loss_out);
 int sb_grad_get(sb_engine* e, const char* weight_path, float* host, size_t n);
 int sb_sync(sb_engine* e);
+/* loss of the latest forward (or the combined loss after sb_group_average_device): one stream sync + 4-byte D2H */
+int sb_read_loss(sb_engine* e, float* loss_out);
 
 /* ---- raw access for host plumbing (torch.distributed over NCCL, timing on the right stream) ---- */
 /* device pointer + float count of the averaged arena region [model params | optimizer state] */
@@ -244,6 +246,12 @@ void sb_group_destroy(sb_group* g);
 int sb_group_create_ipc(sb_engine* self, int rank, int k, const void* handles, int avg_mode,
                         const float* weights_or_null, sb_group** out);
 int sb_group_average_local(sb_group* g);
+/* Device-synchronised variant for IPC groups (one process per GPU, every rank on its OWN GPU): ONE kernel per rank does
+ * a flag barrier over NVLink peer memory (all epochs done), the fused reduce-scatter + all-gather of the arena, the
+ * combination of the k last-batch losses (same weights and order; result replaces this engine's loss, read it with
+ * sb_read_loss) and a second flag barrier (all slices stored).  No host synchronisation: the call only enqueues.
+ * `epoch` must increase by one per call on every rank. */
+int sb_group_average_device(sb_group* g, uint64_t epoch);
 /* effective weights the group applies (length k) */
 int sb_group_weights(const sb_group* g, float* weights_out);
 /* the Spark 3.3.1 treeReduce(depth=2) weight vector for k partitions in ascending completion order */

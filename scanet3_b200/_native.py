@@ -92,6 +92,7 @@ PROTOTYPES = {
     "sb_compute_grads": (C.c_int, [_P, _P, _P, _FP]),
     "sb_grad_get": (C.c_int, [_P, C.c_char_p, _P, C.c_size_t]),
     "sb_sync": (C.c_int, [_P]),
+    "sb_read_loss": (C.c_int, [_P, _FP]),
     "sb_arena": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
     "sb_stream": (C.c_int, [_P, C.POINTER(_P)]),
     "sb_arena_scale": (C.c_int, [_P, C.c_float]),
@@ -102,6 +103,7 @@ PROTOTYPES = {
     "sb_group_destroy": (None, [_P]),
     "sb_group_create_ipc": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _FP, C.POINTER(_P)]),
     "sb_group_average_local": (C.c_int, [_P]),
+    "sb_group_average_device": (C.c_int, [_P, C.c_uint64]),
     "sb_group_weights": (C.c_int, [_P, _FP]),
     "sb_spark_chain_weights": (C.c_int, [C.c_int, _FP]),
     "sb_profile_enable": (C.c_int, [_P, C.c_int]),

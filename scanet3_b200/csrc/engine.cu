@@ -391,8 +391,9 @@ static void plan_fusions(sb_engine* e) {
 static void allocate(sb_engine* e) {
   SB_CUDA(cudaSetDevice(e->device));
   SB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-  e->arena = dmalloc_floats(e->arena_floats);
-  SB_CUDA(cudaMemsetAsync(e->arena, 0, (size_t)e->arena_floats * 4, e->stream));
+  // the arena allocation carries a tail of cross-GPU flags / scalars behind the tensors (one IPC handle maps both)
+  e->arena = dmalloc_floats(e->arena_floats + sb::kArenaTailFloats);
+  SB_CUDA(cudaMemsetAsync(e->arena, 0, (size_t)(e->arena_floats + sb::kArenaTailFloats) * 4, e->stream));
   e->grads = dmalloc_floats(e->nW);
   SB_CUDA(cudaMemsetAsync(e->grads, 0, (size_t)std::max<int64_t>(e->nW, 32) * 4, e->stream));
   const int nb = (int)e->act_numel.size();
@@ -1178,6 +1179,15 @@ extern "C" int sb_grad_get(sb_engine* e, const char* path, float* host, size_t n
   DeviceGuard dg(e->device);
   SB_CUDA(cudaMemcpyAsync(host, e->grads + p.offset, n * 4, cudaMemcpyDeviceToHost, e->stream));
   SB_CUDA(cudaStreamSynchronize(e->stream));
+  SB_API_END
+}
+
+extern "C" int sb_read_loss(sb_engine* e, float* loss_out) {
+  SB_API_BEGIN
+  need_device(e);
+  if (!loss_out) SB_FAIL(SB_ERR_INVALID_ARG, "null argument");
+  DeviceGuard dg(e->device);
+  *loss_out = read_loss(e);
   SB_API_END
 }
 

@@ -11,6 +11,8 @@
 
 namespace sb {
 
+constexpr int64_t kArenaTailFloats = 1024;  // flags + scalars of the device-synchronised averaging (group.cu)
+
 struct Shape {
   int rank = 0;
   int64_t d[5] = {0, 0, 0, 0, 0};

@@ -86,6 +86,97 @@ __global__ void __launch_bounds__(256) p2p_average_kernel(PeerSet ps, long long 
   }
 }
 
+// ---- device-synchronised variant: flag barrier + reduce + loss combine + flag barrier in ONE kernel per rank ----
+// Tail of every arena allocation (kArenaTailFloats floats behind the tensors), written by peers over NVLink:
+//   u64 arrive[8] | u64 done[8] | float loss[8]          (slot q is written by rank q)
+struct SyncArgs {
+  long long tail_off;  // floats from the arena base
+  unsigned long long epoch;
+  int rank;
+  float* my_loss;       // this engine's StepState.loss: read before the barrier, replaced by the combined loss
+  unsigned int* ticket; // local CTA-completion counter (zero between launches)
+};
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// bounded: a rank that never arrives traps this kernel (launch error) instead of hanging the GPU
+__device__ __forceinline__ void wait_flag(const unsigned long long* p, unsigned long long epoch) {
+  for (unsigned long long spins = 0; ld_acquire_sys(p) < epoch; ++spins) {
+    __nanosleep(200);
+    if (spins > (1ull << 26)) __trap();  // ~15 s
+  }
+}
+__global__ void __launch_bounds__(256) p2p_average_sync_kernel(PeerSet ps, long long lo4, long long hi4, SyncArgs a) {
+  unsigned long long* my_tail = reinterpret_cast<unsigned long long*>(ps.ptr[a.rank] + a.tail_off);
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0) {
+      const float l = *a.my_loss;
+      for (int q = 0; q < ps.k; ++q) (ps.ptr[q] + a.tail_off + 32)[a.rank] = l;
+      __threadfence_system();
+      for (int q = 0; q < ps.k; ++q)
+        st_release_sys(reinterpret_cast<unsigned long long*>(ps.ptr[q] + a.tail_off) + a.rank, a.epoch);
+    }
+    for (int q = 0; q < ps.k; ++q) wait_flag(my_tail + q, a.epoch);  // every rank finished its epoch
+    if (blockIdx.x == 0) {
+      // loss: the same weights in the same order (Optimizer.scala:221)
+      const float* ls = ps.ptr[a.rank] + a.tail_off + 32;
+      float tot = 0.f;
+      for (int gi = 0; gi < ps.n_groups; ++gi) {
+        float acc = 0.f;
+        bool first = true;
+        for (int q = gi; q < ps.k; q += ps.n_groups) {
+          const float t = __fmul_rn(__ldcv(ls + q), ps.w[q]);
+          acc = first ? t : __fadd_rn(acc, t);
+          first = false;
+        }
+        tot = gi == 0 ? acc : __fadd_rn(tot, acc);
+      }
+      *a.my_loss = tot;
+    }
+  }
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = lo4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi4; i += stride) {
+    float4 v[kMaxRanks];
+#pragma unroll
+    for (int q = 0; q < kMaxRanks; ++q)
+      if (q < ps.k) v[q] = __ldcv(reinterpret_cast<const float4*>(ps.ptr[q]) + i);
+    float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int gi = 0; gi < ps.n_groups; ++gi) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      bool first = true;
+#pragma unroll
+      for (int q = 0; q < kMaxRanks; ++q) {
+        if (q >= ps.k || (q % ps.n_groups) != gi) continue;
+        const float w = ps.w[q];
+        float4 t = make_float4(__fmul_rn(v[q].x, w), __fmul_rn(v[q].y, w), __fmul_rn(v[q].z, w), __fmul_rn(v[q].w, w));
+        if (first) { acc = t; first = false; }
+        else { acc.x = __fadd_rn(acc.x, t.x); acc.y = __fadd_rn(acc.y, t.y); acc.z = __fadd_rn(acc.z, t.z); acc.w = __fadd_rn(acc.w, t.w); }
+      }
+      if (gi == 0) tot = acc;
+      else { tot.x = __fadd_rn(tot.x, acc.x); tot.y = __fadd_rn(tot.y, acc.y); tot.z = __fadd_rn(tot.z, acc.z); tot.w = __fadd_rn(tot.w, acc.w); }
+    }
+#pragma unroll
+    for (int q = 0; q < kMaxRanks; ++q)
+      if (q < ps.k) reinterpret_cast<float4*>(ps.ptr[q])[i] = tot;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(a.ticket, 1u) == gridDim.x - 1) {  // last CTA of this rank: its slice is stored everywhere
+      *a.ticket = 0;
+      for (int q = 0; q < ps.k; ++q)
+        st_release_sys(reinterpret_cast<unsigned long long*>(ps.ptr[q] + a.tail_off) + 8 + a.rank, a.epoch);
+      for (int q = 0; q < ps.k; ++q) wait_flag(my_tail + 8 + q, a.epoch);  // every slice of MY arena has landed
+    }
+  }
+}
+
 // ---- Spark 3.3.1 RDD.treeReduce(f, depth = 2) shape under ascending completion order ----
 static void chain_weights(int n, std::vector<double>& w) {
   w.assign(n, 1.0);
@@ -178,6 +269,7 @@ struct sb_group {
   int n_groups = 1;
   PeerSet ps[kMaxRanks];  // per local rank: peer pointers as seen from that device
   std::vector<void*> ipc_opened;
+  unsigned int* ticket = nullptr;  // device counter of the device-synchronised kernel
   NcclApi nccl;
   std::vector<ncclComm_t> comms;
 };
@@ -300,6 +392,35 @@ extern "C" int sb_group_average_local(sb_group* g) {
   SB_API_END
 }
 
+extern "C" int sb_group_average_device(sb_group* g, uint64_t epoch) {
+  SB_API_BEGIN
+  if (!g || g->rank < 0) SB_FAIL(SB_ERR_INVALID_ARG, "not an IPC group");
+  if (g->k == 1) return SB_OK;
+  sb_engine* e = g->es[g->rank];
+  SB_CUDA(cudaSetDevice(e->device));
+  if (!g->ticket) {
+    SB_CUDA(cudaMalloc((void**)&g->ticket, 64));
+    SB_CUDA(cudaMemsetAsync(g->ticket, 0, 64, e->stream));
+  }
+  const long long n4 = e->arena_floats / 4;
+  const long long per = (n4 + g->k - 1) / g->k;
+  const long long lo = per * g->rank, hi = std::min(n4, per * (g->rank + 1));
+  // every CTA polls flags, so the whole grid must be co-resident: <= 4 CTAs of 256 threads per SM
+  int blocks = (int)std::min<long long>(std::max<long long>((hi - lo + 255) / 256, 1), (long long)kNumSMs * 4);
+  SyncArgs a;
+  a.tail_off = e->arena_floats;
+  a.epoch = epoch;
+  a.rank = g->rank;
+  a.my_loss = &e->st->loss;
+  a.ticket = g->ticket;
+  p2p_average_sync_kernel<<<blocks, 256, 0, e->stream>>>(g->ps[g->rank], lo, hi, a);
+  SB_LAUNCHED();
+  e->launches += 1;
+  int rc = sb_reset_unaggregated(e);  // aggregation == None tensors are re-initialised (Optimizer.scala:209)
+  if (rc != SB_OK) return rc;
+  SB_API_END
+}
+
 extern "C" int sb_group_average(sb_group* g, float* loss_inout, int64_t* iterations_inout) {
   SB_API_BEGIN
   if (!g || g->rank >= 0) SB_FAIL(SB_ERR_INVALID_ARG, "single-process group required");
@@ -371,6 +492,7 @@ extern "C" int sb_group_weights(const sb_group* g, float* weights_out) {
 extern "C" void sb_group_destroy(sb_group* g) {
   if (!g) return;
   for (void* p : g->ipc_opened) cudaIpcCloseMemHandle(p);
+  if (g->ticket) cudaFree(g->ticket);
   if (g->nccl.CommDestroy)
     for (ncclComm_t c : g->comms)
       if (c) g->nccl.CommDestroy(c);

@@ -104,9 +104,14 @@ class RankAverager:
     """Averages this rank's engine arena with its peers' at an epoch boundary."""
 
     def __init__(self, engine, avg_mode: int = N.AVG_SPARK_CHAIN, collective: int = N.COLL_P2P,
-                 weights: Optional[Sequence[float]] = None):
+                 weights: Optional[Sequence[float]] = None, device_sync: bool = True):
         import torch.distributed as dist
         self.engine, self.collective = engine, collective
+        # device_sync: the cross-rank barriers and the loss combination run INSIDE the averaging kernel (flags over NVLink
+        # peer memory), so an epoch boundary costs one kernel and no host collective.  Needs every rank on its own GPU.
+        self.device_sync = device_sync
+        self._epoch = 0
+        self._iters_cache = None
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.weights, self.n_groups = averaging_weights(self.world, avg_mode, weights)
         self._g = None
@@ -130,6 +135,8 @@ class RankAverager:
         import torch.distributed as dist
         if self.world == 1:
             return loss, iterations
+        if self._g is not None and self.device_sync:
+            return self._average_device(iterations)
         self.engine.sync()  # this rank's epoch is done
         if self._g is not None:
             dist.barrier()  # every rank's epoch is done: peers' arenas are final
@@ -142,7 +149,25 @@ class RankAverager:
         self.engine.reset_unaggregated()
         return combine_scalars(loss, iterations, self.weights, self.n_groups)
 
+    def average_async(self, iterations: int) -> int:
+        """Enqueue the device-synchronised averaging; returns the summed iteration count.  The combined loss stays on the
+        device (engine.read_loss()).  The per-rank iteration counts are exchanged once: a rank's shard (hence its number of
+        full batches per epoch) does not change between epochs."""
+        import torch.distributed as dist
+        if self._iters_cache is None or self._iters_cache[0] != int(iterations):
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, int(iterations))
+            self._iters_cache = (int(iterations), sum(gathered))
+        self._epoch += 1
+        N.check(N.lib().sb_group_average_device(self._g, self._epoch))
+        return self._iters_cache[1]
+
+    def _average_device(self, iterations: int) -> Tuple[float, int]:
+        total = self.average_async(iterations)
+        return self.engine.read_loss(), total
+
     def close(self):
         if self._g is not None:
+            self.engine.sync()
             N.lib().sb_group_destroy(self._g)
             self._g = None

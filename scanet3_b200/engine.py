@@ -188,6 +188,11 @@ class Engine:
             grads[p] = g
         return loss.value, grads
 
+    def read_loss(self) -> float:
+        out = C.c_float()
+        N.check(self._lib.sb_read_loss(self._h, C.byref(out)))
+        return float(out.value)
+
     def sync(self):
         N.check(self._lib.sb_sync(self._h))
 
