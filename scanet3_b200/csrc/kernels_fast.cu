@@ -173,13 +173,13 @@ __device__ __forceinline__ void acc_if(float4& acc, const Idx4& k, int pos, cons
 template <bool RELU>
 __global__ void __launch_bounds__(256) pool22_bwd_strip_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                float* __restrict__ dx, PoolGeom g, float thr, int seg_len,
-                                                               long long n_threads) {
+                                                               int segs, long long n_threads) {
   const int C4 = g.C >> 2;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_threads) return;
   const int c4 = (int)(i % C4);
   long long t = i / C4;
-  const int seg = (int)(t % kPoolSegs); t /= kPoolSegs;
+  const int seg = (int)(t % segs); t /= segs;
   const int h = (int)(t % g.H);
   const int b = (int)(t / g.H);
   const int w0 = seg * seg_len;
@@ -239,10 +239,22 @@ __global__ void __launch_bounds__(256) pool22_bwd_strip_kernel(const float* __re
 }
 void pool_max_bwd_v4(const float* x, const float* dy, float* dx, const PoolGeom& g, int relu, float thr, cudaStream_t s) {
   if (pool_is_22s1(g)) {
-    const long long nt = (long long)g.N * g.H * kPoolSegs * (g.C / 4);
-    const int seg_len = (g.W + kPoolSegs - 1) / kPoolSegs;
-    if (relu) pool22_bwd_strip_kernel<true><<<(int)((nt + 255) / 256), 256, 0, s>>>(x, dy, dx, g, thr, seg_len, nt);
-    else pool22_bwd_strip_kernel<false><<<(int)((nt + 255) / 256), 256, 0, s>>>(x, dy, dx, g, 0.f, seg_len, nt);
+    // segments per row: cost ~ whole waves x (columns per thread + 1 prologue column); a wave = what 148 SMs hold at the
+    // kernel's register footprint (5 CTAs of 128 threads)
+    const long long wave = (long long)kNumSMs * 5 * 128;
+    int best_segs = 1;
+    double best = 1e30;
+    for (int segs = 1; segs <= 8; ++segs) {
+      const int len = (g.W + segs - 1) / segs;
+      if ((segs - 1) * len >= g.W) continue;
+      const long long nt = (long long)g.N * g.H * segs * (g.C / 4);
+      const double cost = (double)((nt + wave - 1) / wave) * (len + 1.5);
+      if (cost < best) { best = cost; best_segs = segs; }
+    }
+    const int seg_len = (g.W + best_segs - 1) / best_segs;
+    const long long nt = (long long)g.N * g.H * best_segs * (g.C / 4);
+    if (relu) pool22_bwd_strip_kernel<true><<<(int)((nt + 127) / 128), 128, 0, s>>>(x, dy, dx, g, thr, seg_len, best_segs, nt);
+    else pool22_bwd_strip_kernel<false><<<(int)((nt + 127) / 128), 128, 0, s>>>(x, dy, dx, g, 0.f, seg_len, best_segs, nt);
     SB_LAUNCHED();
     return;
   }
@@ -289,7 +301,80 @@ __global__ void __launch_bounds__(256) conv_smallk_fwd_kernel(const float* __res
     st4(y + i * 4, acc);
   }
 }
+// Specialised forward for the filter shapes the first layer of the BASELINE CNNs uses (stride 1): a thread owns 4 output
+// channels x PW consecutive output pixels of one row, so the input patch and the filter slab (shared memory) are each read once
+// for PW pixels and every loop is fully unrolled.
+template <int KH, int KW, int CIN, int PW>
+__global__ void __launch_bounds__(256) conv_smallk_fwd_tile_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                   float* __restrict__ y, ConvGeom g, int relu, float thr,
+                                                                   int segs, long long n_threads) {
+  constexpr int K = KH * KW * CIN;
+  const int C4 = g.Cout >> 2;
+  extern __shared__ __align__(16) float swt[];  // filter [K][Cout]
+  for (int i = threadIdx.x; i < K * g.Cout; i += blockDim.x) swt[i] = w[i];
+  __syncthreads();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_threads) return;
+  const int c4 = (int)(i % C4);
+  long long t = i / C4;
+  const int seg = (int)(t % segs); t /= segs;
+  const int oh = (int)(t % g.OH);
+  const int b = (int)(t / g.OH);
+  const int ow0 = seg * PW;
+  float4 acc[PW];
+#pragma unroll
+  for (int p = 0; p < PW; ++p) acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int a = 0; a < KH; ++a) {
+    const int ih = oh + a - g.PT;
+    const bool row_ok = ih >= 0 && ih < g.H;
+    const float* xr = x + ((long long)b * g.H + (row_ok ? ih : 0)) * g.W * CIN;
+    float xv[(PW + KW - 1) * CIN];
+#pragma unroll
+    for (int q = 0; q < PW + KW - 1; ++q) {
+      const int iw = ow0 + q - g.PL;
+      const bool ok = row_ok && iw >= 0 && iw < g.W;
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) xv[q * CIN + ci] = ok ? __ldg(xr + (long long)iw * CIN + ci) : 0.f;
+    }
+#pragma unroll
+    for (int bb = 0; bb < KW; ++bb)
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) {
+        const float4 wv = *reinterpret_cast<const float4*>(&swt[((a * KW + bb) * CIN + ci) * g.Cout + c4 * 4]);
+#pragma unroll
+        for (int p = 0; p < PW; ++p) {
+          const float v = xv[(p + bb) * CIN + ci];
+          acc[p].x = fmaf(v, wv.x, acc[p].x); acc[p].y = fmaf(v, wv.y, acc[p].y);
+          acc[p].z = fmaf(v, wv.z, acc[p].z); acc[p].w = fmaf(v, wv.w, acc[p].w);
+        }
+      }
+  }
+  float* yo = y + (((long long)b * g.OH + oh) * g.OW + ow0) * g.Cout + c4 * 4;
+#pragma unroll
+  for (int p = 0; p < PW; ++p) {
+    if (ow0 + p >= g.OW) break;
+    float4 o = acc[p];
+    if (relu) { o.x = fmaxf(thr, o.x); o.y = fmaxf(thr, o.y); o.z = fmaxf(thr, o.z); o.w = fmaxf(thr, o.w); }
+    st4(yo + (long long)p * g.Cout, o);
+  }
+}
+template <int KH, int KW, int CIN>
+static void launch_smallk_tile(const float* x, const float* w, float* y, const ConvGeom& g, int relu, float thr, cudaStream_t s) {
+  constexpr int PW = 4;
+  const int segs = (g.OW + PW - 1) / PW;
+  const long long nt = (long long)g.N * g.OH * segs * (g.Cout / 4);
+  const size_t smem = (size_t)KH * KW * CIN * g.Cout * sizeof(float);
+  conv_smallk_fwd_tile_kernel<KH, KW, CIN, PW><<<(int)((nt + 255) / 256), 256, smem, s>>>(x, w, y, g, relu, thr, segs, nt);
+  SB_LAUNCHED();
+}
 void conv_smallk_fwd(const float* x, const float* w, float* y, const ConvGeom& g, int relu, float thr, cudaStream_t s) {
+  if (g.SH == 1 && g.SW == 1) {
+    const int shape = g.KH * 100 + g.KW * 10 + g.Cin;
+    if (shape == 331) return launch_smallk_tile<3, 3, 1>(x, w, y, g, relu, thr, s);
+    if (shape == 333) return launch_smallk_tile<3, 3, 3>(x, w, y, g, relu, thr, s);
+    if (shape == 551) return launch_smallk_tile<5, 5, 1>(x, w, y, g, relu, thr, s);
+  }
   const long long n4 = (long long)g.N * g.OH * g.OW * (g.Cout / 4);
   conv_smallk_fwd_kernel<<<grid_for(n4, 256), 256, 0, s>>>(x, w, y, g, relu, thr, n4);
   SB_LAUNCHED();
@@ -308,14 +393,20 @@ __global__ void __launch_bounds__(256) conv_smallk_wgrad_kernel(const float* __r
   float4 acc[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // every pixel lane walks a CONTIGUOUS run of output pixels: (b, oh, ow) advance incrementally (no divisions in the loop),
+  // neighbouring pixels share input taps in L1, and the next pixel's dY is fetched while this one is accumulated
   const long long p0 = (long long)blockIdx.x * pix_per_block;
   const long long p1 = p0 + pix_per_block < pixels ? p0 + pix_per_block : pixels;
-  for (long long p = p0 + lane; p < p1; p += lanes) {
-    const int ow = (int)(p % g.OW);
-    long long t = p / g.OW;
-    const int oh = (int)(t % g.OH);
-    const int b = (int)(t / g.OH);
-    const float4 gy = ld4(dy + p * g.Cout + c4 * 4);
+  const long long run = (p1 - p0 + lanes - 1) / lanes;
+  long long p = p0 + lane * run;
+  const long long pe = p + run < p1 ? p + run : p1;
+  int ow = (int)(p % g.OW);
+  int oh = (int)((p / g.OW) % g.OH);
+  int b = (int)(p / ((long long)g.OW * g.OH));
+  float4 gy = p < pe ? ld4(dy + p * g.Cout + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (; p < pe; ++p) {
+    const float4 gcur = gy;
+    if (p + 1 < pe) gy = ld4(dy + (p + 1) * g.Cout + c4 * 4);
 #pragma unroll
     for (int a = 0; a < KH; ++a) {
       const int ih = oh * g.SH + a - g.PT;
@@ -328,27 +419,41 @@ __global__ void __launch_bounds__(256) conv_smallk_wgrad_kernel(const float* __r
         for (int ci = 0; ci < CIN; ++ci) {
           const float xv = ok ? __ldg(xp + ci) : 0.f;
           float4& r = acc[(a * KW + bb) * CIN + ci];
-          r.x = fmaf(xv, gy.x, r.x); r.y = fmaf(xv, gy.y, r.y); r.z = fmaf(xv, gy.z, r.z); r.w = fmaf(xv, gy.w, r.w);
+          r.x = fmaf(xv, gcur.x, r.x); r.y = fmaf(xv, gcur.y, r.y); r.z = fmaf(xv, gcur.z, r.z); r.w = fmaf(xv, gcur.w, r.w);
         }
       }
     }
+    if (++ow == g.OW) {
+      ow = 0;
+      if (++oh == g.OH) { oh = 0; ++b; }
+    }
   }
-  // cross-lane sum in lane order, one k at a time through shared memory
-  __shared__ float4 red[256];
-  float* part = partial + (long long)blockIdx.x * K * g.Cout;
+  // cross-lane sum, fixed order: (1) the blockDim/32 ... pixel lanes that share a warp by shuffles (xor C4, 2*C4, ..),
+  // (2) the warps in warp order through shared memory.  Requires C4 to be a power of two <= 32 (checked by the launcher).
+  const int wl = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-    red[threadIdx.x] = acc[k];
-    __syncthreads();
-    if (lane == 0) {
-      float4 tot = red[c4];
-      for (int l = 1; l < lanes; ++l) {
-        const float4 v = red[l * C4 + c4];
-        tot.x = __fadd_rn(tot.x, v.x); tot.y = __fadd_rn(tot.y, v.y); tot.z = __fadd_rn(tot.z, v.z); tot.w = __fadd_rn(tot.w, v.w);
-      }
-      st4(part + k * g.Cout + c4 * 4, tot);
+    for (int o = C4; o < 32; o <<= 1) {
+      acc[k].x = __fadd_rn(acc[k].x, __shfl_xor_sync(0xffffffffu, acc[k].x, o));
+      acc[k].y = __fadd_rn(acc[k].y, __shfl_xor_sync(0xffffffffu, acc[k].y, o));
+      acc[k].z = __fadd_rn(acc[k].z, __shfl_xor_sync(0xffffffffu, acc[k].z, o));
+      acc[k].w = __fadd_rn(acc[k].w, __shfl_xor_sync(0xffffffffu, acc[k].w, o));
     }
-    __syncthreads();
+  }
+  extern __shared__ __align__(16) float4 red[];  // [nwarps][K][C4]
+  if (wl < C4) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) red[(wid * K + k) * C4 + wl] = acc[k];
+  }
+  __syncthreads();
+  float* part = partial + (long long)blockIdx.x * K * g.Cout;
+  for (int i = threadIdx.x; i < K * C4; i += blockDim.x) {
+    float4 tot = red[i];
+    for (int wq = 1; wq < nwarps; ++wq) {
+      const float4 v = red[wq * K * C4 + i];
+      tot.x = __fadd_rn(tot.x, v.x); tot.y = __fadd_rn(tot.y, v.y); tot.z = __fadd_rn(tot.z, v.z); tot.w = __fadd_rn(tot.w, v.w);
+    }
+    st4(part + (i / C4) * g.Cout + (i % C4) * 4, tot);
   }
 }
 void partial_reduce(const float* partial, float* out, int n, int parts, cudaStream_t s);
@@ -357,17 +462,26 @@ bool conv_smallk_wgrad(const float* x, const float* dy, float* dw, const ConvGeo
   const int K = g.KH * g.KW * g.Cin;
   const int C4 = g.Cout / 4;
   const int shape = g.KH * 100 + g.KW * 10 + g.Cin;
-  if ((shape != 331 && shape != 333 && shape != 551) || C4 > 256 || 256 % C4) return false;
+  if ((shape != 331 && shape != 333 && shape != 551) || C4 > 32 || (C4 & (C4 - 1))) return false;
   const long long pixels = (long long)g.N * g.OH * g.OW;
+  const size_t smem = (size_t)8 * K * C4 * sizeof(float4);
+  if (smem > 160 * 1024) return false;
+  static bool attr = false;
+  if (!attr) {
+    SB_CUDA(cudaFuncSetAttribute(conv_smallk_wgrad_kernel<3, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    SB_CUDA(cudaFuncSetAttribute(conv_smallk_wgrad_kernel<3, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    SB_CUDA(cudaFuncSetAttribute(conv_smallk_wgrad_kernel<5, 5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr = true;
+  }
   int blocks = 2 * kNumSMs;
   if ((size_t)blocks * K * g.Cout > ws_floats) blocks = (int)(ws_floats / ((size_t)K * g.Cout));
   if (blocks < 1) return false;
   if (blocks > pixels) blocks = (int)pixels;
   const long long ppb = (pixels + blocks - 1) / blocks;
   blocks = (int)((pixels + ppb - 1) / ppb);
-  if (shape == 331) conv_smallk_wgrad_kernel<3, 3, 1><<<blocks, 256, 0, s>>>(x, dy, ws, g, pixels, ppb);
-  else if (shape == 333) conv_smallk_wgrad_kernel<3, 3, 3><<<blocks, 256, 0, s>>>(x, dy, ws, g, pixels, ppb);
-  else conv_smallk_wgrad_kernel<5, 5, 1><<<blocks, 256, 0, s>>>(x, dy, ws, g, pixels, ppb);
+  if (shape == 331) conv_smallk_wgrad_kernel<3, 3, 1><<<blocks, 256, smem, s>>>(x, dy, ws, g, pixels, ppb);
+  else if (shape == 333) conv_smallk_wgrad_kernel<3, 3, 3><<<blocks, 256, smem, s>>>(x, dy, ws, g, pixels, ppb);
+  else conv_smallk_wgrad_kernel<5, 5, 1><<<blocks, 256, smem, s>>>(x, dy, ws, g, pixels, ppb);
   SB_LAUNCHED();
   const int n = K * g.Cout;
   partial_reduce(ws, dw, n, blocks, s);
@@ -512,7 +626,7 @@ bool dense_skinny_fwd(const float* x, const float* w, float* z, int M, int N, in
 // Backward, wgrad and dgrad in ONE pass over X / dX:  dW[k][n] = sum_m X[m][k] G[m][n] ;  dX[m][k] = sum_n G[m][n] W[k][n].
 // Thread = one k (coalesced along K) x one of 4 row groups; G and the W slab of the CTA are staged in shared memory; the row
 // groups' dW partials are summed in group order through shared memory.
-constexpr int kBwdK = 64, kBwdGroups = 4;
+constexpr int kBwdK = 32, kBwdGroups = 4;  // 128-thread CTAs: ~1000 CTAs on cfg2 fill one wave at 7 CTAs/SM
 template <int NT, bool DGRAD>
 __global__ void __launch_bounds__(kBwdK* kBwdGroups) dense_head_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gmat,
                                                                             const float* __restrict__ w, float* __restrict__ dw,
