@@ -19,34 +19,80 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-BATCH = 100
-IN_SHAPE = (28, 28, 1)
-CLASSES = 10
-ROWS_TOTAL = 60000
-WORKLOAD = ("cfg2 LeNet Conv2D(32,ReLU)>>Pool2D>>Conv2D(64,ReLU)>>Pool2D>>Flatten>>Dense(10,Softmax), CCE, Adam(0.001), "
-            "batch 100/GPU, synthetic 60000x28x28x1 sharded over the ranks")
-FLOP_PER_SAMPLE = 61_140_480
+METRIC = "train samples/sec (MNIST-shape CNN)"
+# BASELINE.json configs; cfg2 (configs[1]) is the workload the metric is quoted on and the default.  The others are run with
+# --config for profiles/ only.  flop = algorithmic FLOP per sample of one train step.
+CONFIGS = {
+    "cfg1": dict(batch=1000, in_shape=(784,), out=10, rows=30000, flop=159_800, loss="cce", rate=0.01,
+                 workload="cfg1 MLP Dense(50,Sigmoid)>>Dense(10,Softmax), CCE, Adam(0.01), batch 1000/GPU, synthetic 30000x784"),
+    "cfg2": dict(batch=100, in_shape=(28, 28, 1), out=10, rows=60000, flop=61_140_480, loss="cce", rate=0.001,
+                 workload="cfg2 LeNet Conv2D(32,ReLU)>>Pool2D>>Conv2D(64,ReLU)>>Pool2D>>Flatten>>Dense(10,Softmax), CCE, "
+                          "Adam(0.001), batch 100/GPU, synthetic 60000x28x28x1 sharded over the ranks"),
+    "cfg3": dict(batch=1024, in_shape=(64, 1), out=1, rows=8192, flop=101_058_048, loss="mse", rate=0.001,
+                 workload="cfg3 LSTM(256)>>Dense(1,Tanh), MSE, Adam(0.001), seq len 64, batch 1024/GPU, synthetic 8192x64x1"),
+    "cfg4": dict(batch=8192, in_shape=(784,), out=10, rows=32768, flop=315_080_704, loss="cce", rate=0.001,
+                 workload="cfg4 wide MLP 4xDense(4096,ReLU)>>Dense(10,Softmax), CCE, Adam(0.001), batch 8192/GPU, synthetic 32768x784"),
+    "cfg5": dict(batch=256, in_shape=(32, 32, 3), out=10, rows=5120, flop=109_353_984, loss="cce", rate=0.001,
+                 workload="cfg5 CIFAR-shape CNN Conv2D(64,ReLU)>>BatchNorm>>Pool2D(s2)>>Conv2D(128,ReLU)>>BatchNorm>>Pool2D(s2)>>"
+                          "Conv2D(256,ReLU)>>BatchNorm>>Pool2D(s2)>>Flatten>>Dense(10,Softmax), CCE, Adam(0.001), batch 256/GPU, "
+                          "synthetic 5120x32x32x3"),
+}
+CFG = CONFIGS["cfg2"]
+BATCH, IN_SHAPE, CLASSES, ROWS_TOTAL = CFG["batch"], CFG["in_shape"], CFG["out"], CFG["rows"]
+WORKLOAD, FLOP_PER_SAMPLE = CFG["workload"], CFG["flop"]
+
+
+def select_config(name):
+    global CFG, BATCH, IN_SHAPE, CLASSES, ROWS_TOTAL, WORKLOAD, FLOP_PER_SAMPLE
+    CFG = CONFIGS[name]
+    BATCH, IN_SHAPE, CLASSES, ROWS_TOTAL = CFG["batch"], CFG["in_shape"], CFG["out"], CFG["rows"]
+    WORKLOAD, FLOP_PER_SAMPLE = CFG["workload"], CFG["flop"]
 
 
 def synth(rows, seed):
-    """features U[1/256,1] (MNIST pixels are (ubyte+1)/256), one-hot labels class = row % 10; PCG64."""
+    """features U[1/256,1] (MNIST pixels are (ubyte+1)/256), one-hot labels class = row % 10 (regression: targets U[0,1],
+    the min-max scaled sunspot prep); PCG64."""
     rng = np.random.Generator(np.random.PCG64(seed))
     x = rng.uniform(1.0 / 256, 1.0, size=(rows,) + IN_SHAPE).astype(np.float32)
+    if CFG["loss"] == "mse":
+        return x, rng.uniform(0.0, 1.0, size=(rows, CLASSES)).astype(np.float32)
     y = np.zeros((rows, CLASSES), np.float32)
     y[np.arange(rows), np.arange(rows) % CLASSES] = 1.0
     return x, y
 
 
+def build_model(S, name, seed=1):
+    """the BASELINE model in the product DSL (S = scanet3_b200) or, with the snake_case keywords, in the oracle's"""
+    kw = (lambda i: {"kernelInitializer": i}) if hasattr(S, "Engine") else (lambda i: {"kernel_initializer": i})
+    g = S.GlorotUniform(seed)
+    if name == "cfg1":
+        return S.Dense(50, S.Sigmoid, **kw(g)) >> S.Dense(10, S.Softmax, **kw(g))
+    if name == "cfg2":
+        return (S.Conv2D(32, activation=S.ReLU(), **kw(g)) >> S.Pool2D() >> S.Conv2D(64, activation=S.ReLU(), **kw(g))
+                >> S.Pool2D() >> S.Flatten >> S.Dense(10, S.Softmax, **kw(g)))
+    if name == "cfg3":
+        rk = {"recurrentInitializer": S.Orthogonal(seed=seed)} if hasattr(S, "Engine") else {"recurrent_initializer": S.Orthogonal(seed=seed)}
+        return S.LSTM(256, **kw(g), **rk) >> S.Dense(1, S.Tanh, **kw(g))
+    if name == "cfg4":
+        m = S.Dense(4096, S.ReLU(), **kw(g))
+        for _ in range(3):
+            m = m >> S.Dense(4096, S.ReLU(), **kw(g))
+        return m >> S.Dense(10, S.Softmax, **kw(g))
+    if name == "cfg5":
+        s2 = dict(strides=(2, 2))
+        return (S.Conv2D(64, activation=S.ReLU(), **kw(g)) >> S.BatchNorm() >> S.Pool2D(**s2)
+                >> S.Conv2D(128, activation=S.ReLU(), **kw(g)) >> S.BatchNorm() >> S.Pool2D(**s2)
+                >> S.Conv2D(256, activation=S.ReLU(), **kw(g)) >> S.BatchNorm() >> S.Pool2D(**s2)
+                >> S.Flatten >> S.Dense(10, S.Softmax, **kw(g)))
+    raise ValueError(name)
+
+
 def lenet(S, seed=1):
-    return (S.Conv2D(32, activation=S.ReLU(), kernelInitializer=S.GlorotUniform(seed)) >> S.Pool2D()
-            >> S.Conv2D(64, activation=S.ReLU(), kernelInitializer=S.GlorotUniform(seed)) >> S.Pool2D() >> S.Flatten
-            >> S.Dense(10, S.Softmax, kernelInitializer=S.GlorotUniform(seed)))
+    return build_model(S, "cfg2", seed)
 
 
 def lenet_oracle(O, seed=1):
-    return (O.Conv2D(32, activation=O.ReLU(), kernel_initializer=O.GlorotUniform(seed)) >> O.Pool2D()
-            >> O.Conv2D(64, activation=O.ReLU(), kernel_initializer=O.GlorotUniform(seed)) >> O.Pool2D() >> O.Flatten
-            >> O.Dense(10, O.Softmax, kernel_initializer=O.GlorotUniform(seed)))
+    return build_model(O, "cfg2", seed)
 
 
 def cpu_port_samples_per_sec(max_steps, budget_s):
@@ -154,7 +200,8 @@ def run_ours(args):
     rows = ROWS_TOTAL // world
     steps_per_epoch = rows // BATCH
     x, y = synth(rows, 1234 + 2 + 1000 * rank)  # seed = 1234 + config index (+ a per-rank stream for its shard)
-    eng = S.Engine(lenet(S), S.CategoricalCrossentropy, S.Adam(0.001), BATCH, IN_SHAPE, (CLASSES,), device=local_rank,
+    loss = S.MeanSquaredError if CFG["loss"] == "mse" else S.CategoricalCrossentropy
+    eng = S.Engine(build_model(S, args.config), loss, S.Adam(CFG["rate"]), BATCH, IN_SHAPE, (CLASSES,), device=local_rank,
                    precision=precision, use_graph=True)
     eng.init_params()
     eng.upload_dataset(x, y)
@@ -284,14 +331,14 @@ def run_ours(args):
         roofline["avg_launch_us"] = per_launch_ms * 1000.0
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config == "cfg2":
         sps, n, dt = cpu_port_samples_per_sec(max_steps=40, budget_s=20.0)
         cpu = {"value": sps, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
                "sample": f"{n} train steps of batch {BATCH} ({dt:.1f} s) of the same workload, NumPy/BLAS oracle port"}
 
     if rank == 0:
         line = {
-            "metric": "train samples/sec (MNIST-shape CNN)", "value": value, "unit": "samples/s", "n_gpus": world,
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if precision == N.PREC_FP32 else ("f32 storage, tf32 tensor-core contractions (fp32 accumulate)"
@@ -299,7 +346,8 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "precision": args.precision, "steps_per_epoch": steps_per_epoch,
                        "averaging": "none (1 worker)" if world == 1 else f"{args.collective} every {steps_per_epoch} steps",
-                       "l2": "shard 188 MB/N > L2 is streamed batch by batch; per-step activations (~55 MB) are L2-resident by nature",
+                       "l2": f"shard {rows * int(np.prod(IN_SHAPE)) * 4 / 1e6:.0f} MB per rank is streamed batch by batch (cfg2: 188 MB/N > L2); "
+                             "per-step activations are L2-resident by nature",
                        "cuda_graph": True, "flop_per_sample": FLOP_PER_SAMPLE},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": xb + yb, "d2h_bytes_per_step": 4,
                     "wall_s": e2e_wall, "last_loss": last_loss},
@@ -326,7 +374,9 @@ def main():
     ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "3xtf32"])
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS), help="BASELINE config (cfg2 = the metric's workload)")
     args = ap.parse_args()
+    select_config(args.config)
     if args.impl == "reference":
         run_reference(args)
     else:

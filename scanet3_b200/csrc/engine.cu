@@ -347,7 +347,8 @@ static void plan_fusions(sb_engine* e) {
   if (e->train.loss == SB_LOSS_CCE && last.d.kind == SB_LAYER_ACTIVATE && last.d.activation == SB_ACT_SOFTMAX && last.inplace &&
       last.out.rank == 2) {
     e->softmax_cce_fused = true;
-    if (e->fast && nl >= 2 && e->L[nl - 2].d.kind == SB_LAYER_BIAS && e->L[nl - 2].inplace && last.out.d[1] <= 32) {
+    if (e->fast && nl >= 2 && e->L[nl - 2].d.kind == SB_LAYER_BIAS && e->L[nl - 2].inplace && last.out.d[1] <= 32 &&
+        last.out.d[0] <= 10240) {
       e->head_fused = true;
       e->L[nl - 2].head_skip = true;
     }
@@ -379,8 +380,19 @@ static void plan_fusions(sb_engine* e) {
         }
         break;
       }
+      case SB_LAYER_BIAS: {
+        // backward of the in-place activation that follows folds into this layer's column sum (one pass over g and y)
+        const int nx = li + 1;
+        if (L.inplace && !L.head_skip && nx < nl && e->L[nx].d.kind == SB_LAYER_ACTIVATE && e->L[nx].inplace && !e->L[nx].head_skip &&
+            !e->L[nx].skip_bwd && e->L[nx].d.activation != SB_ACT_SOFTMAX && e->L[nx].d.activation != SB_ACT_IDENTITY &&
+            e->L[nx].need_dx && L.d.units % 4 == 0) {
+          L.fuse_act_bwd = true;
+          e->L[nx].skip_bwd = true;
+        }
+        break;
+      }
       case SB_LAYER_DENSE:
-        L.fast_skinny = L.out.d[1] <= 16 && L.in.d[1] >= 2048 && L.in.d[1] % 4 == 0 && L.in.d[0] <= 128;
+        L.fast_skinny = L.out.d[1] <= 16 && L.in.d[1] >= 512 && L.in.d[1] % 4 == 0;
         break;
       default:
         break;
@@ -587,8 +599,9 @@ static void run_loss(sb_engine* e, bool with_grad) {
   if (e->head_fused) {
     const LayerPlan& bias = e->L[e->L.size() - 2];
     Prof pr(e, "head_bias_softmax_cce", 4.0 * 4.0 * (double)rows * cols, 0);
-    head_bias_softmax_cce(pred, e->head_chunks > 0 ? e->ws : nullptr, e->head_chunks, P(e, bias.p_w), e->by, dpred,
-                          with_grad ? G(e, bias.p_w) : nullptr, e->st, (int)rows, (int)cols, e->head_scratch, e->stream);
+    if (!head_bias_softmax_cce(pred, e->head_chunks > 0 ? e->ws : nullptr, e->head_chunks, P(e, bias.p_w), e->by, dpred,
+                               with_grad ? G(e, bias.p_w) : nullptr, e->st, (int)rows, (int)cols, e->head_scratch, e->stream))
+      SB_FAIL(SB_ERR_CUDA, "fused classifier head rejected a planned shape");
   } else if (e->softmax_cce_fused) {
     Prof pr(e, "softmax_cce_fused", 4.0 * 4.0 * (double)rows * cols, 0);
     softmax_cce_fwd_bwd(pred, e->by, dpred, e->st, (int)rows, (int)cols, e->stream);
@@ -627,7 +640,7 @@ static void run_backward(sb_engine* e) {
         if (L.fast_skinny && !wdone) {
           const bool dg = L.need_dx && din;
           Prof pr(e, "dense_head_bwd", db + (dg ? 4.0 * M * K : 0.0), (dg ? 4.0 : 2.0) * M * N * K);
-          wdone = ddone = dense_head_bwd(in, dout, P(e, L.p_w), G(e, L.p_w), dg ? din : nullptr, M, N, K, s);
+          wdone = ddone = dense_head_bwd(in, dout, P(e, L.p_w), G(e, L.p_w), dg ? din : nullptr, M, N, K, e->ws, e->ws_floats, s);
         }
         if (!wdone) {
           Prof pr(e, "dense_wgrad_f32", db, 2.0 * M * N * K);
@@ -640,7 +653,19 @@ static void run_backward(sb_engine* e) {
         break;
       }
       case SB_LAYER_BIAS: {
+        if (L.fuse_act_bwd) {
+          const LayerPlan& A = e->L[li + 1];
+          Prof pr(e, "act_bwd_bias_grad", 12.0 * n_out, 0);
+          if (!act_bwd_col_sum(dout, e->acts[A.buf_out], A.d.activation, A.d.relu_threshold, G(e, L.p_w), n_out / L.d.units,
+                               L.d.units, e->ws, e->ws_floats, s))
+            SB_FAIL(SB_ERR_CUDA, "act_bwd_col_sum rejected a planned shape");
+          break;
+        }
         Prof pr(e, "bias_grad", 4.0 * n_out, 0);
+        if (e->fast && act_bwd_col_sum(dout, nullptr, 0, 0.f, G(e, L.p_w), n_out / L.d.units, L.d.units, e->ws, e->ws_floats, s)) {
+          if (!L.inplace && L.need_dx && din) SB_CUDA(cudaMemcpyAsync(din, dout, (size_t)n_out * 4, cudaMemcpyDeviceToDevice, s));
+          break;
+        }
         col_sum(dout, G(e, L.p_w), n_out / L.d.units, L.d.units, e->ws, e->ws_floats, s);
         if (!L.inplace && L.need_dx && din) SB_CUDA(cudaMemcpyAsync(din, dout, (size_t)n_out * 4, cudaMemcpyDeviceToDevice, s));
         break;

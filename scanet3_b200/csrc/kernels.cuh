@@ -102,12 +102,16 @@ bool dense_skinny_fwd(const float* x, const float* w, float* z, int M, int N, in
 bool dense_head_fwd(const float* x, const float* w, float* partial, int* chunks_out, int M, int N, int K, size_t ws_floats,
                     cudaStream_t s);
 // wgrad and (dx != null) dgrad in one pass
-bool dense_head_bwd(const float* x, const float* g, const float* w, float* dw, float* dx, int M, int N, int K, cudaStream_t s);
+bool dense_head_bwd(const float* x, const float* g, const float* w, float* dw, float* dx, int M, int N, int K, float* ws,
+                    size_t ws_floats, cudaStream_t s);
 // z (or the sum of `chunks` split-K partials when partial != null) + bias -> softmax -> CCE loss, dz, dbias
 // scratch: kHeadScratchFloats floats, zero-initialised once (per-CTA partials + the completion ticket)
 constexpr size_t kHeadScratchFloats = 1024 * 40 + 32;
 bool head_bias_softmax_cce(float* z, const float* partial, int chunks, const float* bias, const float* y, float* dz, float* dbias,
                            StepState* st, int rows, int C, float* scratch, cudaStream_t s);
+// g <- act'(y)*g in place and out[c] = column sums of the result, one pass (act = 0: plain column sum); false if C % 4 != 0
+bool act_bwd_col_sum(float* g, const float* y, int act, float thr, float* out, long long rows, int C, float* ws, size_t ws_floats,
+                     cudaStream_t s);
 // out[i] = sum_c partial[c*n + i], fixed order
 void partial_reduce(const float* partial, float* out, int n, int parts, cudaStream_t s);
 }  // namespace sb

@@ -3,6 +3,8 @@
 //   * Conv2D with a tiny reduction (KH*KW*Cin <= 32, e.g. the first layer on 1- or 3-channel images): fprop (+ReLU) and wgrad,
 //   * the skinny dense head (N <= 16 outputs): split-K forward, fused bias + softmax + CCE (+ bias gradient), wgrad, dgrad.
 // All reductions use fixed orders (no atomics), so results are run-to-run deterministic.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "tc_sm100.cuh"
@@ -526,16 +528,21 @@ void partial_reduce(const float* partial, float* out, int n, int parts, cudaStre
 constexpr int kHeadKQ = 4;
 template <int NT>
 __global__ void __launch_bounds__(kHeadThreads* kHeadKQ) dense_head_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                                               float* __restrict__ partial, int M, int K, int N, int KC) {
+                                                                               float* __restrict__ partial, int Mtot, int K, int N, int KC) {
   extern __shared__ __align__(128) float sm[];
   const int xs_stride = KC + 4;
-  float* xs = sm;                                        // [M][KC+4]
-  float* ws = xs + (size_t)M * xs_stride;                // [KC][NT]
-  float* red = ws + (size_t)KC * NT;                     // [kHeadKQ][M][NT+1]
+  const int Mcap = min(kHeadThreads, Mtot);
+  float* xs = sm;                                        // [Mcap][KC+4]
+  float* ws = xs + (size_t)Mcap * xs_stride;             // [KC][NT]
+  float* red = ws + (size_t)KC * NT;                     // [kHeadKQ][Mcap][NT+1]
   __shared__ __align__(8) uint64_t bar;
   const int tid = threadIdx.x;
   const int k0 = blockIdx.x * KC;
   const int kc = min(KC, K - k0);
+  // rows [mbase, mbase + M) of the Mtot-row problem (blockIdx.y = row chunk of <= 128 rows)
+  const int mbase = blockIdx.y * kHeadThreads;
+  const int M = min(kHeadThreads, Mtot - mbase);
+  x += (size_t)mbase * K;
   if (tid == 0) {
     tc::mbar_init(&bar, 1);
     tc::fence_barrier_init();
@@ -588,30 +595,34 @@ __global__ void __launch_bounds__(kHeadThreads* kHeadKQ) dense_head_fwd_kernel(c
     float t = red[(size_t)mm * (NT + 1) + n];
 #pragma unroll
     for (int q = 1; q < kHeadKQ; ++q) t = __fadd_rn(t, red[((size_t)q * M + mm) * (NT + 1) + n]);
-    partial[(size_t)blockIdx.x * M * N + i] = t;
+    partial[((size_t)blockIdx.x * Mtot + mbase) * N + i] = t;
   }
 }
 static int head_smem_bytes(int M, int KC, int NT) { return (M * (KC + 4) + KC * NT + kHeadKQ * M * (NT + 1)) * 4; }
 // writes partial[chunks][M][N] into `partial`; *chunks_out = number of partials.  K % 4 == 0 (16-byte row alignment).
 bool dense_head_fwd(const float* x, const float* w, float* partial, int* chunks_out, int M, int N, int K, size_t ws_floats,
                     cudaStream_t s) {
-  if (N > kSkinnyN || M > kHeadThreads || (K & 3) || (((uintptr_t)x) & 15)) return false;
+  if (N > kSkinnyN || M < 1 || (K & 3) || (((uintptr_t)x) & 15)) return false;
   const int NT = N <= 12 ? 12 : 16;
-  int KC = ((K + kNumSMs - 1) / kNumSMs + 15) & ~15;  // one wave of CTAs; multiple of 16 (=> (KC+4)/4 is odd)
+  const int m_chunks = (M + kHeadThreads - 1) / kHeadThreads, Mcap = std::min(M, kHeadThreads);
+  // CTAs = K chunks x row chunks: one wave when a single row chunk (few partials for the head kernel to sum), else two
+  const int want_k = std::max(1, (m_chunks == 1 ? kNumSMs : 2 * kNumSMs) / m_chunks);
+  int KC = ((K + want_k - 1) / want_k + 15) & ~15;  // multiple of 16 (=> (KC+4)/4 is odd: conflict-free LDS.128)
   if (KC < 64) KC = 64;
-  while (head_smem_bytes(M, KC, NT) > 200 * 1024 && KC > 64) KC = ((KC / 2) + 15) & ~15;
-  if (head_smem_bytes(M, KC, NT) > 200 * 1024) return false;
+  while (head_smem_bytes(Mcap, KC, NT) > 200 * 1024 && KC > 64) KC = ((KC / 2) + 15) & ~15;
+  if (head_smem_bytes(Mcap, KC, NT) > 200 * 1024) return false;
   const int chunks = (K + KC - 1) / KC;
   if ((size_t)chunks * M * N > ws_floats) return false;
-  const int smem = head_smem_bytes(M, KC, NT);
+  const int smem = head_smem_bytes(Mcap, KC, NT);
   static bool attr = false;
   if (!attr) {
     SB_CUDA(cudaFuncSetAttribute(dense_head_fwd_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     SB_CUDA(cudaFuncSetAttribute(dense_head_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
-  if (NT == 12) dense_head_fwd_kernel<12><<<chunks, kHeadThreads * kHeadKQ, smem, s>>>(x, w, partial, M, K, N, KC);
-  else dense_head_fwd_kernel<16><<<chunks, kHeadThreads * kHeadKQ, smem, s>>>(x, w, partial, M, K, N, KC);
+  const dim3 grid(chunks, m_chunks);
+  if (NT == 12) dense_head_fwd_kernel<12><<<grid, kHeadThreads * kHeadKQ, smem, s>>>(x, w, partial, M, K, N, KC);
+  else dense_head_fwd_kernel<16><<<grid, kHeadThreads * kHeadKQ, smem, s>>>(x, w, partial, M, K, N, KC);
   SB_LAUNCHED();
   *chunks_out = chunks;
   return true;
@@ -627,20 +638,21 @@ bool dense_skinny_fwd(const float* x, const float* w, float* z, int M, int N, in
 // Thread = one k (coalesced along K) x one of 4 row groups; G and the W slab of the CTA are staged in shared memory; the row
 // groups' dW partials are summed in group order through shared memory.
 constexpr int kBwdK = 32, kBwdGroups = 4;  // 128-thread CTAs: ~1000 CTAs on cfg2 fill one wave at 7 CTAs/SM
+constexpr int kBwdRows = 128;  // rows of G staged per pass
 template <int NT, bool DGRAD>
 __global__ void __launch_bounds__(kBwdK* kBwdGroups) dense_head_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gmat,
                                                                             const float* __restrict__ w, float* __restrict__ dw,
-                                                                            float* __restrict__ dx, int M, int K, int N) {
-  extern __shared__ __align__(16) float sm[];
-  float* sg = sm;                          // [M][NT]
-  float* sw = sg + (size_t)M * NT;         // [kBwdK][NT+1]
-  float* red = sw + kBwdK * (NT + 1);      // [kBwdGroups][kBwdK][NT+1]
+                                                                            float* __restrict__ dx, int Mtot, int K, int N,
+                                                                            int rows_per_split) {
+  extern __shared__ __align__(128) float sm[];
+  // blockIdx.y = row split: rows [mlo, mhi); its dW goes to slice blockIdx.y of `dw` (summed in split order afterwards)
+  const int mlo = blockIdx.y * rows_per_split, M = min(Mtot, mlo + rows_per_split);
+  dw += (size_t)blockIdx.y * K * N;
+  float* sg = sm;                              // [kBwdRows][NT]
+  float* sw = sg + (size_t)kBwdRows * NT;      // [kBwdK][NT+1]
+  float* red = sw + kBwdK * (NT + 1);          // [kBwdGroups][kBwdK][NT+1]
   const int tid = threadIdx.x, kk = tid % kBwdK, rg = tid / kBwdK;
   const int k0 = blockIdx.x * kBwdK, k = k0 + kk;
-  for (int i = tid; i < M * NT; i += blockDim.x) {
-    const int m = i / NT, n = i % NT;
-    sg[i] = n < N ? __ldg(gmat + (size_t)m * N + n) : 0.f;
-  }
   if (DGRAD) {
     const int kn = min(kBwdK, K - k0) * N;
     for (int i = tid; i < kn; i += blockDim.x) sw[(i / N) * (NT + 1) + i % N] = __ldg(w + (size_t)k0 * N + i);
@@ -652,24 +664,33 @@ __global__ void __launch_bounds__(kBwdK* kBwdGroups) dense_head_bwd_kernel(const
     acc[n] = 0.f;
     wr[n] = (DGRAD && n < N) ? sw[kk * (NT + 1) + n] : 0.f;
   }
-  const int rows_per = (M + kBwdGroups - 1) / kBwdGroups;
-  const int m0 = rg * rows_per, m1 = min(M, m0 + rows_per);
-  if (k < K) {
-#pragma unroll 5
-    for (int m = m0; m < m1; ++m) {
-      const float xv = __ldg(x + (size_t)m * K + k);
-      float d = 0.f;
+  for (int mb = mlo; mb < M; mb += kBwdRows) {  // row chunks in order: the dW sum runs over rows in ascending chunks
+    const int mc = min(kBwdRows, M - mb);
+    __syncthreads();
+    for (int i = tid; i < mc * NT; i += blockDim.x) {
+      const int m = i / NT, n = i - m * NT;
+      sg[i] = n < N ? __ldg(gmat + (size_t)(mb + m) * N + n) : 0.f;
+    }
+    __syncthreads();
+    const int rows_per = (mc + kBwdGroups - 1) / kBwdGroups;
+    const int m0 = rg * rows_per, m1 = min(mc, m0 + rows_per);
+    if (k < K) {
+#pragma unroll 4
+      for (int m = m0; m < m1; ++m) {
+        const float xv = __ldg(x + (size_t)(mb + m) * K + k);
+        float d = 0.f;
 #pragma unroll
-      for (int n4 = 0; n4 < NT; n4 += 4) {
-        const float4 gv = *reinterpret_cast<const float4*>(sg + m * NT + n4);
-        acc[n4] = fmaf(xv, gv.x, acc[n4]); acc[n4 + 1] = fmaf(xv, gv.y, acc[n4 + 1]);
-        acc[n4 + 2] = fmaf(xv, gv.z, acc[n4 + 2]); acc[n4 + 3] = fmaf(xv, gv.w, acc[n4 + 3]);
-        if (DGRAD) {
-          d = fmaf(gv.x, wr[n4], d); d = fmaf(gv.y, wr[n4 + 1], d);
-          d = fmaf(gv.z, wr[n4 + 2], d); d = fmaf(gv.w, wr[n4 + 3], d);
+        for (int n4 = 0; n4 < NT; n4 += 4) {
+          const float4 gv = *reinterpret_cast<const float4*>(sg + m * NT + n4);
+          acc[n4] = fmaf(xv, gv.x, acc[n4]); acc[n4 + 1] = fmaf(xv, gv.y, acc[n4 + 1]);
+          acc[n4 + 2] = fmaf(xv, gv.z, acc[n4 + 2]); acc[n4 + 3] = fmaf(xv, gv.w, acc[n4 + 3]);
+          if (DGRAD) {
+            d = fmaf(gv.x, wr[n4], d); d = fmaf(gv.y, wr[n4 + 1], d);
+            d = fmaf(gv.z, wr[n4 + 2], d); d = fmaf(gv.w, wr[n4 + 3], d);
+          }
         }
+        if (DGRAD) dx[(size_t)(mb + m) * K + k] = d;
       }
-      if (DGRAD) dx[(size_t)m * K + k] = d;
     }
   }
 #pragma unroll
@@ -685,20 +706,91 @@ __global__ void __launch_bounds__(kBwdK* kBwdGroups) dense_head_bwd_kernel(const
     dw[(size_t)k0 * N + i] = t;
   }
 }
-bool dense_head_bwd(const float* x, const float* g, const float* w, float* dw, float* dx, int M, int N, int K, cudaStream_t s) {
+bool dense_head_bwd(const float* x, const float* g, const float* w, float* dw, float* dx, int M, int N, int K, float* ws,
+                    size_t ws_floats, cudaStream_t s) {
   if (N > kSkinnyN) return false;
   const int NT = N <= 12 ? 12 : 16;
-  const size_t smem = ((size_t)M * NT + kBwdK * (NT + 1) + (size_t)kBwdGroups * kBwdK * (NT + 1)) * 4;
+  const size_t smem = ((size_t)kBwdRows * NT + kBwdK * (NT + 1) + (size_t)kBwdGroups * kBwdK * (NT + 1)) * 4;
   if (smem > 48 * 1024) return false;
-  const int grid = (K + kBwdK - 1) / kBwdK, thr = kBwdK * kBwdGroups;
+  const int kblocks = (K + kBwdK - 1) / kBwdK, thr = kBwdK * kBwdGroups;
+  // enough CTAs for ~2 waves at 7 CTAs/SM: split the rows when K alone does not give them
+  int splits = std::max(1, std::min({(2 * 7 * kNumSMs + kblocks - 1) / kblocks, (M + kBwdRows - 1) / kBwdRows,
+                                     (int)(ws_floats / ((size_t)K * N))}));
+  const int rows_per_split = ((M + splits - 1) / splits + kBwdRows - 1) / kBwdRows * kBwdRows;
+  splits = (M + rows_per_split - 1) / rows_per_split;
+  float* dwo = splits > 1 ? ws : dw;
+  const dim3 grid(kblocks, splits);
   if (NT == 12) {
-    if (dx) dense_head_bwd_kernel<12, true><<<grid, thr, smem, s>>>(x, g, w, dw, dx, M, K, N);
-    else dense_head_bwd_kernel<12, false><<<grid, thr, smem, s>>>(x, g, w, dw, dx, M, K, N);
+    if (dx) dense_head_bwd_kernel<12, true><<<grid, thr, smem, s>>>(x, g, w, dwo, dx, M, K, N, rows_per_split);
+    else dense_head_bwd_kernel<12, false><<<grid, thr, smem, s>>>(x, g, w, dwo, dx, M, K, N, rows_per_split);
   } else {
-    if (dx) dense_head_bwd_kernel<16, true><<<grid, thr, smem, s>>>(x, g, w, dw, dx, M, K, N);
-    else dense_head_bwd_kernel<16, false><<<grid, thr, smem, s>>>(x, g, w, dw, dx, M, K, N);
+    if (dx) dense_head_bwd_kernel<16, true><<<grid, thr, smem, s>>>(x, g, w, dwo, dx, M, K, N, rows_per_split);
+    else dense_head_bwd_kernel<16, false><<<grid, thr, smem, s>>>(x, g, w, dwo, dx, M, K, N, rows_per_split);
   }
   SB_LAUNCHED();
+  if (splits > 1) partial_reduce(ws, dw, K * N, splits, s);
+  return true;
+}
+
+// =====================================================================================================================
+// Bias gradient fused with the backward of the in-place activation that follows the Bias (layer/Bias.scala:32-33 under
+// layer/Activate.scala:16-17):  g <- act'(y) * g  (in place)  and  db[c] = sum_rows g[r][c]  in ONE pass over g and y.
+// Block = 32 column quads (128 columns) x 8 row lanes over a chunk of rows; per-chunk partials, summed in chunk order.
+// act = 0 gives the plain column sum (g untouched, y unused).
+// =====================================================================================================================
+__device__ __forceinline__ float act_grad1(float g, float y, int act, float thr) {
+  switch (act) {
+    case 1: return __fmul_rn(__fmul_rn(y, __fsub_rn(1.f, y)), g);
+    case 2: return __fmul_rn(__fsub_rn(1.f, __fmul_rn(y, y)), g);
+    case 4: return y > thr ? g : 0.f;
+    default: return g;
+  }
+}
+__global__ void __launch_bounds__(256) act_bwd_col_sum_kernel(float* __restrict__ g, const float* __restrict__ y, int act, float thr,
+                                                              float* __restrict__ partial, long long rows, int C,
+                                                              long long rows_per_chunk) {
+  __shared__ float4 red[8][33];
+  const int c4 = blockIdx.x * 32 + threadIdx.x;  // column quad
+  const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+  const long long r1 = r0 + rows_per_chunk < rows ? r0 + rows_per_chunk : rows;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c4 * 4 < C) {
+#pragma unroll 4
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8) {
+      float4 gv = *reinterpret_cast<const float4*>(g + r * C + c4 * 4);
+      if (act) {
+        const float4 yv = ld4(y + r * C + c4 * 4);
+        gv.x = act_grad1(gv.x, yv.x, act, thr); gv.y = act_grad1(gv.y, yv.y, act, thr);
+        gv.z = act_grad1(gv.z, yv.z, act, thr); gv.w = act_grad1(gv.w, yv.w, act, thr);
+        st4(g + r * C + c4 * 4, gv);
+      }
+      acc.x = __fadd_rn(acc.x, gv.x); acc.y = __fadd_rn(acc.y, gv.y); acc.z = __fadd_rn(acc.z, gv.z); acc.w = __fadd_rn(acc.w, gv.w);
+    }
+  }
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c4 * 4 < C) {
+    for (int j = 1; j < 8; ++j) {
+      const float4 v = red[j][threadIdx.x];
+      acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y); acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
+    }
+    st4(partial + (long long)blockIdx.y * C + c4 * 4, acc);
+  }
+}
+// returns false when the shape is not covered (C % 4 != 0): the caller runs act_bwd + col_sum
+bool act_bwd_col_sum(float* g, const float* y, int act, float thr, float* out, long long rows, int C, float* ws, size_t ws_floats,
+                     cudaStream_t s) {
+  if ((C & 3) || rows < 1) return false;
+  const int col_blocks = (C / 4 + 31) / 32;
+  long long chunks = (4LL * kNumSMs + col_blocks - 1) / col_blocks;
+  if (chunks > (rows + 31) / 32) chunks = (rows + 31) / 32;
+  if (chunks > (long long)(ws_floats / (size_t)C)) chunks = (long long)(ws_floats / (size_t)C);
+  if (chunks < 1) return false;
+  const long long rpc = (rows + chunks - 1) / chunks;
+  chunks = (rows + rpc - 1) / rpc;
+  act_bwd_col_sum_kernel<<<dim3(col_blocks, (unsigned)chunks), dim3(32, 8), 0, s>>>(g, y, act, thr, ws, rows, C, rpc);
+  SB_LAUNCHED();
+  partial_reduce(ws, out, C, (int)chunks, s);
   return true;
 }
 
@@ -808,7 +900,7 @@ bool head_bias_softmax_cce(float* z, const float* partial, int chunks, const flo
                            StepState* st, int rows, int C, float* scratch, cudaStream_t s) {
   if (C > 32) return false;
   const int grid = (rows + kHeadRows - 1) / kHeadRows;
-  if (grid > 1024) return false;
+  if (grid > 1024) return false;  // scratch holds 1024 CTA partials
   head_bias_softmax_cce_kernel<<<grid, 1024, 0, s>>>(z, partial, chunks, bias, y, dz, dbias, st, rows, C, scratch,
                                                      reinterpret_cast<unsigned int*>(scratch + 1024 * 40));
   SB_LAUNCHED();

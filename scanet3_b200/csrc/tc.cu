@@ -230,6 +230,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 //   Rows with c >= Wg are computed and dropped by the epilogue (KW-1 of every P).  The whole filter is resident in shared
 //   memory for the life of the CTA.  Per tile: kchunks TMA issues and taps*kchunks*4 MMAs -- no per-tap traffic.
 // =====================================================================================================================
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all_groups() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 struct HaloParams {
   int n_tiles, tiles_per_img;
   int Hg, Wg, BH, P;
@@ -245,12 +255,14 @@ struct HaloParams {
   int relu;
   float thr;
   float* out;          // [n_img, Hg, Wg, N]
+  int tma_store;       // epilogue through swizzled shared staging + TMA stores (one box per grid row and 32-channel chunk)
   long long* dbg;      // developer timeline (SB_TC_DEBUG=1): 64 clock64 slots per CTA, null in production
   int bo_mode;         // debug: 1 = also encode the start row's swizzle phase in the descriptor's base-offset field
 };
 
 __global__ void __launch_bounds__(kIgemmThreads, 1)
-conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const HaloParams p) {
+conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_c, const HaloParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int taps = p.KH * p.KW;
@@ -259,7 +271,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int stage_bytes = p.kchunks * p.a_tile_bytes;
   uint8_t* sm_b = smem;
   uint8_t* sm_a = smem + b_bytes;
-  uint64_t* full_bar = (uint64_t*)(sm_a + (size_t)p.stages * stage_bytes);
+  uint8_t* sm_stg = sm_a + (size_t)p.stages * stage_bytes;        // 2 x (N/32) x [128 rows x 128 B], TMA-store staging
+  const int stg_bytes = p.tma_store ? (p.N / 32) * 16384 : 0;
+  uint64_t* full_bar = (uint64_t*)(sm_stg + 2 * stg_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full = empty_bar + p.stages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -276,6 +290,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     HALO_T(0);
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    if (p.tma_store) tma_prefetch_desc(&map_c);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -387,27 +402,50 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       tc_fence_after();
       if (threadIdx.x == 64 && ti < 6) HALO_T(24 + ti * 2);
       float* orow = p.out + ((size_t)(img * p.Hg + h0 + r) * p.Wg + c) * p.N;
+      uint8_t* sbuf = sm_stg + (size_t)(ti & 1) * stg_bytes;
+      if (p.tma_store) {
+        // the staging buffer is free once the stores issued two tiles ago have READ it
+        if (threadIdx.x == 64) tma_store_wait_read1();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
       for (int c0 = 0; c0 < p.N; c0 += 32) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * p.N + c0), v);
         tmem_ld_wait();
-        if (valid) {
+        if (p.relu) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            if (p.relu) {
-              o.x = fmaxf(p.thr, o.x); o.y = fmaxf(p.thr, o.y); o.z = fmaxf(p.thr, o.z); o.w = fmaxf(p.thr, o.w);
-            }
-            *reinterpret_cast<float4*>(orow + c0 + j) = o;
-          }
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(p.thr, v[j]);
+        }
+        if (p.tma_store) {
+          // row m of the 32-channel chunk tile: 128 B, 16-byte piece j at position j ^ (m & 7) (the 128B swizzle of map_c)
+          uint8_t* srow = sbuf + (size_t)(c0 >> 5) * 16384 + m * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(srow + ((j ^ (m & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(orow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
       }
+      // the accumulator is drained: release it to the MMA warp before the (slower) store issue
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (p.tma_store) {
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) {
+          const int rows = min(p.BH, p.Hg - h0);
+          for (int rr = 0; rr < rows; ++rr)
+            for (int cc = 0; cc < p.N / 32; ++cc)
+              tma_store_4d(&map_c, sbuf + (size_t)cc * 16384 + (size_t)rr * p.P * 128, cc * 32, 0, h0 + rr, img);
+          tma_store_commit_group();
+        }
+      }
       if (threadIdx.x == 64 && ti < 6) HALO_T(25 + ti * 2);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.tma_store && threadIdx.x == 64) tma_store_wait_all_groups();  // global writes complete before the kernel ends
   }
   tc_fence_before();
   __syncthreads();
@@ -576,6 +614,7 @@ struct ConvTcPlan {
   IgemmParams fwd{}, dg{};
   HaloParams hfwd{}, hdg{};
   CUtensorMap map_x_h, map_dy_h;       // halo kernels: source boxes [32 ch, P, BH+KH-1, 1]
+  CUtensorMap map_y_out, map_dx_out;   // halo kernels: TMA-store boxes [32 ch, Wg, 1, 1]
   bool halo_fwd = false, halo_dg = false;
   int hfwd_smem = 0, hdg_smem = 0, hfwd_grid = 0, hdg_grid = 0;
   WgradParams wg{};
@@ -598,7 +637,7 @@ static bool conv_fits(const ConvGeom& g) {
 
 
 // Fill a HaloParams for an output grid Hg x Wg whose taps read a source tensor [Csrc, Ws, Hs, N] at origin (ox, oy).
-static bool plan_halo(HaloParams& p, CUtensorMap* map, const float* src, int Csrc, int Ws, int Hs, int Nimg, int Hg, int Wg,
+static bool plan_halo(HaloParams& p, CUtensorMap* map, CUtensorMap* map_out, const float* src, int Csrc, int Ws, int Hs, int Nimg, int Hg, int Wg,
                       int KH, int KW, int Nacc, int b_mn_major, int b_rows_per_tap, int flip, int ox, int oy, float* out,
                       int dev_smem, int* smem_out) {
   p.Hg = Hg; p.Wg = Wg; p.KH = KH; p.KW = KW; p.kchunks = Csrc / 32; p.N = Nacc;
@@ -624,9 +663,20 @@ static bool plan_halo(HaloParams& p, CUtensorMap* map, const float* src, int Csr
   p.bo_mode = (bo && bo[0] == '1') ? 1 : 0;
   const int b_bytes = KH * KW * p.kchunks * Nacc * 128;
   const int stage_bytes = p.kchunks * p.a_tile_bytes;
-  const int fixed = b_bytes + 16 * 16 + 1024 + 256;
+  const char* ts = getenv("SB_TC_TMA_STORE");
+  p.tma_store = !(ts && ts[0] == '0') && p.Wg <= 256;
+  int fixed = b_bytes + 16 * 16 + 1024 + 256 + (p.tma_store ? 2 * (Nacc / 32) * 16384 : 0);
+  if (p.tma_store && (dev_smem - fixed) / stage_bytes < 2) {  // staging does not fit: per-thread stores
+    p.tma_store = 0;
+    fixed = b_bytes + 16 * 16 + 1024 + 256;
+  }
   p.stages = std::min(6, (dev_smem - fixed) / stage_bytes);
   if (p.stages < 2) return false;
+  {
+    uint64_t od[4] = {(uint64_t)Nacc, (uint64_t)Wg, (uint64_t)Hg, (uint64_t)Nimg};
+    uint32_t ob[4] = {32, (uint32_t)Wg, 1, 1};
+    *map_out = make_map(out, 4, od, ob);
+  }
   *smem_out = fixed + p.stages * stage_bytes;
   uint64_t d[4] = {(uint64_t)Csrc, (uint64_t)Ws, (uint64_t)Hs, (uint64_t)Nimg};
   uint32_t b[4] = {32, (uint32_t)p.P, (uint32_t)box_h, 1};
@@ -720,7 +770,7 @@ void tc_plan_layers(sb_engine* e) {
       P->fwd_grid = std::min(p.n_tiles, kNumSMs);
       const char* h = getenv("SB_TC_HALO");
       const bool halo_on = !(h && h[0] == '0');
-      if (halo_on && plan_halo(P->hfwd, &P->map_x_h, x, g.Cin, g.W, g.H, g.N, g.OH, g.OW, g.KH, g.KW, g.Cout, 1, g.Cin, 0, -g.PL,
+      if (halo_on && plan_halo(P->hfwd, &P->map_x_h, &P->map_y_out, x, g.Cin, g.W, g.H, g.N, g.OH, g.OW, g.KH, g.KW, g.Cout, 1, g.Cin, 0, -g.PL,
                                -g.PT, y, dev_smem, &P->hfwd_smem)) {
         P->hfwd.relu = p.relu; P->hfwd.thr = p.thr;
         P->hfwd_grid = std::min(P->hfwd.n_tiles, kNumSMs);
@@ -749,7 +799,7 @@ void tc_plan_layers(sb_engine* e) {
       P->dg_grid = std::min(p.n_tiles, kNumSMs);
       const char* h = getenv("SB_TC_HALO");
       const bool halo_on = !(h && h[0] == '0');
-      if (halo_on && plan_halo(P->hdg, &P->map_dy_h, dy, g.Cout, g.OW, g.OH, g.N, g.H, g.W, g.KH, g.KW, g.Cin, 0, g.Cin, 1,
+      if (halo_on && plan_halo(P->hdg, &P->map_dy_h, &P->map_dx_out, dy, g.Cout, g.OW, g.OH, g.N, g.H, g.W, g.KH, g.KW, g.Cin, 0, g.Cin, 1,
                                -(g.KW - 1 - g.PL), -(g.KH - 1 - g.PT), dx, dev_smem, &P->hdg_smem)) {
         P->hdg_grid = std::min(P->hdg.n_tiles, kNumSMs);
         P->halo_dg = true;
@@ -851,7 +901,7 @@ bool tc_conv_fwd(sb_engine* e, LayerPlan& L, int) {
   ConvTcPlan* P = (ConvTcPlan*)L.tc_plan;
   if (!P || L.tc_kind != 1) return false;
   if (P->halo_fwd) {
-    conv_halo_kernel<<<P->hfwd_grid, kIgemmThreads, P->hfwd_smem, e->stream>>>(P->map_x_h, P->map_w_fwd, P->hfwd);
+    conv_halo_kernel<<<P->hfwd_grid, kIgemmThreads, P->hfwd_smem, e->stream>>>(P->map_x_h, P->map_w_fwd, P->map_y_out, P->hfwd);
     SB_LAUNCHED();
     return true;
   }
@@ -867,8 +917,7 @@ bool tc_conv_wgrad(sb_engine* e, LayerPlan& L, int) {
   const int n = g.KH * g.KW * g.Cin * g.Cout;
   conv_wgrad_kernel<<<P->wg_grid, kWgradThreads, P->wg_smem, e->stream>>>(P->map_dy_wg, P->map_x_wg, P->wg);
   SB_LAUNCHED();
-  wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(P->wg_partial, e->grads + e->params[L.p_w].offset, n, P->wg_grid);
-  SB_LAUNCHED();
+  partial_reduce(P->wg_partial, e->grads + e->params[L.p_w].offset, n, P->wg_grid, e->stream);  // fixed order, 8-way parallel
   return true;
 }
 
@@ -876,7 +925,7 @@ bool tc_conv_dgrad(sb_engine* e, LayerPlan& L, int) {
   ConvTcPlan* P = (ConvTcPlan*)L.tc_plan;
   if (!P || !P->has_dgrad) return false;
   if (P->halo_dg) {
-    conv_halo_kernel<<<P->hdg_grid, kIgemmThreads, P->hdg_smem, e->stream>>>(P->map_dy_h, P->map_w_dg, P->hdg);
+    conv_halo_kernel<<<P->hdg_grid, kIgemmThreads, P->hdg_smem, e->stream>>>(P->map_dy_h, P->map_w_dg, P->map_dx_out, P->hdg);
     SB_LAUNCHED();
     return true;
   }

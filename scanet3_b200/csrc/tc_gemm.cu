@@ -30,6 +30,7 @@ struct GemmParams {
   int M, N, K;
   int BN;
   int a_mn_major, b_mn_major;
+  int a_grouped, b_grouped;  // MN-major operand fetched as ONE 4-D box [32, 32 k, groups, 1] (inner dim % 32 == 0)
   int m_tiles, n_tiles, splits, kb_total, kb_per_split;
   int stages;
   int za, zb, zc;
@@ -46,6 +47,13 @@ __device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* m, ui
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
           smem_u32(smem)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_g(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem, int c0, int c1, int c2) {
@@ -68,6 +76,17 @@ __device__ __forceinline__ float epi_act(float v, int act, float thr) {
     case 4: return fmaxf(thr, v);
     default: return v;
   }
+}
+
+// Tile order: groups of kGroupM row tiles sweep all column tiles before the next group starts, so the CTAs running at any
+// moment share a small set of A row panels (L2-resident) instead of streaming all of A once per column tile.
+constexpr int kGroupM = 16;
+__device__ __forceinline__ void tile_to_mn(int tile, int m_tiles, int n_tiles, int& mt, int& nt) {
+  const int per_group = kGroupM * n_tiles;
+  const int grp = tile / per_group, in = tile - grp * per_group;
+  const int gm = min(kGroupM, m_tiles - grp * kGroupM);  // rows in this (possibly last, shorter) group
+  nt = in / gm;
+  mt = grp * kGroupM + (in - nt * gm);
 }
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -117,7 +136,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       uint32_t phase = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
         const int split = w / tiles, tile = w - split * tiles;
-        const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
+        int mt, nt;
+        tile_to_mn(tile, p.m_tiles, p.n_tiles, mt, nt);
         const int m0 = mt * 128, n0 = nt * p.BN;
         const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -125,13 +145,17 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
           uint8_t* sb = sa + kGemmATile;
           mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-          if (p.a_mn_major) {
+          if (p.a_grouped) {
+            tma_load_4d_g(sa, &map_a, &full_bar[stage], 0, kb * 32, m0 >> 5, p.za);
+          } else if (p.a_mn_major) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) tma_load_3d(sa + j * 4096, &map_a, &full_bar[stage], m0 + j * 32, kb * 32, p.za);
           } else {
             tma_load_3d(sa, &map_a, &full_bar[stage], kb * 32, m0, p.za);
           }
-          if (p.b_mn_major) {
+          if (p.b_grouped) {
+            tma_load_4d_g(sb, &map_b, &full_bar[stage], 0, kb * 32, n0 >> 5, p.zb);
+          } else if (p.b_mn_major) {
             for (int j = 0; j < p.BN / 32; ++j) tma_load_3d(sb + j * 4096, &map_b, &full_bar[stage], n0 + j * 32, kb * 32, p.zb);
           } else {
             tma_load_3d(sb, &map_b, &full_bar[stage], kb * 32, n0, p.zb);
@@ -184,7 +208,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
       const int split = w / tiles, tile = w - split * tiles;
-      const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
+      int mt, nt;
+      tile_to_mn(tile, p.m_tiles, p.n_tiles, mt, nt);
       const int m0 = mt * 128 + sub * 32, n0 = nt * p.BN;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -263,6 +288,19 @@ static CUtensorMap map3(const float* base, uint64_t inner, uint64_t outer, uint6
   return m;
 }
 
+// MN-major operand [slices][K][inner] with inner % 32 == 0, viewed as [slices][inner/32][K][32]: one box {32, 32 k, groups, 1}
+// lands in shared memory as `groups` consecutive [32 k x 128 B] blocks -- exactly the UMMA MN-major tile (LBO = 4096)
+static CUtensorMap map4_grouped(const float* base, uint64_t inner, uint64_t K, uint64_t slices, uint32_t groups) {
+  CUtensorMap m;
+  cuuint64_t gdim[4] = {32, K, inner / 32, slices};
+  cuuint64_t gstr[3] = {inner * 4, 128, inner * K * 4};
+  cuuint32_t box[4] = {32, 32, groups, 1}, es[4] = {1, 1, 1, 1};
+  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled (grouped) failed with code " + std::to_string((int)r));
+  return m;
+}
+
 struct TcGemm {
   CUtensorMap map_a, map_b, map_c;
   GemmParams p{};
@@ -311,8 +349,14 @@ TcGemm* tc_gemm_create(int a_mn_major, int b_mn_major, const float* A, int a_sli
   if (p.stages < 2) { delete g; return nullptr; }
   g->smem = fixed + p.stages * stage_bytes;
   g->grid = std::min(tiles * p.splits, kNumSMs);
-  g->map_a = a_mn_major ? map3(A, M, K, a_slices, 32, true) : map3(A, K, M, a_slices, 128, false);
-  g->map_b = b_mn_major ? map3(B, N, K, b_slices, 32, true) : map3(B, K, N, b_slices, (uint32_t)p.BN, false);
+  const char* ng = getenv("SB_TC_GEMM_NO_GROUPED");
+  const bool grouped_ok = !(ng && ng[0] == '1');
+  p.a_grouped = a_mn_major && grouped_ok && (M % 32 == 0);
+  p.b_grouped = b_mn_major && grouped_ok && (N % 32 == 0);
+  g->map_a = p.a_grouped ? map4_grouped(A, M, K, a_slices, 4)
+                         : (a_mn_major ? map3(A, M, K, a_slices, 32, true) : map3(A, K, M, a_slices, 128, false));
+  g->map_b = p.b_grouped ? map4_grouped(B, N, K, b_slices, (uint32_t)(p.BN / 32))
+                         : (b_mn_major ? map3(B, N, K, b_slices, 32, true) : map3(B, K, N, b_slices, (uint32_t)p.BN, false));
   g->c = C;
   g->c_slice = (long long)M * N;
   if (p.splits > 1) {
