@@ -764,7 +764,12 @@ static void run_optimizer(sb_engine* e, int advance_batch) {
 static void run_prologue(sb_engine* e, bool resident) {
   Prof pr(e, "step_prologue", resident ? 8.0 * (double)(e->in_shape.numel() + e->label_shape.numel()) : 0, 0);
   step_prologue(e->st, resident ? e->ds_x : nullptr, resident ? e->ds_y : nullptr, e->acts[0], e->by, e->in_shape.numel(),
-                e->label_shape.numel(), e->train.beta1, e->train.beta2, e->stream);
+                e->label_shape.numel(), e->train.beta1, e->train.beta2, 1, e->stream);
+}
+static void run_prologue_staged(sb_engine* e, int parity) {
+  Prof pr(e, "step_prologue", 8.0 * (double)(e->in_shape.numel() + e->label_shape.numel()), 0);
+  step_prologue(e->st, e->stage_x[parity], e->stage_y[parity], e->acts[0], e->by, e->in_shape.numel(), e->label_shape.numel(),
+                e->train.beta1, e->train.beta2, 0, e->stream);
 }
 
 static void run_train_step_body(sb_engine* e, bool resident) {
@@ -773,6 +778,15 @@ static void run_train_step_body(sb_engine* e, bool resident) {
   run_loss(e, true);
   run_backward(e);
   run_optimizer(e, resident ? 1 : 0);
+}
+
+// host-fed step whose batch sits in staging buffer `parity` (the bool carries the parity through `capture`)
+static void run_train_step_body_staged(sb_engine* e, bool parity) {
+  run_prologue_staged(e, parity ? 1 : 0);
+  run_forward(e, FWD_TRAIN);
+  run_loss(e, true);
+  run_backward(e);
+  run_optimizer(e, 0);
 }
 
 static cudaGraphExec_t capture(sb_engine* e, long long* nodes, void (*body)(sb_engine*, bool), bool flag) {
@@ -814,6 +828,40 @@ static void launch_train_step(sb_engine* e, bool resident) {
     run_train_step_body(e, resident);
     e->launches += tl_launch_count - before;
   }
+}
+
+static void ensure_staging(sb_engine* e) {
+  if (e->cstream) return;
+  SB_CUDA(cudaStreamCreateWithFlags(&e->cstream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    e->stage_x[i] = dmalloc_floats(pad32(e->in_shape.numel()));
+    e->stage_y[i] = dmalloc_floats(pad32(e->label_shape.numel()));
+    SB_CUDA(cudaEventCreateWithFlags(&e->ev_copied[i], cudaEventDisableTiming));
+    SB_CUDA(cudaEventCreateWithFlags(&e->ev_free[i], cudaEventDisableTiming));
+    SB_CUDA(cudaEventRecord(e->ev_free[i], e->stream));
+  }
+}
+
+// H2D of the batch on the copy stream into the free staging buffer, then the step on the main stream
+static void launch_train_step_staged(sb_engine* e, const float* x, const float* y) {
+  ensure_staging(e);
+  const int par = e->stage_parity;
+  e->stage_parity ^= 1;
+  SB_CUDA(cudaStreamWaitEvent(e->cstream, e->ev_free[par], 0));  // the step that last read this buffer is done
+  SB_CUDA(cudaMemcpyAsync(e->stage_x[par], x, (size_t)e->in_shape.numel() * 4, cudaMemcpyHostToDevice, e->cstream));
+  SB_CUDA(cudaMemcpyAsync(e->stage_y[par], y, (size_t)e->label_shape.numel() * 4, cudaMemcpyHostToDevice, e->cstream));
+  SB_CUDA(cudaEventRecord(e->ev_copied[par], e->cstream));
+  SB_CUDA(cudaStreamWaitEvent(e->stream, e->ev_copied[par], 0));
+  const long long before = tl_launch_count;
+  if (use_graph(e)) {
+    if (!e->g_staged[par]) e->g_staged[par] = capture(e, &e->nodes_staged[par], run_train_step_body_staged, par != 0);
+    SB_CUDA(cudaGraphLaunch(e->g_staged[par], e->stream));
+    e->launches += e->nodes_staged[par];
+  } else {
+    run_train_step_body_staged(e, par != 0);
+    e->launches += tl_launch_count - before;
+  }
+  SB_CUDA(cudaEventRecord(e->ev_free[par], e->stream));
 }
 
 static void launch_loss(sb_engine* e) {
@@ -963,6 +1011,13 @@ extern "C" void sb_engine_destroy(sb_engine* e) {
     if (e->g_resident) cudaGraphExecDestroy(e->g_resident);
     if (e->g_hostfed) cudaGraphExecDestroy(e->g_hostfed);
     if (e->g_loss) cudaGraphExecDestroy(e->g_loss);
+    for (int i = 0; i < 2; ++i) {
+      if (e->g_staged[i]) cudaGraphExecDestroy(e->g_staged[i]);
+      cudaFree(e->stage_x[i]); cudaFree(e->stage_y[i]);
+      if (e->ev_copied[i]) cudaEventDestroy(e->ev_copied[i]);
+      if (e->ev_free[i]) cudaEventDestroy(e->ev_free[i]);
+    }
+    if (e->cstream) { cudaStreamSynchronize(e->cstream); cudaStreamDestroy(e->cstream); }
     tc_free_layers(e);
     lstm_free(e);
     for (auto& L : e->L) { cudaFree(L.bn_save_mean); cudaFree(L.bn_save_var); }
@@ -1144,8 +1199,8 @@ extern "C" int sb_train_step_async(sb_engine* e, const float* x, const float* y,
   if (iter < 1) SB_FAIL(SB_ERR_INVALID_ARG, "iter is the 1-based global step");
   DeviceGuard dg(e->device);
   if (e->host_iter_mirror != iter - 1) set_device_iter(e, iter - 1, 0);
-  upload_batch(e, x, y);
-  launch_train_step(e, false);
+  if (!x) SB_FAIL(SB_ERR_INVALID_ARG, "null x");
+  launch_train_step_staged(e, x, y);
   e->host_iter_mirror = iter;
   if (loss_out_host)
     SB_CUDA(cudaMemcpyAsync(loss_out_host, &e->st->loss, sizeof(float), cudaMemcpyDeviceToHost, e->stream));

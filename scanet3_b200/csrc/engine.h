@@ -115,6 +115,15 @@ struct sb_engine {
   float* head_scratch = nullptr;  // per-CTA partials + completion ticket of the fused classifier-head kernel
   size_t ws_floats = 0;
   cudaStream_t stream = nullptr;
+  // host-fed pipeline (sb_train_step_async): the H2D copy of batch t+1 runs on `cstream` into the other staging buffer while
+  // batch t computes; the step's prologue gathers from its staging buffer
+  cudaStream_t cstream = nullptr;
+  float* stage_x[2] = {nullptr, nullptr};
+  float* stage_y[2] = {nullptr, nullptr};
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+  cudaGraphExec_t g_staged[2] = {nullptr, nullptr};
+  long long nodes_staged[2] = {0, 0};
+  int stage_parity = 0;
   cudaGraphExec_t g_resident = nullptr, g_hostfed = nullptr, g_loss = nullptr;
   long long nodes_resident = 0, nodes_hostfed = 0, nodes_loss = 0;
   long long launches = 0;

@@ -35,7 +35,7 @@ struct OptDesc {
 
 // ---- step prologue: gather the batch out of the resident shard + advance iter / bias corrections ----
 void step_prologue(StepState* st, const float* ds_x, const float* ds_y, float* bx, float* by, long long x_per_batch,
-                   long long y_per_batch, float beta1, float beta2, cudaStream_t s);
+                   long long y_per_batch, float beta1, float beta2, int batch_from_state, cudaStream_t s);
 
 // ---- fp32 FFMA contractions (parity mode; also the shapes tcgen05 does not fit) ----
 // C[M,N] = A[M,K] . B[K,N]

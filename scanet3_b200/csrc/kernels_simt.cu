@@ -15,8 +15,10 @@ thread_local long long tl_launch_count = 0;
 template <typename V>
 __global__ void step_prologue_kernel(StepState* st, const V* __restrict__ ds_x, const V* __restrict__ ds_y,
                                      V* __restrict__ bx, V* __restrict__ by, long long x4, long long y4,
-                                     float beta1, float beta2) {
-  const long long b = st->batch_idx;  // only the optimizer kernel of the previous step writes it
+                                     float beta1, float beta2, int batch_from_state) {
+  // resident shard: batch index from the device state (only the optimizer kernel of the previous step writes it);
+  // host-fed staging buffer: always its single batch
+  const long long b = batch_from_state ? st->batch_idx : 0;
   if (ds_x != nullptr) {
     const V* sx = ds_x + b * x4;
     const V* sy = ds_y + b * y4;
@@ -39,7 +41,7 @@ __global__ void step_prologue_kernel(StepState* st, const V* __restrict__ ds_x, 
 }
 
 void step_prologue(StepState* st, const float* ds_x, const float* ds_y, float* bx, float* by, long long x_per_batch,
-                   long long y_per_batch, float beta1, float beta2, cudaStream_t s) {
+                   long long y_per_batch, float beta1, float beta2, int batch_from_state, cudaStream_t s) {
   // 128-bit copies when every batch of the shard starts 16-byte aligned, scalar copies otherwise
   const bool vec = (x_per_batch % 4 == 0) && (y_per_batch % 4 == 0);
   const long long xn = vec ? x_per_batch / 4 : x_per_batch, yn = vec ? y_per_batch / 4 : y_per_batch;
@@ -48,9 +50,9 @@ void step_prologue(StepState* st, const float* ds_x, const float* ds_y, float* b
   if (blocks < 1) blocks = 1;
   if (vec)
     step_prologue_kernel<float4><<<blocks, 256, 0, s>>>(st, (const float4*)ds_x, (const float4*)ds_y, (float4*)bx,
-                                                        (float4*)by, xn, yn, beta1, beta2);
+                                                        (float4*)by, xn, yn, beta1, beta2, batch_from_state);
   else
-    step_prologue_kernel<float><<<blocks, 256, 0, s>>>(st, ds_x, ds_y, bx, by, xn, yn, beta1, beta2);
+    step_prologue_kernel<float><<<blocks, 256, 0, s>>>(st, ds_x, ds_y, bx, by, xn, yn, beta1, beta2, batch_from_state);
   SB_LAUNCHED();
 }
 

@@ -590,6 +590,150 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   }
 }
 
+
+// =====================================================================================================================
+// Conv2D wgrad, halo form (stride 1).  K = pixels of a chunk of BH output rows laid out on a pitch of P pixels (k = r*P + c);
+// per chunk ONE box brings the dY rows [32 co, P, BH] (columns >= OW zero-filled) and ONE box the X halo rows
+// [32 ci, P, BH+KH-1] per 32-channel slice.  For a kernel row kh and channel slice j the A operand is X^T viewed MN-major with
+// its 32-element M groups ONE pixel row (128 B) apart (LBO = 128): group g is the tap kw = g, so a single M = 128 MMA computes
+// the KW taps of the row at once (rows 32*KW.. of D are unused):
+//     D_(kh,j)[m = (kw, ci), n = co] += sum_k X[k + kh*P + kw][ci] * dY[k][co]
+// -- KH * Cin/32 MMAs per 8 pixels instead of KH*KW*Cin/32.  Accumulators for all (kh, j) stay in TMEM for the CTA's chunks;
+// one partial filter gradient per CTA, reduced in CTA order afterwards (deterministic).
+// =====================================================================================================================
+struct WgradHaloParams {
+  int n_chunks, chunks_per_img;
+  int BH, P, KH, KW, Cin, Cout, OH;
+  int ox, oy;           // X box origin relative to the chunk's first output pixel: (-PL, -PT)
+  int dy_tile_bytes;    // one 32-co slice of the dY chunk (multiple of 1024)
+  int x_tile_bytes;     // one 32-ci slice of the X halo chunk, incl. the KW-1 zeroed tail rows (multiple of 1024)
+  int x_box_bytes, dy_box_bytes;
+  int stages;
+  float* partial;       // [gridDim.x][KH*KW*Cin*Cout]
+};
+
+__global__ void __launch_bounds__(kWgradThreads, 1)
+conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, const WgradHaloParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int co_slices = p.Cout / 32, ci_slices = p.Cin / 32;
+  const int a_bytes = ci_slices * p.x_tile_bytes, b_bytes = co_slices * p.dy_tile_bytes;
+  const int stage_bytes = a_bytes + b_bytes;
+  uint64_t* full_bar = (uint64_t*)(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* done_bar = empty_bar + p.stages;
+  uint32_t* tmem_slot = (uint32_t*)(done_bar + 1);
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const int n_acc = p.KH * ci_slices;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < n_acc * p.Cout) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_dy);
+    tma_prefetch_desc(&map_x);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  // rows of every X tile that TMA never writes (they meet zero dY rows) must not hold NaN bit patterns
+  for (int s = 0; s < p.stages; ++s)
+    for (int j = 0; j < ci_slices; ++j) {
+      uint8_t* t = smem + (size_t)s * stage_bytes + (size_t)j * p.x_tile_bytes;
+      for (int i = p.x_box_bytes + threadIdx.x * 16; i < p.x_tile_bytes; i += blockDim.x * 16) *reinterpret_cast<float4*>(t + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const bool has_work = (int)blockIdx.x < p.n_chunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int ch = blockIdx.x; ch < p.n_chunks; ch += gridDim.x) {
+        const int img = ch / p.chunks_per_img, h0 = (ch - img * p.chunks_per_img) * p.BH;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + (size_t)stage * stage_bytes;
+        uint8_t* sb = sa + a_bytes;
+        mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(ci_slices * p.x_box_bytes + co_slices * p.dy_box_bytes));
+        for (int j = 0; j < ci_slices; ++j) tma_load_4d(sa + (size_t)j * p.x_tile_bytes, &map_x, &full_bar[stage], j * 32, p.ox, h0 + p.oy, img);
+        for (int j = 0; j < co_slices; ++j) tma_load_4d(sb + (size_t)j * p.dy_tile_bytes, &map_dy, &full_bar[stage], j * 32, 0, h0, img);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (has_work) {  // warp-uniform loop, one elected lane issues
+      const uint32_t idesc = idesc_tf32(128, p.Cout, 1, 1);
+      // MN-major SW128 (32-byte atoms): 8 K-rows (1024 B) per instruction; A: 32-element M groups 128 B apart (the KW taps);
+      // B: 32-element N groups one dY slice apart
+      const uint64_t a_d = smem_desc(0, 128, 512, 1), b_d = smem_desc(0, (uint32_t)p.dy_tile_bytes, 512, 1);
+      const uint32_t a_hi = (uint32_t)(a_d >> 32), a_lo0 = (uint32_t)a_d, b_hi = (uint32_t)(b_d >> 32), b_lo0 = (uint32_t)b_d;
+      const int nks = p.BH * p.P / 8;
+      const uint32_t kh_step = (uint32_t)(p.P * 128) >> 4, x_tile = (uint32_t)p.x_tile_bytes >> 4;
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t accumulate = 0;
+      for (int ch = blockIdx.x; ch < p.n_chunks; ch += gridDim.x) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = a_lo0 + (smem_u32(smem + (size_t)stage * stage_bytes) >> 4);
+        const uint32_t sb = b_lo0 + ((smem_u32(smem + (size_t)stage * stage_bytes) + (uint32_t)a_bytes) >> 4);
+        for (int ks = 0; ks < nks; ++ks) {
+          uint32_t d_col = 0;
+          uint32_t at_kh = sa + ks * 64;
+          for (int kh = 0; kh < p.KH; ++kh, at_kh += kh_step) {
+            uint32_t at = at_kh;
+            for (int j = 0; j < ci_slices; ++j, at += x_tile, d_col += p.Cout)
+              umma_tf32_elect(tmem_base + d_col, ((uint64_t)a_hi << 32) | at, ((uint64_t)b_hi << 32) | (sb + ks * 64), idesc, accumulate);
+          }
+          accumulate = 1;
+        }
+        umma_commit_elect(&empty_bar[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit_elect(done_bar);
+    }
+  } else {
+    // epilogue: partial[cta][((kh*KW + kw)*Cin + j*32 + ci)*Cout + co] = D_(kh,j)[kw*32 + ci][co]
+    const int sub = warp & 3;  // = kw (TMEM lanes 32*sub .. 32*sub+31)
+    float* part = p.partial + (size_t)blockIdx.x * p.KH * p.KW * p.Cin * p.Cout;
+    if (has_work) {
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
+    }
+    for (int a = 0; a < n_acc; ++a) {
+      const int kh = a / ci_slices, j = a - kh * ci_slices;
+      float* row = part + ((size_t)((kh * p.KW + sub) * p.Cin + j * 32 + lane)) * p.Cout;
+      for (int c0 = 0; c0 < p.Cout; c0 += 32) {
+        float v[32];
+        if (has_work) {
+          tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(a * p.Cout + c0), v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v[q] = 0.f;
+        }
+        if (sub < p.KW) {
+#pragma unroll
+          for (int q = 0; q < 32; q += 4) *reinterpret_cast<float4*>(row + c0 + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int n, int parts) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -618,6 +762,10 @@ struct ConvTcPlan {
   bool halo_fwd = false, halo_dg = false;
   int hfwd_smem = 0, hdg_smem = 0, hfwd_grid = 0, hdg_grid = 0;
   WgradParams wg{};
+  WgradHaloParams hwg{};
+  CUtensorMap map_dy_hwg, map_x_hwg;
+  bool halo_wg = false;
+  int hwg_smem = 0, hwg_grid = 0;
   int fwd_smem = 0, dg_smem = 0, wg_smem = 0;
   int fwd_grid = 0, dg_grid = 0, wg_grid = 0;
   float* wg_partial = nullptr;
@@ -829,6 +977,55 @@ void tc_plan_layers(sb_engine* e) {
       uint64_t xd[4] = {(uint64_t)g.Cin, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.N};
       P->map_x_wg = make_map(x, 4, xd, yb, true);
     }
+    // ---- wgrad, halo form: KW <= 4 taps share one M = 128 MMA; all KH * Cin/32 accumulators must fit TMEM ----
+    {
+      // Measured on B200 (profiles/r1_notes.md): with MN-major tf32 operands the MMA is bound by the operand fetch, not by
+      // the instruction count, so sharing the KW taps in one M = 128 MMA buys nothing (24.5 us vs 21.1 us for the per-tap
+      // kernel on LeNet conv2).  Kept selectable (SB_TC_HALO_WGRAD=1) and parity-tested; off by default.
+      const char* h = getenv("SB_TC_HALO_WGRAD");
+      const bool on = h && h[0] == '1';
+      WgradHaloParams& p = P->hwg;
+      const int n_acc = g.KH * (g.Cin / 32);
+      if (on && g.KW <= 4 && n_acc * g.Cout <= 512) {
+        // pitch P >= OW + KW - 1 and rows per chunk BH: BH*P % 8 == 0, boxes <= 256 rows; minimise rounds x k-steps per chunk
+        double best = 1e30;
+        int bP = 0, bBH = 0;
+        for (int Pc = g.OW + g.KW - 1; Pc <= g.OW + g.KW - 1 + 8 && Pc <= 256; ++Pc)
+          for (int BH = 1; BH <= g.OH; ++BH) {
+            if ((BH * Pc) % 8 || (BH + g.KH - 1) > 256) continue;
+            const int rows_x = (BH + g.KH - 1) * Pc + g.KW - 1;
+            const int stage = (g.Cin / 32) * ((rows_x + 7) / 8) * 1024 + (g.Cout / 32) * BH * Pc * 128;
+            if (2 * stage + 4096 > dev_smem) continue;
+            const long long chunks = (long long)g.N * ((g.OH + BH - 1) / BH);
+            const double cost = (double)((chunks + kNumSMs - 1) / kNumSMs) * (BH * Pc / 8 + 6);
+            if (cost < best) { best = cost; bP = Pc; bBH = BH; }
+          }
+        if (bP) {
+          p.BH = bBH; p.P = bP; p.KH = g.KH; p.KW = g.KW; p.Cin = g.Cin; p.Cout = g.Cout; p.OH = g.OH;
+          p.ox = -g.PL; p.oy = -g.PT;
+          p.chunks_per_img = (g.OH + p.BH - 1) / p.BH;
+          p.n_chunks = g.N * p.chunks_per_img;
+          p.dy_box_bytes = p.BH * p.P * 128;
+          p.dy_tile_bytes = p.dy_box_bytes;  // BH*P % 8 == 0 => multiple of 1024
+          p.x_box_bytes = (p.BH + g.KH - 1) * p.P * 128;
+          p.x_tile_bytes = (((p.BH + g.KH - 1) * p.P + g.KW - 1 + 7) / 8) * 1024;
+          const int stage_bytes = (g.Cin / 32) * p.x_tile_bytes + (g.Cout / 32) * p.dy_tile_bytes;
+          p.stages = std::max(2, std::min(4, (dev_smem - 4096) / stage_bytes));
+          P->hwg_grid = (int)std::min<long long>(p.n_chunks, kNumSMs);
+          P->hwg_smem = p.stages * stage_bytes + 16 * (2 * p.stages + 2) + 16 + 1024;
+          if (P->hwg_smem <= dev_smem && P->hwg_grid <= P->wg_grid) {  // the partial buffer is sized for wg_grid CTAs
+            p.partial = P->wg_partial;
+            uint64_t yd[4] = {(uint64_t)g.Cout, (uint64_t)g.OW, (uint64_t)g.OH, (uint64_t)g.N};
+            uint32_t yb[4] = {32, (uint32_t)p.P, (uint32_t)p.BH, 1};
+            P->map_dy_hwg = make_map(dy, 4, yd, yb, true);
+            uint64_t xd[4] = {(uint64_t)g.Cin, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.N};
+            uint32_t xb[4] = {32, (uint32_t)p.P, (uint32_t)(p.BH + g.KH - 1), 1};
+            P->map_x_hwg = make_map(x, 4, xd, xb, true);
+            P->halo_wg = true;
+          }
+        }
+      }
+    }
     if (P->fwd_smem > dev_smem || P->dg_smem > dev_smem || P->wg_smem > dev_smem) {
       cudaFree(P->wg_partial);
       delete P;
@@ -843,6 +1040,7 @@ void tc_plan_layers(sb_engine* e) {
     SB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
     SB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
     SB_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
+    SB_CUDA(cudaFuncSetAttribute(conv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
     attr_set = true;
   }
 }
@@ -915,6 +1113,12 @@ bool tc_conv_wgrad(sb_engine* e, LayerPlan& L, int) {
   if (!P) return false;
   const ConvGeom& g = L.cg;
   const int n = g.KH * g.KW * g.Cin * g.Cout;
+  if (P->halo_wg) {
+    conv_wgrad_halo_kernel<<<P->hwg_grid, kWgradThreads, P->hwg_smem, e->stream>>>(P->map_dy_hwg, P->map_x_hwg, P->hwg);
+    SB_LAUNCHED();
+    partial_reduce(P->wg_partial, e->grads + e->params[L.p_w].offset, n, P->hwg_grid, e->stream);
+    return true;
+  }
   conv_wgrad_kernel<<<P->wg_grid, kWgradThreads, P->wg_smem, e->stream>>>(P->map_dy_wg, P->map_x_wg, P->wg);
   SB_LAUNCHED();
   partial_reduce(P->wg_partial, e->grads + e->params[L.p_w].offset, n, P->wg_grid, e->stream);  // fixed order, 8-way parallel
