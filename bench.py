@@ -315,20 +315,30 @@ def run_ours(args):
         eng.profile_enable(False)
         tot = sum(r["total_ms"] for r in prof_rows) or 1.0
         top = prof_rows[0]
-        per_launch_ms = top["total_ms"] / max(psteps, 1)
-        tensor_bound = top["flops"] > 0 and ("tf32" in top["name"] or "tc" in top["name"])
+        n_launch = max(top["launches"], 1)                     # launches of the class over the profiled steps
+        per_launch_s = top["total_ms"] / 1000.0 / n_launch     # average launch duration (CUDA events, engine stream)
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(top["name"], {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        tensor_bound = top["flops"] > 0 and "tcgen05" in top["name"]
         if tensor_bound:
-            ach = top["flops"] / psteps / (per_launch_ms / 1000.0) / 1e12
+            ach = top["flops"] / n_launch / per_launch_s / 1e12
             peak = bf16 / 2.0
             roofline = {"bound": "tensor", "kernel": top["name"], "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                        "frac": ach / peak, "traffic": None, "share_of_step": top["total_ms"] / tot,
+                        "frac": ach / peak, "traffic": traffic, "share_of_step": top["total_ms"] / tot,
                         "peak_note": f"TF32 dense peak taken as 1/2 x bf16 cuBLAS sustained ({bf16:.0f} TF/s) {which}"}
         else:
-            ach = top["bytes"] / psteps / (per_launch_ms / 1000.0) / 1e9
+            ach = top["bytes"] / n_launch / per_launch_s / 1e9
             roofline = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": hbm, "unit": "GB/s",
-                        "frac": ach / hbm, "traffic": None, "share_of_step": top["total_ms"] / tot,
+                        "frac": ach / hbm, "traffic": traffic, "share_of_step": top["total_ms"] / tot,
                         "peak_note": f"HBM copy bandwidth {which}"}
-        roofline["avg_launch_us"] = per_launch_ms * 1000.0
+        roofline["avg_launch_us"] = per_launch_s * 1e6
+        roofline["launches_per_step"] = n_launch / max(psteps, 1)
+        roofline["algorithmic_per_launch"] = (top["flops"] if tensor_bound else top["bytes"]) / n_launch
+        roofline["traffic_note"] = ("dram bytes per launch from profiles/r1_traffic.json (one ncu --set full capture, cold L2)"
+                                    if traffic else "no ncu capture of this kernel class")
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config == "cfg2":
