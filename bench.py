@@ -293,6 +293,28 @@ def run_ours(args):
     e2e_value = world * args.steps * BATCH / max(e2e_ms / 1000.0, 1e-9)
     last_loss = float(loss_h[max(args.warmup, 3) + args.steps - 1].item())
 
+    # ---- the exchange step alone: fused P2P averaging kernel (flag barriers + reduce-scatter + all-gather over NVLink) ----
+    averaging = None
+    if avg is not None and coll == N.COLL_P2P:
+        reps = 10
+        avg.average_async(steps_per_epoch)
+        barrier()
+        ev0.record(stream)
+        for _ in range(reps):
+            avg.average_async(steps_per_epoch)
+        ev1.record(stream)
+        barrier()
+        a_ms = ev0.elapsed_time(ev1) / reps
+        t = torch.tensor([a_ms], device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        a_ms = float(t.item())
+        arena_bytes = eng.arena()[1] * 4
+        bus = 2.0 * (world - 1) / world * arena_bytes / (a_ms / 1000.0) / 1e9  # per GPU, each direction carries (k-1)/k of it
+        averaging = {"ms": a_ms, "arena_bytes": arena_bytes, "bus_GBps_per_gpu": bus, "per_direction_GBps": bus / 2.0,
+                     "peak_per_direction_GBps": 770.0, "frac": bus / 2.0 / 770.0,
+                     "note": "one kernel per rank incl. two cross-GPU flag barriers; peak = measured NVLink peer copy per direction "
+                             "(B200_PROFILING.md)"}
+
     # ---- per-kernel-class device times over the same steps (eager launches bracketed by CUDA events on the engine
     #      stream) -> the dominant kernel and its roofline ----
     roofline = None
@@ -361,7 +383,7 @@ def run_ours(args):
                        "cuda_graph": True, "flop_per_sample": FLOP_PER_SAMPLE},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": xb + yb, "d2h_bytes_per_step": 4,
                     "wall_s": e2e_wall, "last_loss": last_loss},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "averaging": averaging,
             "model_tflops": value * FLOP_PER_SAMPLE / 1e12,
             "kernels": [{"name": r["name"], "ms_per_step": r["total_ms"] / max(1, min(args.steps, 50, steps_per_epoch)),
                          "launches_per_step": r["launches"] / max(1, min(args.steps, 50, steps_per_epoch))} for r in prof_rows[:16]],

@@ -78,7 +78,9 @@ struct IgemmParams {
   int stages;
   int relu;
   float thr;
-  float* out;         // [n_img*Hg*Wg, N]
+  float* out;         // [n_img*Hg*Wg, ldc]: this launch writes columns [n0, n0 + N)
+  int ldc, n0;        // output row pitch (all channels) and the first output channel of this launch
+  int pt, pl;         // padding before (top, left) of the source grid: taps read (h + sign*kh - pt, w + sign*kw - pl)
 };
 
 constexpr int kIgemmThreads = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..5: epilogue
@@ -97,7 +99,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // shfl: provably warp-uniform
   const int a_box_bytes = p.BH * p.Wg * 128;
   const int kblocks = p.KH * p.KW * p.kchunks;
   uint32_t tmem_cols = 32;
@@ -129,28 +131,32 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const int img = tile / p.tiles_per_img, h0 = (tile % p.tiles_per_img) * p.BH;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          const int tap = kb / p.kchunks, kc = kb % p.kchunks;
-          const int kh = tap / p.KW, kw = tap % p.KW;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + (size_t)stage * stage_bytes;
-          uint8_t* sb = sa + kATileBytes;
-          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(a_box_bytes + b_tile_bytes));
-          tma_load_4d(sa, &map_a, &full_bar[stage], kc * 32, p.sign * kw, h0 + p.sign * kh, img);
-          if (p.b_mn_major) {
-            for (int j = 0; j < p.N / 32; ++j)
-              tma_load_2d(sb + j * 4096, &map_b, &full_bar[stage], j * 32, tap * p.b_rows_per_tap + kc * 32);
-          } else {
-            tma_load_2d(sb, &map_b, &full_bar[stage], kc * 32, tap * p.b_rows_per_tap);
-          }
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
-        }
+        int tap = 0;
+        for (int kh = 0; kh < p.KH; ++kh)
+          for (int kw = 0; kw < p.KW; ++kw, ++tap)
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* sa = smem + (size_t)stage * stage_bytes;
+              uint8_t* sb = sa + kATileBytes;
+              mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(a_box_bytes + b_tile_bytes));
+              tma_load_4d(sa, &map_a, &full_bar[stage], kc * 32, p.sign * kw - p.pl, h0 + p.sign * kh - p.pt, img);
+              if (p.b_mn_major) {
+                for (int j = 0; j < p.N / 32; ++j)
+                  tma_load_2d(sb + j * 4096, &map_b, &full_bar[stage], p.n0 + j * 32, tap * p.b_rows_per_tap + kc * 32);
+              } else {
+                tma_load_2d(sb, &map_b, &full_bar[stage], kc * 32, tap * p.b_rows_per_tap + p.n0);
+              }
+              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer (one thread) =================
-    if (lane == 0) {
+    // ================= MMA issuer: warp-uniform loop, one elected lane issues =================
+    {
       const uint32_t idesc = idesc_tf32(128, p.N, 0, p.b_mn_major);
+      const uint64_t a_d = smem_desc_sw128(0, 16, 1024), b_d = p.b_mn_major ? smem_desc(0, 4096, 512, 1) : smem_desc_sw128(0, 16, 1024);
+      const uint32_t a_hi = (uint32_t)(a_d >> 32), a_lo0 = (uint32_t)a_d, b_hi = (uint32_t)(b_d >> 32), b_lo0 = (uint32_t)b_d;
+      const uint32_t b_ks_step = p.b_mn_major ? (1024u >> 4) : (32u >> 4);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -159,21 +165,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.N);
+        uint32_t accumulate = 0;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint32_t sb = sa + kATileBytes;
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes) >> 4;
+          const uint32_t at = a_lo0 + sa, bt = b_lo0 + sa + (uint32_t)(kATileBytes >> 4);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {  // 4 x (K = 8 tf32) per 32-channel chunk
-            const uint64_t da = smem_desc_sw128(sa + ks * 32, 16, 1024);
-            const uint64_t db = p.b_mn_major ? smem_desc(sb + ks * 1024, 4096, 512, 1) : smem_desc_sw128(sb + ks * 32, 16, 1024);
-            umma_tf32(d_tmem, da, db, idesc, (kb | ks) ? 1u : 0u);
+            umma_tf32_elect(d_tmem, ((uint64_t)a_hi << 32) | (at + ks * 2), ((uint64_t)b_hi << 32) | (bt + ks * b_ks_step), idesc, accumulate);
+            accumulate = 1;
           }
-          umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs have read it
+          umma_commit_elect(&empty_bar[stage]);  // smem slot is free once these MMAs have read it
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);
+        umma_commit_elect(&tmem_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -188,7 +194,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const int rows_valid = min(p.BH, p.Hg - h0) * p.Wg;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      float* orow = p.out + ((size_t)(img * p.Hg + h0) * p.Wg + row) * p.N;
+      float* orow = p.out + ((size_t)(img * p.Hg + h0) * p.Wg + row) * p.ldc + p.n0;
       for (int c0 = 0; c0 < p.N; c0 += 32) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * p.N + c0), v);
@@ -468,6 +474,9 @@ struct WgradParams {
   int n_chunks, chunks_per_img;
   int BH, WK;
   int KH, KW, Cin, Cout;
+  int t0, nt;      // this launch accumulates taps [t0, t0 + nt)  (nt * Cin <= 512 TMEM columns)
+  int co0, Mh;     // ... for output channels [co0, co0 + Mh), Mh = 64 or 128 (the UMMA M)
+  int pt, pl;      // padding before: tap (kh,kw) pairs dY(oh,ow) with X(oh + kh - pt, ow + kw - pl); OOB pixels are zero-filled
   int stages;
   float* partial;  // [gridDim.x][taps*Cin*Cout]
 };
@@ -477,10 +486,10 @@ __global__ void __launch_bounds__(kWgradThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, const WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const int taps = p.KH * p.KW;
+  const int taps = p.nt;  // taps of this launch
   const int krows = p.BH * p.WK;            // K rows per chunk (multiple of 8)
   const int box_bytes = krows * 128;        // one 32-channel box
-  const int a_bytes = (p.Cout / 32) * box_bytes;
+  const int a_bytes = (p.Mh / 32) * box_bytes;
   const int b_bytes = taps * (p.Cin / 32) * box_bytes;
   const int stage_bytes = ((a_bytes + b_bytes + 1023) / 1024) * 1024;
   uint64_t* full_bar = (uint64_t*)(smem + (size_t)p.stages * stage_bytes);
@@ -519,16 +528,17 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
         uint8_t* sa = smem + (size_t)stage * stage_bytes;
         uint8_t* sb = sa + a_bytes;
         mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(a_bytes + b_bytes));
-        for (int j = 0; j < p.Cout / 32; ++j) tma_load_4d(sa + j * box_bytes, &map_dy, &full_bar[stage], j * 32, 0, h0, img);
+        for (int j = 0; j < p.Mh / 32; ++j) tma_load_4d(sa + j * box_bytes, &map_dy, &full_bar[stage], p.co0 + j * 32, 0, h0, img);
         for (int t = 0; t < taps; ++t)
           for (int j = 0; j < p.Cin / 32; ++j)
-            tma_load_4d(sb + (t * (p.Cin / 32) + j) * box_bytes, &map_x, &full_bar[stage], j * 32, t % p.KW, h0 + t / p.KW, img);
+            tma_load_4d(sb + (t * (p.Cin / 32) + j) * box_bytes, &map_x, &full_bar[stage], j * 32, (p.t0 + t) % p.KW - p.pl,
+                        h0 + (p.t0 + t) / p.KW - p.pt, img);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (has_work) {  // warp-uniform loop, one elected lane issues
-      const uint32_t idesc = idesc_tf32(p.Cout, p.Cin, 1, 1);  // M = Cout (64 or 128), N = Cin, both MN-major
+      const uint32_t idesc = idesc_tf32(p.Mh, p.Cin, 1, 1);  // M = 64 or 128 output channels, N = Cin, both MN-major
       // MN-major SW128 (32-byte atoms): 8 K-rows per instruction (one swizzle atom deep), 32-element groups along M/N LBO apart
       const uint64_t tmpl = smem_desc(0, (uint32_t)box_bytes, 512, 1);
       const uint32_t d_hi = (uint32_t)(tmpl >> 32), d_lo = (uint32_t)tmpl;
@@ -559,9 +569,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   } else {
     // epilogue: partial[cta][(t*Cin + ci)*Cout + co] = D_t[co][ci]
     const int sub = warp & 3;
-    float* part = p.partial + (size_t)blockIdx.x * taps * p.Cin * p.Cout;
+    float* part = p.partial + (size_t)blockIdx.x * p.KH * p.KW * p.Cin * p.Cout + (size_t)p.t0 * p.Cin * p.Cout + p.co0;
     int co = -1;
-    if (p.Cout == 128) co = sub * 32 + lane;                  // M = 128: TMEM lane == row
+    if (p.Mh == 128) co = sub * 32 + lane;                    // M = 128: TMEM lane == row
     else if (lane < 16) co = sub * 16 + lane;                 // M = 64: row m sits in lane (m % 16) + 32 * (m / 16)
     if (has_work) {
       mbar_wait(done_bar, 0);
@@ -762,6 +772,9 @@ struct ConvTcPlan {
   bool halo_fwd = false, halo_dg = false;
   int hfwd_smem = 0, hdg_smem = 0, hfwd_grid = 0, hdg_grid = 0;
   WgradParams wg{};
+  std::vector<WgradParams> wg_list;   // launches of the per-tap wgrad kernel (tap groups x channel halves)
+  std::vector<int> wg_smem_list;
+  bool wg_ok = false;
   WgradHaloParams hwg{};
   CUtensorMap map_dy_hwg, map_x_hwg;
   bool halo_wg = false;
@@ -774,12 +787,12 @@ struct ConvTcPlan {
 };
 
 static bool conv_fits(const ConvGeom& g) {
-  // stride 1, VALID, channel counts that tile into 32-float (128 B) swizzle rows and legal UMMA shapes
-  if (g.SH != 1 || g.SW != 1 || g.PT != 0 || g.PL != 0) return false;
+  // stride 1 (any padding: TMA zero-fills out-of-bounds pixels), channel counts that tile into 32-float (128 B) swizzle rows
+  // and legal UMMA N.  wgrad additionally needs Cout % 64 == 0 (UMMA M) and runs as several launches when taps*Cin > 512
+  // TMEM columns or Cout > 128; when it does not fit the fp32 kernel computes the filter gradient.
+  if (g.SH != 1 || g.SW != 1) return false;
   if (g.Cin % 32 || g.Cout % 32 || g.Cin > 256 || g.Cout > 256) return false;
   if (g.OW > 128 || g.W > 128) return false;
-  if (g.Cout != 64 && g.Cout != 128) return false;          // wgrad: UMMA M = Cout
-  if (g.KH * g.KW * g.Cin > 512) return false;               // wgrad: taps*Cin TMEM columns
   return true;
 }
 
@@ -907,6 +920,7 @@ void tc_plan_layers(sb_engine* e) {
       p.relu = P->relu_fused ? 1 : 0;
       p.thr = P->relu_fused ? e->L[li + 1].d.relu_threshold : 0.f;
       p.out = y;
+      p.ldc = g.Cout; p.n0 = 0; p.pt = g.PT; p.pl = g.PL;
       p.stages = std::max(2, std::min(8, (dev_smem - 2048) / (kATileBytes + p.N * 128)));
       uint64_t xd[4] = {(uint64_t)g.Cin, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.N};
       uint32_t xb[4] = {32, (uint32_t)p.Wg, (uint32_t)p.BH, 1};
@@ -936,6 +950,7 @@ void tc_plan_layers(sb_engine* e) {
       p.b_rows_per_tap = g.Cin;
       p.relu = 0; p.thr = 0.f;
       p.out = dx;
+      p.ldc = g.Cin; p.n0 = 0; p.pt = -g.PT; p.pl = -g.PL;
       p.stages = std::max(2, std::min(8, (dev_smem - 2048) / (kATileBytes + p.N * 128)));
       uint64_t yd[4] = {(uint64_t)g.Cout, (uint64_t)g.OW, (uint64_t)g.OH, (uint64_t)g.N};
       uint32_t yb[4] = {32, (uint32_t)p.Wg, (uint32_t)p.BH, 1};
@@ -953,24 +968,37 @@ void tc_plan_layers(sb_engine* e) {
         P->halo_dg = true;
       }
     }
-    // ---- wgrad ----
-    {
-      WgradParams& p = P->wg;
-      p.KH = g.KH; p.KW = g.KW; p.Cin = g.Cin; p.Cout = g.Cout;
+    // ---- wgrad: one launch per (group of taps whose accumulators fit 512 TMEM columns) x (64/128 output channels) ----
+    P->wg_ok = g.Cout % 64 == 0;
+    if (P->wg_ok) {
+      const int Mh = g.Cout % 128 == 0 ? 128 : 64;
+      const int tpp = std::max(1, std::min(taps, 512 / g.Cin));  // taps per launch
+      WgradParams p{};
+      p.KH = g.KH; p.KW = g.KW; p.Cin = g.Cin; p.Cout = g.Cout; p.Mh = Mh; p.pt = g.PT; p.pl = g.PL;
       p.WK = (g.OW + 7) / 8 * 8;
       const int box_row_bytes = p.WK * 128;  // one grid row of one 32-channel box
-      const int per_bh = (g.Cout / 32 + taps * (g.Cin / 32)) * box_row_bytes;
+      const int per_bh = (Mh / 32 + tpp * (g.Cin / 32)) * box_row_bytes;
       // deepest chunk that still leaves >= 2 pipeline stages
       p.BH = std::max(1, std::min(g.OH, (dev_smem - 4096) / 2 / per_bh));
       while (p.BH > 1 && 256 / p.WK < p.BH) --p.BH;  // TMA box dims <= 256
-      const int stage_bytes = ((p.BH * per_bh + 1023) / 1024) * 1024;
-      p.stages = std::max(1, std::min(4, (dev_smem - 4096) / stage_bytes));
       p.chunks_per_img = (g.OH + p.BH - 1) / p.BH;
       p.n_chunks = g.N * p.chunks_per_img;
       P->wg_grid = std::min(p.n_chunks, kNumSMs);
-      P->wg_smem = p.stages * stage_bytes + 16 * (2 * p.stages + 2) + 16 + 1024;
       SB_CUDA(cudaMalloc((void**)&P->wg_partial, (size_t)P->wg_grid * taps * g.Cin * g.Cout * sizeof(float)));
       p.partial = P->wg_partial;
+      for (int t0 = 0; t0 < taps; t0 += tpp)
+        for (int co0 = 0; co0 < g.Cout; co0 += Mh) {
+          WgradParams q = p;
+          q.t0 = t0; q.nt = std::min(tpp, taps - t0); q.co0 = co0;
+          const int stage_bytes = ((p.BH * (Mh / 32 + q.nt * (g.Cin / 32)) * box_row_bytes + 1023) / 1024) * 1024;
+          q.stages = std::max(1, std::min(4, (dev_smem - 4096) / stage_bytes));
+          const int smem = q.stages * stage_bytes + 16 * (2 * q.stages + 2) + 16 + 1024;
+          if (smem > dev_smem) P->wg_ok = false;
+          P->wg_list.push_back(q);
+          P->wg_smem_list.push_back(smem);
+          P->wg_smem = std::max(P->wg_smem, smem);
+        }
+      P->wg = P->wg_list[0];
       uint64_t yd[4] = {(uint64_t)g.Cout, (uint64_t)g.OW, (uint64_t)g.OH, (uint64_t)g.N};
       uint32_t yb[4] = {32, (uint32_t)p.WK, (uint32_t)p.BH, 1};
       P->map_dy_wg = make_map(dy, 4, yd, yb, true);
@@ -986,7 +1014,7 @@ void tc_plan_layers(sb_engine* e) {
       const bool on = h && h[0] == '1';
       WgradHaloParams& p = P->hwg;
       const int n_acc = g.KH * (g.Cin / 32);
-      if (on && g.KW <= 4 && n_acc * g.Cout <= 512) {
+      if (on && P->wg_ok && g.KW <= 4 && n_acc * g.Cout <= 512) {
         // pitch P >= OW + KW - 1 and rows per chunk BH: BH*P % 8 == 0, boxes <= 256 rows; minimise rounds x k-steps per chunk
         double best = 1e30;
         int bP = 0, bBH = 0;
@@ -1026,7 +1054,7 @@ void tc_plan_layers(sb_engine* e) {
         }
       }
     }
-    if (P->fwd_smem > dev_smem || P->dg_smem > dev_smem || P->wg_smem > dev_smem) {
+    if (P->fwd_smem > dev_smem || P->dg_smem > dev_smem) {
       cudaFree(P->wg_partial);
       delete P;
       continue;
@@ -1110,7 +1138,7 @@ bool tc_conv_fwd(sb_engine* e, LayerPlan& L, int) {
 
 bool tc_conv_wgrad(sb_engine* e, LayerPlan& L, int) {
   ConvTcPlan* P = (ConvTcPlan*)L.tc_plan;
-  if (!P) return false;
+  if (!P || L.tc_kind != 1 || !P->wg_ok) return false;
   const ConvGeom& g = L.cg;
   const int n = g.KH * g.KW * g.Cin * g.Cout;
   if (P->halo_wg) {
@@ -1119,15 +1147,17 @@ bool tc_conv_wgrad(sb_engine* e, LayerPlan& L, int) {
     partial_reduce(P->wg_partial, e->grads + e->params[L.p_w].offset, n, P->hwg_grid, e->stream);
     return true;
   }
-  conv_wgrad_kernel<<<P->wg_grid, kWgradThreads, P->wg_smem, e->stream>>>(P->map_dy_wg, P->map_x_wg, P->wg);
-  SB_LAUNCHED();
+  for (size_t i = 0; i < P->wg_list.size(); ++i) {
+    conv_wgrad_kernel<<<P->wg_grid, kWgradThreads, P->wg_smem_list[i], e->stream>>>(P->map_dy_wg, P->map_x_wg, P->wg_list[i]);
+    SB_LAUNCHED();
+  }
   partial_reduce(P->wg_partial, e->grads + e->params[L.p_w].offset, n, P->wg_grid, e->stream);  // fixed order, 8-way parallel
   return true;
 }
 
 bool tc_conv_dgrad(sb_engine* e, LayerPlan& L, int) {
   ConvTcPlan* P = (ConvTcPlan*)L.tc_plan;
-  if (!P || !P->has_dgrad) return false;
+  if (!P || L.tc_kind != 1 || !P->has_dgrad) return false;
   if (P->halo_dg) {
     conv_halo_kernel<<<P->hdg_grid, kIgemmThreads, P->hdg_smem, e->stream>>>(P->map_dy_h, P->map_w_dg, P->map_dx_out, P->hdg);
     SB_LAUNCHED();

@@ -49,6 +49,12 @@ CONV_STACKS = [
                      ("flatten",), ("dense", 10, "softmax")], 3, (7, 9, 1)),
     ("cout128_tanh", [("conv", 64, "tanh", (3, 3), (1, 1), "Valid", False), ("conv", 128, "tanh", (2, 2), (1, 1), "Valid", False),
                       ("flatten",), ("dense", 10, "softmax")], 4, (13, 13, 3)),
+    # BASELINE config 5 geometry (Cin 64 -> Cout 128 -> Cout 256, 3x3): the filter no longer fits shared memory (per-tap kernel),
+    # taps*Cin > 512 TMEM columns and Cout = 256 (wgrad in tap groups x channel halves), tiny 6x6 -> 4x4 grids
+    ("cifar_tail_tanh", [("conv", 64, "tanh", (3, 3), (1, 1), "Valid", False), ("conv", 128, "tanh", (3, 3), (1, 1), "Valid", False),
+                         ("conv", 256, "tanh", (3, 3), (1, 1), "Valid", False), ("flatten",), ("dense", 10, "softmax")], 6, (10, 10, 3)),
+    ("same_pad_tanh", [("conv", 32, "tanh", (3, 3), (1, 1), "Valid", False), ("conv", 64, "tanh", (3, 3), (1, 1), "Same", False),
+                       ("flatten",), ("dense", 10, "softmax")], 4, (9, 9, 2)),
     ("ragged_1x3_tanh", [("conv", 32, "tanh", (2, 2), (1, 1), "Valid", False), ("conv", 64, "tanh", (1, 3), (1, 1), "Valid", False),
                          ("flatten",), ("dense", 10, "softmax")], 7, (5, 37, 2)),
 ]
