@@ -692,17 +692,146 @@ __global__ void bn_apply_kernel(const float* __restrict__ x, float* __restrict__
     y[i] = o;
   }
 }
+
+// ---- 128-bit BatchNorm kernels (C % 4 == 0): same arithmetic as the scalar functors above, four channels per thread ----
+// MODE 0: (sum x, -)   MODE 1: (sum (x - mean)^2, -)   MODE 2: (sum dy, sum dy * (x - mean_in))
+template <int MODE>
+__global__ void __launch_bounds__(256) bn_col_reduce4_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                             const float* __restrict__ save_mean, const float* __restrict__ save_var,
+                                                             float* __restrict__ partial, long long rows, int C, long long rows_per_chunk,
+                                                             float frows, int quirk) {
+  __shared__ float4 r0s[8][33];
+  __shared__ float4 r1s[8][33];
+  const int c4 = blockIdx.x * 32 + threadIdx.x;
+  const bool ok = c4 * 4 < C;
+  const long long ra = (long long)blockIdx.y * rows_per_chunk;
+  const long long rb = ra + rows_per_chunk < rows ? ra + rows_per_chunk : rows;
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, mu = a0;
+  if (ok && MODE >= 1) {
+    mu = *reinterpret_cast<const float4*>(save_mean + c4 * 4);
+    if (MODE == 2 && quirk) {  // reference wiring: the "mean" fed back is var_b * R/(R-1)
+      const float4 v = *reinterpret_cast<const float4*>(save_var + c4 * 4);
+      const float k = __fdiv_rn(frows, __fsub_rn(frows, 1.f));
+      mu = make_float4(__fmul_rn(v.x, k), __fmul_rn(v.y, k), __fmul_rn(v.z, k), __fmul_rn(v.w, k));
+    }
+  }
+  if (ok) {
+#pragma unroll 4
+    for (long long r = ra + threadIdx.y; r < rb; r += 8) {
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(x + r * C + c4 * 4));
+      if (MODE == 0) {
+        a0.x = __fadd_rn(a0.x, xv.x); a0.y = __fadd_rn(a0.y, xv.y); a0.z = __fadd_rn(a0.z, xv.z); a0.w = __fadd_rn(a0.w, xv.w);
+      } else if (MODE == 1) {
+        const float dx_ = __fsub_rn(xv.x, mu.x), dy_ = __fsub_rn(xv.y, mu.y), dz_ = __fsub_rn(xv.z, mu.z), dw_ = __fsub_rn(xv.w, mu.w);
+        a0.x = __fadd_rn(a0.x, __fmul_rn(dx_, dx_)); a0.y = __fadd_rn(a0.y, __fmul_rn(dy_, dy_));
+        a0.z = __fadd_rn(a0.z, __fmul_rn(dz_, dz_)); a0.w = __fadd_rn(a0.w, __fmul_rn(dw_, dw_));
+      } else {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(dy + r * C + c4 * 4));
+        a0.x = __fadd_rn(a0.x, g.x); a0.y = __fadd_rn(a0.y, g.y); a0.z = __fadd_rn(a0.z, g.z); a0.w = __fadd_rn(a0.w, g.w);
+        a1.x = __fadd_rn(a1.x, __fmul_rn(g.x, __fsub_rn(xv.x, mu.x))); a1.y = __fadd_rn(a1.y, __fmul_rn(g.y, __fsub_rn(xv.y, mu.y)));
+        a1.z = __fadd_rn(a1.z, __fmul_rn(g.z, __fsub_rn(xv.z, mu.z))); a1.w = __fadd_rn(a1.w, __fmul_rn(g.w, __fsub_rn(xv.w, mu.w)));
+      }
+    }
+  }
+  r0s[threadIdx.y][threadIdx.x] = a0;
+  r1s[threadIdx.y][threadIdx.x] = a1;
+  __syncthreads();
+  if (threadIdx.y == 0 && ok) {
+    for (int j = 1; j < 8; ++j) {
+      const float4 u = r0s[j][threadIdx.x], v = r1s[j][threadIdx.x];
+      a0.x = __fadd_rn(a0.x, u.x); a0.y = __fadd_rn(a0.y, u.y); a0.z = __fadd_rn(a0.z, u.z); a0.w = __fadd_rn(a0.w, u.w);
+      a1.x = __fadd_rn(a1.x, v.x); a1.y = __fadd_rn(a1.y, v.y); a1.z = __fadd_rn(a1.z, v.z); a1.w = __fadd_rn(a1.w, v.w);
+    }
+    // same partial layout as col_reduce_kernel: [chunk][2][C]
+    *reinterpret_cast<float4*>(partial + ((long long)blockIdx.y * 2 + 0) * C + c4 * 4) = a0;
+    *reinterpret_cast<float4*>(partial + ((long long)blockIdx.y * 2 + 1) * C + c4 * 4) = a1;
+  }
+}
+template <int MODE>
+static ColChunks launch_bn_reduce4(const float* x, const float* dy, const float* save_mean, const float* save_var, float* ws, size_t wsf,
+                                   long long rows, int C, int quirk, cudaStream_t s) {
+  const int col_blocks = ceil_div(C / 4, 32);
+  long long want = ceil_div(4 * kNumSMs, col_blocks);
+  if (want > (rows + 31) / 32) want = (rows + 31) / 32;
+  const long long max_by_ws = (long long)(wsf / ((size_t)2 * C));
+  if (want > max_by_ws) want = max_by_ws;
+  if (want < 1) want = 1;
+  const long long rpc = (rows + want - 1) / want;
+  const int chunks = ceil_div(rows, rpc);
+  bn_col_reduce4_kernel<MODE><<<dim3(col_blocks, chunks), dim3(32, 8), 0, s>>>(x, dy, save_mean, save_var, ws, rows, C, rpc, (float)rows, quirk);
+  SB_LAUNCHED();
+  return ColChunks{chunks, rpc};
+}
+__global__ void __launch_bounds__(256) bn_apply4_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, const float* __restrict__ mean,
+                                                        const float* __restrict__ var, float eps, int fused, long long n4, int C4) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const int c = (int)(i % C4) * 4;
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + i);
+    const float4 vr = __ldg(reinterpret_cast<const float4*>(var + c)), gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 mn = __ldg(reinterpret_cast<const float4*>(mean + c)), bt = __ldg(reinterpret_cast<const float4*>(beta + c));
+    float4 o;
+#define SB_BN1(f)                                                                                      \
+    {                                                                                                  \
+      const float inv = __fmul_rn(__fdiv_rn(1.f, sqrtf(__fadd_rn(vr.f, eps))), gm.f);                \
+      o.f = fused ? __fadd_rn(__fmul_rn(__fsub_rn(xv.f, mn.f), inv), bt.f)                            \
+                  : __fadd_rn(__fsub_rn(__fmul_rn(xv.f, inv), __fmul_rn(mn.f, inv)), bt.f);           \
+    }
+    SB_BN1(x) SB_BN1(y) SB_BN1(z) SB_BN1(w)
+#undef SB_BN1
+    reinterpret_cast<float4*>(y)[i] = o;
+  }
+}
+__global__ void __launch_bounds__(256) bn_bwd_apply4_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx,
+                                                            const float* __restrict__ gamma, const float* __restrict__ save_mean,
+                                                            const float* __restrict__ save_var, const float* __restrict__ sums, float eps,
+                                                            float rows, int quirk, long long n4, int C) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int C4 = C >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const int c = (int)(i % C4) * 4;
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + i), g = __ldg(reinterpret_cast<const float4*>(dy) + i);
+    const float4 m4 = __ldg(reinterpret_cast<const float4*>(save_mean + c)), v4 = __ldg(reinterpret_cast<const float4*>(save_var + c));
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(sums + c)), s1 = __ldg(reinterpret_cast<const float4*>(sums + C + c));
+    const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    float4 o;
+#define SB_BNB(f)                                                                                                   \
+    {                                                                                                               \
+      const float mean_in = quirk ? __fmul_rn(v4.f, __fdiv_rn(rows, __fsub_rn(rows, 1.f))) : m4.f;                 \
+      const float ve = __fadd_rn(quirk ? m4.f : v4.f, eps);                                                        \
+      const float istd = __fdiv_rn(1.f, sqrtf(ve));                                                                \
+      const float mg = __fdiv_rn(s0.f, rows), mgx = __fdiv_rn(s1.f, rows);                                         \
+      const float xc = __fsub_rn(xv.f, mean_in);                                                                   \
+      const float t = __fsub_rn(__fsub_rn(g.f, mg), __fdiv_rn(__fmul_rn(xc, mgx), ve));                            \
+      o.f = __fmul_rn(__fmul_rn(gm.f, istd), t);                                                                   \
+    }
+    SB_BNB(x) SB_BNB(y) SB_BNB(z) SB_BNB(w)
+#undef SB_BNB
+    reinterpret_cast<float4*>(dx)[i] = o;
+  }
+}
+
 void bn_fwd(const float* x, float* y, const float* gamma, const float* beta, float* mov_mean, float* mov_var,
             float* save_mean, float* save_var, long long rows, int C, float eps, float momentum, int fused, int bn_mode,
             int update_moving, float* ws, size_t wsf, cudaStream_t s) {
-  ColChunks cc = launch_col_reduce(FBnSum{x, C}, ws, wsf, rows, C, s);
+  const bool v4 = (C % 4 == 0) && ((((uintptr_t)x) | ((uintptr_t)y)) % 16 == 0);
+  ColChunks cc = v4 ? launch_bn_reduce4<0>(x, nullptr, nullptr, nullptr, ws, wsf, rows, C, 0, s)
+                    : launch_col_reduce(FBnSum{x, C}, ws, wsf, rows, C, s);
   bn_mean_kernel<<<ceil_div(C, 128), 128, 0, s>>>(ws, save_mean, cc.chunks, C, (float)rows);
   SB_LAUNCHED();
-  cc = launch_col_reduce(FBnSqDev2{x, save_mean, C}, ws, wsf, rows, C, s);
+  cc = v4 ? launch_bn_reduce4<1>(x, nullptr, save_mean, nullptr, ws, wsf, rows, C, 0, s)
+          : launch_col_reduce(FBnSqDev2{x, save_mean, C}, ws, wsf, rows, C, s);
   bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, s>>>(ws, cc.chunks, C, (float)rows, gamma, beta, save_mean, save_var, mov_mean,
                                                       mov_var, eps, momentum, fused, bn_mode, update_moving);
   SB_LAUNCHED();
   long long n = rows * C;
+  if (v4) {
+    int blocks = (int)fmin((double)ceil_div(n / 4, 256), (double)kNumSMs * 16);
+    bn_apply4_kernel<<<blocks, 256, 0, s>>>(x, y, gamma, beta, save_mean, save_var, eps, fused, n / 4, C / 4);
+    SB_LAUNCHED();
+    return;
+  }
   int blocks = (int)fmin((double)ceil_div(n, 256), (double)kNumSMs * 16);
   bn_apply_kernel<<<blocks, 256, 0, s>>>(x, y, gamma, beta, save_mean, save_var, eps, fused, n, C);
   SB_LAUNCHED();
@@ -774,10 +903,17 @@ void bn_bwd(const float* x, const float* dy, float* dx, const float* gamma, cons
   // ws layout: [2*C sums][partials...]
   float* sums = ws;
   float* part = ws + 2 * (size_t)C;
-  ColChunks cc = launch_col_reduce(FBnBwd{x, dy, save_mean, save_var, C, (float)rows, quirk}, part, wsf - 2 * (size_t)C, rows, C, s);
+  const bool v4 = (C % 4 == 0) && ((((uintptr_t)x) | ((uintptr_t)dy) | ((uintptr_t)dx)) % 16 == 0);
+  ColChunks cc = v4 ? launch_bn_reduce4<2>(x, dy, save_mean, save_var, part, wsf - 2 * (size_t)C, rows, C, quirk, s)
+                    : launch_col_reduce(FBnBwd{x, dy, save_mean, save_var, C, (float)rows, quirk}, part, wsf - 2 * (size_t)C, rows, C, s);
   bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, s>>>(part, cc.chunks, C, save_mean, save_var, eps, quirk, dgamma, dbeta, sums);
   SB_LAUNCHED();
-  if (dx) {
+  if (dx && v4) {
+    const long long n4 = rows * C / 4;
+    int blocks = (int)fmin((double)ceil_div(n4, 256), (double)kNumSMs * 16);
+    bn_bwd_apply4_kernel<<<blocks, 256, 0, s>>>(x, dy, dx, gamma, save_mean, save_var, sums, eps, (float)rows, quirk, n4, C);
+    SB_LAUNCHED();
+  } else if (dx) {
     long long n = rows * C;
     int blocks = (int)fmin((double)ceil_div(n, 256), (double)kNumSMs * 16);
     bn_bwd_apply_kernel<<<blocks, 256, 0, s>>>(x, dy, dx, gamma, save_mean, save_var, sums, eps, (float)rows, quirk, n, C);
