@@ -122,7 +122,7 @@ typedef enum {
 typedef enum {
   SB_PREC_FP32 = 0,  /* fp32 FFMA kernels: parity mode */
   SB_PREC_TF32 = 1,  /* tcgen05 kind::tf32, fp32 accumulate in TMEM (throughput mode) where the shape fits */
-  SB_PREC_3XTF32 = 2 /* split-operand 3xTF32 on tcgen05 (fp32-class accuracy) where the shape fits */
+  SB_PREC_3XTF32 = 2 /* MatMul: split-operand 3xTF32 on tcgen05 (fp32-class accuracy); Conv2D: the fp32 FFMA kernels */
 } sb_precision;
 
 typedef struct {

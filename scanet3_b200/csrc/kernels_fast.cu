@@ -568,9 +568,10 @@ __global__ void __launch_bounds__(kHeadThreads* kHeadKQ) dense_head_fwd_kernel(c
   const int m = tid & (kHeadThreads - 1), kq = tid / kHeadThreads;
   const int KQ = KC / kHeadKQ;
   if (m < M) {
-    float acc[NT];
+    // packed fp32x2 FMAs (FFMA2): two output columns per instruction
+    float2 acc2[NT / 2];
 #pragma unroll
-    for (int n = 0; n < NT; ++n) acc[n] = 0.f;
+    for (int n = 0; n < NT / 2; ++n) acc2[n] = make_float2(0.f, 0.f);
     const float* xr = xs + (size_t)m * xs_stride + kq * KQ;
     const float* wr = ws + (size_t)kq * KQ * NT;
     for (int k = 0; k < KQ; k += 4) {
@@ -578,16 +579,20 @@ __global__ void __launch_bounds__(kHeadThreads* kHeadKQ) dense_head_fwd_kernel(c
       const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
+        const float2 xx = make_float2(xa[j], xa[j]);
 #pragma unroll
         for (int n4 = 0; n4 < NT; n4 += 4) {
           const float4 wv = *reinterpret_cast<const float4*>(wr + (k + j) * NT + n4);
-          acc[n4] = fmaf(xa[j], wv.x, acc[n4]); acc[n4 + 1] = fmaf(xa[j], wv.y, acc[n4 + 1]);
-          acc[n4 + 2] = fmaf(xa[j], wv.z, acc[n4 + 2]); acc[n4 + 3] = fmaf(xa[j], wv.w, acc[n4 + 3]);
+          acc2[n4 / 2] = __ffma2_rn(xx, make_float2(wv.x, wv.y), acc2[n4 / 2]);
+          acc2[n4 / 2 + 1] = __ffma2_rn(xx, make_float2(wv.z, wv.w), acc2[n4 / 2 + 1]);
         }
       }
     }
 #pragma unroll
-    for (int n = 0; n < NT; ++n) red[((size_t)kq * M + m) * (NT + 1) + n] = acc[n];
+    for (int n = 0; n < NT / 2; ++n) {
+      red[((size_t)kq * M + m) * (NT + 1) + 2 * n] = acc2[n].x;
+      red[((size_t)kq * M + m) * (NT + 1) + 2 * n + 1] = acc2[n].y;
+    }
   }
   __syncthreads();
   for (int i = tid; i < M * N; i += blockDim.x) {
@@ -658,11 +663,11 @@ __global__ void __launch_bounds__(kBwdK* kBwdGroups) dense_head_bwd_kernel(const
     for (int i = tid; i < kn; i += blockDim.x) sw[(i / N) * (NT + 1) + i % N] = __ldg(w + (size_t)k0 * N + i);
   }
   __syncthreads();
-  float acc[NT], wr[NT];
+  float2 acc2[NT / 2], wr2[NT / 2];  // packed fp32x2 FMAs (FFMA2)
 #pragma unroll
-  for (int n = 0; n < NT; ++n) {
-    acc[n] = 0.f;
-    wr[n] = (DGRAD && n < N) ? sw[kk * (NT + 1) + n] : 0.f;
+  for (int n = 0; n < NT / 2; ++n) {
+    acc2[n] = make_float2(0.f, 0.f);
+    wr2[n] = make_float2((DGRAD && 2 * n < N) ? sw[kk * (NT + 1) + 2 * n] : 0.f, (DGRAD && 2 * n + 1 < N) ? sw[kk * (NT + 1) + 2 * n + 1] : 0.f);
   }
   for (int mb = mlo; mb < M; mb += kBwdRows) {  // row chunks in order: the dW sum runs over rows in ascending chunks
     const int mc = min(kBwdRows, M - mb);
@@ -678,23 +683,28 @@ __global__ void __launch_bounds__(kBwdK* kBwdGroups) dense_head_bwd_kernel(const
 #pragma unroll 4
       for (int m = m0; m < m1; ++m) {
         const float xv = __ldg(x + (size_t)(mb + m) * K + k);
-        float d = 0.f;
+        const float2 xx = make_float2(xv, xv);
+        float2 d2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int n4 = 0; n4 < NT; n4 += 4) {
           const float4 gv = *reinterpret_cast<const float4*>(sg + m * NT + n4);
-          acc[n4] = fmaf(xv, gv.x, acc[n4]); acc[n4 + 1] = fmaf(xv, gv.y, acc[n4 + 1]);
-          acc[n4 + 2] = fmaf(xv, gv.z, acc[n4 + 2]); acc[n4 + 3] = fmaf(xv, gv.w, acc[n4 + 3]);
+          const float2 g0 = make_float2(gv.x, gv.y), g1 = make_float2(gv.z, gv.w);
+          acc2[n4 / 2] = __ffma2_rn(xx, g0, acc2[n4 / 2]);
+          acc2[n4 / 2 + 1] = __ffma2_rn(xx, g1, acc2[n4 / 2 + 1]);
           if (DGRAD) {
-            d = fmaf(gv.x, wr[n4], d); d = fmaf(gv.y, wr[n4 + 1], d);
-            d = fmaf(gv.z, wr[n4 + 2], d); d = fmaf(gv.w, wr[n4 + 3], d);
+            d2 = __ffma2_rn(g0, wr2[n4 / 2], d2);
+            d2 = __ffma2_rn(g1, wr2[n4 / 2 + 1], d2);
           }
         }
-        if (DGRAD) dx[(size_t)(mb + m) * K + k] = d;
+        if (DGRAD) dx[(size_t)(mb + m) * K + k] = __fadd_rn(d2.x, d2.y);
       }
     }
   }
 #pragma unroll
-  for (int n = 0; n < NT; ++n) red[(rg * kBwdK + kk) * (NT + 1) + n] = acc[n];
+  for (int n = 0; n < NT / 2; ++n) {
+    red[(rg * kBwdK + kk) * (NT + 1) + 2 * n] = acc2[n].x;
+    red[(rg * kBwdK + kk) * (NT + 1) + 2 * n + 1] = acc2[n].y;
+  }
   __syncthreads();
   // dW slab [kBwdK][N] is contiguous in memory: write it coalesced
   const int kn = min(kBwdK, K - k0) * N;

@@ -189,11 +189,12 @@ LstmWs* ws_of(sb_engine* e, LayerPlan& L) {
   w->dwk_cat = dalloc(F * 4 * U);
   w->db_cat = dalloc(4 * U);
   if (L.need_dx) w->dx_tm = dalloc(T * B * F);
-  if (e->train.precision == SB_PREC_TF32 && B * U * 4 * U >= (1 << 22)) {
-    w->g_fwd = tc_gemm_create(0, 1, w->h, (int)T + 1, w->wr_cat, 1, w->acts, (int)T, (int)B, (int)(4 * U), (int)U, 0, nullptr, 0, e->device);
-    w->g_bwd = tc_gemm_create(0, 0, w->acts, (int)T, w->wr_cat, 1, w->dh, 1, (int)B, (int)U, (int)(4 * U), 0, nullptr, 0, e->device);
+  if (e->train.precision != SB_PREC_FP32 && B * U * 4 * U >= (1 << 22)) {
+    const int x3 = e->train.precision == SB_PREC_3XTF32 ? 1 : 0;
+    w->g_fwd = tc_gemm_create(0, 1, w->h, (int)T + 1, w->wr_cat, 1, w->acts, (int)T, (int)B, (int)(4 * U), (int)U, 0, nullptr, 0, e->device, x3);
+    w->g_bwd = tc_gemm_create(0, 0, w->acts, (int)T, w->wr_cat, 1, w->dh, 1, (int)B, (int)U, (int)(4 * U), 0, nullptr, 0, e->device, x3);
     w->g_dwr = tc_gemm_create(1, 1, w->h, 1, w->acts, 1, w->dwr_cat, 1, (int)U, (int)(4 * U), (int)(T * B), 1, e->ws, e->ws_floats,
-                              e->device);
+                              e->device, x3);
   }
   L.lstm = w;
   return w;

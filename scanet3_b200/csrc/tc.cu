@@ -849,7 +849,9 @@ static int igemm_smem(const IgemmParams& p) { return p.stages * (kATileBytes + p
 
 void tc_plan_layers(sb_engine* e) {
   if (e->train.precision == SB_PREC_FP32) return;
-  if (e->train.precision == SB_PREC_3XTF32) return;  // TODO(round 2): split-operand 3xTF32; fp32 FFMA kernels serve it for now
+  // SB_PREC_3XTF32: MatMul contractions run the split-operand 3xTF32 GEMM (fp32-class accuracy on the tensor cores);
+  // convolutions stay on the fp32 FFMA kernels in that mode
+  const int x3 = e->train.precision == SB_PREC_3XTF32 ? 1 : 0;
   int dev_smem = 0;
   SB_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device));
   for (size_t li = 0; li < e->L.size(); ++li) {
@@ -865,10 +867,10 @@ void tc_plan_layers(sb_engine* e) {
       float* w = e->arena + e->params[L.p_w].offset;
       float* dw = e->grads + e->params[L.p_w].offset;
       DenseTcPlan* D = new DenseTcPlan();
-      D->fwd = tc_gemm_create(0, 1, x, 1, w, 1, z, 1, M, N, K, 0, nullptr, 0, e->device);
-      D->wgrad = tc_gemm_create(1, 1, x, 1, dz, 1, dw, 1, K, N, M, 1, e->ws, e->ws_floats, e->device);
+      D->fwd = tc_gemm_create(0, 1, x, 1, w, 1, z, 1, M, N, K, 0, nullptr, 0, e->device, x3);
+      D->wgrad = tc_gemm_create(1, 1, x, 1, dz, 1, dw, 1, K, N, M, 1, e->ws, e->ws_floats, e->device, x3);
       const bool want_dgrad = L.need_dx && dx != nullptr;
-      if (want_dgrad) D->dgrad = tc_gemm_create(0, 0, dz, 1, w, 1, dx, 1, M, K, N, 1, e->ws, e->ws_floats, e->device);
+      if (want_dgrad) D->dgrad = tc_gemm_create(0, 0, dz, 1, w, 1, dx, 1, M, K, N, 1, e->ws, e->ws_floats, e->device, x3);
       if (!D->fwd || !D->wgrad || (want_dgrad && !D->dgrad)) {
         tc_gemm_destroy(D->fwd); tc_gemm_destroy(D->wgrad); tc_gemm_destroy(D->dgrad);
         delete D;
@@ -895,7 +897,7 @@ void tc_plan_layers(sb_engine* e) {
       L.tc_plan = D;
       continue;
     }
-    if (L.d.kind != SB_LAYER_CONV2D || !conv_fits(L.cg)) continue;
+    if (x3 || L.d.kind != SB_LAYER_CONV2D || !conv_fits(L.cg)) continue;
     const ConvGeom& g = L.cg;
     ConvTcPlan* P = new ConvTcPlan();
     float* x = e->acts[L.buf_in];

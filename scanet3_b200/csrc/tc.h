@@ -22,7 +22,7 @@ struct TcGemm;
 // C[M,N] = op(A).op(B).  a_mn_major: A stored [K][M] (else [M][K]); b_mn_major: B stored [K][N] (else [N][K]).
 // Returns null when the shape / alignment does not fit (caller falls back to the fp32 kernels).
 TcGemm* tc_gemm_create(int a_mn_major, int b_mn_major, const float* A, int a_slices, const float* B, int b_slices, float* C,
-                       int c_slices, int M, int N, int K, int allow_split, float* ws, size_t ws_floats, int device);
+                       int c_slices, int M, int N, int K, int allow_split, float* ws, size_t ws_floats, int device, int x3 = 0);
 void tc_gemm_set_epilogue(TcGemm* g, const float* bias, int act, float thr);
 bool tc_gemm_is_split(const TcGemm* g);
 void tc_gemm_run(TcGemm* g, int za, int zb, int zc, cudaStream_t s);

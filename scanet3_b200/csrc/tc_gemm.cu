@@ -34,12 +34,14 @@ struct GemmParams {
   int m_tiles, n_tiles, splits, kb_total, kb_per_split;
   int stages;
   int za, zb, zc;
+  int x3;   // 3xTF32: split operands (hi = tf32(x), lo = x - hi), D += A_hi.B_lo + A_lo.B_hi + A_hi.B_hi  (fp32-class accuracy)
   int act;  // sb_activation applied in the epilogue (0 none, 1 sigmoid, 2 tanh, 4 relu)
   float thr;
   const float* bias;  // [N] or null
 };
 
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 192;       // producer, MMA issuer, 4 epilogue warps
+constexpr int kGemmThreadsX3 = 320;     // + 4 converter warps that materialise the low-order operand tiles
 constexpr int kGemmATile = 128 * 128;  // 128 rows x 32 fp32
 
 __device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
@@ -89,17 +91,19 @@ __device__ __forceinline__ void tile_to_mn(int tile, int m_tiles, int n_tiles, i
   mt = grp * kGroupM + (in - nt * gm);
 }
 
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreadsX3, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_c, const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int b_tile = p.BN * 128;
-  const int stage_bytes = kGemmATile + b_tile;
+  const int hi_bytes = kGemmATile + b_tile;                  // [A | B] as loaded by TMA
+  const int stage_bytes = p.x3 ? 2 * hi_bytes : hi_bytes;    // 3xTF32: followed by [A_lo | B_lo]
   uint8_t* sm_epi = smem + (size_t)p.stages * stage_bytes;  // 4 warps x 2 buffers x 4 KB
   uint64_t* full_bar = (uint64_t*)(sm_epi + 4 * 2 * 4096);
   uint64_t* empty_bar = full_bar + p.stages;
-  uint64_t* tmem_full = empty_bar + p.stages;
+  uint64_t* conv_bar = empty_bar + p.stages;  // 3xTF32: low-order tiles of the stage are written
+  uint64_t* tmem_full = conv_bar + p.stages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
 
@@ -116,6 +120,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&conv_bar[s], 4);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
@@ -129,7 +134,36 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp >= 6) {
+    // ================= 3xTF32 converters: lo = x - tf32(x) for every word of the stage's A and B tiles =================
+    // kind::tf32 reads fp32 words and ignores the low 13 mantissa bits, so the hi tiles ARE the tiles TMA wrote; the lo
+    // tiles have the same (swizzled) layout, word for word.
+    const int t = threadIdx.x - 192;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      const int split = w / tiles;
+      const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        const float4* hi = reinterpret_cast<const float4*>(smem + (size_t)stage * stage_bytes);
+        float4* lo = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes + hi_bytes);
+        for (int i = t; i < hi_bytes / 16; i += 128) {
+          const float4 v = hi[i];
+          float4 r;
+          r.x = __fsub_rn(v.x, __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
+          r.y = __fsub_rn(v.y, __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
+          r.z = __fsub_rn(v.z, __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
+          r.w = __fsub_rn(v.w, __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+          lo[i] = r;
+        }
+        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&conv_bar[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
       int stage = 0;
@@ -144,7 +178,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
           uint8_t* sb = sa + kGemmATile;
-          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)hi_bytes);
           if (p.a_grouped) {
             tma_load_4d_g(sa, &map_a, &full_bar[stage], 0, kb * 32, m0 >> 5, p.za);
           } else if (p.a_mn_major) {
@@ -183,15 +217,27 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
       uint32_t accumulate = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+        mbar_wait(p.x3 ? &conv_bar[stage] : &full_bar[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes) >> 4;
         const uint32_t at = a_lo0 + sa, bt = b_lo0 + sa + (uint32_t)(kGemmATile >> 4);
+        if (p.x3) {
+          const uint32_t lo_off = (uint32_t)(hi_bytes >> 4);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {  // 4 x (K = 8 tf32) per 32-wide k block
-          umma_tf32_elect(d_tmem, ((uint64_t)a_hi << 32) | (at + ks * a_step), ((uint64_t)b_hi << 32) | (bt + ks * b_step), idesc,
-                          accumulate);
-          accumulate = 1;
+          for (int ks = 0; ks < 4; ++ks) {  // small terms first: A_hi.B_lo, A_lo.B_hi, then A_hi.B_hi
+            const uint64_t da = ((uint64_t)a_hi << 32) | (at + ks * a_step), db = ((uint64_t)b_hi << 32) | (bt + ks * b_step);
+            umma_tf32_elect(d_tmem, da, db + lo_off, idesc, accumulate);
+            umma_tf32_elect(d_tmem, da + lo_off, db, idesc, 1u);
+            umma_tf32_elect(d_tmem, da, db, idesc, 1u);
+            accumulate = 1;
+          }
+        } else {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {  // 4 x (K = 8 tf32) per 32-wide k block
+            umma_tf32_elect(d_tmem, ((uint64_t)a_hi << 32) | (at + ks * a_step), ((uint64_t)b_hi << 32) | (bt + ks * b_step), idesc,
+                            accumulate);
+            accumulate = 1;
+          }
         }
         umma_commit_elect(&empty_bar[stage]);  // the smem slot is free once these MMAs have read it
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -311,7 +357,7 @@ struct TcGemm {
 };
 
 TcGemm* tc_gemm_create(int a_mn_major, int b_mn_major, const float* A, int a_slices, const float* B, int b_slices, float* C,
-                       int c_slices, int M, int N, int K, int allow_split, float* ws, size_t ws_floats, int device) {
+                       int c_slices, int M, int N, int K, int allow_split, float* ws, size_t ws_floats, int device, int x3) {
   // 16-byte global strides / base addresses
   const int a_inner = a_mn_major ? M : K, b_inner = b_mn_major ? N : K;
   if ((a_inner & 3) || (b_inner & 3) || (N & 3) || M < 1 || N < 8 || K < 1) return nullptr;
@@ -320,13 +366,14 @@ TcGemm* tc_gemm_create(int a_mn_major, int b_mn_major, const float* A, int a_sli
   SB_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   TcGemm* g = new TcGemm();
   GemmParams& p = g->p;
-  p.M = M; p.N = N; p.K = K; p.a_mn_major = a_mn_major; p.b_mn_major = b_mn_major;
+  p.M = M; p.N = N; p.K = K; p.a_mn_major = a_mn_major; p.b_mn_major = b_mn_major; p.x3 = x3 ? 1 : 0;
   p.m_tiles = (M + 127) / 128;
   p.kb_total = (K + 31) / 32;
   // tile width / split-K: maximise (SM utilisation over whole waves) x (MMA efficiency of the tile width)
   const int n_cap = (N + 31) / 32 * 32;
   double best = -1.0;
   for (int bn : {256, 128, 64, 32}) {
+    if (x3 && bn > 128) continue;  // the low-order tiles double the stage: keep >= 3 stages
     const int BNc = std::min(bn, n_cap);
     const int tiles = p.m_tiles * ((N + BNc - 1) / BNc);
     int splits = 1;
@@ -343,8 +390,8 @@ TcGemm* tc_gemm_create(int a_mn_major, int b_mn_major, const float* A, int a_sli
   const int tiles = p.m_tiles * p.n_tiles;
   p.kb_per_split = (p.kb_total + p.splits - 1) / p.splits;
   p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
-  const int stage_bytes = kGemmATile + p.BN * 128;
-  const int fixed = 4 * 2 * 4096 + 16 * 16 + 64 + 1024;
+  const int stage_bytes = (x3 ? 2 : 1) * (kGemmATile + p.BN * 128);
+  const int fixed = 4 * 2 * 4096 + 16 * 24 + 64 + 1024;
   p.stages = std::min(8, (dev_smem - fixed) / stage_bytes);
   if (p.stages < 2) { delete g; return nullptr; }
   g->smem = fixed + p.stages * stage_bytes;
@@ -382,7 +429,7 @@ bool tc_gemm_is_split(const TcGemm* g) { return g->p.splits > 1; }
 void tc_gemm_run(TcGemm* g, int za, int zb, int zc, cudaStream_t s) {
   GemmParams p = g->p;
   p.za = za; p.zb = zb; p.zc = p.splits > 1 ? 0 : zc;
-  gemm_tf32_kernel<<<g->grid, kGemmThreads, g->smem, s>>>(g->map_a, g->map_b, g->map_c, p);
+  gemm_tf32_kernel<<<g->grid, p.x3 ? kGemmThreadsX3 : kGemmThreads, g->smem, s>>>(g->map_a, g->map_b, g->map_c, p);
   SB_LAUNCHED();
   if (p.splits > 1) partial_reduce(g->partial, g->c + (long long)zc * g->c_slice, p.M * p.N, p.splits, s);
 }

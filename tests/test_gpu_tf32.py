@@ -219,3 +219,34 @@ def test_tf32_lstm_matches_fp32_engine():
     assert abs(ltc - l32) <= 4e-3 * abs(l32)
     for k in g32:
         assert rel_to_max(gtc[k], g32[k]) < 1e-2, k
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# 3xTF32: split-operand tensor-core GEMM that holds fp32 tolerance (hi = tf32(x), lo = x - hi; A_hi.B_lo + A_lo.B_hi + A_hi.B_hi)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,spec,batch,nin", DENSE_STACKS[:2] + DENSE_STACKS[3:], ids=[c[0] for c in DENSE_STACKS[:2] + DENSE_STACKS[3:]])
+def test_3xtf32_dense_holds_fp32_tolerance(name, spec, batch, nin):
+    om, sm = build_models(spec)
+    e32 = S.Engine(sm, S.CategoricalCrossentropy, S.Adam(0.001), batch, (nin,), (10,), device=0, precision=S.PREC_FP32)
+    e3x = S.Engine(sm, S.CategoricalCrossentropy, S.Adam(0.001), batch, (nin,), (10,), device=0, precision=S.PREC_3XTF32)
+    e1x = S.Engine(sm, S.CategoricalCrossentropy, S.Adam(0.001), batch, (nin,), (10,), device=0, precision=S.PREC_TF32)
+    for e in (e32, e3x, e1x):
+        e.init_params()
+    x, y = synth_classification(batch, (nin,), 10, 33)
+    x = (x - 0.5).astype(f32)
+    p32, p3x, p1x = e32.predict(x), e3x.predict(x), e1x.predict(x)
+    # the two fp32-class paths agree to a few 1e-6 of the largest value; plain TF32 is ~100x further away
+    assert rel_to_max(p3x, p32) < 5e-6
+    assert rel_to_max(p1x, p32) > 10 * rel_to_max(p3x, p32)
+    l32, g32 = e32.compute_grads(x, y)
+    l3x, g3x = e3x.compute_grads(x, y)
+    assert abs(l3x - l32) <= 2e-6 * abs(l32)
+    for k in g32:
+        assert rel_to_max(g3x[k], g32[k]) < 2e-5, k
+    e3x.profile_enable(True)
+    e3x.compute_grads(x, y)
+    names = [r["name"] for r in e3x.profile()]
+    e3x.profile_enable(False)
+    assert any(n.startswith("dense_") and "tcgen05" in n for n in names), names  # on the tensor cores, not the FFMA fallback
+    for e in (e32, e3x, e1x):
+        e.close()
