@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SB_ABI_VERSION 1
+#define SB_ABI_VERSION 2
 
 typedef enum {
   SB_OK = 0,
@@ -60,6 +60,10 @@ typedef enum {
 typedef enum { SB_ACT_IDENTITY = 0, SB_ACT_SIGMOID = 1, SB_ACT_TANH = 2, SB_ACT_SOFTMAX = 3, SB_ACT_RELU = 4 } sb_activation;
 typedef enum { SB_PAD_VALID = 0, SB_PAD_SAME = 1 } sb_padding;
 typedef enum { SB_POOL_MAX = 0, SB_POOL_AVG = 1 } sb_pool_reduce;
+/* models/Regularization.scala:16-44: penalty lambda*sum|w|/2 (L1) or lambda*sum(w^2)/2 (L2) added to the loss
+ * (models/Model.scala:97).  Gradients follow the reference's autodiff: L2 -> lambda*w; L1 -> |lambda|/2 per element
+ * (the reference's Abs.localGrad is |g|, math/alg/AllKernels.scala:330-336 -- reproduced). */
+typedef enum { SB_REG_ZERO = 0, SB_REG_L1 = 1, SB_REG_L2 = 2 } sb_regularization;
 
 /* models/Initializer.scala:28-220.  Random kinds are bit-compatible with TF's seeded Philox ops
  * (math/rand/AllKernels.scala:12-43); an unseeded random initializer is rejected. */
@@ -99,6 +103,8 @@ typedef struct {
   int32_t bn_fused;             /* -1 = None (auto), 0 = Some(false), 1 = Some(true) */
   sb_initializer init[4];       /* [0] kernel | gamma, [1] recurrent | beta, [2] bias | moving_mean,
                                    [3] forget-bias | moving_variance */
+  int32_t reg_kind;             /* sb_regularization of this layer's "weights" (Dense kernel, Bias) */
+  float reg_lambda;
 } sb_layer_desc;
 
 typedef struct {

@@ -29,7 +29,8 @@ object Native {
     JAVA_INT.withName("stride_w"), JAVA_INT.withName("padding"), JAVA_INT.withName("pool_reduce"),
     JAVA_INT.withName("use_bias"), JAVA_INT.withName("trainable"), JAVA_FLOAT.withName("bn_momentum"),
     JAVA_FLOAT.withName("bn_epsilon"), JAVA_INT.withName("bn_mode"), JAVA_INT.withName("bn_fused"),
-    MemoryLayout.paddingLayout(4), MemoryLayout.sequenceLayout(4, Initializer).withName("init"))
+    MemoryLayout.paddingLayout(4), MemoryLayout.sequenceLayout(4, Initializer).withName("init"),
+    JAVA_INT.withName("reg_kind"), JAVA_FLOAT.withName("reg_lambda"))
   val ModelDesc: StructLayout = MemoryLayout.structLayout(
     JAVA_INT.withName("n_layers"), MemoryLayout.paddingLayout(4), ADDRESS.withName("layers"),
     JAVA_INT.withName("input_rank"), MemoryLayout.paddingLayout(4),

@@ -50,7 +50,7 @@ class sb_layer_desc(C.Structure):
                 ("relu_threshold", C.c_float), ("window_h", C.c_int32), ("window_w", C.c_int32), ("stride_h", C.c_int32),
                 ("stride_w", C.c_int32), ("padding", C.c_int32), ("pool_reduce", C.c_int32), ("use_bias", C.c_int32),
                 ("trainable", C.c_int32), ("bn_momentum", C.c_float), ("bn_epsilon", C.c_float), ("bn_mode", C.c_int32),
-                ("bn_fused", C.c_int32), ("init", sb_initializer * 4)]
+                ("bn_fused", C.c_int32), ("init", sb_initializer * 4), ("reg_kind", C.c_int32), ("reg_lambda", C.c_float)]
 
 
 class sb_model_desc(C.Structure):

@@ -111,6 +111,14 @@ static int add_param(sb_engine* e, const std::string& path, std::initializer_lis
   return (int)e->params.size() - 1;
 }
 
+static void set_reg(sb_engine* e, int pi, const sb_layer_desc& d) {
+  if (d.reg_kind == SB_REG_ZERO || d.reg_lambda == 0.f) return;
+  if (d.reg_kind != SB_REG_L1 && d.reg_kind != SB_REG_L2) SB_FAIL(SB_ERR_INVALID_ARG, "unknown regularization kind");
+  e->params[pi].reg_kind = d.reg_kind;
+  e->params[pi].reg_lambda = d.reg_lambda;
+  e->has_reg = true;
+}
+
 static const char* kGateNames[4] = {"forget", "input", "gate", "output"};
 
 static int opt_slots(int kind) {
@@ -165,6 +173,8 @@ static void build_plan(sb_engine* e) {
     L.buf_in = cur_buf;
     L.need_dx = any_trainable_before;
     const sb_layer_desc& d = L.d;
+    if (d.reg_kind != SB_REG_ZERO && d.reg_lambda != 0.f && d.kind != SB_LAYER_DENSE && d.kind != SB_LAYER_BIAS)
+      SB_FAIL(SB_ERR_UNSUPPORTED, "regularisation is accelerated for Dense kernels and Bias layers only");
     const std::string pre = std::to_string(li) + "/";
     Shape out = cur;
     bool new_buf = true;
@@ -174,6 +184,7 @@ static void build_plan(sb_engine* e) {
         if (d.units <= 0) SB_FAIL(SB_ERR_INVALID_ARG, "Dense outputs must be positive");
         if (!d.trainable) SB_FAIL(SB_ERR_UNSUPPORTED, "frozen layers are outside the accelerated path");
         L.p_w = add_param(e, pre + "weights", {cur.d[1], (int64_t)d.units}, SB_ROLE_WEIGHT, SB_AGG_AVG, d.init[0], li);
+        set_reg(e, L.p_w, d);
         out.d[1] = d.units;
         any_trainable_before = true;
         break;
@@ -182,6 +193,7 @@ static void build_plan(sb_engine* e) {
         if (cur.d[cur.rank - 1] != d.units) SB_FAIL(SB_ERR_INVALID_ARG, "Bias features must equal the last input dimension");
         if (!d.trainable) SB_FAIL(SB_ERR_UNSUPPORTED, "frozen layers are outside the accelerated path");
         L.p_w = add_param(e, pre + "weights", {(int64_t)d.units}, SB_ROLE_WEIGHT, SB_AGG_AVG, d.init[2], li);
+        set_reg(e, L.p_w, d);
         new_buf = (cur_buf == 0) || output_needed[cur_buf];
         any_trainable_before = true;
         break;
@@ -739,6 +751,21 @@ static void run_backward(sb_engine* e) {
   }
 }
 
+// loss += penalty(theta) and (with_grad) grad += dPenalty/dw, tensors in model order (models/Model.scala:92-119)
+static void run_reg(sb_engine* e, bool with_grad) {
+  if (!e->has_reg) return;
+  int n_reg = 0, seen = 0;
+  for (const Param& p : e->params)
+    if (p.role == SB_ROLE_WEIGHT && p.reg_kind) ++n_reg;
+  Prof pr(e, "reg_penalty", 0, 0);
+  for (const Param& p : e->params) {
+    if (p.role != SB_ROLE_WEIGHT || !p.reg_kind) continue;
+    reg_penalty_grad(e->arena + p.offset, with_grad ? e->grads + p.offset : nullptr, p.numel, p.reg_kind, p.reg_lambda, e->st,
+                     seen == 0, seen == n_reg - 1, e->stream);
+    ++seen;
+  }
+}
+
 static OptDesc opt_desc(const sb_engine* e) {
   OptDesc o;
   o.kind = e->train.optimizer;
@@ -777,6 +804,7 @@ static void run_train_step_body(sb_engine* e, bool resident) {
   run_forward(e, FWD_TRAIN);
   run_loss(e, true);
   run_backward(e);
+  run_reg(e, true);
   run_optimizer(e, resident ? 1 : 0);
 }
 
@@ -786,6 +814,7 @@ static void run_train_step_body_staged(sb_engine* e, bool parity) {
   run_forward(e, FWD_TRAIN);
   run_loss(e, true);
   run_backward(e);
+  run_reg(e, true);
   run_optimizer(e, 0);
 }
 
@@ -812,6 +841,7 @@ static cudaGraphExec_t capture(sb_engine* e, long long* nodes, void (*body)(sb_e
 static void loss_body(sb_engine* e, bool) {
   run_forward(e, FWD_LOSS_ONLY);
   run_loss(e, false);
+  run_reg(e, false);
 }
 
 static bool use_graph(const sb_engine* e) { return e->train.use_graph && !e->profiling; }
@@ -1245,6 +1275,7 @@ extern "C" int sb_compute_grads(sb_engine* e, const float* x, const float* y, fl
   run_forward(e, FWD_LOSS_ONLY);
   run_loss(e, true);
   run_backward(e);
+  run_reg(e, true);
   e->launches += tl_launch_count - before;
   float loss = read_loss(e);
   if (loss_out) *loss_out = loss;

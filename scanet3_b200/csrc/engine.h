@@ -36,6 +36,8 @@ struct Param {
   int layer = -1;
   int weight_param = -1;  // role OPT: index of the weight this state belongs to
   int slot = -1;          // role OPT: state slot 0..2
+  int reg_kind = 0;       // sb_regularization of a trainable weight (models/Regularization.scala)
+  float reg_lambda = 0.f;
 };
 
 struct LayerPlan {
@@ -130,6 +132,7 @@ struct sb_engine {
   long long host_iter_mirror = -1;  // device st->iter as far as the host knows (-1 unknown)
   bool params_ready = false, opt_ready = false;
   bool softmax_cce_fused = false;
+  bool has_reg = false;      // some weight carries an L1/L2 penalty
   bool head_fused = false;   // last layers Dense >> Bias >> Softmax with CCE: one fused bias+softmax+loss+dz+dbias kernel
   int head_chunks = 0;       // split-K partials of the head's Dense waiting in `ws` for the head kernel (0: none)
   bool fast = true;          // vectorised / fused bandwidth kernels (SB_DISABLE_FAST=1 turns them off for debugging)

@@ -76,6 +76,12 @@ void bn_bwd(const float* x, const float* dy, float* dx, const float* gamma, cons
             float* dgamma, float* dbeta, long long rows, int C, float eps, int fused, int bn_mode, float* ws,
             size_t ws_floats, cudaStream_t s);
 
+// L1/L2 penalty of one weight tensor (models/Regularization.scala:16-44; models/Model.scala:97):
+//   st->loss += lambda * sum(|w| or w^2) / 2  -- penalties are summed in tensor order into a scratch first (first/last flags),
+//   g (may be null) += dPenalty/dw  (L2: lambda*w ; L1: |lambda|/2, the reference's Abs gradient)
+void reg_penalty_grad(const float* w, float* g, long long n, int kind, float lambda, StepState* st, int first, int last,
+                      cudaStream_t s);
+
 // fused multi-tensor optimizer over the flat arena: w,g,state regions of n floats each
 void optimizer_step(const OptDesc& o, float* w, const float* g, float* s0, float* s1, float* s2, long long n,
                     StepState* st, int advance_batch, cudaStream_t s);

@@ -922,6 +922,32 @@ void bn_bwd(const float* x, const float* dy, float* dx, const float* gamma, cons
 }
 
 // =================================================================================================
+// regularisation penalties (models/Regularization.scala:16-44): one CTA per tensor, deterministic tree
+// =================================================================================================
+__global__ void __launch_bounds__(1024) reg_penalty_kernel(const float* __restrict__ w, float* __restrict__ g, long long n, int kind,
+                                                           float lambda, StepState* st, int first, int last) {
+  float acc = 0.f;
+  const float gl1 = __fdiv_rn(fabsf(lambda), 2.f);
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const float wi = w[i];
+    acc = __fadd_rn(acc, kind == 2 ? __fmul_rn(wi, wi) : fabsf(wi));
+    if (g) g[i] = __fadd_rn(g[i], kind == 2 ? __fmul_rn(lambda, wi) : gl1);
+  }
+  const float tot = block_sum_1024(acc);
+  if (threadIdx.x == 0) {
+    const float pen = __fdiv_rn(__fmul_rn(lambda, tot), 2.f);
+    const float run = first ? pen : __fadd_rn(st->pad, pen);  // penalties add up in tensor order ...
+    st->pad = run;
+    if (last) st->loss = __fadd_rn(st->loss, run);            // ... and the total joins the loss (Model.scala:97)
+  }
+}
+void reg_penalty_grad(const float* w, float* g, long long n, int kind, float lambda, StepState* st, int first, int last,
+                      cudaStream_t s) {
+  reg_penalty_kernel<<<1, 1024, 0, s>>>(w, g, n, kind, lambda, st, first, last);
+  SB_LAUNCHED();
+}
+
+// =================================================================================================
 // fused multi-tensor optimizer over the flat arena (optimizers/*.scala; caller does w - delta,
 // Optimizer.scala:186).  28 B/param for Adam: reads w,g,m,v ; writes w,m,v.
 // =================================================================================================

@@ -103,8 +103,10 @@ BinaryCrossentropy = Loss(N.LOSS_BCE, "BinaryCrossentropy")
 CategoricalCrossentropy = Loss(N.LOSS_CCE, "CategoricalCrossentropy")
 
 
-# ---- regularisation: only `Zero` is on the accelerated path --------------------------------------
+# ---- regularisation (models/Regularization.scala:16-44) ------------------------------------------------------
 class _Zero:
+    code, lam = 0, 0.0
+
     def __repr__(self):
         return "Zero"
 
@@ -112,9 +114,31 @@ class _Zero:
 Zero = _Zero()
 
 
+class L1:
+    """penalty lambda * sum|w| / 2"""
+    code = 1
+
+    def __init__(self, lam: float = 0.01):
+        self.lam = float(lam)
+
+    def __repr__(self):
+        return f"L1({self.lam})"
+
+
+class L2:
+    """penalty lambda * sum(w^2) / 2"""
+    code = 2
+
+    def __init__(self, lam: float = 0.01):
+        self.lam = float(lam)
+
+    def __repr__(self):
+        return f"L2({self.lam})"
+
+
 def _check_reg(reg):
-    if reg is not Zero:
-        raise N.Unsupported(N.SB_ERR_UNSUPPORTED, "non-zero regularisation is outside the accelerated path (SURVEY 8b)")
+    if not isinstance(reg, (_Zero, L1, L2)):
+        raise N.IllegalArgument(N.SB_ERR_INVALID_ARG, f"unknown regularisation {reg!r}")
 
 
 # ---- layers --------------------------------------------------------------------------------------------------
@@ -161,11 +185,12 @@ class Composed(Layer):
 
 
 class _DenseKernel(Layer):
-    def __init__(self, outputs, initializer, trainable):
-        self.outputs, self.initializer, self.trainable = outputs, initializer, trainable
+    def __init__(self, outputs, initializer, trainable, reg=Zero):
+        self.outputs, self.initializer, self.trainable, self.reg = outputs, initializer, trainable, reg
 
     def to_native(self):
-        d = self._desc(N.LAYER_DENSE, units=self.outputs, trainable=int(self.trainable))
+        d = self._desc(N.LAYER_DENSE, units=self.outputs, trainable=int(self.trainable), reg_kind=self.reg.code,
+                       reg_lambda=self.reg.lam)
         d.init[0] = self.initializer.to_native()
         return d
 
@@ -176,10 +201,11 @@ class _DenseKernel(Layer):
 class Bias(Layer):
     def __init__(self, features, reg=Zero, initializer=Zeros, trainable=True):
         _check_reg(reg)
-        self.features, self.initializer, self.trainable = features, initializer, trainable
+        self.features, self.initializer, self.trainable, self.reg = features, initializer, trainable, reg
 
     def to_native(self):
-        d = self._desc(N.LAYER_BIAS, units=self.features, trainable=int(self.trainable))
+        d = self._desc(N.LAYER_BIAS, units=self.features, trainable=int(self.trainable), reg_kind=self.reg.code,
+                       reg_lambda=self.reg.lam)
         d.init[2] = self.initializer.to_native()
         return d
 
@@ -214,7 +240,7 @@ def Dense(outputs: int, activation: Activation = Identity, reg=Zero, bias: bool 
           trainable: bool = True) -> Layer:
     """layer/Dense.scala:30-41 -> Dense >> Bias >> activation.layer"""
     _check_reg(reg)
-    layers: List[Layer] = [_DenseKernel(outputs, kernelInitializer, trainable)]
+    layers: List[Layer] = [_DenseKernel(outputs, kernelInitializer, trainable, reg)]
     if bias:
         layers.append(Bias(outputs, reg, biasInitializer))
     if not activation.identity:

@@ -374,3 +374,39 @@ def test_adam_logistic_regression_spec(fixtures_dir):  # optimizers/AdamSpec.sca
     assert S.accuracy(trained, ds) >= 0.9
     probe = trained.result(np.array([[0.3462, 0.7802], [0.6018, 0.8630]], f32))
     assert np.array_equal(np.round(probe), [[0], [1]])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# regularisation penalties (models/Regularization.scala:16-44; loss + penalty, models/Model.scala:97)
+# ---------------------------------------------------------------------------------------------------------------
+def test_l2_penalty_goldens():  # models/layer/ComposedLayerSpec.scala:50-69, 97-120
+    model = S.Dense(3, S.Sigmoid, S.L2(1.0)) >> S.Dense(1, S.Sigmoid, S.L2(1.0))
+    e = make_engine(model, S.MeanSquaredError, S.SGD(), 2, (3,), (1,))
+    e.set_params({"0/weights": np.array([[1, 0.5, 1], [0.1, 1, 1], [1, 0, 0.2]], f32), "1/weights": np.zeros(3, f32),
+                  "3/weights": np.array([[0.1], [0.5], [1]], f32), "4/weights": np.zeros(1, f32)})
+    x, y = np.array([[0, 0, 1], [0, 1, 1]], f32), np.array([[1], [0]], f32)
+    assert abs(e.eval_loss(x, y) - 3.6199622) < 1e-6  # 0.339962 (MSE) + 3.28 (penalty)
+    e.close()
+
+
+@pytest.mark.parametrize("reg", ["l1", "l2"])
+def test_regularised_mlp_trajectory(reg):
+    oreg, sreg = (O.L1(0.02), S.L1(0.02)) if reg == "l1" else (O.L2(0.05), S.L2(0.05))
+    om = O.Dense(24, O.Sigmoid, reg=oreg, kernel_initializer=O.GlorotUniform(1)) >> O.Dense(10, O.Softmax, reg=oreg,
+                                                                                             kernel_initializer=O.GlorotUniform(1))
+    sm = S.Dense(24, S.Sigmoid, sreg, kernelInitializer=S.GlorotUniform(1)) >> S.Dense(10, S.Softmax, sreg,
+                                                                                      kernelInitializer=S.GlorotUniform(1))
+    batch, steps = 32, 8
+    x, y = synth_classification(batch * steps, (40,), 10, 3)
+    e = make_engine(sm, S.CategoricalCrossentropy, S.Adam(0.01), batch, (40,), (10,))
+    e.init_params()
+    oalg = O.Adam(0.01)
+    _, mp, op = oracle_init(om, oalg, (batch, 40))
+    lm = O.LossModel(om, O.CategoricalCrossentropy)
+    for t in range(1, steps + 1):
+        xb, yb = x[(t - 1) * batch:t * batch], y[(t - 1) * batch:t * batch]
+        gl = e.train_step(xb, yb, t)
+        mp, op, ol = O.train_step(lm, oalg, xb, yb, mp, op, t)
+        assert abs(gl - float(ol)) <= 2e-5 * abs(float(ol)) + 1e-6, (t, gl, float(ol))  # loss includes the penalty
+    assert_params_close(e.get_model_params(), mp, 1e-3, 2e-5, reg)
+    e.close()
