@@ -76,7 +76,11 @@ typedef enum {
   SB_INIT_GLOROT_UNIFORM = 5,
   SB_INIT_HE_UNIFORM = 6,
   SB_INIT_LECUN_UNIFORM = 7,
-  SB_INIT_ORTHOGONAL = 8      /* a = gain (0 => none); QR on the host, values uploaded */
+  SB_INIT_ORTHOGONAL = 8,     /* a = gain (0 => none); QR on the host, values uploaded */
+  SB_INIT_TRUNCATED_NORMAL = 9, /* a = mean, b = std (RandomNormalTruncated) */
+  SB_INIT_GLOROT_NORMAL = 10, /* truncated normal, std = sqrt(2/(fan_in+fan_out)) / 0.8796... */
+  SB_INIT_HE_NORMAL = 11,     /* std = sqrt(2/fan_in) / 0.8796...  */
+  SB_INIT_LECUN_NORMAL = 12   /* std = sqrt(1/fan_in) / 0.8796...  */
 } sb_init_kind;
 
 typedef struct {

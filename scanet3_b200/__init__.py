@@ -5,9 +5,9 @@ from ._native import (AVG_MEAN, AVG_SPARK_CHAIN, AVG_WEIGHTS, COLL_NCCL, COLL_P2
                       IllegalArgument, NativeError, Unsupported)
 from .dsl import *  # noqa: F401,F403
 from .dsl import (Activate, Activation, AdaDelta, AdaGrad, Adam, Adamax, Algorithm, AMSGrad, BatchNorm, Bias,
-                  BinaryCrossentropy, CategoricalCrossentropy, Composed, Const, Conv2D, Dense, Flatten, GlorotUniform,
-                  HeUniform, Identity, Initializer, L1, L2, LecunUniform, LinearRegression, LogisticRegression, Loss, LSTM,
-                  LSTMCell, MeanSquaredError, Nadam, Ones, Orthogonal, Pool2D, RandomNormal, RandomUniform, ReLU, RMSProp,
+                  BinaryCrossentropy, CategoricalCrossentropy, Composed, Const, Conv2D, Dense, Flatten, GlorotNormal, GlorotUniform, HeNormal,
+                  HeUniform, Identity, Initializer, L1, L2, LecunNormal, LecunUniform, LinearRegression, LogisticRegression, Loss, LSTM,
+                  LSTMCell, MeanSquaredError, Nadam, Ones, Orthogonal, Pool2D, RandomNormal, RandomNormalTruncated, RandomUniform, ReLU, RMSProp,
                   RNN, Same, SGD, Sigmoid, Softmax, Tanh, Valid, Zero, Zeros)
 from .engine import Engine, Group, spark_chain_weights
 from .optimizer import (Builder, Dataset, LossModel, Optimizer, RecordAccuracy, RecordIteration, RecordLoss, Step,

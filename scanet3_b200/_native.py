@@ -16,7 +16,7 @@ ACT_IDENTITY, ACT_SIGMOID, ACT_TANH, ACT_SOFTMAX, ACT_RELU = range(5)
 PAD_VALID, PAD_SAME = 0, 1
 POOL_MAX, POOL_AVG = 0, 1
 (INIT_ZEROS, INIT_ONES, INIT_CONST, INIT_RANDOM_UNIFORM, INIT_RANDOM_NORMAL, INIT_GLOROT_UNIFORM, INIT_HE_UNIFORM,
- INIT_LECUN_UNIFORM, INIT_ORTHOGONAL) = range(9)
+ INIT_LECUN_UNIFORM, INIT_ORTHOGONAL, INIT_TRUNCATED_NORMAL, INIT_GLOROT_NORMAL, INIT_HE_NORMAL, INIT_LECUN_NORMAL) = range(13)
 LOSS_MSE, LOSS_BCE, LOSS_CCE = range(3)
 OPT_SGD, OPT_ADAM, OPT_ADAGRAD, OPT_RMSPROP, OPT_ADADELTA, OPT_ADAMAX, OPT_NADAM, OPT_AMSGRAD = range(8)
 PREC_FP32, PREC_TF32, PREC_3XTF32 = range(3)

@@ -991,6 +991,17 @@ static void init_param(sb_engine* e, const Param& p) {
       philox_fill(dst, p.numel, (unsigned long long)in.seed, 0, 2.0f * limit, 1, -limit, 1, s);
       break;
     }
+    case SB_INIT_TRUNCATED_NORMAL: need_seed(); philox_fill(dst, p.numel, (unsigned long long)in.seed, 2, in.b, 1, in.a, 1, s); break;
+    case SB_INIT_GLOROT_NORMAL:
+    case SB_INIT_HE_NORMAL:
+    case SB_INIT_LECUN_NORMAL: {
+      // truncated normal with std = sqrt(c / fan) / 0.87962566 (models/Initializer.scala:93-110, 128-150, 168-190)
+      need_seed();
+      const float std_ = in.kind == SB_INIT_GLOROT_NORMAL ? f32_sqrt_ratio(2.0f, fin + fout)
+                                                          : f32_sqrt_ratio(in.kind == SB_INIT_HE_NORMAL ? 2.0f : 1.0f, fin);
+      philox_fill(dst, p.numel, (unsigned long long)in.seed, 2, std_ / 0.87962566103423978f, 1, 0.f, 0, s);
+      break;
+    }
     case SB_INIT_ORTHOGONAL: {
       need_seed();
       std::vector<float> host((size_t)p.numel);

@@ -1120,7 +1120,25 @@ __global__ void philox_fill_kernel(float* __restrict__ p, long long n, unsigned 
   unsigned int w[4];
   philox_block(seed, (unsigned long long)blk, w);
   float v[4];
-  if (!normal) {
+  if (normal == 2) {
+    // TF TruncatedNormal(float32): every group of 4 outputs restarts the generator at counter group*256 and draws word pairs
+    // (Box-Muller) until four values with |x| < 2 are found (random_distributions.h TruncatedNormalDistribution)
+    int got = 0;
+    unsigned long long ctr = (unsigned long long)blk * 256ull;
+    while (got < 4) {
+      philox_block(seed, ctr++, w);
+      for (int j = 0; j < 4 && got < 4; j += 2) {
+        float u1 = fmaxf(u32_to_float(w[j]), 1.0e-7f);
+        float v1 = (float)(6.283185307179586 * (double)u32_to_float(w[j + 1]));
+        float u2 = sqrtf(__fmul_rn(-2.0f, logf(u1)));
+        float sn, cs;
+        sincosf(v1, &sn, &cs);
+        const float f0 = __fmul_rn(sn, u2), f1 = __fmul_rn(cs, u2);
+        if (fabsf(f0) < 2.0f) v[got++] = f0;
+        if (got < 4 && fabsf(f1) < 2.0f) v[got++] = f1;
+      }
+    }
+  } else if (!normal) {
     for (int j = 0; j < 4; ++j) v[j] = u32_to_float(w[j]);
   } else {
     for (int j = 0; j < 4; j += 2) {  // BoxMullerFloat

@@ -55,6 +55,23 @@ def LecunUniform(seed: Optional[int] = None):
     return Initializer(N.INIT_LECUN_UNIFORM, seed, name="LecunUniform")
 
 
+def RandomNormalTruncated(mean: float = 0.0, std: float = 0.05, seed: Optional[int] = None):
+    """models/Initializer.scala:62-70 (TF TruncatedNormal)"""
+    return Initializer(N.INIT_TRUNCATED_NORMAL, seed, mean, std, name="RandomNormalTruncated")
+
+
+def GlorotNormal(seed: Optional[int] = None):
+    return Initializer(N.INIT_GLOROT_NORMAL, seed, name="GlorotNormal")
+
+
+def HeNormal(seed: Optional[int] = None):
+    return Initializer(N.INIT_HE_NORMAL, seed, name="HeNormal")
+
+
+def LecunNormal(seed: Optional[int] = None):
+    return Initializer(N.INIT_LECUN_NORMAL, seed, name="LecunNormal")
+
+
 def Orthogonal(gain: Optional[float] = None, seed: Optional[int] = None):
     return Initializer(N.INIT_ORTHOGONAL, seed, 0.0 if gain is None else gain, name="Orthogonal")
 

@@ -410,3 +410,21 @@ def test_regularised_mlp_trajectory(reg):
         assert abs(gl - float(ol)) <= 2e-5 * abs(float(ol)) + 1e-6, (t, gl, float(ol))  # loss includes the penalty
     assert_params_close(e.get_model_params(), mp, 1e-3, 2e-5, reg)
     e.close()
+
+
+def test_device_truncated_normal_initializers():  # models/InitializerSpec.scala:44-66 goldens + the oracle's restated TF stream
+    e = make_engine(S.Dense(3, kernelInitializer=S.RandomNormalTruncated(0.0, 1.0, seed=1), bias=False), S.MeanSquaredError, S.SGD(),
+                    1, (1,), (3,))
+    e.init_params()
+    w = e.get_param("weights").reshape(-1)
+    assert np.array_equal(np.round(w * f32(100)) / f32(100), np.array([0.31, 0.57, 0.42], f32))
+    e.close()
+    for sinit, oinit, shape in [(S.GlorotNormal(2), O.GlorotNormal(seed=2), (37, 50)), (S.HeNormal(3), O.HeNormal(seed=3), (64, 9)),
+                                (S.LecunNormal(4), O.LecunNormal(seed=4), (5, 130)),
+                                (S.RandomNormalTruncated(0.5, 0.2, seed=9), O.RandomNormalTruncated(0.5, 0.2, seed=9), (33, 7))]:
+        e = make_engine(S.Dense(shape[1], kernelInitializer=sinit, bias=False), S.MeanSquaredError, S.SGD(), 1, (shape[0],), (shape[1],))
+        e.init_params()
+        got, want = e.get_param("weights"), oinit.build(shape)
+        assert np.max(np.abs(got)) < 2.0 * np.max(np.abs(want)) + 1.0
+        np.testing.assert_allclose(got, want, rtol=0, atol=3e-6)  # same accepted samples; libm vs CUDA sincos/log at the ulp level
+        e.close()
