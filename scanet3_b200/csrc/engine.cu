@@ -25,6 +25,13 @@ struct ApiError : std::runtime_error {
   ApiError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
 };
 void set_error(const std::string& m) { tl_error = m; }
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* v = getenv("SB_PDL");
+    return !(v && v[0] == '0');
+  }();
+  return on;
+}
 }  // namespace sb
 #define SB_FAIL(code, msg) throw ::sb::ApiError((code), (msg))
 #define SB_API_BEGIN try {

@@ -59,6 +59,7 @@ struct PeerSet {
 
 // float4 slice [lo4, hi4) of the arena: load from every peer, weighted ordered sum, store to every peer
 __global__ void __launch_bounds__(256) p2p_average_kernel(PeerSet ps, long long lo4, long long hi4) {
+  pdl_prologue();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = lo4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi4; i += stride) {
     float4 v[kMaxRanks];
@@ -112,6 +113,7 @@ __device__ __forceinline__ void wait_flag(const unsigned long long* p, unsigned 
   }
 }
 __global__ void __launch_bounds__(256) p2p_average_sync_kernel(PeerSet ps, long long lo4, long long hi4, SyncArgs a) {
+  pdl_prologue();
   unsigned long long* my_tail = reinterpret_cast<unsigned long long*>(ps.ptr[a.rank] + a.tail_off);
   if (threadIdx.x == 0) {
     if (blockIdx.x == 0) {
@@ -380,7 +382,7 @@ static void launch_slice(sb_group* g, int r) {
   const long long lo = per * r, hi = std::min(n4, per * (r + 1));
   if (hi <= lo) return;
   int blocks = (int)std::min<long long>((hi - lo + 255) / 256, (long long)kNumSMs * 4);
-  p2p_average_kernel<<<blocks, 256, 0, e->stream>>>(g->ps[r], lo, hi);
+  launch_k(p2p_average_kernel, blocks, 256, 0, e->stream, g->ps[r], lo, hi);
   SB_LAUNCHED();
   e->launches += 1;
 }
@@ -413,7 +415,7 @@ extern "C" int sb_group_average_device(sb_group* g, uint64_t epoch) {
   a.rank = g->rank;
   a.my_loss = &e->st->loss;
   a.ticket = g->ticket;
-  p2p_average_sync_kernel<<<blocks, 256, 0, e->stream>>>(g->ps[g->rank], lo, hi, a);
+  launch_k(p2p_average_sync_kernel, blocks, 256, 0, e->stream, g->ps[g->rank], lo, hi, a);
   SB_LAUNCHED();
   e->launches += 1;
   int rc = sb_reset_unaggregated(e);  // aggregation == None tensors are re-initialised (Optimizer.scala:209)

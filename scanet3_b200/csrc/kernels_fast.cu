@@ -26,6 +26,7 @@ static int grid_for(long long n, int threads) {
 // max pool, C % 4 == 0  (math/nn/AllKernels.scala:270-324)
 // =====================================================================================================================
 __global__ void __launch_bounds__(256) pool_max_fwd_v4_kernel(const float* __restrict__ x, float* __restrict__ y, PoolGeom g, long long n4) {
+  pdl_prologue();
   const int C4 = g.C >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const int c4 = (int)(i % C4);
@@ -53,6 +54,7 @@ __global__ void __launch_bounds__(256) pool_max_fwd_v4_kernel(const float* __res
 constexpr int kPoolSegs = 4;
 __global__ void __launch_bounds__(256) pool22_fwd_strip_kernel(const float* __restrict__ x, float* __restrict__ y, PoolGeom g,
                                                                int seg_len, long long n_threads) {
+  pdl_prologue();
   const int C4 = g.C >> 2;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_threads) return;
@@ -82,12 +84,12 @@ void pool_max_fwd_v4(const float* x, float* y, const PoolGeom& g, cudaStream_t s
   if (pool_is_22s1(g)) {
     const long long nt = (long long)g.N * g.OH * kPoolSegs * (g.C / 4);
     const int seg_len = (g.OW + kPoolSegs - 1) / kPoolSegs;
-    pool22_fwd_strip_kernel<<<(int)((nt + 255) / 256), 256, 0, s>>>(x, y, g, seg_len, nt);
+    launch_k(pool22_fwd_strip_kernel, (int)((nt + 255) / 256), 256, 0, s, x, y, g, seg_len, nt);
     SB_LAUNCHED();
     return;
   }
   const long long n4 = (long long)g.N * g.OH * g.OW * (g.C / 4);
-  pool_max_fwd_v4_kernel<<<grid_for(n4, 256), 256, 0, s>>>(x, y, g, n4);
+  launch_k(pool_max_fwd_v4_kernel, grid_for(n4, 256), 256, 0, s, x, y, g, n4);
   SB_LAUNCHED();
 }
 
@@ -99,6 +101,7 @@ __device__ __forceinline__ void pool_win_acc(float self, float v, bool earlier, 
 template <bool RELU>
 __global__ void __launch_bounds__(256) pool_max_bwd_v4_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                               float* __restrict__ dx, PoolGeom g, float thr, long long n4) {
+  pdl_prologue();
   const int C4 = g.C >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const int c4 = (int)(i % C4);
@@ -176,6 +179,7 @@ template <bool RELU>
 __global__ void __launch_bounds__(256) pool22_bwd_strip_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                float* __restrict__ dx, PoolGeom g, float thr, int seg_len,
                                                                int segs, long long n_threads) {
+  pdl_prologue();
   const int C4 = g.C >> 2;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_threads) return;
@@ -255,14 +259,14 @@ void pool_max_bwd_v4(const float* x, const float* dy, float* dx, const PoolGeom&
     }
     const int seg_len = (g.W + best_segs - 1) / best_segs;
     const long long nt = (long long)g.N * g.H * best_segs * (g.C / 4);
-    if (relu) pool22_bwd_strip_kernel<true><<<(int)((nt + 127) / 128), 128, 0, s>>>(x, dy, dx, g, thr, seg_len, best_segs, nt);
-    else pool22_bwd_strip_kernel<false><<<(int)((nt + 127) / 128), 128, 0, s>>>(x, dy, dx, g, 0.f, seg_len, best_segs, nt);
+    if (relu) launch_k(pool22_bwd_strip_kernel<true>, (int)((nt + 127) / 128), 128, 0, s, x, dy, dx, g, thr, seg_len, best_segs, nt);
+    else launch_k(pool22_bwd_strip_kernel<false>, (int)((nt + 127) / 128), 128, 0, s, x, dy, dx, g, 0.f, seg_len, best_segs, nt);
     SB_LAUNCHED();
     return;
   }
   const long long n4 = (long long)g.N * g.H * g.W * (g.C / 4);
-  if (relu) pool_max_bwd_v4_kernel<true><<<grid_for(n4, 256), 256, 0, s>>>(x, dy, dx, g, thr, n4);
-  else pool_max_bwd_v4_kernel<false><<<grid_for(n4, 256), 256, 0, s>>>(x, dy, dx, g, 0.f, n4);
+  if (relu) launch_k(pool_max_bwd_v4_kernel<true>, grid_for(n4, 256), 256, 0, s, x, dy, dx, g, thr, n4);
+  else launch_k(pool_max_bwd_v4_kernel<false>, grid_for(n4, 256), 256, 0, s, x, dy, dx, g, 0.f, n4);
   SB_LAUNCHED();
 }
 
@@ -272,6 +276,7 @@ void pool_max_bwd_v4(const float* x, const float* dy, float* dx, const PoolGeom&
 constexpr int kSmallK = 32;
 __global__ void __launch_bounds__(256) conv_smallk_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                               float* __restrict__ y, ConvGeom g, int relu, float thr, long long n4) {
+  pdl_prologue();
   const int C4 = g.Cout >> 2;
   const int K = g.KH * g.KW * g.Cin;
   __shared__ float sw[kSmallK * 256];  // filter [K][Cout], Cout <= 256
@@ -310,6 +315,7 @@ template <int KH, int KW, int CIN, int PW>
 __global__ void __launch_bounds__(256) conv_smallk_fwd_tile_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                    float* __restrict__ y, ConvGeom g, int relu, float thr,
                                                                    int segs, long long n_threads) {
+  pdl_prologue();
   constexpr int K = KH * KW * CIN;
   const int C4 = g.Cout >> 2;
   extern __shared__ __align__(16) float swt[];  // filter [K][Cout]
@@ -367,7 +373,7 @@ static void launch_smallk_tile(const float* x, const float* w, float* y, const C
   const int segs = (g.OW + PW - 1) / PW;
   const long long nt = (long long)g.N * g.OH * segs * (g.Cout / 4);
   const size_t smem = (size_t)KH * KW * CIN * g.Cout * sizeof(float);
-  conv_smallk_fwd_tile_kernel<KH, KW, CIN, PW><<<(int)((nt + 255) / 256), 256, smem, s>>>(x, w, y, g, relu, thr, segs, nt);
+  launch_k(conv_smallk_fwd_tile_kernel<KH, KW, CIN, PW>, (int)((nt + 255) / 256), 256, smem, s, x, w, y, g, relu, thr, segs, nt);
   SB_LAUNCHED();
 }
 void conv_smallk_fwd(const float* x, const float* w, float* y, const ConvGeom& g, int relu, float thr, cudaStream_t s) {
@@ -378,7 +384,7 @@ void conv_smallk_fwd(const float* x, const float* w, float* y, const ConvGeom& g
     if (shape == 551) return launch_smallk_tile<5, 5, 1>(x, w, y, g, relu, thr, s);
   }
   const long long n4 = (long long)g.N * g.OH * g.OW * (g.Cout / 4);
-  conv_smallk_fwd_kernel<<<grid_for(n4, 256), 256, 0, s>>>(x, w, y, g, relu, thr, n4);
+  launch_k(conv_smallk_fwd_kernel, grid_for(n4, 256), 256, 0, s, x, w, y, g, relu, thr, n4);
   SB_LAUNCHED();
 }
 
@@ -388,6 +394,7 @@ template <int KH, int KW, int CIN>
 __global__ void __launch_bounds__(256) conv_smallk_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                 float* __restrict__ partial, ConvGeom g, long long pixels,
                                                                 long long pix_per_block) {
+  pdl_prologue();
   constexpr int K = KH * KW * CIN;
   const int C4 = g.Cout >> 2;
   const int lanes = blockDim.x / C4;
@@ -481,9 +488,9 @@ bool conv_smallk_wgrad(const float* x, const float* dy, float* dw, const ConvGeo
   if (blocks > pixels) blocks = (int)pixels;
   const long long ppb = (pixels + blocks - 1) / blocks;
   blocks = (int)((pixels + ppb - 1) / ppb);
-  if (shape == 331) conv_smallk_wgrad_kernel<3, 3, 1><<<blocks, 256, smem, s>>>(x, dy, ws, g, pixels, ppb);
-  else if (shape == 333) conv_smallk_wgrad_kernel<3, 3, 3><<<blocks, 256, smem, s>>>(x, dy, ws, g, pixels, ppb);
-  else conv_smallk_wgrad_kernel<5, 5, 1><<<blocks, 256, smem, s>>>(x, dy, ws, g, pixels, ppb);
+  if (shape == 331) launch_k(conv_smallk_wgrad_kernel<3, 3, 1>, blocks, 256, smem, s, x, dy, ws, g, pixels, ppb);
+  else if (shape == 333) launch_k(conv_smallk_wgrad_kernel<3, 3, 3>, blocks, 256, smem, s, x, dy, ws, g, pixels, ppb);
+  else launch_k(conv_smallk_wgrad_kernel<5, 5, 1>, blocks, 256, smem, s, x, dy, ws, g, pixels, ppb);
   SB_LAUNCHED();
   const int n = K * g.Cout;
   partial_reduce(ws, dw, n, blocks, s);
@@ -501,6 +508,7 @@ constexpr int kHeadThreads = 128;
 // generic deterministic column reduction  out[i] = sum_c partial[c][i]  (c ascending inside a lane group, then a fixed tree)
 __global__ void __launch_bounds__(256) partial_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int n,
                                                              int parts) {
+  pdl_prologue();
   __shared__ float red[8][33];
   const int i = blockIdx.x * 32 + threadIdx.x, y = threadIdx.y;
   float acc = 0.f;
@@ -516,7 +524,7 @@ __global__ void __launch_bounds__(256) partial_reduce_kernel(const float* __rest
   }
 }
 void partial_reduce(const float* partial, float* out, int n, int parts, cudaStream_t s) {
-  partial_reduce_kernel<<<(n + 31) / 32, dim3(32, 8), 0, s>>>(partial, out, n, parts);
+  launch_k(partial_reduce_kernel, (n + 31) / 32, dim3(32, 8), 0, s, partial, out, n, parts);
   SB_LAUNCHED();
 }
 
@@ -529,6 +537,7 @@ constexpr int kHeadKQ = 4;
 template <int NT>
 __global__ void __launch_bounds__(kHeadThreads* kHeadKQ) dense_head_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                                float* __restrict__ partial, int Mtot, int K, int N, int KC) {
+  pdl_prologue();
   extern __shared__ __align__(128) float sm[];
   const int xs_stride = KC + 4;
   const int Mcap = min(kHeadThreads, Mtot);
@@ -626,8 +635,8 @@ bool dense_head_fwd(const float* x, const float* w, float* partial, int* chunks_
     attr = true;
   }
   const dim3 grid(chunks, m_chunks);
-  if (NT == 12) dense_head_fwd_kernel<12><<<grid, kHeadThreads * kHeadKQ, smem, s>>>(x, w, partial, M, K, N, KC);
-  else dense_head_fwd_kernel<16><<<grid, kHeadThreads * kHeadKQ, smem, s>>>(x, w, partial, M, K, N, KC);
+  if (NT == 12) launch_k(dense_head_fwd_kernel<12>, grid, kHeadThreads * kHeadKQ, smem, s, x, w, partial, M, K, N, KC);
+  else launch_k(dense_head_fwd_kernel<16>, grid, kHeadThreads * kHeadKQ, smem, s, x, w, partial, M, K, N, KC);
   SB_LAUNCHED();
   *chunks_out = chunks;
   return true;
@@ -649,6 +658,7 @@ __global__ void __launch_bounds__(kBwdK* kBwdGroups) dense_head_bwd_kernel(const
                                                                             const float* __restrict__ w, float* __restrict__ dw,
                                                                             float* __restrict__ dx, int Mtot, int K, int N,
                                                                             int rows_per_split) {
+  pdl_prologue();
   extern __shared__ __align__(128) float sm[];
   // blockIdx.y = row split: rows [mlo, mhi); its dW goes to slice blockIdx.y of `dw` (summed in split order afterwards)
   const int mlo = blockIdx.y * rows_per_split, M = min(Mtot, mlo + rows_per_split);
@@ -731,11 +741,11 @@ bool dense_head_bwd(const float* x, const float* g, const float* w, float* dw, f
   float* dwo = splits > 1 ? ws : dw;
   const dim3 grid(kblocks, splits);
   if (NT == 12) {
-    if (dx) dense_head_bwd_kernel<12, true><<<grid, thr, smem, s>>>(x, g, w, dwo, dx, M, K, N, rows_per_split);
-    else dense_head_bwd_kernel<12, false><<<grid, thr, smem, s>>>(x, g, w, dwo, dx, M, K, N, rows_per_split);
+    if (dx) launch_k(dense_head_bwd_kernel<12, true>, grid, thr, smem, s, x, g, w, dwo, dx, M, K, N, rows_per_split);
+    else launch_k(dense_head_bwd_kernel<12, false>, grid, thr, smem, s, x, g, w, dwo, dx, M, K, N, rows_per_split);
   } else {
-    if (dx) dense_head_bwd_kernel<16, true><<<grid, thr, smem, s>>>(x, g, w, dwo, dx, M, K, N, rows_per_split);
-    else dense_head_bwd_kernel<16, false><<<grid, thr, smem, s>>>(x, g, w, dwo, dx, M, K, N, rows_per_split);
+    if (dx) launch_k(dense_head_bwd_kernel<16, true>, grid, thr, smem, s, x, g, w, dwo, dx, M, K, N, rows_per_split);
+    else launch_k(dense_head_bwd_kernel<16, false>, grid, thr, smem, s, x, g, w, dwo, dx, M, K, N, rows_per_split);
   }
   SB_LAUNCHED();
   if (splits > 1) partial_reduce(ws, dw, K * N, splits, s);
@@ -759,6 +769,7 @@ __device__ __forceinline__ float act_grad1(float g, float y, int act, float thr)
 __global__ void __launch_bounds__(256) act_bwd_col_sum_kernel(float* __restrict__ g, const float* __restrict__ y, int act, float thr,
                                                               float* __restrict__ partial, long long rows, int C,
                                                               long long rows_per_chunk) {
+  pdl_prologue();
   __shared__ float4 red[8][33];
   const int c4 = blockIdx.x * 32 + threadIdx.x;  // column quad
   const long long r0 = (long long)blockIdx.y * rows_per_chunk;
@@ -798,7 +809,7 @@ bool act_bwd_col_sum(float* g, const float* y, int act, float thr, float* out, l
   if (chunks < 1) return false;
   const long long rpc = (rows + chunks - 1) / chunks;
   chunks = (rows + rpc - 1) / rpc;
-  act_bwd_col_sum_kernel<<<dim3(col_blocks, (unsigned)chunks), dim3(32, 8), 0, s>>>(g, y, act, thr, ws, rows, C, rpc);
+  launch_k(act_bwd_col_sum_kernel, dim3(col_blocks, (unsigned)chunks), dim3(32, 8), 0, s, g, y, act, thr, ws, rows, C, rpc);
   SB_LAUNCHED();
   partial_reduce(ws, out, C, (int)chunks, s);
   return true;
@@ -816,6 +827,7 @@ __global__ void __launch_bounds__(1024) head_bias_softmax_cce_kernel(float* __re
                                                                      const float* __restrict__ y, float* __restrict__ dz,
                                                                      float* __restrict__ dbias, StepState* st, int rows, int C,
                                                                      float* __restrict__ scratch, unsigned int* ticket) {
+  pdl_prologue();
   __shared__ float zs[8][kHeadRows * 32];
   __shared__ float sl[kHeadRows];
   __shared__ float sdb[kHeadRows][33];
@@ -911,7 +923,7 @@ bool head_bias_softmax_cce(float* z, const float* partial, int chunks, const flo
   if (C > 32) return false;
   const int grid = (rows + kHeadRows - 1) / kHeadRows;
   if (grid > 1024) return false;  // scratch holds 1024 CTA partials
-  head_bias_softmax_cce_kernel<<<grid, 1024, 0, s>>>(z, partial, chunks, bias, y, dz, dbias, st, rows, C, scratch,
+  launch_k(head_bias_softmax_cce_kernel, grid, 1024, 0, s, z, partial, chunks, bias, y, dz, dbias, st, rows, C, scratch,
                                                      reinterpret_cast<unsigned int*>(scratch + 1024 * 40));
   SB_LAUNCHED();
   return true;

@@ -16,6 +16,7 @@ template <typename V>
 __global__ void step_prologue_kernel(StepState* st, const V* __restrict__ ds_x, const V* __restrict__ ds_y,
                                      V* __restrict__ bx, V* __restrict__ by, long long x4, long long y4,
                                      float beta1, float beta2, int batch_from_state) {
+  pdl_prologue();
   // resident shard: batch index from the device state (only the optimizer kernel of the previous step writes it);
   // host-fed staging buffer: always its single batch
   const long long b = batch_from_state ? st->batch_idx : 0;
@@ -49,10 +50,10 @@ void step_prologue(StepState* st, const float* ds_x, const float* ds_y, float* b
   if (ds_x) blocks = (int)fmin((double)ceil_div(xn + yn, 256), (double)kNumSMs * 8);
   if (blocks < 1) blocks = 1;
   if (vec)
-    step_prologue_kernel<float4><<<blocks, 256, 0, s>>>(st, (const float4*)ds_x, (const float4*)ds_y, (float4*)bx,
+    launch_k(step_prologue_kernel<float4>, blocks, 256, 0, s, st, (const float4*)ds_x, (const float4*)ds_y, (float4*)bx,
                                                         (float4*)by, xn, yn, beta1, beta2, batch_from_state);
   else
-    step_prologue_kernel<float><<<blocks, 256, 0, s>>>(st, ds_x, ds_y, bx, by, xn, yn, beta1, beta2, batch_from_state);
+    launch_k(step_prologue_kernel<float>, blocks, 256, 0, s, st, ds_x, ds_y, bx, by, xn, yn, beta1, beta2, batch_from_state);
   SB_LAUNCHED();
 }
 
@@ -123,6 +124,7 @@ struct LdConvWgradA {
 template <class AL, class BL, bool A_K_CONTIG, bool B_N_CONTIG>
 __global__ void __launch_bounds__(256) gemm_tiled_kernel(AL a, BL b, float* __restrict__ C, int M, int N, int K,
                                                          int k_per_split, float* __restrict__ partial) {
+  pdl_prologue();
   __shared__ float As[16][68];
   __shared__ float Bs[16][68];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -181,6 +183,7 @@ __global__ void __launch_bounds__(256) gemm_tiled_kernel(AL a, BL b, float* __re
 }
 
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, float* __restrict__ C, long long mn, int splits) {
+  pdl_prologue();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= mn) return;
   float acc = partial[i];
@@ -206,11 +209,11 @@ static void launch_gemm(AL a, BL b, float* C, int M, int N, int K, float* ws, si
   kps = ((kps + 15) / 16) * 16;
   splits = ceil_div(K, kps);
   dim3 grid(mt, nt, splits);
-  gemm_tiled_kernel<AL, BL, A_K_CONTIG, B_N_CONTIG><<<grid, 256, 0, s>>>(a, b, C, M, N, K, kps, splits > 1 ? ws : nullptr);
+  launch_k(gemm_tiled_kernel<AL, BL, A_K_CONTIG, B_N_CONTIG>, grid, 256, 0, s, a, b, C, M, N, K, kps, splits > 1 ? ws : nullptr);
   SB_LAUNCHED();
   if (splits > 1) {
     long long mn = (long long)M * N;
-    splitk_reduce_kernel<<<ceil_div(mn, 256), 256, 0, s>>>(ws, C, mn, splits);
+    launch_k(splitk_reduce_kernel, ceil_div(mn, 256), 256, 0, s, ws, C, mn, splits);
     SB_LAUNCHED();
   }
 }
@@ -243,6 +246,7 @@ void conv2d_wgrad(const float* x, const float* dy, float* dw, const ConvGeom& g,
 // bias add / column sums (layer/Bias.scala:32-33; gradient = Sum over all-but-last axes, alg:12-33)
 // =================================================================================================
 __global__ void bias_add_kernel(float* __restrict__ x, const float* __restrict__ b, long long n, int C) {
+  pdl_prologue();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) x[i] = __fadd_rn(x[i], __ldg(b + (int)(i % C)));
@@ -250,7 +254,7 @@ __global__ void bias_add_kernel(float* __restrict__ x, const float* __restrict__
 void bias_add(float* x, const float* b, long long rows, int C, cudaStream_t s) {
   long long n = rows * C;
   int blocks = (int)fmin((double)ceil_div(n, 256), (double)kNumSMs * 16);
-  bias_add_kernel<<<blocks, 256, 0, s>>>(x, b, n, C);
+  launch_k(bias_add_kernel, blocks, 256, 0, s, x, b, n, C);
   SB_LAUNCHED();
 }
 
@@ -259,6 +263,7 @@ void bias_add(float* x, const float* b, long long rows, int C, cudaStream_t s) {
 template <class F>
 __global__ void __launch_bounds__(256) col_reduce_kernel(F f, float* __restrict__ partial, long long rows, int C,
                                                          long long rows_per_chunk) {
+  pdl_prologue();
   __shared__ float sm0[8][33], sm1[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const long long r0 = (long long)blockIdx.y * rows_per_chunk;
@@ -301,7 +306,7 @@ template <class F>
 static ColChunks launch_col_reduce(F f, float* ws, size_t wsf, long long rows, int C, cudaStream_t s) {
   ColChunks cc = col_chunks(rows, C, wsf);
   dim3 grid(ceil_div(C, 32), cc.chunks);
-  col_reduce_kernel<F><<<grid, dim3(32, 8), 0, s>>>(f, ws, rows, C, cc.rows_per_chunk);
+  launch_k(col_reduce_kernel<F>, grid, dim3(32, 8), 0, s, f, ws, rows, C, cc.rows_per_chunk);
   SB_LAUNCHED();
   return cc;
 }
@@ -320,12 +325,13 @@ struct FSum {
   __device__ __forceinline__ float2 operator()(long long r, int c) const { return make_float2(__ldg(g + r * C + c), 0.f); }
 };
 __global__ void col_sum_finalize_kernel(const float* __restrict__ partial, float* __restrict__ out, int chunks, int C) {
+  pdl_prologue();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) out[c] = finalize_partials(partial, chunks, C, c).x;
 }
 void col_sum(const float* g, float* out, long long rows, int C, float* ws, size_t wsf, cudaStream_t s) {
   ColChunks cc = launch_col_reduce(FSum{g, C}, ws, wsf, rows, C, s);
-  col_sum_finalize_kernel<<<ceil_div(C, 128), 128, 0, s>>>(ws, out, cc.chunks, C);
+  launch_k(col_sum_finalize_kernel, ceil_div(C, 128), 128, 0, s, ws, out, cc.chunks, C);
   SB_LAUNCHED();
 }
 
@@ -351,6 +357,7 @@ __device__ __forceinline__ float act_grad(float g, float y, int act, float thr) 
   }
 }
 __global__ void act_fwd_kernel(float* __restrict__ x, int act, float thr, long long n) {
+  pdl_prologue();
   long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const long long stride = (long long)gridDim.x * blockDim.x * 4;
   for (; i < n; i += stride) {
@@ -365,6 +372,7 @@ __global__ void act_fwd_kernel(float* __restrict__ x, int act, float thr, long l
   }
 }
 __global__ void act_bwd_kernel(float* __restrict__ g, const float* __restrict__ y, int act, float thr, long long n) {
+  pdl_prologue();
   long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const long long stride = (long long)gridDim.x * blockDim.x * 4;
   for (; i < n; i += stride) {
@@ -387,12 +395,12 @@ static int ew_blocks(long long n) {
 }
 void act_fwd(float* x, int act, float thr, long long n, cudaStream_t s) {
   if (act == 0 || n == 0) return;
-  act_fwd_kernel<<<ew_blocks(n), 256, 0, s>>>(x, act, thr, n);
+  launch_k(act_fwd_kernel, ew_blocks(n), 256, 0, s, x, act, thr, n);
   SB_LAUNCHED();
 }
 void act_bwd(float* g, const float* y, int act, float thr, long long n, cudaStream_t s) {
   if (act == 0 || n == 0) return;
-  act_bwd_kernel<<<ew_blocks(n), 256, 0, s>>>(g, y, act, thr, n);
+  launch_k(act_bwd_kernel, ew_blocks(n), 256, 0, s, g, y, act, thr, n);
   SB_LAUNCHED();
 }
 
@@ -403,6 +411,7 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 __global__ void softmax_fwd_kernel(float* __restrict__ x, int rows, int C) {
+  pdl_prologue();
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -418,6 +427,7 @@ __global__ void softmax_fwd_kernel(float* __restrict__ x, int rows, int C) {
 }
 // dz = p * (g - sum_j g_j p_j)
 __global__ void softmax_bwd_kernel(float* __restrict__ g, const float* __restrict__ p, int rows, int C) {
+  pdl_prologue();
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -429,11 +439,11 @@ __global__ void softmax_bwd_kernel(float* __restrict__ g, const float* __restric
   for (int c = lane; c < C; c += 32) gr[c] = __fmul_rn(pr[c], __fsub_rn(gr[c], dot));
 }
 void softmax_fwd(float* x, int rows, int C, cudaStream_t s) {
-  softmax_fwd_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(x, rows, C);
+  launch_k(softmax_fwd_kernel, ceil_div(rows, 8), 256, 0, s, x, rows, C);
   SB_LAUNCHED();
 }
 void softmax_bwd(float* g, const float* p, int rows, int C, cudaStream_t s) {
-  softmax_bwd_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(g, p, rows, C);
+  launch_k(softmax_bwd_kernel, ceil_div(rows, 8), 256, 0, s, g, p, rows, C);
   SB_LAUNCHED();
 }
 
@@ -455,6 +465,7 @@ __device__ float block_sum_1024(float v) {
 }
 __global__ void __launch_bounds__(1024) loss_kernel(int loss, const float* __restrict__ p, const float* __restrict__ y,
                                                     float* __restrict__ dp, StepState* st, long long rows, long long n) {
+  pdl_prologue();
   const float eps = 1e-8f;
   const float fn = (float)n, fr = (float)rows;
   float acc = 0.f;
@@ -482,7 +493,7 @@ __global__ void __launch_bounds__(1024) loss_kernel(int loss, const float* __res
 }
 void loss_fwd_bwd(int loss, const float* pred, const float* y, float* dpred, StepState* st, long long rows, long long cols,
                   cudaStream_t s) {
-  loss_kernel<<<1, 1024, 0, s>>>(loss, pred, y, dpred, st, rows, rows * cols);
+  launch_k(loss_kernel, 1, 1024, 0, s, loss, pred, y, dpred, st, rows, rows * cols);
   SB_LAUNCHED();
 }
 
@@ -490,6 +501,7 @@ void loss_fwd_bwd(int loss, const float* pred, const float* y, float* dpred, Ste
 // r_i = y_i/(p_i+eps);  dz_j = -(p_j/B) * (r_j - sum_i r_i p_i)
 __global__ void __launch_bounds__(1024) softmax_cce_kernel(float* __restrict__ z, const float* __restrict__ y,
                                                            float* __restrict__ dz, StepState* st, int rows, int C) {
+  pdl_prologue();
   const float eps = 1e-8f, fr = (float)rows;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   float acc = 0.f;
@@ -526,7 +538,7 @@ __global__ void __launch_bounds__(1024) softmax_cce_kernel(float* __restrict__ z
   if (threadIdx.x == 0) st->loss = __fdiv_rn(-tot, fr);
 }
 void softmax_cce_fwd_bwd(float* z, const float* y, float* dz, StepState* st, int rows, int C, cudaStream_t s) {
-  softmax_cce_kernel<<<1, 1024, 0, s>>>(z, y, dz, st, rows, C);
+  launch_k(softmax_cce_kernel, 1, 1024, 0, s, z, y, dz, st, rows, C);
   SB_LAUNCHED();
 }
 
@@ -534,6 +546,7 @@ void softmax_cce_fwd_bwd(float* z, const float* y, float* dz, StepState* st, int
 // Pool2D (math/nn/AllKernels.scala:270-374).  NHWC, channel fastest => coalesced.
 // =================================================================================================
 __global__ void pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, PoolGeom g, int reduce, long long n) {
+  pdl_prologue();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
@@ -562,7 +575,7 @@ __global__ void pool_fwd_kernel(const float* __restrict__ x, float* __restrict__
 void pool_fwd(const float* x, float* y, const PoolGeom& g, int reduce, cudaStream_t s) {
   long long n = (long long)g.N * g.OH * g.OW * g.C;
   int blocks = (int)fmin((double)ceil_div(n, 256), (double)kNumSMs * 16);
-  pool_fwd_kernel<<<blocks, 256, 0, s>>>(x, y, g, reduce, n);
+  launch_k(pool_fwd_kernel, blocks, 256, 0, s, x, y, g, reduce, n);
   SB_LAUNCHED();
 }
 
@@ -571,6 +584,7 @@ void pool_fwd(const float* x, float* y, const PoolGeom& g, int reduce, cudaStrea
 template <bool RELU>
 __global__ void pool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, PoolGeom g,
                                 int reduce, float thr, long long n) {
+  pdl_prologue();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
@@ -626,13 +640,13 @@ __global__ void pool_bwd_kernel(const float* __restrict__ x, const float* __rest
 void pool_bwd(const float* x, const float* dy, float* dx, const PoolGeom& g, int reduce, cudaStream_t s) {
   long long n = (long long)g.N * g.H * g.W * g.C;
   int blocks = (int)fmin((double)ceil_div(n, 256), (double)kNumSMs * 16);
-  pool_bwd_kernel<false><<<blocks, 256, 0, s>>>(x, dy, dx, g, reduce, 0.f, n);
+  launch_k(pool_bwd_kernel<false>, blocks, 256, 0, s, x, dy, dx, g, reduce, 0.f, n);
   SB_LAUNCHED();
 }
 void pool_bwd_relu(const float* x, const float* dy, float* dx, const PoolGeom& g, float thr, cudaStream_t s) {
   long long n = (long long)g.N * g.H * g.W * g.C;
   int blocks = (int)fmin((double)ceil_div(n, 256), (double)kNumSMs * 16);
-  pool_bwd_kernel<true><<<blocks, 256, 0, s>>>(x, dy, dx, g, 0, thr, n);
+  launch_k(pool_bwd_kernel<true>, blocks, 256, 0, s, x, dy, dx, g, 0, thr, n);
   SB_LAUNCHED();
 }
 
@@ -645,6 +659,7 @@ struct FBnSum {
   __device__ __forceinline__ float2 operator()(long long r, int c) const { return make_float2(__ldg(x + r * C + c), 0.f); }
 };
 __global__ void bn_mean_kernel(const float* __restrict__ partial, float* __restrict__ mean, int chunks, int C, float rows) {
+  pdl_prologue();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) mean[c] = __fdiv_rn(finalize_partials(partial, chunks, C, c).x, rows);
 }
@@ -662,6 +677,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int chunks
                                    const float* __restrict__ beta, const float* __restrict__ mean, float* __restrict__ var_out,
                                    float* __restrict__ mov_mean, float* __restrict__ mov_var, float eps, float momentum,
                                    int fused, int bn_mode, int update_moving) {
+  pdl_prologue();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float v = __fdiv_rn(finalize_partials(partial, chunks, C, c).x, rows);  // biased
@@ -680,6 +696,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int chunks
 __global__ void bn_apply_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ var,
                                 float eps, int fused, long long n, int C) {
+  pdl_prologue();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
@@ -700,6 +717,7 @@ __global__ void __launch_bounds__(256) bn_col_reduce4_kernel(const float* __rest
                                                              const float* __restrict__ save_mean, const float* __restrict__ save_var,
                                                              float* __restrict__ partial, long long rows, int C, long long rows_per_chunk,
                                                              float frows, int quirk) {
+  pdl_prologue();
   __shared__ float4 r0s[8][33];
   __shared__ float4 r1s[8][33];
   const int c4 = blockIdx.x * 32 + threadIdx.x;
@@ -758,13 +776,14 @@ static ColChunks launch_bn_reduce4(const float* x, const float* dy, const float*
   if (want < 1) want = 1;
   const long long rpc = (rows + want - 1) / want;
   const int chunks = ceil_div(rows, rpc);
-  bn_col_reduce4_kernel<MODE><<<dim3(col_blocks, chunks), dim3(32, 8), 0, s>>>(x, dy, save_mean, save_var, ws, rows, C, rpc, (float)rows, quirk);
+  launch_k(bn_col_reduce4_kernel<MODE>, dim3(col_blocks, chunks), dim3(32, 8), 0, s, x, dy, save_mean, save_var, ws, rows, C, rpc, (float)rows, quirk);
   SB_LAUNCHED();
   return ColChunks{chunks, rpc};
 }
 __global__ void __launch_bounds__(256) bn_apply4_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, const float* __restrict__ mean,
                                                         const float* __restrict__ var, float eps, int fused, long long n4, int C4) {
+  pdl_prologue();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const int c = (int)(i % C4) * 4;
@@ -787,6 +806,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply4_kernel(const float* __restr
                                                             const float* __restrict__ gamma, const float* __restrict__ save_mean,
                                                             const float* __restrict__ save_var, const float* __restrict__ sums, float eps,
                                                             float rows, int quirk, long long n4, int C) {
+  pdl_prologue();
   const long long stride = (long long)gridDim.x * blockDim.x;
   const int C4 = C >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -818,22 +838,22 @@ void bn_fwd(const float* x, float* y, const float* gamma, const float* beta, flo
   const bool v4 = (C % 4 == 0) && ((((uintptr_t)x) | ((uintptr_t)y)) % 16 == 0);
   ColChunks cc = v4 ? launch_bn_reduce4<0>(x, nullptr, nullptr, nullptr, ws, wsf, rows, C, 0, s)
                     : launch_col_reduce(FBnSum{x, C}, ws, wsf, rows, C, s);
-  bn_mean_kernel<<<ceil_div(C, 128), 128, 0, s>>>(ws, save_mean, cc.chunks, C, (float)rows);
+  launch_k(bn_mean_kernel, ceil_div(C, 128), 128, 0, s, ws, save_mean, cc.chunks, C, (float)rows);
   SB_LAUNCHED();
   cc = v4 ? launch_bn_reduce4<1>(x, nullptr, save_mean, nullptr, ws, wsf, rows, C, 0, s)
           : launch_col_reduce(FBnSqDev2{x, save_mean, C}, ws, wsf, rows, C, s);
-  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, s>>>(ws, cc.chunks, C, (float)rows, gamma, beta, save_mean, save_var, mov_mean,
+  launch_k(bn_finalize_kernel, ceil_div(C, 128), 128, 0, s, ws, cc.chunks, C, (float)rows, gamma, beta, save_mean, save_var, mov_mean,
                                                       mov_var, eps, momentum, fused, bn_mode, update_moving);
   SB_LAUNCHED();
   long long n = rows * C;
   if (v4) {
     int blocks = (int)fmin((double)ceil_div(n / 4, 256), (double)kNumSMs * 16);
-    bn_apply4_kernel<<<blocks, 256, 0, s>>>(x, y, gamma, beta, save_mean, save_var, eps, fused, n / 4, C / 4);
+    launch_k(bn_apply4_kernel, blocks, 256, 0, s, x, y, gamma, beta, save_mean, save_var, eps, fused, n / 4, C / 4);
     SB_LAUNCHED();
     return;
   }
   int blocks = (int)fmin((double)ceil_div(n, 256), (double)kNumSMs * 16);
-  bn_apply_kernel<<<blocks, 256, 0, s>>>(x, y, gamma, beta, save_mean, save_var, eps, fused, n, C);
+  launch_k(bn_apply_kernel, blocks, 256, 0, s, x, y, gamma, beta, save_mean, save_var, eps, fused, n, C);
   SB_LAUNCHED();
 }
 
@@ -842,7 +862,7 @@ void bn_fwd_infer(const float* x, float* y, const float* gamma, const float* bet
   // `freeze` => is_training=false: normalise with the moving statistics (layer/BatchNorm.scala:126)
   long long n = rows * C;
   int blocks = (int)fmin((double)ceil_div(n, 256), (double)kNumSMs * 16);
-  bn_apply_kernel<<<blocks, 256, 0, s>>>(x, y, gamma, beta, mov_mean, mov_var, eps, fused, n, C);
+  launch_k(bn_apply_kernel, blocks, 256, 0, s, x, y, gamma, beta, mov_mean, mov_var, eps, fused, n, C);
   SB_LAUNCHED();
 }
 
@@ -867,6 +887,7 @@ struct FBnBwd {
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int chunks, int C, const float* __restrict__ save_mean,
                                        const float* __restrict__ save_var, float eps, int quirk, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, float* __restrict__ sums) {
+  pdl_prologue();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float2 sv = finalize_partials(partial, chunks, C, c);
@@ -881,6 +902,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ x, const float* __
                                     const float* __restrict__ gamma, const float* __restrict__ save_mean,
                                     const float* __restrict__ save_var, const float* __restrict__ sums, float eps, float rows,
                                     int quirk, long long n, int C) {
+  pdl_prologue();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
@@ -906,17 +928,17 @@ void bn_bwd(const float* x, const float* dy, float* dx, const float* gamma, cons
   const bool v4 = (C % 4 == 0) && ((((uintptr_t)x) | ((uintptr_t)dy) | ((uintptr_t)dx)) % 16 == 0);
   ColChunks cc = v4 ? launch_bn_reduce4<2>(x, dy, save_mean, save_var, part, wsf - 2 * (size_t)C, rows, C, quirk, s)
                     : launch_col_reduce(FBnBwd{x, dy, save_mean, save_var, C, (float)rows, quirk}, part, wsf - 2 * (size_t)C, rows, C, s);
-  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, s>>>(part, cc.chunks, C, save_mean, save_var, eps, quirk, dgamma, dbeta, sums);
+  launch_k(bn_bwd_finalize_kernel, ceil_div(C, 128), 128, 0, s, part, cc.chunks, C, save_mean, save_var, eps, quirk, dgamma, dbeta, sums);
   SB_LAUNCHED();
   if (dx && v4) {
     const long long n4 = rows * C / 4;
     int blocks = (int)fmin((double)ceil_div(n4, 256), (double)kNumSMs * 16);
-    bn_bwd_apply4_kernel<<<blocks, 256, 0, s>>>(x, dy, dx, gamma, save_mean, save_var, sums, eps, (float)rows, quirk, n4, C);
+    launch_k(bn_bwd_apply4_kernel, blocks, 256, 0, s, x, dy, dx, gamma, save_mean, save_var, sums, eps, (float)rows, quirk, n4, C);
     SB_LAUNCHED();
   } else if (dx) {
     long long n = rows * C;
     int blocks = (int)fmin((double)ceil_div(n, 256), (double)kNumSMs * 16);
-    bn_bwd_apply_kernel<<<blocks, 256, 0, s>>>(x, dy, dx, gamma, save_mean, save_var, sums, eps, (float)rows, quirk, n, C);
+    launch_k(bn_bwd_apply_kernel, blocks, 256, 0, s, x, dy, dx, gamma, save_mean, save_var, sums, eps, (float)rows, quirk, n, C);
     SB_LAUNCHED();
   }
 }
@@ -926,6 +948,7 @@ void bn_bwd(const float* x, const float* dy, float* dx, const float* gamma, cons
 // =================================================================================================
 __global__ void __launch_bounds__(1024) reg_penalty_kernel(const float* __restrict__ w, float* __restrict__ g, long long n, int kind,
                                                            float lambda, StepState* st, int first, int last) {
+  pdl_prologue();
   float acc = 0.f;
   const float gl1 = __fdiv_rn(fabsf(lambda), 2.f);
   for (long long i = threadIdx.x; i < n; i += blockDim.x) {
@@ -943,7 +966,7 @@ __global__ void __launch_bounds__(1024) reg_penalty_kernel(const float* __restri
 }
 void reg_penalty_grad(const float* w, float* g, long long n, int kind, float lambda, StepState* st, int first, int last,
                       cudaStream_t s) {
-  reg_penalty_kernel<<<1, 1024, 0, s>>>(w, g, n, kind, lambda, st, first, last);
+  launch_k(reg_penalty_kernel, 1, 1024, 0, s, w, g, n, kind, lambda, st, first, last);
   SB_LAUNCHED();
 }
 
@@ -1011,6 +1034,7 @@ __global__ void __launch_bounds__(256) optimizer_kernel(OptDesc od, float4* __re
                                                         float4* __restrict__ s0, float4* __restrict__ s1,
                                                         float4* __restrict__ s2, long long n4, StepState* st,
                                                         int advance_batch) {
+  pdl_prologue();
   OptScalars o;
   o.rate = od.rate; o.b1 = od.beta1; o.b2 = od.beta2; o.eps = od.epsilon; o.nesterov = od.nesterov;
   o.om_b1 = __fsub_rn(1.f, od.beta1);
@@ -1043,7 +1067,7 @@ void optimizer_step(const OptDesc& o, float* w, const float* g, float* s0, float
   if (blocks < 1) blocks = 1;
 #define SB_OPT(K)                                                                                             \
   case K:                                                                                                     \
-    optimizer_kernel<K><<<blocks, 256, 0, s>>>(o, (float4*)w, (const float4*)g, (float4*)s0, (float4*)s1, \
+    launch_k(optimizer_kernel<K>, blocks, 256, 0, s, o, (float4*)w, (const float4*)g, (float4*)s0, (float4*)s1, \
                                                  (float4*)s2, n4, st, advance_batch);                         \
     break;
   switch (o.kind) {
@@ -1058,6 +1082,7 @@ void optimizer_step(const OptDesc& o, float* w, const float* g, float* s0, float
 // init / utility
 // =================================================================================================
 __global__ void fill_kernel(float* __restrict__ p, float v, long long n) {
+  pdl_prologue();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) p[i] = v;
@@ -1065,6 +1090,7 @@ __global__ void fill_kernel(float* __restrict__ p, float v, long long n) {
 // Busy-wait `ns` nanoseconds on one thread.  Profiling mode enqueues it ahead of a batch of event-bracketed launches so the
 // host runs ahead of the device and the events measure kernel time, not launch gaps.
 __global__ void delay_kernel(long long ns) {
+  pdl_prologue();
   unsigned long long t0, t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   do {
@@ -1073,16 +1099,17 @@ __global__ void delay_kernel(long long ns) {
   } while ((long long)(t - t0) < ns);
 }
 void device_delay(long long ns, cudaStream_t s) {
-  delay_kernel<<<1, 1, 0, s>>>(ns);
+  launch_k(delay_kernel, 1, 1, 0, s, ns);
   SB_CUDA(cudaPeekAtLastError());
 }
 void fill_const(float* p, float v, long long n, cudaStream_t s) {
   if (n <= 0) return;
   int blocks = (int)fmin((double)ceil_div(n, 256), (double)kNumSMs * 16);
-  fill_kernel<<<blocks, 256, 0, s>>>(p, v, n);
+  launch_k(fill_kernel, blocks, 256, 0, s, p, v, n);
   SB_LAUNCHED();
 }
 __global__ void scale_kernel(float* __restrict__ p, float w, long long n) {
+  pdl_prologue();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) p[i] = __fmul_rn(p[i], w);
@@ -1090,7 +1117,7 @@ __global__ void scale_kernel(float* __restrict__ p, float w, long long n) {
 void scale_inplace(float* p, float w, long long n, cudaStream_t s) {
   if (n <= 0) return;
   int blocks = (int)fmin((double)ceil_div(n, 256), (double)kNumSMs * 16);
-  scale_kernel<<<blocks, 256, 0, s>>>(p, w, n);
+  launch_k(scale_kernel, blocks, 256, 0, s, p, w, n);
   SB_LAUNCHED();
 }
 
@@ -1114,6 +1141,7 @@ __device__ __forceinline__ float u32_to_float(unsigned int x) {
 }
 __global__ void philox_fill_kernel(float* __restrict__ p, long long n, unsigned long long seed, int normal, float scale,
                                    int has_scale, float shift, int has_shift) {
+  pdl_prologue();
   long long blk = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long nblk = (n + 3) / 4;
   if (blk >= nblk) return;
@@ -1165,7 +1193,7 @@ void philox_fill(float* p, long long n, unsigned long long seed, int normal, flo
                  int has_shift, cudaStream_t s) {
   if (n <= 0) return;
   long long nblk = (n + 3) / 4;
-  philox_fill_kernel<<<ceil_div(nblk, 256), 256, 0, s>>>(p, n, seed, normal, scale, has_scale, shift, has_shift);
+  launch_k(philox_fill_kernel, ceil_div(nblk, 256), 256, 0, s, p, n, seed, normal, scale, has_scale, shift, has_shift);
   SB_LAUNCHED();
 }
 

@@ -69,6 +69,7 @@ struct Gate4 {
   float* p[4];
 };
 __global__ void lstm_pack_kernel(Gate4 src, float* __restrict__ cat, int rows, int U) {
+  pdl_prologue();
   const long long n = (long long)rows * 4 * U;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int col = (int)(i % (4 * U)), r = (int)(i / (4 * U));
@@ -77,6 +78,7 @@ __global__ void lstm_pack_kernel(Gate4 src, float* __restrict__ cat, int rows, i
   }
 }
 __global__ void lstm_unpack_kernel(const float* __restrict__ cat, Gate4 dst, int rows, int U) {
+  pdl_prologue();
   const long long n = (long long)rows * 4 * U;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int col = (int)(i % (4 * U)), r = (int)(i / (4 * U));
@@ -86,6 +88,7 @@ __global__ void lstm_unpack_kernel(const float* __restrict__ cat, Gate4 dst, int
 }
 // [B,T,F] <-> [T,B,F]
 __global__ void lstm_transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int D0, int D1, int F) {
+  pdl_prologue();
   const long long n = (long long)D0 * D1 * F;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int f = (int)(i % F);
@@ -102,6 +105,7 @@ __global__ void __launch_bounds__(256) lstm_gates_fwd_kernel(float* __restrict__
                                                              const float* __restrict__ xw_t, const float* __restrict__ c_prev,
                                                              float* __restrict__ c_out, float* __restrict__ h_out, int B, int U,
                                                              int first, int act, int ract, int has_bias) {
+  pdl_prologue();
   const long long n = (long long)B * U;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int j = (int)(i % U);
@@ -136,6 +140,7 @@ __global__ void __launch_bounds__(256) lstm_gates_bwd_kernel(float* __restrict__
                                                              const float* __restrict__ c_prev, const float* __restrict__ dh,
                                                              float* __restrict__ dc_io, int B, int U, int first, int last, int act,
                                                              int ract) {
+  pdl_prologue();
   const long long n = (long long)B * U;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int j = (int)(i % U);
@@ -213,7 +218,7 @@ template <int FI>
 void launch_gates_fwd(LstmWs* w, float* z, const float* x_t, const float* xw_t, const float* c_prev, float* c_out, float* h_out,
                       int first, int act, int ract, int has_bias, cudaStream_t s) {
   const long long n = (long long)w->B * w->U;
-  lstm_gates_fwd_kernel<FI><<<ew_grid(n), 256, 0, s>>>(z, x_t, w->wk_cat, w->b_cat, xw_t, c_prev, c_out, h_out, w->B, w->U, first,
+  launch_k(lstm_gates_fwd_kernel<FI>, ew_grid(n), 256, 0, s, z, x_t, w->wk_cat, w->b_cat, xw_t, c_prev, c_out, h_out, w->B, w->U, first,
                                                        act, ract, has_bias);
   SB_LAUNCHED();
 }
@@ -232,15 +237,15 @@ void lstm_forward(sb_engine* e, LayerPlan& L, int) {
   const long long BU = (long long)B * U;
   const int act = L.d.activation, ract = L.d.recurrent_activation;
   // pack the per-gate tensors (the optimizer updated them since the last step)
-  lstm_pack_kernel<<<ew_grid((long long)U * 4 * U), 256, 0, s>>>(gate_ptrs(e, L, 1, false), w->wr_cat, U, U);
+  launch_k(lstm_pack_kernel, ew_grid((long long)U * 4 * U), 256, 0, s, gate_ptrs(e, L, 1, false), w->wr_cat, U, U);
   SB_LAUNCHED();
-  lstm_pack_kernel<<<ew_grid((long long)F * 4 * U), 256, 0, s>>>(gate_ptrs(e, L, 0, false), w->wk_cat, F, U);
+  launch_k(lstm_pack_kernel, ew_grid((long long)F * 4 * U), 256, 0, s, gate_ptrs(e, L, 0, false), w->wk_cat, F, U);
   SB_LAUNCHED();
   if (L.d.use_bias) {
-    lstm_pack_kernel<<<ew_grid(4LL * U), 256, 0, s>>>(gate_ptrs(e, L, 2, false), w->b_cat, 1, U);
+    launch_k(lstm_pack_kernel, ew_grid(4LL * U), 256, 0, s, gate_ptrs(e, L, 2, false), w->b_cat, 1, U);
     SB_LAUNCHED();
   }
-  lstm_transpose_kernel<<<ew_grid((long long)B * T * F), 256, 0, s>>>(e->acts[L.buf_in], w->x_tm, B, T, F);
+  launch_k(lstm_transpose_kernel, ew_grid((long long)B * T * F), 256, 0, s, e->acts[L.buf_in], w->x_tm, B, T, F);
   SB_LAUNCHED();
   if (w->xw) gemm_nn(w->x_tm, w->wk_cat, w->xw, T * B, 4 * U, F, e->ws, e->ws_floats, s);
   for (int t = 0; t < T; ++t) {
@@ -283,7 +288,7 @@ void lstm_backward(sb_engine* e, LayerPlan& L, int) {
     float* a = w->acts + (long long)t * B * 4 * U;
     const float* c_t = w->c + (long long)t * BU;
     const float* c_prev = t ? w->c + (long long)(t - 1) * BU : nullptr;
-    lstm_gates_bwd_kernel<<<ew_grid(BU), 256, 0, s>>>(a, c_t, c_prev, dh, w->dc, B, U, t == 0, t == T - 1, act, ract);
+    launch_k(lstm_gates_bwd_kernel, ew_grid(BU), 256, 0, s, a, c_t, c_prev, dh, w->dc, B, U, t == 0, t == T - 1, act, ract);
     SB_LAUNCHED();
     if (t > 0) {
       if (w->g_bwd) tc_gemm_run(w->g_bwd, t, 0, 0, s);  // dH_{t-1} = dZ_t . Wr_cat^T
@@ -295,19 +300,19 @@ void lstm_backward(sb_engine* e, LayerPlan& L, int) {
   if (w->g_dwr) tc_gemm_run(w->g_dwr, 0, 0, 0, s);
   else gemm_tn(w->h, w->acts, w->dwr_cat, U, 4 * U, T * B, e->ws, e->ws_floats, s);
   gemm_tn(w->x_tm, w->acts, w->dwk_cat, F, 4 * U, T * B, e->ws, e->ws_floats, s);
-  lstm_unpack_kernel<<<ew_grid((long long)U * 4 * U), 256, 0, s>>>(w->dwr_cat, gate_ptrs(e, L, 1, true), U, U);
+  launch_k(lstm_unpack_kernel, ew_grid((long long)U * 4 * U), 256, 0, s, w->dwr_cat, gate_ptrs(e, L, 1, true), U, U);
   SB_LAUNCHED();
-  lstm_unpack_kernel<<<ew_grid((long long)F * 4 * U), 256, 0, s>>>(w->dwk_cat, gate_ptrs(e, L, 0, true), F, U);
+  launch_k(lstm_unpack_kernel, ew_grid((long long)F * 4 * U), 256, 0, s, w->dwk_cat, gate_ptrs(e, L, 0, true), F, U);
   SB_LAUNCHED();
   if (L.d.use_bias) {
     col_sum(w->acts, w->db_cat, (long long)T * B, 4 * U, e->ws, e->ws_floats, s);
-    lstm_unpack_kernel<<<ew_grid(4LL * U), 256, 0, s>>>(w->db_cat, gate_ptrs(e, L, 2, true), 1, U);
+    launch_k(lstm_unpack_kernel, ew_grid(4LL * U), 256, 0, s, w->db_cat, gate_ptrs(e, L, 2, true), 1, U);
     SB_LAUNCHED();
   }
   float* din = e->dacts[L.buf_in];
   if (L.need_dx && din && w->dx_tm) {
     gemm_nt(w->acts, w->wk_cat, w->dx_tm, T * B, F, 4 * U, e->ws, e->ws_floats, s);  // dX_t = dZ_t . Wk_cat^T
-    lstm_transpose_kernel<<<ew_grid((long long)B * T * F), 256, 0, s>>>(w->dx_tm, din, T, B, F);
+    launch_k(lstm_transpose_kernel, ew_grid((long long)B * T * F), 256, 0, s, w->dx_tm, din, T, B, F);
     SB_LAUNCHED();
   }
 }

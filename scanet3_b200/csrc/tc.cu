@@ -123,6 +123,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // the on-chip setup above overlapped the previous kernel; global memory from here on
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -313,6 +314,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // the on-chip setup above overlapped the previous kernel; global memory from here on
   if (threadIdx.x == 0) HALO_T(1);
 
   if (warp == 0) {
@@ -516,6 +518,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // the on-chip setup above overlapped the previous kernel; global memory from here on
   const bool has_work = (int)blockIdx.x < p.n_chunks;
 
   if (warp == 0) {
@@ -660,6 +663,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // the on-chip setup above overlapped the previous kernel; global memory from here on
   const bool has_work = (int)blockIdx.x < p.n_chunks;
 
   if (warp == 0) {
@@ -745,6 +749,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
 }
 
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int n, int parts) {
+  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float acc = partial[i];
@@ -1129,11 +1134,11 @@ bool tc_conv_fwd(sb_engine* e, LayerPlan& L, int) {
   ConvTcPlan* P = (ConvTcPlan*)L.tc_plan;
   if (!P || L.tc_kind != 1) return false;
   if (P->halo_fwd) {
-    conv_halo_kernel<<<P->hfwd_grid, kIgemmThreads, P->hfwd_smem, e->stream>>>(P->map_x_h, P->map_w_fwd, P->map_y_out, P->hfwd);
+    launch_k(conv_halo_kernel, P->hfwd_grid, kIgemmThreads, P->hfwd_smem, e->stream, P->map_x_h, P->map_w_fwd, P->map_y_out, P->hfwd);
     SB_LAUNCHED();
     return true;
   }
-  conv_igemm_kernel<<<P->fwd_grid, kIgemmThreads, P->fwd_smem, e->stream>>>(P->map_x_fwd, P->map_w_fwd, P->fwd);
+  launch_k(conv_igemm_kernel, P->fwd_grid, kIgemmThreads, P->fwd_smem, e->stream, P->map_x_fwd, P->map_w_fwd, P->fwd);
   SB_LAUNCHED();
   return true;
 }
@@ -1144,13 +1149,13 @@ bool tc_conv_wgrad(sb_engine* e, LayerPlan& L, int) {
   const ConvGeom& g = L.cg;
   const int n = g.KH * g.KW * g.Cin * g.Cout;
   if (P->halo_wg) {
-    conv_wgrad_halo_kernel<<<P->hwg_grid, kWgradThreads, P->hwg_smem, e->stream>>>(P->map_dy_hwg, P->map_x_hwg, P->hwg);
+    launch_k(conv_wgrad_halo_kernel, P->hwg_grid, kWgradThreads, P->hwg_smem, e->stream, P->map_dy_hwg, P->map_x_hwg, P->hwg);
     SB_LAUNCHED();
     partial_reduce(P->wg_partial, e->grads + e->params[L.p_w].offset, n, P->hwg_grid, e->stream);
     return true;
   }
   for (size_t i = 0; i < P->wg_list.size(); ++i) {
-    conv_wgrad_kernel<<<P->wg_grid, kWgradThreads, P->wg_smem_list[i], e->stream>>>(P->map_dy_wg, P->map_x_wg, P->wg_list[i]);
+    launch_k(conv_wgrad_kernel, P->wg_grid, kWgradThreads, P->wg_smem_list[i], e->stream, P->map_dy_wg, P->map_x_wg, P->wg_list[i]);
     SB_LAUNCHED();
   }
   partial_reduce(P->wg_partial, e->grads + e->params[L.p_w].offset, n, P->wg_grid, e->stream);  // fixed order, 8-way parallel
@@ -1161,11 +1166,11 @@ bool tc_conv_dgrad(sb_engine* e, LayerPlan& L, int) {
   ConvTcPlan* P = (ConvTcPlan*)L.tc_plan;
   if (!P || L.tc_kind != 1 || !P->has_dgrad) return false;
   if (P->halo_dg) {
-    conv_halo_kernel<<<P->hdg_grid, kIgemmThreads, P->hdg_smem, e->stream>>>(P->map_dy_h, P->map_w_dg, P->map_dx_out, P->hdg);
+    launch_k(conv_halo_kernel, P->hdg_grid, kIgemmThreads, P->hdg_smem, e->stream, P->map_dy_h, P->map_w_dg, P->map_dx_out, P->hdg);
     SB_LAUNCHED();
     return true;
   }
-  conv_igemm_kernel<<<P->dg_grid, kIgemmThreads, P->dg_smem, e->stream>>>(P->map_dy_dg, P->map_w_dg, P->dg);
+  launch_k(conv_igemm_kernel, P->dg_grid, kIgemmThreads, P->dg_smem, e->stream, P->map_dy_dg, P->map_w_dg, P->dg);
   SB_LAUNCHED();
   return true;
 }

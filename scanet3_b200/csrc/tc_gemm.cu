@@ -133,6 +133,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // the on-chip setup above overlapped the previous kernel; global memory from here on
 
   if (warp >= 6) {
     // ================= 3xTF32 converters: lo = x - tf32(x) for every word of the stage's A and B tiles =================
@@ -429,7 +430,7 @@ bool tc_gemm_is_split(const TcGemm* g) { return g->p.splits > 1; }
 void tc_gemm_run(TcGemm* g, int za, int zb, int zc, cudaStream_t s) {
   GemmParams p = g->p;
   p.za = za; p.zb = zb; p.zc = p.splits > 1 ? 0 : zc;
-  gemm_tf32_kernel<<<g->grid, p.x3 ? kGemmThreadsX3 : kGemmThreads, g->smem, s>>>(g->map_a, g->map_b, g->map_c, p);
+  launch_k(gemm_tf32_kernel, g->grid, p.x3 ? kGemmThreadsX3 : kGemmThreads, g->smem, s, g->map_a, g->map_b, g->map_c, p);
   SB_LAUNCHED();
   if (p.splits > 1) partial_reduce(g->partial, g->c + (long long)zc * g->c_slice, p.M * p.N, p.splits, s);
 }
