@@ -428,3 +428,46 @@ def test_device_truncated_normal_initializers():  # models/InitializerSpec.scala
         assert np.max(np.abs(got)) < 2.0 * np.max(np.abs(want)) + 1.0
         np.testing.assert_allclose(got, want, rtol=0, atol=3e-6)  # same accepted samples; libm vs CUDA sincos/log at the ulp level
         e.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# geometry sweep of the vectorised / fused kernels (strip max-pool, small-K conv, skinny head, fused bias+activation backward):
+# ragged widths, single rows/columns, channel counts that fall back to the generic kernels, batch 1 and batch > 128
+# ---------------------------------------------------------------------------------------------------------------
+GEOMETRIES = [
+    # (id, spec, batch, in_shape, classes)
+    ("pool_w2_c4", [("conv", 4, "relu", (3, 3), (1, 1), "Valid", False), ("pool", (2, 2), (1, 1), "Valid"), ("flatten",),
+                    ("dense", 3, "softmax")], 2, (4, 4, 1), 3),
+    ("pool_odd_c12", [("conv", 12, "relu", (3, 3), (1, 1), "Valid", False), ("pool", (2, 2), (1, 1), "Valid"), ("flatten",),
+                      ("dense", 10, "softmax")], 3, (9, 13, 3), 10),
+    ("pool_c6_fallback", [("conv", 6, "relu", (3, 3), (1, 1), "Valid", False), ("pool", (2, 2), (1, 1), "Valid"), ("flatten",),
+                          ("dense", 10, "softmax")], 3, (7, 8, 1), 10),
+    ("pool_3x3_s2_same", [("conv", 8, "tanh", (3, 3), (1, 1), "Same", False), ("pool", (3, 3), (2, 2), "Same"), ("flatten",),
+                          ("dense", 10, "softmax")], 2, (9, 7, 3), 10),
+    ("conv5x5_same", [("conv", 16, "relu", (5, 5), (1, 1), "Same", False), ("pool", (2, 2), (1, 1), "Valid"), ("flatten",),
+                      ("dense", 10, "softmax")], 2, (8, 9, 1), 10),
+    ("conv_strided_smallk", [("conv", 8, "sigmoid", (3, 3), (2, 2), "Valid", True), ("flatten",), ("dense", 10, "softmax")], 3,
+     (11, 9, 3), 10),
+    ("head_k2048_n16", [("dense", 2048, "tanh"), ("dense", 16, "softmax")], 5, (40,), 16),
+    ("head_batch130", [("dense", 512, "sigmoid"), ("dense", 10, "softmax")], 130, (24,), 10),
+    ("head_batch1_n3", [("dense", 1024, "tanh"), ("dense", 3, "softmax")], 1, (8,), 3),
+    ("head_k_not_mult4_fallback", [("dense", 1026, "tanh"), ("dense", 10, "softmax")], 4, (8,), 10),
+    ("bias_act_c6_fallback", [("dense", 6, "relu"), ("dense", 10, "softmax")], 9, (5,), 10),
+]
+
+
+@pytest.mark.parametrize("gid,spec,batch,in_shape,classes", GEOMETRIES, ids=[g[0] for g in GEOMETRIES])
+def test_fast_kernel_geometries_match_the_oracle(gid, spec, batch, in_shape, classes):
+    om, sm = build_models(spec)
+    x, y = synth_classification(batch, in_shape, classes, 77)
+    x = (x - 0.5).astype(f32)  # both signs: ReLU masks and max-pool ties are exercised
+    e = make_engine(sm, S.CategoricalCrossentropy, S.Adam(0.001), batch, in_shape, (classes,))
+    e.init_params()
+    _, mp, _ = oracle_init(om, O.Adam(0.001), (batch,) + tuple(in_shape))
+    ol, og, _ = O.LossModel(om, O.CategoricalCrossentropy).grad_stateful(x, y, mp)
+    gl, gg = e.compute_grads(x, y)
+    assert abs(gl - float(ol)) <= 2e-5 * abs(float(ol)) + 1e-7
+    for k, v in og.items():
+        np.testing.assert_allclose(gg[k], v, rtol=2e-4, atol=2e-6, err_msg=k)
+    np.testing.assert_allclose(e.predict(x), O.model_forward(om, x, mp)[0], rtol=2e-5, atol=2e-6)
+    e.close()
