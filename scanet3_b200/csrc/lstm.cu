@@ -5,7 +5,8 @@
 // g = activation ; c_t = c_{t-1} * f + i * g ; h_t = o * act(c_t) ; the layer output is h_{T-1}.
 //
 // Device layout.  The per-gate tensors keep the reference's paths in the arena; every step starts by packing them into
-//   Wr_cat[U, 4U], Wk_cat[F, 4U], b_cat[4U]   (column block G*U.. of gate G; 1 MB at U = 256)
+//   Wr_cat[U, 4U], Wk_cat[F, 4U], b_cat[4U]   (column 4*j + G = gate G of unit j: the four gates of a unit are adjacent, so a
+//   thread that owns 4k consecutive columns of a GEMM row owns k whole units; 1 MB at U = 256)
 // so that one GEMM per time step produces all four gates:  Z_t[B,4U] = H_{t-1}[B,U] . Wr_cat.  The gate kernel adds the input
 // projection (inline for F <= 8, from a pre-computed X . Wk_cat otherwise) and the bias, applies the activations IN PLACE
 // (Z_t becomes the saved gate activations) and writes c_t, h_t.  Saved for BPTT: acts[T,B,4U], c[T,B,U], h[T,B,U].
@@ -39,6 +40,7 @@ struct LstmWs {
   float* dwr_cat = nullptr;  // [U, 4U]
   float* dwk_cat = nullptr;  // [F, 4U]
   float* db_cat = nullptr;   // [4U]
+  float* dwkb_cat = nullptr; // [1 + F][4U]: db_cat row followed by dWk_cat rows (F <= 8: one fused pass)
   float* dx_tm = nullptr;    // [T, B, F] (only when the input gradient is needed)
   // tcgen05 TF32 plans (SB_PREC_TF32): one plan per contraction serves every time step through the tensor maps' slice coordinate
   TcGemm* g_fwd = nullptr;   // Z_t = H_{t-1} . Wr_cat           A slice t of h, C slice t of acts
@@ -73,7 +75,7 @@ __global__ void lstm_pack_kernel(Gate4 src, float* __restrict__ cat, int rows, i
   const long long n = (long long)rows * 4 * U;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int col = (int)(i % (4 * U)), r = (int)(i / (4 * U));
-    const int g = col / U, j = col - g * U;
+    const int j = col >> 2, g = col & 3;
     cat[i] = src.p[g] ? src.p[g][(long long)r * U + j] : 0.f;
   }
 }
@@ -82,7 +84,7 @@ __global__ void lstm_unpack_kernel(const float* __restrict__ cat, Gate4 dst, int
   const long long n = (long long)rows * 4 * U;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int col = (int)(i % (4 * U)), r = (int)(i / (4 * U));
-    const int g = col / U, j = col - g * U;
+    const int j = col >> 2, g = col & 3;
     if (dst.p[g]) dst.p[g][(long long)r * U + j] = cat[i];
   }
 }
@@ -111,9 +113,12 @@ __global__ void __launch_bounds__(256) lstm_gates_fwd_kernel(float* __restrict__
     const int j = (int)(i % U);
     const long long b = i / U;
     float a[4];
+    float4* zq = reinterpret_cast<float4*>(z + b * 4 * U + 4 * j);  // the unit's four gates are adjacent
+    const float4 zr = first ? make_float4(0.f, 0.f, 0.f, 0.f) : *zq;
+    const float zin[4] = {zr.x, zr.y, zr.z, zr.w};
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      const int col = g * U + j;
+      const int col = 4 * j + g;
       float xp;
       if (FI > 0) {
         xp = 0.f;
@@ -122,11 +127,11 @@ __global__ void __launch_bounds__(256) lstm_gates_fwd_kernel(float* __restrict__
       } else {
         xp = xw_t[b * 4 * U + col];
       }
-      float v = first ? xp : __fadd_rn(xp, z[b * 4 * U + col]);  // (x.Wk + h.Wr)
-      if (has_bias) v = __fadd_rn(v, __ldg(b_cat + col));          // + b
+      float v = first ? xp : __fadd_rn(xp, zin[g]);           // (x.Wk + h.Wr)
+      if (has_bias) v = __fadd_rn(v, __ldg(b_cat + col));       // + b
       a[g] = actf(v, g == 2 ? act : ract);
-      z[b * 4 * U + col] = a[g];
     }
+    *zq = make_float4(a[0], a[1], a[2], a[3]);
     const float cp = first ? 0.f : c_prev[i];
     const float c = __fadd_rn(__fmul_rn(cp, a[0]), __fmul_rn(a[1], a[2]));  // c_prev*f + i*g
     c_out[i] = c;
@@ -145,20 +150,78 @@ __global__ void __launch_bounds__(256) lstm_gates_bwd_kernel(float* __restrict__
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int j = (int)(i % U);
     const long long b = i / U;
-    float* row = acts_dz + b * 4 * U;
-    const float f = row[j], ig = row[U + j], g = row[2 * U + j], o = row[3 * U + j];
+    float4* q = reinterpret_cast<float4*>(acts_dz + b * 4 * U + 4 * j);
+    const float4 a4 = *q;
+    const float f = a4.x, ig = a4.y, g = a4.z, o = a4.w;
     const float ac = actf(c_t[i], act);
     const float dhv = dh[i];
     const float d_o = __fmul_rn(dhv, ac);
     float dc = actg(__fmul_rn(dhv, o), ac, act);
     if (!last) dc = __fadd_rn(dc, dc_io[i]);
     const float cp = first ? 0.f : c_prev[i];
-    row[j] = actg(__fmul_rn(dc, cp), f, ract);
-    row[U + j] = actg(__fmul_rn(dc, g), ig, ract);
-    row[2 * U + j] = actg(__fmul_rn(dc, ig), g, act);
-    row[3 * U + j] = actg(d_o, o, ract);
+    *q = make_float4(actg(__fmul_rn(dc, cp), f, ract), actg(__fmul_rn(dc, g), ig, ract), actg(__fmul_rn(dc, ig), g, act),
+                     actg(d_o, o, ract));
     dc_io[i] = __fmul_rn(dc, f);
   }
+}
+
+
+// Bias and input-kernel gradients in ONE pass over dZ_all[R, 4U] (R = T*B):  db[c] = sum_r dZ[r][c] ;  dWk[f][c] = sum_r X[r][f] dZ[r][c]
+// (F <= 8 input features: the "GEMM" has M = F rows, i.e. it is a weighted column sum).  Block = 32 column quads x 8 row lanes
+// over a chunk of rows; partial[chunk][1 + F][4U], summed in chunk order by partial_reduce.
+template <int FI>
+__global__ void __launch_bounds__(256) lstm_dwk_db_kernel(const float* __restrict__ dz, const float* __restrict__ x, float* __restrict__ partial,
+                                                          long long rows, int C, long long rows_per_chunk) {
+  pdl_prologue();
+  __shared__ float4 red[8][33];
+  const int c4 = blockIdx.x * 32 + threadIdx.x;
+  const bool ok = c4 * 4 < C;
+  const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+  const long long r1 = r0 + rows_per_chunk < rows ? r0 + rows_per_chunk : rows;
+  float4 acc[FI + 1];
+#pragma unroll
+  for (int f = 0; f <= FI; ++f) acc[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ok) {
+#pragma unroll 2
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(dz + r * C + c4 * 4));
+      acc[0].x = __fadd_rn(acc[0].x, g.x); acc[0].y = __fadd_rn(acc[0].y, g.y); acc[0].z = __fadd_rn(acc[0].z, g.z); acc[0].w = __fadd_rn(acc[0].w, g.w);
+#pragma unroll
+      for (int f = 0; f < FI; ++f) {
+        const float xv = __ldg(x + r * FI + f);
+        acc[f + 1].x = fmaf(xv, g.x, acc[f + 1].x); acc[f + 1].y = fmaf(xv, g.y, acc[f + 1].y);
+        acc[f + 1].z = fmaf(xv, g.z, acc[f + 1].z); acc[f + 1].w = fmaf(xv, g.w, acc[f + 1].w);
+      }
+    }
+  }
+#pragma unroll
+  for (int f = 0; f <= FI; ++f) {
+    red[threadIdx.y][threadIdx.x] = acc[f];
+    __syncthreads();
+    if (threadIdx.y == 0 && ok) {
+      float4 t = red[0][threadIdx.x];
+      for (int j = 1; j < 8; ++j) {
+        const float4 v = red[j][threadIdx.x];
+        t.x = __fadd_rn(t.x, v.x); t.y = __fadd_rn(t.y, v.y); t.z = __fadd_rn(t.z, v.z); t.w = __fadd_rn(t.w, v.w);
+      }
+      *reinterpret_cast<float4*>(partial + ((long long)blockIdx.y * (FI + 1) + f) * C + c4 * 4) = t;
+    }
+    __syncthreads();
+  }
+}
+template <int FI>
+bool launch_dwk_db(const float* dz, const float* x, float* out, long long rows, int C, float* ws, size_t ws_floats, cudaStream_t s) {
+  const int col_blocks = (C / 4 + 31) / 32;
+  long long chunks = (4LL * kNumSMs + col_blocks - 1) / col_blocks;
+  if (chunks > (rows + 31) / 32) chunks = (rows + 31) / 32;
+  if (chunks > (long long)(ws_floats / ((size_t)(FI + 1) * C))) chunks = (long long)(ws_floats / ((size_t)(FI + 1) * C));
+  if (chunks < 1) return false;
+  const long long rpc = (rows + chunks - 1) / chunks;
+  chunks = (rows + rpc - 1) / rpc;
+  launch_k(lstm_dwk_db_kernel<FI>, dim3(col_blocks, (unsigned)chunks), dim3(32, 8), 0, s, dz, x, ws, rows, C, rpc);
+  SB_LAUNCHED();
+  partial_reduce(ws, out, (FI + 1) * C, (int)chunks, s);
+  return true;
 }
 
 int ew_grid(long long n) {
@@ -193,6 +256,7 @@ LstmWs* ws_of(sb_engine* e, LayerPlan& L) {
   w->dwr_cat = dalloc(U * 4 * U);
   w->dwk_cat = dalloc(F * 4 * U);
   w->db_cat = dalloc(4 * U);
+  if (F <= 8) w->dwkb_cat = dalloc((F + 1) * 4 * U);
   if (L.need_dx) w->dx_tm = dalloc(T * B * F);
   if (e->train.precision != SB_PREC_FP32 && B * U * 4 * U >= (1 << 22)) {
     const int x3 = e->train.precision == SB_PREC_3XTF32 ? 1 : 0;
@@ -299,14 +363,31 @@ void lstm_backward(sb_engine* e, LayerPlan& L, int) {
   // weight gradients over the whole sequence (acts now holds dZ_all[T*B, 4U]; h slots 0..T-1 are H_prev_all[T*B, U])
   if (w->g_dwr) tc_gemm_run(w->g_dwr, 0, 0, 0, s);
   else gemm_tn(w->h, w->acts, w->dwr_cat, U, 4 * U, T * B, e->ws, e->ws_floats, s);
-  gemm_tn(w->x_tm, w->acts, w->dwk_cat, F, 4 * U, T * B, e->ws, e->ws_floats, s);
+  bool fused_kb = false;
+  if (w->dwkb_cat) {  // db and dWk in one pass over dZ_all
+    const long long R = (long long)T * B;
+    switch (F) {
+      case 1: fused_kb = launch_dwk_db<1>(w->acts, w->x_tm, w->dwkb_cat, R, 4 * U, e->ws, e->ws_floats, s); break;
+      case 2: fused_kb = launch_dwk_db<2>(w->acts, w->x_tm, w->dwkb_cat, R, 4 * U, e->ws, e->ws_floats, s); break;
+      case 3: fused_kb = launch_dwk_db<3>(w->acts, w->x_tm, w->dwkb_cat, R, 4 * U, e->ws, e->ws_floats, s); break;
+      case 4: fused_kb = launch_dwk_db<4>(w->acts, w->x_tm, w->dwkb_cat, R, 4 * U, e->ws, e->ws_floats, s); break;
+      case 5: fused_kb = launch_dwk_db<5>(w->acts, w->x_tm, w->dwkb_cat, R, 4 * U, e->ws, e->ws_floats, s); break;
+      case 6: fused_kb = launch_dwk_db<6>(w->acts, w->x_tm, w->dwkb_cat, R, 4 * U, e->ws, e->ws_floats, s); break;
+      case 7: fused_kb = launch_dwk_db<7>(w->acts, w->x_tm, w->dwkb_cat, R, 4 * U, e->ws, e->ws_floats, s); break;
+      case 8: fused_kb = launch_dwk_db<8>(w->acts, w->x_tm, w->dwkb_cat, R, 4 * U, e->ws, e->ws_floats, s); break;
+      default: break;
+    }
+  }
+  const float* dwk_src = fused_kb ? w->dwkb_cat + 4 * U : w->dwk_cat;
+  const float* db_src = fused_kb ? w->dwkb_cat : w->db_cat;
+  if (!fused_kb) gemm_tn(w->x_tm, w->acts, w->dwk_cat, F, 4 * U, T * B, e->ws, e->ws_floats, s);
   launch_k(lstm_unpack_kernel, ew_grid((long long)U * 4 * U), 256, 0, s, w->dwr_cat, gate_ptrs(e, L, 1, true), U, U);
   SB_LAUNCHED();
-  launch_k(lstm_unpack_kernel, ew_grid((long long)F * 4 * U), 256, 0, s, w->dwk_cat, gate_ptrs(e, L, 0, true), F, U);
+  launch_k(lstm_unpack_kernel, ew_grid((long long)F * 4 * U), 256, 0, s, dwk_src, gate_ptrs(e, L, 0, true), F, U);
   SB_LAUNCHED();
   if (L.d.use_bias) {
-    col_sum(w->acts, w->db_cat, (long long)T * B, 4 * U, e->ws, e->ws_floats, s);
-    launch_k(lstm_unpack_kernel, ew_grid(4LL * U), 256, 0, s, w->db_cat, gate_ptrs(e, L, 2, true), 1, U);
+    if (!fused_kb) col_sum(w->acts, w->db_cat, (long long)T * B, 4 * U, e->ws, e->ws_floats, s);
+    launch_k(lstm_unpack_kernel, ew_grid(4LL * U), 256, 0, s, db_src, gate_ptrs(e, L, 2, true), 1, U);
     SB_LAUNCHED();
   }
   float* din = e->dacts[L.buf_in];
@@ -322,7 +403,7 @@ void lstm_free(sb_engine* e) {
     if (!L.lstm) continue;
     LstmWs* w = (LstmWs*)L.lstm;
     for (float* p : {w->wr_cat, w->wk_cat, w->b_cat, w->x_tm, w->acts, w->c, w->h, w->xw, w->dh, w->dc, w->dwr_cat, w->dwk_cat,
-                     w->db_cat, w->dx_tm})
+                     w->db_cat, w->dwkb_cat, w->dx_tm})
       cudaFree(p);
     tc_gemm_destroy(w->g_fwd); tc_gemm_destroy(w->g_bwd); tc_gemm_destroy(w->g_dwr);
     delete w;
