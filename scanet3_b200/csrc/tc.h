@@ -26,6 +26,23 @@ TcGemm* tc_gemm_create(int a_mn_major, int b_mn_major, const float* A, int a_sli
 void tc_gemm_set_epilogue(TcGemm* g, const float* bias, int act, float thr);
 bool tc_gemm_is_split(const TcGemm* g);
 void tc_gemm_run(TcGemm* g, int za, int zb, int zc, cudaStream_t s);
+// LSTM pointwise work fused into the GEMM epilogue (columns are unit-interleaved: col = 4*unit + gate, csrc/lstm.cu):
+//  mode 1 (forward, C = Z_t = H_{t-1}.Wr_cat): z += x_t.Wk_cat + b ; activations written to C in place of z ; c_t, h_t stored
+//  mode 2 (backward, C = dH_{t-1} = dZ_t.Wr_cat^T, not stored): the gate backward of step t-1 -> dZ_{t-1} in place of acts_{t-1}
+struct LstmEpi {
+  int mode;
+  int F, U, act, ract, has_bias;
+  const float* x_t;     // [B, F]   (mode 1)
+  const float* wk_cat;  // [F, 4U]
+  const float* b_cat;   // [4U]
+  const float* c_prev;  // [B, U]   mode 1: c_{t-1} ; mode 2: c_{t-2} (null when step t-1 is the first)
+  float* c_out;         // [B, U]   mode 1: c_t
+  float* h_out;         // [B, U]   mode 1: h_t
+  float* acts_dz;       // [B, 4U]  mode 2: acts_{t-1} in, dZ_{t-1} out
+  const float* c_cur;   // [B, U]   mode 2: c_{t-1}
+  float* dc_io;         // [B, U]   mode 2: dc_t in, dc_{t-1} out
+};
+void tc_gemm_run_lstm(TcGemm* g, int za, int zb, int zc, const LstmEpi& epi, cudaStream_t s);
 void tc_gemm_destroy(TcGemm* g);
 
 void lstm_plan(sb_engine* e);

@@ -38,6 +38,7 @@ struct GemmParams {
   int act;  // sb_activation applied in the epilogue (0 none, 1 sigmoid, 2 tanh, 4 relu)
   float thr;
   const float* bias;  // [N] or null
+  LstmEpi le;         // le.mode != 0: LSTM gate math in the epilogue (tc.h)
 };
 
 constexpr int kGemmThreads = 192;       // producer, MMA issuer, 4 epilogue warps
@@ -89,6 +90,69 @@ __device__ __forceinline__ void tile_to_mn(int tile, int m_tiles, int n_tiles, i
   const int gm = min(kGroupM, m_tiles - grp * kGroupM);  // rows in this (possibly last, shorter) group
   nt = in / gm;
   mt = grp * kGroupM + (in - nt * gm);
+}
+
+// ---- LSTM epilogues (layer/RNN.scala:319-339; the same arithmetic as lstm_gates_fwd/bwd_kernel in lstm.cu) ----
+__device__ __forceinline__ float lstm_actf(float x, int act) {
+  switch (act) {
+    case 1: return __fdiv_rn(1.f, __fadd_rn(1.f, expf(-x)));
+    case 2: return tanhf(x);
+    case 4: return fmaxf(0.f, x);
+    default: return x;
+  }
+}
+__device__ __forceinline__ float lstm_actg(float g, float y, int act) {
+  switch (act) {
+    case 1: return __fmul_rn(__fmul_rn(y, __fsub_rn(1.f, y)), g);
+    case 2: return __fmul_rn(__fsub_rn(1.f, __fmul_rn(y, y)), g);
+    case 4: return y > 0.f ? g : 0.f;
+    default: return g;
+  }
+}
+// v[32] = z of row b, columns col0..col0+31 = units col0/4 .. col0/4+7 (4 gates each): becomes the activations
+__device__ __forceinline__ void lstm_epi_fwd(float* v, long long b, int col0, const LstmEpi& le) {
+  const int j0 = col0 >> 2;
+  float cp[8], cn[8], hn[8];
+  *reinterpret_cast<float4*>(cp) = *reinterpret_cast<const float4*>(le.c_prev + b * le.U + j0);
+  *reinterpret_cast<float4*>(cp + 4) = *reinterpret_cast<const float4*>(le.c_prev + b * le.U + j0 + 4);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    float a[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int col = col0 + 4 * u + g;
+      float xp = 0.f;
+      for (int f = 0; f < le.F; ++f) xp = fmaf(__ldg(le.x_t + b * le.F + f), __ldg(le.wk_cat + (long long)f * 4 * le.U + col), xp);
+      float z = __fadd_rn(xp, v[4 * u + g]);                    // (x.Wk + h.Wr)
+      if (le.has_bias) z = __fadd_rn(z, __ldg(le.b_cat + col));  // + b
+      a[g] = lstm_actf(z, g == 2 ? le.act : le.ract);
+      v[4 * u + g] = a[g];
+    }
+    cn[u] = __fadd_rn(__fmul_rn(cp[u], a[0]), __fmul_rn(a[1], a[2]));  // c_prev*f + i*g
+    hn[u] = __fmul_rn(a[3], lstm_actf(cn[u], le.act));                   // o * act(c)
+  }
+  *reinterpret_cast<float4*>(le.c_out + b * le.U + j0) = *reinterpret_cast<float4*>(cn);
+  *reinterpret_cast<float4*>(le.c_out + b * le.U + j0 + 4) = *reinterpret_cast<float4*>(cn + 4);
+  *reinterpret_cast<float4*>(le.h_out + b * le.U + j0) = *reinterpret_cast<float4*>(hn);
+  *reinterpret_cast<float4*>(le.h_out + b * le.U + j0 + 4) = *reinterpret_cast<float4*>(hn + 4);
+}
+// v[32] = dH_{t-1} of row b, units j0..j0+31: gate backward of step t-1 (oracle/layers.py LSTMCell.step_bwd)
+__device__ __forceinline__ void lstm_epi_bwd(const float* v, long long b, int j0, const LstmEpi& le) {
+#pragma unroll 4
+  for (int u = 0; u < 32; ++u) {
+    const long long i = b * le.U + j0 + u;
+    float4* q = reinterpret_cast<float4*>(le.acts_dz + b * 4 * le.U + 4 * (j0 + u));
+    const float4 a4 = *q;
+    const float f = a4.x, ig = a4.y, g = a4.z, o = a4.w;
+    const float ac = lstm_actf(le.c_cur[i], le.act);
+    const float dhv = v[u];
+    const float d_o = __fmul_rn(dhv, ac);
+    const float dc = __fadd_rn(lstm_actg(__fmul_rn(dhv, o), ac, le.act), le.dc_io[i]);
+    const float cp = le.c_prev ? le.c_prev[i] : 0.f;
+    *q = make_float4(lstm_actg(__fmul_rn(dc, cp), f, le.ract), lstm_actg(__fmul_rn(dc, g), ig, le.ract),
+                     lstm_actg(__fmul_rn(dc, ig), g, le.act), lstm_actg(d_o, o, le.ract));
+    le.dc_io[i] = __fmul_rn(dc, f);
+  }
 }
 
 __global__ void __launch_bounds__(kGemmThreadsX3, 1)
@@ -264,7 +328,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * p.BN + c0), v);
         tmem_ld_wait();
+        if (p.le.mode == 2) {  // LSTM backward: dH is consumed here, nothing is stored
+          if (n0 + c0 < p.N && m0 + lane < p.M) lstm_epi_bwd(v, m0 + lane, n0 + c0, p.le);
+          continue;
+        }
         if (n0 + c0 < p.N) {  // whole 32-column chunks beyond N are skipped (the store would be clipped anyway)
+          if (p.le.mode == 1 && m0 + lane < p.M) lstm_epi_fwd(v, m0 + lane, n0 + c0, p.le);
           if (p.bias) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __fadd_rn(v[j], (n0 + c0 + j < p.N) ? __ldg(p.bias + n0 + c0 + j) : 0.f);
@@ -433,6 +502,17 @@ void tc_gemm_run(TcGemm* g, int za, int zb, int zc, cudaStream_t s) {
   launch_k(gemm_tf32_kernel, g->grid, p.x3 ? kGemmThreadsX3 : kGemmThreads, g->smem, s, g->map_a, g->map_b, g->map_c, p);
   SB_LAUNCHED();
   if (p.splits > 1) partial_reduce(g->partial, g->c + (long long)zc * g->c_slice, p.M * p.N, p.splits, s);
+}
+
+void tc_gemm_run_lstm(TcGemm* g, int za, int zb, int zc, const LstmEpi& epi, cudaStream_t s) {
+  if (g->p.splits > 1) throw std::runtime_error("LSTM epilogue is not available with split-K");
+  if (epi.mode == 1 && (g->p.N != 4 * epi.U || (epi.U & 7))) throw std::runtime_error("LSTM forward epilogue: N must be 4U, U % 8 == 0");
+  if (epi.mode == 2 && (g->p.N != epi.U || (epi.U & 31))) throw std::runtime_error("LSTM backward epilogue: N must be U, U % 32 == 0");
+  GemmParams p = g->p;
+  p.za = za; p.zb = zb; p.zc = zc;
+  p.le = epi;
+  launch_k(gemm_tf32_kernel, g->grid, p.x3 ? kGemmThreadsX3 : kGemmThreads, g->smem, s, g->map_a, g->map_b, g->map_c, p);
+  SB_LAUNCHED();
 }
 
 void tc_gemm_destroy(TcGemm* g) { delete g; }

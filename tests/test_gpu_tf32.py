@@ -201,24 +201,32 @@ def test_tf32_wide_mlp_trajectory_config4_pattern():  # BASELINE config 4 patter
     e.close()
 
 
-def test_tf32_lstm_matches_fp32_engine():
+@pytest.mark.parametrize("f,fused", [(1, "0"), (3, "0"), (1, "1"), (3, "1")])
+def test_tf32_lstm_matches_fp32_engine(f, fused, monkeypatch):
+    # fused = "1": gate math inside the tcgen05 GEMM epilogues (forward and backward; an option, see csrc/lstm.cu)
+    monkeypatch.setenv("SB_LSTM_FUSED_EPILOGUE", fused)
     spec = [("lstm", 64), ("dense", 1, "tanh")]
     om, sm = build_models(spec)
-    batch, t, f = 256, 12, 1
+    batch, t = 256, 12
     rng = np.random.Generator(np.random.PCG64(8))
     x = rng.uniform(0, 1, size=(batch, t, f)).astype(f32)
     y = rng.uniform(0, 1, size=(batch, 1)).astype(f32)
     res = []
-    for prec in (S.PREC_FP32, S.PREC_TF32):
+    for prec in (S.PREC_FP32, S.PREC_TF32, S.PREC_3XTF32):
         e = S.Engine(sm, S.MeanSquaredError, S.Adam(1e-3), batch, (t, f), (1,), device=0, precision=prec)
         e.init_params()
         res.append((e.predict(x),) + e.compute_grads(x, y))
         e.close()
-    (p32, l32, g32), (ptc, ltc, gtc) = res
+    (p32, l32, g32), (ptc, ltc, gtc), (p3x, l3x, g3x) = res
     assert rel_to_max(ptc, p32) < 4e-3
     assert abs(ltc - l32) <= 4e-3 * abs(l32)
     for k in g32:
         assert rel_to_max(gtc[k], g32[k]) < 1e-2, k
+    # 3xTF32 holds fp32 tolerance through the 12-step recurrence
+    assert rel_to_max(p3x, p32) < 2e-5
+    assert abs(l3x - l32) <= 1e-5 * abs(l32)
+    for k in g32:
+        assert rel_to_max(g3x[k], g32[k]) < 1e-4, k
 
 
 # ---------------------------------------------------------------------------------------------------------------
