@@ -396,3 +396,29 @@ def test_sgd_minimises_x_squared():  # SGDSpec.scala:16-31 with models/Math.scal
         delta, st = alg.build(f32(2) * w, st, t)
         w = w - delta
     assert float(w * w) <= 0.1
+
+
+# ---- the timed CPU baseline of bench.py is a torch-CPU port of the cfg2 step: pin it against the NumPy oracle ----
+def test_torch_port_matches_numpy_oracle():
+    torch = pytest.importorskip("torch")
+    from oracle.torch_port import TorchLeNetPort
+    om = (O.Conv2D(32, activation=O.ReLU(), kernel_initializer=O.GlorotUniform(1)) >> O.Pool2D()
+          >> O.Conv2D(64, activation=O.ReLU(), kernel_initializer=O.GlorotUniform(1)) >> O.Pool2D() >> O.Flatten
+          >> O.Dense(10, O.Softmax, kernel_initializer=O.GlorotUniform(1)))
+    alg = O.Adam(0.001)
+    batch = 20
+    _, mp, op = O.init_params(om, alg, (batch, 28, 28, 1))
+    lm = O.LossModel(om, O.CategoricalCrossentropy)
+    rng = np.random.Generator(np.random.PCG64(5))
+    x = rng.uniform(1 / 256, 1.0, size=(3 * batch, 28, 28, 1)).astype(f32)
+    y = np.zeros((3 * batch, 10), f32)
+    y[np.arange(3 * batch), np.arange(3 * batch) % 10] = 1
+    port = TorchLeNetPort(mp, rate=0.001)
+    for t in range(1, 4):
+        xb, yb = x[(t - 1) * batch:t * batch], y[(t - 1) * batch:t * batch]
+        mp, op, ol = O.train_step(lm, alg, xb, yb, mp, op, t)
+        tl = port.train_step(xb, yb, t)
+        assert abs(tl - float(ol)) <= 2e-5 * abs(float(ol)), (t, tl, float(ol))
+    got = port.params_numpy()
+    for k, v in mp.items():  # a sign flip of a near-zero gradient moves a weight by one Adam step (1e-3)
+        assert float(np.max(np.abs(got[k] - v))) <= 3e-3 and float(np.mean(np.abs(got[k] - v))) <= 5e-5, k
