@@ -343,6 +343,16 @@ def run_ours(args):
         hbm = float(peaks.get("hbm_gbs", 6650.0))
         bf16 = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
         which = "of measured" if peaks else "of fallback"
+        # TF32 denominator: cuBLAS TF32 8192^3 measured on this pool's B200 with MEASURED_PEAKS.json's protocol
+        # (tools/measure_tf32_peak.py -> profiles/r1_tf32_peak.json); the step draws little power (clocks stay at max), so the
+        # burst figure applies.  Fallback: half of the measured bf16 figure.
+        tf32_peak, tf32_note = bf16 / 2.0, f"TF32 dense peak taken as 1/2 x bf16 cuBLAS sustained ({bf16:.0f} TF/s) {which}"
+        try:
+            tp = json.load(open(os.path.join(ROOT, "profiles", "r1_tf32_peak.json")))
+            tf32_peak = float(tp["tf32_tflops"])
+            tf32_note = f"cuBLAS TF32 8192^3 burst measured on this pool's B200 ({tf32_peak:.0f} TF/s; sustained {tp['tf32_tflops_sustained']:.0f})"
+        except Exception:
+            pass
         eng.profile_enable(True)
         eng.profile_reset()
         psteps = max(1, min(args.steps, 50, steps_per_epoch))
@@ -362,10 +372,9 @@ def run_ours(args):
         tensor_bound = top["flops"] > 0 and "tcgen05" in top["name"]
         if tensor_bound:
             ach = top["flops"] / n_launch / per_launch_s / 1e12
-            peak = bf16 / 2.0
+            peak = tf32_peak
             roofline = {"bound": "tensor", "kernel": top["name"], "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                        "frac": ach / peak, "traffic": traffic, "share_of_step": top["total_ms"] / tot,
-                        "peak_note": f"TF32 dense peak taken as 1/2 x bf16 cuBLAS sustained ({bf16:.0f} TF/s) {which}"}
+                        "frac": ach / peak, "traffic": traffic, "share_of_step": top["total_ms"] / tot, "peak_note": tf32_note}
         else:
             ach = top["bytes"] / n_launch / per_launch_s / 1e9
             roofline = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": hbm, "unit": "GB/s",
