@@ -367,7 +367,7 @@ static void plan_fusions(sb_engine* e) {
       last.out.rank == 2) {
     e->softmax_cce_fused = true;
     if (e->fast && nl >= 2 && e->L[nl - 2].d.kind == SB_LAYER_BIAS && e->L[nl - 2].inplace && last.out.d[1] <= 32 &&
-        last.out.d[0] <= 10240) {
+        std::max<int64_t>(std::max<int64_t>(1, 32 / last.out.d[1]), (last.out.d[0] + 1023) / 1024) * last.out.d[1] <= 128) {
       e->head_fused = true;
       e->L[nl - 2].head_skip = true;
     }

@@ -506,25 +506,29 @@ constexpr int kSkinnyN = 16;
 constexpr int kHeadThreads = 128;
 
 // generic deterministic column reduction  out[i] = sum_c partial[c][i]  (c ascending inside a lane group, then a fixed tree)
-__global__ void __launch_bounds__(256) partial_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int n,
-                                                             int parts) {
+template <int YG>
+__global__ void __launch_bounds__(32 * YG) partial_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int n,
+                                                                int parts) {
   pdl_prologue();
-  __shared__ float red[8][33];
+  __shared__ float red[YG][33];
   const int i = blockIdx.x * 32 + threadIdx.x, y = threadIdx.y;
   float acc = 0.f;
   if (i < n)
-    for (int c = y; c < parts; c += 8) acc = __fadd_rn(acc, __ldg(partial + (size_t)c * n + i));
+    for (int c = y; c < parts; c += YG) acc = __fadd_rn(acc, __ldg(partial + (size_t)c * n + i));
   red[y][threadIdx.x] = acc;
   __syncthreads();
   if (y == 0 && i < n) {
     float t = red[0][threadIdx.x];
 #pragma unroll
-    for (int j = 1; j < 8; ++j) t = __fadd_rn(t, red[j][threadIdx.x]);
+    for (int j = 1; j < YG; ++j) t = __fadd_rn(t, red[j][threadIdx.x]);
     out[i] = t;
   }
 }
+// part c goes to lane group c % YG (summed in ascending c inside the group), then the groups in order: a fixed order for a
+// given `parts`.  Many partials -> 32 groups so that no thread walks more than ~parts/32 dependent loads.
 void partial_reduce(const float* partial, float* out, int n, int parts, cudaStream_t s) {
-  launch_k(partial_reduce_kernel, (n + 31) / 32, dim3(32, 8), 0, s, partial, out, n, parts);
+  if (parts > 48) launch_k(partial_reduce_kernel<32>, (n + 31) / 32, dim3(32, 32), 0, s, partial, out, n, parts);
+  else launch_k(partial_reduce_kernel<8>, (n + 31) / 32, dim3(32, 8), 0, s, partial, out, n, parts);
   SB_LAUNCHED();
 }
 
@@ -821,33 +825,36 @@ bool act_bwd_col_sum(float* g, const float* y, int act, float thr, float* out, l
 // loss / dz; per-CTA loss and bias-gradient partials go to `scratch` and the LAST CTA to finish (ticket) adds them in CTA order,
 // so the result does not depend on which CTA that is.  (layer/Bias.scala:32-33, models/Activation.scala:63-69,
 // models/Loss.scala:44-57)
-constexpr int kHeadRows = 10;  // rows per CTA
+constexpr int kHeadMaxRows = 32;   // rows per CTA (one warp per row)
+constexpr int kHeadMaxCnt = 128;   // (row, class) outputs per CTA
 __global__ void __launch_bounds__(1024) head_bias_softmax_cce_kernel(float* __restrict__ z, const float* __restrict__ partial,
                                                                      int chunks, const float* __restrict__ bias,
                                                                      const float* __restrict__ y, float* __restrict__ dz,
                                                                      float* __restrict__ dbias, StepState* st, int rows, int C,
-                                                                     float* __restrict__ scratch, unsigned int* ticket) {
+                                                                     int rows_per_cta, float* __restrict__ scratch,
+                                                                     unsigned int* ticket) {
   pdl_prologue();
-  __shared__ float zs[8][kHeadRows * 32];
-  __shared__ float sl[kHeadRows];
-  __shared__ float sdb[kHeadRows][33];
+  __shared__ float zs[32][kHeadMaxCnt];
+  __shared__ float sl[kHeadMaxRows];
+  __shared__ float sdb[kHeadMaxRows][33];
   __shared__ bool last;
   const float eps = 1e-8f, fr = (float)rows;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int row0 = blockIdx.x * kHeadRows, nrows = min(kHeadRows, rows - row0);
+  const int row0 = blockIdx.x * rows_per_cta, nrows = min(rows_per_cta, rows - row0);
   const int mn = rows * C, cnt = nrows * C;
-  // ---- z for this CTA's rows ----
+  // ---- z for this CTA's rows: L lanes (one per output) x G groups; chunk c goes to group c % G, groups are added in order ----
+  const int L = (cnt + 31) & ~31, G = 1024 / L;
   {
-    const int grp = tid / 128, i = tid % 128;  // 8 groups x 128 lanes
-    for (int j = i; j < cnt; j += 128) {
+    const int grp = tid / L, i = tid - grp * L;
+    if (grp < G && i < cnt) {
       float v = 0.f;
       if (partial) {
-        const float* pp = partial + (size_t)row0 * C + j;
-        for (int c = grp; c < chunks; c += 8) v = __fadd_rn(v, __ldg(pp + (size_t)c * mn));
+        const float* pp = partial + (size_t)row0 * C + i;
+        for (int c = grp; c < chunks; c += G) v = __fadd_rn(v, __ldg(pp + (size_t)c * mn));
       } else if (grp == 0) {
-        v = z[(size_t)row0 * C + j];
+        v = z[(size_t)row0 * C + i];
       }
-      zs[grp][j] = v;
+      zs[grp][i] = v;
     }
   }
   __syncthreads();
@@ -857,8 +864,7 @@ __global__ void __launch_bounds__(1024) head_bias_softmax_cce_kernel(float* __re
     float e = 0.f, yv = 0.f;
     if (lane < C) {
       float v = zs[0][wid * C + lane];
-#pragma unroll
-      for (int g2 = 1; g2 < 8; ++g2) v = __fadd_rn(v, zs[g2][wid * C + lane]);
+      for (int g2 = 1; g2 < G; ++g2) v = __fadd_rn(v, zs[g2][wid * C + lane]);
       if (bias) v = __fadd_rn(v, __ldg(bias + lane));
       e = expf(v);
       yv = y[(size_t)row * C + lane];
@@ -905,26 +911,30 @@ __global__ void __launch_bounds__(1024) head_bias_softmax_cce_kernel(float* __re
   __syncthreads();
   if (!last) return;
   __threadfence();
-  if (tid == 0) {
+  // the LAST CTA to finish adds the per-CTA partials in CTA order (one warp per quantity, lanes stride the CTAs, fixed tree)
+  const int q = wid;  // 0: loss, 1..C: bias gradient of class q-1
+  if (q <= C) {
     float t = 0.f;
-    for (unsigned g2 = 0; g2 < gridDim.x; ++g2) t = __fadd_rn(t, __ldcg(scratch + (size_t)g2 * 40));
-    st->loss = __fdiv_rn(-t, fr);
-    *ticket = 0;  // ready for the next launch
+    for (unsigned g2 = lane; g2 < gridDim.x; g2 += 32) t = __fadd_rn(t, __ldcg(scratch + (size_t)g2 * 40 + q));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t = __fadd_rn(t, __shfl_xor_sync(0xffffffffu, t, o));
+    if (lane == 0) {
+      if (q == 0) st->loss = __fdiv_rn(-t, fr);
+      else if (dz && dbias) dbias[q - 1] = t;
+    }
   }
-  if (dz && dbias && tid >= 32 && tid < 32 + C) {
-    float t = 0.f;
-    for (unsigned g2 = 0; g2 < gridDim.x; ++g2) t = __fadd_rn(t, __ldcg(scratch + (size_t)g2 * 40 + 1 + tid - 32));
-    dbias[tid - 32] = t;
-  }
+  if (tid == 0) *ticket = 0;  // ready for the next launch
 }
-// scratch: >= ceil(rows/10)*40 floats followed by one zero-initialised 32-bit ticket (the kernel leaves it zero)
+// scratch: 1024 x 40 floats of per-CTA partials followed by one zero-initialised 32-bit ticket (the kernel leaves it zero)
 bool head_bias_softmax_cce(float* z, const float* partial, int chunks, const float* bias, const float* y, float* dz, float* dbias,
                            StepState* st, int rows, int C, float* scratch, cudaStream_t s) {
-  if (C > 32) return false;
-  const int grid = (rows + kHeadRows - 1) / kHeadRows;
-  if (grid > 1024) return false;  // scratch holds 1024 CTA partials
-  launch_k(head_bias_softmax_cce_kernel, grid, 1024, 0, s, z, partial, chunks, bias, y, dz, dbias, st, rows, C, scratch,
-                                                     reinterpret_cast<unsigned int*>(scratch + 1024 * 40));
+  if (C > 32 || rows < 1) return false;
+  // few rows per CTA (a short dependent-load chain over the split-K partials), but at most 1024 CTAs
+  int rpc = std::max(std::max(1, 32 / C), (rows + 1023) / 1024);
+  if (rpc > kHeadMaxRows || rpc * C > kHeadMaxCnt) return false;
+  const int grid = (rows + rpc - 1) / rpc;
+  launch_k(head_bias_softmax_cce_kernel, grid, 1024, 0, s, z, partial, chunks, bias, y, dz, dbias, st, rows, C, rpc, scratch,
+           reinterpret_cast<unsigned int*>(scratch + 1024 * 40));
   SB_LAUNCHED();
   return true;
 }
