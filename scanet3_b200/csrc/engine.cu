@@ -867,6 +867,24 @@ static void launch_train_step(sb_engine* e, bool resident) {
   }
 }
 
+// several resident steps in one graph: the device-side batch index / iter advance inside the graph, so the body is simply
+// repeated; one graph boundary per kStepsPerGraph steps instead of per step
+constexpr int kStepsPerGraph = 8;
+static void run_train_steps_body_multi(sb_engine* e, bool) {
+  for (int i = 0; i < kStepsPerGraph; ++i) run_train_step_body(e, true);
+}
+static void launch_train_steps_resident(sb_engine* e, int64_t n_steps) {
+  int64_t j = 0;
+  if (use_graph(e) && n_steps >= kStepsPerGraph) {
+    if (!e->g_resident_multi) e->g_resident_multi = capture(e, &e->nodes_resident_multi, run_train_steps_body_multi, true);
+    for (; j + kStepsPerGraph <= n_steps; j += kStepsPerGraph) {
+      SB_CUDA(cudaGraphLaunch(e->g_resident_multi, e->stream));
+      e->launches += e->nodes_resident_multi;
+    }
+  }
+  for (; j < n_steps; ++j) launch_train_step(e, true);
+}
+
 static void ensure_staging(sb_engine* e) {
   if (e->cstream) return;
   SB_CUDA(cudaStreamCreateWithFlags(&e->cstream, cudaStreamNonBlocking));
@@ -1057,6 +1075,7 @@ extern "C" void sb_engine_destroy(sb_engine* e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (auto& pp : e->prof_pending) { cudaEventDestroy(pp.a); cudaEventDestroy(pp.b); }
     if (e->g_resident) cudaGraphExecDestroy(e->g_resident);
+    if (e->g_resident_multi) cudaGraphExecDestroy(e->g_resident_multi);
     if (e->g_hostfed) cudaGraphExecDestroy(e->g_hostfed);
     if (e->g_loss) cudaGraphExecDestroy(e->g_loss);
     for (int i = 0; i < 2; ++i) {
@@ -1183,6 +1202,7 @@ extern "C" int sb_dataset_upload(sb_engine* e, const float* x, const float* y, i
   e->ds_rows = n_rows;
   // the captured graphs hold the dataset pointers
   if (e->g_resident) { cudaGraphExecDestroy(e->g_resident); e->g_resident = nullptr; }
+  if (e->g_resident_multi) { cudaGraphExecDestroy(e->g_resident_multi); e->g_resident_multi = nullptr; }
   SB_API_END
 }
 
@@ -1199,7 +1219,7 @@ extern "C" int sb_train_steps_async(sb_engine* e, int64_t global_iter, int64_t f
   // profiling: hold the device back while the host enqueues the event-bracketed launches (~3 API calls per kernel), so
   // the events time kernels back to back instead of launch gaps
   if (e->profiling) device_delay(std::min<long long>(400000000LL, 2000000LL + n_steps * 600000LL), e->stream);
-  for (int64_t j = 0; j < n_steps; ++j) launch_train_step(e, true);
+  launch_train_steps_resident(e, n_steps);
   e->host_iter_mirror = global_iter + n_steps;
   SB_API_END
 }
@@ -1214,7 +1234,7 @@ extern "C" int sb_train_epoch(sb_engine* e, int64_t global_iter, int64_t* iterat
     SB_FAIL(SB_ERR_INVALID_ARG, "NoSuchElementException: the shard holds fewer rows than one batch (Iterators.scala:79-81)");
   DeviceGuard dg(e->device);
   set_device_iter(e, global_iter, 0);
-  for (int64_t j = 0; j < n_batches; ++j) launch_train_step(e, true);
+  launch_train_steps_resident(e, n_batches);
   e->host_iter_mirror = global_iter + n_batches;
   launch_loss(e);  // forward-only loss on the LAST batch with the UPDATED params (Optimizer.scala:148)
   float loss = read_loss(e);

@@ -127,6 +127,8 @@ struct sb_engine {
   long long nodes_staged[2] = {0, 0};
   int stage_parity = 0;
   cudaGraphExec_t g_resident = nullptr, g_hostfed = nullptr, g_loss = nullptr;
+  cudaGraphExec_t g_resident_multi = nullptr;  // kStepsPerGraph resident steps in one graph (fewer graph boundaries per epoch)
+  long long nodes_resident_multi = 0;
   long long nodes_resident = 0, nodes_hostfed = 0, nodes_loss = 0;
   long long launches = 0;
   long long host_iter_mirror = -1;  // device st->iter as far as the host knows (-1 unknown)
