@@ -397,6 +397,23 @@ static void plan_fusions(sb_engine* e) {
           L.fused_thr = e->L[li - 1].d.relu_threshold;
           e->L[li - 1].skip_bwd = true;
         }
+        // conv(small K, first trainable layer) >> [in-place ReLU] >> pool(2x2, stride 1): the pool backward holds dA for
+        // every pixel, so it also accumulates the conv's filter gradient and dA never goes to memory
+        {
+          const int ci = L.pool_relu_bwd ? li - 2 : li - 1;
+          const PoolGeom& g = L.pg;
+          const char* off = getenv("SB_NO_POOL_WGRAD_FUSION");
+          if (!(off && off[0] == '1') && L.need_dx && L.fast_pool && ci >= 0 && e->L[ci].d.kind == SB_LAYER_CONV2D && e->L[ci].fast_smallk &&
+              !e->L[ci].need_dx && e->L[ci].buf_out == L.buf_in && g.KH == 2 && g.KW == 2 && g.SH == 1 && g.SW == 1 && g.PT == 0 &&
+              g.PL == 0 && e->L[ci].cg.SH == 1 && e->L[ci].cg.SW == 1) {
+            const ConvGeom& cg = e->L[ci].cg;
+            const int shape = cg.KH * 100 + cg.KW * 10 + cg.Cin, C4 = g.C / 4;
+            if ((shape == 331 || shape == 333 || shape == 551) && C4 <= 32 && (C4 & (C4 - 1)) == 0) {
+              L.fuse_conv_wgrad = ci;
+              e->L[ci].wgrad_in_pool = true;
+            }
+          }
+        }
         break;
       }
       case SB_LAYER_BIAS: {
@@ -708,7 +725,7 @@ static void run_backward(sb_engine* e) {
         const ConvGeom& g = L.cg;
         const double fl = 2.0 * g.N * g.OH * g.OW * (double)g.Cout * g.KH * g.KW * g.Cin;
         const double cb = 4.0 * ((double)L.in.numel() + n_out + e->params[L.p_w].numel);
-        bool wdone = false, ddone = false;
+        bool wdone = L.wgrad_in_pool, ddone = false;  // wgrad_in_pool: done by the following pool's backward kernel
         if (L.tc_kind) {
           {
             Prof pr(e, "conv2d_wgrad_tf32_tcgen05", cb, fl);
@@ -735,6 +752,15 @@ static void run_backward(sb_engine* e) {
       }
       case SB_LAYER_POOL2D: {
         if (!L.need_dx || !din) break;
+        if (L.fuse_conv_wgrad >= 0) {
+          LayerPlan& CL = e->L[L.fuse_conv_wgrad];
+          Prof pr(e, "pool_relu_bwd_conv_wgrad", 4.0 * ((double)L.in.numel() + n_out + CL.in.numel()),
+                  2.0 * CL.cg.N * CL.cg.OH * CL.cg.OW * (double)CL.cg.Cout * CL.cg.KH * CL.cg.KW * CL.cg.Cin);
+          if (pool_bwd_conv_wgrad(in, dout, din, L.pg, L.pool_relu_bwd, L.fused_thr, e->acts[CL.buf_in], CL.cg, G(e, CL.p_w), 0, e->ws,
+                                  e->ws_floats, s))
+            break;
+          SB_FAIL(SB_ERR_CUDA, "pool_bwd_conv_wgrad rejected a planned shape");
+        }
         Prof pr(e, L.pool_relu_bwd ? "pool_relu_bwd" : "pool_bwd", 4.0 * (2.0 * L.in.numel() + 2.0 * n_out), 0);
         if (L.fast_pool) pool_max_bwd_v4(in, dout, din, L.pg, L.pool_relu_bwd, L.fused_thr, s);
         else if (L.pool_relu_bwd) pool_bwd_relu(in, dout, din, L.pg, L.fused_thr, s);

@@ -62,6 +62,8 @@ struct LayerPlan {
   bool fuse_relu_fwd = false;     // small-K conv: apply the following in-place ReLU in the store
   bool pool_relu_bwd = false;     // max-pool backward also applies the mask of the in-place ReLU that produced its input
   float fused_thr = 0.f;
+  int fuse_conv_wgrad = -1;       // Pool2D: its backward also computes the filter gradient of this (small-K) conv layer
+  bool wgrad_in_pool = false;     // Conv2D: the filter gradient is produced by the following pool's backward kernel
   bool fuse_act_bwd = false;      // Bias: also applies the backward of the in-place activation that follows (one pass)
   bool head_skip = false;         // Bias / Softmax of the fused classifier head: executed by the head kernel when training
   bool fast_smallk = false;       // Conv2D with KH*KW*Cin <= 32: register-tiled direct kernel instead of the implicit GEMM

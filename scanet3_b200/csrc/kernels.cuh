@@ -101,6 +101,10 @@ namespace sb {
 // ---- kernels_fast.cu: vectorised / fused variants (return false when the shape is not covered) ----
 void pool_max_fwd_v4(const float* x, float* y, const PoolGeom& g, cudaStream_t s);
 void pool_max_bwd_v4(const float* x, const float* dy, float* dx, const PoolGeom& g, int relu, float thr, cudaStream_t s);
+// 2x2 stride-1 max-pool backward (+ReLU mask) that also accumulates the filter gradient of the small-K Conv2D feeding the pool
+// (conv >> [in-place ReLU] >> pool); dx is written only when store_dx.  false: shape not covered
+bool pool_bwd_conv_wgrad(const float* x, const float* dy, float* dx, const PoolGeom& g, int relu, float thr, const float* conv_in,
+                         const ConvGeom& cg, float* dw, int store_dx, float* ws, size_t ws_floats, cudaStream_t s);
 void conv_smallk_fwd(const float* x, const float* w, float* y, const ConvGeom& g, int relu, float thr, cudaStream_t s);
 bool conv_smallk_wgrad(const float* x, const float* dy, float* dw, const ConvGeom& g, float* ws, size_t ws_floats, cudaStream_t s);
 bool dense_skinny_fwd(const float* x, const float* w, float* z, int M, int N, int K, float* ws, size_t ws_floats, cudaStream_t s);

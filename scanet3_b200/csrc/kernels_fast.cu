@@ -175,14 +175,26 @@ __device__ __forceinline__ void acc_if(float4& acc, const Idx4& k, int pos, cons
 // evaluates the two windows whose top-left corner is in column w (rows h-1 and h) once -- 3 x loads + 2 dy loads -- and
 // keeps them for column w+1, where the element is their right-hand member.  Summation order per element: windows
 // (h-1,w-1), (h-1,w), (h,w-1), (h,w) -- the same as the generic gather kernel.
-template <bool RELU>
-__global__ void __launch_bounds__(256) pool22_bwd_strip_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+//
+// WG = KH*100 + KW*10 + CIN != 0 additionally fuses the FILTER GRADIENT of the small-K Conv2D that produced the pool's input
+// (conv -> in-place ReLU -> pool, the first block of the BASELINE CNNs): the thread already holds dA = dLoss/d(conv output)
+// for its pixel and 4 channels, so it accumulates dW[kh][kw][ci][co] += X[pixel + tap][ci] * dA[co] in registers over its strip
+// (the conv input window slides with the walk: KH*CIN loads per column); threads of a CTA are then summed (shuffles + shared
+// memory, fixed order) into one partial per CTA.  dA itself is only stored when something else needs it.
+struct PoolWgradFuse {
+  const float* xin;  // conv input [N, Hin, Win, CIN]
+  float* partial;    // [gridDim.x][KH*KW*CIN][C]
+  int Hin, Win, PT, PL;
+  int store_dx;
+};
+template <bool RELU, int WG>
+__global__ void __launch_bounds__(128) pool22_bwd_strip_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                float* __restrict__ dx, PoolGeom g, float thr, int seg_len,
-                                                               int segs, long long n_threads) {
+                                                               int segs, long long n_threads, PoolWgradFuse wf) {
   pdl_prologue();
+  constexpr int KH = WG / 100, KW = (WG / 10) % 10, CIN = WG % 10, K = KH * KW * CIN;
   const int C4 = g.C >> 2;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_threads) return;
   const int c4 = (int)(i % C4);
   long long t = i / C4;
   const int seg = (int)(t % segs); t /= segs;
@@ -190,77 +202,181 @@ __global__ void __launch_bounds__(256) pool22_bwd_strip_kernel(const float* __re
   const int b = (int)(t / g.H);
   const int w0 = seg * seg_len;
   const int w1 = min(w0 + seg_len, g.W);
-  if (w0 >= w1) return;
-  const bool top_ok = h >= 1, bot_ok = h <= g.H - 2;  // window rows h-1 and h exist
-  const long long rs = (long long)g.W * g.C;
-  const float* xm = x + (((long long)b * g.H + h) * g.W) * g.C + c4 * 4;  // row h
-  const float* xt = top_ok ? xm - rs : xm;                                 // row h-1 (clamped: its windows then carry dy = 0)
-  const float* xb = bot_ok ? xm + rs : xm;                                 // row h+1
-  const float* dt = dy + (((long long)b * g.OH + (top_ok ? h - 1 : 0)) * g.OW) * g.C + c4 * 4;
-  const float* db = dy + (((long long)b * g.OH + (bot_ok ? h : 0)) * g.OW) * g.C + c4 * 4;
-  float* dxo = dx + (((long long)b * g.H + h) * g.W) * g.C + c4 * 4;
-  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-  // state of column w-1: its x values and the two windows anchored there
-  float4 ct, cm, cb;          // x[h-1][w], x[h][w], x[h+1][w] of the CURRENT column
-  Idx4 pkt{-1, -1, -1, -1}, pkb{-1, -1, -1, -1};
-  float4 pgt = zero, pgb = zero;
-  if (w0 >= 1) {
-    const long long o = (long long)(w0 - 1) * g.C;
-    const float4 lt = ld4(xt + o), lm = ld4(xm + o), lb = ld4(xb + o);
-    ct = ld4(xt + o + g.C); cm = ld4(xm + o + g.C); cb = ld4(xb + o + g.C);
-    pkt = argmax22_4(lt, ct, lm, cm);
-    pkb = argmax22_4(lm, cm, lb, cb);
-    pgt = top_ok ? ld4(dt + o) : zero;
-    pgb = bot_ok ? ld4(db + o) : zero;
-  } else {
-    ct = ld4(xt); cm = ld4(xm); cb = ld4(xb);
+  const bool active = i < n_threads && w0 < w1;
+  float4 dwacc[K > 0 ? K : 1];
+  if (WG) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) dwacc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  if (active) {
+    const bool top_ok = h >= 1, bot_ok = h <= g.H - 2;  // window rows h-1 and h exist
+    const long long rs = (long long)g.W * g.C;
+    const float* xm = x + (((long long)b * g.H + h) * g.W) * g.C + c4 * 4;  // row h
+    const float* xt = top_ok ? xm - rs : xm;                                 // row h-1 (clamped: its windows then carry dy = 0)
+    const float* xb = bot_ok ? xm + rs : xm;                                 // row h+1
+    const float* dt = dy + (((long long)b * g.OH + (top_ok ? h - 1 : 0)) * g.OW) * g.C + c4 * 4;
+    const float* db = dy + (((long long)b * g.OH + (bot_ok ? h : 0)) * g.OW) * g.C + c4 * 4;
+    float* dxo = dx + (((long long)b * g.H + h) * g.W) * g.C + c4 * 4;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    // state of column w-1: its x values and the two windows anchored there
+    float4 ct, cm, cb;          // x[h-1][w], x[h][w], x[h+1][w] of the CURRENT column
+    Idx4 pkt{-1, -1, -1, -1}, pkb{-1, -1, -1, -1};
+    float4 pgt = zero, pgb = zero;
+    if (w0 >= 1) {
+      const long long o = (long long)(w0 - 1) * g.C;
+      const float4 lt = ld4(xt + o), lm = ld4(xm + o), lb = ld4(xb + o);
+      ct = ld4(xt + o + g.C); cm = ld4(xm + o + g.C); cb = ld4(xb + o + g.C);
+      pkt = argmax22_4(lt, ct, lm, cm);
+      pkb = argmax22_4(lm, cm, lb, cb);
+      pgt = top_ok ? ld4(dt + o) : zero;
+      pgb = bot_ok ? ld4(db + o) : zero;
+    } else {
+      ct = ld4(xt); cm = ld4(xm); cb = ld4(xb);
+    }
+    // conv input window of the current pixel: rows h+a-PT, columns w+bb-PL (zero outside the image)
+    float xw[KH > 0 ? KH : 1][KW > 0 ? KW : 1][CIN > 0 ? CIN : 1];
+    auto load_col = [&](int col_in, int slot) {
+#pragma unroll
+      for (int a = 0; a < KH; ++a) {
+        const int ih = h + a - wf.PT;
+        const bool ok = ih >= 0 && ih < wf.Hin && col_in >= 0 && col_in < wf.Win;
+        const float* p = wf.xin + (((long long)b * wf.Hin + (ok ? ih : 0)) * wf.Win + (ok ? col_in : 0)) * CIN;
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) xw[a][slot][ci] = ok ? __ldg(p + ci) : 0.f;
+      }
+    };
+    if (WG) {
+#pragma unroll
+      for (int bb = 0; bb + 1 < KW; ++bb) load_col(w0 - wf.PL + bb, bb + 1);  // shifted into place by the first iteration
+    }
 #pragma unroll 2
-  for (int w = w0; w < w1; ++w) {
-    const long long o = (long long)w * g.C;
-    Idx4 kt{-1, -1, -1, -1}, kb{-1, -1, -1, -1};
-    float4 gt = zero, gb = zero, nt = ct, nm = cm, nb = cb;
-    if (w <= g.W - 2) {  // windows anchored in column w exist
-      nt = ld4(xt + o + g.C); nm = ld4(xm + o + g.C); nb = ld4(xb + o + g.C);
-      kt = argmax22_4(ct, nt, cm, nm);
-      kb = argmax22_4(cm, nm, cb, nb);
-      gt = top_ok ? ld4(dt + o) : zero;
-      gb = bot_ok ? ld4(db + o) : zero;
+    for (int w = w0; w < w1; ++w) {
+      const long long o = (long long)w * g.C;
+      Idx4 kt{-1, -1, -1, -1}, kb{-1, -1, -1, -1};
+      float4 gt = zero, gb = zero, nt = ct, nm = cm, nb = cb;
+      if (w <= g.W - 2) {  // windows anchored in column w exist
+        nt = ld4(xt + o + g.C); nm = ld4(xm + o + g.C); nb = ld4(xb + o + g.C);
+        kt = argmax22_4(ct, nt, cm, nm);
+        kb = argmax22_4(cm, nm, cb, nb);
+        gt = top_ok ? ld4(dt + o) : zero;
+        gb = bot_ok ? ld4(db + o) : zero;
+      }
+      float4 acc = zero;
+      acc_if(acc, pkt, 3, pgt);  // window (h-1, w-1): element is its bottom-right member
+      acc_if(acc, kt, 2, gt);    // window (h-1, w)  : bottom-left
+      acc_if(acc, pkb, 1, pgb);  // window (h,   w-1): top-right
+      acc_if(acc, kb, 0, gb);    // window (h,   w)  : top-left
+      if (RELU) {
+        if (!(cm.x > thr)) acc.x = 0.f;
+        if (!(cm.y > thr)) acc.y = 0.f;
+        if (!(cm.z > thr)) acc.z = 0.f;
+        if (!(cm.w > thr)) acc.w = 0.f;
+      }
+      if (!WG || wf.store_dx) st4(dxo + o, acc);
+      if (WG) {
+#pragma unroll
+        for (int a = 0; a < KH; ++a)
+#pragma unroll
+          for (int bb = 0; bb + 1 < KW; ++bb)
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) xw[a][bb][ci] = xw[a][bb + 1][ci];
+        load_col(w - wf.PL + KW - 1, KW - 1);
+#pragma unroll
+        for (int a = 0; a < KH; ++a)
+#pragma unroll
+          for (int bb = 0; bb < KW; ++bb)
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) {
+              const float xv = xw[a][bb][ci];
+              float4& r = dwacc[(a * KW + bb) * CIN + ci];
+              r.x = fmaf(xv, acc.x, r.x); r.y = fmaf(xv, acc.y, r.y); r.z = fmaf(xv, acc.z, r.z); r.w = fmaf(xv, acc.w, r.w);
+            }
+      }
+      pkt = kt; pkb = kb; pgt = gt; pgb = gb;
+      ct = nt; cm = nm; cb = nb;
     }
-    float4 acc = zero;
-    acc_if(acc, pkt, 3, pgt);  // window (h-1, w-1): element is its bottom-right member
-    acc_if(acc, kt, 2, gt);    // window (h-1, w)  : bottom-left
-    acc_if(acc, pkb, 1, pgb);  // window (h,   w-1): top-right
-    acc_if(acc, kb, 0, gb);    // window (h,   w)  : top-left
-    if (RELU) {
-      if (!(cm.x > thr)) acc.x = 0.f;
-      if (!(cm.y > thr)) acc.y = 0.f;
-      if (!(cm.z > thr)) acc.z = 0.f;
-      if (!(cm.w > thr)) acc.w = 0.f;
-    }
-    st4(dxo + o, acc);
-    pkt = kt; pkb = kb; pgt = gt; pgb = gb;
-    ct = nt; cm = nm; cb = nb;
   }
+  if (WG) {
+    // CTA-level sum in a fixed order: lanes with the same channel quad inside a warp (xor C4, 2*C4, ..), then the warps
+    extern __shared__ __align__(16) float4 red[];  // [nwarps][K][C4]
+    const int wl = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int cq = threadIdx.x % C4;  // == c4 when C4 divides the CTA size (checked by the launcher)
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+      for (int o = C4; o < 32; o <<= 1) {
+        dwacc[k].x = __fadd_rn(dwacc[k].x, __shfl_xor_sync(0xffffffffu, dwacc[k].x, o));
+        dwacc[k].y = __fadd_rn(dwacc[k].y, __shfl_xor_sync(0xffffffffu, dwacc[k].y, o));
+        dwacc[k].z = __fadd_rn(dwacc[k].z, __shfl_xor_sync(0xffffffffu, dwacc[k].z, o));
+        dwacc[k].w = __fadd_rn(dwacc[k].w, __shfl_xor_sync(0xffffffffu, dwacc[k].w, o));
+      }
+    if (wl < C4) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) red[(wid * K + k) * C4 + cq] = dwacc[k];
+    }
+    __syncthreads();
+    float* part = wf.partial + (size_t)blockIdx.x * K * g.C;
+    for (int q = threadIdx.x; q < K * C4; q += blockDim.x) {
+      float4 tot = red[q];
+      for (int wq = 1; wq < nwarps; ++wq) {
+        const float4 v = red[wq * K * C4 + q];
+        tot.x = __fadd_rn(tot.x, v.x); tot.y = __fadd_rn(tot.y, v.y); tot.z = __fadd_rn(tot.z, v.z); tot.w = __fadd_rn(tot.w, v.w);
+      }
+      st4(part + (q / C4) * g.C + (q % C4) * 4, tot);
+    }
+  }
+}
+// segments per row: cost ~ whole waves x (columns per thread + prologue columns); a wave = what 148 SMs hold at the kernel's
+// register footprint
+static void pool22_segments(const PoolGeom& g, int ctas_per_sm, int* segs_out, int* seg_len_out) {
+  const long long wave = (long long)kNumSMs * ctas_per_sm * 128;
+  int best_segs = 1;
+  double best = 1e30;
+  for (int segs = 1; segs <= 8; ++segs) {
+    const int len = (g.W + segs - 1) / segs;
+    if ((segs - 1) * len >= g.W) continue;
+    const long long nt = (long long)g.N * g.H * segs * (g.C / 4);
+    const double cost = (double)((nt + wave - 1) / wave) * (len + 1.5);
+    if (cost < best) { best = cost; best_segs = segs; }
+  }
+  *segs_out = best_segs;
+  *seg_len_out = (g.W + best_segs - 1) / best_segs;
+}
+static bool pool_is_22s1(const PoolGeom& g);
+// max-pool backward (+ReLU mask) with the filter gradient of the preceding small-K conv: returns false when not covered
+bool pool_bwd_conv_wgrad(const float* x, const float* dy, float* dx, const PoolGeom& g, int relu, float thr, const float* conv_in,
+                         const ConvGeom& cg, float* dw, int store_dx, float* ws, size_t ws_floats, cudaStream_t s) {
+  const int C4 = g.C / 4, shape = cg.KH * 100 + cg.KW * 10 + cg.Cin;
+  if (!pool_is_22s1(g) || (g.C & 3) || C4 > 32 || (C4 & (C4 - 1)) || cg.SH != 1 || cg.SW != 1) return false;
+  if (cg.OH != g.H || cg.OW != g.W || cg.Cout != g.C || cg.N != g.N) return false;
+  if (shape != 331 && shape != 333 && shape != 551) return false;
+  int segs, seg_len;
+  pool22_segments(g, 3, &segs, &seg_len);
+  const long long nt = (long long)g.N * g.H * segs * C4;
+  const int blocks = (int)((nt + 127) / 128);
+  const int K = cg.KH * cg.KW * cg.Cin;
+  if ((size_t)blocks * K * g.C > ws_floats) return false;
+  const size_t smem = (size_t)4 * K * C4 * sizeof(float4);
+  PoolWgradFuse wf{conv_in, ws, cg.H, cg.W, cg.PT, cg.PL, store_dx};
+#define SB_POOL_WG(R, S) \
+  launch_k(pool22_bwd_strip_kernel<R, S>, blocks, 128, smem, s, x, dy, dx, g, thr, seg_len, segs, nt, wf)
+  if (relu) {
+    if (shape == 331) SB_POOL_WG(true, 331); else if (shape == 333) SB_POOL_WG(true, 333); else SB_POOL_WG(true, 551);
+  } else {
+    if (shape == 331) SB_POOL_WG(false, 331); else if (shape == 333) SB_POOL_WG(false, 333); else SB_POOL_WG(false, 551);
+  }
+#undef SB_POOL_WG
+  SB_LAUNCHED();
+  partial_reduce(ws, dw, K * g.C, blocks, s);
+  return true;
 }
 void pool_max_bwd_v4(const float* x, const float* dy, float* dx, const PoolGeom& g, int relu, float thr, cudaStream_t s) {
   if (pool_is_22s1(g)) {
-    // segments per row: cost ~ whole waves x (columns per thread + 1 prologue column); a wave = what 148 SMs hold at the
-    // kernel's register footprint (5 CTAs of 128 threads)
-    const long long wave = (long long)kNumSMs * 5 * 128;
-    int best_segs = 1;
-    double best = 1e30;
-    for (int segs = 1; segs <= 8; ++segs) {
-      const int len = (g.W + segs - 1) / segs;
-      if ((segs - 1) * len >= g.W) continue;
-      const long long nt = (long long)g.N * g.H * segs * (g.C / 4);
-      const double cost = (double)((nt + wave - 1) / wave) * (len + 1.5);
-      if (cost < best) { best = cost; best_segs = segs; }
-    }
-    const int seg_len = (g.W + best_segs - 1) / best_segs;
-    const long long nt = (long long)g.N * g.H * best_segs * (g.C / 4);
-    if (relu) launch_k(pool22_bwd_strip_kernel<true>, (int)((nt + 127) / 128), 128, 0, s, x, dy, dx, g, thr, seg_len, best_segs, nt);
-    else launch_k(pool22_bwd_strip_kernel<false>, (int)((nt + 127) / 128), 128, 0, s, x, dy, dx, g, 0.f, seg_len, best_segs, nt);
+    int segs, seg_len;
+    pool22_segments(g, 5, &segs, &seg_len);
+    const long long nt = (long long)g.N * g.H * segs * (g.C / 4);
+    PoolWgradFuse none{};
+    if (relu) launch_k(pool22_bwd_strip_kernel<true, 0>, (int)((nt + 127) / 128), 128, 0, s, x, dy, dx, g, thr, seg_len, segs, nt, none);
+    else launch_k(pool22_bwd_strip_kernel<false, 0>, (int)((nt + 127) / 128), 128, 0, s, x, dy, dx, g, 0.f, seg_len, segs, nt, none);
     SB_LAUNCHED();
     return;
   }
