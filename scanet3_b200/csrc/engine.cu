@@ -895,13 +895,21 @@ static void launch_train_step(sb_engine* e, bool resident) {
 
 // several resident steps in one graph: the device-side batch index / iter advance inside the graph, so the body is simply
 // repeated; one graph boundary per kStepsPerGraph steps instead of per step
-constexpr int kStepsPerGraph = 8;
+static int steps_per_graph() {
+  static const int n = [] {
+    const char* v = getenv("SB_STEPS_PER_GRAPH");
+    const int k = v ? atoi(v) : 8;
+    return k < 1 ? 1 : (k > 64 ? 64 : k);
+  }();
+  return n;
+}
 static void run_train_steps_body_multi(sb_engine* e, bool) {
-  for (int i = 0; i < kStepsPerGraph; ++i) run_train_step_body(e, true);
+  for (int i = 0; i < steps_per_graph(); ++i) run_train_step_body(e, true);
 }
 static void launch_train_steps_resident(sb_engine* e, int64_t n_steps) {
   int64_t j = 0;
-  if (use_graph(e) && n_steps >= kStepsPerGraph) {
+  const int kStepsPerGraph = steps_per_graph();
+  if (use_graph(e) && kStepsPerGraph > 1 && n_steps >= kStepsPerGraph) {
     if (!e->g_resident_multi) e->g_resident_multi = capture(e, &e->nodes_resident_multi, run_train_steps_body_multi, true);
     for (; j + kStepsPerGraph <= n_steps; j += kStepsPerGraph) {
       SB_CUDA(cudaGraphLaunch(e->g_resident_multi, e->stream));
