@@ -326,9 +326,11 @@ def run_ours(args):
         arena_bytes = eng.arena()[1] * 4
         bus = 2.0 * (world - 1) / world * arena_bytes / (a_ms / 1000.0) / 1e9  # per GPU, each direction carries (k-1)/k of it
         averaging = {"ms": a_ms, "arena_bytes": arena_bytes, "bus_GBps_per_gpu": bus, "per_direction_GBps": bus / 2.0,
-                     "peak_per_direction_GBps": 770.0, "frac": bus / 2.0 / 770.0,
-                     "note": "one kernel per rank incl. two cross-GPU flag barriers; peak = measured NVLink peer copy per direction "
-                             "(B200_PROFILING.md)"}
+                     "peak_per_direction_GBps": 770.0, "frac": bus / 2.0 / 770.0, "nccl_allreduce_busbw_ref_GBps": 725.0,
+                     "frac_of_nccl_busbw": bus / 725.0,
+                     "note": "one kernel per rank incl. two cross-GPU flag barriers and the loss combine; bus = 2(k-1)/k x arena / time "
+                             "(NCCL's bus-bandwidth convention); references: measured NVLink peer copy 770 GB/s per direction and "
+                             "8-rank NCCL all-reduce bus bandwidth 725 GB/s at 1 GiB (B200_PROFILING.md)"}
 
     # ---- per-kernel-class device times over the same steps (eager launches bracketed by CUDA events on the engine
     #      stream) -> the dominant kernel and its roofline ----
