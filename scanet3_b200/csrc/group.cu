@@ -12,6 +12,7 @@
 // link-time NCCL dependency (the JVM / torch process brings its own).
 #include <dlfcn.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <memory>
@@ -407,8 +408,9 @@ extern "C" int sb_group_average_device(sb_group* g, uint64_t epoch) {
   const long long n4 = e->arena_floats / 4;
   const long long per = (n4 + g->k - 1) / g->k;
   const long long lo = per * g->rank, hi = std::min(n4, per * (g->rank + 1));
-  // every CTA polls flags, so the whole grid must be co-resident: <= 4 CTAs of 256 threads per SM
-  int blocks = (int)std::min<long long>(std::max<long long>((hi - lo + 255) / 256, 1), (long long)kNumSMs * 4);
+  // every CTA polls flags, so the whole grid must be co-resident: <= 8 CTAs of 256 threads per SM (SB_P2P_CTAS_PER_SM tunes)
+  static const int per_sm = [] { const char* v = getenv("SB_P2P_CTAS_PER_SM"); int k = v ? atoi(v) : 4; return k < 1 ? 1 : (k > 8 ? 8 : k); }();
+  int blocks = (int)std::min<long long>(std::max<long long>((hi - lo + 255) / 256, 1), (long long)kNumSMs * per_sm);
   SyncArgs a;
   a.tail_off = e->arena_floats;
   a.epoch = epoch;
