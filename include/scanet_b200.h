@@ -186,6 +186,23 @@ int sb_init_params(sb_engine* e);
 /* only the optimizer state (when model params came from `initParams`) */
 int sb_init_opt_params(sb_engine* e);
 
+/* ---- parameter wire format + checkpoint / resume ----
+ * One tensor record is byte-for-byte the reference's Kryo `TensorSerializer.write` (optimizers/KryoSerializers.scala:33-49,
+ * Kryo 4.0.2: fixed-width big-endian ints): int32 type code (DT_FLOAT = 1) | int32 rank | int64 dims[rank] | int32 payload
+ * bytes | row-major little-endian fp32 payload (core/Tensor.scala:46-52) -- `TensorSerializer.read` (:51-64) rebuilds the
+ * `Tensor[Float]`.  buf == NULL in an encode call only reports the size in *written. */
+int sb_wire_encode(const int64_t* dims, int32_t rank, const float* data, void* buf, size_t cap, size_t* written);
+/* data == NULL: parse the header only (rank, dims, *consumed = record size) */
+int sb_wire_decode(const void* buf, size_t n, int64_t* dims, int32_t dims_cap, int32_t* rank, float* data, size_t data_cap,
+                   size_t* consumed);
+int sb_param_to_wire(sb_engine* e, const char* path, void* buf, size_t cap, size_t* written);
+int sb_param_from_wire(sb_engine* e, const char* path, const void* buf, size_t n, size_t* consumed);
+/* Every tensor of the arena (weights, layer state, optimizer state) keyed by the reference's path strings, plus the global
+ * iteration and epoch (`Step`, Optimizer.scala:17-24), in one file: "SB3CKPT1" | int64 BE iter | int64 BE epoch | int32 BE n | n x { int32 BE path bytes | path | tensor record }.
+ * The reference has no checkpointing (README.md:112); a resumed run continues bit-identically (tests/test_gpu_parity.py). */
+int sb_checkpoint_save(sb_engine* e, const char* file, int64_t global_iter, int64_t epoch);
+int sb_checkpoint_load(sb_engine* e, const char* file, int64_t* global_iter, int64_t* epoch);
+
 /* ---- the train path ---- */
 /* shard resident in HBM (the partition iterator + TensorIterator, Iterators.scala:39-83).
  * x: [n_rows, prod(input_dims)], y: [n_rows, prod(label_dims)]; host memory (pinned or pageable). */
@@ -209,6 +226,16 @@ int sb_train_step_async(sb_engine* e, const float* x, const float* y, int64_t it
 int sb_eval_loss(sb_engine* e, const float* x, const float* y, float* loss_out);
 /* forward only (`TrainedModel.result`, models/Model.scala:154-163): out[batch, ...] on the host */
 int sb_predict(sb_engine* e, const float* x, float* out, size_t n_out);
+/* Estimators on the device (estimators/package.scala:18-137; `RecordAccuracy`, optimizers/Effect.scala:52-64): forwards
+ * n_rows rows in inference mode, batch by batch (the tail batch is partial, `remaining = Partial`), and reduces on the GPU.
+ * x == NULL: the rows of the resident shard (sb_dataset_upload), n_rows <= 0 meaning all of them; otherwise HOST buffers.
+ *   out[0]: ACCURACY -> positives (rows with round(prediction) == label on every output, :30-33);
+ *           SQUARED_ERROR / ABS_ERROR -> sum of (p-y)^2 / |p-y| over all outputs (:53-63; MSE/MAE = out[0]/out[1]);
+ *           R2 -> sum (p-y)^2 (:127-131)
+ *   out[1]: rows evaluated;  out[2], out[3] (R2 only, labels of shape (1)): sum p, sum p^2 -- the reference centres
+ *           SST on the mean of the PREDICTIONS (`map(_._2)`, :124), so R2 = 1 - out[0] / (out[3] - out[2]^2/out[1]). */
+typedef enum { SB_EST_ACCURACY = 0, SB_EST_SQUARED_ERROR = 1, SB_EST_ABS_ERROR = 2, SB_EST_R2 = 3 } sb_estimator;
+int sb_estimate(sb_engine* e, int estimator, const float* x, const float* y, int64_t n_rows, double out[4]);
 /* gradients of the trainable weights for one HOST batch without updating anything
  * (`LossModel.grad`, models/Model.scala:107-111) -- parity-test hook. */
 int sb_compute_grads(sb_engine* e, const float* x, const float* y, float* loss_out);

@@ -31,3 +31,4 @@ from .layers import *  # noqa: F401,F403
 from .losses import *  # noqa: F401,F403
 from .optimizers import *  # noqa: F401,F403
 from .train import *  # noqa: F401,F403
+from . import estimators  # noqa: F401,E402

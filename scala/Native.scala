@@ -61,6 +61,13 @@ object Native {
   val trainStep: MethodHandle = fn("sb_train_step", JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS)
   val evalLoss: MethodHandle = fn("sb_eval_loss", JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS)
   val predict: MethodHandle = fn("sb_predict", JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG)
+  // estimators/package.scala:18-137 on the device: (engine, kind, x|NULL, y|NULL, rows, double[4])
+  val estimate: MethodHandle = fn("sb_estimate", JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS)
+  // KryoSerializers.scala:27-63 records <-> arena tensors, and whole-arena checkpoints
+  val paramToWire: MethodHandle = fn("sb_param_to_wire", JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS)
+  val paramFromWire: MethodHandle = fn("sb_param_from_wire", JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS)
+  val checkpointSave: MethodHandle = fn("sb_checkpoint_save", JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG)
+  val checkpointLoad: MethodHandle = fn("sb_checkpoint_load", JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS)
   val groupCreate: MethodHandle = fn("sb_group_create", JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, JAVA_INT, ADDRESS)
   val groupAverage: MethodHandle = fn("sb_group_average", JAVA_INT, ADDRESS, ADDRESS, ADDRESS)
   val groupDestroy: MethodHandle =

@@ -9,6 +9,6 @@ from .dsl import (Activate, Activation, AdaDelta, AdaGrad, Adam, Adamax, Algorit
                   HeUniform, Identity, Initializer, L1, L2, LecunNormal, LecunUniform, LinearRegression, LogisticRegression, Loss, LSTM,
                   LSTMCell, MeanSquaredError, Nadam, Ones, Orthogonal, Pool2D, RandomNormal, RandomNormalTruncated, RandomUniform, ReLU, RMSProp,
                   RNN, Same, SGD, Sigmoid, Softmax, Tanh, Valid, Zero, Zeros)
-from .engine import Engine, Group, spark_chain_weights
-from .optimizer import (Builder, Dataset, LossModel, Optimizer, RecordAccuracy, RecordIteration, RecordLoss, Step,
-                        TrainedModel, accuracy, always, epochs, iterations, maximize, minimize, never)
+from .engine import Engine, Group, spark_chain_weights, wire_decode, wire_encode
+from .optimizer import (Builder, Dataset, LossModel, Optimizer, RecordAccuracy, RecordIteration, RecordLoss, SaveCheckpoint, Step,
+                        TrainedModel, MAE, MSE, R2Score, RMSE, accuracy, always, epochs, iterations, maximize, minimize, never)

@@ -24,6 +24,7 @@ ROLE_WEIGHT, ROLE_STATE, ROLE_OPT = range(3)
 AGG_NONE, AGG_AVG = 0, 1
 AVG_MEAN, AVG_SPARK_CHAIN, AVG_WEIGHTS = range(3)
 COLL_P2P, COLL_NCCL = 0, 1
+EST_ACCURACY, EST_SQUARED_ERROR, EST_ABS_ERROR, EST_R2 = range(4)
 
 
 class NativeError(RuntimeError):
@@ -89,6 +90,14 @@ PROTOTYPES = {
     "sb_train_step_async": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     "sb_eval_loss": (C.c_int, [_P, _P, _P, _FP]),
     "sb_predict": (C.c_int, [_P, _P, _P, C.c_size_t]),
+    "sb_wire_encode": (C.c_int, [C.POINTER(C.c_int64), C.c_int32, _P, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "sb_wire_decode": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_int64), C.c_int32, C.POINTER(C.c_int32), _P, C.c_size_t,
+                                 C.POINTER(C.c_size_t)]),
+    "sb_param_to_wire": (C.c_int, [_P, C.c_char_p, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "sb_param_from_wire": (C.c_int, [_P, C.c_char_p, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "sb_checkpoint_save": (C.c_int, [_P, C.c_char_p, C.c_int64, C.c_int64]),
+    "sb_checkpoint_load": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "sb_estimate": (C.c_int, [_P, C.c_int, _P, _P, C.c_int64, C.POINTER(C.c_double)]),
     "sb_compute_grads": (C.c_int, [_P, _P, _P, _FP]),
     "sb_grad_get": (C.c_int, [_P, C.c_char_p, _P, C.c_size_t]),
     "sb_sync": (C.c_int, [_P]),

@@ -52,6 +52,8 @@ bool pdl_enabled() {
   return SB_OK;
 
 extern "C" const char* sb_last_error(void) { return tl_error.c_str(); }
+// internal hooks of wire.cpp (host-only translation unit above the public ABI); not declared in the public header
+extern "C" void sb_internal_set_last_error(const char* msg) { tl_error = msg ? msg : ""; }
 extern "C" int sb_abi_version(void) { return SB_ABI_VERSION; }
 extern "C" int sb_device_count(void) {
   int n = 0;
@@ -1125,7 +1127,7 @@ extern "C" void sb_engine_destroy(sb_engine* e) {
     for (float* p : e->acts) cudaFree(p);
     for (float* p : e->dacts) cudaFree(p);
     cudaFree(e->arena); cudaFree(e->grads); cudaFree(e->by); cudaFree(e->ds_x); cudaFree(e->ds_y);
-    cudaFree(e->st); cudaFree(e->ws); cudaFree(e->head_scratch);
+    cudaFree(e->st); cudaFree(e->ws); cudaFree(e->head_scratch); cudaFree(e->est_acc);
     if (e->st_host) cudaFreeHost(e->st_host);
     if (e->stream) cudaStreamDestroy(e->stream);
   }
@@ -1216,6 +1218,14 @@ extern "C" int sb_init_params(sb_engine* e) {
   SB_CUDA(cudaStreamSynchronize(e->stream));
   tc_params_changed(e);
   e->params_ready = e->opt_ready = true;
+  SB_API_END
+}
+
+extern "C" int sb_internal_mark_params_ready(sb_engine* e) {  // every tensor of the arena was restored from a checkpoint
+  SB_API_BEGIN
+  need_device(e);
+  e->params_ready = e->opt_ready = true;
+  e->host_iter_mirror = -1;
   SB_API_END
 }
 
@@ -1332,6 +1342,47 @@ extern "C" int sb_predict(sb_engine* e, const float* x, float* out, size_t n_out
   run_forward(e, FWD_INFER);
   e->launches += tl_launch_count - before;
   SB_CUDA(cudaMemcpyAsync(out, e->acts[e->L.back().buf_out], n_out * 4, cudaMemcpyDeviceToHost, e->stream));
+  SB_CUDA(cudaStreamSynchronize(e->stream));
+  SB_API_END
+}
+
+extern "C" int sb_estimate(sb_engine* e, int estimator, const float* x, const float* y, int64_t n_rows, double out[4]) {
+  SB_API_BEGIN
+  need_device(e);
+  if (!e->params_ready) SB_FAIL(SB_ERR_STATE, "model parameters are not initialised");
+  if (!out) SB_FAIL(SB_ERR_INVALID_ARG, "null output");
+  if (estimator < SB_EST_ACCURACY || estimator > SB_EST_R2) SB_FAIL(SB_ERR_INVALID_ARG, "unknown estimator");
+  if (e->out_shape.numel() != e->label_shape.numel())
+    SB_FAIL(SB_ERR_INVALID_ARG, "estimators compare the model output with the labels element by element: shapes differ");
+  if (estimator == SB_EST_R2 && e->y_per_row != 1)
+    SB_FAIL(SB_ERR_INVALID_ARG, "labels should have shape (1)");  // estimators/package.scala:103
+  const bool resident = x == nullptr;
+  if (resident) {
+    if (!e->ds_x) SB_FAIL(SB_ERR_STATE, "no resident shard: call sb_dataset_upload first or pass host buffers");
+    if (n_rows <= 0 || n_rows > e->ds_rows) n_rows = e->ds_rows;
+    x = e->ds_x;
+    y = e->ds_y;
+  } else {
+    if (!y) SB_FAIL(SB_ERR_INVALID_ARG, "null y");
+    if (n_rows < 0) SB_FAIL(SB_ERR_INVALID_ARG, "negative row count");
+  }
+  DeviceGuard dg(e->device);
+  if (!e->est_acc) SB_CUDA(cudaMalloc(&e->est_acc, 4 * sizeof(double)));
+  SB_CUDA(cudaMemsetAsync(e->est_acc, 0, 4 * sizeof(double), e->stream));
+  const int64_t B = e->in_shape.d[0];
+  const int C = (int)e->y_per_row;
+  const cudaMemcpyKind kind = resident ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  const long long before = tl_launch_count;
+  for (int64_t r0 = 0; r0 < n_rows; r0 += B) {
+    // rows are independent in inference mode: a partial tail leaves the rest of the batch buffers as they were
+    const int64_t nv = std::min<int64_t>(B, n_rows - r0);
+    SB_CUDA(cudaMemcpyAsync(e->acts[0], x + r0 * e->x_per_row, (size_t)(nv * e->x_per_row) * 4, kind, e->stream));
+    SB_CUDA(cudaMemcpyAsync(e->by, y + r0 * e->y_per_row, (size_t)(nv * e->y_per_row) * 4, kind, e->stream));
+    run_forward(e, FWD_INFER);
+    estimator_accumulate(e->acts[e->L.back().buf_out], e->by, nv, C, estimator, e->est_acc, e->stream);
+  }
+  e->launches += tl_launch_count - before;
+  SB_CUDA(cudaMemcpyAsync(out, e->est_acc, 4 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
   SB_CUDA(cudaStreamSynchronize(e->stream));
   SB_API_END
 }

@@ -116,6 +116,7 @@ struct sb_engine {
   sb::StepState* st = nullptr;
   sb::StepState* st_host = nullptr;  // pinned mirror
   float* ws = nullptr;
+  double* est_acc = nullptr;      // 4 running sums of sb_estimate
   float* head_scratch = nullptr;  // per-CTA partials + completion ticket of the fused classifier-head kernel
   size_t ws_floats = 0;
   cudaStream_t stream = nullptr;

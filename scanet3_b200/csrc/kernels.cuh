@@ -82,6 +82,12 @@ void bn_bwd(const float* x, const float* dy, float* dx, const float* gamma, cons
 void reg_penalty_grad(const float* w, float* g, long long n, int kind, float lambda, StepState* st, int first, int last,
                       cudaStream_t s);
 
+// estimators (estimators/package.scala:18-137) over one forwarded batch: pred,y [rows,C]; acc[4] (doubles) accumulates
+//   kind 0 accuracy : acc[0] += rows where rint(pred) == y on every output
+//   kind 1/2 squared / absolute error : acc[0] += sum (pred-y)^2 | |pred-y|
+//   kind 3 R2 (C == 1): acc[0] += (pred-y)^2, acc[2] += pred, acc[3] += pred^2 ; acc[1] += rows always
+void estimator_accumulate(const float* pred, const float* y, long long rows, int C, int kind, double* acc, cudaStream_t s);
+
 // fused multi-tensor optimizer over the flat arena: w,g,state regions of n floats each
 void optimizer_step(const OptDesc& o, float* w, const float* g, float* s0, float* s1, float* s2, long long n,
                     StepState* st, int advance_batch, cudaStream_t s);

@@ -971,6 +971,52 @@ void reg_penalty_grad(const float* w, float* g, long long n, int kind, float lam
 }
 
 // =================================================================================================
+// estimators (estimators/package.scala:18-137): per-batch partial sums, accumulated in double on the device
+// =================================================================================================
+__global__ void __launch_bounds__(256) estimator_kernel(const float* __restrict__ pred, const float* __restrict__ y, long long rows,
+                                                        int C, int kind, double* __restrict__ acc) {
+  pdl_prologue();
+  double a0 = 0.0, a2 = 0.0, a3 = 0.0;
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
+    const float* p = pred + r * C;
+    const float* t = y + r * C;
+    if (kind == 0) {  // yPredicted = result.round ; positive when every output matches (package.scala:30-33)
+      bool all = true;
+      for (int c = 0; c < C; ++c) all = all && (rintf(p[c]) == t[c]);
+      a0 += all ? 1.0 : 0.0;
+    } else {
+      for (int c = 0; c < C; ++c) {
+        const float d = __fsub_rn(p[c], t[c]);
+        a0 += kind == 2 ? (double)fabsf(d) : (double)__fmul_rn(d, d);
+        if (kind == 3) { a2 += (double)p[c]; a3 += (double)p[c] * (double)p[c]; }
+      }
+    }
+  }
+  __shared__ double sh[3][8];
+  for (int o = 16; o; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sh[0][w] = a0; sh[1][w] = a2; sh[2][w] = a3; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s0 = 0, s2 = 0, s3 = 0;
+    for (int i = 0; i < 8; ++i) { s0 += sh[0][i]; s2 += sh[1][i]; s3 += sh[2][i]; }
+    atomicAdd(acc + 0, s0);
+    if (blockIdx.x == 0) atomicAdd(acc + 1, (double)rows);
+    if (kind == 3) { atomicAdd(acc + 2, s2); atomicAdd(acc + 3, s3); }
+  }
+}
+void estimator_accumulate(const float* pred, const float* y, long long rows, int C, int kind, double* acc, cudaStream_t s) {
+  if (rows <= 0) return;
+  const int grid = (int)std::min<long long>((rows + 255) / 256, 148 * 4);
+  launch_k(estimator_kernel, grid, 256, 0, s, pred, y, rows, C, kind, acc);
+  SB_LAUNCHED();
+}
+
+// =================================================================================================
 // fused multi-tensor optimizer over the flat arena (optimizers/*.scala; caller does w - delta,
 // Optimizer.scala:186).  28 B/param for Adam: reads w,g,m,v ; writes w,m,v.
 // =================================================================================================

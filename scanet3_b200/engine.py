@@ -1,5 +1,6 @@
 """Thin object wrapper over the C ABI (one `Engine` = one worker = one GPU)."""
 import ctypes as C
+import os
 from collections import OrderedDict
 from typing import Dict, Optional, Sequence, Tuple
 
@@ -171,6 +172,38 @@ class Engine:
         N.check(self._lib.sb_eval_loss(self._h, x.ctypes.data, y.ctypes.data, C.byref(loss)))
         return loss.value
 
+    # ---- wire format / checkpoint (optimizers/KryoSerializers.scala:27-63 layout per tensor) ----
+    def param_to_wire(self, path: str) -> bytes:
+        n = C.c_size_t()
+        N.check(self._lib.sb_param_to_wire(self._h, self._np(path), None, 0, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        N.check(self._lib.sb_param_to_wire(self._h, self._np(path), buf, n.value, C.byref(n)))
+        return buf.raw[:n.value]
+
+    def param_from_wire(self, path: str, record: bytes) -> int:
+        used = C.c_size_t()
+        N.check(self._lib.sb_param_from_wire(self._h, self._np(path), record, len(record), C.byref(used)))
+        return used.value
+
+    def save_checkpoint(self, file: str, global_iter: int, epoch: int = 0):
+        N.check(self._lib.sb_checkpoint_save(self._h, os.fsencode(file), int(global_iter), int(epoch)))
+
+    def load_checkpoint(self, file: str) -> Tuple[int, int]:
+        """-> (global_iter, epoch) ; every tensor of the arena is restored"""
+        it, ep = C.c_int64(), C.c_int64()
+        N.check(self._lib.sb_checkpoint_load(self._h, os.fsencode(file), C.byref(it), C.byref(ep)))
+        return it.value, ep.value
+
+    def estimate(self, kind: int, x=None, y=None, rows: int = 0) -> Tuple[float, float, float, float]:
+        """Device-side estimator sums (`sb_estimate`): host buffers, or the resident shard when x is None."""
+        out = (C.c_double * 4)()
+        if x is None:
+            N.check(self._lib.sb_estimate(self._h, int(kind), None, None, int(rows), out))
+        else:
+            x, y = _f32(x), _f32(y)
+            N.check(self._lib.sb_estimate(self._h, int(kind), x.ctypes.data, y.ctypes.data, int(x.shape[0]), out))
+        return tuple(out)
+
     def predict(self, x) -> np.ndarray:
         x = _f32(x)
         out = np.empty(self.output_shape, np.float32)
@@ -252,6 +285,30 @@ class Engine:
 
     def launch_count(self) -> int:
         return int(self._lib.sb_launch_count(self._h))
+
+
+def wire_encode(t) -> bytes:
+    """One `TensorSerializer.write` record of an fp32 array (KryoSerializers.scala:33-49)."""
+    t = np.array(t, dtype=np.float32, order="C")  # keeps rank 0 (ascontiguousarray would promote a scalar to rank 1)
+    dims = (C.c_int64 * max(1, t.ndim))(*t.shape)
+    n = C.c_size_t()
+    lib = N.lib()
+    N.check(lib.sb_wire_encode(dims, t.ndim, None, None, 0, C.byref(n)))
+    buf = C.create_string_buffer(n.value)
+    N.check(lib.sb_wire_encode(dims, t.ndim, t.ctypes.data, buf, n.value, C.byref(n)))
+    return buf.raw[:n.value]
+
+
+def wire_decode(record: bytes):
+    """-> (array, bytes consumed) ; the inverse of `wire_encode` (`TensorSerializer.read`, KryoSerializers.scala:51-64)."""
+    lib = N.lib()
+    dims = (C.c_int64 * 8)()
+    rank, used = C.c_int32(), C.c_size_t()
+    N.check(lib.sb_wire_decode(record, len(record), dims, 8, C.byref(rank), None, 0, C.byref(used)))
+    shape = tuple(dims[i] for i in range(rank.value))
+    out = np.empty(shape, np.float32)
+    N.check(lib.sb_wire_decode(record, len(record), dims, 8, C.byref(rank), out.ctypes.data, out.size, C.byref(used)))
+    return out, used.value
 
 
 def spark_chain_weights(k: int):

@@ -140,6 +140,17 @@ class RecordAccuracy:
             events.append(f"accuracy: {a}")
 
 
+class SaveCheckpoint:
+    """Effect: write the averaged arena (weights, layer state, optimizer state) + `Step` to `file` (atomic rename).  The
+    reference has no checkpointing (README.md:112); tensors use its Kryo `TensorSerializer` layout (KryoSerializers.scala:27-63)."""
+
+    def __init__(self, file: str):
+        self.file = file
+
+    def __call__(self, events, ctx):
+        ctx.engine.save_checkpoint(self.file, ctx.step.iter, ctx.step.epoch)
+
+
 # ---- models (models/Model.scala:84-187) ------------------------------------------------------------------------------
 @dataclass(frozen=True)
 class LossModel:
@@ -179,12 +190,38 @@ class TrainedModel:
         return self._engine.output_shape
 
 
+# ---- estimators (estimators/package.scala:18-137): forward + reduction on the device (`sb_estimate`) ---------------------
+# `batch` is accepted for signature parity; the engine forwards in batches of its compiled size (rows are independent).
 def accuracy(model: TrainedModel, ds: Dataset, batch: int = 1000) -> float:
     """estimators/package.scala:18-43: a row is positive when round(prediction) == label on every output."""
-    pred = np.round(model.result(ds.features))
-    lab = ds.labels.reshape(pred.shape)
-    pos = np.sum(np.all(pred == lab, axis=tuple(range(1, pred.ndim))))
-    return float(pos) / float(len(ds))
+    pos, total, _, _ = model._engine.estimate(N.EST_ACCURACY, ds.features, ds.labels)
+    return float(np.float32(pos) / np.float32(total))
+
+
+def MSE(model: TrainedModel, ds: Dataset, batch: int = 1000) -> float:
+    """estimators/package.scala:51-57: sum of squared errors over all outputs / rows."""
+    s, total, _, _ = model._engine.estimate(N.EST_SQUARED_ERROR, ds.features, ds.labels)
+    return float(np.float32(s) / np.float32(total))
+
+
+def RMSE(model: TrainedModel, ds: Dataset, batch: int = 1000) -> float:
+    """estimators/package.scala:45-49."""
+    return float(np.float32(np.sqrt(MSE(model, ds, batch))))
+
+
+def MAE(model: TrainedModel, ds: Dataset, batch: int = 1000) -> float:
+    """estimators/package.scala:59-65."""
+    s, total, _, _ = model._engine.estimate(N.EST_ABS_ERROR, ds.features, ds.labels)
+    return float(np.float32(s) / np.float32(total))
+
+
+def R2Score(model: TrainedModel, ds: Dataset, batch: int = 1000) -> float:
+    """estimators/package.scala:99-137; SST is centred on the mean of the PREDICTIONS, as the reference does (:124)."""
+    if tuple(np.shape(ds.labels)[1:]) not in ((1,), ()):
+        raise ValueError("requirement failed: labels should have shape (1)")
+    ssr, n, sp, sp2 = model._engine.estimate(N.EST_R2, ds.features, ds.labels)
+    sst = sp2 - sp * sp / n
+    return float(np.float32(1.0 - ssr / sst))
 
 
 # ---- builder (Optimizer.scala:267-338) ---------------------------------------------------------------------------
@@ -206,6 +243,7 @@ class _Config:
     devices: Optional[tuple] = None
     use_graph: bool = True
     quiet: bool = False
+    resume: Optional[str] = None
 
 
 class Builder:
@@ -261,6 +299,10 @@ class Builder:
     def graph(self, on: bool):
         return self._with(use_graph=bool(on))
 
+    def resumeFrom(self, file: str):
+        """continue from a `SaveCheckpoint` file: params, optimizer state, iteration and epoch counters"""
+        return self._with(resume=str(file))
+
     def quiet(self, on: bool = True):
         return self._with(quiet=bool(on))
 
@@ -304,9 +346,14 @@ class Optimizer:
         group = Group(engines, c.avg_mode, collective=c.collective) if k > 1 else None
         pool = ThreadPoolExecutor(max_workers=k) if k > 1 else None
         try:
+            step = Step(c.batchSize)
             for i, e in enumerate(engines):
                 x, y = ds.shard(i, k)
                 e.upload_dataset(x, y)
+                if c.resume is not None:  # every worker restarts from the same averaged arena
+                    it, ep = e.load_checkpoint(c.resume)
+                    step = Step(c.batchSize, ep, it)
+                    continue
                 # epoch 0: every partition initialises (Optimizer.scala:123-131); seeded => identical starts
                 init = c.initParams() if c.initParams is not None else None
                 if init is not None:
@@ -317,7 +364,6 @@ class Optimizer:
                     e.init_opt_params()
                 else:
                     e.init_params()
-            step = Step(c.batchSize)
             while True:
                 start = time.time()
                 if pool is None:

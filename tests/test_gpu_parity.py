@@ -471,3 +471,96 @@ def test_fast_kernel_geometries_match_the_oracle(gid, spec, batch, in_shape, cla
         np.testing.assert_allclose(gg[k], v, rtol=2e-4, atol=2e-6, err_msg=k)
     np.testing.assert_allclose(e.predict(x), O.model_forward(om, x, mp)[0], rtol=2e-5, atol=2e-6)
     e.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# estimators on the device (estimators/package.scala:18-137)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows", [64, 150, 37])  # whole batches, a partial tail (`remaining = Partial`), less than one batch
+def test_device_estimators_match_the_oracle_classifier(rows):
+    spec = [("dense", 16, "sigmoid"), ("dense", 4, "softmax")]
+    om, sm = build_models(spec)
+    x, y = synth_classification(rows, (12,), 4, seed=5)
+    e = make_engine(sm, S.CategoricalCrossentropy, S.Adam(0.05), 32, (12,), (4,))
+    _, mp, _ = oracle_init(om, O.Adam(rate=0.05), (32, 12))
+    e.set_params(mp)
+    e.init_opt_params()
+    # train a little on full batches so that predictions are not all on one side of 0.5
+    xt, yt = synth_classification(32 * 20, (12,), 4, seed=6)
+    for t in range(20):
+        e.train_step(xt[t * 32:(t + 1) * 32], yt[t * 32:(t + 1) * 32], t + 1)
+    params = e.get_model_params()
+    trained = S.TrainedModel(S.LossModel(sm, S.CategoricalCrossentropy), params, e)
+    ds = S.Dataset(x, y)
+    # counts are exact as long as no prediction sits within rounding noise of .5; the oracle runs on the ENGINE's weights
+    assert S.accuracy(trained, ds) == O.estimators.accuracy(om, params, x, y, batch=32)
+    np.testing.assert_allclose(S.MSE(trained, ds), O.estimators.mse(om, params, x, y, batch=32), rtol=2e-5)
+    np.testing.assert_allclose(S.RMSE(trained, ds), O.estimators.rmse(om, params, x, y, batch=32), rtol=2e-5)
+    np.testing.assert_allclose(S.MAE(trained, ds), O.estimators.mae(om, params, x, y, batch=32), rtol=2e-5)
+    # resident-shard variant gives the same sums as the host-buffer variant
+    if rows >= 32:
+        e.upload_dataset(x, y)
+        assert e.estimate(S.native.EST_ACCURACY) == e.estimate(S.native.EST_ACCURACY, x, y)
+        a, b = e.estimate(S.native.EST_SQUARED_ERROR), e.estimate(S.native.EST_SQUARED_ERROR, x, y)
+        np.testing.assert_allclose(a, b, rtol=1e-12)
+    e.close()
+
+
+def test_device_r2_score_matches_the_oracle(fixtures_dir):  # estimators/package.scala:99-137, labels of shape (1)
+    ds = _linear(fixtures_dir)
+    trained = (ds.train(S.LinearRegression()).loss(S.MeanSquaredError).using(S.Adam(rate=0.1)).batch(97)
+               .stopAfter(S.epochs(30)).quiet().run())
+    om = O.Dense(1, O.Identity, kernel_initializer=O.Zeros)
+    want = O.estimators.r2_score(om, trained.params, ds.features, ds.labels, batch=97)
+    np.testing.assert_allclose(S.R2Score(trained, ds), want, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(S.MSE(trained, ds), O.estimators.mse(om, trained.params, ds.features, ds.labels, batch=97),
+                               rtol=2e-5)
+    with pytest.raises(ValueError):  # `require(ds.labelsShape == Shape(1))`
+        S.R2Score(trained, S.Dataset(ds.features, np.concatenate([ds.labels, ds.labels], axis=1)))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# wire format + checkpoint / resume (optimizers/KryoSerializers.scala:27-63)
+# ---------------------------------------------------------------------------------------------------------------
+def test_param_wire_records_round_trip_through_the_device():
+    from oracle import wire as W
+    spec = [("conv", 4, "relu", (3, 3), (1, 1), "Valid", True), ("flatten",), ("dense", 3, "softmax")]
+    _, sm = build_models(spec)
+    e = make_engine(sm, S.CategoricalCrossentropy, S.Adam(0.01), 8, (6, 6, 2), (3,))
+    e.init_params()
+    for path, t in e.get_params().items():
+        rec = e.param_to_wire(path)
+        assert rec == W.tensor_write(t), path       # TensorSerializer.write layout, byte for byte
+        e.set_param(path, np.zeros_like(t))
+        assert e.param_from_wire(path, rec) == len(rec)
+        assert np.array_equal(e.get_param(path), t)
+    w = next(iter(e.get_params()))
+    with pytest.raises(S.native.IllegalArgument):   # a record of another shape is refused
+        e.param_from_wire(w, W.tensor_write(np.zeros((2, 2), np.float32)))
+    e.close()
+
+
+@pytest.mark.parametrize("k", [1, 2])
+def test_checkpoint_resume_continues_bit_identically(tmp_path, k):
+    spec = [("dense", 24, "tanh"), ("bn", 0.9, 0), ("dense", 5, "softmax")]
+    x, y = synth_classification(64 * 4 * k, (10,), 5, seed=11)
+
+    def builder():
+        _, sm = build_models(spec)
+        return (S.Dataset(x, y, partitions=k).train(sm).loss(S.CategoricalCrossentropy).using(S.Adam(0.02)).batch(64)
+                .devices([0] * k).quiet())
+
+    rec_full = S.RecordLoss(console=False)
+    full = builder().each(S.epochs(1), rec_full).stopAfter(S.epochs(6)).run()
+    ck = str(tmp_path / "model.sb3")
+    rec_a, rec_b = S.RecordLoss(console=False), S.RecordLoss(console=False)
+    builder().each(S.epochs(1), rec_a).each(S.epochs(3), S.SaveCheckpoint(ck)).stopAfter(S.epochs(4)).run()
+    # the file was last written at epoch 3; a fresh process-equivalent resumes there and runs to epoch 6
+    resumed = builder().resumeFrom(ck).each(S.epochs(1), rec_b).stopAfter(S.epochs(6)).run()
+    assert rec_a.history[:3] + rec_b.history == rec_full.history
+    for p, t in full.params.items():
+        assert np.array_equal(resumed.params[p], t), p
+    with pytest.raises(S.native.IllegalArgument):   # a checkpoint of another model is refused
+        _, other = build_models([("dense", 5, "softmax")])
+        (S.Dataset(x, y).train(other).loss(S.CategoricalCrossentropy).using(S.Adam(0.02)).batch(64).resumeFrom(ck)
+         .stopAfter(S.epochs(1)).quiet().run())

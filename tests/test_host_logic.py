@@ -189,3 +189,34 @@ print("RANK_OK", rank)
     outs = [p.communicate(timeout=240)[0].decode() for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"RANK_OK {r}" in o, o
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# parameter wire format (optimizers/KryoSerializers.scala:27-63): host-only entry points, no GPU needed
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(), (1,), (5,), (3, 4), (2, 3, 1, 5), (0, 7)])
+def test_wire_records_match_the_kryo_layout(shape):
+    from oracle import wire as W
+    rng = np.random.default_rng(3)
+    t = rng.standard_normal(shape).astype(np.float32)
+    rec = S.wire_encode(t)
+    assert rec == W.tensor_write(t)                      # byte for byte what TensorSerializer.write emits
+    assert rec[:8] == bytes([0, 0, 0, 1, 0, 0, 0, len(shape)])  # big-endian type code DT_FLOAT, rank
+    back, used = S.wire_decode(rec + b"trailing")
+    assert used == len(rec) and back.shape == t.shape and np.array_equal(back, t)
+    want, used2 = W.tensor_read(rec)
+    assert used2 == len(rec) and np.array_equal(want, t)
+
+
+def test_wire_decode_rejects_malformed_records():
+    rec = S.wire_encode(np.arange(6, dtype=np.float32).reshape(2, 3))
+    with pytest.raises(N.IllegalArgument):
+        S.wire_decode(rec[:-1])                          # truncated payload
+    with pytest.raises(N.IllegalArgument):
+        S.wire_decode(rec[:10])                          # truncated header
+    bad = bytearray(rec); bad[3] = 2                     # DT_DOUBLE
+    with pytest.raises(N.Unsupported):
+        S.wire_decode(bytes(bad))
+    bad = bytearray(rec); bad[27] = 20                   # payload size disagrees with the shape
+    with pytest.raises(N.IllegalArgument):
+        S.wire_decode(bytes(bad))

@@ -422,3 +422,21 @@ def test_torch_port_matches_numpy_oracle():
     got = port.params_numpy()
     for k, v in mp.items():  # a sign flip of a near-zero gradient moves a weight by one Adam step (1e-3)
         assert float(np.max(np.abs(got[k] - v))) <= 3e-3 and float(np.mean(np.abs(got[k] - v))) <= 5e-5, k
+
+
+def test_estimators_hand_computed():  # estimators/package.scala:18-137 on y = 2x with one label off by one
+    om = O.Dense(1, O.Identity, kernel_initializer=O.Zeros)
+    defs = O.model_params(om, (2, 1))
+    params = {k: (np.full(d.shape, 2.0, np.float32) if len(d.shape) == 2 else np.zeros(d.shape, np.float32))
+              for k, d in defs.items()}
+    x = np.array([[1], [2], [3]], np.float32)
+    y = np.array([[2], [4], [7]], np.float32)  # predictions 2, 4, 6
+    E = O.estimators
+    assert E.accuracy(om, params, x, y, batch=2) == pytest.approx(2 / 3, rel=1e-6)   # tail batch is partial, not dropped
+    assert E.mse(om, params, x, y, batch=2) == pytest.approx(1 / 3, rel=1e-6)
+    assert E.mae(om, params, x, y, batch=2) == pytest.approx(1 / 3, rel=1e-6)
+    assert E.rmse(om, params, x, y, batch=2) == pytest.approx(np.sqrt(1 / 3), rel=1e-6)
+    # SST is centred on the mean PREDICTION (4): sst = 8, ssr = 1
+    assert E.r2_score(om, params, x, y, batch=2) == pytest.approx(0.875, rel=1e-6)
+    with pytest.raises(ValueError):
+        E.r2_score(om, params, x, np.concatenate([y, y], axis=1))
