@@ -263,10 +263,14 @@ struct HaloParams {
   float thr;
   float* out;          // [n_img, Hg, Wg, N]
   int tma_store;       // epilogue through swizzled shared staging + TMA stores (one box per grid row and 32-channel chunk)
+  int early_filter;    // load the filter before the programmatic-dependency wait (SB_TC_EARLY_FILTER=0 turns it off)
   long long* dbg;      // developer timeline (SB_TC_DEBUG=1): 64 clock64 slots per CTA, null in production
   int bo_mode;         // debug: 1 = also encode the start row's swizzle phase in the descriptor's base-offset field
 };
 
+// TKH/TKW/TKC: compile-time KH, KW and Cin/32 (0 = from the parameters): runtime trip counts in the MMA issue loop cost far more
+// than the MMAs themselves (profiles/r1_notes.md item 11)
+template <int TKH, int TKW, int TKC>
 __global__ void __launch_bounds__(kIgemmThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_c, const HaloParams p) {
@@ -314,23 +318,29 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();  // the on-chip setup above overlapped the previous kernel; global memory from here on
+  // The filter is only ever written by the optimizer / averaging / host uploads, never by the kernel right before this one (a
+  // batch-gather or an activation kernel always sits in between, and that kernel itself waited for its predecessors), so its
+  // load may start before the programmatic-dependency wait and overlap the previous kernel's tail.
+  auto load_filter = [&]() {
+    mbar_arrive_expect_tx(b_bar, (uint32_t)b_bytes);
+    for (int tap = 0; tap < taps; ++tap)
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        uint8_t* sb = sm_b + (size_t)(tap * p.kchunks + kc) * b_tile_bytes;
+        if (p.b_mn_major) {
+          for (int j = 0; j < p.N / 32; ++j) tma_load_2d(sb + j * 4096, &map_b, b_bar, j * 32, tap * p.b_rows_per_tap + kc * 32);
+        } else {
+          tma_load_2d(sb, &map_b, b_bar, kc * 32, tap * p.b_rows_per_tap);
+        }
+      }
+  };
+  if (threadIdx.x == 0 && p.early_filter) load_filter();
+  pdl_wait();  // the on-chip setup above overlapped the previous kernel; activations in global memory from here on
   if (threadIdx.x == 0) HALO_T(1);
 
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
-      // the filter, once
-      mbar_arrive_expect_tx(b_bar, (uint32_t)b_bytes);
-      for (int tap = 0; tap < taps; ++tap)
-        for (int kc = 0; kc < p.kchunks; ++kc) {
-          uint8_t* sb = sm_b + (size_t)(tap * p.kchunks + kc) * b_tile_bytes;
-          if (p.b_mn_major) {
-            for (int j = 0; j < p.N / 32; ++j) tma_load_2d(sb + j * 4096, &map_b, b_bar, j * 32, tap * p.b_rows_per_tap + kc * 32);
-          } else {
-            tma_load_2d(sb, &map_b, b_bar, kc * 32, tap * p.b_rows_per_tap);
-          }
-        }
+      if (!p.early_filter) load_filter();  // the filter, once
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -353,7 +363,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const uint32_t b_ks_step = p.b_mn_major ? (1024u >> 4) : (32u >> 4);
       const uint32_t sb0 = b_lo0 + (smem_u32(sm_b) >> 4);
       const uint32_t a_chunk = (uint32_t)(p.a_tile_bytes >> 4), b_chunk = (uint32_t)(b_tile_bytes >> 4);
-      const int KH = p.KH, KW = p.KW, kchunks = p.kchunks, P8 = p.P * 8;
+      const int KH = TKH ? TKH : p.KH, KW = TKW ? TKW : p.KW, kchunks = TKC ? TKC : p.kchunks, P8 = p.P * 8;
       mbar_wait(b_bar, 0);
       tc_fence_after();
       if (lane == 0) HALO_T(2);
@@ -374,10 +384,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // tap (kh,kw) reads source rows shifted by (dh*P + dw) pixels = 8 descriptor units (128 B >> 4) each
         uint32_t row_at = sa0 + (p.flip ? (uint32_t)((KH - 1) * P8 + (KW - 1) * 8) : 0u);
         const int32_t step_w = p.flip ? -8 : 8, step_h = p.flip ? -P8 : P8;
+#pragma unroll
         for (int kh = 0; kh < KH; ++kh, row_at += step_h) {
           uint32_t at_tap = row_at;
+#pragma unroll
           for (int kw = 0; kw < KW; ++kw, at_tap += step_w) {
             uint32_t at = at_tap;
+#pragma unroll
             for (int kc = 0; kc < kchunks; ++kc, at += a_chunk, bt += b_chunk) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {  // 4 x (K = 8 tf32) per 32-channel chunk
@@ -481,6 +494,7 @@ struct WgradParams {
   int pt, pl;      // padding before: tap (kh,kw) pairs dY(oh,ow) with X(oh + kh - pt, ow + kw - pl); OOB pixels are zero-filled
   int stages;
   float* partial;  // [gridDim.x][taps*Cin*Cout]
+  long long* dbg;  // developer timeline (SB_TC_DEBUG=1): 64 clock64 slots per CTA, null in production
 };
 constexpr int kWgradThreads = 192;
 
@@ -488,6 +502,9 @@ __global__ void __launch_bounds__(kWgradThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, const WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 64 : nullptr;
+#define WG_T(slot) do { if (dbg) dbg[slot] = clock64(); } while (0)
+  if (threadIdx.x == 0) WG_T(0);
   const int taps = p.nt;  // taps of this launch
   const int krows = p.BH * p.WK;            // K rows per chunk (multiple of 8)
   const int box_bytes = krows * 128;        // one 32-channel box
@@ -518,7 +535,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) WG_T(1);
   pdl_wait();  // the on-chip setup above overlapped the previous kernel; global memory from here on
+  if (threadIdx.x == 0) WG_T(2);
   const bool has_work = (int)blockIdx.x < p.n_chunks;
 
   if (warp == 0) {
@@ -550,9 +569,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       uint32_t accumulate = 0;
-      for (int ch = blockIdx.x; ch < p.n_chunks; ch += gridDim.x) {
+      int ti = 0;
+      for (int ch = blockIdx.x; ch < p.n_chunks; ch += gridDim.x, ++ti) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
+        if (lane == 0 && ti < 12) WG_T(8 + 2 * ti);
         const uint32_t sa = d_lo + (smem_u32(smem + (size_t)stage * stage_bytes) >> 4);
         uint32_t sb = sa + (uint32_t)(a_bytes >> 4);
         for (int t = 0; t < taps; ++t, sb += b_tap) {
@@ -565,6 +586,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
         }
         accumulate = 1;
         umma_commit_elect(&empty_bar[stage]);
+        if (lane == 0 && ti < 12) WG_T(9 + 2 * ti);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
       umma_commit_elect(done_bar);
@@ -580,6 +602,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
       mbar_wait(done_bar, 0);
       tc_fence_after();
     }
+    if (threadIdx.x == 64) WG_T(3);
     for (int c0 = 0; c0 < ncols; c0 += 32) {
       float v[32];
       if (has_work) {
@@ -594,13 +617,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
         for (int j = 0; j < 32; ++j) part[(size_t)(c0 + j) * p.Cout + co] = v[j];
       }
     }
+    if (threadIdx.x == 64) WG_T(4);
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) WG_T(5);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
+#undef WG_T
 }
 
 
@@ -623,13 +649,21 @@ struct WgradHaloParams {
   int x_box_bytes, dy_box_bytes;
   int stages;
   float* partial;       // [gridDim.x][KH*KW*Cin*Cout]
+  long long* dbg;       // developer timeline (SB_TC_DEBUG=1)
+  int dbg_mode;         // developer experiment (SB_WG_EXPERIMENT): 1 = no TMA after the first fill of every stage (wrong results)
 };
 
+// TKH / TCIS: compile-time KH and Cin/32 (0 = read them from the parameters) so that the MMA issue loop is fully unrolled
+template <int TKH, int TCIS>
 __global__ void __launch_bounds__(kWgradThreads, 1)
 conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, const WgradHaloParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const int co_slices = p.Cout / 32, ci_slices = p.Cin / 32;
+  long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 64 : nullptr;
+#define WG_T(slot) do { if (dbg) dbg[slot] = clock64(); } while (0)
+  if (threadIdx.x == 0) WG_T(0);
+  const int KH = TKH ? TKH : p.KH;
+  const int co_slices = p.Cout / 32, ci_slices = TCIS ? TCIS : p.Cin / 32;
   const int a_bytes = ci_slices * p.x_tile_bytes, b_bytes = co_slices * p.dy_tile_bytes;
   const int stage_bytes = a_bytes + b_bytes;
   uint64_t* full_bar = (uint64_t*)(smem + (size_t)p.stages * stage_bytes);
@@ -637,7 +671,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
   uint64_t* done_bar = empty_bar + p.stages;
   uint32_t* tmem_slot = (uint32_t*)(done_bar + 1);
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
-  const int n_acc = p.KH * ci_slices;
+  const int n_acc = KH * ci_slices;
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < n_acc * p.Cout) tmem_cols <<= 1;
 
@@ -663,7 +697,9 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) WG_T(1);
   pdl_wait();  // the on-chip setup above overlapped the previous kernel; global memory from here on
+  if (threadIdx.x == 0) WG_T(2);
   const bool has_work = (int)blockIdx.x < p.n_chunks;
 
   if (warp == 0) {
@@ -675,9 +711,13 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + (size_t)stage * stage_bytes;
         uint8_t* sb = sa + a_bytes;
-        mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(ci_slices * p.x_box_bytes + co_slices * p.dy_box_bytes));
-        for (int j = 0; j < ci_slices; ++j) tma_load_4d(sa + (size_t)j * p.x_tile_bytes, &map_x, &full_bar[stage], j * 32, p.ox, h0 + p.oy, img);
-        for (int j = 0; j < co_slices; ++j) tma_load_4d(sb + (size_t)j * p.dy_tile_bytes, &map_dy, &full_bar[stage], j * 32, 0, h0, img);
+        if (p.dbg_mode == 1 && ch >= (int)blockIdx.x + p.stages * (int)gridDim.x) {
+          mbar_arrive(&full_bar[stage]);
+        } else {
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(ci_slices * p.x_box_bytes + co_slices * p.dy_box_bytes));
+          for (int j = 0; j < ci_slices; ++j) tma_load_4d(sa + (size_t)j * p.x_tile_bytes, &map_x, &full_bar[stage], j * 32, p.ox, h0 + p.oy, img);
+          for (int j = 0; j < co_slices; ++j) tma_load_4d(sb + (size_t)j * p.dy_tile_bytes, &map_dy, &full_bar[stage], j * 32, 0, h0, img);
+        }
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -690,25 +730,33 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
       const uint32_t a_hi = (uint32_t)(a_d >> 32), a_lo0 = (uint32_t)a_d, b_hi = (uint32_t)(b_d >> 32), b_lo0 = (uint32_t)b_d;
       const int nks = p.BH * p.P / 8;
       const uint32_t kh_step = (uint32_t)(p.P * 128) >> 4, x_tile = (uint32_t)p.x_tile_bytes >> 4;
+      // the TMEM base came through shared memory into a vector register: the shuffle makes it provably uniform, so the
+      // accumulator addresses stay in uniform registers (otherwise every MMA pays a VIADD + R2UR: 118 vs 48 cycles per MMA)
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t accumulate = 0;
-      for (int ch = blockIdx.x; ch < p.n_chunks; ch += gridDim.x) {
+      int ti = 0;
+      for (int ch = blockIdx.x; ch < p.n_chunks; ch += gridDim.x, ++ti) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
+        if (lane == 0 && ti < 12) WG_T(8 + 2 * ti);
         const uint32_t sa = a_lo0 + (smem_u32(smem + (size_t)stage * stage_bytes) >> 4);
         const uint32_t sb = b_lo0 + ((smem_u32(smem + (size_t)stage * stage_bytes) + (uint32_t)a_bytes) >> 4);
         for (int ks = 0; ks < nks; ++ks) {
-          uint32_t d_col = 0;
+          uint32_t d_tmem = tmem_u;
           uint32_t at_kh = sa + ks * 64;
-          for (int kh = 0; kh < p.KH; ++kh, at_kh += kh_step) {
+#pragma unroll
+          for (int kh = 0; kh < KH; ++kh, at_kh += kh_step) {
             uint32_t at = at_kh;
-            for (int j = 0; j < ci_slices; ++j, at += x_tile, d_col += p.Cout)
-              umma_tf32_elect(tmem_base + d_col, ((uint64_t)a_hi << 32) | at, ((uint64_t)b_hi << 32) | (sb + ks * 64), idesc, accumulate);
+#pragma unroll
+            for (int j = 0; j < ci_slices; ++j, at += x_tile, d_tmem += p.Cout)
+              umma_tf32_elect(d_tmem, ((uint64_t)a_hi << 32) | at, ((uint64_t)b_hi << 32) | (sb + ks * 64), idesc, accumulate);
           }
           accumulate = 1;
         }
         umma_commit_elect(&empty_bar[stage]);
+        if (lane == 0 && ti < 12) WG_T(9 + 2 * ti);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
       umma_commit_elect(done_bar);
@@ -721,9 +769,17 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
       mbar_wait(done_bar, 0);
       tc_fence_after();
     }
+    if (threadIdx.x == 64) WG_T(3);
+    // This warp's 32 rows (one kw, 32 ci) of accumulator a are ONE contiguous 32 x Cout block of the partial.  Each lane holds a
+    // row: transpose through a padded scratch (the pipeline stages are idle once done_bar fired; row pitch Cout + 4 floats keeps
+    // both the 128-bit row writes and the 128-bit line reads conflict-free) and store whole 512-byte pieces.
+    const int pitch = p.Cout + 4;
+    const uint32_t scratch = smem_u32(smem) + (uint32_t)(sub * 32 * pitch * 4);
+    const int f4_per_row = p.Cout / 4;            // Cout % 32 == 0
+    const int rows_per_it = 32 / f4_per_row > 0 ? 32 / f4_per_row : 1;
     for (int a = 0; a < n_acc; ++a) {
       const int kh = a / ci_slices, j = a - kh * ci_slices;
-      float* row = part + ((size_t)((kh * p.KW + sub) * p.Cin + j * 32 + lane)) * p.Cout;
+      float* blk = part + ((size_t)((kh * p.KW + sub) * p.Cin + j * 32)) * p.Cout;
       for (int c0 = 0; c0 < p.Cout; c0 += 32) {
         float v[32];
         if (has_work) {
@@ -733,19 +789,51 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
 #pragma unroll
           for (int q = 0; q < 32; ++q) v[q] = 0.f;
         }
-        if (sub < p.KW) {
+        const uint32_t dst = scratch + (uint32_t)((lane * pitch + c0) * 4);
 #pragma unroll
-          for (int q = 0; q < 32; q += 4) *reinterpret_cast<float4*>(row + c0 + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+        for (int q = 0; q < 32; q += 4)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + q * 4), "f"(v[q]), "f"(v[q + 1]), "f"(v[q + 2]), "f"(v[q + 3]) : "memory");
+      }
+      __syncwarp();
+      if (sub < p.KW) {
+        if (f4_per_row <= 32) {
+          const int rr = lane / f4_per_row, cc = lane - rr * f4_per_row;
+          for (int r0 = 0; r0 < 32; r0 += 4 * rows_per_it) {
+            float4 t[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int r = r0 + u * rows_per_it + rr;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t[u].x), "=f"(t[u].y), "=f"(t[u].z), "=f"(t[u].w)
+                           : "r"(scratch + (uint32_t)((r * pitch + cc * 4) * 4)));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int r = r0 + u * rows_per_it + rr;
+              *reinterpret_cast<float4*>(blk + (size_t)r * p.Cout + cc * 4) = t[u];
+            }
+          }
+        } else {
+          for (int r = 0; r < 32; ++r)
+            for (int c = lane; c < f4_per_row; c += 32) {
+              float4 t;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                           : "r"(scratch + (uint32_t)((r * pitch + c * 4) * 4)));
+              *reinterpret_cast<float4*>(blk + (size_t)r * p.Cout + c * 4) = t;
+            }
         }
       }
+      __syncwarp();
     }
+    if (threadIdx.x == 64) WG_T(4);
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) WG_T(5);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
+#undef WG_T
 }
 
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int n, int parts) {
@@ -825,6 +913,7 @@ static bool plan_halo(HaloParams& p, CUtensorMap* map, CUtensorMap* map_out, con
     SB_CUDA(cudaMalloc((void**)&p.dbg, (size_t)kNumSMs * 64 * sizeof(long long)));
     SB_CUDA(cudaMemset(p.dbg, 0, (size_t)kNumSMs * 64 * sizeof(long long)));
   }
+  { const char* ef = getenv("SB_TC_EARLY_FILTER"); p.early_filter = !(ef && ef[0] == '0'); }
   const char* bo = getenv("SB_TC_BASE_OFFSET");
   p.bo_mode = (bo && bo[0] == '1') ? 1 : 0;
   const int b_bytes = KH * KW * p.kchunks * Nacc * 128;
@@ -1005,6 +1094,16 @@ void tc_plan_layers(sb_engine* e) {
           P->wg_smem_list.push_back(smem);
           P->wg_smem = std::max(P->wg_smem, smem);
         }
+      {
+        const char* dbg = getenv("SB_TC_DEBUG");
+        if (dbg && dbg[0] == '1') {
+          long long* d = nullptr;
+          SB_CUDA(cudaMalloc((void**)&d, (size_t)kNumSMs * 64 * sizeof(long long)));
+          SB_CUDA(cudaMemset(d, 0, (size_t)kNumSMs * 64 * sizeof(long long)));
+          for (WgradParams& q : P->wg_list) q.dbg = d;
+          P->hwg.dbg = d;
+        }
+      }
       P->wg = P->wg_list[0];
       uint64_t yd[4] = {(uint64_t)g.Cout, (uint64_t)g.OW, (uint64_t)g.OH, (uint64_t)g.N};
       uint32_t yb[4] = {32, (uint32_t)p.WK, (uint32_t)p.BH, 1};
@@ -1014,11 +1113,11 @@ void tc_plan_layers(sb_engine* e) {
     }
     // ---- wgrad, halo form: KW <= 4 taps share one M = 128 MMA; all KH * Cin/32 accumulators must fit TMEM ----
     {
-      // Measured on B200 (profiles/r1_notes.md): with MN-major tf32 operands the MMA is bound by the operand fetch, not by
-      // the instruction count, so sharing the KW taps in one M = 128 MMA buys nothing (24.5 us vs 21.1 us for the per-tap
-      // kernel on LeNet conv2).  Kept selectable (SB_TC_HALO_WGRAD=1) and parity-tested; off by default.
+      // Default since the issue loop keeps its TMEM addresses in uniform registers and the epilogue stores whole lines: one X
+      // box per chunk instead of one per tap removes the per-tap kernel's 9x redundant L2->SMEM traffic, which is what bounds it
+      // (profiles/r1_notes.md item 8).  SB_TC_HALO_WGRAD=0 selects the per-tap kernel.
       const char* h = getenv("SB_TC_HALO_WGRAD");
-      const bool on = h && h[0] == '1';
+      const bool on = !(h && h[0] == '0');
       WgradHaloParams& p = P->hwg;
       const int n_acc = g.KH * (g.Cin / 32);
       if (on && P->wg_ok && g.KW <= 4 && n_acc * g.Cout <= 512) {
@@ -1031,8 +1130,13 @@ void tc_plan_layers(sb_engine* e) {
             const int rows_x = (BH + g.KH - 1) * Pc + g.KW - 1;
             const int stage = (g.Cin / 32) * ((rows_x + 7) / 8) * 1024 + (g.Cout / 32) * BH * Pc * 128;
             if (2 * stage + 4096 > dev_smem) continue;
+            if (4 * 32 * (g.Cout + 4) * 4 > 2 * stage) continue;  // the epilogue's transpose scratch reuses the idle stages
             const long long chunks = (long long)g.N * ((g.OH + BH - 1) / BH);
-            const double cost = (double)((chunks + kNumSMs - 1) / kNumSMs) * (BH * Pc / 8 + 6);
+            // cycles per CTA: rounds x max(MMA issue, TMA fill at ~25 B/cycle/SM with every SM pulling) + the first fill
+            // (MMA rates and the fill rate: profiles/r1_notes.md items 8)
+            const double mma = g.Cout <= 32 ? 40 : g.Cout <= 64 ? 48 : g.Cout / 2;
+            const double fill = stage / 25.0;
+            const double cost = (double)((chunks + kNumSMs - 1) / kNumSMs) * std::max((BH * Pc / 8) * n_acc * mma + 150.0, fill) + fill;
             if (cost < best) { best = cost; bP = Pc; bBH = BH; }
           }
         if (bP) {
@@ -1045,7 +1149,7 @@ void tc_plan_layers(sb_engine* e) {
           p.x_box_bytes = (p.BH + g.KH - 1) * p.P * 128;
           p.x_tile_bytes = (((p.BH + g.KH - 1) * p.P + g.KW - 1 + 7) / 8) * 1024;
           const int stage_bytes = (g.Cin / 32) * p.x_tile_bytes + (g.Cout / 32) * p.dy_tile_bytes;
-          p.stages = std::max(2, std::min(4, (dev_smem - 4096) / stage_bytes));
+          p.stages = std::max(2, std::min(6, (dev_smem - 4096) / stage_bytes));
           P->hwg_grid = (int)std::min<long long>(p.n_chunks, kNumSMs);
           P->hwg_smem = p.stages * stage_bytes + 16 * (2 * p.stages + 2) + 16 + 1024;
           if (P->hwg_smem <= dev_smem && P->hwg_grid <= P->wg_grid) {  // the partial buffer is sized for wg_grid CTAs
@@ -1057,6 +1161,8 @@ void tc_plan_layers(sb_engine* e) {
             uint32_t xb[4] = {32, (uint32_t)p.P, (uint32_t)(p.BH + g.KH - 1), 1};
             P->map_x_hwg = make_map(x, 4, xd, xb, true);
             P->halo_wg = true;
+            { const char* ex = getenv("SB_WG_EXPERIMENT"); p.dbg_mode = ex ? atoi(ex) : 0; }
+            if (p.dbg) fprintf(stderr, "[sb] halo wgrad: BH %d P %d chunks %d stages %d stage_bytes %d grid %d\n", p.BH, p.P, p.n_chunks, p.stages, stage_bytes, P->hwg_grid);
           }
         }
       }
@@ -1074,8 +1180,12 @@ void tc_plan_layers(sb_engine* e) {
   if (!attr_set) {
     SB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
     SB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
-    SB_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
-    SB_CUDA(cudaFuncSetAttribute(conv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
+    SB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
+    SB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<3, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
+    SB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<3, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
+    SB_CUDA(cudaFuncSetAttribute(conv_wgrad_halo_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
+    SB_CUDA(cudaFuncSetAttribute(conv_wgrad_halo_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
+    SB_CUDA(cudaFuncSetAttribute(conv_wgrad_halo_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
     attr_set = true;
   }
 }
@@ -1104,6 +1214,19 @@ void tc_free_layers(sb_engine* e) {
           fclose(f);
         }
         cudaFree(hp->dbg);
+      }
+      if (!P->wg_list.empty() && P->wg_list[0].dbg) {
+        std::vector<long long> h((size_t)kNumSMs * 64);
+        cudaMemcpy(h.data(), P->wg_list[0].dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        FILE* f = fopen("gpurun_out/wgrad_timeline.txt", "w");
+        if (f) {
+          for (int c = 0; c < kNumSMs; ++c) {
+            for (int j = 0; j < 34; ++j) fprintf(f, "%lld ", h[(size_t)c * 64 + j] ? h[(size_t)c * 64 + j] - h[(size_t)c * 64] : -1);
+            fprintf(f, "\n");
+          }
+          fclose(f);
+        }
+        cudaFree(P->wg_list[0].dbg);
       }
       cudaFree(P->wg_partial);
       delete P;
@@ -1134,7 +1257,10 @@ bool tc_conv_fwd(sb_engine* e, LayerPlan& L, int) {
   ConvTcPlan* P = (ConvTcPlan*)L.tc_plan;
   if (!P || L.tc_kind != 1) return false;
   if (P->halo_fwd) {
-    launch_k(conv_halo_kernel, P->hfwd_grid, kIgemmThreads, P->hfwd_smem, e->stream, P->map_x_h, P->map_w_fwd, P->map_y_out, P->hfwd);
+    auto kern = P->hfwd.KH == 3 && P->hfwd.KW == 3 && P->hfwd.kchunks == 1   ? conv_halo_kernel<3, 3, 1>
+                : P->hfwd.KH == 3 && P->hfwd.KW == 3 && P->hfwd.kchunks == 2 ? conv_halo_kernel<3, 3, 2>
+                                                                               : conv_halo_kernel<0, 0, 0>;
+    launch_k(kern, P->hfwd_grid, kIgemmThreads, P->hfwd_smem, e->stream, P->map_x_h, P->map_w_fwd, P->map_y_out, P->hfwd);
     SB_LAUNCHED();
     return true;
   }
@@ -1149,7 +1275,10 @@ bool tc_conv_wgrad(sb_engine* e, LayerPlan& L, int) {
   const ConvGeom& g = L.cg;
   const int n = g.KH * g.KW * g.Cin * g.Cout;
   if (P->halo_wg) {
-    launch_k(conv_wgrad_halo_kernel, P->hwg_grid, kWgradThreads, P->hwg_smem, e->stream, P->map_dy_hwg, P->map_x_hwg, P->hwg);
+    const int cis = P->hwg.Cin / 32;
+    auto kern = P->hwg.KH == 3 && cis == 1 ? conv_wgrad_halo_kernel<3, 1>
+                : P->hwg.KH == 3 && cis == 2 ? conv_wgrad_halo_kernel<3, 2> : conv_wgrad_halo_kernel<0, 0>;
+    launch_k(kern, P->hwg_grid, kWgradThreads, P->hwg_smem, e->stream, P->map_dy_hwg, P->map_x_hwg, P->hwg);
     SB_LAUNCHED();
     partial_reduce(P->wg_partial, e->grads + e->params[L.p_w].offset, n, P->hwg_grid, e->stream);
     return true;
@@ -1166,7 +1295,10 @@ bool tc_conv_dgrad(sb_engine* e, LayerPlan& L, int) {
   ConvTcPlan* P = (ConvTcPlan*)L.tc_plan;
   if (!P || L.tc_kind != 1 || !P->has_dgrad) return false;
   if (P->halo_dg) {
-    launch_k(conv_halo_kernel, P->hdg_grid, kIgemmThreads, P->hdg_smem, e->stream, P->map_dy_h, P->map_w_dg, P->map_dx_out, P->hdg);
+    auto kern = P->hdg.KH == 3 && P->hdg.KW == 3 && P->hdg.kchunks == 1   ? conv_halo_kernel<3, 3, 1>
+                : P->hdg.KH == 3 && P->hdg.KW == 3 && P->hdg.kchunks == 2 ? conv_halo_kernel<3, 3, 2>
+                                                                             : conv_halo_kernel<0, 0, 0>;
+    launch_k(kern, P->hdg_grid, kIgemmThreads, P->hdg_smem, e->stream, P->map_dy_h, P->map_w_dg, P->map_dx_out, P->hdg);
     SB_LAUNCHED();
     return true;
   }

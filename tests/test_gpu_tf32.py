@@ -60,8 +60,10 @@ CONV_STACKS = [
 ]
 
 
+@pytest.mark.parametrize("wgrad", ["halo", "per_tap"])  # filter-gradient kernel: one X box per chunk (default) / one box per tap
 @pytest.mark.parametrize("name,spec,batch,in_shape", CONV_STACKS, ids=[c[0] for c in CONV_STACKS])
-def test_tf32_conv_forward_and_gradients(name, spec, batch, in_shape):
+def test_tf32_conv_forward_and_gradients(name, spec, batch, in_shape, wgrad, monkeypatch):
+    monkeypatch.setenv("SB_TC_HALO_WGRAD", "1" if wgrad == "halo" else "0")
     om, e32, etc = engines(spec, "cce", batch, in_shape, 10)
     x, y = synth_classification(batch, in_shape, 10, 21)
     p32, ptc = e32.predict(x), etc.predict(x)
