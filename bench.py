@@ -277,26 +277,32 @@ def run_ours(args):
     # ---- end to end through the public C-ABI call with HOST buffers (pinned), H2D + loss D2H every step ----
     xh = torch.from_numpy(x[:steps_per_epoch * BATCH]).pin_memory()
     yh = torch.from_numpy(y[:steps_per_epoch * BATCH]).pin_memory()
-    loss_h = torch.zeros(args.steps + args.warmup + 8, dtype=torch.float32).pin_memory()
+    e2e_warm = max(args.warmup, 19)  # at least two 8-step groups (one graph per staging buffer) + single steps get captured untimed
+    loss_h = torch.zeros(args.steps + e2e_warm + 8, dtype=torch.float32).pin_memory()
     xb, yb = BATCH * int(np.prod(IN_SHAPE)) * 4, BATCH * CLASSES * 4
 
     def run_steps_e2e(n, slot0):
-        for j in range(n):
+        # the public host-fed call: consecutive pinned batches, H2D on the copy stream + one loss D2H per step, up to the epoch end
+        j = 0
+        while j < n:
             b = state["batch"]
-            eng.train_step_async_ptr(xh.data_ptr() + b * xb, yh.data_ptr() + b * yb, state["iter"] + 1,
-                                     loss_h.data_ptr() + 4 * (slot0 + j))
-            state["iter"] += 1
-            state["batch"] += 1
+            m = min(n - j, steps_per_epoch - b)
+            eng.train_batches_async_ptr(xh.data_ptr() + b * xb, yh.data_ptr() + b * yb, m, state["iter"],
+                                        (0 if os.environ.get("SB_BENCH_NO_LOSS") else loss_h.data_ptr() + 4 * (slot0 + j)))
+            state["iter"] += m
+            state["batch"] += m
+            j += m
             if state["batch"] == steps_per_epoch:
                 state["batch"] = 0
                 if avg is not None:
                     total = epoch_average()
                     state["iter"] += total - steps_per_epoch
-    run_steps_e2e(max(args.warmup, 3), 0)
+    run_steps_e2e(e2e_warm, 0)
     barrier()
     t0 = time.perf_counter()
     ev0.record(stream)
-    run_steps_e2e(args.steps, max(args.warmup, 3))
+    run_steps_e2e(args.steps, e2e_warm)
+    eng.sync()  # compute stream AND the copy stream that carries the loss read-backs: the D2H reads are inside the timed region
     ev1.record(stream)
     barrier()
     e2e_wall = time.perf_counter() - t0
@@ -306,7 +312,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms, e2e_wall = float(t[0].item()), float(t[1].item()) / 1000.0
     e2e_value = world * args.steps * BATCH / max(e2e_ms / 1000.0, 1e-9)
-    last_loss = float(loss_h[max(args.warmup, 3) + args.steps - 1].item())
+    last_loss = float(loss_h[e2e_warm + args.steps - 1].item())
 
     # ---- the exchange step alone: fused P2P averaging kernel (flag barriers + reduce-scatter + all-gather over NVLink) ----
     averaging = None

@@ -222,6 +222,13 @@ int sb_train_step(sb_engine* e, const float* x, const float* y, int64_t iter, fl
  * step, and a D2H read of the PRE-update loss into `loss_out_host` (pinned; may be NULL).  No sync: call sb_sync
  * before reading the loss or reusing x / y. */
 int sb_train_step_async(sb_engine* e, const float* x, const float* y, int64_t iter, float* loss_out_host);
+/* The `optimize` loop over HOST batches (Optimizer.scala:135-147): n_batches consecutive batches x[n_batches*batch,...],
+ * y[n_batches*batch,...] (pinned memory for real overlap) stream through a double-buffered staging area in groups of up to 8;
+ * a group is one H2D copy pair on the copy stream and one CUDA graph of that many steps on the compute stream, so the copy of
+ * group g+1 overlaps the steps of group g.  Batch j runs with iter = global_iter + j + 1.  losses_out_host (optional, pinned,
+ * n_batches floats) receives the PRE-update loss of every batch.  No sync: call sb_sync before reading them or reusing x / y. */
+int sb_train_batches_async(sb_engine* e, const float* x, const float* y, int64_t n_batches, int64_t global_iter,
+                           float* losses_out_host);
 /* the `loss` closure on HOST buffers (training-mode forward, state discarded) */
 int sb_eval_loss(sb_engine* e, const float* x, const float* y, float* loss_out);
 /* forward only (`TrainedModel.result`, models/Model.scala:154-163): out[batch, ...] on the host */

@@ -59,6 +59,8 @@ object Native {
   val datasetUpload: MethodHandle = fn("sb_dataset_upload", JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG)
   val trainEpoch: MethodHandle = fn("sb_train_epoch", JAVA_INT, ADDRESS, JAVA_LONG, ADDRESS, ADDRESS)
   val trainStep: MethodHandle = fn("sb_train_step", JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS)
+  val trainBatchesAsync: MethodHandle =
+    fn("sb_train_batches_async", JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG, ADDRESS)
   val evalLoss: MethodHandle = fn("sb_eval_loss", JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS)
   val predict: MethodHandle = fn("sb_predict", JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG)
   // estimators/package.scala:18-137 on the device: (engine, kind, x|NULL, y|NULL, rows, double[4])

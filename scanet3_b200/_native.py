@@ -88,6 +88,7 @@ PROTOTYPES = {
     "sb_train_steps_async": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64]),
     "sb_train_step": (C.c_int, [_P, _P, _P, C.c_int64, _FP]),
     "sb_train_step_async": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
+    "sb_train_batches_async": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, _P]),
     "sb_eval_loss": (C.c_int, [_P, _P, _P, _FP]),
     "sb_predict": (C.c_int, [_P, _P, _P, C.c_size_t]),
     "sb_wire_encode": (C.c_int, [C.POINTER(C.c_int64), C.c_int32, _P, _P, C.c_size_t, C.POINTER(C.c_size_t)]),

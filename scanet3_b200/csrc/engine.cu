@@ -828,10 +828,12 @@ static void run_prologue(sb_engine* e, bool resident) {
   step_prologue(e->st, resident ? e->ds_x : nullptr, resident ? e->ds_y : nullptr, e->acts[0], e->by, e->in_shape.numel(),
                 e->label_shape.numel(), e->train.beta1, e->train.beta2, 1, e->stream);
 }
-static void run_prologue_staged(sb_engine* e, int parity) {
+static void run_prologue_staged(sb_engine* e, int parity, int j = 0) {
   Prof pr(e, "step_prologue", 8.0 * (double)(e->in_shape.numel() + e->label_shape.numel()), 0);
-  step_prologue(e->st, e->stage_x[parity], e->stage_y[parity], e->acts[0], e->by, e->in_shape.numel(), e->label_shape.numel(),
-                e->train.beta1, e->train.beta2, 0, e->stream);
+  // batch j of the staging buffer; from the second step of a group on, the prologue also files the previous step's loss
+  step_prologue(e->st, e->stage_x[parity] + (size_t)j * e->in_shape.numel(), e->stage_y[parity] + (size_t)j * e->label_shape.numel(),
+                e->acts[0], e->by, e->in_shape.numel(), e->label_shape.numel(), e->train.beta1, e->train.beta2, 0, e->stream,
+                j > 0 ? e->loss_hist[parity] + (j - 1) : nullptr);
 }
 
 static void run_train_step_body(sb_engine* e, bool resident) {
@@ -851,6 +853,19 @@ static void run_train_step_body_staged(sb_engine* e, bool parity) {
   run_backward(e);
   run_reg(e, true);
   run_optimizer(e, 0);
+}
+
+// `stage_batches` host-fed steps back to back (one graph): batch j comes from slot j of staging buffer `parity`
+static void run_train_group_body_staged(sb_engine* e, bool parity) {
+  for (int j = 0; j < e->stage_batches; ++j) {
+    run_prologue_staged(e, parity ? 1 : 0, j);
+    run_forward(e, FWD_TRAIN);
+    run_loss(e, true);
+    run_backward(e);
+    run_reg(e, true);
+    run_optimizer(e, 0);
+  }
+  store_loss(e->st, e->loss_hist[parity ? 1 : 0] + (e->stage_batches - 1), e->stream);
 }
 
 static cudaGraphExec_t capture(sb_engine* e, long long* nodes, void (*body)(sb_engine*, bool), bool flag) {
@@ -924,9 +939,13 @@ static void launch_train_steps_resident(sb_engine* e, int64_t n_steps) {
 static void ensure_staging(sb_engine* e) {
   if (e->cstream) return;
   SB_CUDA(cudaStreamCreateWithFlags(&e->cstream, cudaStreamNonBlocking));
+  // group size of sb_train_batches_async: as many steps as a resident graph holds, within 64 MB of staging per buffer
+  const int64_t batch_bytes = (e->in_shape.numel() + e->label_shape.numel()) * 4;
+  e->stage_batches = (int)std::max<int64_t>(1, std::min<int64_t>(steps_per_graph(), (64ll << 20) / std::max<int64_t>(1, batch_bytes)));
   for (int i = 0; i < 2; ++i) {
-    e->stage_x[i] = dmalloc_floats(pad32(e->in_shape.numel()));
-    e->stage_y[i] = dmalloc_floats(pad32(e->label_shape.numel()));
+    e->stage_x[i] = dmalloc_floats(pad32(e->stage_batches * e->in_shape.numel()));
+    e->stage_y[i] = dmalloc_floats(pad32(e->stage_batches * e->label_shape.numel()));
+    e->loss_hist[i] = dmalloc_floats(pad32(e->stage_batches));
     SB_CUDA(cudaEventCreateWithFlags(&e->ev_copied[i], cudaEventDisableTiming));
     SB_CUDA(cudaEventCreateWithFlags(&e->ev_free[i], cudaEventDisableTiming));
     SB_CUDA(cudaEventRecord(e->ev_free[i], e->stream));
@@ -953,6 +972,38 @@ static void launch_train_step_staged(sb_engine* e, const float* x, const float* 
     e->launches += tl_launch_count - before;
   }
   SB_CUDA(cudaEventRecord(e->ev_free[par], e->stream));
+}
+
+// Loss read-back of a finished group, on the copy stream (a D2H in the compute stream stalls it ~25 us).  It waits for that
+// group's compute, so it is queued only AFTER the next group's H2D copy -- otherwise that copy would no longer overlap compute.
+// loss_hist[par] is rewritten two groups later, by a graph that waits for an H2D queued behind this D2H: no race.
+static void flush_pending_losses(sb_engine* e) {
+  if (!e->pending_loss_host) return;
+  const int par = e->pending_loss_par;
+  SB_CUDA(cudaStreamWaitEvent(e->cstream, e->ev_free[par], 0));
+  SB_CUDA(cudaMemcpyAsync(e->pending_loss_host, e->loss_hist[par], (size_t)e->stage_batches * 4, cudaMemcpyDeviceToHost, e->cstream));
+  e->pending_loss_host = nullptr;
+}
+
+// `stage_batches` consecutive host batches: one H2D pair on the copy stream, one graph, one read-back of the group's losses
+static void launch_train_group_staged(sb_engine* e, const float* x, const float* y, float* losses_out_host) {
+  ensure_staging(e);
+  const int par = e->stage_parity, G = e->stage_batches;
+  e->stage_parity ^= 1;
+  SB_CUDA(cudaStreamWaitEvent(e->cstream, e->ev_free[par], 0));
+  SB_CUDA(cudaMemcpyAsync(e->stage_x[par], x, (size_t)G * e->in_shape.numel() * 4, cudaMemcpyHostToDevice, e->cstream));
+  SB_CUDA(cudaMemcpyAsync(e->stage_y[par], y, (size_t)G * e->label_shape.numel() * 4, cudaMemcpyHostToDevice, e->cstream));
+  SB_CUDA(cudaEventRecord(e->ev_copied[par], e->cstream));
+  flush_pending_losses(e);
+  SB_CUDA(cudaStreamWaitEvent(e->stream, e->ev_copied[par], 0));
+  if (!e->g_group[par]) e->g_group[par] = capture(e, &e->nodes_group[par], run_train_group_body_staged, par != 0);
+  SB_CUDA(cudaGraphLaunch(e->g_group[par], e->stream));
+  e->launches += e->nodes_group[par];
+  SB_CUDA(cudaEventRecord(e->ev_free[par], e->stream));
+  if (losses_out_host) {
+    e->pending_loss_host = losses_out_host;
+    e->pending_loss_par = par;
+  }
 }
 
 static void launch_loss(sb_engine* e) {
@@ -1116,7 +1167,8 @@ extern "C" void sb_engine_destroy(sb_engine* e) {
     if (e->g_loss) cudaGraphExecDestroy(e->g_loss);
     for (int i = 0; i < 2; ++i) {
       if (e->g_staged[i]) cudaGraphExecDestroy(e->g_staged[i]);
-      cudaFree(e->stage_x[i]); cudaFree(e->stage_y[i]);
+      if (e->g_group[i]) cudaGraphExecDestroy(e->g_group[i]);
+      cudaFree(e->stage_x[i]); cudaFree(e->stage_y[i]); cudaFree(e->loss_hist[i]);
       if (e->ev_copied[i]) cudaEventDestroy(e->ev_copied[i]);
       if (e->ev_free[i]) cudaEventDestroy(e->ev_free[i]);
     }
@@ -1319,6 +1371,31 @@ extern "C" int sb_train_step_async(sb_engine* e, const float* x, const float* y,
   SB_API_END
 }
 
+extern "C" int sb_train_batches_async(sb_engine* e, const float* x, const float* y, int64_t n_batches, int64_t global_iter,
+                                      float* losses_out_host) {
+  SB_API_BEGIN
+  need_device(e);
+  require_ready(e);
+  if (!x || !y) SB_FAIL(SB_ERR_INVALID_ARG, "null batch buffers");
+  if (n_batches < 0 || global_iter < 0) SB_FAIL(SB_ERR_INVALID_ARG, "negative batch count or iteration");
+  DeviceGuard dg(e->device);
+  if (e->host_iter_mirror != global_iter) set_device_iter(e, global_iter, 0);
+  ensure_staging(e);
+  const int64_t xn = e->in_shape.numel(), yn = e->label_shape.numel();
+  int64_t j = 0;
+  if (use_graph(e) && e->stage_batches > 1)
+    for (; j + e->stage_batches <= n_batches; j += e->stage_batches)
+      launch_train_group_staged(e, x + j * xn, y + j * yn, losses_out_host ? losses_out_host + j : nullptr);
+  flush_pending_losses(e);
+  for (; j < n_batches; ++j) {
+    launch_train_step_staged(e, x + j * xn, y + j * yn);
+    if (losses_out_host)
+      SB_CUDA(cudaMemcpyAsync(losses_out_host + j, &e->st->loss, sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  }
+  e->host_iter_mirror = global_iter + n_batches;
+  SB_API_END
+}
+
 extern "C" int sb_eval_loss(sb_engine* e, const float* x, const float* y, float* loss_out) {
   SB_API_BEGIN
   need_device(e);
@@ -1430,6 +1507,7 @@ extern "C" int sb_sync(sb_engine* e) {
   need_device(e);
   DeviceGuard dg(e->device);
   SB_CUDA(cudaStreamSynchronize(e->stream));
+  if (e->cstream) SB_CUDA(cudaStreamSynchronize(e->cstream));  // loss read-backs of sb_train_batches_async
   if (e->profiling) prof_resolve(e);
   SB_API_END
 }

@@ -128,6 +128,13 @@ struct sb_engine {
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   cudaGraphExec_t g_staged[2] = {nullptr, nullptr};
   long long nodes_staged[2] = {0, 0};
+  // sb_train_batches_async: each staging buffer holds `stage_batches` consecutive host batches; one graph runs them all
+  int stage_batches = 1;
+  cudaGraphExec_t g_group[2] = {nullptr, nullptr};
+  long long nodes_group[2] = {0, 0};
+  float* loss_hist[2] = {nullptr, nullptr};  // per staging buffer: pre-update losses of the group's steps
+  float* pending_loss_host = nullptr;        // read-back of the latest group, queued behind the NEXT group's H2D copy
+  int pending_loss_par = 0;
   int stage_parity = 0;
   cudaGraphExec_t g_resident = nullptr, g_hostfed = nullptr, g_loss = nullptr;
   cudaGraphExec_t g_resident_multi = nullptr;  // kStepsPerGraph resident steps in one graph (fewer graph boundaries per epoch)

@@ -34,8 +34,12 @@ struct OptDesc {
 };
 
 // ---- step prologue: gather the batch out of the resident shard + advance iter / bias corrections ----
+// prev_loss_slot (may be null): receives st->loss, i.e. the loss of the step BEFORE this one (steps chained in one graph)
 void step_prologue(StepState* st, const float* ds_x, const float* ds_y, float* bx, float* by, long long x_per_batch,
-                   long long y_per_batch, float beta1, float beta2, int batch_from_state, cudaStream_t s);
+                   long long y_per_batch, float beta1, float beta2, int batch_from_state, cudaStream_t s,
+                   float* prev_loss_slot = nullptr);
+
+void store_loss(const StepState* st, float* slot, cudaStream_t s);  // *slot = st->loss (last step of a host-fed group)
 
 // ---- fp32 FFMA contractions (parity mode; also the shapes tcgen05 does not fit) ----
 // C[M,N] = A[M,K] . B[K,N]

@@ -15,7 +15,7 @@ thread_local long long tl_launch_count = 0;
 template <typename V>
 __global__ void step_prologue_kernel(StepState* st, const V* __restrict__ ds_x, const V* __restrict__ ds_y,
                                      V* __restrict__ bx, V* __restrict__ by, long long x4, long long y4,
-                                     float beta1, float beta2, int batch_from_state) {
+                                     float beta1, float beta2, int batch_from_state, float* __restrict__ prev_loss_slot) {
   pdl_prologue();
   // resident shard: batch index from the device state (only the optimizer kernel of the previous step writes it);
   // host-fed staging buffer: always its single batch
@@ -30,6 +30,7 @@ __global__ void step_prologue_kernel(StepState* st, const V* __restrict__ ds_x, 
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (prev_loss_slot) *prev_loss_slot = st->loss;
     // t = globalIter + localIter + 1, fed as int32 and cast to float (optimizers/Optimizer.scala:143);
     // boost(x, rate, t) = x / (1 - rate^float(t)) (math/alg/AllKernels.scala:546-549).  The power is
     // evaluated in double and rounded once, i.e. the correctly rounded powf TF-CPU (glibc) returns.
@@ -42,7 +43,7 @@ __global__ void step_prologue_kernel(StepState* st, const V* __restrict__ ds_x, 
 }
 
 void step_prologue(StepState* st, const float* ds_x, const float* ds_y, float* bx, float* by, long long x_per_batch,
-                   long long y_per_batch, float beta1, float beta2, int batch_from_state, cudaStream_t s) {
+                   long long y_per_batch, float beta1, float beta2, int batch_from_state, cudaStream_t s, float* prev_loss_slot) {
   // 128-bit copies when every batch of the shard starts 16-byte aligned, scalar copies otherwise
   const bool vec = (x_per_batch % 4 == 0) && (y_per_batch % 4 == 0);
   const long long xn = vec ? x_per_batch / 4 : x_per_batch, yn = vec ? y_per_batch / 4 : y_per_batch;
@@ -51,9 +52,19 @@ void step_prologue(StepState* st, const float* ds_x, const float* ds_y, float* b
   if (blocks < 1) blocks = 1;
   if (vec)
     launch_k(step_prologue_kernel<float4>, blocks, 256, 0, s, st, (const float4*)ds_x, (const float4*)ds_y, (float4*)bx,
-                                                        (float4*)by, xn, yn, beta1, beta2, batch_from_state);
+                                                        (float4*)by, xn, yn, beta1, beta2, batch_from_state, prev_loss_slot);
   else
-    launch_k(step_prologue_kernel<float>, blocks, 256, 0, s, st, ds_x, ds_y, bx, by, xn, yn, beta1, beta2, batch_from_state);
+    launch_k(step_prologue_kernel<float>, blocks, 256, 0, s, st, ds_x, ds_y, bx, by, xn, yn, beta1, beta2, batch_from_state,
+             prev_loss_slot);
+  SB_LAUNCHED();
+}
+
+__global__ void store_loss_kernel(const StepState* __restrict__ st, float* __restrict__ slot) {
+  pdl_prologue();
+  *slot = st->loss;
+}
+void store_loss(const StepState* st, float* slot, cudaStream_t s) {
+  launch_k(store_loss_kernel, 1, 1, 0, s, st, slot);
   SB_LAUNCHED();
 }
 

@@ -166,6 +166,19 @@ class Engine:
         """pointer form for pinned host buffers (end-to-end timing)"""
         N.check(self._lib.sb_train_step_async(self._h, x_ptr, y_ptr, int(it), loss_ptr or None))
 
+    def train_batches_async_ptr(self, x_ptr: int, y_ptr: int, n_batches: int, global_iter: int, losses_ptr: int = 0):
+        """`sb_train_batches_async`: n consecutive HOST batches (pinned) in groups of up to 8 steps per graph; no sync."""
+        N.check(self._lib.sb_train_batches_async(self._h, x_ptr, y_ptr, int(n_batches), int(global_iter), losses_ptr or None))
+
+    def train_batches(self, x, y, global_iter: int) -> np.ndarray:
+        """synchronous convenience form: -> the PRE-update loss of every full batch of (x, y)"""
+        x, y = _f32(x), _f32(y)
+        n = x.shape[0] // self.batch
+        losses = np.empty(n, np.float32)
+        N.check(self._lib.sb_train_batches_async(self._h, x.ctypes.data, y.ctypes.data, n, int(global_iter), losses.ctypes.data))
+        self.sync()
+        return losses
+
     def eval_loss(self, x, y) -> float:
         x, y = _f32(x), _f32(y)
         loss = C.c_float()

@@ -564,3 +564,36 @@ def test_checkpoint_resume_continues_bit_identically(tmp_path, k):
         _, other = build_models([("dense", 5, "softmax")])
         (S.Dataset(x, y).train(other).loss(S.CategoricalCrossentropy).using(S.Adam(0.02)).batch(64).resumeFrom(ck)
          .stopAfter(S.epochs(1)).quiet().run())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# host-fed multi-batch call (the `optimize` loop over host batches, Optimizer.scala:135-147)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_batches", [19, 8, 3])  # two graph groups + 3 single steps / exactly one group / singles only
+def test_train_batches_matches_step_by_step(n_batches):
+    spec = [("conv", 4, "relu", (3, 3), (1, 1), "Valid", False), ("pool", (2, 2), (1, 1), "Valid"), ("flatten",),
+            ("dense", 5, "softmax")]
+    om, sm = build_models(spec)
+    B = 16
+    x, y = synth_classification(B * n_batches + 5, (8, 8, 1), 5, seed=13)  # 5 trailing rows: the partial batch is dropped
+    _, mp, _ = oracle_init(om, O.Adam(rate=0.01), (B, 8, 8, 1))
+    ea = make_engine(sm, S.CategoricalCrossentropy, S.Adam(0.01), B, (8, 8, 1), (5,))
+    eb = make_engine(sm, S.CategoricalCrossentropy, S.Adam(0.01), B, (8, 8, 1), (5,))
+    for e in (ea, eb):
+        e.set_params(mp)
+        e.init_opt_params()
+    it0 = 7  # a resumed run: global iteration does not start at 0
+    want = [ea.train_step(x[j * B:(j + 1) * B], y[j * B:(j + 1) * B], it0 + j + 1) for j in range(n_batches)]
+    got = eb.train_batches(x, y, it0)
+    assert got.shape == (n_batches,)
+    assert np.array_equal(got, np.asarray(want, np.float32))            # same kernels, same order: bit-identical
+    pa, pb = ea.get_params(), eb.get_params()
+    for k in pa:
+        assert np.array_equal(pa[k], pb[k]), k
+    # and the trajectory is the oracle's
+    lm = O.LossModel(om, O.CategoricalCrossentropy)
+    p, op = dict(mp), O.init_params(om, O.Adam(rate=0.01), (B, 8, 8, 1), np.float32, mp)[2]
+    for j in range(min(n_batches, 4)):
+        p, op, loss = O.train_step(lm, O.Adam(rate=0.01), x[j * B:(j + 1) * B], y[j * B:(j + 1) * B], p, op, it0 + j + 1)
+        np.testing.assert_allclose(got[j], loss, rtol=1e-4)
+    ea.close(); eb.close()
