@@ -25,6 +25,13 @@ struct ApiError : std::runtime_error {
   ApiError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
 };
 void set_error(const std::string& m) { tl_error = m; }
+bool fork_enabled() {  // SB_BWD_FORK=0: the conv filter gradient stays in the main stream
+  static const bool on = [] {
+    const char* v = getenv("SB_BWD_FORK");
+    return !(v && v[0] == '0');
+  }();
+  return on;
+}
 bool pdl_enabled() {
   static const bool on = [] {
     const char* v = getenv("SB_PDL");
@@ -441,6 +448,9 @@ static void plan_fusions(sb_engine* e) {
 static void allocate(sb_engine* e) {
   SB_CUDA(cudaSetDevice(e->device));
   SB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  SB_CUDA(cudaStreamCreateWithFlags(&e->bstream, cudaStreamNonBlocking));  // backward side branch (created outside any capture)
+  SB_CUDA(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+  SB_CUDA(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
   // the arena allocation carries a tail of cross-GPU flags / scalars behind the tensors (one IPC handle maps both)
   e->arena = dmalloc_floats(e->arena_floats + sb::kArenaTailFloats);
   SB_CUDA(cudaMemsetAsync(e->arena, 0, (size_t)(e->arena_floats + sb::kArenaTailFloats) * 4, e->stream));
@@ -729,13 +739,26 @@ static void run_backward(sb_engine* e) {
         const double cb = 4.0 * ((double)L.in.numel() + n_out + e->params[L.p_w].numel);
         bool wdone = L.wgrad_in_pool, ddone = false;  // wgrad_in_pool: done by the following pool's backward kernel
         if (L.tc_kind) {
-          {
+          // With an input-gradient chain behind it, the filter gradient (tensor-core kernel + reduce) moves to a side branch
+          // that starts AFTER the dgrad kernel: both want every SM's shared memory, whereas the pool / activation backward
+          // kernels that follow dgrad leave room for it (not while per-kernel timing is on).
+          const bool fork = fork_enabled() && !e->profiling && L.need_dx && din && !L.wgrad_in_pool;
+          if (!fork) {
             Prof pr(e, "conv2d_wgrad_tf32_tcgen05", cb, fl);
             wdone = tc_conv_wgrad(e, L, li);
           }
           if (L.need_dx && din) {
             Prof pr(e, "conv2d_dgrad_tf32_tcgen05", cb, fl);
             ddone = tc_conv_dgrad(e, L, li);
+          }
+          if (fork) {
+            if (e->bwd_forked) SB_CUDA(cudaStreamWaitEvent(s, e->ev_join, 0));  // one side branch at a time keeps the join simple
+            SB_CUDA(cudaEventRecord(e->ev_fork, s));
+            SB_CUDA(cudaStreamWaitEvent(e->bstream, e->ev_fork, 0));
+            wdone = tc_conv_wgrad(e, L, li, e->bstream);
+            SB_CUDA(cudaEventRecord(e->ev_join, e->bstream));
+            e->bwd_forked = true;
+            if (!wdone) SB_FAIL(SB_ERR_CUDA, "tensor-core filter gradient rejected a planned shape");
           }
         }
         if (!wdone && L.fast_smallk) {
@@ -783,6 +806,10 @@ static void run_backward(sb_engine* e) {
         break;
       }
     }
+  }
+  if (e->bwd_forked) {  // every gradient is in place before the penalties / the optimizer / a read-back
+    SB_CUDA(cudaStreamWaitEvent(s, e->ev_join, 0));
+    e->bwd_forked = false;
   }
 }
 
@@ -1173,6 +1200,7 @@ extern "C" void sb_engine_destroy(sb_engine* e) {
       if (e->ev_free[i]) cudaEventDestroy(e->ev_free[i]);
     }
     if (e->cstream) { cudaStreamSynchronize(e->cstream); cudaStreamDestroy(e->cstream); }
+    if (e->bstream) { cudaStreamSynchronize(e->bstream); cudaStreamDestroy(e->bstream); cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join); }
     tc_free_layers(e);
     lstm_free(e);
     for (auto& L : e->L) { cudaFree(L.bn_save_mean); cudaFree(L.bn_save_var); }

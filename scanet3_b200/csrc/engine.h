@@ -122,6 +122,11 @@ struct sb_engine {
   cudaStream_t stream = nullptr;
   // host-fed pipeline (sb_train_step_async): the H2D copy of batch t+1 runs on `cstream` into the other staging buffer while
   // batch t computes; the step's prologue gathers from its staging buffer
+  // backward fork: a conv layer's filter gradient (tensor-core kernel + reduce) runs on `bstream` next to the input-gradient
+  // chain (dgrad -> pool backward ...), joined before the penalties / optimizer; inside a captured graph this is a parallel branch
+  cudaStream_t bstream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool bwd_forked = false;
   cudaStream_t cstream = nullptr;
   float* stage_x[2] = {nullptr, nullptr};
   float* stage_y[2] = {nullptr, nullptr};

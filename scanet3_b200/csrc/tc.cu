@@ -1269,8 +1269,9 @@ bool tc_conv_fwd(sb_engine* e, LayerPlan& L, int) {
   return true;
 }
 
-bool tc_conv_wgrad(sb_engine* e, LayerPlan& L, int) {
+bool tc_conv_wgrad(sb_engine* e, LayerPlan& L, int, cudaStream_t side) {
   ConvTcPlan* P = (ConvTcPlan*)L.tc_plan;
+  cudaStream_t st = side ? side : e->stream;
   if (!P || L.tc_kind != 1 || !P->wg_ok) return false;
   const ConvGeom& g = L.cg;
   const int n = g.KH * g.KW * g.Cin * g.Cout;
@@ -1278,16 +1279,16 @@ bool tc_conv_wgrad(sb_engine* e, LayerPlan& L, int) {
     const int cis = P->hwg.Cin / 32;
     auto kern = P->hwg.KH == 3 && cis == 1 ? conv_wgrad_halo_kernel<3, 1>
                 : P->hwg.KH == 3 && cis == 2 ? conv_wgrad_halo_kernel<3, 2> : conv_wgrad_halo_kernel<0, 0>;
-    launch_k(kern, P->hwg_grid, kWgradThreads, P->hwg_smem, e->stream, P->map_dy_hwg, P->map_x_hwg, P->hwg);
+    launch_k(kern, P->hwg_grid, kWgradThreads, P->hwg_smem, st, P->map_dy_hwg, P->map_x_hwg, P->hwg);
     SB_LAUNCHED();
-    partial_reduce(P->wg_partial, e->grads + e->params[L.p_w].offset, n, P->hwg_grid, e->stream);
+    partial_reduce(P->wg_partial, e->grads + e->params[L.p_w].offset, n, P->hwg_grid, st);
     return true;
   }
   for (size_t i = 0; i < P->wg_list.size(); ++i) {
-    launch_k(conv_wgrad_kernel, P->wg_grid, kWgradThreads, P->wg_smem_list[i], e->stream, P->map_dy_wg, P->map_x_wg, P->wg_list[i]);
+    launch_k(conv_wgrad_kernel, P->wg_grid, kWgradThreads, P->wg_smem_list[i], st, P->map_dy_wg, P->map_x_wg, P->wg_list[i]);
     SB_LAUNCHED();
   }
-  partial_reduce(P->wg_partial, e->grads + e->params[L.p_w].offset, n, P->wg_grid, e->stream);  // fixed order, 8-way parallel
+  partial_reduce(P->wg_partial, e->grads + e->params[L.p_w].offset, n, P->wg_grid, st);  // fixed order, 8-way parallel
   return true;
 }
 

@@ -14,7 +14,7 @@ bool tc_dense_fwd(sb_engine* e, LayerPlan& L, int li);
 bool tc_dense_wgrad(sb_engine* e, LayerPlan& L, int li);
 bool tc_dense_dgrad(sb_engine* e, LayerPlan& L, int li);
 bool tc_conv_fwd(sb_engine* e, LayerPlan& L, int li);
-bool tc_conv_wgrad(sb_engine* e, LayerPlan& L, int li);
+bool tc_conv_wgrad(sb_engine* e, LayerPlan& L, int li, cudaStream_t s = nullptr);  // s: side stream (null = the engine's)
 bool tc_conv_dgrad(sb_engine* e, LayerPlan& L, int li);
 
 // ---- tc_gemm.cu: tcgen05 TF32 GEMM plans (3-D tensor maps: the outer coordinate picks a slice, e.g. an LSTM time step) ----
