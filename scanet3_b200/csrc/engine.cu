@@ -423,6 +423,22 @@ static void plan_fusions(sb_engine* e) {
             }
           }
         }
+        // forward twin: conv(small K) >> [fused ReLU] >> pool(2x2, stride 1) in one pass (the conv output is written, never re-read)
+        {
+          const int ci = (li >= 1 && e->L[li - 1].d.kind == SB_LAYER_ACTIVATE && e->L[li - 1].skip_fwd) ? li - 2 : li - 1;
+          const PoolGeom& g = L.pg;
+          const char* off = getenv("SB_NO_CONV_POOL_FUSION");
+          if (!(off && off[0] == '1') && L.fast_pool && ci >= 0 && e->L[ci].d.kind == SB_LAYER_CONV2D && e->L[ci].fast_smallk &&
+              (ci == li - 1 || e->L[ci].fuse_relu_fwd) && e->L[ci].buf_out == L.buf_in && g.KH == 2 && g.KW == 2 && g.SH == 1 &&
+              g.SW == 1 && g.PT == 0 && g.PL == 0 && g.OH == g.H - 1 && g.OW == g.W - 1 && e->L[ci].cg.SH == 1 && e->L[ci].cg.SW == 1) {
+            const ConvGeom& cg = e->L[ci].cg;
+            const int shape = cg.KH * 100 + cg.KW * 10 + cg.Cin;
+            if (shape == 331 || shape == 333) {
+              e->L[ci].fuse_pool_fwd = li;
+              L.skip_fwd = true;
+            }
+          }
+        }
         break;
       }
       case SB_LAYER_BIAS: {
@@ -599,6 +615,12 @@ static void run_forward(sb_engine* e, int mode) {
         if (L.tc_kind) {
           Prof pr(e, "conv2d_fwd_tf32_tcgen05", cbytes, cflops);
           if (tc_conv_fwd(e, L, li)) break;
+        }
+        if (L.fast_smallk && L.fuse_pool_fwd >= 0) {
+          LayerPlan& PLy = e->L[L.fuse_pool_fwd];
+          Prof pr(e, "conv2d_smallk_pool_fwd", cbytes + 4.0 * (double)PLy.out.numel(), cflops);
+          if (conv_smallk_pool_fwd(in, P(e, L.p_w), out, e->acts[PLy.buf_out], g, L.fuse_relu_fwd, L.fused_thr, s)) break;
+          SB_FAIL(SB_ERR_CUDA, "conv_smallk_pool_fwd rejected a planned shape");
         }
         if (L.fast_smallk) {
           Prof pr(e, "conv2d_smallk_fwd", cbytes, cflops);

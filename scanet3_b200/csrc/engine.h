@@ -63,6 +63,7 @@ struct LayerPlan {
   bool pool_relu_bwd = false;     // max-pool backward also applies the mask of the in-place ReLU that produced its input
   float fused_thr = 0.f;
   int fuse_conv_wgrad = -1;       // Pool2D: its backward also computes the filter gradient of this (small-K) conv layer
+  int fuse_pool_fwd = -1;         // Conv2D (small K): its forward kernel also produces this Pool2D layer's output
   bool wgrad_in_pool = false;     // Conv2D: the filter gradient is produced by the following pool's backward kernel
   bool fuse_act_bwd = false;      // Bias: also applies the backward of the in-place activation that follows (one pass)
   bool head_skip = false;         // Bias / Softmax of the fused classifier head: executed by the head kernel when training

@@ -116,6 +116,10 @@ void pool_max_bwd_v4(const float* x, const float* dy, float* dx, const PoolGeom&
 bool pool_bwd_conv_wgrad(const float* x, const float* dy, float* dx, const PoolGeom& g, int relu, float thr, const float* conv_in,
                          const ConvGeom& cg, float* dw, int store_dx, float* ws, size_t ws_floats, cudaStream_t s);
 void conv_smallk_fwd(const float* x, const float* w, float* y, const ConvGeom& g, int relu, float thr, cudaStream_t s);
+// conv (small K, stride 1) >> [ReLU] >> max-pool 2x2 stride 1 VALID: y = the (activated) conv output, pooled = the pool output.
+// false: shape not covered
+bool conv_smallk_pool_fwd(const float* x, const float* w, float* y, float* pooled, const ConvGeom& g, int relu, float thr,
+                          cudaStream_t s);
 bool conv_smallk_wgrad(const float* x, const float* dy, float* dw, const ConvGeom& g, float* ws, size_t ws_floats, cudaStream_t s);
 bool dense_skinny_fwd(const float* x, const float* w, float* z, int M, int N, int K, float* ws, size_t ws_floats, cudaStream_t s);
 // split-K partials only (partial[chunks][M][N]); the consumer (head kernel or partial_reduce) sums them in chunk order

@@ -492,6 +492,118 @@ static void launch_smallk_tile(const float* x, const float* w, float* y, const C
   launch_k(conv_smallk_fwd_tile_kernel<KH, KW, CIN, PW>, (int)((nt + 255) / 256), 256, smem, s, x, w, y, g, relu, thr, segs, nt);
   SB_LAUNCHED();
 }
+// Small-K conv (stride 1) >> [ReLU] >> max-pool 2x2 stride 1 VALID in ONE pass: a thread owns 4 channels x PW pool outputs of pool
+// row pr, i.e. the conv outputs of rows pr, pr+1 and columns ow0 .. ow0+PW.  It stores its own conv row (the backward needs the
+// activations: ReLU mask and pool arg-max) and the pooled row; conv row pr+1 is recomputed by the thread below with the same FMA
+// order, so the stored activation and the pooled maximum are the same bits.  The conv output is never re-read.
+template <int KH, int KW, int CIN, int PW>
+__global__ void __launch_bounds__(256) conv_smallk_pool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                   float* __restrict__ y, float* __restrict__ pooled, ConvGeom g,
+                                                                   int relu, float thr, int segs, long long n_threads) {
+  pdl_prologue();
+  constexpr int K = KH * KW * CIN;
+  const int C4 = g.Cout >> 2;
+  extern __shared__ __align__(16) float swt[];  // filter [K][Cout]
+  for (int i = threadIdx.x; i < K * g.Cout; i += blockDim.x) swt[i] = w[i];
+  __syncthreads();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_threads) return;
+  const int OHp = g.OH - 1, OWp = g.OW - 1;
+  const int c4 = (int)(i % C4);
+  long long t = i / C4;
+  const int seg = (int)(t % segs); t /= segs;
+  const int pr = (int)(t % OHp);
+  const int b = (int)(t / OHp);
+  const int ow0 = seg * PW;
+  float4 acc[2][PW + 1];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int p = 0; p <= PW; ++p) acc[r][p] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int a = 0; a <= KH; ++a) {  // input row pr + a - PT feeds conv row pr (filter row a) and conv row pr+1 (filter row a-1)
+    const int ih = pr + a - g.PT;
+    const bool row_ok = ih >= 0 && ih < g.H;
+    const float* xr = x + ((long long)b * g.H + (row_ok ? ih : 0)) * g.W * CIN;
+    float xv[(PW + KW) * CIN];
+#pragma unroll
+    for (int q = 0; q < PW + KW; ++q) {
+      const int iw = ow0 + q - g.PL;
+      const bool ok = row_ok && iw >= 0 && iw < g.W;
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) xv[q * CIN + ci] = ok ? __ldg(xr + (long long)iw * CIN + ci) : 0.f;
+    }
+#pragma unroll
+    for (int bb = 0; bb < KW; ++bb)
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) {
+        if (a < KH) {
+          const float4 wv = *reinterpret_cast<const float4*>(&swt[((a * KW + bb) * CIN + ci) * g.Cout + c4 * 4]);
+#pragma unroll
+          for (int p = 0; p <= PW; ++p) {
+            const float v = xv[(p + bb) * CIN + ci];
+            acc[0][p].x = fmaf(v, wv.x, acc[0][p].x); acc[0][p].y = fmaf(v, wv.y, acc[0][p].y);
+            acc[0][p].z = fmaf(v, wv.z, acc[0][p].z); acc[0][p].w = fmaf(v, wv.w, acc[0][p].w);
+          }
+        }
+        if (a >= 1) {
+          const float4 wv = *reinterpret_cast<const float4*>(&swt[(((a - 1) * KW + bb) * CIN + ci) * g.Cout + c4 * 4]);
+#pragma unroll
+          for (int p = 0; p <= PW; ++p) {
+            const float v = xv[(p + bb) * CIN + ci];
+            acc[1][p].x = fmaf(v, wv.x, acc[1][p].x); acc[1][p].y = fmaf(v, wv.y, acc[1][p].y);
+            acc[1][p].z = fmaf(v, wv.z, acc[1][p].z); acc[1][p].w = fmaf(v, wv.w, acc[1][p].w);
+          }
+        }
+      }
+  }
+  if (relu) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int p = 0; p <= PW; ++p) {
+        float4& o = acc[r][p];
+        o.x = fmaxf(thr, o.x); o.y = fmaxf(thr, o.y); o.z = fmaxf(thr, o.z); o.w = fmaxf(thr, o.w);
+      }
+  }
+  // the conv activations: own row, and the last conv row from the last pool row
+  const int rows_out = pr == OHp - 1 ? 2 : 1;
+  for (int r = 0; r < rows_out; ++r) {
+    float* yo = y + (((long long)b * g.OH + pr + r) * g.OW + ow0) * g.Cout + c4 * 4;
+#pragma unroll
+    for (int p = 0; p < PW; ++p)
+      if (ow0 + p < g.OW) st4(yo + (long long)p * g.Cout, acc[r][p]);
+  }
+  float* po = pooled + (((long long)b * OHp + pr) * OWp + ow0) * g.Cout + c4 * 4;
+#pragma unroll
+  for (int p = 0; p < PW; ++p) {
+    if (ow0 + p >= OWp) break;
+    float4 m;
+    m.x = fmaxf(fmaxf(acc[0][p].x, acc[0][p + 1].x), fmaxf(acc[1][p].x, acc[1][p + 1].x));
+    m.y = fmaxf(fmaxf(acc[0][p].y, acc[0][p + 1].y), fmaxf(acc[1][p].y, acc[1][p + 1].y));
+    m.z = fmaxf(fmaxf(acc[0][p].z, acc[0][p + 1].z), fmaxf(acc[1][p].z, acc[1][p + 1].z));
+    m.w = fmaxf(fmaxf(acc[0][p].w, acc[0][p + 1].w), fmaxf(acc[1][p].w, acc[1][p + 1].w));
+    st4(po + (long long)p * g.Cout, m);
+  }
+}
+template <int KH, int KW, int CIN>
+static void launch_smallk_pool(const float* x, const float* w, float* y, float* pooled, const ConvGeom& g, int relu, float thr,
+                               cudaStream_t s) {
+  constexpr int PW = 4;
+  const int segs = (g.OW + PW - 1) / PW;  // covers the conv columns; the pool columns are one fewer
+  const long long nt = (long long)g.N * (g.OH - 1) * segs * (g.Cout / 4);
+  const size_t smem = (size_t)KH * KW * CIN * g.Cout * sizeof(float);
+  launch_k(conv_smallk_pool_fwd_kernel<KH, KW, CIN, PW>, (int)((nt + 255) / 256), 256, smem, s, x, w, y, pooled, g, relu, thr, segs, nt);
+  SB_LAUNCHED();
+}
+bool conv_smallk_pool_fwd(const float* x, const float* w, float* y, float* pooled, const ConvGeom& g, int relu, float thr, cudaStream_t s) {
+  if (g.SH != 1 || g.SW != 1 || g.OH < 2 || g.OW < 2 || g.Cout % 4) return false;
+  const int shape = g.KH * 100 + g.KW * 10 + g.Cin;
+  if (shape == 331) { launch_smallk_pool<3, 3, 1>(x, w, y, pooled, g, relu, thr, s); return true; }
+  if (shape == 333) { launch_smallk_pool<3, 3, 3>(x, w, y, pooled, g, relu, thr, s); return true; }
+  return false;
+}
+
 void conv_smallk_fwd(const float* x, const float* w, float* y, const ConvGeom& g, int relu, float thr, cudaStream_t s) {
   if (g.SH == 1 && g.SW == 1) {
     const int shape = g.KH * 100 + g.KW * 10 + g.Cin;
