@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SB_ABI_VERSION 2
+#define SB_ABI_VERSION 3
 
 typedef enum {
   SB_OK = 0,
@@ -58,7 +58,9 @@ typedef enum {
 } sb_layer_kind;
 
 typedef enum { SB_ACT_IDENTITY = 0, SB_ACT_SIGMOID = 1, SB_ACT_TANH = 2, SB_ACT_SOFTMAX = 3, SB_ACT_RELU = 4 } sb_activation;
-typedef enum { SB_PAD_VALID = 0, SB_PAD_SAME = 1 } sb_padding;
+/* math/nn/AllKernels.scala:39-103.  EXPLICIT (Conv2D only; Pool2D refuses it like the reference, :270-277) takes the four
+ * pad_* fields of the layer: `Explicit(height = (top, bottom), width = (left, right))`. */
+typedef enum { SB_PAD_VALID = 0, SB_PAD_SAME = 1, SB_PAD_EXPLICIT = 2 } sb_padding;
 typedef enum { SB_POOL_MAX = 0, SB_POOL_AVG = 1 } sb_pool_reduce;
 /* models/Regularization.scala:16-44: penalty lambda*sum|w|/2 (L1) or lambda*sum(w^2)/2 (L2) added to the loss
  * (models/Model.scala:97).  Gradients follow the reference's autodiff: L2 -> lambda*w; L1 -> |lambda|/2 per element
@@ -109,6 +111,7 @@ typedef struct {
                                    [3] forget-bias | moving_variance */
   int32_t reg_kind;             /* sb_regularization of this layer's "weights" (Dense kernel, Bias) */
   float reg_lambda;
+  int32_t pad_top, pad_bottom, pad_left, pad_right; /* Conv2D with SB_PAD_EXPLICIT (math/nn/AllKernels.scala:67-102) */
 } sb_layer_desc;
 
 typedef struct {

@@ -4,7 +4,7 @@ from . import _native as native
 from ._native import (AVG_MEAN, AVG_SPARK_CHAIN, AVG_WEIGHTS, COLL_NCCL, COLL_P2P, PREC_3XTF32, PREC_FP32, PREC_TF32,
                       IllegalArgument, NativeError, Unsupported)
 from .dsl import *  # noqa: F401,F403
-from .dsl import (Activate, Activation, AdaDelta, AdaGrad, Adam, Adamax, Algorithm, AMSGrad, BatchNorm, Bias,
+from .dsl import (Explicit, Activate, Activation, AdaDelta, AdaGrad, Adam, Adamax, Algorithm, AMSGrad, BatchNorm, Bias,
                   BinaryCrossentropy, CategoricalCrossentropy, Composed, Const, Conv2D, Dense, Flatten, GlorotNormal, GlorotUniform, HeNormal,
                   HeUniform, Identity, Initializer, L1, L2, LecunNormal, LecunUniform, LinearRegression, LogisticRegression, Loss, LSTM,
                   LSTMCell, MeanSquaredError, Nadam, Ones, Orthogonal, Pool2D, RandomNormal, RandomNormalTruncated, RandomUniform, ReLU, RMSProp,

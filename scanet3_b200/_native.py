@@ -13,7 +13,7 @@ SB_OK, SB_ERR_INVALID_ARG, SB_ERR_UNSUPPORTED, SB_ERR_CUDA, SB_ERR_NCCL, SB_ERR_
 # enums (mirror include/scanet_b200.h)
 LAYER_DENSE, LAYER_BIAS, LAYER_ACTIVATE, LAYER_FLATTEN, LAYER_CONV2D, LAYER_POOL2D, LAYER_BATCHNORM, LAYER_LSTM = range(1, 9)
 ACT_IDENTITY, ACT_SIGMOID, ACT_TANH, ACT_SOFTMAX, ACT_RELU = range(5)
-PAD_VALID, PAD_SAME = 0, 1
+PAD_VALID, PAD_SAME, PAD_EXPLICIT = 0, 1, 2
 POOL_MAX, POOL_AVG = 0, 1
 (INIT_ZEROS, INIT_ONES, INIT_CONST, INIT_RANDOM_UNIFORM, INIT_RANDOM_NORMAL, INIT_GLOROT_UNIFORM, INIT_HE_UNIFORM,
  INIT_LECUN_UNIFORM, INIT_ORTHOGONAL, INIT_TRUNCATED_NORMAL, INIT_GLOROT_NORMAL, INIT_HE_NORMAL, INIT_LECUN_NORMAL) = range(13)
@@ -51,7 +51,8 @@ class sb_layer_desc(C.Structure):
                 ("relu_threshold", C.c_float), ("window_h", C.c_int32), ("window_w", C.c_int32), ("stride_h", C.c_int32),
                 ("stride_w", C.c_int32), ("padding", C.c_int32), ("pool_reduce", C.c_int32), ("use_bias", C.c_int32),
                 ("trainable", C.c_int32), ("bn_momentum", C.c_float), ("bn_epsilon", C.c_float), ("bn_mode", C.c_int32),
-                ("bn_fused", C.c_int32), ("init", sb_initializer * 4), ("reg_kind", C.c_int32), ("reg_lambda", C.c_float)]
+                ("bn_fused", C.c_int32), ("init", sb_initializer * 4), ("reg_kind", C.c_int32), ("reg_lambda", C.c_float),
+                ("pad_top", C.c_int32), ("pad_bottom", C.c_int32), ("pad_left", C.c_int32), ("pad_right", C.c_int32)]
 
 
 class sb_model_desc(C.Structure):

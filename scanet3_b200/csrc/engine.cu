@@ -232,12 +232,26 @@ static void build_plan(sb_engine* e) {
         if (!d.trainable) SB_FAIL(SB_ERR_UNSUPPORTED, "frozen layers are outside the accelerated path");
         if (d.units <= 0 || d.window_h <= 0 || d.window_w <= 0 || d.stride_h <= 0 || d.stride_w <= 0)
           SB_FAIL(SB_ERR_INVALID_ARG, "Conv2D filters/kernel/strides must be positive");
-        if (d.padding != SB_PAD_VALID && d.padding != SB_PAD_SAME) SB_FAIL(SB_ERR_UNSUPPORTED, "EXPLICIT padding is unsupported");
+        if (d.padding != SB_PAD_VALID && d.padding != SB_PAD_SAME && d.padding != SB_PAD_EXPLICIT)
+          SB_FAIL(SB_ERR_INVALID_ARG, "unknown padding kind");
         ConvGeom& g = L.cg;
         g.N = (int)cur.d[0]; g.H = (int)cur.d[1]; g.W = (int)cur.d[2]; g.Cin = (int)cur.d[3];
         g.Cout = d.units; g.KH = d.window_h; g.KW = d.window_w; g.SH = d.stride_h; g.SW = d.stride_w;
-        conv_pad(d.padding, g.H, g.KH, g.SH, &g.OH, &g.PT);
-        conv_pad(d.padding, g.W, g.KW, g.SW, &g.OW, &g.PL);
+        if (d.padding == SB_PAD_EXPLICIT) {
+          // Explicit(height = (top, bottom), width = (left, right)) (math/nn/AllKernels.scala:67-102).  The kernels need the
+          // leading pads only: rows / columns past the input are zero whichever pad they belong to; bottom / right enter
+          // through the output size.  TF floors where the reference's `size` ceils: equal exactly when the padding "fits".
+          if (d.pad_top < 0 || d.pad_bottom < 0 || d.pad_left < 0 || d.pad_right < 0) SB_FAIL(SB_ERR_INVALID_ARG, "negative explicit padding");
+          const int th = g.H + d.pad_top + d.pad_bottom - g.KH, tw = g.W + d.pad_left + d.pad_right - g.KW;
+          if (th < 0 || tw < 0) SB_FAIL(SB_ERR_INVALID_ARG, "Conv2D output would be empty");
+          if (th % g.SH || tw % g.SW)
+            SB_FAIL(SB_ERR_INVALID_ARG, "explicit padding does not fit the strides (the reference's shape and TensorFlow's would differ)");
+          g.OH = th / g.SH + 1; g.PT = d.pad_top;
+          g.OW = tw / g.SW + 1; g.PL = d.pad_left;
+        } else {
+          conv_pad(d.padding, g.H, g.KH, g.SH, &g.OH, &g.PT);
+          conv_pad(d.padding, g.W, g.KW, g.SW, &g.OW, &g.PL);
+        }
         if (g.OH <= 0 || g.OW <= 0) SB_FAIL(SB_ERR_INVALID_ARG, "Conv2D output would be empty");
         L.p_w = add_param(e, pre + "weights", {(int64_t)g.KH, (int64_t)g.KW, (int64_t)g.Cin, (int64_t)g.Cout}, SB_ROLE_WEIGHT,
                           SB_AGG_AVG, d.init[0], li);

@@ -269,9 +269,27 @@ Valid, Same = "Valid", "Same"
 _PAD = {Valid: N.PAD_VALID, Same: N.PAD_SAME}
 
 
+class Explicit:
+    """`Explicit(height = (pad_top, pad_bottom), width = (pad_left, pad_right))` (math/nn/AllKernels.scala:67-102); Conv2D only."""
+
+    def __init__(self, height: Tuple[int, int], width: Tuple[int, int]):
+        self.height, self.width = (int(height[0]), int(height[1])), (int(width[0]), int(width[1]))
+
+    def __repr__(self):
+        return f"Explicit({self.height},{self.width})"
+
+    def __eq__(self, other):
+        return isinstance(other, Explicit) and (self.height, self.width) == (other.height, other.width)
+
+    def __hash__(self):
+        return hash((self.height, self.width))
+
+
 def _pad_code(padding):
+    if isinstance(padding, Explicit):
+        return N.PAD_EXPLICIT
     if padding not in _PAD:
-        raise N.Unsupported(N.SB_ERR_UNSUPPORTED, f"padding {padding!r}: only Valid/Same are on the accelerated path")
+        raise ValueError(f"unknown padding {padding!r}")
     return _PAD[padding]
 
 
@@ -284,6 +302,8 @@ class _Conv2DKernel(Layer):
         d = self._desc(N.LAYER_CONV2D, units=self.filters, window_h=self.kernel[0], window_w=self.kernel[1],
                        stride_h=self.strides[0], stride_w=self.strides[1], padding=_pad_code(self.padding),
                        trainable=int(self.trainable))
+        if isinstance(self.padding, Explicit):
+            (d.pad_top, d.pad_bottom), (d.pad_left, d.pad_right) = self.padding.height, self.padding.width
         d.init[0] = self.initializer.to_native()
         return d
 
@@ -313,7 +333,7 @@ class Pool2D(Layer):
     def __init__(self, window=(2, 2), strides=(1, 1), padding=Valid, format="NHWC", reduce="Max"):
         if format != "NHWC":
             raise N.Unsupported(N.SB_ERR_UNSUPPORTED, "NCHW is outside the accelerated path (SURVEY 8b)")
-        if padding not in _PAD:
+        if isinstance(padding, Explicit) or padding not in _PAD:
             raise ValueError("requirement failed: only [Same, Valid] paddings are supported")
         self.window, self.strides, self.padding, self.reduce = tuple(window), tuple(strides), padding, reduce
 

@@ -23,8 +23,11 @@ def build_models(spec, seed=1):
             sl.append(S.Dense(units, _SACT[act], kernelInitializer=S.GlorotUniform(seed)))
         elif kind == "conv":
             _, filters, act, kernel, strides, padding, bias = it
-            ol.append(O.Conv2D(filters, kernel, strides, padding.lower(), _OACT[act], bias, O.GlorotUniform(seed)))
-            sl.append(S.Conv2D(filters, kernel, strides, padding, activation=_SACT[act], bias=bias,
+            # padding: "Valid" | "Same" | ((top, bottom), (left, right)) for Explicit
+            opad = padding.lower() if isinstance(padding, str) else padding
+            spad = padding if isinstance(padding, str) else S.Explicit(*padding)
+            ol.append(O.Conv2D(filters, kernel, strides, opad, _OACT[act], bias, O.GlorotUniform(seed)))
+            sl.append(S.Conv2D(filters, kernel, strides, spad, activation=_SACT[act], bias=bias,
                                kernelInitializer=S.GlorotUniform(seed)))
         elif kind == "pool":
             _, window, strides, padding = it

@@ -121,8 +121,9 @@ FIL = np.array([[2, 3], [0, 1]], f32).reshape(2, 2, 1, 1)
     ("Same", (2, 2), [[10, 6, 2], [7, 16, 0], [0, 9, 4]]),
     ("Valid", (1, 1), [[10, 10, 6, 6], [12, 15, 13, 13], [7, 11, 16, 7], [10, 7, 4, 7]]),
     ("Valid", (2, 2), [[10, 6], [7, 16]]),
+    (S.Explicit(height=(1, 0), width=(1, 0)), (2, 2), [[2, 2, 1], [4, 15, 13], [6, 7, 7]]),  # KernelsSpec.scala:105-119
 ])
-def test_conv2d_goldens(padding, strides, expected):  # math/nn/KernelsSpec.scala:45-106; Conv2DLayerSpec.scala:13-36
+def test_conv2d_goldens(padding, strides, expected):  # math/nn/KernelsSpec.scala:45-119; Conv2DLayerSpec.scala:13-36
     exp = np.array(expected, f32)
     e = make_engine(S.Conv2D(1, (2, 2), strides, padding), S.MeanSquaredError, S.SGD(), 1, (5, 5, 1), exp.shape + (1,))
     e.set_param("weights", FIL)
@@ -597,3 +598,17 @@ def test_train_batches_matches_step_by_step(n_batches):
         p, op, loss = O.train_step(lm, O.Adam(rate=0.01), x[j * B:(j + 1) * B], y[j * B:(j + 1) * B], p, op, it0 + j + 1)
         np.testing.assert_allclose(got[j], loss, rtol=1e-4)
     ea.close(); eb.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Explicit padding (math/nn/AllKernels.scala:67-102)
+# ---------------------------------------------------------------------------------------------------------------
+def test_explicit_padding_trajectory_and_errors():
+    # asymmetric pads, stride 2 on the second conv (pads chosen to fit), bias + sigmoid: forward, wgrad, dgrad and updates
+    spec = [("conv", 4, "relu", (3, 3), (1, 1), ((2, 1), (0, 3)), False), ("pool", (2, 2), (1, 1), "Valid"),
+            ("conv", 8, "sigmoid", (2, 2), (2, 2), ((1, 0), (1, 1)), True), ("flatten",), ("dense", 5, "softmax")]
+    run_trajectory(spec, "cce", "adam", dict(rate=0.01), batch=6, in_shape=(7, 6, 2), classes=5, steps=8)
+    with pytest.raises(S.IllegalArgument):  # pads that do not fit the stride: the reference's ceil and TF's floor would disagree
+        make_engine(S.Conv2D(2, (2, 2), (2, 2), S.Explicit((1, 0), (0, 0))), S.MeanSquaredError, S.SGD(), 1, (4, 4, 1), (3, 2, 2))
+    with pytest.raises(ValueError):         # Pool2D refuses Explicit like the reference (KernelsSpec.scala:258-268)
+        S.Pool2D(padding=S.Explicit((1, 0), (1, 0)))

@@ -55,6 +55,8 @@ CONV_STACKS = [
                          ("conv", 256, "tanh", (3, 3), (1, 1), "Valid", False), ("flatten",), ("dense", 10, "softmax")], 6, (10, 10, 3)),
     ("same_pad_tanh", [("conv", 32, "tanh", (3, 3), (1, 1), "Valid", False), ("conv", 64, "tanh", (3, 3), (1, 1), "Same", False),
                        ("flatten",), ("dense", 10, "softmax")], 4, (9, 9, 2)),
+    ("explicit_pad_tanh", [("conv", 32, "tanh", (3, 3), (1, 1), "Valid", False), ("conv", 64, "tanh", (3, 3), (1, 1), ((1, 2), (0, 1)), False),
+                           ("flatten",), ("dense", 10, "softmax")], 4, (9, 9, 2)),
     ("ragged_1x3_tanh", [("conv", 32, "tanh", (2, 2), (1, 1), "Valid", False), ("conv", 64, "tanh", (1, 3), (1, 1), "Valid", False),
                          ("flatten",), ("dense", 10, "softmax")], 7, (5, 37, 2)),
 ]
