@@ -112,6 +112,7 @@ typedef struct {
   int32_t reg_kind;             /* sb_regularization of this layer's "weights" (Dense kernel, Bias) */
   float reg_lambda;
   int32_t pad_top, pad_bottom, pad_left, pad_right; /* Conv2D with SB_PAD_EXPLICIT (math/nn/AllKernels.scala:67-102) */
+  int32_t return_sequence;      /* LSTM: output (batch, time, units) instead of the last step (layer/RNN.scala:21-27, 69-71) */
 } sb_layer_desc;
 
 typedef struct {

@@ -770,6 +770,7 @@ class LSTMCell(Layer):
         dacts = {"forget": dc * c_prev, "input": dc * g, "gate": dc * i, "output": do}
         dc_prev = dc * f
         dh_prev = np.zeros_like(h_prev)
+        dx = np.zeros_like(x)
         grads = {}
         for gname in self.GATES:
             dz = self._act(gname).bwd(dacts[gname], zs[gname], acts[gname])
@@ -778,6 +779,8 @@ class LSTMCell(Layer):
             if self.bias:
                 grads[f"{gname}/1/weights"] = np.sum(dz, axis=0, dtype=dh.dtype)
             dh_prev = dh_prev + dz @ p[f"{gname}/0/recurrent_weights"].T
+            dx = dx + dz @ p[f"{gname}/0/kernel_weights"].T  # MatMul grad w.r.t. the step input (alg/AllKernels.scala:370-389)
+        self._last_dx = dx
         return dh_prev, dc_prev, grads
 
     def __repr__(self):
@@ -833,15 +836,18 @@ class RNN(Layer):
         grads: Dict[str, np.ndarray] = {}
         dstate = np.zeros((b, u), g.dtype)  # dL/d(recurrent input of step t+1)
         dc = np.zeros((b, u), g.dtype)
+        dx = np.zeros(xshape, g.dtype) if (need_dx and lstm) else None
         for t in range(T - 1, -1, -1):
             dout = g[:, t, :] if self.return_sequence else (g if t == T - 1 else np.zeros((b, u), g.dtype))
             if lstm:
                 dstate, dc, gr = self.cell.step_bwd(dout + dstate, dc, caches[t], p)
+                if dx is not None:
+                    dx[:, t, :] = self.cell._last_dx  # a stacked RNN: the layer below needs dL/d(sequence input)
             else:
                 dstate, gr = self.cell.step_bwd(dout, dstate, caches[t], p)
             for k, v in gr.items():
                 grads[k] = grads[k] + v if k in grads else v
-        return None, grads  # gradient w.r.t. the sequence input is never requested on this path
+        return dx, grads  # (SimpleRNN: the gradient w.r.t. the sequence input is not restated)
 
     def __repr__(self):
         return f"RNN({self.cell!r})"

@@ -304,8 +304,14 @@ static void build_plan(sb_engine* e) {
           if (d.use_bias)
             L.p_aux[gi * 3 + 2] = add_param(e, gp + "1/weights", {U}, SB_ROLE_WEIGHT, SB_AGG_AVG, gi == 0 ? d.init[3] : d.init[2], li);
         }
-        out.rank = 2;
-        out.d[1] = U;
+        if (d.return_sequence) {  // (batch, time, units): `joinAlong(outputs, 1)` (layer/RNN.scala:69-71)
+          out.rank = 3;
+          out.d[1] = cur.d[1];
+          out.d[2] = U;
+        } else {
+          out.rank = 2;
+          out.d[1] = U;
+        }
         any_trainable_before = true;
         break;
       }

@@ -44,6 +44,7 @@ struct LstmWs {
   float* db_cat = nullptr;   // [4U]
   float* dwkb_cat = nullptr; // [1 + F][4U]: db_cat row followed by dWk_cat rows (F <= 8: one fused pass)
   float* dx_tm = nullptr;    // [T, B, F] (only when the input gradient is needed)
+  float* dout_tm = nullptr;  // [T, B, U] time-major copy of dLoss/d(output sequence) (returnSequence only)
   // tcgen05 TF32 plans (SB_PREC_TF32): one plan per contraction serves every time step through the tensor maps' slice coordinate
   TcGemm* g_fwd = nullptr;   // Z_t = H_{t-1} . Wr_cat           A slice t of h, C slice t of acts
   TcGemm* g_bwd = nullptr;   // dH_{t-1} = dZ_t . Wr_cat^T       A slice t of acts
@@ -149,8 +150,8 @@ __global__ void __launch_bounds__(256) lstm_gates_fwd_kernel(float* __restrict__
 //   do = dh*ac ; dc = act'(dh*o ; ac) + dc_next ; df = dc*c_prev ; di = dc*g ; dg = dc*i ; dz_G = act_G'(d_G ; a_G) ; dc_prev = dc*f
 __global__ void __launch_bounds__(256) lstm_gates_bwd_kernel(float* __restrict__ acts_dz, const float* __restrict__ c_t,
                                                              const float* __restrict__ c_prev, const float* __restrict__ dh,
-                                                             float* __restrict__ dc_io, int B, int U, int first, int last, int act,
-                                                             int ract) {
+                                                             const float* __restrict__ dh_seq, float* __restrict__ dc_io, int B, int U,
+                                                             int first, int last, int act, int ract) {
   pdl_prologue();
   const long long n = (long long)B * U;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -160,7 +161,8 @@ __global__ void __launch_bounds__(256) lstm_gates_bwd_kernel(float* __restrict__
     const float4 a4 = *q;
     const float f = a4.x, ig = a4.y, g = a4.z, o = a4.w;
     const float ac = actf(c_t[i], act);
-    const float dhv = dh[i];
+    // returnSequence: this step's own output gradient joins the recurrent one (`dout + dstate`, oracle RNN.backward)
+    const float dhv = dh_seq ? __fadd_rn(dh_seq[i], dh[i]) : dh[i];
     const float d_o = __fmul_rn(dhv, ac);
     float dc = actg(__fmul_rn(dhv, o), ac, act);
     if (!last) dc = __fadd_rn(dc, dc_io[i]);
@@ -264,6 +266,7 @@ LstmWs* ws_of(sb_engine* e, LayerPlan& L) {
   w->db_cat = dalloc(4 * U);
   if (F <= 8) w->dwkb_cat = dalloc((F + 1) * 4 * U);
   if (L.need_dx) w->dx_tm = dalloc(T * B * F);
+  if (L.d.return_sequence) w->dout_tm = dalloc(T * B * U);
   if (e->train.precision != SB_PREC_FP32 && B * U * 4 * U >= (1 << 22) && U % 32 == 0) {
     const int x3 = e->train.precision == SB_PREC_3XTF32 ? 1 : 0;
     w->g_fwd = tc_gemm_create(0, 1, w->h, (int)T + 1, w->wr_cat, 1, w->acts, (int)T, (int)B, (int)(4 * U), (int)U, 0, nullptr, 0, e->device, x3);
@@ -271,7 +274,7 @@ LstmWs* ws_of(sb_engine* e, LayerPlan& L) {
     w->g_dwr = tc_gemm_create(1, 1, w->h, 1, w->acts, 1, w->dwr_cat, 1, (int)U, (int)(4 * U), (int)(T * B), 1, e->ws, e->ws_floats,
                               e->device, x3);
     const char* fe = getenv("SB_LSTM_FUSED_EPILOGUE");
-    w->fused_epilogue = fe && fe[0] == '1' && w->g_fwd && w->g_bwd;
+    w->fused_epilogue = fe && fe[0] == '1' && w->g_fwd && w->g_bwd && !L.d.return_sequence;
   }
   L.lstm = w;
   return w;
@@ -354,8 +357,12 @@ void lstm_forward(sb_engine* e, LayerPlan& L, int) {
       default: launch_gates_fwd<8>(w, z, x_t, xw_t, c_prev, c_t, h_t, first, act, ract, L.d.use_bias, s); break;
     }
   }
-  // the layer output is the last hidden state (returnSequence = false)
-  SB_CUDA(cudaMemcpyAsync(e->acts[L.buf_out], w->h + (long long)T * BU, (size_t)BU * 4, cudaMemcpyDeviceToDevice, s));
+  if (L.d.return_sequence) {  // (batch, time, units) <- the time-major hidden states h_0 .. h_{T-1}
+    launch_k(lstm_transpose_kernel, ew_grid((long long)T * BU), 256, 0, s, w->h + BU, e->acts[L.buf_out], T, B, U);
+    SB_LAUNCHED();
+  } else {  // the last hidden state
+    SB_CUDA(cudaMemcpyAsync(e->acts[L.buf_out], w->h + (long long)T * BU, (size_t)BU * 4, cudaMemcpyDeviceToDevice, s));
+  }
 }
 
 void lstm_backward(sb_engine* e, LayerPlan& L, int) {
@@ -365,12 +372,19 @@ void lstm_backward(sb_engine* e, LayerPlan& L, int) {
   const long long BU = (long long)B * U;
   const int act = L.d.activation, ract = L.d.recurrent_activation;
   const float* dh = e->dacts[L.buf_out];  // dLoss/dh_{T-1}
+  const bool seq = L.d.return_sequence != 0;
+  if (seq) {  // dLoss/d(output)[B, T, U] -> time-major; step t adds its slice to the recurrent gradient
+    launch_k(lstm_transpose_kernel, ew_grid((long long)T * BU), 256, 0, s, e->dacts[L.buf_out], w->dout_tm, B, T, U);
+    SB_LAUNCHED();
+    dh = w->dout_tm + (long long)(T - 1) * BU;
+  }
   for (int t = T - 1; t >= 0; --t) {
     float* a = w->acts + (long long)t * B * 4 * U;
     const float* c_t = w->c + (long long)t * BU;
     const float* c_prev = t ? w->c + (long long)(t - 1) * BU : nullptr;
     if (t == T - 1 || !w->fused_epilogue) {  // fused mode: the gate backward of step t < T-1 ran in the epilogue of step t+1
-      launch_k(lstm_gates_bwd_kernel, ew_grid(BU), 256, 0, s, a, c_t, c_prev, dh, w->dc, B, U, t == 0, t == T - 1, act, ract);
+      const float* dh_seq = (seq && t < T - 1) ? w->dout_tm + (long long)t * BU : nullptr;
+      launch_k(lstm_gates_bwd_kernel, ew_grid(BU), 256, 0, s, a, c_t, c_prev, dh, dh_seq, w->dc, B, U, t == 0, t == T - 1, act, ract);
       SB_LAUNCHED();
     }
     if (t > 0) {
@@ -433,7 +447,7 @@ void lstm_free(sb_engine* e) {
     if (!L.lstm) continue;
     LstmWs* w = (LstmWs*)L.lstm;
     for (float* p : {w->wr_cat, w->wk_cat, w->b_cat, w->x_tm, w->acts, w->c, w->h, w->xw, w->dh, w->dc, w->dwr_cat, w->dwk_cat,
-                     w->db_cat, w->dwkb_cat, w->dx_tm})
+                     w->db_cat, w->dwkb_cat, w->dx_tm, w->dout_tm})
       cudaFree(p);
     tc_gemm_destroy(w->g_fwd); tc_gemm_destroy(w->g_bwd); tc_gemm_destroy(w->g_dwr);
     delete w;

@@ -374,16 +374,17 @@ class RNN(Layer):
     """layer/RNN.scala:27-94 with an LSTMCell (the only cell on the accelerated path)."""
 
     def __init__(self, cell: "LSTMCell", returnSequence=False, stateful=False):
-        if returnSequence or stateful:
-            raise N.Unsupported(N.SB_ERR_UNSUPPORTED, "returnSequence / stateful RNNs are outside the accelerated path")
+        if stateful:
+            raise N.Unsupported(N.SB_ERR_UNSUPPORTED, "stateful RNNs are outside the accelerated path")
         if not isinstance(cell, LSTMCell):
             raise N.Unsupported(N.SB_ERR_UNSUPPORTED, "only LSTMCell is on the accelerated path")
-        self.cell = cell
+        self.cell, self.returnSequence = cell, bool(returnSequence)
 
     def to_native(self):
         c = self.cell
         d = self._desc(N.LAYER_LSTM, units=c.units, activation=c.activation.code,
-                       recurrent_activation=c.recurrentActivation.code, use_bias=int(c.bias))
+                       recurrent_activation=c.recurrentActivation.code, use_bias=int(c.bias),
+                       return_sequence=int(self.returnSequence))
         for i, init in enumerate((c.kernelInitializer, c.recurrentInitializer, c.biasInitializer, c.biasForgetInitializer)):
             d.init[i] = init.to_native()
         return d

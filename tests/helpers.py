@@ -41,9 +41,11 @@ def build_models(spec, seed=1):
             ol.append(O.BatchNorm(momentum=momentum, bn_mode=mode))
             sl.append(S.BatchNorm(momentum=momentum, bnMode=mode))
         elif kind == "lstm":
-            _, units = it
-            ol.append(O.LSTM(units, kernel_initializer=O.GlorotUniform(seed), recurrent_initializer=O.Orthogonal(seed=seed)))
-            sl.append(S.LSTM(units, kernelInitializer=S.GlorotUniform(seed), recurrentInitializer=S.Orthogonal(seed=seed)))
+            units, seq = it[1], (len(it) > 2 and bool(it[2]))  # ("lstm", units[, return_sequence])
+            ol.append(O.LSTM(units, return_sequence=seq, kernel_initializer=O.GlorotUniform(seed),
+                             recurrent_initializer=O.Orthogonal(seed=seed)))
+            sl.append(S.LSTM(units, kernelInitializer=S.GlorotUniform(seed), recurrentInitializer=S.Orthogonal(seed=seed),
+                             returnSequence=seq))
         elif kind == "act":
             ol.append(O.Activate(_OACT[it[1]]))
             sl.append(S.Activate(_SACT[it[1]]))

@@ -91,3 +91,63 @@ def test_lstm_resident_epoch_and_graph_determinism():
     assert res[0][:2] == res[1][:2]
     for k in res[0][2]:
         assert np.array_equal(res[0][2][k], res[1][2][k]), k
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# returnSequence = true (layer/RNN.scala:21-27, 69-71): the sequence output, and LSTMs stacked on it
+# ---------------------------------------------------------------------------------------------------------------
+SEQ_MODELS = {
+    "sequence_into_dense": ([("lstm", 6, True), ("flatten",), ("dense", 1, "tanh")], 5, 3, 7),
+    "stacked": ([("lstm", 8, True), ("lstm", 5), ("dense", 1, "tanh")], 6, 2, 9),
+    "stacked_wide_input_projection": ([("lstm", 12, True), ("lstm", 4, True), ("lstm", 3), ("dense", 1, "tanh")], 4, 3, 5),
+}
+
+
+@pytest.mark.parametrize("name", list(SEQ_MODELS))
+def test_lstm_return_sequence_gradients_match_oracle(name):
+    spec, t, f, batch = SEQ_MODELS[name]
+    om, sm = build_models(spec)
+    x, y = synth_series(batch, t, f, 17)
+    e = S.Engine(sm, S.MeanSquaredError, S.Adam(), batch, (t, f), (1,), device=0)
+    _, mp, _ = O.init_params(om, O.Adam(), (batch, t, f))
+    assert set(e.model_param_paths()) == set(mp.keys())
+    e.set_params(mp)
+    e.init_opt_params()
+    ol, og, _ = O.LossModel(om, O.MeanSquaredError).grad_stateful(x, y, mp)
+    gl, gg = e.compute_grads(x, y)
+    assert abs(gl - float(ol)) <= 2e-5 * abs(float(ol)) + 1e-7
+    for k, v in og.items():
+        np.testing.assert_allclose(gg[k], v, rtol=3e-4, atol=3e-6, err_msg=k)
+    np.testing.assert_allclose(e.predict(x), O.model_forward(om, x, mp)[0], rtol=2e-5, atol=2e-6)
+    e.close()
+
+
+def test_lstm_return_sequence_output_shape_and_values():
+    om, sm = build_models([("lstm", 4, True)])
+    x = synth_series(3, 5, 2, 23)[0]
+    e = S.Engine(sm, S.MeanSquaredError, S.SGD(), 3, (5, 2), (5, 4), device=0)
+    assert tuple(e.output_shape) == (3, 5, 4)                      # (batch, time, units)
+    _, mp, _ = O.init_params(om, O.SGD(), (3, 5, 2))
+    e.set_params(mp)
+    np.testing.assert_allclose(e.predict(x), O.model_forward(om, x, mp)[0], rtol=2e-5, atol=2e-6)
+    e.close()
+
+
+def test_stacked_lstm_trajectory():
+    spec = [("lstm", 8, True), ("lstm", 6), ("dense", 1, "tanh")]
+    om, sm = build_models(spec)
+    batch, t, f, steps, rate = 16, 6, 2, 8, 2e-3
+    x, y = synth_series(batch * steps, t, f, 29)
+    e = S.Engine(sm, S.MeanSquaredError, S.Adam(rate), batch, (t, f), (1,), device=0)
+    oalg = O.Adam(rate)
+    _, mp, op = O.init_params(om, oalg, (batch, t, f))
+    e.set_params(mp)
+    e.init_opt_params()
+    lm = O.LossModel(om, O.MeanSquaredError)
+    for s_ in range(1, steps + 1):
+        xb, yb = x[(s_ - 1) * batch:s_ * batch], y[(s_ - 1) * batch:s_ * batch]
+        gl = e.train_step(xb, yb, s_)
+        mp, op, ol = O.train_step(lm, oalg, xb, yb, mp, op, s_)
+        assert abs(gl - float(ol)) <= 1e-4 * abs(float(ol)) + 1e-7, (s_, gl, float(ol))
+    assert_params_close(e.get_model_params(), mp, 2e-3, 3e-5, f"after {steps} steps")
+    e.close()

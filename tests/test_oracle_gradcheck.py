@@ -44,6 +44,12 @@ def test_lstm_bptt_gradients():
              O.MeanSquaredError, (3, 6, 2), 1)
 
 
+def test_stacked_lstm_gradients_through_the_returned_sequence():  # returnSequence = true feeds a second LSTM (RNN.scala:24-25, 70)
+    model = (O.LSTM(4, return_sequence=True, kernel_initializer=O.GlorotUniform(1), recurrent_initializer=O.Orthogonal(seed=1))
+             >> O.LSTM(3, kernel_initializer=O.GlorotUniform(2), recurrent_initializer=O.Orthogonal(seed=2)) >> O.Dense(1, O.Tanh))
+    fd_check(model, O.MeanSquaredError, (3, 5, 2), 1)
+
+
 def test_simple_rnn_gradients_with_the_pre_activation_state_quirk():
     fd_check(O.SimpleRNN(4, kernel_initializer=O.GlorotUniform(1), recurrent_initializer=O.Orthogonal(seed=1)) >> O.Dense(1),
              O.MeanSquaredError, (3, 5, 2), 1)
