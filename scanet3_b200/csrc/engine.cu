@@ -483,8 +483,12 @@ static void plan_fusions(sb_engine* e) {
 
 static void allocate(sb_engine* e) {
   SB_CUDA(cudaSetDevice(e->device));
-  SB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-  SB_CUDA(cudaStreamCreateWithFlags(&e->bstream, cudaStreamNonBlocking));  // backward side branch (created outside any capture)
+  // the main stream outranks the backward side branch: filter gradients fill SMs the input-gradient chain leaves idle, they must
+  // not delay it (stream priorities are captured into the graph's kernel nodes)
+  int prio_lo = 0, prio_hi = 0;
+  SB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  SB_CUDA(cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, prio_hi));
+  SB_CUDA(cudaStreamCreateWithPriority(&e->bstream, cudaStreamNonBlocking, prio_lo));  // created outside any capture
   SB_CUDA(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
   SB_CUDA(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
   // the arena allocation carries a tail of cross-GPU flags / scalars behind the tensors (one IPC handle maps both)
@@ -604,6 +608,7 @@ static void run_forward(sb_engine* e, int mode) {
           e->head_chunks = 0;
           if (e->head_fused && li == nl - 3 && mode != FWD_INFER) {
             // split-K partials stay in the workspace: the head kernel (next launch) sums them in chunk order
+            if (tc_head_fwd(e, L, in, P(e, L.p_w), e->ws, e->ws_floats, &e->head_chunks)) break;
             if (dense_head_fwd(in, P(e, L.p_w), e->ws, &e->head_chunks, M, N, K, e->ws_floats, s)) break;
           } else if (dense_skinny_fwd(in, P(e, L.p_w), out, M, N, K, e->ws, e->ws_floats, s)) {
             break;
@@ -701,6 +706,18 @@ static void run_loss(sb_engine* e, bool with_grad) {
   }
 }
 
+// Side branch of the backward pass: work that only the optimizer waits for (filter gradients) is queued on `bstream` behind the
+// point the main stream has reached; successive branches simply queue up there (in order), and the main stream joins the last
+// one at the end of run_backward.  Inside a captured graph these become parallel branches.
+static void side_branch_begin(sb_engine* e) {
+  SB_CUDA(cudaEventRecord(e->ev_fork, e->stream));
+  SB_CUDA(cudaStreamWaitEvent(e->bstream, e->ev_fork, 0));
+}
+static void side_branch_end(sb_engine* e) {
+  SB_CUDA(cudaEventRecord(e->ev_join, e->bstream));
+  e->bwd_forked = true;
+}
+
 static void run_backward(sb_engine* e) {
   cudaStream_t s = e->stream;
   const int nl = (int)e->L.size();
@@ -794,12 +811,9 @@ static void run_backward(sb_engine* e) {
             ddone = tc_conv_dgrad(e, L, li);
           }
           if (fork) {
-            if (e->bwd_forked) SB_CUDA(cudaStreamWaitEvent(s, e->ev_join, 0));  // one side branch at a time keeps the join simple
-            SB_CUDA(cudaEventRecord(e->ev_fork, s));
-            SB_CUDA(cudaStreamWaitEvent(e->bstream, e->ev_fork, 0));
+            side_branch_begin(e);
             wdone = tc_conv_wgrad(e, L, li, e->bstream);
-            SB_CUDA(cudaEventRecord(e->ev_join, e->bstream));
-            e->bwd_forked = true;
+            side_branch_end(e);
             if (!wdone) SB_FAIL(SB_ERR_CUDA, "tensor-core filter gradient rejected a planned shape");
           }
         }

@@ -72,6 +72,7 @@ struct LayerPlan {
   bool fast_skinny = false;       // Dense with <= 16 outputs and a long reduction: split-K skinny kernels
   int tc_kind = 0;                // 0 none, otherwise a tcgen05 kernel variant
   void* tc_plan = nullptr;        // opaque plan of the tensor-core path (TMA descriptors, buffers)
+  void* head_tc = nullptr;        // opaque plan of the tensor-core classifier-head forward (tc.cu)
   void* lstm = nullptr;           // opaque LSTM workspace
 };
 

@@ -1190,8 +1190,10 @@ void tc_plan_layers(sb_engine* e) {
   }
 }
 
+static void head_tc_free(LayerPlan& L);  // defined with the kernel below
 void tc_free_layers(sb_engine* e) {
   for (auto& L : e->L) {
+    head_tc_free(L);
     if (L.tc_plan && L.tc_kind == 2) {
       DenseTcPlan* D = (DenseTcPlan*)L.tc_plan;
       tc_gemm_destroy(D->fwd); tc_gemm_destroy(D->wgrad); tc_gemm_destroy(D->dgrad);
@@ -1266,6 +1268,144 @@ bool tc_conv_fwd(sb_engine* e, LayerPlan& L, int) {
   }
   launch_k(conv_igemm_kernel, P->fwd_grid, kIgemmThreads, P->fwd_smem, e->stream, P->map_x_fwd, P->map_w_fwd, P->fwd);
   SB_LAUNCHED();
+  return true;
+}
+
+// =====================================================================================================================
+// Skinny classifier head forward on the tensor cores:  Z[M <= 128, N <= 16] = X[M, K] . W[K, N], split-K.
+// CTA c owns K range [c*KC, c*KC + KC): its X tiles [128 rows x 32 k] arrive by TMA (rows >= M are zero fill), one mbarrier per
+// tile so the MMAs start with the first tile; the W slab is tiny (KC x N floats, row pitch N*4 bytes is not TMA-able) and is
+// written by the threads straight into the K-major SWIZZLE_128B layout TMA would have produced (row n, 16-byte chunk
+// (k/4) ^ (n%8)).  D[128, 16] accumulates in TMEM; partial[c][m][n] feeds the fused bias+softmax+loss kernel as before.
+// The FFMA version (kernels_fast.cu) spends as long on its multiply phase as on the fill; here only the fill remains.
+// =====================================================================================================================
+struct HeadFwdParams {
+  int M, K, N, KC, chunks;
+  const float* w;
+  float* partial;
+};
+constexpr int kHeadTcThreads = 192;
+constexpr int kHeadTcMaxTiles = 10;
+
+__global__ void __launch_bounds__(kHeadTcThreads, 1) head_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const HeadFwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int nkt_max = p.KC / 32;
+  uint8_t* sm_a = smem;                                  // nkt x [128 rows x 128 B]
+  uint8_t* sm_b = smem + (size_t)nkt_max * 16384;        // nkt x [16 rows x 128 B]
+  uint64_t* full_bar = (uint64_t*)(sm_b + (size_t)nkt_max * 2048);
+  uint64_t* done_bar = full_bar + kHeadTcMaxTiles;
+  uint32_t* tmem_slot = (uint32_t*)(done_bar + 1);
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * p.KC;
+  const int nkt = min(nkt_max, (p.K - k0) / 32);
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_x);
+    for (int t = 0; t < nkt_max; ++t) mbar_init(&full_bar[t], 1);
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 32);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // the weights were last written by the optimizer, never by the kernel just before this one: stage them before the
+  // programmatic-dependency wait.  Element (n, k) of tile t: row n (128 B), chunk ((k%32)/4) ^ (n%8), word k%4.
+  for (int i = threadIdx.x; i < nkt * 32 * 16; i += blockDim.x) {
+    const int n = i & 15, k = i >> 4;
+    const float v = n < p.N ? __ldg(p.w + (size_t)(k0 + k) * p.N + n) : 0.f;
+    const int t = k >> 5, kk = k & 31;
+    *reinterpret_cast<float*>(sm_b + (size_t)t * 2048 + n * 128 + ((((kk >> 2) ^ (n & 7)) << 4) | ((kk & 3) << 2))) = v;
+  }
+  fence_proxy_async();
+  pdl_wait();
+  __syncthreads();
+  if (warp == 0) {
+    if (lane == 0)
+      for (int t = 0; t < nkt; ++t) {
+        mbar_arrive_expect_tx(&full_bar[t], 16384u);
+        tma_load_2d(sm_a + (size_t)t * 16384, &map_x, &full_bar[t], k0 + t * 32, 0);
+      }
+  } else if (warp == 1) {
+    const uint32_t idesc = idesc_tf32(128, 16, 0, 0);
+    const uint64_t d = smem_desc_sw128(0, 16, 1024);
+    const uint32_t d_hi = (uint32_t)(d >> 32), d_lo = (uint32_t)d;
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t a0 = d_lo + (smem_u32(sm_a) >> 4), b0 = d_lo + (smem_u32(sm_b) >> 4);
+    uint32_t accumulate = 0;
+    for (int t = 0; t < nkt; ++t) {
+      mbar_wait(&full_bar[t], 0);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        umma_tf32_elect(tmem_u, ((uint64_t)d_hi << 32) | (a0 + t * 1024 + ks * 2), ((uint64_t)d_hi << 32) | (b0 + t * 128 + ks * 2), idesc,
+                        accumulate);
+        accumulate = 1;
+      }
+    }
+    umma_commit_elect(done_bar);
+  } else {
+    const int sub = warp & 3, row = sub * 32 + lane;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    float v[32];
+    tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16), v);
+    tmem_ld_wait();
+    if (row < p.M) {
+      float* o = p.partial + ((size_t)blockIdx.x * p.M + row) * p.N;
+#pragma unroll
+      for (int n = 0; n < 16; ++n)
+        if (n < p.N) o[n] = v[n];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 32);
+  }
+}
+
+struct HeadTcPlan {
+  CUtensorMap map_x;
+  HeadFwdParams p;
+  const float* x;
+  int smem;
+};
+
+static void head_tc_free(LayerPlan& L) {
+  delete (HeadTcPlan*)L.head_tc;
+  L.head_tc = nullptr;
+}
+
+bool tc_head_fwd(sb_engine* e, LayerPlan& L, const float* x, const float* w, float* partial, size_t partial_floats, int* chunks_out) {
+  static const bool enabled = [] { const char* v = getenv("SB_TC_HEAD"); return !(v && v[0] == '0'); }();
+  if (!enabled || e->train.precision != SB_PREC_TF32) return false;
+  const int M = (int)L.in.d[0], K = (int)L.in.d[1], N = (int)L.out.d[1];
+  if (M > 128 || N > 16 || (K % 32) || K < 32 * kNumSMs || (((uintptr_t)x) & 127)) return false;
+  HeadTcPlan* P = (HeadTcPlan*)L.head_tc;
+  if (!P || P->x != x) {
+    delete P;
+    P = new HeadTcPlan();
+    const int tiles = K / 32;
+    int per = (tiles + kNumSMs - 1) / kNumSMs;
+    if (per > kHeadTcMaxTiles) { delete P; L.head_tc = nullptr; return false; }
+    P->p.M = M; P->p.K = K; P->p.N = N; P->p.KC = per * 32; P->p.chunks = (tiles + per - 1) / per;
+    uint64_t xd[2] = {(uint64_t)K, (uint64_t)M};
+    uint32_t xb[2] = {32, 128};
+    P->map_x = make_map(x, 2, xd, xb);
+    P->x = x;
+    P->smem = per * (16384 + 2048) + 16 * (kHeadTcMaxTiles + 2) + 1024;
+    SB_CUDA(cudaFuncSetAttribute(head_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P->smem));
+    L.head_tc = P;
+  }
+  if ((size_t)P->p.chunks * M * N > partial_floats) return false;
+  P->p.w = w;
+  P->p.partial = partial;
+  launch_k(head_fwd_tc_kernel, P->p.chunks, kHeadTcThreads, P->smem, e->stream, P->map_x, P->p);
+  SB_LAUNCHED();
+  *chunks_out = P->p.chunks;
   return true;
 }
 
