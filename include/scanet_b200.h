@@ -54,7 +54,10 @@ typedef enum {
   SB_LAYER_CONV2D = 5,    /* layer/Conv2D.scala:70-125 params: "weights" [KH,KW,Cin,filters]             */
   SB_LAYER_POOL2D = 6,    /* layer/Pool2D.scala:28-57  no params; always Max (the layer ignores `reduce`) */
   SB_LAYER_BATCHNORM = 7, /* layer/BatchNorm.scala:63-174 params: beta,gamma (+state moving_mean/variance) */
-  SB_LAYER_LSTM = 8       /* layer/RNN.scala:208-339   RNN(LSTMCell): per gate kernel/recurrent/bias       */
+  SB_LAYER_LSTM = 8,      /* layer/RNN.scala:208-339   RNN(LSTMCell): per gate kernel/recurrent/bias       */
+  SB_LAYER_SIMPLE_RNN = 9 /* layer/RNN.scala:96-206    RNN(SimpleRNNCell >> Bias >> act): "0/kernel_weights" [F,U],
+                             "0/recurrent_weights" [U,U], "1/weights" [U]; the state fed back is the PRE-bias,
+                             PRE-activation sum (:190-196), as in the reference                                   */
 } sb_layer_kind;
 
 typedef enum { SB_ACT_IDENTITY = 0, SB_ACT_SIGMOID = 1, SB_ACT_TANH = 2, SB_ACT_SOFTMAX = 3, SB_ACT_RELU = 4 } sb_activation;
@@ -102,7 +105,7 @@ typedef struct {
   int32_t stride_h, stride_w;
   int32_t padding;              /* sb_padding */
   int32_t pool_reduce;          /* sb_pool_reduce, recorded but ignored like the reference layer */
-  int32_t use_bias;             /* LSTM */
+  int32_t use_bias;             /* LSTM, SimpleRNN */
   int32_t trainable;
   float bn_momentum, bn_epsilon;
   int32_t bn_mode;              /* 0 = reference (bug-for-bug fused wiring), 1 = correct */
@@ -112,7 +115,7 @@ typedef struct {
   int32_t reg_kind;             /* sb_regularization of this layer's "weights" (Dense kernel, Bias) */
   float reg_lambda;
   int32_t pad_top, pad_bottom, pad_left, pad_right; /* Conv2D with SB_PAD_EXPLICIT (math/nn/AllKernels.scala:67-102) */
-  int32_t return_sequence;      /* LSTM: output (batch, time, units) instead of the last step (layer/RNN.scala:21-27, 69-71) */
+  int32_t return_sequence;      /* LSTM, SimpleRNN: output (batch, time, units) instead of the last step (layer/RNN.scala:21-27, 69-71) */
 } sb_layer_desc;
 
 typedef struct {

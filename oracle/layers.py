@@ -707,6 +707,7 @@ class SimpleRNNCell(Layer):
         g = {"0/kernel_weights": x.T @ dz, "0/recurrent_weights": state.T @ dz}
         if self.bias:
             g["1/weights"] = np.sum(dzb, axis=0, dtype=dh.dtype)
+        self._last_dx = dz @ p["0/kernel_weights"].T  # MatMul grad w.r.t. the step input (a stacked RNN below needs it)
         return dz @ p["0/recurrent_weights"].T, g
 
     def __repr__(self):
@@ -836,7 +837,7 @@ class RNN(Layer):
         grads: Dict[str, np.ndarray] = {}
         dstate = np.zeros((b, u), g.dtype)  # dL/d(recurrent input of step t+1)
         dc = np.zeros((b, u), g.dtype)
-        dx = np.zeros(xshape, g.dtype) if (need_dx and lstm) else None
+        dx = np.zeros(xshape, g.dtype) if need_dx else None
         for t in range(T - 1, -1, -1):
             dout = g[:, t, :] if self.return_sequence else (g if t == T - 1 else np.zeros((b, u), g.dtype))
             if lstm:
@@ -845,9 +846,11 @@ class RNN(Layer):
                     dx[:, t, :] = self.cell._last_dx  # a stacked RNN: the layer below needs dL/d(sequence input)
             else:
                 dstate, gr = self.cell.step_bwd(dout, dstate, caches[t], p)
+                if dx is not None:
+                    dx[:, t, :] = self.cell._last_dx
             for k, v in gr.items():
                 grads[k] = grads[k] + v if k in grads else v
-        return dx, grads  # (SimpleRNN: the gradient w.r.t. the sequence input is not restated)
+        return dx, grads
 
     def __repr__(self):
         return f"RNN({self.cell!r})"

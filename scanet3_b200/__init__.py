@@ -8,7 +8,7 @@ from .dsl import (Explicit, Activate, Activation, AdaDelta, AdaGrad, Adam, Adama
                   BinaryCrossentropy, CategoricalCrossentropy, Composed, Const, Conv2D, Dense, Flatten, GlorotNormal, GlorotUniform, HeNormal,
                   HeUniform, Identity, Initializer, L1, L2, LecunNormal, LecunUniform, LinearRegression, LogisticRegression, Loss, LSTM,
                   LSTMCell, MeanSquaredError, Nadam, Ones, Orthogonal, Pool2D, RandomNormal, RandomNormalTruncated, RandomUniform, ReLU, RMSProp,
-                  RNN, Same, SGD, Sigmoid, Softmax, Tanh, Valid, Zero, Zeros)
+                  RNN, Same, SGD, Sigmoid, SimpleRNN, SimpleRNNCell, Softmax, Tanh, Valid, Zero, Zeros)
 from .engine import Engine, Group, spark_chain_weights, wire_decode, wire_encode
 from .optimizer import (Builder, Dataset, LossModel, Optimizer, RecordAccuracy, RecordIteration, RecordLoss, SaveCheckpoint, Step,
                         TrainedModel, MAE, MSE, R2Score, RMSE, accuracy, always, epochs, iterations, maximize, minimize, never)

@@ -11,7 +11,8 @@ LIB_PATH = os.path.join(_HERE, "libscanet_b200.so")
 SB_OK, SB_ERR_INVALID_ARG, SB_ERR_UNSUPPORTED, SB_ERR_CUDA, SB_ERR_NCCL, SB_ERR_STATE = range(6)
 
 # enums (mirror include/scanet_b200.h)
-LAYER_DENSE, LAYER_BIAS, LAYER_ACTIVATE, LAYER_FLATTEN, LAYER_CONV2D, LAYER_POOL2D, LAYER_BATCHNORM, LAYER_LSTM = range(1, 9)
+(LAYER_DENSE, LAYER_BIAS, LAYER_ACTIVATE, LAYER_FLATTEN, LAYER_CONV2D, LAYER_POOL2D, LAYER_BATCHNORM, LAYER_LSTM,
+ LAYER_SIMPLE_RNN) = range(1, 10)
 ACT_IDENTITY, ACT_SIGMOID, ACT_TANH, ACT_SOFTMAX, ACT_RELU = range(5)
 PAD_VALID, PAD_SAME, PAD_EXPLICIT = 0, 1, 2
 POOL_MAX, POOL_AVG = 0, 1

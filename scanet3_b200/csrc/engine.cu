@@ -315,6 +315,29 @@ static void build_plan(sb_engine* e) {
         any_trainable_before = true;
         break;
       }
+      case SB_LAYER_SIMPLE_RNN: {
+        if (cur.rank != 3) SB_FAIL(SB_ERR_INVALID_ARG, "requirement failed: RNN requires input to have Shape(batch, time, features)");
+        if (!d.trainable) SB_FAIL(SB_ERR_UNSUPPORTED, "frozen layers are outside the accelerated path");
+        if (d.units <= 0) SB_FAIL(SB_ERR_INVALID_ARG, "requirement failed: RNN Cell should contain at least one unit");
+        if (d.activation == SB_ACT_SOFTMAX) SB_FAIL(SB_ERR_UNSUPPORTED, "Softmax inside a SimpleRNN cell is outside the accelerated path");
+        if (!d.use_bias && d.activation == SB_ACT_IDENTITY)
+          SB_FAIL(SB_ERR_UNSUPPORTED, "a bare SimpleRNNCell (no bias, identity activation) names its parameters without the cell index");
+        const int64_t F = cur.d[2], U = d.units;
+        // the composed cell `SimpleRNNCell >> Bias >> act` prefixes its leaves' parameters with their index (layer/Composed.scala:18-27)
+        L.p_aux[0] = add_param(e, pre + "0/kernel_weights", {F, U}, SB_ROLE_WEIGHT, SB_AGG_AVG, d.init[0], li);
+        L.p_aux[1] = add_param(e, pre + "0/recurrent_weights", {U, U}, SB_ROLE_WEIGHT, SB_AGG_AVG, d.init[1], li);
+        if (d.use_bias) L.p_aux[2] = add_param(e, pre + "1/weights", {U}, SB_ROLE_WEIGHT, SB_AGG_AVG, d.init[2], li);
+        if (d.return_sequence) {
+          out.rank = 3;
+          out.d[1] = cur.d[1];
+          out.d[2] = U;
+        } else {
+          out.rank = 2;
+          out.d[1] = U;
+        }
+        any_trainable_before = true;
+        break;
+      }
       default:
         SB_FAIL(SB_ERR_INVALID_ARG, "unknown layer kind " + std::to_string(d.kind));
     }
@@ -525,6 +548,7 @@ static void allocate(sb_engine* e) {
   tc_plan_layers(e);  // tensor-core fast paths (TMA descriptors, padded-grid buffers)
   plan_fusions(e);    // vectorised / fused bandwidth kernels
   lstm_plan(e);       // LSTM workspaces (saved gate activations for BPTT)
+  rnn_plan(e);        // SimpleRNN workspaces
   SB_CUDA(cudaStreamSynchronize(e->stream));
 }
 
@@ -679,6 +703,11 @@ static void run_forward(sb_engine* e, int mode) {
       case SB_LAYER_LSTM: {
         Prof pr(e, "lstm_fwd", 0, 0);
         lstm_forward(e, L, li);
+        break;
+      }
+      case SB_LAYER_SIMPLE_RNN: {
+        Prof pr(e, "rnn_fwd", 0, 0);
+        rnn_forward(e, L, li);
         break;
       }
     }
@@ -859,6 +888,11 @@ static void run_backward(sb_engine* e) {
       case SB_LAYER_LSTM: {
         Prof pr(e, "lstm_bwd", 0, 0);
         lstm_backward(e, L, li);
+        break;
+      }
+      case SB_LAYER_SIMPLE_RNN: {
+        Prof pr(e, "rnn_bwd", 0, 0);
+        rnn_backward(e, L, li);
         break;
       }
     }
@@ -1258,6 +1292,7 @@ extern "C" void sb_engine_destroy(sb_engine* e) {
     if (e->cstream) { cudaStreamSynchronize(e->cstream); cudaStreamDestroy(e->cstream); }
     if (e->bstream) { cudaStreamSynchronize(e->bstream); cudaStreamDestroy(e->bstream); cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join); }
     tc_free_layers(e);
+    rnn_free(e);
     lstm_free(e);
     for (auto& L : e->L) { cudaFree(L.bn_save_mean); cudaFree(L.bn_save_var); }
     for (float* p : e->acts) cudaFree(p);

@@ -444,7 +444,7 @@ void lstm_backward(sb_engine* e, LayerPlan& L, int) {
 
 void lstm_free(sb_engine* e) {
   for (auto& L : e->L) {
-    if (!L.lstm) continue;
+    if (!L.lstm || L.d.kind != SB_LAYER_LSTM) continue;
     LstmWs* w = (LstmWs*)L.lstm;
     for (float* p : {w->wr_cat, w->wk_cat, w->b_cat, w->x_tm, w->acts, w->c, w->h, w->xw, w->dh, w->dc, w->dwr_cat, w->dwk_cat,
                      w->db_cat, w->dwkb_cat, w->dx_tm, w->dout_tm})

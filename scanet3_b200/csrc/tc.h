@@ -51,6 +51,11 @@ void lstm_plan(sb_engine* e);
 void lstm_forward(sb_engine* e, LayerPlan& L, int li);
 void lstm_backward(sb_engine* e, LayerPlan& L, int li);
 void lstm_free(sb_engine* e);
+// RNN(SimpleRNNCell >> Bias >> Activate) (rnn.cu)
+void rnn_plan(sb_engine* e);
+void rnn_forward(sb_engine* e, LayerPlan& L, int li);
+void rnn_backward(sb_engine* e, LayerPlan& L, int li);
+void rnn_free(sb_engine* e);
 
 // Orthogonal initializer (models/Initializer.scala:202-219): QR of a TF-Philox normal matrix on the host
 void orthogonal_host(float* out, int64_t rows, int64_t cols, unsigned long long seed, float gain);

@@ -371,17 +371,24 @@ class BatchNorm(Layer):
 
 
 class RNN(Layer):
-    """layer/RNN.scala:27-94 with an LSTMCell (the only cell on the accelerated path)."""
+    """layer/RNN.scala:27-94 around an LSTMCell or a SimpleRNNCell (>> Bias >> activation)."""
 
-    def __init__(self, cell: "LSTMCell", returnSequence=False, stateful=False):
+    def __init__(self, cell, returnSequence=False, stateful=False):
         if stateful:
             raise N.Unsupported(N.SB_ERR_UNSUPPORTED, "stateful RNNs are outside the accelerated path")
-        if not isinstance(cell, LSTMCell):
-            raise N.Unsupported(N.SB_ERR_UNSUPPORTED, "only LSTMCell is on the accelerated path")
+        if not isinstance(cell, (LSTMCell, SimpleRNNCell)):
+            raise N.Unsupported(N.SB_ERR_UNSUPPORTED, "only LSTMCell and SimpleRNNCell are on the accelerated path")
         self.cell, self.returnSequence = cell, bool(returnSequence)
 
     def to_native(self):
         c = self.cell
+        if isinstance(c, SimpleRNNCell):
+            d = self._desc(N.LAYER_SIMPLE_RNN, units=c.units, activation=c.activation.code, use_bias=int(c.bias),
+                           return_sequence=int(self.returnSequence),
+                           relu_threshold=float(getattr(c.activation, "threshold", 0.0)))
+            for i, init in enumerate((c.kernelInitializer, c.recurrentInitializer, c.biasInitializer)):
+                d.init[i] = init.to_native()
+            return d
         d = self._desc(N.LAYER_LSTM, units=c.units, activation=c.activation.code,
                        recurrent_activation=c.recurrentActivation.code, use_bias=int(c.bias),
                        return_sequence=int(self.returnSequence))
@@ -406,6 +413,32 @@ class LSTMCell:
 
     def __repr__(self):
         return f"LSTMCell({self.units},{self.activation!r},{self.recurrentActivation!r},{str(self.bias).lower()})"
+
+
+@dataclass
+class SimpleRNNCell:
+    """layer/RNN.scala:140-206: `SimpleRNNCell >> Bias >> activation`; the state fed back is the pre-bias, pre-activation sum."""
+    units: int
+    activation: Activation = Tanh
+    bias: bool = True
+    kernelInitializer: Initializer = GlorotUniform()
+    recurrentInitializer: Initializer = Orthogonal()
+    biasInitializer: Initializer = Zeros
+
+    def __repr__(self):
+        s = f"SimpleRNNCell({self.units})"
+        if self.bias:
+            s += f" >> Bias({self.units})"
+        if not self.activation.identity:
+            s += f" >> {self.activation!r}"
+        return s
+
+
+def SimpleRNN(units, activation=Tanh, bias=True, kernelInitializer=GlorotUniform(), recurrentInitializer=Orthogonal(),
+              biasInitializer=Zeros, returnSequence=False, stateful=False) -> RNN:
+    """layer/RNN.scala:96-138"""
+    return RNN(SimpleRNNCell(units, activation, bias, kernelInitializer, recurrentInitializer, biasInitializer), returnSequence,
+               stateful)
 
 
 def LSTM(units, activation=Tanh, recurrentActivation=Sigmoid, bias=True, kernelInitializer=GlorotUniform(),

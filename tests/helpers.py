@@ -46,6 +46,15 @@ def build_models(spec, seed=1):
                              recurrent_initializer=O.Orthogonal(seed=seed)))
             sl.append(S.LSTM(units, kernelInitializer=S.GlorotUniform(seed), recurrentInitializer=S.Orthogonal(seed=seed),
                              returnSequence=seq))
+        elif kind == "rnn":
+            # ("rnn", units, act[, return_sequence[, bias]])
+            units, act = it[1], it[2]
+            seq = len(it) > 3 and bool(it[3])
+            bias = it[4] if len(it) > 4 else True
+            ol.append(O.SimpleRNN(units, _OACT[act], bias, seq, kernel_initializer=O.GlorotUniform(seed),
+                                  recurrent_initializer=O.Orthogonal(seed=seed)))
+            sl.append(S.SimpleRNN(units, _SACT[act], bias, kernelInitializer=S.GlorotUniform(seed),
+                                  recurrentInitializer=S.Orthogonal(seed=seed), returnSequence=seq))
         elif kind == "act":
             ol.append(O.Activate(_OACT[it[1]]))
             sl.append(S.Activate(_SACT[it[1]]))

@@ -151,3 +151,70 @@ def test_stacked_lstm_trajectory():
         assert abs(gl - float(ol)) <= 1e-4 * abs(float(ol)) + 1e-7, (s_, gl, float(ol))
     assert_params_close(e.get_model_params(), mp, 2e-3, 3e-5, f"after {steps} steps")
     e.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# RNN(SimpleRNNCell >> Bias >> act) (layer/RNN.scala:96-206).  The state fed back is the pre-bias,
+# pre-activation sum (reference quirk); forward golden models/layer/RNNLayerSpec.scala:17-34
+# ---------------------------------------------------------------------------------------------------------------
+def test_simple_rnn_forward_golden_through_the_engine():
+    e = S.Engine(S.SimpleRNN(2, activation=S.Identity), S.MeanSquaredError, S.SGD(), 1, (3, 1), (2,), device=0)
+    assert set(e.model_param_paths()) == {"0/kernel_weights", "0/recurrent_weights", "1/weights"}
+    e.set_params({"0/kernel_weights": np.array([[-0.5302748, -1.2049599]], f32),
+                  "0/recurrent_weights": np.array([[-0.77547526, -0.6313778], [-0.6313778, 0.7754754]], f32),
+                  "1/weights": np.zeros(2, f32)})
+    y = e.predict(np.array([1, 2, 3], f32).reshape(1, 3, 1))
+    np.testing.assert_allclose(y, np.array([[0.222901, -6.019066]], f32), atol=2e-6)
+    e.close()
+    assert repr(S.SimpleRNN(2)) == "RNN(SimpleRNNCell(2) >> Bias(2) >> Tanh)"
+
+
+RNN_MODELS = {
+    "last_step_tanh": ([("rnn", 8, "tanh"), ("dense", 1, "tanh")], 6, 3, 7),
+    "sequence_into_dense_sigmoid": ([("rnn", 5, "sigmoid", True), ("flatten",), ("dense", 1, "identity")], 4, 2, 5),
+    "stacked_no_bias_relu": ([("rnn", 6, "tanh", True), ("rnn", 4, "relu", False, False), ("dense", 1, "tanh")], 5, 2, 9),
+    "under_an_lstm": ([("rnn", 6, "tanh", True), ("lstm", 4), ("dense", 1, "tanh")], 5, 3, 6),
+}
+
+
+@pytest.mark.parametrize("name", list(RNN_MODELS))
+def test_simple_rnn_gradients_match_oracle_bptt(name):
+    spec, t, f, batch = RNN_MODELS[name]
+    om, sm = build_models(spec)
+    x, y = synth_series(batch, t, f, 31)
+    e = S.Engine(sm, S.MeanSquaredError, S.Adam(), batch, (t, f), (1,), device=0)
+    _, mp, _ = O.init_params(om, O.Adam(), (batch, t, f))
+    assert set(e.model_param_paths()) == set(mp.keys())
+    e.set_params(mp)
+    e.init_opt_params()
+    ol, og, _ = O.LossModel(om, O.MeanSquaredError).grad_stateful(x, y, mp)
+    gl, gg = e.compute_grads(x, y)
+    assert abs(gl - float(ol)) <= 2e-5 * abs(float(ol)) + 1e-7
+    for k, v in og.items():
+        np.testing.assert_allclose(gg[k], v, rtol=3e-4, atol=3e-6, err_msg=k)
+    np.testing.assert_allclose(e.predict(x), O.model_forward(om, x, mp)[0], rtol=2e-5, atol=2e-6)
+    e.close()
+
+
+def test_simple_rnn_trajectory_and_device_init():
+    spec = [("rnn", 8, "tanh"), ("dense", 1, "tanh")]
+    om, sm = build_models(spec)
+    batch, t, f, steps, rate = 16, 6, 2, 8, 2e-3
+    x, y = synth_series(batch * steps, t, f, 37)
+    e = S.Engine(sm, S.MeanSquaredError, S.Adam(rate), batch, (t, f), (1,), device=0)
+    e.init_params()
+    oalg = O.Adam(rate)
+    _, mp, op = O.init_params(om, oalg, (batch, t, f))
+    assert_params_close(e.get_model_params(), mp, 0, 2e-6, "init")  # GlorotUniform bit exact, Orthogonal by host QR
+    e.set_params(mp)
+    e.init_opt_params()
+    lm = O.LossModel(om, O.MeanSquaredError)
+    for s_ in range(1, steps + 1):
+        xb, yb = x[(s_ - 1) * batch:s_ * batch], y[(s_ - 1) * batch:s_ * batch]
+        gl = e.train_step(xb, yb, s_)
+        mp, op, ol = O.train_step(lm, oalg, xb, yb, mp, op, s_)
+        assert abs(gl - float(ol)) <= 1e-4 * abs(float(ol)) + 1e-7, (s_, gl, float(ol))
+    assert_params_close(e.get_model_params(), mp, 2e-3, 3e-5, f"after {steps} steps")
+    e.close()
+    with pytest.raises(S.Unsupported):
+        S.SimpleRNN(4, stateful=True)

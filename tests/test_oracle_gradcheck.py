@@ -55,6 +55,13 @@ def test_simple_rnn_gradients_with_the_pre_activation_state_quirk():
              O.MeanSquaredError, (3, 5, 2), 1)
 
 
+def test_stacked_simple_rnn_gradients_through_the_returned_sequence():
+    model = (O.SimpleRNN(4, return_sequence=True, kernel_initializer=O.GlorotUniform(1), recurrent_initializer=O.Orthogonal(seed=1))
+             >> O.SimpleRNN(3, activation=O.Sigmoid, kernel_initializer=O.GlorotUniform(2), recurrent_initializer=O.Orthogonal(seed=2))
+             >> O.Dense(1))
+    fd_check(model, O.MeanSquaredError, (3, 5, 2), 1)
+
+
 def test_lenet_style_cnn_gradients():
     model = (O.Conv2D(3, activation=O.ReLU()) >> O.Pool2D() >> O.Conv2D(4, (2, 2), (2, 2), "same", O.Sigmoid, bias=True)
              >> O.Pool2D((2, 2), (2, 2), "same") >> O.Flatten >> O.Dense(3, O.Softmax))
