@@ -40,13 +40,26 @@ static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) 
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_prologue() {
-#ifdef SB_PDL_EARLY_TRIGGER
-  pdl_trigger();  // measured on cfg2: resident-but-waiting CTAs of the next kernel slow multi-wave kernels down (-2.5 %)
-#endif
+__device__ __forceinline__ void pdl_prologue() { pdl_wait(); }
+// Wait, then let the dependents launch: their CTAs fill whatever this grid leaves free and run their own pre-wait setup (a
+// tensor-core kernel's barrier init, TMEM allocation, filter fill) under it; they still block in griddepcontrol.wait until this
+// grid has completed.  Triggering AFTER the wait keeps the invariant the early filter fill relies on: when a kernel's pre-wait
+// code runs, the grid two launches back is complete.  Used by the kernels of the CNN step, where it was measured kernel by kernel
+// (cfg2: 854 k -> 906 k samples/s, profiles/r1_notes.md item 17); NOT by the generic fp32 GEMM / pointwise kernels: with it on
+// every kernel the latency-bound MLP step (cfg1) lost 14 % (waiting dependents take slots from its multi-wave GEMMs).
+__device__ __forceinline__ void pdl_prologue_trigger() {
   pdl_wait();
+  pdl_trigger();
+}
+// the four kernels that the MLP step shares with the CNN step (prologue, optimizer, classifier-head loss, partial reduce) take the
+// decision as an argument: the engine sets it per model (early_hint(): CNN path yes, plain fp32-GEMM MLP no)
+__device__ __forceinline__ void pdl_prologue_trigger_if(int early) {
+  pdl_wait();
+  if (early) pdl_trigger();
 }
 bool pdl_enabled();  // SB_PDL=0 turns the launch attribute off (engine.cu)
+int pdl_early_hint();               // host side, per thread: set by the engine for the model it is running (engine.cu)
+void set_pdl_early_hint(int on);
 template <typename K, typename... A>
 inline void launch_k(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t s, A&&... args) {
   cudaLaunchConfig_t cfg = {};

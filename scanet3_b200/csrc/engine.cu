@@ -32,6 +32,9 @@ bool fork_enabled() {  // SB_BWD_FORK=0: the conv filter gradient stays in the m
   }();
   return on;
 }
+static thread_local int tl_pdl_early = 0;
+int pdl_early_hint() { return tl_pdl_early; }
+void set_pdl_early_hint(int on) { tl_pdl_early = on; }
 bool pdl_enabled() {
   static const bool on = [] {
     const char* v = getenv("SB_PDL");
@@ -75,6 +78,7 @@ static void need_device(const sb_engine* e) {
   if (e == nullptr) SB_FAIL(SB_ERR_INVALID_ARG, "null engine");
   if (e->plan_only)
     SB_FAIL(SB_ERR_CUDA, "plan-only engine (device < 0): no CUDA device bound; this library has no CPU fallback");
+  sb::set_pdl_early_hint(e->pdl_early ? 1 : 0);  // every compute entry point passes here: the launches that follow are this model's
 }
 struct DeviceGuard {
   int prev = -1;
@@ -355,6 +359,11 @@ static void build_plan(sb_engine* e) {
     cur = out;
   }
   e->out_shape = cur;
+  // early programmatic-launch trigger in the kernels shared by every model: measured per BASELINE config (common.cuh) -- the CNN
+  // step gains 6 %, the latency-bound fp32-GEMM MLP step loses 14 %
+  e->pdl_early = false;
+  for (const LayerPlan& Lp : e->L)
+    if (Lp.d.kind == SB_LAYER_CONV2D || Lp.d.kind == SB_LAYER_POOL2D) e->pdl_early = true;
   if (cur.numel() != e->label_shape.numel())
     SB_FAIL(SB_ERR_INVALID_ARG, "model output " + std::to_string(cur.numel()) + " elements per batch does not match the labels " +
                                     std::to_string(e->label_shape.numel()));

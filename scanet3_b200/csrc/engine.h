@@ -129,6 +129,7 @@ struct sb_engine {
   cudaStream_t bstream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool bwd_forked = false;
+  bool pdl_early = false;   // the shared kernels (prologue, optimizer, head loss, partial reduce) trigger their dependents early
   cudaStream_t cstream = nullptr;
   float* stage_x[2] = {nullptr, nullptr};
   float* stage_y[2] = {nullptr, nullptr};

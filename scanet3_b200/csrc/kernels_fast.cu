@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256) pool_max_fwd_v4_kernel(const float* __res
 constexpr int kPoolSegs = 4;
 __global__ void __launch_bounds__(256) pool22_fwd_strip_kernel(const float* __restrict__ x, float* __restrict__ y, PoolGeom g,
                                                                int seg_len, long long n_threads) {
-  pdl_prologue();
+  pdl_prologue_trigger();
   const int C4 = g.C >> 2;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_threads) return;
@@ -191,7 +191,7 @@ template <bool RELU, int WG>
 __global__ void __launch_bounds__(128) pool22_bwd_strip_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                float* __restrict__ dx, PoolGeom g, float thr, int seg_len,
                                                                int segs, long long n_threads, PoolWgradFuse wf) {
-  pdl_prologue();
+  pdl_prologue_trigger();
   constexpr int KH = WG / 100, KW = (WG / 10) % 10, CIN = WG % 10, K = KH * KW * CIN;
   const int C4 = g.C >> 2;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -500,7 +500,7 @@ template <int KH, int KW, int CIN, int PW>
 __global__ void __launch_bounds__(256) conv_smallk_pool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                    float* __restrict__ y, float* __restrict__ pooled, ConvGeom g,
                                                                    int relu, float thr, int segs, long long n_threads) {
-  pdl_prologue();
+  pdl_prologue_trigger();
   constexpr int K = KH * KW * CIN;
   const int C4 = g.Cout >> 2;
   extern __shared__ __align__(16) float swt[];  // filter [K][Cout]
@@ -736,8 +736,8 @@ constexpr int kHeadThreads = 128;
 // generic deterministic column reduction  out[i] = sum_c partial[c][i]  (c ascending inside a lane group, then a fixed tree)
 template <int YG>
 __global__ void __launch_bounds__(32 * YG) partial_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int n,
-                                                                int parts) {
-  pdl_prologue();
+                                                                int parts, int early) {
+  pdl_prologue_trigger_if(early);
   __shared__ float red[YG][33];
   const int i = blockIdx.x * 32 + threadIdx.x, y = threadIdx.y;
   float acc = 0.f;
@@ -755,8 +755,8 @@ __global__ void __launch_bounds__(32 * YG) partial_reduce_kernel(const float* __
 // part c goes to lane group c % YG (summed in ascending c inside the group), then the groups in order: a fixed order for a
 // given `parts`.  Many partials -> 32 groups so that no thread walks more than ~parts/32 dependent loads.
 void partial_reduce(const float* partial, float* out, int n, int parts, cudaStream_t s) {
-  if (parts > 48) launch_k(partial_reduce_kernel<32>, (n + 31) / 32, dim3(32, 32), 0, s, partial, out, n, parts);
-  else launch_k(partial_reduce_kernel<8>, (n + 31) / 32, dim3(32, 8), 0, s, partial, out, n, parts);
+  if (parts > 48) launch_k(partial_reduce_kernel<32>, (n + 31) / 32, dim3(32, 32), 0, s, partial, out, n, parts, pdl_early_hint());
+  else launch_k(partial_reduce_kernel<8>, (n + 31) / 32, dim3(32, 8), 0, s, partial, out, n, parts, pdl_early_hint());
   SB_LAUNCHED();
 }
 
@@ -889,8 +889,8 @@ template <int NT, bool DGRAD>
 __global__ void __launch_bounds__(kBwdK* kBwdGroups) dense_head_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gmat,
                                                                             const float* __restrict__ w, float* __restrict__ dw,
                                                                             float* __restrict__ dx, int Mtot, int K, int N,
-                                                                            int rows_per_split) {
-  pdl_prologue();
+                                                                            int rows_per_split, int early) {
+  pdl_prologue_trigger_if(early);
   extern __shared__ __align__(128) float sm[];
   // blockIdx.y = row split: rows [mlo, mhi); its dW goes to slice blockIdx.y of `dw` (summed in split order afterwards)
   const int mlo = blockIdx.y * rows_per_split, M = min(Mtot, mlo + rows_per_split);
@@ -973,11 +973,11 @@ bool dense_head_bwd(const float* x, const float* g, const float* w, float* dw, f
   float* dwo = splits > 1 ? ws : dw;
   const dim3 grid(kblocks, splits);
   if (NT == 12) {
-    if (dx) launch_k(dense_head_bwd_kernel<12, true>, grid, thr, smem, s, x, g, w, dwo, dx, M, K, N, rows_per_split);
-    else launch_k(dense_head_bwd_kernel<12, false>, grid, thr, smem, s, x, g, w, dwo, dx, M, K, N, rows_per_split);
+    if (dx) launch_k(dense_head_bwd_kernel<12, true>, grid, thr, smem, s, x, g, w, dwo, dx, M, K, N, rows_per_split, pdl_early_hint());
+    else launch_k(dense_head_bwd_kernel<12, false>, grid, thr, smem, s, x, g, w, dwo, dx, M, K, N, rows_per_split, pdl_early_hint());
   } else {
-    if (dx) launch_k(dense_head_bwd_kernel<16, true>, grid, thr, smem, s, x, g, w, dwo, dx, M, K, N, rows_per_split);
-    else launch_k(dense_head_bwd_kernel<16, false>, grid, thr, smem, s, x, g, w, dwo, dx, M, K, N, rows_per_split);
+    if (dx) launch_k(dense_head_bwd_kernel<16, true>, grid, thr, smem, s, x, g, w, dwo, dx, M, K, N, rows_per_split, pdl_early_hint());
+    else launch_k(dense_head_bwd_kernel<16, false>, grid, thr, smem, s, x, g, w, dwo, dx, M, K, N, rows_per_split, pdl_early_hint());
   }
   SB_LAUNCHED();
   if (splits > 1) partial_reduce(ws, dw, K * N, splits, s);
@@ -1060,8 +1060,8 @@ __global__ void __launch_bounds__(1024) head_bias_softmax_cce_kernel(float* __re
                                                                      const float* __restrict__ y, float* __restrict__ dz,
                                                                      float* __restrict__ dbias, StepState* st, int rows, int C,
                                                                      int rows_per_cta, float* __restrict__ scratch,
-                                                                     unsigned int* ticket) {
-  pdl_prologue();
+                                                                     unsigned int* ticket, int early) {
+  pdl_prologue_trigger_if(early);
   __shared__ float zs[32][kHeadMaxCnt];
   __shared__ float sl[kHeadMaxRows];
   __shared__ float sdb[kHeadMaxRows][33];
@@ -1162,7 +1162,7 @@ bool head_bias_softmax_cce(float* z, const float* partial, int chunks, const flo
   if (rpc > kHeadMaxRows || rpc * C > kHeadMaxCnt) return false;
   const int grid = (rows + rpc - 1) / rpc;
   launch_k(head_bias_softmax_cce_kernel, grid, 1024, 0, s, z, partial, chunks, bias, y, dz, dbias, st, rows, C, rpc, scratch,
-           reinterpret_cast<unsigned int*>(scratch + 1024 * 40));
+           reinterpret_cast<unsigned int*>(scratch + 1024 * 40), pdl_early_hint());
   SB_LAUNCHED();
   return true;
 }

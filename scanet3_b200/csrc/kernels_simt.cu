@@ -15,8 +15,8 @@ thread_local long long tl_launch_count = 0;
 template <typename V>
 __global__ void step_prologue_kernel(StepState* st, const V* __restrict__ ds_x, const V* __restrict__ ds_y,
                                      V* __restrict__ bx, V* __restrict__ by, long long x4, long long y4,
-                                     float beta1, float beta2, int batch_from_state, float* __restrict__ prev_loss_slot) {
-  pdl_prologue();
+                                     float beta1, float beta2, int batch_from_state, float* __restrict__ prev_loss_slot, int early) {
+  pdl_prologue_trigger_if(early);
   // resident shard: batch index from the device state (only the optimizer kernel of the previous step writes it);
   // host-fed staging buffer: always its single batch
   const long long b = batch_from_state ? st->batch_idx : 0;
@@ -52,10 +52,10 @@ void step_prologue(StepState* st, const float* ds_x, const float* ds_y, float* b
   if (blocks < 1) blocks = 1;
   if (vec)
     launch_k(step_prologue_kernel<float4>, blocks, 256, 0, s, st, (const float4*)ds_x, (const float4*)ds_y, (float4*)bx,
-                                                        (float4*)by, xn, yn, beta1, beta2, batch_from_state, prev_loss_slot);
+                                                        (float4*)by, xn, yn, beta1, beta2, batch_from_state, prev_loss_slot, pdl_early_hint());
   else
     launch_k(step_prologue_kernel<float>, blocks, 256, 0, s, st, ds_x, ds_y, bx, by, xn, yn, beta1, beta2, batch_from_state,
-             prev_loss_slot);
+             prev_loss_slot, pdl_early_hint());
   SB_LAUNCHED();
 }
 
@@ -1090,8 +1090,8 @@ template <int KIND>
 __global__ void __launch_bounds__(256) optimizer_kernel(OptDesc od, float4* __restrict__ w, const float4* __restrict__ g,
                                                         float4* __restrict__ s0, float4* __restrict__ s1,
                                                         float4* __restrict__ s2, long long n4, StepState* st,
-                                                        int advance_batch) {
-  pdl_prologue();
+                                                        int advance_batch, int early) {
+  pdl_prologue_trigger_if(early);
   OptScalars o;
   o.rate = od.rate; o.b1 = od.beta1; o.b2 = od.beta2; o.eps = od.epsilon; o.nesterov = od.nesterov;
   o.om_b1 = __fsub_rn(1.f, od.beta1);
@@ -1125,7 +1125,7 @@ void optimizer_step(const OptDesc& o, float* w, const float* g, float* s0, float
 #define SB_OPT(K)                                                                                             \
   case K:                                                                                                     \
     launch_k(optimizer_kernel<K>, blocks, 256, 0, s, o, (float4*)w, (const float4*)g, (float4*)s0, (float4*)s1, \
-                                                 (float4*)s2, n4, st, advance_batch);                         \
+                                                 (float4*)s2, n4, st, advance_batch, pdl_early_hint());        \
     break;
   switch (o.kind) {
     SB_OPT(0) SB_OPT(1) SB_OPT(2) SB_OPT(3) SB_OPT(4) SB_OPT(5) SB_OPT(6) SB_OPT(7)

@@ -124,6 +124,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // the on-chip setup above overlapped the previous kernel; global memory from here on
+  pdl_trigger();  // dependents may start their own on-chip setup now (they still wait for this grid before touching its output)
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -335,6 +336,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   };
   if (threadIdx.x == 0 && p.early_filter) load_filter();
   pdl_wait();  // the on-chip setup above overlapped the previous kernel; activations in global memory from here on
+  pdl_trigger();  // dependents may start their own on-chip setup now (they still wait for this grid before touching its output)
   if (threadIdx.x == 0) HALO_T(1);
 
   if (warp == 0) {
@@ -537,6 +539,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) WG_T(1);
   pdl_wait();  // the on-chip setup above overlapped the previous kernel; global memory from here on
+  pdl_trigger();  // dependents may start their own on-chip setup now (they still wait for this grid before touching its output)
   if (threadIdx.x == 0) WG_T(2);
   const bool has_work = (int)blockIdx.x < p.n_chunks;
 
@@ -699,6 +702,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) WG_T(1);
   pdl_wait();  // the on-chip setup above overlapped the previous kernel; global memory from here on
+  pdl_trigger();  // dependents may start their own on-chip setup now (they still wait for this grid before touching its output)
   if (threadIdx.x == 0) WG_T(2);
   const bool has_work = (int)blockIdx.x < p.n_chunks;
 
@@ -1320,6 +1324,7 @@ __global__ void __launch_bounds__(kHeadTcThreads, 1) head_fwd_tc_kernel(const __
   }
   fence_proxy_async();
   pdl_wait();
+  pdl_trigger();  // dependents may start their own on-chip setup now (they still wait for this grid before touching its output)
   __syncthreads();
   if (warp == 0) {
     if (lane == 0)
