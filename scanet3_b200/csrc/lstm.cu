@@ -78,7 +78,7 @@ struct Gate4 {
   float* p[4];
 };
 __global__ void lstm_pack_kernel(Gate4 src, float* __restrict__ cat, int rows, int U) {
-  pdl_prologue();
+  pdl_prologue_trigger();
   const long long n = (long long)rows * 4 * U;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int col = (int)(i % (4 * U)), r = (int)(i / (4 * U));
@@ -87,7 +87,7 @@ __global__ void lstm_pack_kernel(Gate4 src, float* __restrict__ cat, int rows, i
   }
 }
 __global__ void lstm_unpack_kernel(const float* __restrict__ cat, Gate4 dst, int rows, int U) {
-  pdl_prologue();
+  pdl_prologue_trigger();
   const long long n = (long long)rows * 4 * U;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int col = (int)(i % (4 * U)), r = (int)(i / (4 * U));
@@ -97,7 +97,7 @@ __global__ void lstm_unpack_kernel(const float* __restrict__ cat, Gate4 dst, int
 }
 // [B,T,F] <-> [T,B,F]
 __global__ void lstm_transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int D0, int D1, int F) {
-  pdl_prologue();
+  pdl_prologue_trigger();
   const long long n = (long long)D0 * D1 * F;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int f = (int)(i % F);
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(256) lstm_gates_fwd_kernel(float* __restrict__
                                                              const float* __restrict__ xw_t, const float* __restrict__ c_prev,
                                                              float* __restrict__ c_out, float* __restrict__ h_out, int B, int U,
                                                              int first, int act, int ract, int has_bias) {
-  pdl_prologue();
+  pdl_prologue_trigger();
   const long long n = (long long)B * U;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int j = (int)(i % U);
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(256) lstm_gates_bwd_kernel(float* __restrict__
                                                              const float* __restrict__ c_prev, const float* __restrict__ dh,
                                                              const float* __restrict__ dh_seq, float* __restrict__ dc_io, int B, int U,
                                                              int first, int last, int act, int ract) {
-  pdl_prologue();
+  pdl_prologue_trigger();
   const long long n = (long long)B * U;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int j = (int)(i % U);
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256) lstm_gates_bwd_kernel(float* __restrict__
 template <int FI>
 __global__ void __launch_bounds__(256) lstm_dwk_db_kernel(const float* __restrict__ dz, const float* __restrict__ x, float* __restrict__ partial,
                                                           long long rows, int C, long long rows_per_chunk) {
-  pdl_prologue();
+  pdl_prologue_trigger();
   __shared__ float4 red[8][33];
   const int c4 = blockIdx.x * 32 + threadIdx.x;
   const bool ok = c4 * 4 < C;
