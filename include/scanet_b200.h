@@ -116,6 +116,9 @@ typedef struct {
   float reg_lambda;
   int32_t pad_top, pad_bottom, pad_left, pad_right; /* Conv2D with SB_PAD_EXPLICIT (math/nn/AllKernels.scala:67-102) */
   int32_t return_sequence;      /* LSTM, SimpleRNN: output (batch, time, units) instead of the last step (layer/RNN.scala:21-27, 69-71) */
+  int32_t stateful;             /* LSTM, SimpleRNN: the state tensors ("cell_state", "hidden_state" | "0/state", [batch, units],
+                                   Zeros, aggregation None) are parameters: they seed the first step and every train step stores
+                                   the last cell state back (layer/RNN.scala:32-35, 66-72; Optimizer.scala:141-144) */
 } sb_layer_desc;
 
 typedef struct {

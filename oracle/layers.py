@@ -795,15 +795,18 @@ class RNN(Layer):
     def __init__(self, cell, return_sequence=False, stateful=False):
         self.cell, self.return_sequence, self.stateful = cell, return_sequence, stateful
         self.trainable = cell.trainable
-        if stateful:
-            raise NotImplementedError("stateful RNN is outside the hot path (SURVEY 8f-4)")
 
     def _drop_time(self, s):
         return (s[0],) + tuple(s[2:])
 
     def params(self, in_shape):
         allp = self.cell.params(self._drop_time(in_shape))
+        if self.stateful:  # `if (stateful) state ++ weights else weights` (RNN.scala:32-35)
+            return allp
         return OrderedDict((k, d) for k, d in allp.items() if not k.split("/")[-1].endswith("state"))
+
+    def _state_keys(self):
+        return ("cell_state", "hidden_state") if isinstance(self.cell, LSTMCell) else ("0/state",)
 
     def out_shape(self, in_shape):
         co = self.cell.out_shape(self._drop_time(in_shape))
@@ -817,6 +820,11 @@ class RNN(Layer):
         c = np.zeros((b, u), x.dtype)
         caches, outs = [], []
         lstm = isinstance(self.cell, LSTMCell)
+        if self.stateful:  # the state params ARE the initial state (RNN.scala:66-67); zeros otherwise
+            if lstm:
+                c, h = p["cell_state"].astype(x.dtype), p["hidden_state"].astype(x.dtype)
+            else:
+                h = p["0/state"].astype(x.dtype)
         for t in range(T):
             xt = x[:, t, :]
             if lstm:
@@ -827,7 +835,12 @@ class RNN(Layer):
             caches.append(cache)
             outs.append(out)
         y = np.stack(outs, axis=1) if self.return_sequence else outs[-1]
-        return y, (caches, x.shape), {}
+        # the last cell state is the layer's output state (RNN.scala:68-72); only a stateful RNN declares it, so only then does it
+        # travel on with the params (the stateless case is SURVEY App. B-Q13)
+        state = {}
+        if self.stateful:
+            state = {"cell_state": c, "hidden_state": h} if lstm else {"0/state": h}
+        return y, (caches, x.shape), state
 
     def backward(self, g, cache, p, need_dx):
         caches, xshape = cache

@@ -308,6 +308,12 @@ static void build_plan(sb_engine* e) {
           if (d.use_bias)
             L.p_aux[gi * 3 + 2] = add_param(e, gp + "1/weights", {U}, SB_ROLE_WEIGHT, SB_AGG_AVG, gi == 0 ? d.init[3] : d.init[2], li);
         }
+        if (d.stateful) {  // `if (stateful) state ++ weights` (layer/RNN.scala:32-35; LSTMCell states :253-254, 302-304)
+          sb_initializer zeros{};
+          zeros.kind = SB_INIT_ZEROS;
+          L.p_aux[12] = add_param(e, pre + "cell_state", {cur.d[0], U}, SB_ROLE_STATE, SB_AGG_NONE, zeros, li);
+          L.p_aux[13] = add_param(e, pre + "hidden_state", {cur.d[0], U}, SB_ROLE_STATE, SB_AGG_NONE, zeros, li);
+        }
         if (d.return_sequence) {  // (batch, time, units): `joinAlong(outputs, 1)` (layer/RNN.scala:69-71)
           out.rank = 3;
           out.d[1] = cur.d[1];
@@ -331,6 +337,11 @@ static void build_plan(sb_engine* e) {
         L.p_aux[0] = add_param(e, pre + "0/kernel_weights", {F, U}, SB_ROLE_WEIGHT, SB_AGG_AVG, d.init[0], li);
         L.p_aux[1] = add_param(e, pre + "0/recurrent_weights", {U, U}, SB_ROLE_WEIGHT, SB_AGG_AVG, d.init[1], li);
         if (d.use_bias) L.p_aux[2] = add_param(e, pre + "1/weights", {U}, SB_ROLE_WEIGHT, SB_AGG_AVG, d.init[2], li);
+        if (d.stateful) {  // SimpleRNNCell.State (layer/RNN.scala:170-172)
+          sb_initializer zeros{};
+          zeros.kind = SB_INIT_ZEROS;
+          L.p_aux[3] = add_param(e, pre + "0/state", {cur.d[0], U}, SB_ROLE_STATE, SB_AGG_NONE, zeros, li);
+        }
         if (d.return_sequence) {
           out.rank = 3;
           out.d[1] = cur.d[1];
@@ -711,12 +722,12 @@ static void run_forward(sb_engine* e, int mode) {
       }
       case SB_LAYER_LSTM: {
         Prof pr(e, "lstm_fwd", 0, 0);
-        lstm_forward(e, L, li);
+        lstm_forward(e, L, li, mode == FWD_TRAIN);
         break;
       }
       case SB_LAYER_SIMPLE_RNN: {
         Prof pr(e, "rnn_fwd", 0, 0);
-        rnn_forward(e, L, li);
+        rnn_forward(e, L, li, mode == FWD_TRAIN);
         break;
       }
     }

@@ -45,6 +45,8 @@ struct LstmWs {
   float* dwkb_cat = nullptr; // [1 + F][4U]: db_cat row followed by dWk_cat rows (F <= 8: one fused pass)
   float* dx_tm = nullptr;    // [T, B, F] (only when the input gradient is needed)
   float* dout_tm = nullptr;  // [T, B, U] time-major copy of dLoss/d(output sequence) (returnSequence only)
+  float* c_init = nullptr;   // [B, U] stateful: c_{-1} as it was when the forward pass started (the backward pass needs it after
+                             // the train step has stored the new state)
   // tcgen05 TF32 plans (SB_PREC_TF32): one plan per contraction serves every time step through the tensor maps' slice coordinate
   TcGemm* g_fwd = nullptr;   // Z_t = H_{t-1} . Wr_cat           A slice t of h, C slice t of acts
   TcGemm* g_bwd = nullptr;   // dH_{t-1} = dZ_t . Wr_cat^T       A slice t of acts
@@ -267,6 +269,7 @@ LstmWs* ws_of(sb_engine* e, LayerPlan& L) {
   if (F <= 8) w->dwkb_cat = dalloc((F + 1) * 4 * U);
   if (L.need_dx) w->dx_tm = dalloc(T * B * F);
   if (L.d.return_sequence) w->dout_tm = dalloc(T * B * U);
+  if (L.d.stateful) w->c_init = dalloc(B * U);
   if (e->train.precision != SB_PREC_FP32 && B * U * 4 * U >= (1 << 22) && U % 32 == 0) {
     const int x3 = e->train.precision == SB_PREC_3XTF32 ? 1 : 0;
     w->g_fwd = tc_gemm_create(0, 1, w->h, (int)T + 1, w->wr_cat, 1, w->acts, (int)T, (int)B, (int)(4 * U), (int)U, 0, nullptr, 0, e->device, x3);
@@ -274,7 +277,7 @@ LstmWs* ws_of(sb_engine* e, LayerPlan& L) {
     w->g_dwr = tc_gemm_create(1, 1, w->h, 1, w->acts, 1, w->dwr_cat, 1, (int)U, (int)(4 * U), (int)(T * B), 1, e->ws, e->ws_floats,
                               e->device, x3);
     const char* fe = getenv("SB_LSTM_FUSED_EPILOGUE");
-    w->fused_epilogue = fe && fe[0] == '1' && w->g_fwd && w->g_bwd && !L.d.return_sequence;
+    w->fused_epilogue = fe && fe[0] == '1' && w->g_fwd && w->g_bwd && !L.d.return_sequence && !L.d.stateful;
   }
   L.lstm = w;
   return w;
@@ -305,7 +308,7 @@ void lstm_plan(sb_engine* e) {
     if (L.d.kind == SB_LAYER_LSTM) ws_of(e, L);  // allocate outside any stream capture
 }
 
-void lstm_forward(sb_engine* e, LayerPlan& L, int) {
+void lstm_forward(sb_engine* e, LayerPlan& L, int, bool store_state) {
   LstmWs* w = ws_of(e, L);
   cudaStream_t s = e->stream;
   const int B = w->B, T = w->T, F = w->F, U = w->U;
@@ -323,12 +326,21 @@ void lstm_forward(sb_engine* e, LayerPlan& L, int) {
   launch_k(lstm_transpose_kernel, ew_grid((long long)B * T * F), 256, 0, s, e->acts[L.buf_in], w->x_tm, B, T, F);
   SB_LAUNCHED();
   if (w->xw) gemm_nn(w->x_tm, w->wk_cat, w->xw, T * B, 4 * U, F, e->ws, e->ws_floats, s);
+  // stateful: the state parameters seed the first step (layer/RNN.scala:66-67).  h_{-1} goes into slot 0 of the hidden states
+  // (so H_prev_all stays one matrix for dWr), c_{-1} into its own buffer: the arena copies are overwritten by this very step.
+  const bool stateful = L.d.stateful != 0;
+  float* st_c = stateful ? e->arena + e->params[L.p_aux[12]].offset : nullptr;
+  float* st_h = stateful ? e->arena + e->params[L.p_aux[13]].offset : nullptr;
+  if (stateful) {
+    SB_CUDA(cudaMemcpyAsync(w->h, st_h, (size_t)BU * 4, cudaMemcpyDeviceToDevice, s));
+    SB_CUDA(cudaMemcpyAsync(w->c_init, st_c, (size_t)BU * 4, cudaMemcpyDeviceToDevice, s));
+  }
   for (int t = 0; t < T; ++t) {
     float* z = w->acts + (long long)t * B * 4 * U;
     const float* h_prev = w->h + (long long)t * BU;
     float* h_t = w->h + (long long)(t + 1) * BU;
     float* c_t = w->c + (long long)t * BU;
-    const float* c_prev = t ? w->c + (long long)(t - 1) * BU : nullptr;
+    const float* c_prev = t ? w->c + (long long)(t - 1) * BU : (stateful ? w->c_init : nullptr);
     if (t > 0 && w->fused_epilogue && !w->xw) {
       // Z_t = H_{t-1} . Wr_cat with the gate math in the GEMM epilogue: activations -> acts[t], c_t, h_t (no separate kernel)
       LstmEpi ep{};
@@ -338,13 +350,13 @@ void lstm_forward(sb_engine* e, LayerPlan& L, int) {
       tc_gemm_run_lstm(w->g_fwd, t, 0, t, ep, s);
       continue;
     }
-    if (t > 0) {  // h_{-1} = 0: no product at t = 0
+    if (t > 0 || stateful) {  // stateless: h_{-1} = 0, no product at t = 0
       if (w->g_fwd) tc_gemm_run(w->g_fwd, t, 0, t, s);
       else gemm_nn(h_prev, w->wr_cat, z, B, 4 * U, U, e->ws, e->ws_floats, s);
     }
     const float* x_t = w->x_tm + (long long)t * B * F;
     const float* xw_t = w->xw ? w->xw + (long long)t * B * 4 * U : nullptr;
-    const int first = t == 0;
+    const int first = t == 0 && !stateful;
     switch (w->xw ? 0 : F) {
       case 0: launch_gates_fwd<0>(w, z, x_t, xw_t, c_prev, c_t, h_t, first, act, ract, L.d.use_bias, s); break;
       case 1: launch_gates_fwd<1>(w, z, x_t, xw_t, c_prev, c_t, h_t, first, act, ract, L.d.use_bias, s); break;
@@ -356,6 +368,11 @@ void lstm_forward(sb_engine* e, LayerPlan& L, int) {
       case 7: launch_gates_fwd<7>(w, z, x_t, xw_t, c_prev, c_t, h_t, first, act, ract, L.d.use_bias, s); break;
       default: launch_gates_fwd<8>(w, z, x_t, xw_t, c_prev, c_t, h_t, first, act, ract, L.d.use_bias, s); break;
     }
+  }
+  // a train step hands the last cell state on with the parameters (`nextParams = nextWeights ++ nextState`, Optimizer.scala:141-144)
+  if (stateful && store_state) {
+    SB_CUDA(cudaMemcpyAsync(st_h, w->h + (long long)T * BU, (size_t)BU * 4, cudaMemcpyDeviceToDevice, s));
+    SB_CUDA(cudaMemcpyAsync(st_c, w->c + (long long)(T - 1) * BU, (size_t)BU * 4, cudaMemcpyDeviceToDevice, s));
   }
   if (L.d.return_sequence) {  // (batch, time, units) <- the time-major hidden states h_0 .. h_{T-1}
     launch_k(lstm_transpose_kernel, ew_grid((long long)T * BU), 256, 0, s, w->h + BU, e->acts[L.buf_out], T, B, U);
@@ -381,10 +398,12 @@ void lstm_backward(sb_engine* e, LayerPlan& L, int) {
   for (int t = T - 1; t >= 0; --t) {
     float* a = w->acts + (long long)t * B * 4 * U;
     const float* c_t = w->c + (long long)t * BU;
-    const float* c_prev = t ? w->c + (long long)(t - 1) * BU : nullptr;
+    const bool stateful = L.d.stateful != 0;
+    const float* c_prev = t ? w->c + (long long)(t - 1) * BU : (stateful ? w->c_init : nullptr);
     if (t == T - 1 || !w->fused_epilogue) {  // fused mode: the gate backward of step t < T-1 ran in the epilogue of step t+1
       const float* dh_seq = (seq && t < T - 1) ? w->dout_tm + (long long)t * BU : nullptr;
-      launch_k(lstm_gates_bwd_kernel, ew_grid(BU), 256, 0, s, a, c_t, c_prev, dh, dh_seq, w->dc, B, U, t == 0, t == T - 1, act, ract);
+      launch_k(lstm_gates_bwd_kernel, ew_grid(BU), 256, 0, s, a, c_t, c_prev, dh, dh_seq, w->dc, B, U, t == 0 && !stateful, t == T - 1, act,
+               ract);
       SB_LAUNCHED();
     }
     if (t > 0) {
@@ -447,7 +466,7 @@ void lstm_free(sb_engine* e) {
     if (!L.lstm || L.d.kind != SB_LAYER_LSTM) continue;
     LstmWs* w = (LstmWs*)L.lstm;
     for (float* p : {w->wr_cat, w->wk_cat, w->b_cat, w->x_tm, w->acts, w->c, w->h, w->xw, w->dh, w->dc, w->dwr_cat, w->dwk_cat,
-                     w->db_cat, w->dwkb_cat, w->dx_tm, w->dout_tm})
+                     w->db_cat, w->dwkb_cat, w->dx_tm, w->dout_tm, w->c_init})
       cudaFree(p);
     tc_gemm_destroy(w->g_fwd); tc_gemm_destroy(w->g_bwd); tc_gemm_destroy(w->g_dwr);
     delete w;

@@ -118,7 +118,7 @@ void rnn_plan(sb_engine* e) {
     if (L.d.kind == SB_LAYER_SIMPLE_RNN) ws_of(e, L);  // allocate outside any stream capture
 }
 
-void rnn_forward(sb_engine* e, LayerPlan& L, int) {
+void rnn_forward(sb_engine* e, LayerPlan& L, int, bool store_state) {
   RnnWs* w = ws_of(e, L);
   cudaStream_t s = e->stream;
   const int B = w->B, T = w->T, F = w->F, U = w->U;
@@ -129,13 +129,21 @@ void rnn_forward(sb_engine* e, LayerPlan& L, int) {
   launch_k(rnn_transpose_kernel, grid_of((long long)B * T * F), 256, 0, s, e->acts[L.buf_in], w->x_tm, B, T, F);
   SB_LAUNCHED();
   gemm_nn(w->x_tm, Wk, w->z + BU, T * B, U, F, e->ws, e->ws_floats, s);  // X_all . Wk straight into the z slots 1..T
+  const bool stateful = L.d.stateful != 0;
+  float* state = stateful ? e->arena + e->params[L.p_aux[3]].offset : nullptr;
+  // stateful: z_{-1} is the state parameter (slot 0 keeps it for the backward pass: dWr needs z_{-1} too); zeros otherwise
+  if (stateful) SB_CUDA(cudaMemcpyAsync(w->z, state, (size_t)BU * 4, cudaMemcpyDeviceToDevice, s));
   for (int t = 0; t < T; ++t) {
     float* z_t = w->z + (long long)(t + 1) * BU;
-    if (t > 0) gemm_nn(w->z + (long long)t * BU, Wr, w->rec, B, U, U, e->ws, e->ws_floats, s);
-    launch_k(rnn_step_fwd_kernel, grid_of(BU), 256, 0, s, z_t, t > 0 ? w->rec : nullptr, b, w->out + (long long)t * BU, BU, U,
+    const bool rec = t > 0 || stateful;
+    if (rec) gemm_nn(w->z + (long long)t * BU, Wr, w->rec, B, U, U, e->ws, e->ws_floats, s);
+    launch_k(rnn_step_fwd_kernel, grid_of(BU), 256, 0, s, z_t, rec ? w->rec : nullptr, b, w->out + (long long)t * BU, BU, U,
              L.d.activation, L.d.relu_threshold);
     SB_LAUNCHED();
   }
+  // a train step hands the last state on with the parameters (`nextParams = nextWeights ++ nextState`, Optimizer.scala:141-144)
+  if (stateful && store_state)
+    SB_CUDA(cudaMemcpyAsync(state, w->z + (long long)T * BU, (size_t)BU * 4, cudaMemcpyDeviceToDevice, s));
   if (L.d.return_sequence) {
     launch_k(rnn_transpose_kernel, grid_of((long long)T * BU), 256, 0, s, w->out, e->acts[L.buf_out], T, B, U);
     SB_LAUNCHED();

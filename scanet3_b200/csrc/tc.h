@@ -48,12 +48,12 @@ void tc_gemm_run_lstm(TcGemm* g, int za, int zb, int zc, const LstmEpi& epi, cud
 void tc_gemm_destroy(TcGemm* g);
 
 void lstm_plan(sb_engine* e);
-void lstm_forward(sb_engine* e, LayerPlan& L, int li);
+void lstm_forward(sb_engine* e, LayerPlan& L, int li, bool store_state);  // store_state: a train step of a stateful RNN
 void lstm_backward(sb_engine* e, LayerPlan& L, int li);
 void lstm_free(sb_engine* e);
 // RNN(SimpleRNNCell >> Bias >> Activate) (rnn.cu)
 void rnn_plan(sb_engine* e);
-void rnn_forward(sb_engine* e, LayerPlan& L, int li);
+void rnn_forward(sb_engine* e, LayerPlan& L, int li, bool store_state);
 void rnn_backward(sb_engine* e, LayerPlan& L, int li);
 void rnn_free(sb_engine* e);
 

@@ -198,7 +198,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // the on-chip setup above overlapped the previous kernel; global memory from here on
-  pdl_trigger();  // the next kernel may start ITS setup now (it still waits for this grid before reading its output)
+  // (no early launch trigger here: measured on cfg3 / cfg4, waiting dependents cost this persistent GEMM 2 %; profiles/r1_notes.md 17)
 
   if (warp >= 6) {
     // ================= 3xTF32 converters: lo = x - tf32(x) for every word of the stage's A and B tiles =================

@@ -374,24 +374,22 @@ class RNN(Layer):
     """layer/RNN.scala:27-94 around an LSTMCell or a SimpleRNNCell (>> Bias >> activation)."""
 
     def __init__(self, cell, returnSequence=False, stateful=False):
-        if stateful:
-            raise N.Unsupported(N.SB_ERR_UNSUPPORTED, "stateful RNNs are outside the accelerated path")
         if not isinstance(cell, (LSTMCell, SimpleRNNCell)):
             raise N.Unsupported(N.SB_ERR_UNSUPPORTED, "only LSTMCell and SimpleRNNCell are on the accelerated path")
-        self.cell, self.returnSequence = cell, bool(returnSequence)
+        self.cell, self.returnSequence, self.stateful = cell, bool(returnSequence), bool(stateful)
 
     def to_native(self):
         c = self.cell
         if isinstance(c, SimpleRNNCell):
             d = self._desc(N.LAYER_SIMPLE_RNN, units=c.units, activation=c.activation.code, use_bias=int(c.bias),
-                           return_sequence=int(self.returnSequence),
+                           return_sequence=int(self.returnSequence), stateful=int(self.stateful),
                            relu_threshold=float(getattr(c.activation, "threshold", 0.0)))
             for i, init in enumerate((c.kernelInitializer, c.recurrentInitializer, c.biasInitializer)):
                 d.init[i] = init.to_native()
             return d
         d = self._desc(N.LAYER_LSTM, units=c.units, activation=c.activation.code,
                        recurrent_activation=c.recurrentActivation.code, use_bias=int(c.bias),
-                       return_sequence=int(self.returnSequence))
+                       return_sequence=int(self.returnSequence), stateful=int(self.stateful))
         for i, init in enumerate((c.kernelInitializer, c.recurrentInitializer, c.biasInitializer, c.biasForgetInitializer)):
             d.init[i] = init.to_native()
         return d

@@ -41,20 +41,23 @@ def build_models(spec, seed=1):
             ol.append(O.BatchNorm(momentum=momentum, bn_mode=mode))
             sl.append(S.BatchNorm(momentum=momentum, bnMode=mode))
         elif kind == "lstm":
-            units, seq = it[1], (len(it) > 2 and bool(it[2]))  # ("lstm", units[, return_sequence])
-            ol.append(O.LSTM(units, return_sequence=seq, kernel_initializer=O.GlorotUniform(seed),
-                             recurrent_initializer=O.Orthogonal(seed=seed)))
+            # ("lstm", units[, return_sequence[, stateful]])
+            units, seq, stateful = it[1], (len(it) > 2 and bool(it[2])), (len(it) > 3 and bool(it[3]))
+            ocell = O.LSTMCell(units, kernel_initializer=O.GlorotUniform(seed), recurrent_initializer=O.Orthogonal(seed=seed))
+            ol.append(O.RNN(ocell, seq, stateful))
             sl.append(S.LSTM(units, kernelInitializer=S.GlorotUniform(seed), recurrentInitializer=S.Orthogonal(seed=seed),
-                             returnSequence=seq))
+                             returnSequence=seq, stateful=stateful))
         elif kind == "rnn":
-            # ("rnn", units, act[, return_sequence[, bias]])
+            # ("rnn", units, act[, return_sequence[, bias[, stateful]]])
             units, act = it[1], it[2]
             seq = len(it) > 3 and bool(it[3])
             bias = it[4] if len(it) > 4 else True
-            ol.append(O.SimpleRNN(units, _OACT[act], bias, seq, kernel_initializer=O.GlorotUniform(seed),
-                                  recurrent_initializer=O.Orthogonal(seed=seed)))
+            stateful = len(it) > 5 and bool(it[5])
+            ocell = O.SimpleRNNCell(units, _OACT[act], bias, kernel_initializer=O.GlorotUniform(seed),
+                                    recurrent_initializer=O.Orthogonal(seed=seed))
+            ol.append(O.RNN(ocell, seq, stateful))
             sl.append(S.SimpleRNN(units, _SACT[act], bias, kernelInitializer=S.GlorotUniform(seed),
-                                  recurrentInitializer=S.Orthogonal(seed=seed), returnSequence=seq))
+                                  recurrentInitializer=S.Orthogonal(seed=seed), returnSequence=seq, stateful=stateful))
         elif kind == "act":
             ol.append(O.Activate(_OACT[it[1]]))
             sl.append(S.Activate(_SACT[it[1]]))

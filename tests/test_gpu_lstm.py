@@ -216,5 +216,58 @@ def test_simple_rnn_trajectory_and_device_init():
         assert abs(gl - float(ol)) <= 1e-4 * abs(float(ol)) + 1e-7, (s_, gl, float(ol))
     assert_params_close(e.get_model_params(), mp, 2e-3, 3e-5, f"after {steps} steps")
     e.close()
-    with pytest.raises(S.Unsupported):
-        S.SimpleRNN(4, stateful=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# stateful = true (layer/RNN.scala:32-35, 66-72): the state tensors are parameters -- they seed the first step, every train step
+# stores the last cell state back (Optimizer.scala:141-144), the `loss` closure discards it (:163-167)
+# ---------------------------------------------------------------------------------------------------------------
+STATEFUL = {
+    "lstm": ([("lstm", 6, False, True), ("dense", 1, "tanh")], {"0/cell_state", "0/hidden_state"}),
+    "lstm_sequence_stack": ([("lstm", 5, True, True), ("lstm", 4, False, True), ("dense", 1, "tanh")],
+                            {"0/cell_state", "0/hidden_state", "1/cell_state", "1/hidden_state"}),
+    "simple_rnn": ([("rnn", 6, "tanh", False, True, True), ("dense", 1, "tanh")], {"0/0/state"}),
+}
+
+
+@pytest.mark.parametrize("name", list(STATEFUL))
+def test_stateful_rnn_trajectory_carries_the_state(name):
+    spec, state_paths = STATEFUL[name]
+    om, sm = build_models(spec)
+    batch, t, f, steps, rate = 8, 5, 2, 6, 5e-3
+    x, y = synth_series(batch * steps, t, f, 41)
+    e = S.Engine(sm, S.MeanSquaredError, S.Adam(rate), batch, (t, f), (1,), device=0)
+    oalg = O.Adam(rate)
+    _, mp, op = O.init_params(om, oalg, (batch, t, f))
+    assert set(e.model_param_paths()) == set(mp.keys()) and state_paths <= set(mp.keys())
+    e.set_params(mp)
+    e.init_opt_params()
+    lm = O.LossModel(om, O.MeanSquaredError)
+    for s_ in range(1, steps + 1):
+        xb, yb = x[(s_ - 1) * batch:s_ * batch], y[(s_ - 1) * batch:s_ * batch]
+        gl = e.train_step(xb, yb, s_)
+        mp, op, ol = O.train_step(lm, oalg, xb, yb, mp, op, s_)
+        assert abs(gl - float(ol)) <= 2e-4 * abs(float(ol)) + 1e-7, (s_, gl, float(ol))
+    got = e.get_model_params()
+    for k in state_paths:
+        assert np.abs(got[k]).max() > 1e-3                        # the state moved away from its Zeros initialiser ...
+    assert_params_close(got, mp, 3e-3, 5e-5, f"after {steps} steps")  # ... exactly as the oracle's did
+    # the `loss` closure and inference read the state but do not store it
+    before = {k: got[k].copy() for k in state_paths}
+    l1 = e.eval_loss(x[:batch], y[:batch])
+    np.testing.assert_allclose(l1, float(O.eval_loss(lm, x[:batch], y[:batch], mp)), rtol=2e-4)
+    e.predict(x[:batch])
+    after = e.get_model_params()
+    for k in state_paths:
+        assert np.array_equal(after[k], before[k]), k
+    e.close()
+
+
+def test_stateful_state_is_reinitialised_by_the_averaging():  # aggregation None => `paramDef.initializer.build` (Optimizer.scala:209)
+    _, sm = build_models([("lstm", 4, False, True), ("dense", 1, "tanh")])
+    x, y = synth_series(8 * 4, 4, 2, 43)
+    trained = (S.Dataset(x, y, partitions=2).train(sm).loss(S.MeanSquaredError).using(S.Adam(1e-3)).batch(8).devices([0, 0])
+               .stopAfter(S.epochs(2)).quiet().run())
+    assert np.all(trained.params["0/cell_state"] == 0) and np.all(trained.params["0/hidden_state"] == 0)
+    single = (S.Dataset(x, y).train(sm).loss(S.MeanSquaredError).using(S.Adam(1e-3)).batch(8).stopAfter(S.epochs(2)).quiet().run())
+    assert np.abs(single.params["0/hidden_state"]).max() > 0      # one partition: nothing is reduced, the state lives on
