@@ -104,7 +104,7 @@ typedef struct {
   int32_t window_h, window_w;   /* Conv2D kernel | Pool2D window */
   int32_t stride_h, stride_w;
   int32_t padding;              /* sb_padding */
-  int32_t pool_reduce;          /* sb_pool_reduce, recorded but ignored like the reference layer */
+  int32_t pool_reduce;          /* sb_pool_reduce, recorded but ignored like the reference layer unless pool_honor_reduce */
   int32_t use_bias;             /* LSTM, SimpleRNN */
   int32_t trainable;
   float bn_momentum, bn_epsilon;
@@ -116,6 +116,8 @@ typedef struct {
   float reg_lambda;
   int32_t pad_top, pad_bottom, pad_left, pad_right; /* Conv2D with SB_PAD_EXPLICIT (math/nn/AllKernels.scala:67-102) */
   int32_t return_sequence;      /* LSTM, SimpleRNN: output (batch, time, units) instead of the last step (layer/RNN.scala:21-27, 69-71) */
+  int32_t pool_honor_reduce;    /* Pool2D: 1 = apply `pool_reduce` (Avg pooling works); 0 = the reference layer's behaviour, which never
+                                   forwards `reduce` and therefore always max-pools (layer/Pool2D.scala:36-42) */
   int32_t stateful;             /* LSTM, SimpleRNN: the state tensors ("cell_state", "hidden_state" | "0/state", [batch, units],
                                    Zeros, aggregation None) are parameters: they seed the first step and every train step stores
                                    the last cell state back (layer/RNN.scala:32-35, 66-72; Optimizer.scala:141-144) */

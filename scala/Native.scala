@@ -32,7 +32,7 @@ object Native {
     MemoryLayout.paddingLayout(4), MemoryLayout.sequenceLayout(4, Initializer).withName("init"),
     JAVA_INT.withName("reg_kind"), JAVA_FLOAT.withName("reg_lambda"),
     JAVA_INT.withName("pad_top"), JAVA_INT.withName("pad_bottom"), JAVA_INT.withName("pad_left"), JAVA_INT.withName("pad_right"),
-    JAVA_INT.withName("return_sequence"), JAVA_INT.withName("stateful"))
+    JAVA_INT.withName("return_sequence"), JAVA_INT.withName("pool_honor_reduce"), JAVA_INT.withName("stateful"))
   val ModelDesc: StructLayout = MemoryLayout.structLayout(
     JAVA_INT.withName("n_layers"), MemoryLayout.paddingLayout(4), ADDRESS.withName("layers"),
     JAVA_INT.withName("input_rank"), MemoryLayout.paddingLayout(4),

@@ -54,7 +54,7 @@ class sb_layer_desc(C.Structure):
                 ("trainable", C.c_int32), ("bn_momentum", C.c_float), ("bn_epsilon", C.c_float), ("bn_mode", C.c_int32),
                 ("bn_fused", C.c_int32), ("init", sb_initializer * 4), ("reg_kind", C.c_int32), ("reg_lambda", C.c_float),
                 ("pad_top", C.c_int32), ("pad_bottom", C.c_int32), ("pad_left", C.c_int32), ("pad_right", C.c_int32),
-                ("return_sequence", C.c_int32), ("stateful", C.c_int32)]
+                ("return_sequence", C.c_int32), ("pool_honor_reduce", C.c_int32), ("stateful", C.c_int32)]
 
 
 class sb_model_desc(C.Structure):

@@ -462,6 +462,7 @@ static void plan_fusions(sb_engine* e) {
         break;
       }
       case SB_LAYER_POOL2D: {
+        if (L.d.pool_honor_reduce && L.d.pool_reduce == SB_POOL_AVG) break;  // average pooling: the generic kernels, no fusions
         L.fast_pool = L.pg.C % 4 == 0;
         // dx = [x > thr] * maxpool_grad: the mask of the in-place ReLU that produced this layer's input
         if (L.need_dx && inplace_relu(li - 1) && e->L[li - 1].buf_out == L.buf_in) {
@@ -702,9 +703,9 @@ static void run_forward(sb_engine* e, int mode) {
       }
       case SB_LAYER_POOL2D: {
         Prof pr(e, "pool_fwd", 4.0 * ((double)L.in.numel() + n_out), 0);
-        // the layer ignores `reduce` (layer/Pool2D.scala:36-42): always max
+        // the reference layer ignores `reduce` (layer/Pool2D.scala:36-42): always max, unless the descriptor asks to honour it
         if (L.fast_pool) pool_max_fwd_v4(in, out, L.pg, s);
-        else pool_fwd(in, out, L.pg, SB_POOL_MAX, s);
+        else pool_fwd(in, out, L.pg, (L.d.pool_honor_reduce && L.d.pool_reduce == SB_POOL_AVG) ? SB_POOL_AVG : SB_POOL_MAX, s);
         break;
       }
       case SB_LAYER_BATCHNORM: {
@@ -894,7 +895,7 @@ static void run_backward(sb_engine* e) {
         Prof pr(e, L.pool_relu_bwd ? "pool_relu_bwd" : "pool_bwd", 4.0 * (2.0 * L.in.numel() + 2.0 * n_out), 0);
         if (L.fast_pool) pool_max_bwd_v4(in, dout, din, L.pg, L.pool_relu_bwd, L.fused_thr, s);
         else if (L.pool_relu_bwd) pool_bwd_relu(in, dout, din, L.pg, L.fused_thr, s);
-        else pool_bwd(in, dout, din, L.pg, SB_POOL_MAX, s);
+        else pool_bwd(in, dout, din, L.pg, (L.d.pool_honor_reduce && L.d.pool_reduce == SB_POOL_AVG) ? SB_POOL_AVG : SB_POOL_MAX, s);
         break;
       }
       case SB_LAYER_BATCHNORM: {

@@ -330,7 +330,8 @@ class Pool2D(Layer):
     """layer/Pool2D.scala:28-57: window (2,2), strides (1,1), Valid, Max.  `reduce` is recorded but the layer's
     build never forwards it, so pooling is always Max."""
 
-    def __init__(self, window=(2, 2), strides=(1, 1), padding=Valid, format="NHWC", reduce="Max"):
+    def __init__(self, window=(2, 2), strides=(1, 1), padding=Valid, format="NHWC", reduce="Max", honorReduce=False):
+        self.honorReduce = bool(honorReduce)  # not in the reference: True makes `reduce="Avg"` average-pool
         if format != "NHWC":
             raise N.Unsupported(N.SB_ERR_UNSUPPORTED, "NCHW is outside the accelerated path (SURVEY 8b)")
         if isinstance(padding, Explicit) or padding not in _PAD:
@@ -340,7 +341,8 @@ class Pool2D(Layer):
     def to_native(self):
         return self._desc(N.LAYER_POOL2D, window_h=self.window[0], window_w=self.window[1], stride_h=self.strides[0],
                           stride_w=self.strides[1], padding=_PAD[self.padding],
-                          pool_reduce=N.POOL_AVG if self.reduce == "Avg" else N.POOL_MAX)
+                          pool_reduce=N.POOL_AVG if self.reduce == "Avg" else N.POOL_MAX,
+                          pool_honor_reduce=int(self.honorReduce))
 
     def __repr__(self):
         return f"Pool2D(({self.window[0]},{self.window[1]}),({self.strides[0]},{self.strides[1]}),{self.padding},NHWC,{self.reduce})"

@@ -30,9 +30,13 @@ def build_models(spec, seed=1):
             sl.append(S.Conv2D(filters, kernel, strides, spad, activation=_SACT[act], bias=bias,
                                kernelInitializer=S.GlorotUniform(seed)))
         elif kind == "pool":
-            _, window, strides, padding = it
-            ol.append(O.Pool2D(window, strides, padding.lower()))
-            sl.append(S.Pool2D(window, strides, padding))
+            window, strides, padding = it[1], it[2], it[3]  # ("pool", window, strides, padding[, reduce honoured])
+            if len(it) > 4:
+                ol.append(O.Pool2D(window, strides, padding.lower(), it[4].lower(), honor_reduce=True))
+                sl.append(S.Pool2D(window, strides, padding, reduce=it[4], honorReduce=True))
+            else:
+                ol.append(O.Pool2D(window, strides, padding.lower()))
+                sl.append(S.Pool2D(window, strides, padding))
         elif kind == "flatten":
             ol.append(O.Flatten)
             sl.append(S.Flatten)

@@ -612,3 +612,24 @@ def test_explicit_padding_trajectory_and_errors():
         make_engine(S.Conv2D(2, (2, 2), (2, 2), S.Explicit((1, 0), (0, 0))), S.MeanSquaredError, S.SGD(), 1, (4, 4, 1), (3, 2, 2))
     with pytest.raises(ValueError):         # Pool2D refuses Explicit like the reference (KernelsSpec.scala:258-268)
         S.Pool2D(padding=S.Explicit((1, 0), (1, 0)))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# average pooling when the descriptor asks to honour `reduce` (math/nn/KernelsSpec.scala:213-225, 294-305)
+# ---------------------------------------------------------------------------------------------------------------
+def test_avg_pool_goldens_and_trajectory():
+    exp = np.array([[1.75, 2.0, 1.5, 1.5, 2.0], [1.5, 2.25, 2.5, 2.0, 1.5], [1.5, 1.5, 1.75, 1.25, 0.5],
+                    [1.0, 1.25, 1.25, 1.25, 1.5], [0.0, 1.5, 2.0, 1.5, 2.0]], f32)
+    e = make_engine(S.Pool2D((2, 2), (1, 1), "Same", reduce="Avg", honorReduce=True), S.MeanSquaredError, S.SGD(), 1, (5, 5, 1),
+                    (5, 5, 1))
+    e.init_params()
+    assert np.array_equal(e.predict(IMG).reshape(5, 5), exp)
+    e.close()
+    e = make_engine(S.Pool2D((2, 2), (1, 1), "Same", reduce="Avg"), S.MeanSquaredError, S.SGD(), 1, (5, 5, 1), (5, 5, 1))
+    e.init_params()
+    assert e.predict(IMG).reshape(5, 5)[0, 0] == 3.0          # the reference layer: `reduce` ignored, max-pools
+    e.close()
+    spec = [("conv", 4, "relu", (3, 3), (1, 1), "Valid", False), ("pool", (2, 2), (2, 2), "Same", "Avg"),
+            ("conv", 6, "tanh", (2, 2), (1, 1), "Valid", True), ("pool", (2, 2), (1, 1), "Valid", "Avg"), ("flatten",),
+            ("dense", 5, "softmax")]
+    run_trajectory(spec, "cce", "adam", dict(rate=0.01), batch=6, in_shape=(9, 8, 2), classes=5, steps=8)
