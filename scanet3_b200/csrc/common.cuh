@@ -60,6 +60,13 @@ __device__ __forceinline__ void pdl_prologue_trigger_if(int early) {
 bool pdl_enabled();  // SB_PDL=0 turns the launch attribute off (engine.cu)
 int pdl_early_hint();               // host side, per thread: set by the engine for the model it is running (engine.cu)
 void set_pdl_early_hint(int on);
+// Pre-wait weight reads (a conv kernel's filter fill, the head kernels' W slab) are legal only if the kernel launched just before
+// does not write weights: the dependency wait covers that kernel alone, and everything older is complete only because that
+// kernel itself waited.  Host side, per thread: every launch sets it to 1, the launchers of weight-writing kernels (optimizer,
+// initialisers, scaling, averaging) and every API entry set it to 0; kernels that read weights before their wait take it as an
+// argument at launch (a forward pass started right behind an optimizer step -- the epoch's closing loss -- gets 0).
+int prewait_ok();
+void set_prewait_ok(int ok);
 template <typename K, typename... A>
 inline void launch_k(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t s, A&&... args) {
   cudaLaunchConfig_t cfg = {};
@@ -73,6 +80,7 @@ inline void launch_k(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t 
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   SB_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<A&&>(args)...));
+  set_prewait_ok(1);
 }
 #endif
 

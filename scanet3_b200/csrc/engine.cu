@@ -32,6 +32,9 @@ bool fork_enabled() {  // SB_BWD_FORK=0: the conv filter gradient stays in the m
   }();
   return on;
 }
+static thread_local int tl_prewait_ok = 0;
+int prewait_ok() { return tl_prewait_ok; }
+void set_prewait_ok(int ok) { tl_prewait_ok = ok; }
 static thread_local int tl_pdl_early = 0;
 int pdl_early_hint() { return tl_pdl_early; }
 void set_pdl_early_hint(int on) { tl_pdl_early = on; }
@@ -79,6 +82,7 @@ static void need_device(const sb_engine* e) {
   if (e->plan_only)
     SB_FAIL(SB_ERR_CUDA, "plan-only engine (device < 0): no CUDA device bound; this library has no CPU fallback");
   sb::set_pdl_early_hint(e->pdl_early ? 1 : 0);  // every compute entry point passes here: the launches that follow are this model's
+  sb::set_prewait_ok(0);                          // what ran last on the stream is unknown at an API boundary
 }
 struct DeviceGuard {
   int prev = -1;
@@ -1041,6 +1045,7 @@ static void launch_train_step(sb_engine* e, bool resident) {
     long long& nodes = resident ? e->nodes_resident : e->nodes_hostfed;
     if (!g) g = capture(e, &nodes, run_train_step_body, resident);
     SB_CUDA(cudaGraphLaunch(g, e->stream));
+    set_prewait_ok(0);  // a replayed graph may end in the optimizer
     e->launches += nodes;
   } else {
     run_train_step_body(e, resident);
@@ -1068,6 +1073,7 @@ static void launch_train_steps_resident(sb_engine* e, int64_t n_steps) {
     if (!e->g_resident_multi) e->g_resident_multi = capture(e, &e->nodes_resident_multi, run_train_steps_body_multi, true);
     for (; j + kStepsPerGraph <= n_steps; j += kStepsPerGraph) {
       SB_CUDA(cudaGraphLaunch(e->g_resident_multi, e->stream));
+      set_prewait_ok(0);  // a replayed graph may end in the optimizer
       e->launches += e->nodes_resident_multi;
     }
   }
@@ -1104,6 +1110,7 @@ static void launch_train_step_staged(sb_engine* e, const float* x, const float* 
   if (use_graph(e)) {
     if (!e->g_staged[par]) e->g_staged[par] = capture(e, &e->nodes_staged[par], run_train_step_body_staged, par != 0);
     SB_CUDA(cudaGraphLaunch(e->g_staged[par], e->stream));
+    set_prewait_ok(0);  // a replayed graph may end in the optimizer
     e->launches += e->nodes_staged[par];
   } else {
     run_train_step_body_staged(e, par != 0);
@@ -1136,6 +1143,7 @@ static void launch_train_group_staged(sb_engine* e, const float* x, const float*
   SB_CUDA(cudaStreamWaitEvent(e->stream, e->ev_copied[par], 0));
   if (!e->g_group[par]) e->g_group[par] = capture(e, &e->nodes_group[par], run_train_group_body_staged, par != 0);
   SB_CUDA(cudaGraphLaunch(e->g_group[par], e->stream));
+  set_prewait_ok(0);  // a replayed graph may end in the optimizer
   e->launches += e->nodes_group[par];
   SB_CUDA(cudaEventRecord(e->ev_free[par], e->stream));
   if (losses_out_host) {
@@ -1149,6 +1157,7 @@ static void launch_loss(sb_engine* e) {
   if (use_graph(e)) {
     if (!e->g_loss) e->g_loss = capture(e, &e->nodes_loss, loss_body, false);
     SB_CUDA(cudaGraphLaunch(e->g_loss, e->stream));
+    set_prewait_ok(0);  // a replayed graph may end in the optimizer
     e->launches += e->nodes_loss;
   } else {
     loss_body(e, false);

@@ -385,6 +385,7 @@ static void launch_slice(sb_group* g, int r) {
   int blocks = (int)std::min<long long>((hi - lo + 255) / 256, (long long)kNumSMs * 4);
   launch_k(p2p_average_kernel, blocks, 256, 0, e->stream, g->ps[r], lo, hi);
   SB_LAUNCHED();
+  set_prewait_ok(0);  // writes weights
   e->launches += 1;
 }
 
@@ -419,6 +420,7 @@ extern "C" int sb_group_average_device(sb_group* g, uint64_t epoch) {
   a.ticket = g->ticket;
   launch_k(p2p_average_sync_kernel, blocks, 256, 0, e->stream, g->ps[g->rank], lo, hi, a);
   SB_LAUNCHED();
+  set_prewait_ok(0);  // writes weights
   e->launches += 1;
   int rc = sb_reset_unaggregated(e);  // aggregation == None tensors are re-initialised (Optimizer.scala:209)
   if (rc != SB_OK) return rc;

@@ -499,12 +499,17 @@ static void launch_smallk_tile(const float* x, const float* w, float* y, const C
 template <int KH, int KW, int CIN, int PW>
 __global__ void __launch_bounds__(256) conv_smallk_pool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                    float* __restrict__ y, float* __restrict__ pooled, ConvGeom g,
-                                                                   int relu, float thr, int segs, long long n_threads) {
-  pdl_prologue_trigger();
+                                                                   int relu, float thr, int segs, long long n_threads,
+                                                                   int prewait) {
   constexpr int K = KH * KW * CIN;
   const int C4 = g.Cout >> 2;
   extern __shared__ __align__(16) float swt[];  // filter [K][Cout]
+  // prewait (common.cuh: prewait_ok): the kernel launched just before this one does not write weights, so the filter is staged
+  // under that kernel's tail, before the dependency wait; otherwise after it
+  if (!prewait) pdl_wait();
   for (int i = threadIdx.x; i < K * g.Cout; i += blockDim.x) swt[i] = w[i];
+  if (prewait) pdl_wait();
+  pdl_trigger();
   __syncthreads();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_threads) return;
@@ -593,7 +598,8 @@ static void launch_smallk_pool(const float* x, const float* w, float* y, float* 
   const int segs = (g.OW + PW - 1) / PW;  // covers the conv columns; the pool columns are one fewer
   const long long nt = (long long)g.N * (g.OH - 1) * segs * (g.Cout / 4);
   const size_t smem = (size_t)KH * KW * CIN * g.Cout * sizeof(float);
-  launch_k(conv_smallk_pool_fwd_kernel<KH, KW, CIN, PW>, (int)((nt + 255) / 256), 256, smem, s, x, w, y, pooled, g, relu, thr, segs, nt);
+  launch_k(conv_smallk_pool_fwd_kernel<KH, KW, CIN, PW>, (int)((nt + 255) / 256), 256, smem, s, x, w, y, pooled, g, relu, thr, segs, nt,
+           prewait_ok());
   SB_LAUNCHED();
 }
 bool conv_smallk_pool_fwd(const float* x, const float* w, float* y, float* pooled, const ConvGeom& g, int relu, float thr, cudaStream_t s) {
@@ -889,8 +895,7 @@ template <int NT, bool DGRAD>
 __global__ void __launch_bounds__(kBwdK* kBwdGroups) dense_head_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gmat,
                                                                             const float* __restrict__ w, float* __restrict__ dw,
                                                                             float* __restrict__ dx, int Mtot, int K, int N,
-                                                                            int rows_per_split, int early) {
-  pdl_prologue_trigger_if(early);
+                                                                            int rows_per_split, int early, int prewait) {
   extern __shared__ __align__(128) float sm[];
   // blockIdx.y = row split: rows [mlo, mhi); its dW goes to slice blockIdx.y of `dw` (summed in split order afterwards)
   const int mlo = blockIdx.y * rows_per_split, M = min(Mtot, mlo + rows_per_split);
@@ -900,10 +905,15 @@ __global__ void __launch_bounds__(kBwdK* kBwdGroups) dense_head_bwd_kernel(const
   float* red = sw + kBwdK * (NT + 1);          // [kBwdGroups][kBwdK][NT+1]
   const int tid = threadIdx.x, kk = tid % kBwdK, rg = tid / kBwdK;
   const int k0 = blockIdx.x * kBwdK, k = k0 + kk;
+  // prewait (common.cuh: prewait_ok): the kernel before this one (normally the loss kernel) does not write weights, so the W
+  // slab is staged before the dependency wait; otherwise after it
+  if (!prewait) pdl_wait();
   if (DGRAD) {
     const int kn = min(kBwdK, K - k0) * N;
     for (int i = tid; i < kn; i += blockDim.x) sw[(i / N) * (NT + 1) + i % N] = __ldg(w + (size_t)k0 * N + i);
   }
+  if (prewait) pdl_wait();
+  if (early) pdl_trigger();
   __syncthreads();
   float2 acc2[NT / 2], wr2[NT / 2];  // packed fp32x2 FMAs (FFMA2)
 #pragma unroll
@@ -972,12 +982,13 @@ bool dense_head_bwd(const float* x, const float* g, const float* w, float* dw, f
   splits = (M + rows_per_split - 1) / rows_per_split;
   float* dwo = splits > 1 ? ws : dw;
   const dim3 grid(kblocks, splits);
+  const int pw = prewait_ok();
   if (NT == 12) {
-    if (dx) launch_k(dense_head_bwd_kernel<12, true>, grid, thr, smem, s, x, g, w, dwo, dx, M, K, N, rows_per_split, pdl_early_hint());
-    else launch_k(dense_head_bwd_kernel<12, false>, grid, thr, smem, s, x, g, w, dwo, dx, M, K, N, rows_per_split, pdl_early_hint());
+    if (dx) launch_k(dense_head_bwd_kernel<12, true>, grid, thr, smem, s, x, g, w, dwo, dx, M, K, N, rows_per_split, pdl_early_hint(), pw);
+    else launch_k(dense_head_bwd_kernel<12, false>, grid, thr, smem, s, x, g, w, dwo, dx, M, K, N, rows_per_split, pdl_early_hint(), pw);
   } else {
-    if (dx) launch_k(dense_head_bwd_kernel<16, true>, grid, thr, smem, s, x, g, w, dwo, dx, M, K, N, rows_per_split, pdl_early_hint());
-    else launch_k(dense_head_bwd_kernel<16, false>, grid, thr, smem, s, x, g, w, dwo, dx, M, K, N, rows_per_split, pdl_early_hint());
+    if (dx) launch_k(dense_head_bwd_kernel<16, true>, grid, thr, smem, s, x, g, w, dwo, dx, M, K, N, rows_per_split, pdl_early_hint(), pw);
+    else launch_k(dense_head_bwd_kernel<16, false>, grid, thr, smem, s, x, g, w, dwo, dx, M, K, N, rows_per_split, pdl_early_hint(), pw);
   }
   SB_LAUNCHED();
   if (splits > 1) partial_reduce(ws, dw, K * N, splits, s);

@@ -1133,6 +1133,7 @@ void optimizer_step(const OptDesc& o, float* w, const float* g, float* s0, float
   }
 #undef SB_OPT
   SB_LAUNCHED();
+  set_prewait_ok(0);  // writes weights / optimizer state: the next kernel must not read weights before its wait
 }
 
 // =================================================================================================
@@ -1164,6 +1165,7 @@ void fill_const(float* p, float v, long long n, cudaStream_t s) {
   int blocks = (int)fmin((double)ceil_div(n, 256), (double)kNumSMs * 16);
   launch_k(fill_kernel, blocks, 256, 0, s, p, v, n);
   SB_LAUNCHED();
+  set_prewait_ok(0);  // writes weights / optimizer state: the next kernel must not read weights before its wait
 }
 __global__ void scale_kernel(float* __restrict__ p, float w, long long n) {
   pdl_prologue();
@@ -1176,6 +1178,7 @@ void scale_inplace(float* p, float w, long long n, cudaStream_t s) {
   int blocks = (int)fmin((double)ceil_div(n, 256), (double)kNumSMs * 16);
   launch_k(scale_kernel, blocks, 256, 0, s, p, w, n);
   SB_LAUNCHED();
+  set_prewait_ok(0);  // writes weights / optimizer state: the next kernel must not read weights before its wait
 }
 
 // TF's seeded RandomUniform / RandomStandardNormal: Philox-4x32-10, key = seed, counter = block index
@@ -1252,6 +1255,7 @@ void philox_fill(float* p, long long n, unsigned long long seed, int normal, flo
   long long nblk = (n + 3) / 4;
   launch_k(philox_fill_kernel, ceil_div(nblk, 256), 256, 0, s, p, n, seed, normal, scale, has_scale, shift, has_shift);
   SB_LAUNCHED();
+  set_prewait_ok(0);  // writes weights / optimizer state: the next kernel must not read weights before its wait
 }
 
 }  // namespace sb

@@ -1285,6 +1285,7 @@ bool tc_conv_fwd(sb_engine* e, LayerPlan& L, int) {
 // =====================================================================================================================
 struct HeadFwdParams {
   int M, K, N, KC, chunks;
+  int prewait;  // common.cuh prewait_ok(): the W slab may be read before the dependency wait
   const float* w;
   float* partial;
 };
@@ -1314,8 +1315,9 @@ __global__ void __launch_bounds__(kHeadTcThreads, 1) head_fwd_tc_kernel(const __
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // the weights were last written by the optimizer, never by the kernel just before this one: stage them before the
-  // programmatic-dependency wait.  Element (n, k) of tile t: row n (128 B), chunk ((k%32)/4) ^ (n%8), word k%4.
+  // W slab: element (n, k) of tile t goes to row n (128 B), chunk ((k%32)/4) ^ (n%8), word k%4.  When the kernel launched just
+  // before this one does not write weights (p.prewait, common.cuh) it is staged before the programmatic-dependency wait
+  if (!p.prewait) pdl_wait();
   for (int i = threadIdx.x; i < nkt * 32 * 16; i += blockDim.x) {
     const int n = i & 15, k = i >> 4;
     const float v = n < p.N ? __ldg(p.w + (size_t)(k0 + k) * p.N + n) : 0.f;
@@ -1323,7 +1325,7 @@ __global__ void __launch_bounds__(kHeadTcThreads, 1) head_fwd_tc_kernel(const __
     *reinterpret_cast<float*>(sm_b + (size_t)t * 2048 + n * 128 + ((((kk >> 2) ^ (n & 7)) << 4) | ((kk & 3) << 2))) = v;
   }
   fence_proxy_async();
-  pdl_wait();
+  if (p.prewait) pdl_wait();
   pdl_trigger();  // dependents may start their own on-chip setup now (they still wait for this grid before touching its output)
   __syncthreads();
   if (warp == 0) {
@@ -1408,6 +1410,7 @@ bool tc_head_fwd(sb_engine* e, LayerPlan& L, const float* x, const float* w, flo
   if ((size_t)P->p.chunks * M * N > partial_floats) return false;
   P->p.w = w;
   P->p.partial = partial;
+  P->p.prewait = prewait_ok();
   launch_k(head_fwd_tc_kernel, P->p.chunks, kHeadTcThreads, P->smem, e->stream, P->map_x, P->p);
   SB_LAUNCHED();
   *chunks_out = P->p.chunks;

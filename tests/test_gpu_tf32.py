@@ -143,6 +143,30 @@ def test_tf32_resident_epoch_runs_in_a_cuda_graph_and_matches_eager():
         assert np.array_equal(res[0][4][k], res[1][4][k]), k
 
 
+def test_tf32_head_only_model_closing_loss_sees_the_updated_weights():
+    # the classifier head is the FIRST kernel of the epoch's closing loss, launched right behind the optimizer: its W slab must not be
+    # staged ahead of the programmatic-dependency wait there (common.cuh prewait_ok); eager launches and graph replays must agree
+    _, sm = build_models([("dense", 10, "softmax")])
+    # 8192 features: K >= 32 * 148 puts the head forward on the tcgen05 split-K kernel (tc.cu tc_head_fwd)
+    x, y = synth_classification(100 * 5, (8192,), 10, 11)
+    res = []
+    for use_graph in (True, False):
+        e = S.Engine(sm, S.CategoricalCrossentropy, S.Adam(0.001), 100, (8192,), (10,), device=0, precision=S.PREC_TF32,
+                     use_graph=use_graph)
+        e.init_params()
+        e.upload_dataset(x, y)
+        it, loss = e.train_epoch(0)
+        it2, loss2 = e.train_epoch(it)
+        step_loss = e.train_step(x[:100], y[:100], it2 + 1)
+        after = e.eval_loss(x[:100], y[:100])  # again right behind an optimizer launch
+        res.append((it, loss, it2, loss2, step_loss, after, e.get_model_params()))
+        e.close()
+    assert all(np.isfinite(v) for v in res[0][:6])
+    assert res[0][:6] == res[1][:6]
+    for k in res[0][6]:
+        assert np.array_equal(res[0][6][k], res[1][6][k]), k
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # Dense (MatMul fwd / dgrad / wgrad) and the LSTM contractions on the tcgen05 GEMM
 # ---------------------------------------------------------------------------------------------------------------
