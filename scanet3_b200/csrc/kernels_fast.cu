@@ -149,31 +149,10 @@ __global__ void __launch_bounds__(256) pool_max_bwd_v4_kernel(const float* __res
   }
 }
 
-// first maximum of a 2x2 window in row-major order (strict > keeps the earlier element): 0..3
-__device__ __forceinline__ int argmax22(float p0, float p1, float p2, float p3) {
-  int k = 0;
-  float best = p0;
-  if (p1 > best) { best = p1; k = 1; }
-  if (p2 > best) { best = p2; k = 2; }
-  if (p3 > best) { k = 3; }
-  return k;
-}
-struct Idx4 { int x, y, z, w; };
-__device__ __forceinline__ Idx4 argmax22_4(float4 p0, float4 p1, float4 p2, float4 p3) {
-  Idx4 r;
-  r.x = argmax22(p0.x, p1.x, p2.x, p3.x); r.y = argmax22(p0.y, p1.y, p2.y, p3.y);
-  r.z = argmax22(p0.z, p1.z, p2.z, p3.z); r.w = argmax22(p0.w, p1.w, p2.w, p3.w);
-  return r;
-}
-__device__ __forceinline__ void acc_if(float4& acc, const Idx4& k, int pos, const float4& gy) {
-  if (k.x == pos) acc.x = __fadd_rn(acc.x, gy.x);
-  if (k.y == pos) acc.y = __fadd_rn(acc.y, gy.y);
-  if (k.z == pos) acc.z = __fadd_rn(acc.z, gy.z);
-  if (k.w == pos) acc.w = __fadd_rn(acc.w, gy.w);
-}
 // Backward strip: a thread owns (image, INPUT row h, channel quad) and walks a segment of the row.  Column w of the walk
-// evaluates the two windows whose top-left corner is in column w (rows h-1 and h) once -- 3 x loads + 2 dy loads -- and
-// keeps them for column w+1, where the element is their right-hand member.  Summation order per element: windows
+// loads column w+1 of the rows h-1, h, h+1 and the dy of the two windows whose top-left corner is in column w (3 x loads +
+// 2 dy loads) and keeps columns w-1, w in registers; the element (h, w) takes dy of a window iff it is that window's FIRST
+// maximum, decided by compares against maxima of its 8 neighbours.  Summation order per element: windows
 // (h-1,w-1), (h-1,w), (h,w-1), (h,w) -- the same as the generic gather kernel.
 //
 // WG = KH*100 + KW*10 + CIN != 0 additionally fuses the FILTER GRADIENT of the small-K Conv2D that produced the pool's input
@@ -218,20 +197,18 @@ __global__ void __launch_bounds__(128) pool22_bwd_strip_kernel(const float* __re
     const float* db = dy + (((long long)b * g.OH + (bot_ok ? h : 0)) * g.OW) * g.C + c4 * 4;
     float* dxo = dx + (((long long)b * g.H + h) * g.W) * g.C + c4 * 4;
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    // state of column w-1: its x values and the two windows anchored there
-    float4 ct, cm, cb;          // x[h-1][w], x[h][w], x[h+1][w] of the CURRENT column
-    Idx4 pkt{-1, -1, -1, -1}, pkb{-1, -1, -1, -1};
+    // columns w-1 (p*), w (c*) of the rows h-1, h, h+1 and the dy of the two windows anchored in column w-1
+    float4 pt, pm, pb, ct, cm, cb;
     float4 pgt = zero, pgb = zero;
     if (w0 >= 1) {
-      const long long o = (long long)(w0 - 1) * g.C;
-      const float4 lt = ld4(xt + o), lm = ld4(xm + o), lb = ld4(xb + o);
+      const int o = (w0 - 1) * g.C;  // offsets inside one image row fit 32 bits
+      pt = ld4(xt + o); pm = ld4(xm + o); pb = ld4(xb + o);
       ct = ld4(xt + o + g.C); cm = ld4(xm + o + g.C); cb = ld4(xb + o + g.C);
-      pkt = argmax22_4(lt, ct, lm, cm);
-      pkb = argmax22_4(lm, cm, lb, cb);
       pgt = top_ok ? ld4(dt + o) : zero;
       pgb = bot_ok ? ld4(db + o) : zero;
     } else {
       ct = ld4(xt); cm = ld4(xm); cb = ld4(xb);
+      pt = ct; pm = cm; pb = cb;  // no windows in column -1: their dy is zero
     }
     // conv input window of the current pixel: rows h+a-PT, columns w+bb-PL (zero outside the image)
     float xw[KH > 0 ? KH : 1][KW > 0 ? KW : 1][CIN > 0 ? CIN : 1];
@@ -249,30 +226,43 @@ __global__ void __launch_bounds__(128) pool22_bwd_strip_kernel(const float* __re
 #pragma unroll
       for (int bb = 0; bb + 1 < KW; ++bb) load_col(w0 - wf.PL + bb, bb + 1);  // shifted into place by the first iteration
     }
+    // running pointers (one 64-bit add per pointer and column instead of an index multiply + sign extension each)
+    const float *nxt = xt + (w0 + 1) * g.C, *nxm = xm + (w0 + 1) * g.C, *nxb = xb + (w0 + 1) * g.C;  // column w+1 of the three rows
+    const float *dtw = dt + w0 * g.C, *dbw = db + w0 * g.C;                                          // dy of the windows of column w
+    float* dxw = dxo + w0 * g.C;
 #pragma unroll 2
     for (int w = w0; w < w1; ++w) {
-      const long long o = (long long)w * g.C;
-      Idx4 kt{-1, -1, -1, -1}, kb{-1, -1, -1, -1};
       float4 gt = zero, gb = zero, nt = ct, nm = cm, nb = cb;
       if (w <= g.W - 2) {  // windows anchored in column w exist
-        nt = ld4(xt + o + g.C); nm = ld4(xm + o + g.C); nb = ld4(xb + o + g.C);
-        kt = argmax22_4(ct, nt, cm, nm);
-        kb = argmax22_4(cm, nm, cb, nb);
-        gt = top_ok ? ld4(dt + o) : zero;
-        gb = bot_ok ? ld4(db + o) : zero;
+        nt = ld4(nxt); nm = ld4(nxm); nb = ld4(nxb);
+        gt = top_ok ? ld4(dtw) : zero;
+        gb = bot_ok ? ld4(dbw) : zero;
       }
+      nxt += g.C; nxm += g.C; nxb += g.C; dtw += g.C; dbw += g.C;
+      // the element is the FIRST maximum of a window (row-major order, strict > displaces an earlier member) iff it beats the
+      // earlier members strictly and the later ones weakly: compares against maxima of its 8 neighbours (FMNMX / FMNMX3) instead
+      // of two 4-way arg-maxes with index bookkeeping
       float4 acc = zero;
-      acc_if(acc, pkt, 3, pgt);  // window (h-1, w-1): element is its bottom-right member
-      acc_if(acc, kt, 2, gt);    // window (h-1, w)  : bottom-left
-      acc_if(acc, pkb, 1, pgb);  // window (h,   w-1): top-right
-      acc_if(acc, kb, 0, gb);    // window (h,   w)  : top-left
+#define SB_WIN(c)                                                                                                        \
+  {                                                                                                                      \
+    const float e = cm.c;                                                                                                \
+    const float m1 = fmaxf(fmaxf(pt.c, ct.c), pm.c), m2 = fmaxf(ct.c, nt.c);                                             \
+    const float m3 = fmaxf(pb.c, cb.c), m4 = fmaxf(fmaxf(nm.c, cb.c), nb.c);                                             \
+    if (e > m1) acc.c = __fadd_rn(acc.c, pgt.c);                /* window (h-1, w-1): the bottom-right member */          \
+    if (e > m2 && e >= nm.c) acc.c = __fadd_rn(acc.c, gt.c);    /* window (h-1, w)  : bottom-left             */          \
+    if (e > pm.c && e >= m3) acc.c = __fadd_rn(acc.c, pgb.c);   /* window (h,   w-1): top-right               */          \
+    if (e >= m4) acc.c = __fadd_rn(acc.c, gb.c);                /* window (h,   w)  : top-left                */          \
+  }
+      SB_WIN(x) SB_WIN(y) SB_WIN(z) SB_WIN(w)
+#undef SB_WIN
       if (RELU) {
         if (!(cm.x > thr)) acc.x = 0.f;
         if (!(cm.y > thr)) acc.y = 0.f;
         if (!(cm.z > thr)) acc.z = 0.f;
         if (!(cm.w > thr)) acc.w = 0.f;
       }
-      if (!WG || wf.store_dx) st4(dxo + o, acc);
+      if (!WG || wf.store_dx) st4(dxw, acc);
+      dxw += g.C;
       if (WG) {
 #pragma unroll
         for (int a = 0; a < KH; ++a)
@@ -292,7 +282,8 @@ __global__ void __launch_bounds__(128) pool22_bwd_strip_kernel(const float* __re
               r.x = fmaf(xv, acc.x, r.x); r.y = fmaf(xv, acc.y, r.y); r.z = fmaf(xv, acc.z, r.z); r.w = fmaf(xv, acc.w, r.w);
             }
       }
-      pkt = kt; pkb = kb; pgt = gt; pgb = gb;
+      pgt = gt; pgb = gb;
+      pt = ct; pm = cm; pb = cb;
       ct = nt; cm = nm; cb = nb;
     }
   }
@@ -326,7 +317,9 @@ __global__ void __launch_bounds__(128) pool22_bwd_strip_kernel(const float* __re
   }
 }
 // segments per row: cost ~ whole waves x (columns per thread + prologue columns); a wave = what 148 SMs hold at the kernel's
-// register footprint
+// register footprint.  The prologue (index split, pointer setup, the column before the segment) costs ~2.5 columns of the walk
+// (SASS: 315 instructions against 119 per column): LeNet's pool2 backward (23 columns) then takes 2 segments in one wave instead
+// of 5 in two (933.5 k -> 937.7 k samples/s)
 static void pool22_segments(const PoolGeom& g, int ctas_per_sm, int* segs_out, int* seg_len_out) {
   const long long wave = (long long)kNumSMs * ctas_per_sm * 128;
   int best_segs = 1;
@@ -335,7 +328,7 @@ static void pool22_segments(const PoolGeom& g, int ctas_per_sm, int* segs_out, i
     const int len = (g.W + segs - 1) / segs;
     if ((segs - 1) * len >= g.W) continue;
     const long long nt = (long long)g.N * g.H * segs * (g.C / 4);
-    const double cost = (double)((nt + wave - 1) / wave) * (len + 1.5);
+    const double cost = (double)((nt + wave - 1) / wave) * (len + 2.5);
     if (cost < best) { best = cost; best_segs = segs; }
   }
   *segs_out = best_segs;
