@@ -56,13 +56,13 @@ __global__ void __launch_bounds__(256) pool22_fwd_strip_kernel(const float* __re
                                                                int seg_len, long long n_threads) {
   pdl_prologue_trigger();
   const int C4 = g.C >> 2;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_threads) return;
-  const int c4 = (int)(i % C4);
-  long long t = i / C4;
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;  // 32-bit index split (the launcher keeps n_threads < 2^31)
+  if ((long long)i >= n_threads) return;
+  const int c4 = (int)(i % (unsigned)C4);
+  unsigned t = i / (unsigned)C4;
   const int seg = (int)(t % kPoolSegs); t /= kPoolSegs;
-  const int oh = (int)(t % g.OH);
-  const int b = (int)(t / g.OH);
+  const int oh = (int)(t % (unsigned)g.OH);
+  const int b = (int)(t / (unsigned)g.OH);
   const int w0 = seg * seg_len;
   const int w1 = min(w0 + seg_len, g.OW);
   if (w0 >= w1) return;
@@ -81,8 +81,9 @@ static bool pool_is_22s1(const PoolGeom& g) {
   return g.KH == 2 && g.KW == 2 && g.SH == 1 && g.SW == 1 && g.PT == 0 && g.PL == 0 && g.OH == g.H - 1 && g.OW == g.W - 1;
 }
 void pool_max_fwd_v4(const float* x, float* y, const PoolGeom& g, cudaStream_t s) {
-  if (pool_is_22s1(g)) {
-    const long long nt = (long long)g.N * g.OH * kPoolSegs * (g.C / 4);
+  const long long nt22 = (long long)g.N * g.OH * kPoolSegs * (g.C / 4);
+  if (pool_is_22s1(g) && nt22 < (1LL << 31)) {  // the strip kernels split a 32-bit thread index
+    const long long nt = nt22;
     const int seg_len = (g.OW + kPoolSegs - 1) / kPoolSegs;
     launch_k(pool22_fwd_strip_kernel, (int)((nt + 255) / 256), 256, 0, s, x, y, g, seg_len, nt);
     SB_LAUNCHED();
@@ -173,15 +174,15 @@ __global__ void __launch_bounds__(128) pool22_bwd_strip_kernel(const float* __re
   pdl_prologue_trigger();
   constexpr int KH = WG / 100, KW = (WG / 10) % 10, CIN = WG % 10, K = KH * KW * CIN;
   const int C4 = g.C >> 2;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int c4 = (int)(i % C4);
-  long long t = i / C4;
-  const int seg = (int)(t % segs); t /= segs;
-  const int h = (int)(t % g.H);
-  const int b = (int)(t / g.H);
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;  // 32-bit index split (the launcher keeps n_threads < 2^31)
+  const int c4 = (int)(i % (unsigned)C4);
+  unsigned t = i / (unsigned)C4;
+  const int seg = (int)(t % (unsigned)segs); t /= (unsigned)segs;
+  const int h = (int)(t % (unsigned)g.H);
+  const int b = (int)(t / (unsigned)g.H);
   const int w0 = seg * seg_len;
   const int w1 = min(w0 + seg_len, g.W);
-  const bool active = i < n_threads && w0 < w1;
+  const bool active = (long long)i < n_threads && w0 < w1;
   float4 dwacc[K > 0 ? K : 1];
   if (WG) {
 #pragma unroll
@@ -345,6 +346,7 @@ bool pool_bwd_conv_wgrad(const float* x, const float* dy, float* dx, const PoolG
   int segs, seg_len;
   pool22_segments(g, 3, &segs, &seg_len);
   const long long nt = (long long)g.N * g.H * segs * C4;
+  if (nt >= (1LL << 31)) return false;  // the strip kernel splits a 32-bit thread index
   const int blocks = (int)((nt + 127) / 128);
   const int K = cg.KH * cg.KW * cg.Cin;
   if ((size_t)blocks * K * g.C > ws_floats) return false;
@@ -363,7 +365,7 @@ bool pool_bwd_conv_wgrad(const float* x, const float* dy, float* dx, const PoolG
   return true;
 }
 void pool_max_bwd_v4(const float* x, const float* dy, float* dx, const PoolGeom& g, int relu, float thr, cudaStream_t s) {
-  if (pool_is_22s1(g)) {
+  if (pool_is_22s1(g) && (long long)g.N * g.H * 8 * (g.C / 4) < (1LL << 31)) {  // <= 8 segments; 32-bit thread index in the kernel
     int segs, seg_len;
     pool22_segments(g, 5, &segs, &seg_len);
     const long long nt = (long long)g.N * g.H * segs * (g.C / 4);
@@ -504,84 +506,101 @@ __global__ void __launch_bounds__(256) conv_smallk_pool_fwd_kernel(const float* 
   if (prewait) pdl_wait();
   pdl_trigger();
   __syncthreads();
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_threads) return;
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;  // 32-bit index split (the launcher keeps n_threads < 2^31)
+  if ((long long)i >= n_threads) return;
   const int OHp = g.OH - 1, OWp = g.OW - 1;
-  const int c4 = (int)(i % C4);
-  long long t = i / C4;
-  const int seg = (int)(t % segs); t /= segs;
-  const int pr = (int)(t % OHp);
-  const int b = (int)(t / OHp);
+  const int c4 = (int)(i % (unsigned)C4);
+  unsigned t = i / (unsigned)C4;
+  const int seg = (int)(t % (unsigned)segs); t /= (unsigned)segs;
+  const int pr = (int)(t % (unsigned)OHp);
+  const int b = (int)(t / (unsigned)OHp);
   const int ow0 = seg * PW;
-  float4 acc[2][PW + 1];
+  // packed fp32x2 FMAs (FFMA2: two independent IEEE FMAs, the same bits as the scalar form): channel pairs (0,1) and (2,3)
+  float2 acc[2][PW + 1][2];
 #pragma unroll
   for (int r = 0; r < 2; ++r)
 #pragma unroll
-    for (int p = 0; p <= PW; ++p) acc[r][p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = 0; p <= PW; ++p) acc[r][p][0] = acc[r][p][1] = make_float2(0.f, 0.f);
+  // single-channel rows without left padding whose pitch keeps 16-byte alignment: the PW + KW <= 8 inputs of a row are two
+  // float4 loads (the second only when it stays inside the row) instead of PW + KW bounds-checked scalar loads
+  const bool vec_rows = CIN == 1 && PW + KW <= 8 && g.PL == 0 && (g.W & 3) == 0 && (PW & 3) == 0 && ((uintptr_t)x & 15) == 0;
+  // (ow0 and W are multiples of 4: the first quad is always inside the row, the second entirely inside or entirely outside)
+  const float* wq = swt + c4 * 4;
 #pragma unroll
   for (int a = 0; a <= KH; ++a) {  // input row pr + a - PT feeds conv row pr (filter row a) and conv row pr+1 (filter row a-1)
     const int ih = pr + a - g.PT;
     const bool row_ok = ih >= 0 && ih < g.H;
     const float* xr = x + ((long long)b * g.H + (row_ok ? ih : 0)) * g.W * CIN;
-    float xv[(PW + KW) * CIN];
+    float xv[(PW + KW) * CIN > 8 ? (PW + KW) * CIN : 8];
+    if (vec_rows) {
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 lo = row_ok ? ld4(xr + ow0) : z4;  // ow0 < OW <= W: always inside the row
+      const float4 hi = (row_ok && ow0 + 8 <= g.W) ? ld4(xr + ow0 + 4) : z4;
+      xv[0] = lo.x; xv[1] = lo.y; xv[2] = lo.z; xv[3] = lo.w; xv[4] = hi.x; xv[5] = hi.y; xv[6] = hi.z; xv[7] = hi.w;
+    } else {
 #pragma unroll
-    for (int q = 0; q < PW + KW; ++q) {
-      const int iw = ow0 + q - g.PL;
-      const bool ok = row_ok && iw >= 0 && iw < g.W;
+      for (int q = 0; q < PW + KW; ++q) {
+        const int iw = ow0 + q - g.PL;
+        const bool ok = row_ok && iw >= 0 && iw < g.W;
 #pragma unroll
-      for (int ci = 0; ci < CIN; ++ci) xv[q * CIN + ci] = ok ? __ldg(xr + (long long)iw * CIN + ci) : 0.f;
+        for (int ci = 0; ci < CIN; ++ci) xv[q * CIN + ci] = ok ? __ldg(xr + iw * CIN + ci) : 0.f;
+      }
     }
 #pragma unroll
     for (int bb = 0; bb < KW; ++bb)
 #pragma unroll
       for (int ci = 0; ci < CIN; ++ci) {
         if (a < KH) {
-          const float4 wv = *reinterpret_cast<const float4*>(&swt[((a * KW + bb) * CIN + ci) * g.Cout + c4 * 4]);
+          const float4 wv = *reinterpret_cast<const float4*>(wq + ((a * KW + bb) * CIN + ci) * g.Cout);
+          const float2 w01 = make_float2(wv.x, wv.y), w23 = make_float2(wv.z, wv.w);
 #pragma unroll
           for (int p = 0; p <= PW; ++p) {
             const float v = xv[(p + bb) * CIN + ci];
-            acc[0][p].x = fmaf(v, wv.x, acc[0][p].x); acc[0][p].y = fmaf(v, wv.y, acc[0][p].y);
-            acc[0][p].z = fmaf(v, wv.z, acc[0][p].z); acc[0][p].w = fmaf(v, wv.w, acc[0][p].w);
+            const float2 vv = make_float2(v, v);
+            acc[0][p][0] = __ffma2_rn(vv, w01, acc[0][p][0]);
+            acc[0][p][1] = __ffma2_rn(vv, w23, acc[0][p][1]);
           }
         }
         if (a >= 1) {
-          const float4 wv = *reinterpret_cast<const float4*>(&swt[(((a - 1) * KW + bb) * CIN + ci) * g.Cout + c4 * 4]);
+          const float4 wv = *reinterpret_cast<const float4*>(wq + (((a - 1) * KW + bb) * CIN + ci) * g.Cout);
+          const float2 w01 = make_float2(wv.x, wv.y), w23 = make_float2(wv.z, wv.w);
 #pragma unroll
           for (int p = 0; p <= PW; ++p) {
             const float v = xv[(p + bb) * CIN + ci];
-            acc[1][p].x = fmaf(v, wv.x, acc[1][p].x); acc[1][p].y = fmaf(v, wv.y, acc[1][p].y);
-            acc[1][p].z = fmaf(v, wv.z, acc[1][p].z); acc[1][p].w = fmaf(v, wv.w, acc[1][p].w);
+            const float2 vv = make_float2(v, v);
+            acc[1][p][0] = __ffma2_rn(vv, w01, acc[1][p][0]);
+            acc[1][p][1] = __ffma2_rn(vv, w23, acc[1][p][1]);
           }
         }
       }
   }
-  if (relu) {
+  float4 out[2][PW + 1];
 #pragma unroll
-    for (int r = 0; r < 2; ++r)
+  for (int r = 0; r < 2; ++r)
 #pragma unroll
-      for (int p = 0; p <= PW; ++p) {
-        float4& o = acc[r][p];
-        o.x = fmaxf(thr, o.x); o.y = fmaxf(thr, o.y); o.z = fmaxf(thr, o.z); o.w = fmaxf(thr, o.w);
-      }
-  }
+    for (int p = 0; p <= PW; ++p) {
+      float4 o = make_float4(acc[r][p][0].x, acc[r][p][0].y, acc[r][p][1].x, acc[r][p][1].y);
+      if (relu) { o.x = fmaxf(thr, o.x); o.y = fmaxf(thr, o.y); o.z = fmaxf(thr, o.z); o.w = fmaxf(thr, o.w); }
+      out[r][p] = o;
+    }
   // the conv activations: own row, and the last conv row from the last pool row
   const int rows_out = pr == OHp - 1 ? 2 : 1;
   for (int r = 0; r < rows_out; ++r) {
     float* yo = y + (((long long)b * g.OH + pr + r) * g.OW + ow0) * g.Cout + c4 * 4;
 #pragma unroll
     for (int p = 0; p < PW; ++p)
-      if (ow0 + p < g.OW) st4(yo + (long long)p * g.Cout, acc[r][p]);
+      if (ow0 + p < g.OW) st4(yo + p * g.Cout, out[r][p]);
   }
   float* po = pooled + (((long long)b * OHp + pr) * OWp + ow0) * g.Cout + c4 * 4;
 #pragma unroll
   for (int p = 0; p < PW; ++p) {
     if (ow0 + p >= OWp) break;
     float4 m;
-    m.x = fmaxf(fmaxf(acc[0][p].x, acc[0][p + 1].x), fmaxf(acc[1][p].x, acc[1][p + 1].x));
-    m.y = fmaxf(fmaxf(acc[0][p].y, acc[0][p + 1].y), fmaxf(acc[1][p].y, acc[1][p + 1].y));
-    m.z = fmaxf(fmaxf(acc[0][p].z, acc[0][p + 1].z), fmaxf(acc[1][p].z, acc[1][p + 1].z));
-    m.w = fmaxf(fmaxf(acc[0][p].w, acc[0][p + 1].w), fmaxf(acc[1][p].w, acc[1][p + 1].w));
-    st4(po + (long long)p * g.Cout, m);
+    m.x = fmaxf(fmaxf(out[0][p].x, out[0][p + 1].x), fmaxf(out[1][p].x, out[1][p + 1].x));
+    m.y = fmaxf(fmaxf(out[0][p].y, out[0][p + 1].y), fmaxf(out[1][p].y, out[1][p + 1].y));
+    m.z = fmaxf(fmaxf(out[0][p].z, out[0][p + 1].z), fmaxf(out[1][p].z, out[1][p + 1].z));
+    m.w = fmaxf(fmaxf(out[0][p].w, out[0][p + 1].w), fmaxf(out[1][p].w, out[1][p + 1].w));
+    st4(po + p * g.Cout, m);
   }
 }
 template <int KH, int KW, int CIN>
@@ -597,6 +616,7 @@ static void launch_smallk_pool(const float* x, const float* w, float* y, float* 
 }
 bool conv_smallk_pool_fwd(const float* x, const float* w, float* y, float* pooled, const ConvGeom& g, int relu, float thr, cudaStream_t s) {
   if (g.SH != 1 || g.SW != 1 || g.OH < 2 || g.OW < 2 || g.Cout % 4) return false;
+  if ((long long)g.N * g.OH * g.OW * g.Cout >= (1LL << 31)) return false;  // 32-bit thread index and in-row offsets in the kernel
   const int shape = g.KH * 100 + g.KW * 10 + g.Cin;
   if (shape == 331) { launch_smallk_pool<3, 3, 1>(x, w, y, pooled, g, relu, thr, s); return true; }
   if (shape == 333) { launch_smallk_pool<3, 3, 3>(x, w, y, pooled, g, relu, thr, s); return true; }
