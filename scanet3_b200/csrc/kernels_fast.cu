@@ -904,36 +904,46 @@ bool dense_skinny_fwd(const float* x, const float* w, float* z, int M, int N, in
 // groups' dW partials are summed in group order through shared memory.
 constexpr int kBwdK = 32, kBwdGroups = 4;  // 128-thread CTAs: ~1000 CTAs on cfg2 fill one wave at 7 CTAs/SM
 constexpr int kBwdRows = 128;  // rows of G staged per pass
-template <int NT, bool DGRAD, int UNR = 8>  // 8 rows of X in flight per thread: 18.9 -> 17.0 us on cfg2 (4: 64 regs as well)
+// KPT = k columns per thread: 2 (float2 loads of X / stores of dX, K even) shares every LDS of G between two columns, which
+// halves the instructions of the row loop (29 -> 15.5 per row and column)
+template <int NT, bool DGRAD, int KPT, int UNR = 8>
 __global__ void __launch_bounds__(kBwdK* kBwdGroups) dense_head_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gmat,
                                                                             const float* __restrict__ w, float* __restrict__ dw,
                                                                             float* __restrict__ dx, int Mtot, int K, int N,
                                                                             int rows_per_split, int early, int prewait) {
+  constexpr int KB = kBwdK * KPT;  // k columns of a CTA
   extern __shared__ __align__(128) float sm[];
   // blockIdx.y = row split: rows [mlo, mhi); its dW goes to slice blockIdx.y of `dw` (summed in split order afterwards)
   const int mlo = blockIdx.y * rows_per_split, M = min(Mtot, mlo + rows_per_split);
   dw += (size_t)blockIdx.y * K * N;
   float* sg = sm;                              // [kBwdRows][NT]
-  float* sw = sg + (size_t)kBwdRows * NT;      // [kBwdK][NT+1]
-  float* red = sw + kBwdK * (NT + 1);          // [kBwdGroups][kBwdK][NT+1]
+  float* sw = sg + (size_t)kBwdRows * NT;      // [KB][NT+1]
+  float* red = sw + KB * (NT + 1);             // [kBwdGroups][KB][NT+1]
   const int tid = threadIdx.x, kk = tid % kBwdK, rg = tid / kBwdK;
-  const int k0 = blockIdx.x * kBwdK, k = k0 + kk;
+  const int k0 = blockIdx.x * KB, k = k0 + kk * KPT;
+  const int kn = min(KB, K - k0) * N;  // the CTA's slab of W / dW is contiguous in memory
+  const unsigned div_n = (65536u + N - 1) / N;  // i / N for i < 2^16 / N * ... (kn <= 64 * 16): (i * div_n) >> 16
   // prewait (common.cuh: prewait_ok): the kernel before this one (normally the loss kernel) does not write weights, so the W
   // slab is staged before the dependency wait; otherwise after it
   if (!prewait) pdl_wait();
   if (DGRAD) {
-    const int kn = min(kBwdK, K - k0) * N;
-    for (int i = tid; i < kn; i += blockDim.x) sw[(i / N) * (NT + 1) + i % N] = __ldg(w + (size_t)k0 * N + i);
+    for (int i = tid; i < kn; i += blockDim.x) {
+      const int r = (int)(((unsigned)i * div_n) >> 16);
+      sw[r * (NT + 1) + (i - r * N)] = __ldg(w + (size_t)k0 * N + i);
+    }
   }
   if (prewait) pdl_wait();
   if (early) pdl_trigger();
   __syncthreads();
-  float2 acc2[NT / 2], wr2[NT / 2];  // packed fp32x2 FMAs (FFMA2)
+  float2 acc2[KPT][NT / 2], wr2[KPT][NT / 2];  // packed fp32x2 FMAs (FFMA2)
 #pragma unroll
-  for (int n = 0; n < NT / 2; ++n) {
-    acc2[n] = make_float2(0.f, 0.f);
-    wr2[n] = make_float2((DGRAD && 2 * n < N) ? sw[kk * (NT + 1) + 2 * n] : 0.f, (DGRAD && 2 * n + 1 < N) ? sw[kk * (NT + 1) + 2 * n + 1] : 0.f);
-  }
+  for (int j = 0; j < KPT; ++j)
+#pragma unroll
+    for (int n = 0; n < NT / 2; ++n) {
+      acc2[j][n] = make_float2(0.f, 0.f);
+      const float* swr = sw + (kk * KPT + j) * (NT + 1);
+      wr2[j][n] = make_float2((DGRAD && 2 * n < N) ? swr[2 * n] : 0.f, (DGRAD && 2 * n + 1 < N) ? swr[2 * n + 1] : 0.f);
+    }
   for (int mb = mlo; mb < M; mb += kBwdRows) {  // row chunks in order: the dW sum runs over rows in ascending chunks
     const int mc = min(kBwdRows, M - mb);
     __syncthreads();
@@ -944,40 +954,59 @@ __global__ void __launch_bounds__(kBwdK* kBwdGroups) dense_head_bwd_kernel(const
     __syncthreads();
     const int rows_per = (mc + kBwdGroups - 1) / kBwdGroups;
     const int m0 = rg * rows_per, m1 = min(mc, m0 + rows_per);
-    if (k < K) {
+    if (k < K) {  // K % KPT == 0 (launcher): the thread's KPT columns are all inside
+      const float* xp = x + (size_t)(mb + m0) * K + k;
+      float* dxp = dx + (size_t)(mb + m0) * K + k;
 #pragma unroll UNR
-      for (int m = m0; m < m1; ++m) {
-        const float xv = __ldg(x + (size_t)(mb + m) * K + k);
-        const float2 xx = make_float2(xv, xv);
-        float2 d2 = make_float2(0.f, 0.f);
+      for (int m = m0; m < m1; ++m, xp += K, dxp += K) {
+        float xv[KPT], dv[KPT];
+        if (KPT == 2) {
+          const float2 t = __ldg(reinterpret_cast<const float2*>(xp));
+          xv[0] = t.x; xv[KPT - 1] = t.y;
+        } else {
+          xv[0] = __ldg(xp);
+        }
+        float2 d2[KPT];
+#pragma unroll
+        for (int j = 0; j < KPT; ++j) d2[j] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int n4 = 0; n4 < NT; n4 += 4) {
           const float4 gv = *reinterpret_cast<const float4*>(sg + m * NT + n4);
           const float2 g0 = make_float2(gv.x, gv.y), g1 = make_float2(gv.z, gv.w);
-          acc2[n4 / 2] = __ffma2_rn(xx, g0, acc2[n4 / 2]);
-          acc2[n4 / 2 + 1] = __ffma2_rn(xx, g1, acc2[n4 / 2 + 1]);
-          if (DGRAD) {
-            d2 = __ffma2_rn(g0, wr2[n4 / 2], d2);
-            d2 = __ffma2_rn(g1, wr2[n4 / 2 + 1], d2);
+#pragma unroll
+          for (int j = 0; j < KPT; ++j) {
+            const float2 xx = make_float2(xv[j], xv[j]);
+            acc2[j][n4 / 2] = __ffma2_rn(xx, g0, acc2[j][n4 / 2]);
+            acc2[j][n4 / 2 + 1] = __ffma2_rn(xx, g1, acc2[j][n4 / 2 + 1]);
+            if (DGRAD) {
+              d2[j] = __ffma2_rn(g0, wr2[j][n4 / 2], d2[j]);
+              d2[j] = __ffma2_rn(g1, wr2[j][n4 / 2 + 1], d2[j]);
+            }
           }
         }
-        if (DGRAD) dx[(size_t)(mb + m) * K + k] = __fadd_rn(d2.x, d2.y);
+        if (DGRAD) {
+#pragma unroll
+          for (int j = 0; j < KPT; ++j) dv[j] = __fadd_rn(d2[j].x, d2[j].y);
+          if (KPT == 2) *reinterpret_cast<float2*>(dxp) = make_float2(dv[0], dv[KPT - 1]);
+          else *dxp = dv[0];
+        }
       }
     }
   }
 #pragma unroll
-  for (int n = 0; n < NT / 2; ++n) {
-    red[(rg * kBwdK + kk) * (NT + 1) + 2 * n] = acc2[n].x;
-    red[(rg * kBwdK + kk) * (NT + 1) + 2 * n + 1] = acc2[n].y;
-  }
+  for (int j = 0; j < KPT; ++j)
+#pragma unroll
+    for (int n = 0; n < NT / 2; ++n) {
+      red[(rg * KB + kk * KPT + j) * (NT + 1) + 2 * n] = acc2[j][n].x;
+      red[(rg * KB + kk * KPT + j) * (NT + 1) + 2 * n + 1] = acc2[j][n].y;
+    }
   __syncthreads();
-  // dW slab [kBwdK][N] is contiguous in memory: write it coalesced
-  const int kn = min(kBwdK, K - k0) * N;
+  // dW slab [KB][N] is contiguous in memory: write it coalesced
   for (int i = tid; i < kn; i += blockDim.x) {
-    const int r = i / N, n = i % N;
+    const int r = (int)(((unsigned)i * div_n) >> 16), n = i - r * N;
     float t = red[r * (NT + 1) + n];
 #pragma unroll
-    for (int g2 = 1; g2 < kBwdGroups; ++g2) t = __fadd_rn(t, red[(g2 * kBwdK + r) * (NT + 1) + n]);
+    for (int g2 = 1; g2 < kBwdGroups; ++g2) t = __fadd_rn(t, red[(g2 * KB + r) * (NT + 1) + n]);
     dw[(size_t)k0 * N + i] = t;
   }
 }
@@ -985,9 +1014,12 @@ bool dense_head_bwd(const float* x, const float* g, const float* w, float* dw, f
                     size_t ws_floats, cudaStream_t s) {
   if (N > kSkinnyN) return false;
   const int NT = N <= 12 ? 12 : 16;
-  const size_t smem = ((size_t)kBwdRows * NT + kBwdK * (NT + 1) + (size_t)kBwdGroups * kBwdK * (NT + 1)) * 4;
+  // two k columns per thread when X rows keep 8-byte alignment
+  const int kpt = (K % 2 == 0 && ((uintptr_t)x & 7) == 0 && (!dx || ((uintptr_t)dx & 7) == 0)) ? 2 : 1;
+  const int KB = kBwdK * kpt;
+  const size_t smem = ((size_t)kBwdRows * NT + KB * (NT + 1) + (size_t)kBwdGroups * KB * (NT + 1)) * 4;
   if (smem > 48 * 1024) return false;
-  const int kblocks = (K + kBwdK - 1) / kBwdK, thr = kBwdK * kBwdGroups;
+  const int kblocks = (K + KB - 1) / KB, thr = kBwdK * kBwdGroups;
   // enough CTAs for ~2 waves at 7 CTAs/SM: split the rows when K alone does not give them
   int splits = std::max(1, std::min({(2 * 7 * kNumSMs + kblocks - 1) / kblocks, (M + kBwdRows - 1) / kBwdRows,
                                      (int)(ws_floats / ((size_t)K * N))}));
@@ -996,13 +1028,16 @@ bool dense_head_bwd(const float* x, const float* g, const float* w, float* dw, f
   float* dwo = splits > 1 ? ws : dw;
   const dim3 grid(kblocks, splits);
   const int pw = prewait_ok();
+#define SB_HEAD_BWD(NT_, DG_, KP_) \
+  launch_k(dense_head_bwd_kernel<NT_, DG_, KP_>, grid, thr, smem, s, x, g, w, dwo, dx, M, K, N, rows_per_split, pdl_early_hint(), pw)
   if (NT == 12) {
-    if (dx) launch_k(dense_head_bwd_kernel<12, true>, grid, thr, smem, s, x, g, w, dwo, dx, M, K, N, rows_per_split, pdl_early_hint(), pw);
-    else launch_k(dense_head_bwd_kernel<12, false>, grid, thr, smem, s, x, g, w, dwo, dx, M, K, N, rows_per_split, pdl_early_hint(), pw);
+    if (kpt == 2) { if (dx) SB_HEAD_BWD(12, true, 2); else SB_HEAD_BWD(12, false, 2); }
+    else { if (dx) SB_HEAD_BWD(12, true, 1); else SB_HEAD_BWD(12, false, 1); }
   } else {
-    if (dx) launch_k(dense_head_bwd_kernel<16, true>, grid, thr, smem, s, x, g, w, dwo, dx, M, K, N, rows_per_split, pdl_early_hint(), pw);
-    else launch_k(dense_head_bwd_kernel<16, false>, grid, thr, smem, s, x, g, w, dwo, dx, M, K, N, rows_per_split, pdl_early_hint(), pw);
+    if (kpt == 2) { if (dx) SB_HEAD_BWD(16, true, 2); else SB_HEAD_BWD(16, false, 2); }
+    else { if (dx) SB_HEAD_BWD(16, true, 1); else SB_HEAD_BWD(16, false, 1); }
   }
+#undef SB_HEAD_BWD
   SB_LAUNCHED();
   if (splits > 1) partial_reduce(ws, dw, K * N, splits, s);
   return true;
