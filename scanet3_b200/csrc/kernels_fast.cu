@@ -69,11 +69,14 @@ __global__ void __launch_bounds__(256) pool22_fwd_strip_kernel(const float* __re
   const float* r0 = x + (((long long)b * g.H + oh) * g.W) * g.C + c4 * 4;
   const float* r1 = r0 + (long long)g.W * g.C;
   float* yo = y + (((long long)b * g.OH + oh) * g.OW) * g.C + c4 * 4;
-  float4 prev = max4(ld4(r0 + (long long)w0 * g.C), ld4(r1 + (long long)w0 * g.C));
+  r0 += w0 * g.C; r1 += w0 * g.C; yo += w0 * g.C;  // running pointers: one add per pointer and column
+  float4 prev = max4(ld4(r0), ld4(r1));
 #pragma unroll 4
   for (int w = w0; w < w1; ++w) {
-    const float4 next = max4(ld4(r0 + (long long)(w + 1) * g.C), ld4(r1 + (long long)(w + 1) * g.C));
-    st4(yo + (long long)w * g.C, max4(prev, next));
+    r0 += g.C; r1 += g.C;
+    const float4 next = max4(ld4(r0), ld4(r1));
+    st4(yo, max4(prev, next));
+    yo += g.C;
     prev = next;
   }
 }
@@ -81,7 +84,7 @@ static bool pool_is_22s1(const PoolGeom& g) {
   return g.KH == 2 && g.KW == 2 && g.SH == 1 && g.SW == 1 && g.PT == 0 && g.PL == 0 && g.OH == g.H - 1 && g.OW == g.W - 1;
 }
 void pool_max_fwd_v4(const float* x, float* y, const PoolGeom& g, cudaStream_t s) {
-  const long long nt22 = (long long)g.N * g.OH * kPoolSegs * (g.C / 4);
+  const long long nt22 = (long long)g.N * g.OH * kPoolSegs * (g.C / 4);  // 4 segments: 2, 3 and 6 measured 1.3-1.7 % slower on cfg2
   if (pool_is_22s1(g) && nt22 < (1LL << 31)) {  // the strip kernels split a 32-bit thread index
     const long long nt = nt22;
     const int seg_len = (g.OW + kPoolSegs - 1) / kPoolSegs;
@@ -167,8 +170,9 @@ struct PoolWgradFuse {
   int Hin, Win, PT, PL;
   int store_dx;
 };
+// (the 3x3x1 fused form is capped at 128 registers: 4 CTAs per SM and 3 row segments on LeNet's 26-column rows; 40 bytes of spills)
 template <bool RELU, int WG>
-__global__ void __launch_bounds__(128) pool22_bwd_strip_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+__global__ void __launch_bounds__(128, (WG == 331 ? 4 : 1)) pool22_bwd_strip_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                float* __restrict__ dx, PoolGeom g, float thr, int seg_len,
                                                                int segs, long long n_threads, PoolWgradFuse wf) {
   pdl_prologue_trigger();
@@ -344,7 +348,7 @@ bool pool_bwd_conv_wgrad(const float* x, const float* dy, float* dx, const PoolG
   if (cg.OH != g.H || cg.OW != g.W || cg.Cout != g.C || cg.N != g.N) return false;
   if (shape != 331 && shape != 333 && shape != 551) return false;
   int segs, seg_len;
-  pool22_segments(g, 3, &segs, &seg_len);
+  pool22_segments(g, shape == 331 ? 4 : 3, &segs, &seg_len);  // resident CTAs per SM of the instantiation
   const long long nt = (long long)g.N * g.H * segs * C4;
   if (nt >= (1LL << 31)) return false;  // the strip kernel splits a 32-bit thread index
   const int blocks = (int)((nt + 127) / 128);
@@ -906,8 +910,8 @@ constexpr int kBwdK = 32, kBwdGroups = 4;  // 128-thread CTAs: ~1000 CTAs on cfg
 constexpr int kBwdRows = 128;  // rows of G staged per pass
 // KPT = k columns per thread: 2 (float2 loads of X / stores of dX, K even) shares every LDS of G between two columns, which
 // halves the instructions of the row loop (29 -> 15.5 per row and column)
-template <int NT, bool DGRAD, int KPT, int UNR = 8>
-__global__ void __launch_bounds__(kBwdK* kBwdGroups) dense_head_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gmat,
+template <int NT, bool DGRAD, int KPT, int GR = kBwdGroups, int UNR = 8>
+__global__ void __launch_bounds__(kBwdK* GR) dense_head_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gmat,
                                                                             const float* __restrict__ w, float* __restrict__ dw,
                                                                             float* __restrict__ dx, int Mtot, int K, int N,
                                                                             int rows_per_split, int early, int prewait) {
@@ -918,7 +922,7 @@ __global__ void __launch_bounds__(kBwdK* kBwdGroups) dense_head_bwd_kernel(const
   dw += (size_t)blockIdx.y * K * N;
   float* sg = sm;                              // [kBwdRows][NT]
   float* sw = sg + (size_t)kBwdRows * NT;      // [KB][NT+1]
-  float* red = sw + KB * (NT + 1);             // [kBwdGroups][KB][NT+1]
+  float* red = sw + KB * (NT + 1);             // [GR][KB][NT+1]
   const int tid = threadIdx.x, kk = tid % kBwdK, rg = tid / kBwdK;
   const int k0 = blockIdx.x * KB, k = k0 + kk * KPT;
   const int kn = min(KB, K - k0) * N;  // the CTA's slab of W / dW is contiguous in memory
@@ -952,7 +956,7 @@ __global__ void __launch_bounds__(kBwdK* kBwdGroups) dense_head_bwd_kernel(const
       sg[i] = n < N ? __ldg(gmat + (size_t)(mb + m) * N + n) : 0.f;
     }
     __syncthreads();
-    const int rows_per = (mc + kBwdGroups - 1) / kBwdGroups;
+    const int rows_per = (mc + GR - 1) / GR;
     const int m0 = rg * rows_per, m1 = min(mc, m0 + rows_per);
     if (k < K) {  // K % KPT == 0 (launcher): the thread's KPT columns are all inside
       const float* xp = x + (size_t)(mb + m0) * K + k;
@@ -1006,7 +1010,7 @@ __global__ void __launch_bounds__(kBwdK* kBwdGroups) dense_head_bwd_kernel(const
     const int r = (int)(((unsigned)i * div_n) >> 16), n = i - r * N;
     float t = red[r * (NT + 1) + n];
 #pragma unroll
-    for (int g2 = 1; g2 < kBwdGroups; ++g2) t = __fadd_rn(t, red[(g2 * KB + r) * (NT + 1) + n]);
+    for (int g2 = 1; g2 < GR; ++g2) t = __fadd_rn(t, red[(g2 * KB + r) * (NT + 1) + n]);
     dw[(size_t)k0 * N + i] = t;
   }
 }
@@ -1017,9 +1021,10 @@ bool dense_head_bwd(const float* x, const float* g, const float* w, float* dw, f
   // two k columns per thread when X rows keep 8-byte alignment
   const int kpt = (K % 2 == 0 && ((uintptr_t)x & 7) == 0 && (!dx || ((uintptr_t)dx & 7) == 0)) ? 2 : 1;
   const int KB = kBwdK * kpt;
-  const size_t smem = ((size_t)kBwdRows * NT + KB * (NT + 1) + (size_t)kBwdGroups * KB * (NT + 1)) * 4;
+  const int GRr = kBwdGroups;  // (8 row groups = 256-thread CTAs need <= 64 registers to keep the 484 CTAs of cfg2 in one wave: not taken)
+  const size_t smem = ((size_t)kBwdRows * NT + KB * (NT + 1) + (size_t)GRr * KB * (NT + 1)) * 4;
   if (smem > 48 * 1024) return false;
-  const int kblocks = (K + KB - 1) / KB, thr = kBwdK * kBwdGroups;
+  const int kblocks = (K + KB - 1) / KB, thr = kBwdK * GRr;
   // enough CTAs for ~2 waves at 7 CTAs/SM: split the rows when K alone does not give them
   int splits = std::max(1, std::min({(2 * 7 * kNumSMs + kblocks - 1) / kblocks, (M + kBwdRows - 1) / kBwdRows,
                                      (int)(ws_floats / ((size_t)K * N))}));
