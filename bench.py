@@ -393,6 +393,16 @@ def run_ours(args):
         roofline["algorithmic_per_launch"] = (top["flops"] if tensor_bound else top["bytes"]) / n_launch
         roofline["traffic_note"] = ("dram bytes per launch from profiles/r1_traffic.json (one ncu --set full capture, cold L2)"
                                     if traffic else "no ncu capture of this kernel class")
+        # whole step against the same HBM figure: the algorithmic bytes of every kernel class of one step (what the engine
+        # attributes to each launch: logical inputs read once + outputs written once) over the graph-replayed step time
+        try:
+            step_bytes = sum(float(r["bytes"]) for r in prof_rows) / max(psteps, 1)
+            step_s = ms / args.steps / 1000.0
+            roofline["whole_step"] = {"algorithmic_bytes": step_bytes, "achieved": step_bytes / step_s / 1e9, "unit": "GB/s",
+                                      "frac": step_bytes / step_s / 1e9 / hbm,
+                                      "note": "sum of the kernel classes' algorithmic bytes per step / ms_per_step of the timed region"}
+        except Exception:
+            pass
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config == "cfg2":
