@@ -42,6 +42,38 @@ __global__ void step_prologue_kernel(StepState* st, const V* __restrict__ ds_x, 
   }
 }
 
+// EXPERIMENT for round 2 (SB_X_PROLOGUE_V2=1; never measured — see profiles/r1_notes.md "Open leads"): the two double-precision
+// pow() calls, the longest dependent chain of the prologue, start first and run on lane 0 of two different warps of the last CTA.
+// Only those two threads read st->iter; it is advanced after a CTA-wide barrier (no warp-level barrier inside the divergent code).
+template <typename V>
+__global__ void step_prologue2_kernel(StepState* st, const V* __restrict__ ds_x, const V* __restrict__ ds_y,
+                                      V* __restrict__ bx, V* __restrict__ by, long long x4, long long y4,
+                                      float beta1, float beta2, int batch_from_state, float* __restrict__ prev_loss_slot, int early) {
+  pdl_prologue_trigger_if(early);
+  const long long b = batch_from_state ? st->batch_idx : 0;
+  const bool last = blockIdx.x == gridDim.x - 1;
+  long long t = 0;
+  if (last && threadIdx.x == 0) {
+    t = st->iter + 1;
+    if (prev_loss_slot) *prev_loss_slot = st->loss;
+    st->bc1 = __fsub_rn(1.0f, (float)pow((double)beta1, (double)(float)t));
+  } else if (last && threadIdx.x == 32) {
+    const long long t2 = st->iter + 1;
+    st->bc2 = __fsub_rn(1.0f, (float)pow((double)beta2, (double)(float)t2));
+  }
+  if (ds_x != nullptr) {
+    const V* sx = ds_x + b * x4;
+    const V* sy = ds_y + b * y4;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < x4 + y4; i += stride) {
+      if (i < x4) bx[i] = sx[i];
+      else by[i - x4] = sy[i - x4];
+    }
+  }
+  __syncthreads();  // thread 32 has read st->iter
+  if (last && threadIdx.x == 0) st->iter = t;
+}
+
 void step_prologue(StepState* st, const float* ds_x, const float* ds_y, float* bx, float* by, long long x_per_batch,
                    long long y_per_batch, float beta1, float beta2, int batch_from_state, cudaStream_t s, float* prev_loss_slot) {
   // 128-bit copies when every batch of the shard starts 16-byte aligned, scalar copies otherwise
@@ -50,6 +82,13 @@ void step_prologue(StepState* st, const float* ds_x, const float* ds_y, float* b
   int blocks = 1;
   if (ds_x) blocks = (int)fmin((double)ceil_div(xn + yn, 256), (double)kNumSMs * 8);
   if (blocks < 1) blocks = 1;
+  static const bool v2 = [] { const char* v = getenv("SB_X_PROLOGUE_V2"); return v && v[0] == '1'; }();
+  if (v2 && vec) {
+    launch_k(step_prologue2_kernel<float4>, blocks, 256, 0, s, st, (const float4*)ds_x, (const float4*)ds_y, (float4*)bx,
+                                                         (float4*)by, xn, yn, beta1, beta2, batch_from_state, prev_loss_slot, pdl_early_hint());
+    SB_LAUNCHED();
+    return;
+  }
   if (vec)
     launch_k(step_prologue_kernel<float4>, blocks, 256, 0, s, st, (const float4*)ds_x, (const float4*)ds_y, (float4*)bx,
                                                         (float4*)by, xn, yn, beta1, beta2, batch_from_state, prev_loss_slot, pdl_early_hint());
