@@ -102,7 +102,7 @@ Softmax = Activation(N.ACT_SOFTMAX, "Softmax")
 
 
 def ReLU(threshold: float = 0.0):
-    return Activation(N.ACT_RELU, "ReLU" if threshold == 0 else f"ReLU({threshold})", float(threshold))
+    return Activation(N.ACT_RELU, f"ReLU({float(threshold)})", float(threshold))  # case class toString: ReLU(0.0)
 
 
 # ---- losses (models/Loss.scala:10-58) -----------------------------------------------------------------------
@@ -159,11 +159,106 @@ def _check_reg(reg):
 
 
 # ---- layers --------------------------------------------------------------------------------------------------
+# ---- model description: `Model.describe` (models/Model.scala:62-81), printed by `Optimizer.run` (Optimizer.scala:65) ----
+def _power(shape) -> int:
+    n = 1
+    for d in shape:
+        n *= int(d)
+    return n
+
+
+def _shape_str(shape) -> str:
+    """core/Shape.scala toString: `(3, 3, 1, 32)`, `(10)`, `()`"""
+    return "(" + ", ".join(str(int(d)) for d in shape) + ")"
+
+
+def _group_concat(items) -> str:
+    """layer/LayerInfo.scala:10-37: a list made of one repeated group prints as `[group]xN`"""
+    items = list(items)
+    elements, times, size = items, 1, 1
+    while len(items) >= size / 2:
+        if len(items) % size == 0 and len({tuple(items[i:i + size]) for i in range(0, len(items), size)}) == 1:
+            elements, times = items[:size], len(items) // size
+            break
+        size += 1
+    value = ", ".join(str(e) for e in elements)
+    return f"[{value}]x{times}" if times > 1 else value
+
+
+def _format_size(nbytes: int) -> str:
+    """utils/Bytes.scala:4-8"""
+    if nbytes < 1024:
+        return f"{nbytes} B"
+    z = (nbytes.bit_length() - 1) // 10
+    return "%.1f %sB" % (nbytes / float(1 << (z * 10)), " KMGTPE"[z])
+
+
+def _tabulate(table) -> str:
+    """utils/Tabulator.scala:5-30 with a header row"""
+    widths = [max(len(str(row[c])) for row in table) for c in range(len(table[0]))]
+    sep = "+" + "+".join("-" * w for w in widths) + "+"
+    rows = ["|" + "|".join(("" if w == 0 else str(cell).ljust(w)) for cell, w in zip(row, widths)) + "|" for row in table]
+    return "\n".join([sep, rows[0], sep] + rows[1:] + [sep])
+
+
+def _window_out(size: int, window: int, stride: int, padding) -> int:
+    """output extent of a conv / pool axis (math/nn/AllKernels.scala:12-103); `padding` = Valid | Same | (before, after)"""
+    if padding == Same:
+        return -(-size // stride)
+    before, after = (0, 0) if padding == Valid else padding
+    return (size + before + after - window) // stride + 1
+
+
+@dataclass(frozen=True)
+class LayerInfo:
+    """layer/LayerInfo.scala:8-50"""
+    name: str
+    weights: Tuple[Tuple[int, ...], ...]
+    state: Tuple[Tuple[int, ...], ...]
+    output: Tuple[int, ...]
+
+    @property
+    def weightsTotal(self) -> int:
+        return sum(_power(w) for w in self.weights)
+
+    @property
+    def stateTotal(self) -> int:
+        return sum(_power(w) for w in self.state)
+
+    def toRow(self) -> List[str]:
+        return [self.name, _group_concat(_shape_str(w) for w in self.weights), _group_concat(_power(w) for w in self.weights),
+                _group_concat(_power(w) for w in self.state), "(" + ",".join(["_"] + [str(d) for d in self.output[1:]]) + ")"]
+
+
 class Layer:
     """`layer/Layer.scala:24-26`: `>>` composes; compositions flatten (`Composed.scala:89-99`)."""
 
     def leaves(self) -> List["Layer"]:
         return [self]
+
+    # -- shapes and description (host logic only; the engine plans the same shapes in C++) --
+    def outputShape(self, input: Sequence[int]) -> Tuple[int, ...]:
+        return tuple(input)
+
+    def paramDefs(self, input: Sequence[int]) -> List[Tuple[Tuple[int, ...], bool]]:
+        """(shape, trainable) of the layer's parameters in the order of the reference's `params(input)`"""
+        return []
+
+    def info(self, input: Sequence[int]) -> List["LayerInfo"]:
+        """models/Model.scala:62-69: non-trainable parameters are listed as state"""
+        defs = self.paramDefs(input)
+        return [LayerInfo(repr(self), tuple(sh for sh, tr in defs if tr), tuple(sh for sh, tr in defs if not tr),
+                          self.outputShape(input))]
+
+    def describe(self, input: Sequence[int], itemsize: int = 4) -> str:
+        """models/Model.scala:71-81 (`itemsize` = bytes of the element type: 4 for Float).  Rows of Dense / Bias / Activate /
+        Flatten / Conv2D / Pool2D layers are pinned by the reference's golden table (models/CNNSpec.scala:39-63); BatchNorm and RNN
+        rows follow the same rules but the reference has no golden for them (an LSTM's 12 parameters live in a hash map there)."""
+        infos = self.info(input)
+        rows = [LayerInfo("Input", (), (), tuple(input)).toRow()] + [i.toRow() for i in infos]
+        table = _tabulate([["name", "weights", "weights params", "state params", "output"]] + rows)
+        wt, st = sum(i.weightsTotal for i in infos), sum(i.stateTotal for i in infos)
+        return f"{table}\nTotal weight params: {wt} ({_format_size(wt * itemsize)}), state params: {st} ({_format_size(st * itemsize)})"
 
     def __rshift__(self, other: "Layer") -> "Layer":
         return Composed(self.leaves() + other.leaves())
@@ -197,6 +292,25 @@ class Composed(Layer):
     def leaves(self):
         return list(self.layers)
 
+    def outputShape(self, input):
+        for l in self.layers:
+            input = l.outputShape(input)
+        return tuple(input)
+
+    def paramDefs(self, input):
+        out = []
+        for l in self.layers:
+            out += l.paramDefs(input)
+            input = l.outputShape(input)
+        return out
+
+    def info(self, input):  # layer/Composed.scala:71-77
+        out = []
+        for l in self.layers:
+            out += l.info(input)
+            input = l.outputShape(input)
+        return out
+
     def __repr__(self):
         return " >> ".join(repr(l) for l in self.layers)
 
@@ -210,6 +324,12 @@ class _DenseKernel(Layer):
                        reg_lambda=self.reg.lam)
         d.init[0] = self.initializer.to_native()
         return d
+
+    def outputShape(self, input):  # layer/Dense.scala:66
+        return (input[0], self.outputs)
+
+    def paramDefs(self, input):  # layer/Dense.scala:50-55
+        return [((input[1], self.outputs), bool(self.trainable))]
 
     def __repr__(self):
         return f"Dense({self.outputs})"
@@ -225,6 +345,9 @@ class Bias(Layer):
                        reg_lambda=self.reg.lam)
         d.init[2] = self.initializer.to_native()
         return d
+
+    def paramDefs(self, input):  # layer/Bias.scala:27-30
+        return [((self.features,), bool(self.trainable))]
 
     def __repr__(self):
         return f"Bias({self.features})"
@@ -244,6 +367,9 @@ class Activate(Layer):
 class _Flatten(Layer):
     def to_native(self):
         return self._desc(N.LAYER_FLATTEN)
+
+    def outputShape(self, input):  # layer/Flatten.scala:20
+        return (input[0], _power(input[1:]))
 
     def __repr__(self):
         return "Flatten"
@@ -307,6 +433,21 @@ class _Conv2DKernel(Layer):
         d.init[0] = self.initializer.to_native()
         return d
 
+    def _pads(self):
+        if isinstance(self.padding, Explicit):
+            return self.padding.height, self.padding.width
+        return self.padding, self.padding
+
+    def outputShape(self, input):  # layer/Conv2D.scala:109-122
+        if len(input) != 4:
+            raise ValueError(f"requirement failed: Conv2D input should have a shape (NHWC) or (NCHW) but was {_shape_str(input)}")
+        ph, pw = self._pads()
+        return (input[0], _window_out(input[1], self.kernel[0], self.strides[0], ph),
+                _window_out(input[2], self.kernel[1], self.strides[1], pw), self.filters)
+
+    def paramDefs(self, input):  # layer/Conv2D.scala:84-91: HWIO
+        return [((self.kernel[0], self.kernel[1], input[3], self.filters), bool(self.trainable))]
+
     def __repr__(self):
         return f"Conv2D({self.filters},({self.kernel[0]},{self.kernel[1]}),({self.strides[0]},{self.strides[1]}),{self.padding},NHWC)"
 
@@ -344,6 +485,12 @@ class Pool2D(Layer):
                           pool_reduce=N.POOL_AVG if self.reduce == "Avg" else N.POOL_MAX,
                           pool_honor_reduce=int(self.honorReduce))
 
+    def outputShape(self, input):  # layer/Pool2D.scala:44-56
+        if len(input) != 4:
+            raise ValueError(f"requirement failed: Pool2D input should have a shape (NHWC) or (NCHW) but was {_shape_str(input)}")
+        return (input[0], _window_out(input[1], self.window[0], self.strides[0], self.padding),
+                _window_out(input[2], self.window[1], self.strides[1], self.padding), input[3])
+
     def __repr__(self):
         return f"Pool2D(({self.window[0]},{self.window[1]}),({self.strides[0]},{self.strides[1]}),{self.padding},NHWC,{self.reduce})"
 
@@ -367,6 +514,10 @@ class BatchNorm(Layer):
         for i, init in enumerate(self.inits):
             d.init[i] = init.to_native()
         return d
+
+    def paramDefs(self, input):  # layer/BatchNorm.scala:78-95: beta, gamma, moving_mean, moving_variance; axes [-1] keep the last dim
+        shape = tuple([1] * (len(input) - 1) + [input[-1]])
+        return [(shape, bool(self.trainable)), (shape, bool(self.trainable)), (shape, False), (shape, False)]
 
     def __repr__(self):
         return "BatchNorm(List(-1))"
@@ -395,6 +546,18 @@ class RNN(Layer):
         for i, init in enumerate((c.kernelInitializer, c.recurrentInitializer, c.biasInitializer, c.biasForgetInitializer)):
             d.init[i] = init.to_native()
         return d
+
+    def outputShape(self, input):  # layer/RNN.scala:80-86
+        if len(input) != 3:
+            raise ValueError("requirement failed: RNN requires input to have Shape(batch, time, features)")
+        return (input[0], input[1], self.cell.units) if self.returnSequence else (input[0], self.cell.units)
+
+    def paramDefs(self, input):  # layer/RNN.scala:32-39, 182-188, 293-305 (weights first here; the reference's map order is unpinned)
+        c, f, u = self.cell, input[2], self.cell.units
+        per_cell = [((f, u), True), ((u, u), True)] + ([((u,), True)] if c.bias else [])
+        weights = per_cell * (4 if isinstance(c, LSTMCell) else 1)
+        n_state = (2 if isinstance(c, LSTMCell) else 1) if self.stateful else 0
+        return weights + [((input[0], u), False)] * n_state
 
     def __repr__(self):
         return f"RNN({self.cell!r})"

@@ -220,3 +220,72 @@ def test_wire_decode_rejects_malformed_records():
     bad = bytearray(rec); bad[27] = 20                   # payload size disagrees with the shape
     with pytest.raises(N.IllegalArgument):
         S.wire_decode(bytes(bad))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Model.describe (models/Model.scala:62-81), printed by Optimizer.run (optimizers/Optimizer.scala:65)
+# ---------------------------------------------------------------------------------------------------------------
+CNN_DESCRIPTION = """\
++----------------------------------+--------------+--------------+------------+------------+
+|name                              |weights       |weights params|state params|output      |
++----------------------------------+--------------+--------------+------------+------------+
+|Input                             |              |              |            |(_,24,24,1) |
+|Conv2D(32,(3,3),(1,1),Valid,NHWC) |(3, 3, 1, 32) |288           |            |(_,22,22,32)|
+|ReLU(0.0)                         |              |              |            |(_,22,22,32)|
+|Pool2D((2,2),(1,1),Valid,NHWC,Max)|              |              |            |(_,21,21,32)|
+|Conv2D(64,(3,3),(1,1),Valid,NHWC) |(3, 3, 32, 64)|18432         |            |(_,19,19,64)|
+|ReLU(0.0)                         |              |              |            |(_,19,19,64)|
+|Pool2D((2,2),(1,1),Valid,NHWC,Max)|              |              |            |(_,18,18,64)|
+|Flatten                           |              |              |            |(_,20736)   |
+|Dense(10)                         |(20736, 10)   |207360        |            |(_,10)      |
+|Bias(10)                          |(10)          |10            |            |(_,10)      |
+|Softmax                           |              |              |            |(_,10)      |
++----------------------------------+--------------+--------------+------------+------------+
+Total weight params: 226090 (883.2 KB), state params: 0 (0 B)"""
+
+
+def test_model_description_matches_the_reference_golden_table():
+    # models/CNNSpec.scala:39-63 ("be described"), character for character
+    model = (S.Conv2D(32, activation=S.ReLU()) >> S.Pool2D() >> S.Conv2D(64, activation=S.ReLU()) >> S.Pool2D()
+             >> S.Flatten >> S.Dense(10, S.Softmax))
+    assert model.describe((1, 24, 24, 1)) == CNN_DESCRIPTION
+
+
+def test_description_helpers_follow_the_reference_rules():
+    from scanet3_b200 import dsl
+    assert dsl._format_size(0) == "0 B" and dsl._format_size(1023) == "1023 B"  # utils/Bytes.scala:4-8
+    assert dsl._format_size(1024) == "1.0 KB" and dsl._format_size(904360) == "883.2 KB" and dsl._format_size(5 << 20) == "5.0 MB"
+    assert dsl._group_concat([]) == "" and dsl._group_concat(["a"]) == "a" and dsl._group_concat(["a", "b"]) == "a, b"
+    assert dsl._group_concat(["a", "a"]) == "[a]x2" and dsl._group_concat(["a", "b"] * 3) == "[a, b]x3"  # LayerInfo.scala:10-37
+    assert dsl._shape_str(()) == "()" and dsl._shape_str((10,)) == "(10)" and dsl._shape_str((3, 3, 1, 32)) == "(3, 3, 1, 32)"
+
+
+def _all_test_models():
+    import test_gpu_lstm as TL
+    import test_gpu_tf32 as TT
+    for name, (spec, in_shape, batch) in SPECS.items():
+        yield name, spec, (batch,) + tuple(in_shape), (1 if name == "cfg3_lstm" else 10)
+    for name, spec, batch, in_shape in TT.CONV_STACKS:
+        yield name, spec, (batch,) + tuple(in_shape), 10
+    for name, spec, batch, nin in TT.DENSE_STACKS:
+        yield name, spec, (batch, nin), 10
+    for name, (spec, t, f, batch) in list(TL.SEQ_MODELS.items()) + list(TL.RNN_MODELS.items()):
+        yield name, spec, (batch, t, f), 1
+
+
+def test_described_shapes_and_counts_agree_with_the_engine_plan_for_every_test_model():
+    """the Python shape rules behind `describe` against the C++ planner (plan-only engines): per-model weight / state element
+    counts and the output shape, for the BASELINE configs and every model the GPU tests train"""
+    n = 0
+    for name, spec, full_in, out_dim in _all_test_models():
+        _, sm = build_models(spec)
+        infos = sm.info(full_in)
+        e = S.Engine(sm, S.MeanSquaredError, S.SGD(), full_in[0], full_in[1:], (out_dim,), device=-1)
+        plan = [i for i in e.params.values() if i.role != N.ROLE_OPT]
+        assert sum(i.weightsTotal for i in infos) == sum(i.numel for i in plan if i.role == N.ROLE_WEIGHT), name
+        assert sum(i.stateTotal for i in infos) == sum(i.numel for i in plan if i.role != N.ROLE_WEIGHT), name
+        assert tuple(infos[-1].output) == tuple(e.output_shape) == tuple(sm.outputShape(full_in)), name
+        assert sm.describe(full_in).count("\n") == len(infos) + 5, name
+        e.close()
+        n += 1
+    assert n >= 25
