@@ -341,10 +341,11 @@ class Optimizer:
         if len(devices) != k:
             raise ValueError(f"{k} partitions need {k} devices, got {devices}")
         in_shape, lab_shape = ds.shapes
-        try:  # Optimizer.scala:65 (`println(s"Training model:\n${model.describe[A](batchSize +: shapes._1)}")`)
-            print(f"Training model:\n{c.model.describe((c.batchSize,) + tuple(in_shape))}")
-        except Exception as ex:  # a description must never stop a training run
-            print(f"Training model: {c.model!r} (no description: {ex})")
+        if not c.quiet:
+            try:  # Optimizer.scala:65 (`println(s"Training model:\n${model.describe[A](batchSize +: shapes._1)}")`)
+                print(f"Training model:\n{c.model.describe((c.batchSize,) + tuple(in_shape))}")
+            except Exception as ex:  # a description must never stop a training run
+                print(f"Training model: {c.model!r} (no description: {ex})")
         engines = [Engine(c.model, c.loss, c.alg, c.batchSize, in_shape, lab_shape, device=d, precision=c.precision,
                           use_graph=c.use_graph, minimizing=c.minimizing) for d in devices]
         group = Group(engines, c.avg_mode, collective=c.collective) if k > 1 else None
