@@ -37,6 +37,8 @@ final case class B200Optimizer[A: Floating](
   private val k = shards.size
 
   def run(): TrainedModel[A] = {
+    // Optimizer.scala:65 — the reference's own `Model.describe` still runs on the JVM side
+    println(s"Training model:\n${model.describe[A](batchSize +: shards.head._1.shape.tail)}")
     val pool = Executors.newFixedThreadPool(k) // one JVM thread per GPU, like one Spark task per partition
     implicit val ec: ExecutionContext = ExecutionContext.fromExecutor(pool)
     val session = Arena.ofShared()
