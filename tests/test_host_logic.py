@@ -258,6 +258,9 @@ def test_description_helpers_follow_the_reference_rules():
     assert dsl._group_concat([]) == "" and dsl._group_concat(["a"]) == "a" and dsl._group_concat(["a", "b"]) == "a, b"
     assert dsl._group_concat(["a", "a"]) == "[a]x2" and dsl._group_concat(["a", "b"] * 3) == "[a, b]x3"  # LayerInfo.scala:10-37
     assert dsl._shape_str(()) == "()" and dsl._shape_str((10,)) == "(10)" and dsl._shape_str((3, 3, 1, 32)) == "(3, 3, 1, 32)"
+    # utils/TabulatorSpec.scala:10-23
+    assert dsl._tabulate([["name", "age"], ["Pavlo", "31"], ["Yurii Dawg", "28"]]) == (
+        "+----------+---+\n|name      |age|\n+----------+---+\n|Pavlo     |31 |\n|Yurii Dawg|28 |\n+----------+---+")
 
 
 def _all_test_models():

@@ -388,6 +388,21 @@ def test_adam_logistic_regression(fixtures_dir):  # AdamSpec.scala:44-64
     assert np.array_equal(np.round(probe), [[0], [1]])
 
 
+@pytest.mark.parametrize("seed", [1, 2])
+def test_mlp_minimises_logistic_regression(fixtures_dir, seed):  # models/ANNSpec.scala:21-39 (unseeded GlorotUniform there)
+    d = np.loadtxt(os.path.join(fixtures_dir, "logistic_regression_1.scv"), delimiter=",", dtype=np.float64)
+    x = (d[:, :2].astype(f32) / f32(100)).astype(f32)
+    y = d[:, 2:].astype(f32)
+    model = (O.Dense(4, O.Sigmoid, kernel_initializer=O.GlorotUniform(seed))
+             >> O.Dense(1, O.Sigmoid, kernel_initializer=O.GlorotUniform(seed + 10)))
+    mp, _, _ = O.run_training(model, O.BinaryCrossentropy, O.Adam(0.2), x, y, batch=100, epochs=55)
+    assert float(O.eval_loss(O.LossModel(model, O.BinaryCrossentropy), x, y, mp)) <= 0.5
+    pred, _, _ = O.model_forward(model, x, mp)
+    assert np.mean((np.round(pred) == y).astype(np.float64)) >= 0.89
+    probe, _, _ = O.model_forward(model, np.array([[0.3462, 0.7802], [0.6018, 0.8630]], f32), mp)
+    assert np.array_equal(np.round(probe), [[0], [1]])
+
+
 def test_sgd_minimises_x_squared():  # SGDSpec.scala:16-31 with models/Math.scala:11-25
     w = np.array(5.0, f32)
     alg = O.SGD(rate=0.1)
