@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(256) conv_smallk_pool_fwd_kernel(const float* 
   // single-channel rows without left padding whose pitch keeps 16-byte alignment: the PW + KW <= 8 inputs of a row are two
   // float4 loads (the second only when it stays inside the row) instead of PW + KW bounds-checked scalar loads
   const bool vec_rows = CIN == 1 && PW + KW <= 8 && g.PL == 0 && (g.W & 3) == 0 && (PW & 3) == 0 && ((uintptr_t)x & 15) == 0;
-  // (ow0 and W are multiples of 4: the first quad is always inside the row, the second entirely inside or entirely outside)
+  // (ow0 and W are multiples of 4: each of the two quads is entirely inside or entirely outside the row)
   const float* wq = swt + c4 * 4;
 #pragma unroll
   for (int a = 0; a <= KH; ++a) {  // input row pr + a - PT feeds conv row pr (filter row a) and conv row pr+1 (filter row a-1)
@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(256) conv_smallk_pool_fwd_kernel(const float* 
     float xv[(PW + KW) * CIN > 8 ? (PW + KW) * CIN : 8];
     if (vec_rows) {
       const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 lo = row_ok ? ld4(xr + ow0) : z4;  // ow0 < OW <= W: always inside the row
+      const float4 lo = (row_ok && ow0 + 4 <= g.W) ? ld4(xr + ow0) : z4;  // outside only with explicit right padding (OW > W)
       const float4 hi = (row_ok && ow0 + 8 <= g.W) ? ld4(xr + ow0 + 4) : z4;
       xv[0] = lo.x; xv[1] = lo.y; xv[2] = lo.z; xv[3] = lo.w; xv[4] = hi.x; xv[5] = hi.y; xv[6] = hi.z; xv[7] = hi.w;
     } else {

@@ -100,14 +100,15 @@ def test_32_bit_thread_index_split_matches_the_64_bit_one():
 
 def test_vector_row_loads_of_the_fused_conv_cover_exactly_the_in_row_columns():
     # conv_smallk_pool_fwd_kernel, single-channel rows with W % 4 == 0, no left padding: a thread of segment ow0 = 4*seg needs the
-    # PW + KW - 1 = 7 inputs ow0 .. ow0+6 (zero beyond the row); it loads quad ow0..ow0+3 always and quad ow0+4..ow0+7 iff
-    # ow0 + 8 <= W.  The quads are never split by the row end, so this equals the bounds-checked scalar loads.
+    # PW + KW - 1 = 7 inputs ow0 .. ow0+6 (zero beyond the row); it loads quad ow0..ow0+3 iff ow0 + 4 <= W and quad ow0+4..ow0+7
+    # iff ow0 + 8 <= W.  The quads are never split by the row end, so this equals the bounds-checked scalar loads -- also with
+    # explicit right padding, where output columns (and whole segments) lie beyond the input row.
     for W in range(4, 132, 4):
-        OW = W - 2  # 3x3 VALID
-        for seg in range((OW + 3) // 4):
-            ow0 = 4 * seg
-            scalar = [(ow0 + q) if ow0 + q < W else None for q in range(7)]
-            lo = [ow0 + j for j in range(4)]
-            hi = [ow0 + 4 + j for j in range(4)] if ow0 + 8 <= W else [None] * 4
-            assert all(c < W for c in lo)
-            assert (lo + hi)[:7] == scalar, (W, seg)
+        for pad_right in (0, 1, 3, 6):
+            OW = W + pad_right - 2  # 3x3, stride 1
+            for seg in range((OW + 3) // 4):
+                ow0 = 4 * seg
+                scalar = [(ow0 + q) if ow0 + q < W else None for q in range(7)]
+                lo = [ow0 + j for j in range(4)] if ow0 + 4 <= W else [None] * 4
+                hi = [ow0 + 4 + j for j in range(4)] if ow0 + 8 <= W else [None] * 4
+                assert (lo + hi)[:7] == scalar, (W, pad_right, seg)
