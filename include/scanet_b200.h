@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SB_ABI_VERSION 3
+#define SB_ABI_VERSION 4
 
 typedef enum {
   SB_OK = 0,
@@ -42,7 +42,8 @@ typedef enum {
   SB_ERR_UNSUPPORTED = 2, /* a reference feature outside the accelerated path (no CPU fallback)          */
   SB_ERR_CUDA = 3,        /* reference: TF_Status -> RuntimeException (native/package.scala:6-9)          */
   SB_ERR_NCCL = 4,
-  SB_ERR_STATE = 5        /* call order violated (e.g. train before params are initialised)               */
+  SB_ERR_STATE = 5,       /* call order violated (e.g. train before params are initialised)               */
+  SB_ERR_TIMEOUT = 6      /* a peer rank never reached the device-synchronised averaging barrier           */
 } sb_status;
 
 /* ---- model descriptor: the flattened leaf-layer list of `Composed` (layer/Composed.scala:89-99) ---- */
@@ -219,13 +220,22 @@ int sb_checkpoint_load(sb_engine* e, const char* file, int64_t* global_iter, int
 /* shard resident in HBM (the partition iterator + TensorIterator, Iterators.scala:39-83).
  * x: [n_rows, prod(input_dims)], y: [n_rows, prod(label_dims)]; host memory (pinned or pageable). */
 int sb_dataset_upload(sb_engine* e, const float* x, const float* y, int64_t n_rows);
+#define SB_ITER_FROM_DEVICE (-1)
 /* one epoch of `optimizeOnPartition` (Optimizer.scala:135-157): all FULL batches in row order
  * (partial tail dropped), iter = global_iter + j + 1, then the forward-only loss on the last batch
  * with the updated params.  No host sync inside the epoch.  Fewer rows than one batch ->
- * SB_ERR_INVALID_ARG (the reference throws NoSuchElementException, Iterators.scala:79-81). */
+ * SB_ERR_INVALID_ARG (the reference throws NoSuchElementException, Iterators.scala:79-81).
+ * global_iter may be SB_ITER_FROM_DEVICE (see sb_train_steps_async). */
 int sb_train_epoch(sb_engine* e, int64_t global_iter, int64_t* iterations_out, float* last_loss_out);
-/* asynchronous variant: enqueue `n_steps` batches starting at batch `first_batch` of the shard */
+/* asynchronous variant: enqueue `n_steps` batches starting at batch `first_batch` of the shard.
+ * global_iter == SB_ITER_FROM_DEVICE: the device's own step counter continues (after sb_group_average_device it already
+ * holds globalIter + the SUM of all ranks' iteration counts, Optimizer.scala:88,223). */
 int sb_train_steps_async(sb_engine* e, int64_t global_iter, int64_t first_batch, int64_t n_steps);
+/* Capture + instantiate + upload the CUDA graphs of the train path now (the reference's analogue: `compileBackprop` /
+ * `compileLoss` are compiled once per shape signature and cached, Optimizer.scala:132-134, TF.scala:401-417) instead of
+ * lazily inside the first epoch.  Nothing is executed.  SB_WARM_RESIDENT needs an uploaded shard. */
+enum { SB_WARM_RESIDENT = 1, SB_WARM_LOSS = 2, SB_WARM_HOSTFED = 4, SB_WARM_ALL = 7 };
+int sb_warm(sb_engine* e, int what);
 /* single `backprop` call on HOST buffers x[batch,...], y[batch,...] with iter = `iter` (1-based global
  * step): H2D copy, forward, loss, backward, update.  `loss_out` (optional) receives the PRE-update loss
  * of this batch after a D2H read (one sync). */
@@ -299,6 +309,8 @@ void sb_group_destroy(sb_group* g);
  * sb_arena_ipc_handle.  sb_group_average_local launches THIS rank's slice of the fused P2P reduce on the
  * engine stream; the caller places a cross-process barrier before it (all epochs done) and after it
  * (all slices stored), then calls sb_reset_unaggregated and combines loss/iterations itself. */
+/* sb_group_create_ipc also zeroes this rank's barrier flags: put a cross-process barrier before it (no peer still runs an
+ * averaging kernel of an earlier group) and after it (every rank zeroed before anyone raises a flag). */
 int sb_group_create_ipc(sb_engine* self, int rank, int k, const void* handles, int avg_mode,
                         const float* weights_or_null, sb_group** out);
 int sb_group_average_local(sb_group* g);
@@ -306,8 +318,13 @@ int sb_group_average_local(sb_group* g);
  * a flag barrier over NVLink peer memory (all epochs done), the fused reduce-scatter + all-gather of the arena, the
  * combination of the k last-batch losses (same weights and order; result replaces this engine's loss, read it with
  * sb_read_loss) and a second flag barrier (all slices stored).  No host synchronisation: the call only enqueues.
- * `epoch` must increase by one per call on every rank. */
-int sb_group_average_device(sb_group* g, uint64_t epoch);
+ * `epoch` must increase on every call, by the same amount on every rank (a repeated epoch is rejected: stale flags would
+ * open the barrier).  `my_iterations` = batches this rank ran in the epoch; the kernel adds the OTHER ranks' counts to this
+ * engine's device step counter, so the next sb_train_steps_async(SB_ITER_FROM_DEVICE, ...) continues at
+ * globalIter + sum of all counts (Optimizer.scala:88,223) without a host exchange.  A peer that does not arrive within
+ * SB_P2P_TIMEOUT_MS (env, default 600000) leaves this rank's arena un-averaged and the next sb_sync / sb_read_loss returns
+ * SB_ERR_TIMEOUT; the CUDA context stays usable (sb_group_average_local + host barriers is the fallback path). */
+int sb_group_average_device(sb_group* g, uint64_t epoch, int64_t my_iterations);
 /* effective weights the group applies (length k) */
 int sb_group_weights(const sb_group* g, float* weights_out);
 /* the Spark 3.3.1 treeReduce(depth=2) weight vector for k partitions in ascending completion order */

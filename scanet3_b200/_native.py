@@ -8,7 +8,9 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libscanet_b200.so")
 
-SB_OK, SB_ERR_INVALID_ARG, SB_ERR_UNSUPPORTED, SB_ERR_CUDA, SB_ERR_NCCL, SB_ERR_STATE = range(6)
+SB_OK, SB_ERR_INVALID_ARG, SB_ERR_UNSUPPORTED, SB_ERR_CUDA, SB_ERR_NCCL, SB_ERR_STATE, SB_ERR_TIMEOUT = range(7)
+ITER_FROM_DEVICE = -1
+WARM_RESIDENT, WARM_LOSS, WARM_HOSTFED, WARM_ALL = 1, 2, 4, 7
 
 # enums (mirror include/scanet_b200.h)
 (LAYER_DENSE, LAYER_BIAS, LAYER_ACTIVATE, LAYER_FLATTEN, LAYER_CONV2D, LAYER_POOL2D, LAYER_BATCHNORM, LAYER_LSTM,
@@ -89,6 +91,7 @@ PROTOTYPES = {
     "sb_dataset_upload": (C.c_int, [_P, _P, _P, C.c_int64]),
     "sb_train_epoch": (C.c_int, [_P, C.c_int64, C.POINTER(C.c_int64), _FP]),
     "sb_train_steps_async": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64]),
+    "sb_warm": (C.c_int, [_P, C.c_int]),
     "sb_train_step": (C.c_int, [_P, _P, _P, C.c_int64, _FP]),
     "sb_train_step_async": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     "sb_train_batches_async": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, _P]),
@@ -116,7 +119,7 @@ PROTOTYPES = {
     "sb_group_destroy": (None, [_P]),
     "sb_group_create_ipc": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _FP, C.POINTER(_P)]),
     "sb_group_average_local": (C.c_int, [_P]),
-    "sb_group_average_device": (C.c_int, [_P, C.c_uint64]),
+    "sb_group_average_device": (C.c_int, [_P, C.c_uint64, C.c_int64]),
     "sb_group_weights": (C.c_int, [_P, _FP]),
     "sb_spark_chain_weights": (C.c_int, [C.c_int, _FP]),
     "sb_profile_enable": (C.c_int, [_P, C.c_int]),

@@ -1172,14 +1172,29 @@ static void set_device_iter(sb_engine* e, long long iter_done, long long batch_i
   StepState* h = e->st_host + slot;
   h->iter = iter_done;
   h->batch_idx = batch_idx;
+  if (iter_done < 0) {  // SB_ITER_FROM_DEVICE: the device's own counter continues (the averaging kernel added the peers' counts)
+    SB_CUDA(cudaMemcpyAsync(&e->st->batch_idx, &h->batch_idx, sizeof(long long), cudaMemcpyHostToDevice, e->stream));
+    e->host_iter_mirror = -1;
+    return;
+  }
   SB_CUDA(cudaMemcpyAsync(e->st, h, 2 * sizeof(long long), cudaMemcpyHostToDevice, e->stream));
   e->host_iter_mirror = iter_done;
+}
+
+// sticky device-side errors (today: the cross-GPU averaging barrier timed out, group.cu) surface at the next host sync point
+static void check_device_error(sb_engine* e, int err) {
+  if (err == 0) return;
+  SB_CUDA(cudaMemsetAsync(&e->st->err, 0, sizeof(int), e->stream));
+  SB_FAIL(SB_ERR_TIMEOUT, "the device-synchronised averaging timed out waiting for a peer rank (SB_P2P_TIMEOUT_MS); this rank's "
+                          "arena was left un-averaged");
 }
 
 static float read_loss(sb_engine* e) {
   StepState* h = e->st_host + 0;
   SB_CUDA(cudaMemcpyAsync(&h->loss, &e->st->loss, sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  if (e->device_sync_used) SB_CUDA(cudaMemcpyAsync(&h->err, &e->st->err, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
   SB_CUDA(cudaStreamSynchronize(e->stream));
+  if (e->device_sync_used) check_device_error(e, h->err);
   return h->loss;
 }
 
@@ -1460,12 +1475,57 @@ extern "C" int sb_train_steps_async(sb_engine* e, int64_t global_iter, int64_t f
   if (first_batch < 0 || n_steps < 0 || first_batch + n_steps > n_batches)
     SB_FAIL(SB_ERR_INVALID_ARG, "batch range exceeds the shard (" + std::to_string(n_batches) + " full batches)");
   DeviceGuard dg(e->device);
-  set_device_iter(e, global_iter, first_batch);
+  set_device_iter(e, global_iter < 0 ? -1 : global_iter, first_batch);
   // profiling: hold the device back while the host enqueues the event-bracketed launches (~3 API calls per kernel), so
   // the events time kernels back to back instead of launch gaps
   if (e->profiling) device_delay(std::min<long long>(400000000LL, 2000000LL + n_steps * 600000LL), e->stream);
   launch_train_steps_resident(e, n_steps);
-  e->host_iter_mirror = global_iter + n_steps;
+  e->host_iter_mirror = global_iter < 0 ? -1 : global_iter + n_steps;
+  SB_API_END
+}
+
+// Capture, instantiate and upload the CUDA graphs the train path replays, without running anything: the first
+// sb_train_epoch / sb_train_steps_async / sb_train_batches_async after this call costs what every later one costs.
+extern "C" int sb_warm(sb_engine* e, int what) {
+  SB_API_BEGIN
+  need_device(e);
+  require_ready(e);
+  DeviceGuard dg(e->device);
+  if (!e->train.use_graph) return SB_OK;
+  const bool was_profiling = e->profiling;
+  e->profiling = false;
+  auto upload = [&](cudaGraphExec_t g) { if (g) SB_CUDA(cudaGraphUpload(g, e->stream)); };
+  try {
+    if ((what & SB_WARM_RESIDENT) && e->ds_x) {
+      if (!e->g_resident) e->g_resident = capture(e, &e->nodes_resident, run_train_step_body, true);
+      if (steps_per_graph() > 1 && !e->g_resident_multi)
+        e->g_resident_multi = capture(e, &e->nodes_resident_multi, run_train_steps_body_multi, true);
+      upload(e->g_resident);
+      upload(e->g_resident_multi);
+    }
+    if (what & (SB_WARM_RESIDENT | SB_WARM_LOSS)) {
+      if (!e->g_loss) e->g_loss = capture(e, &e->nodes_loss, loss_body, false);
+      upload(e->g_loss);
+    }
+    if (what & SB_WARM_HOSTFED) {
+      ensure_staging(e);
+      if (!e->g_hostfed) e->g_hostfed = capture(e, &e->nodes_hostfed, run_train_step_body, false);
+      upload(e->g_hostfed);
+      for (int par = 0; par < 2; ++par) {
+        if (!e->g_staged[par]) e->g_staged[par] = capture(e, &e->nodes_staged[par], run_train_step_body_staged, par != 0);
+        if (e->stage_batches > 1 && !e->g_group[par])
+          e->g_group[par] = capture(e, &e->nodes_group[par], run_train_group_body_staged, par != 0);
+        upload(e->g_staged[par]);
+        upload(e->g_group[par]);
+      }
+    }
+  } catch (...) {
+    e->profiling = was_profiling;
+    throw;
+  }
+  e->profiling = was_profiling;
+  SB_CUDA(cudaStreamSynchronize(e->stream));
+  set_prewait_ok(0);
   SB_API_END
 }
 
@@ -1478,9 +1538,9 @@ extern "C" int sb_train_epoch(sb_engine* e, int64_t global_iter, int64_t* iterat
   if (n_batches == 0)
     SB_FAIL(SB_ERR_INVALID_ARG, "NoSuchElementException: the shard holds fewer rows than one batch (Iterators.scala:79-81)");
   DeviceGuard dg(e->device);
-  set_device_iter(e, global_iter, 0);
+  set_device_iter(e, global_iter < 0 ? -1 : global_iter, 0);  // SB_ITER_FROM_DEVICE: the device's counter continues
   launch_train_steps_resident(e, n_batches);
-  e->host_iter_mirror = global_iter + n_batches;
+  e->host_iter_mirror = global_iter < 0 ? -1 : global_iter + n_batches;
   launch_loss(e);  // forward-only loss on the LAST batch with the UPDATED params (Optimizer.scala:148)
   float loss = read_loss(e);
   if (e->profiling) prof_resolve(e);
@@ -1655,9 +1715,11 @@ extern "C" int sb_sync(sb_engine* e) {
   SB_API_BEGIN
   need_device(e);
   DeviceGuard dg(e->device);
+  if (e->device_sync_used) SB_CUDA(cudaMemcpyAsync(&e->st_host->err, &e->st->err, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
   SB_CUDA(cudaStreamSynchronize(e->stream));
   if (e->cstream) SB_CUDA(cudaStreamSynchronize(e->cstream));  // loss read-backs of sb_train_batches_async
   if (e->profiling) prof_resolve(e);
+  if (e->device_sync_used) check_device_error(e, e->st_host->err);
   SB_API_END
 }
 

@@ -151,6 +151,7 @@ struct sb_engine {
   long long launches = 0;
   long long host_iter_mirror = -1;  // device st->iter as far as the host knows (-1 unknown)
   bool params_ready = false, opt_ready = false;
+  bool device_sync_used = false;  // took part in sb_group_average_device: host sync points also read StepState.err
   bool softmax_cce_fused = false;
   bool has_reg = false;      // some weight carries an L1/L2 penalty
   bool head_fused = false;   // last layers Dense >> Bias >> Softmax with CCE: one fused bias+softmax+loss+dz+dbias kernel

@@ -90,13 +90,20 @@ __global__ void __launch_bounds__(256) p2p_average_kernel(PeerSet ps, long long 
 
 // ---- device-synchronised variant: flag barrier + reduce + loss combine + flag barrier in ONE kernel per rank ----
 // Tail of every arena allocation (kArenaTailFloats floats behind the tensors), written by peers over NVLink:
-//   u64 arrive[8] | u64 done[8] | float loss[8]          (slot q is written by rank q)
+//   u64 arrive[8] | u64 done[8] | float loss[8] | (pad to 64 floats) | i64 iters[8]        (slot q is written by rank q)
+// The tail is zeroed by sb_group_create_ipc (flags of an earlier group on the same engine must not satisfy this group's
+// barriers); the host plumbing puts a cross-process barrier between creation and first use.
+constexpr int kTailLossOff = 32;   // floats
+constexpr int kTailItersOff = 64;  // floats (8-byte aligned: the arena is padded to 32 floats)
 struct SyncArgs {
   long long tail_off;  // floats from the arena base
   unsigned long long epoch;
   int rank;
-  float* my_loss;       // this engine's StepState.loss: read before the barrier, replaced by the combined loss
+  StepState* st;        // this engine's step state: loss read before the barrier and replaced by the combined loss; iter gets
+                        // the peers' iteration counts added (Optimizer.scala:88,223); err receives the timeout flag
+  long long my_iters;   // iterations this rank ran in the epoch that just ended
   unsigned int* ticket; // local CTA-completion counter (zero between launches)
+  unsigned long long timeout_ns;
 };
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -106,28 +113,45 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-// bounded: a rank that never arrives traps this kernel (launch error) instead of hanging the GPU
-__device__ __forceinline__ void wait_flag(const unsigned long long* p, unsigned long long epoch) {
-  for (unsigned long long spins = 0; ld_acquire_sys(p) < epoch; ++spins) {
-    __nanosleep(200);
-    if (spins > (1ull << 26)) __trap();  // ~15 s
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded in wall-clock time (SB_P2P_TIMEOUT_MS, default 10 min): a rank that never arrives makes this return false; the
+// kernel then records the failure in StepState.err and exits WITHOUT reducing -- the context stays usable and the host gets
+// SB_ERR_TIMEOUT at its next sync point (sb_sync / sb_read_loss) instead of a sticky launch failure.
+__device__ __forceinline__ bool wait_flag(const unsigned long long* p, unsigned long long epoch, unsigned long long t0,
+                                          unsigned long long timeout_ns) {
+  unsigned spins = 0;
+  while (ld_acquire_sys(p) < epoch) {
+    __nanosleep(spins < 64 ? 100 : 1000);
+    if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > timeout_ns) return false;
   }
+  return true;
 }
 __global__ void __launch_bounds__(256) p2p_average_sync_kernel(PeerSet ps, long long lo4, long long hi4, SyncArgs a) {
   pdl_prologue();
+  __shared__ int bail;
   unsigned long long* my_tail = reinterpret_cast<unsigned long long*>(ps.ptr[a.rank] + a.tail_off);
   if (threadIdx.x == 0) {
+    const unsigned long long t0 = globaltimer_ns();
+    bool ok = true;
     if (blockIdx.x == 0) {
-      const float l = *a.my_loss;
-      for (int q = 0; q < ps.k; ++q) (ps.ptr[q] + a.tail_off + 32)[a.rank] = l;
+      const float l = a.st->loss;
+      for (int q = 0; q < ps.k; ++q) {
+        (ps.ptr[q] + a.tail_off + kTailLossOff)[a.rank] = l;
+        reinterpret_cast<long long*>(ps.ptr[q] + a.tail_off + kTailItersOff)[a.rank] = a.my_iters;
+      }
       __threadfence_system();
       for (int q = 0; q < ps.k; ++q)
         st_release_sys(reinterpret_cast<unsigned long long*>(ps.ptr[q] + a.tail_off) + a.rank, a.epoch);
     }
-    for (int q = 0; q < ps.k; ++q) wait_flag(my_tail + q, a.epoch);  // every rank finished its epoch
-    if (blockIdx.x == 0) {
-      // loss: the same weights in the same order (Optimizer.scala:221)
-      const float* ls = ps.ptr[a.rank] + a.tail_off + 32;
+    for (int q = 0; q < ps.k && ok; ++q) ok = wait_flag(my_tail + q, a.epoch, t0, a.timeout_ns);  // every rank finished its epoch
+    if (ok && blockIdx.x == 0) {
+      // loss: the same weights in the same order (Optimizer.scala:221); iterations: a plain sum (Optimizer.scala:223)
+      const float* ls = ps.ptr[a.rank] + a.tail_off + kTailLossOff;
+      const long long* its = reinterpret_cast<const long long*>(ps.ptr[a.rank] + a.tail_off + kTailItersOff);
       float tot = 0.f;
       for (int gi = 0; gi < ps.n_groups; ++gi) {
         float acc = 0.f;
@@ -139,10 +163,17 @@ __global__ void __launch_bounds__(256) p2p_average_sync_kernel(PeerSet ps, long 
         }
         tot = gi == 0 ? acc : __fadd_rn(tot, acc);
       }
-      *a.my_loss = tot;
+      long long others = 0;
+      for (int q = 0; q < ps.k; ++q)
+        if (q != a.rank) others += __ldcv(its + q);
+      a.st->loss = tot;
+      a.st->iter += others;  // the step counter is global: next epoch starts at globalIter + sum of all ranks' counts
     }
+    if (!ok) a.st->err = 1;
+    bail = ok ? 0 : 1;
   }
   __syncthreads();
+  if (bail) return;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = lo4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi4; i += stride) {
     float4 v[kMaxRanks];
@@ -173,9 +204,12 @@ __global__ void __launch_bounds__(256) p2p_average_sync_kernel(PeerSet ps, long 
   if (threadIdx.x == 0) {
     if (atomicAdd(a.ticket, 1u) == gridDim.x - 1) {  // last CTA of this rank: its slice is stored everywhere
       *a.ticket = 0;
+      const unsigned long long t0 = globaltimer_ns();
       for (int q = 0; q < ps.k; ++q)
         st_release_sys(reinterpret_cast<unsigned long long*>(ps.ptr[q] + a.tail_off) + 8 + a.rank, a.epoch);
-      for (int q = 0; q < ps.k; ++q) wait_flag(my_tail + 8 + q, a.epoch);  // every slice of MY arena has landed
+      bool ok = true;
+      for (int q = 0; q < ps.k && ok; ++q) ok = wait_flag(my_tail + 8 + q, a.epoch, t0, a.timeout_ns);  // every slice of MY arena has landed
+      if (!ok) a.st->err = 1;
     }
   }
 }
@@ -273,6 +307,7 @@ struct sb_group {
   PeerSet ps[kMaxRanks];  // per local rank: peer pointers as seen from that device
   std::vector<void*> ipc_opened;
   unsigned int* ticket = nullptr;  // device counter of the device-synchronised kernel
+  uint64_t last_epoch = 0;         // sb_group_average_device: epochs must increase
   NcclApi nccl;
   std::vector<ncclComm_t> comms;
 };
@@ -311,6 +346,9 @@ extern "C" int sb_group_create(sb_engine** engines, int k, int avg_mode, const f
   g->collective = collective;
   check_same_arena(g->es);
   fill_weights(g.get(), avg_mode, weights_or_null);
+  if (collective == SB_COLL_NCCL && g->n_groups > 1)
+    SB_FAIL(SB_ERR_UNSUPPORTED, "SB_COLL_NCCL sums in NCCL's own order and cannot reproduce the grouped Spark chain (k >= 6): use "
+                                "SB_COLL_P2P, or SB_AVG_MEAN / SB_AVG_WEIGHTS with NCCL");
   if (collective == SB_COLL_P2P) {
     for (int r = 0; r < k; ++r) {
       SB_CUDA(cudaSetDevice(g->es[r]->device));
@@ -371,6 +409,12 @@ extern "C" int sb_group_create_ipc(sb_engine* self, int rank, int k, const void*
     g->ipc_opened.push_back(p);
     ps.ptr[q] = (float*)p;
   }
+  // flags / scalars an earlier group left in this rank's tail must not satisfy this group's barriers (epochs restart at 1):
+  // zero it now; the caller barriers across the ranks between this call and the first sb_group_average_device
+  SB_CUDA(cudaMemsetAsync(self->arena + self->arena_floats, 0, (size_t)kArenaTailFloats * 4, self->stream));
+  SB_CUDA(cudaMalloc((void**)&g->ticket, 64));
+  SB_CUDA(cudaMemsetAsync(g->ticket, 0, 64, self->stream));
+  SB_CUDA(cudaStreamSynchronize(self->stream));
   *out = g.release();
   SB_API_END
 }
@@ -396,16 +440,28 @@ extern "C" int sb_group_average_local(sb_group* g) {
   SB_API_END
 }
 
-extern "C" int sb_group_average_device(sb_group* g, uint64_t epoch) {
+static unsigned long long p2p_timeout_ns() {
+  static const unsigned long long ns = [] {
+    const char* v = getenv("SB_P2P_TIMEOUT_MS");
+    const double ms = v ? atof(v) : 600000.0;
+    return (unsigned long long)((ms > 1.0 ? ms : 1.0) * 1e6);
+  }();
+  return ns;
+}
+
+extern "C" int sb_group_average_device(sb_group* g, uint64_t epoch, int64_t my_iterations) {
   SB_API_BEGIN
   if (!g || g->rank < 0) SB_FAIL(SB_ERR_INVALID_ARG, "not an IPC group");
+  if (epoch <= g->last_epoch)
+    SB_FAIL(SB_ERR_INVALID_ARG, "sb_group_average_device: epoch " + std::to_string(epoch) + " does not exceed the last one used (" +
+                                    std::to_string(g->last_epoch) + "): stale flags would open the barrier");
+  g->last_epoch = epoch;
   if (g->k == 1) return SB_OK;
   sb_engine* e = g->es[g->rank];
   SB_CUDA(cudaSetDevice(e->device));
-  if (!g->ticket) {
-    SB_CUDA(cudaMalloc((void**)&g->ticket, 64));
-    SB_CUDA(cudaMemsetAsync(g->ticket, 0, 64, e->stream));
-  }
+  e->device_sync_used = true;
+  e->host_iter_mirror = -1;  // the kernel adds the peers' iteration counts to the device counter
+  SB_CUDA(cudaMemsetAsync(g->ticket, 0, 4, e->stream));  // a timed-out launch leaves it non-zero
   const long long n4 = e->arena_floats / 4;
   const long long per = (n4 + g->k - 1) / g->k;
   const long long lo = per * g->rank, hi = std::min(n4, per * (g->rank + 1));
@@ -416,8 +472,10 @@ extern "C" int sb_group_average_device(sb_group* g, uint64_t epoch) {
   a.tail_off = e->arena_floats;
   a.epoch = epoch;
   a.rank = g->rank;
-  a.my_loss = &e->st->loss;
+  a.st = e->st;
+  a.my_iters = my_iterations;
   a.ticket = g->ticket;
+  a.timeout_ns = p2p_timeout_ns();
   launch_k(p2p_average_sync_kernel, blocks, 256, 0, e->stream, g->ps[g->rank], lo, hi, a);
   SB_LAUNCHED();
   set_prewait_ok(0);  // writes weights

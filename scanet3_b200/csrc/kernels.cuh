@@ -15,7 +15,14 @@ struct StepState {
   float bc1;            // 1 - beta1^t   (`boost`, math/alg/AllKernels.scala:546-549)
   float bc2;            // 1 - beta2^t
   float loss;           // loss of the latest forward
-  float pad;
+  float pad;            // running sum of the L1/L2 penalties (reg_penalty_grad)
+  // bias corrections of step `bc_iter`, computed one step ahead by a spare thread of the optimizer kernel (two double-precision
+  // pow() calls, ~2 us of dependent latency that used to sit on the prologue kernel's critical path); the prologue takes them when
+  // bc_iter matches the step it starts and recomputes otherwise (the host moved `iter`, another optimizer, first step)
+  long long bc_iter;
+  float bc1_next, bc2_next;
+  int err;              // sticky device-side error (1: cross-GPU averaging barrier timed out, group.cu); read by sb_sync / sb_read_loss
+  int pad2;
 };
 
 struct ConvGeom {

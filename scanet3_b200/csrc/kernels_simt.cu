@@ -35,43 +35,16 @@ __global__ void step_prologue_kernel(StepState* st, const V* __restrict__ ds_x, 
     // boost(x, rate, t) = x / (1 - rate^float(t)) (math/alg/AllKernels.scala:546-549).  The power is
     // evaluated in double and rounded once, i.e. the correctly rounded powf TF-CPU (glibc) returns.
     const long long t = st->iter + 1;
-    const double tf = (double)(float)t;
-    st->bc1 = __fsub_rn(1.0f, (float)pow((double)beta1, tf));
-    st->bc2 = __fsub_rn(1.0f, (float)pow((double)beta2, tf));
+    if (st->bc_iter == t) {  // computed one step ahead by the optimizer kernel (same expression, same bits)
+      st->bc1 = st->bc1_next;
+      st->bc2 = st->bc2_next;
+    } else {
+      const double tf = (double)(float)t;
+      st->bc1 = __fsub_rn(1.0f, (float)pow((double)beta1, tf));
+      st->bc2 = __fsub_rn(1.0f, (float)pow((double)beta2, tf));
+    }
     st->iter = t;
   }
-}
-
-// EXPERIMENT for round 2 (SB_X_PROLOGUE_V2=1; never measured — see profiles/r1_notes.md "Open leads"): the two double-precision
-// pow() calls, the longest dependent chain of the prologue, start first and run on lane 0 of two different warps of the last CTA.
-// Only those two threads read st->iter; it is advanced after a CTA-wide barrier (no warp-level barrier inside the divergent code).
-template <typename V>
-__global__ void step_prologue2_kernel(StepState* st, const V* __restrict__ ds_x, const V* __restrict__ ds_y,
-                                      V* __restrict__ bx, V* __restrict__ by, long long x4, long long y4,
-                                      float beta1, float beta2, int batch_from_state, float* __restrict__ prev_loss_slot, int early) {
-  pdl_prologue_trigger_if(early);
-  const long long b = batch_from_state ? st->batch_idx : 0;
-  const bool last = blockIdx.x == gridDim.x - 1;
-  long long t = 0;
-  if (last && threadIdx.x == 0) {
-    t = st->iter + 1;
-    if (prev_loss_slot) *prev_loss_slot = st->loss;
-    st->bc1 = __fsub_rn(1.0f, (float)pow((double)beta1, (double)(float)t));
-  } else if (last && threadIdx.x == 32) {
-    const long long t2 = st->iter + 1;
-    st->bc2 = __fsub_rn(1.0f, (float)pow((double)beta2, (double)(float)t2));
-  }
-  if (ds_x != nullptr) {
-    const V* sx = ds_x + b * x4;
-    const V* sy = ds_y + b * y4;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < x4 + y4; i += stride) {
-      if (i < x4) bx[i] = sx[i];
-      else by[i - x4] = sy[i - x4];
-    }
-  }
-  __syncthreads();  // thread 32 has read st->iter
-  if (last && threadIdx.x == 0) st->iter = t;
 }
 
 void step_prologue(StepState* st, const float* ds_x, const float* ds_y, float* bx, float* by, long long x_per_batch,
@@ -82,13 +55,6 @@ void step_prologue(StepState* st, const float* ds_x, const float* ds_y, float* b
   int blocks = 1;
   if (ds_x) blocks = (int)fmin((double)ceil_div(xn + yn, 256), (double)kNumSMs * 8);
   if (blocks < 1) blocks = 1;
-  static const bool v2 = [] { const char* v = getenv("SB_X_PROLOGUE_V2"); return v && v[0] == '1'; }();
-  if (v2 && vec) {
-    launch_k(step_prologue2_kernel<float4>, blocks, 256, 0, s, st, (const float4*)ds_x, (const float4*)ds_y, (float4*)bx,
-                                                         (float4*)by, xn, yn, beta1, beta2, batch_from_state, prev_loss_slot, pdl_early_hint());
-    SB_LAUNCHED();
-    return;
-  }
   if (vec)
     launch_k(step_prologue_kernel<float4>, blocks, 256, 0, s, st, (const float4*)ds_x, (const float4*)ds_y, (float4*)bx,
                                                         (float4*)by, xn, yn, beta1, beta2, batch_from_state, prev_loss_slot, pdl_early_hint());
@@ -1155,6 +1121,16 @@ __global__ void __launch_bounds__(256) optimizer_kernel(OptDesc od, float4* __re
   }
   // the batch cursor is only read by the NEXT step's prologue kernel, so it can be advanced here
   if (advance_batch && blockIdx.x == 0 && threadIdx.x == 0) st->batch_idx += 1;
+  // the NEXT step's bias corrections 1 - beta^t (`boost`, math/alg/AllKernels.scala:546-549): the double-precision pow pair is the
+  // longest dependent chain of the prologue kernel; here it hides behind the update of the arena.  bc1 / bc2 themselves are left
+  // alone (other threads of this grid are still reading them); the prologue adopts the pair if `iter` is still this step's.
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == blockDim.x - 1) {
+    const long long t = st->iter + 1;
+    const double tf = (double)(float)t;
+    st->bc1_next = __fsub_rn(1.0f, (float)pow((double)od.beta1, tf));
+    st->bc2_next = __fsub_rn(1.0f, (float)pow((double)od.beta2, tf));
+    st->bc_iter = t;
+  }
 }
 void optimizer_step(const OptDesc& o, float* w, const float* g, float* s0, float* s1, float* s2, long long n, StepState* st,
                     int advance_batch, cudaStream_t s) {

@@ -123,7 +123,13 @@ class RankAverager:
             w = (C.c_float * self.world)(*self.weights)
             g = C.c_void_p()
             mode = avg_mode
+            # The barrier flags live in the arena tail and outlive a group: an earlier RankAverager on the same engine left
+            # flags >= this one's epochs.  No peer may still be inside an old averaging kernel when the tails are zeroed
+            # (barrier 1), and every rank must have zeroed its tail before anyone raises a flag again (barrier 2).
+            engine.sync()
+            dist.barrier()
             N.check(N.lib().sb_group_create_ipc(engine.handle, self.rank, self.world, blob, int(mode), w, C.byref(g)))
+            dist.barrier()
             self._g = g
         elif self.world > 1:
             if self.n_groups != 1:
@@ -149,18 +155,25 @@ class RankAverager:
         self.engine.reset_unaggregated()
         return combine_scalars(loss, iterations, self.weights, self.n_groups)
 
-    def average_async(self, iterations: int) -> int:
+    def average_async(self, iterations: int, exchange: bool = False) -> int:
         """Enqueue the device-synchronised averaging; returns the summed iteration count.  The combined loss stays on the
-        device (engine.read_loss()).  The per-rank iteration counts are exchanged once: a rank's shard (hence its number of
-        full batches per epoch) does not change between epochs."""
-        import torch.distributed as dist
-        if self._iters_cache is None or self._iters_cache[0] != int(iterations):
+        device (engine.read_loss()).
+
+        The authoritative sum of the ranks' iteration counts is formed ON THE DEVICE: the kernel adds the peers' counts to the
+        engine's step counter, so `train_steps_async(ITER_FROM_DEVICE, ...)` continues at the reference's global `iter`
+        (Optimizer.scala:88,223) whatever the host believes.  The value returned here is for reporting: it is exchanged
+        collectively on the FIRST call and whenever `exchange=True` is passed -- by every rank in the same call, like any
+        collective (never conditionally on a rank's own count, which would hang the ranks whose count did not change)."""
+        if self.world == 1 or self._g is None:
+            return int(iterations)
+        if self._iters_cache is None or exchange:
+            import torch.distributed as dist
             gathered = [None] * self.world
             dist.all_gather_object(gathered, int(iterations))
-            self._iters_cache = (int(iterations), sum(gathered))
+            self._iters_cache = sum(gathered)
         self._epoch += 1
-        N.check(N.lib().sb_group_average_device(self._g, self._epoch))
-        return self._iters_cache[1]
+        N.check(N.lib().sb_group_average_device(self._g, self._epoch, int(iterations)))
+        return self._iters_cache
 
     def _average_device(self, iterations: int) -> Tuple[float, int]:
         total = self.average_async(iterations)

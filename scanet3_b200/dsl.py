@@ -20,7 +20,14 @@ class Initializer:
     name: str = ""
 
     def to_native(self) -> N.sb_initializer:
-        return N.sb_initializer(self.kind, 0 if self.seed is None else 1, 0 if self.seed is None else int(self.seed),
+        # seed = None: TF draws a fresh seed per `initialize.eval`, and every partition initialises independently on the first
+        # epoch (Optimizer.scala:123-131) -- so the host runtime draws one per lowering (= per engine / partition).  The C ABI
+        # itself only takes explicit seeds; bit parity with the reference is claimed for explicitly seeded initializers only.
+        seed = self.seed
+        if seed is None and self.kind not in (N.INIT_ZEROS, N.INIT_ONES, N.INIT_CONST):
+            import secrets
+            seed = secrets.randbits(31)
+        return N.sb_initializer(self.kind, 0 if seed is None else 1, 0 if seed is None else int(seed),
                                 float(self.a), float(self.b))
 
     def __repr__(self):

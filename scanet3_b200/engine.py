@@ -153,6 +153,12 @@ class Engine:
         N.check(self._lib.sb_train_epoch(self._h, int(global_iter), C.byref(it), C.byref(loss)))
         return it.value, loss.value
 
+    def warm(self, what: int = N.WARM_ALL):
+        """`sb_warm`: capture + instantiate + upload the CUDA graphs of the train path now instead of inside the first epoch."""
+        if not getattr(self, "dataset_rows", 0):
+            what &= ~N.WARM_RESIDENT
+        N.check(self._lib.sb_warm(self._h, int(what)))
+
     def train_steps_async(self, global_iter: int, first_batch: int, n_steps: int):
         N.check(self._lib.sb_train_steps_async(self._h, int(global_iter), int(first_batch), int(n_steps)))
 

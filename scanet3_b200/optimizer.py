@@ -348,9 +348,11 @@ class Optimizer:
                 print(f"Training model: {c.model!r} (no description: {ex})")
         engines = [Engine(c.model, c.loss, c.alg, c.batchSize, in_shape, lab_shape, device=d, precision=c.precision,
                           use_graph=c.use_graph, minimizing=c.minimizing) for d in devices]
-        group = Group(engines, c.avg_mode, collective=c.collective) if k > 1 else None
-        pool = ThreadPoolExecutor(max_workers=k) if k > 1 else None
+        group = pool = None
+        handed_over = False  # engines[0] leaves with the TrainedModel on success; every other path closes all k engines
         try:
+            group = Group(engines, c.avg_mode, collective=c.collective) if k > 1 else None
+            pool = ThreadPoolExecutor(max_workers=k) if k > 1 else None
             step = Step(c.batchSize)
             for i, e in enumerate(engines):
                 x, y = ds.shard(i, k)
@@ -392,11 +394,12 @@ class Optimizer:
                 if c.stop(ctx):
                     params = result.modelParams
                     break
-            for e in engines[1:]:
-                e.close()
+            handed_over = True
             return TrainedModel(self.lossModel, params, engines[0])
         finally:
             if pool is not None:
                 pool.shutdown()
             if group is not None:
                 group.close()
+            for e in (engines[1:] if handed_over else engines):  # device arenas, streams and graphs
+                e.close()

@@ -43,3 +43,47 @@ def test_spark_chain_is_not_the_mean_for_k4():
     N.check(N.lib().sb_spark_chain_weights(4, w))
     assert list(w) == list(np.float32(O.spark_chain_weights(4)))
     assert list(w) != [0.25] * 4
+
+
+def _run_ipc_check(mode, port, timeout_ms):
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SB_P2P_TIMEOUT_MS=str(timeout_ms), SB_P2P_CTAS_PER_SM="1")
+    return subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                           "127.0.0.1", "--master-port", str(port), os.path.join(root, "tests", "ipc_same_gpu_check.py"), mode],
+                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=240, env=env)
+
+
+def test_device_synchronised_averaging_between_two_processes():
+    """`sb_group_create_ipc` + `sb_group_average_device` (the path `bench.py --gpus N` and `RankAverager` use) with two
+    processes on ONE GPU: flag barriers, loss combine, the device-side sum of the iteration counts, and a second group on the
+    same engines (stale flags).  tests/ipc_same_gpu_check.py compares with the oracle's 2-partition run."""
+    r = _run_ipc_check("ok", 29611, 60000)
+    assert r.returncode == 0 and "IPC_CHECK RESULT OK" in r.stdout, r.stdout[-3000:]
+
+
+def test_device_synchronised_averaging_times_out_cleanly():
+    """a peer that never arrives: SB_ERR_TIMEOUT at the next sync point, no trap, the context stays usable"""
+    r = _run_ipc_check("timeout", 29612, 1500)
+    assert r.returncode == 0 and "IPC_CHECK RESULT OK" in r.stdout and "[6]" in r.stdout, r.stdout[-3000:]
+
+
+def test_warmed_graphs_change_nothing():
+    """`sb_warm` only moves graph capture / instantiation ahead of the first epoch: two epochs are bit-identical with and without it"""
+    om, sm = build_models(SPEC)
+    x, y = synth_classification(8 * 11, (12,), 4, 3)
+    outs = []
+    for warm in (False, True):
+        e = S.Engine(sm, S.CategoricalCrossentropy, S.Adam(0.01), 8, (12,), (4,))
+        e.init_params()
+        e.upload_dataset(x, y)
+        if warm:
+            e.warm()
+        it1, l1 = e.train_epoch(0)
+        it2, l2 = e.train_epoch(it1)
+        losses = e.train_batches(x, y, it1 + it2)
+        outs.append((l1, l2, losses.tobytes(), {k: v.tobytes() for k, v in e.get_params().items()}))
+        e.close()
+    assert outs[0] == outs[1]

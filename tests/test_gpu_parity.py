@@ -329,8 +329,28 @@ def test_state_errors_and_unsupported():
     with pytest.raises(S.IllegalArgument, match="missing 9/nope param"):  # core/Params.scala:22-23
         S.native.check(e._lib.sb_params_get(e.handle, b"9/nope", np.zeros(1, f32).ctypes.data, 1))
     e.close()
+    # unseeded random initializers: the host runtime draws a seed per engine, as every partition initialises independently in the
+    # reference (Optimizer.scala:123-131); the C ABI itself refuses a random initializer without a seed
+    ws = []
+    for _ in range(2):
+        e = S.Engine(S.Dense(3, kernelInitializer=S.GlorotUniform()), S.MeanSquaredError, S.SGD(), 2, (2,), (3,))
+        e.init_params()
+        ws.append(e.get_param("0/weights"))
+        e.close()
+    lim = np.sqrt(6.0 / 5.0)
+    assert np.all(np.abs(ws[0]) <= lim) and np.any(ws[0] != 0) and not np.array_equal(ws[0], ws[1])
+    leaves = S.Dense(3, kernelInitializer=S.GlorotUniform(7)).leaves()
+    arr = (S.native.sb_layer_desc * len(leaves))(*[l.to_native() for l in leaves])
+    arr[0].init[0].has_seed = 0
+    md = S.native.sb_model_desc(); md.n_layers = len(leaves); md.layers = arr; md.input_rank = 1; md.label_rank = 1
+    md.input_dims[0] = 2; md.label_dims[0] = 3
+    td = S.native.sb_train_desc(2, S.native.LOSS_MSE, S.native.OPT_SGD, 0.01, 0.9, 0.999, 1e-7, 0.0, 0, 1, 0, 1)
+    import ctypes as C
+    h = C.c_void_p()
+    S.native.check(e._lib.sb_engine_create(C.byref(md), C.byref(td), 0, C.byref(h)))
     with pytest.raises(S.Unsupported):
-        S.Engine(S.Dense(3, kernelInitializer=S.GlorotUniform()), S.MeanSquaredError, S.SGD(), 2, (2,), (3,)).init_params()
+        S.native.check(e._lib.sb_init_params(h))
+    e._lib.sb_engine_destroy(h)
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -27,7 +27,7 @@ def test_library_exports_every_symbol_the_header_declares():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} is declared in include/scanet_b200.h but not exported"
     assert declared == set(N.PROTOTYPES.keys()), declared ^ set(N.PROTOTYPES.keys())
-    assert N.lib().sb_abi_version() == 3
+    assert N.lib().sb_abi_version() == 4
 
 
 def test_no_cpu_fallback_without_a_device():
