@@ -290,7 +290,8 @@ def run_ours(args):
         state["averagings"] += 1
         if coll == N.COLL_P2P:
             state["dev_iter"] = True   # from now on the device's own step counter is the global one
-            return avg.average_async(steps_per_epoch)
+            avg.average_async(steps_per_epoch)
+            return world * steps_per_epoch  # host mirror of the device-side sum: the shards are equal by construction
         return avg.average(0.0, steps_per_epoch)[1]
 
     def at_epoch_end():

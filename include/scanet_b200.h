@@ -325,6 +325,9 @@ int sb_group_average_local(sb_group* g);
  * SB_P2P_TIMEOUT_MS (env, default 600000) leaves this rank's arena un-averaged and the next sb_sync / sb_read_loss returns
  * SB_ERR_TIMEOUT; the CUDA context stays usable (sb_group_average_local + host barriers is the fallback path). */
 int sb_group_average_device(sb_group* g, uint64_t epoch, int64_t my_iterations);
+/* result of the latest sb_group_average_device: one stream sync, the combined loss ((lossL+lossR)/2 chain, Optimizer.scala:221)
+ * and the summed iteration count (Optimizer.scala:223).  SB_ERR_TIMEOUT if a peer never reached the barrier. */
+int sb_group_read_result(sb_group* g, float* loss_out, int64_t* total_iterations_out);
 /* effective weights the group applies (length k) */
 int sb_group_weights(const sb_group* g, float* weights_out);
 /* the Spark 3.3.1 treeReduce(depth=2) weight vector for k partitions in ascending completion order */

@@ -120,6 +120,7 @@ PROTOTYPES = {
     "sb_group_create_ipc": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _FP, C.POINTER(_P)]),
     "sb_group_average_local": (C.c_int, [_P]),
     "sb_group_average_device": (C.c_int, [_P, C.c_uint64, C.c_int64]),
+    "sb_group_read_result": (C.c_int, [_P, _FP, C.POINTER(C.c_int64)]),
     "sb_group_weights": (C.c_int, [_P, _FP]),
     "sb_spark_chain_weights": (C.c_int, [C.c_int, _FP]),
     "sb_profile_enable": (C.c_int, [_P, C.c_int]),

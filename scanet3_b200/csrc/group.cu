@@ -167,6 +167,7 @@ __global__ void __launch_bounds__(256) p2p_average_sync_kernel(PeerSet ps, long 
       for (int q = 0; q < ps.k; ++q)
         if (q != a.rank) others += __ldcv(its + q);
       a.st->loss = tot;
+      a.st->avg_total_iters = others + a.my_iters;
       a.st->iter += others;  // the step counter is global: next epoch starts at globalIter + sum of all ranks' counts
     }
     if (!ok) a.st->err = 1;
@@ -482,6 +483,23 @@ extern "C" int sb_group_average_device(sb_group* g, uint64_t epoch, int64_t my_i
   e->launches += 1;
   int rc = sb_reset_unaggregated(e);  // aggregation == None tensors are re-initialised (Optimizer.scala:209)
   if (rc != SB_OK) return rc;
+  SB_API_END
+}
+
+extern "C" int sb_group_read_result(sb_group* g, float* loss_out, int64_t* total_iterations_out) {
+  SB_API_BEGIN
+  if (!g || g->rank < 0) SB_FAIL(SB_ERR_INVALID_ARG, "not an IPC group");
+  sb_engine* e = g->es[g->rank];
+  SB_CUDA(cudaSetDevice(e->device));
+  float loss = 0.f;
+  int rc = sb_read_loss(e, &loss);  // syncs the stream; SB_ERR_TIMEOUT if a peer never reached the barrier
+  if (rc != SB_OK) return rc;
+  if (loss_out) *loss_out = loss;
+  if (total_iterations_out) {
+    long long t = 0;
+    SB_CUDA(cudaMemcpy(&t, &e->st->avg_total_iters, sizeof t, cudaMemcpyDeviceToHost));
+    *total_iterations_out = t;
+  }
   SB_API_END
 }
 

@@ -21,6 +21,7 @@ struct StepState {
   // bc_iter matches the step it starts and recomputes otherwise (the host moved `iter`, another optimizer, first step)
   long long bc_iter;
   float bc1_next, bc2_next;
+  long long avg_total_iters;  // sum of all ranks' iteration counts at the latest device-synchronised averaging (group.cu)
   int err;              // sticky device-side error (1: cross-GPU averaging barrier timed out, group.cu); read by sb_sync / sb_read_loss
   int pad2;
 };

@@ -155,29 +155,26 @@ class RankAverager:
         self.engine.reset_unaggregated()
         return combine_scalars(loss, iterations, self.weights, self.n_groups)
 
-    def average_async(self, iterations: int, exchange: bool = False) -> int:
-        """Enqueue the device-synchronised averaging; returns the summed iteration count.  The combined loss stays on the
-        device (engine.read_loss()).
-
-        The authoritative sum of the ranks' iteration counts is formed ON THE DEVICE: the kernel adds the peers' counts to the
-        engine's step counter, so `train_steps_async(ITER_FROM_DEVICE, ...)` continues at the reference's global `iter`
-        (Optimizer.scala:88,223) whatever the host believes.  The value returned here is for reporting: it is exchanged
-        collectively on the FIRST call and whenever `exchange=True` is passed -- by every rank in the same call, like any
-        collective (never conditionally on a rank's own count, which would hang the ranks whose count did not change)."""
+    def average_async(self, iterations: int) -> None:
+        """Enqueue the device-synchronised averaging: no host collective, no sync.  The kernel combines the losses and adds the
+        peers' iteration counts to the engine's DEVICE step counter, so `train_steps_async(ITER_FROM_DEVICE, ...)` /
+        `train_epoch(ITER_FROM_DEVICE)` continue at the reference's global `iter` (Optimizer.scala:88,223) whatever the host
+        believes.  `result()` reads the combined loss and the summed count back (one sync)."""
         if self.world == 1 or self._g is None:
-            return int(iterations)
-        if self._iters_cache is None or exchange:
-            import torch.distributed as dist
-            gathered = [None] * self.world
-            dist.all_gather_object(gathered, int(iterations))
-            self._iters_cache = sum(gathered)
+            return
         self._epoch += 1
         N.check(N.lib().sb_group_average_device(self._g, self._epoch, int(iterations)))
-        return self._iters_cache
+
+    def result(self) -> Tuple[float, int]:
+        """(combined loss, summed iteration count) of the latest `average_async`; raises NativeError(SB_ERR_TIMEOUT) if a
+        peer never reached the barrier."""
+        loss, total = C.c_float(), C.c_int64()
+        N.check(N.lib().sb_group_read_result(self._g, C.byref(loss), C.byref(total)))
+        return float(loss.value), int(total.value)
 
     def _average_device(self, iterations: int) -> Tuple[float, int]:
-        total = self.average_async(iterations)
-        return self.engine.read_loss(), total
+        self.average_async(iterations)
+        return self.result()
 
     def close(self):
         if self._g is not None:
