@@ -266,7 +266,7 @@ def run_ours(args):
     if world > 1 and not args.no_parity:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         from multi_gpu_check import run_check
-        parity = [run_check(mode, rank, world, local_rank) for mode in ("spark_chain", "mean")]
+        parity = [run_check(mode, rank, world, local_rank, log=sys.stderr) for mode in ("spark_chain", "mean")]  # stdout: the JSON line only
 
     rows = ROWS_TOTAL // world
     steps_per_epoch = rows // BATCH

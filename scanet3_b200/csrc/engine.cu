@@ -504,6 +504,15 @@ static void plan_fusions(sb_engine* e) {
             if (shape == 331 || shape == 333) {
               e->L[ci].fuse_pool_fwd = li;
               L.skip_fwd = true;
+              // Winner map: when nothing but this pool (and the ReLU folded into its backward) ever reads the conv activations,
+              // the fused forward records one byte per pool output instead of storing them (SB_NO_POOL_MAP=1: the activation path)
+              const char* nm = getenv("SB_NO_POOL_MAP");
+              const bool relu_between = ci == li - 2;
+              if (!(nm && nm[0] == '1') && L.need_dx && pool22_map_ok(g) && (!relu_between || L.pool_relu_bwd)) {
+                void* mp = nullptr;
+                SB_CUDA(cudaMalloc(&mp, (size_t)g.N * g.OH * g.OW * g.C));
+                L.pool_map = (unsigned char*)mp;
+              }
             }
           }
         }
@@ -693,7 +702,7 @@ static void run_forward(sb_engine* e, int mode) {
         if (L.fast_smallk && L.fuse_pool_fwd >= 0) {
           LayerPlan& PLy = e->L[L.fuse_pool_fwd];
           Prof pr(e, "conv2d_smallk_pool_fwd", cbytes + 4.0 * (double)PLy.out.numel(), cflops);
-          if (conv_smallk_pool_fwd(in, P(e, L.p_w), out, e->acts[PLy.buf_out], g, L.fuse_relu_fwd, L.fused_thr, s)) break;
+          if (conv_smallk_pool_fwd(in, P(e, L.p_w), out, e->acts[PLy.buf_out], g, L.fuse_relu_fwd, L.fused_thr, PLy.pool_map, s)) break;
           SB_FAIL(SB_ERR_CUDA, "conv_smallk_pool_fwd rejected a planned shape");
         }
         if (L.fast_smallk) {
@@ -892,12 +901,12 @@ static void run_backward(sb_engine* e) {
           Prof pr(e, "pool_relu_bwd_conv_wgrad", 4.0 * ((double)L.in.numel() + n_out + CL.in.numel()),
                   2.0 * CL.cg.N * CL.cg.OH * CL.cg.OW * (double)CL.cg.Cout * CL.cg.KH * CL.cg.KW * CL.cg.Cin);
           if (pool_bwd_conv_wgrad(in, dout, din, L.pg, L.pool_relu_bwd, L.fused_thr, e->acts[CL.buf_in], CL.cg, G(e, CL.p_w), 0, e->ws,
-                                  e->ws_floats, s))
+                                  e->ws_floats, s, L.pool_map))
             break;
           SB_FAIL(SB_ERR_CUDA, "pool_bwd_conv_wgrad rejected a planned shape");
         }
         Prof pr(e, L.pool_relu_bwd ? "pool_relu_bwd" : "pool_bwd", 4.0 * (2.0 * L.in.numel() + 2.0 * n_out), 0);
-        if (L.fast_pool) pool_max_bwd_v4(in, dout, din, L.pg, L.pool_relu_bwd, L.fused_thr, s);
+        if (L.fast_pool) pool_max_bwd_v4(in, dout, din, L.pg, L.pool_relu_bwd, L.fused_thr, s, L.pool_map);
         else if (L.pool_relu_bwd) pool_bwd_relu(in, dout, din, L.pg, L.fused_thr, s);
         else pool_bwd(in, dout, din, L.pg, (L.d.pool_honor_reduce && L.d.pool_reduce == SB_POOL_AVG) ? SB_POOL_AVG : SB_POOL_MAX, s);
         break;
@@ -995,6 +1004,23 @@ static void run_train_step_body_staged(sb_engine* e, bool parity) {
   run_backward(e);
   run_reg(e, true);
   run_optimizer(e, 0);
+}
+
+// host-fed step whose batch is the one the DEVICE-side cursor (StepState.batch_idx) points at inside staging buffer `parity`: one
+// graph serves every slot, so the tail of an epoch (n_batches % stage_batches steps) needs no D2H in the compute stream; the
+// prologue files the previous step's loss in loss_hist[parity][cursor - 1] and the optimizer advances the cursor
+static void run_train_step_body_cursor(sb_engine* e, bool parity) {
+  const int par = parity ? 1 : 0;
+  {
+    Prof pr(e, "step_prologue", 8.0 * (double)(e->in_shape.numel() + e->label_shape.numel()), 0);
+    step_prologue(e->st, e->stage_x[par], e->stage_y[par], e->acts[0], e->by, e->in_shape.numel(), e->label_shape.numel(),
+                  e->train.beta1, e->train.beta2, 1, e->stream, e->loss_hist[par]);
+  }
+  run_forward(e, FWD_TRAIN);
+  run_loss(e, true);
+  run_backward(e);
+  run_reg(e, true);
+  run_optimizer(e, 1);
 }
 
 // `stage_batches` host-fed steps back to back (one graph): batch j comes from slot j of staging buffer `parity`
@@ -1126,7 +1152,7 @@ static void flush_pending_losses(sb_engine* e) {
   if (!e->pending_loss_host) return;
   const int par = e->pending_loss_par;
   SB_CUDA(cudaStreamWaitEvent(e->cstream, e->ev_free[par], 0));
-  SB_CUDA(cudaMemcpyAsync(e->pending_loss_host, e->loss_hist[par], (size_t)e->stage_batches * 4, cudaMemcpyDeviceToHost, e->cstream));
+  SB_CUDA(cudaMemcpyAsync(e->pending_loss_host, e->loss_hist[par], (size_t)e->pending_loss_n * 4, cudaMemcpyDeviceToHost, e->cstream));
   e->pending_loss_host = nullptr;
 }
 
@@ -1149,6 +1175,42 @@ static void launch_train_group_staged(sb_engine* e, const float* x, const float*
   if (losses_out_host) {
     e->pending_loss_host = losses_out_host;
     e->pending_loss_par = par;
+    e->pending_loss_n = G;
+  }
+}
+
+// r < stage_batches consecutive host batches (the tail of sb_train_batches_async): one H2D pair, r replays of the cursor-driven
+// single-step graph, one read-back of the r losses on the copy stream
+static void launch_train_tail_staged(sb_engine* e, const float* x, const float* y, int r, float* losses_out_host) {
+  ensure_staging(e);
+  const int par = e->stage_parity;
+  e->stage_parity ^= 1;
+  SB_CUDA(cudaStreamWaitEvent(e->cstream, e->ev_free[par], 0));
+  SB_CUDA(cudaMemcpyAsync(e->stage_x[par], x, (size_t)r * e->in_shape.numel() * 4, cudaMemcpyHostToDevice, e->cstream));
+  SB_CUDA(cudaMemcpyAsync(e->stage_y[par], y, (size_t)r * e->label_shape.numel() * 4, cudaMemcpyHostToDevice, e->cstream));
+  SB_CUDA(cudaEventRecord(e->ev_copied[par], e->cstream));
+  flush_pending_losses(e);
+  SB_CUDA(cudaStreamWaitEvent(e->stream, e->ev_copied[par], 0));
+  {  // cursor = 0; the device's step counter continues
+    static thread_local int slot = 0;
+    slot = (slot + 1) & 3;
+    StepState* h = e->st_host + slot;
+    h->batch_idx = 0;
+    SB_CUDA(cudaMemcpyAsync(&e->st->batch_idx, &h->batch_idx, sizeof(long long), cudaMemcpyHostToDevice, e->stream));
+  }
+  if (!e->g_cursor[par]) e->g_cursor[par] = capture(e, &e->nodes_cursor[par], run_train_step_body_cursor, par != 0);
+  for (int q = 0; q < r; ++q) {
+    SB_CUDA(cudaGraphLaunch(e->g_cursor[par], e->stream));
+    e->launches += e->nodes_cursor[par];
+  }
+  set_prewait_ok(0);  // a replayed graph may end in the optimizer
+  store_loss(e->st, e->loss_hist[par], e->stream, 1);
+  e->launches += 1;
+  SB_CUDA(cudaEventRecord(e->ev_free[par], e->stream));
+  if (losses_out_host) {
+    e->pending_loss_host = losses_out_host;
+    e->pending_loss_par = par;
+    e->pending_loss_n = r;
   }
 }
 
@@ -1330,6 +1392,7 @@ extern "C" void sb_engine_destroy(sb_engine* e) {
     for (int i = 0; i < 2; ++i) {
       if (e->g_staged[i]) cudaGraphExecDestroy(e->g_staged[i]);
       if (e->g_group[i]) cudaGraphExecDestroy(e->g_group[i]);
+      if (e->g_cursor[i]) cudaGraphExecDestroy(e->g_cursor[i]);
       cudaFree(e->stage_x[i]); cudaFree(e->stage_y[i]); cudaFree(e->loss_hist[i]);
       if (e->ev_copied[i]) cudaEventDestroy(e->ev_copied[i]);
       if (e->ev_free[i]) cudaEventDestroy(e->ev_free[i]);
@@ -1339,7 +1402,7 @@ extern "C" void sb_engine_destroy(sb_engine* e) {
     tc_free_layers(e);
     rnn_free(e);
     lstm_free(e);
-    for (auto& L : e->L) { cudaFree(L.bn_save_mean); cudaFree(L.bn_save_var); }
+    for (auto& L : e->L) { cudaFree(L.bn_save_mean); cudaFree(L.bn_save_var); cudaFree(L.pool_map); }
     for (float* p : e->acts) cudaFree(p);
     for (float* p : e->dacts) cudaFree(p);
     cudaFree(e->arena); cudaFree(e->grads); cudaFree(e->by); cudaFree(e->ds_x); cudaFree(e->ds_y);
@@ -1515,8 +1578,11 @@ extern "C" int sb_warm(sb_engine* e, int what) {
         if (!e->g_staged[par]) e->g_staged[par] = capture(e, &e->nodes_staged[par], run_train_step_body_staged, par != 0);
         if (e->stage_batches > 1 && !e->g_group[par])
           e->g_group[par] = capture(e, &e->nodes_group[par], run_train_group_body_staged, par != 0);
+        if (e->stage_batches > 1 && !e->g_cursor[par])
+          e->g_cursor[par] = capture(e, &e->nodes_cursor[par], run_train_step_body_cursor, par != 0);
         upload(e->g_staged[par]);
         upload(e->g_group[par]);
+        upload(e->g_cursor[par]);
       }
     }
   } catch (...) {
@@ -1595,6 +1661,10 @@ extern "C" int sb_train_batches_async(sb_engine* e, const float* x, const float*
   if (use_graph(e) && e->stage_batches > 1)
     for (; j + e->stage_batches <= n_batches; j += e->stage_batches)
       launch_train_group_staged(e, x + j * xn, y + j * yn, losses_out_host ? losses_out_host + j : nullptr);
+  if (use_graph(e) && e->stage_batches > 1 && j < n_batches) {  // the tail: fewer than a group's worth of batches
+    launch_train_tail_staged(e, x + j * xn, y + j * yn, (int)(n_batches - j), losses_out_host ? losses_out_host + j : nullptr);
+    j = n_batches;
+  }
   flush_pending_losses(e);
   for (; j < n_batches; ++j) {
     launch_train_step_staged(e, x + j * xn, y + j * yn);

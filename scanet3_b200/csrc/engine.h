@@ -64,6 +64,9 @@ struct LayerPlan {
   float fused_thr = 0.f;
   int fuse_conv_wgrad = -1;       // Pool2D: its backward also computes the filter gradient of this (small-K) conv layer
   int fuse_pool_fwd = -1;         // Conv2D (small K): its forward kernel also produces this Pool2D layer's output
+  unsigned char* pool_map = nullptr;  // Pool2D (2x2 stride 1) whose forward is fused into the producing conv: one winner byte per
+                                      // output and channel (first-max index | ReLU bit); the backward routes dy with it and the
+                                      // conv activations are neither written nor read
   bool wgrad_in_pool = false;     // Conv2D: the filter gradient is produced by the following pool's backward kernel
   bool fuse_act_bwd = false;      // Bias: also applies the backward of the in-place activation that follows (one pass)
   bool head_skip = false;         // Bias / Softmax of the fused classifier head: executed by the head kernel when training
@@ -143,6 +146,9 @@ struct sb_engine {
   float* loss_hist[2] = {nullptr, nullptr};  // per staging buffer: pre-update losses of the group's steps
   float* pending_loss_host = nullptr;        // read-back of the latest group, queued behind the NEXT group's H2D copy
   int pending_loss_par = 0;
+  int pending_loss_n = 0;
+  cudaGraphExec_t g_cursor[2] = {nullptr, nullptr};  // one host-fed step taking its batch through the device-side cursor (epoch tails)
+  long long nodes_cursor[2] = {0, 0};
   int stage_parity = 0;
   cudaGraphExec_t g_resident = nullptr, g_hostfed = nullptr, g_loss = nullptr;
   cudaGraphExec_t g_resident_multi = nullptr;  // kStepsPerGraph resident steps in one graph (fewer graph boundaries per epoch)

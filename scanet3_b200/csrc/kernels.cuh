@@ -47,7 +47,8 @@ void step_prologue(StepState* st, const float* ds_x, const float* ds_y, float* b
                    long long y_per_batch, float beta1, float beta2, int batch_from_state, cudaStream_t s,
                    float* prev_loss_slot = nullptr);
 
-void store_loss(const StepState* st, float* slot, cudaStream_t s);  // *slot = st->loss (last step of a host-fed group)
+// *slot = st->loss (last step of a host-fed group); by_cursor: slot[st->batch_idx - 1] = st->loss
+void store_loss(const StepState* st, float* slot, cudaStream_t s, int by_cursor = 0);
 
 // ---- fp32 FFMA contractions (parity mode; also the shapes tcgen05 does not fit) ----
 // C[M,N] = A[M,K] . B[K,N]
@@ -118,16 +119,22 @@ void philox_fill(float* p, long long n, unsigned long long seed, int normal, flo
 namespace sb {
 // ---- kernels_fast.cu: vectorised / fused variants (return false when the shape is not covered) ----
 void pool_max_fwd_v4(const float* x, float* y, const PoolGeom& g, cudaStream_t s);
-void pool_max_bwd_v4(const float* x, const float* dy, float* dx, const PoolGeom& g, int relu, float thr, cudaStream_t s);
+// map != null (2x2 stride-1 pools whose forward recorded winner bytes): routed by the map, x is not read
+void pool_max_bwd_v4(const float* x, const float* dy, float* dx, const PoolGeom& g, int relu, float thr, cudaStream_t s,
+                     const unsigned char* map = nullptr);
+bool pool22_map_ok(const PoolGeom& g);  // the winner-map kernels cover this pool geometry
 // 2x2 stride-1 max-pool backward (+ReLU mask) that also accumulates the filter gradient of the small-K Conv2D feeding the pool
 // (conv >> [in-place ReLU] >> pool); dx is written only when store_dx.  false: shape not covered
 bool pool_bwd_conv_wgrad(const float* x, const float* dy, float* dx, const PoolGeom& g, int relu, float thr, const float* conv_in,
-                         const ConvGeom& cg, float* dw, int store_dx, float* ws, size_t ws_floats, cudaStream_t s);
+                         const ConvGeom& cg, float* dw, int store_dx, float* ws, size_t ws_floats, cudaStream_t s,
+                         const unsigned char* map = nullptr);
 void conv_smallk_fwd(const float* x, const float* w, float* y, const ConvGeom& g, int relu, float thr, cudaStream_t s);
 // conv (small K, stride 1) >> [ReLU] >> max-pool 2x2 stride 1 VALID: y = the (activated) conv output, pooled = the pool output.
 // false: shape not covered
+// map != null: one winner byte per pool output and channel (index of the first maximum | ReLU bit) is stored INSTEAD of y -- all the
+// backward pass needs from the conv activations (pool_max_bwd_v4 / pool_bwd_conv_wgrad with the same map)
 bool conv_smallk_pool_fwd(const float* x, const float* w, float* y, float* pooled, const ConvGeom& g, int relu, float thr,
-                          cudaStream_t s);
+                          unsigned char* map, cudaStream_t s);
 bool conv_smallk_wgrad(const float* x, const float* dy, float* dw, const ConvGeom& g, float* ws, size_t ws_floats, cudaStream_t s);
 bool dense_skinny_fwd(const float* x, const float* w, float* z, int M, int N, int K, float* ws, size_t ws_floats, cudaStream_t s);
 // split-K partials only (partial[chunks][M][N]); the consumer (head kernel or partial_reduce) sums them in chunk order

@@ -15,6 +15,24 @@ __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float4 max4(float4 a, float4 b) { return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w)); }
 
+// Winner byte of a 2x2 max-pool window (members a b / c d in row-major order): bits 0-1 = index of the FIRST maximum (a later
+// member displaces an earlier one only when strictly greater -- TF's MaxPoolGrad rule, pinned by math/nn/KernelsSpec.scala:277-288),
+// bit 2 = the maximum passes the preceding ReLU (max > thr; always set without a ReLU).  The backward pass routes dy with this
+// byte alone: it never re-reads the activations.
+__device__ __forceinline__ unsigned win4(float a, float b, float c, float d, int relu, float thr, float* mx) {
+  float best = a;
+  unsigned idx = 0;
+  if (b > best) { best = b; idx = 1; }
+  if (c > best) { best = c; idx = 2; }
+  if (d > best) { best = d; idx = 3; }
+  *mx = best;
+  return idx | ((!relu || best > thr) ? 4u : 0u);
+}
+// 0xff in every byte lane of `m` whose winner byte routes to member `idx` (with the ReLU bit set when relu)
+__device__ __forceinline__ unsigned take4(unsigned m, unsigned idx, int relu) {
+  return relu ? __vcmpeq4(m, 0x01010101u * (idx | 4u)) : __vcmpeq4(m & 0x03030303u, 0x01010101u * idx);
+}
+
 static int grid_for(long long n, int threads) {
   long long b = (n + threads - 1) / threads;
   if (b < 1) b = 1;
@@ -321,6 +339,137 @@ __global__ void __launch_bounds__(128, (WG == 331 ? 4 : 1)) pool22_bwd_strip_ker
     }
   }
 }
+// The same walk driven by the forward pass's winner bytes (win4) instead of the activations: column w loads the dy and the map
+// word of the two windows anchored in column w (4 loads, no activation rows) and keeps column w-1's in registers; element (h, w)
+// takes the dy of window (h-1,w-1) iff that window's winner is its member 3 (bottom-right), of (h-1,w) iff member 2, of (h,w-1)
+// iff member 1, of (h,w) iff member 0 -- and, under a ReLU, only when the winner passed it (bit 2).  Same summation order as
+// the activation-driven kernels, hence the same bits.
+template <int WG>
+__global__ void __launch_bounds__(128, (WG == 331 ? 4 : 1)) pool22_bwd_map_kernel(const unsigned* __restrict__ map, const float* __restrict__ dy,
+                                                               float* __restrict__ dx, PoolGeom g, int relu, int seg_len,
+                                                               int segs, long long n_threads, PoolWgradFuse wf) {
+  pdl_prologue_trigger();
+  constexpr int KH = WG / 100, KW = (WG / 10) % 10, CIN = WG % 10, K = KH * KW * CIN;
+  const int C4 = g.C >> 2;
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;  // 32-bit index split (the launcher keeps n_threads < 2^31)
+  const int c4 = (int)(i % (unsigned)C4);
+  unsigned t = i / (unsigned)C4;
+  const int seg = (int)(t % (unsigned)segs); t /= (unsigned)segs;
+  const int h = (int)(t % (unsigned)g.H);
+  const int b = (int)(t / (unsigned)g.H);
+  const int w0 = seg * seg_len;
+  const int w1 = min(w0 + seg_len, g.W);
+  const bool active = (long long)i < n_threads && w0 < w1;
+  float4 dwacc[K > 0 ? K : 1];
+  if (WG) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) dwacc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (active) {
+    const bool top_ok = h >= 1, bot_ok = h <= g.H - 2;  // window rows h-1 and h exist
+    const float* dt = dy + (((long long)b * g.OH + (top_ok ? h - 1 : 0)) * g.OW) * g.C + c4 * 4;
+    const float* db = dy + (((long long)b * g.OH + (bot_ok ? h : 0)) * g.OW) * g.C + c4 * 4;
+    const unsigned* mt = map + (((long long)b * g.OH + (top_ok ? h - 1 : 0)) * g.OW) * C4 + c4;
+    const unsigned* mb = map + (((long long)b * g.OH + (bot_ok ? h : 0)) * g.OW) * C4 + c4;
+    float* dxo = dx + (((long long)b * g.H + h) * g.W) * g.C + c4 * 4;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    // windows anchored in column w-1: dy and winner words of the rows h-1 (t) and h (b); 0xffffffff routes nothing
+    float4 pgt = zero, pgb = zero;
+    unsigned pmt = 0xffffffffu, pmb = 0xffffffffu;
+    if (w0 >= 1) {
+      const int o = (w0 - 1) * g.C, om = (w0 - 1) * C4;
+      if (top_ok) { pgt = ld4(dt + o); pmt = __ldg(mt + om); }
+      if (bot_ok) { pgb = ld4(db + o); pmb = __ldg(mb + om); }
+    }
+    float xw[KH > 0 ? KH : 1][KW > 0 ? KW : 1][CIN > 0 ? CIN : 1];
+    auto load_col = [&](int col_in, int slot) {
+#pragma unroll
+      for (int a = 0; a < KH; ++a) {
+        const int ih = h + a - wf.PT;
+        const bool ok = ih >= 0 && ih < wf.Hin && col_in >= 0 && col_in < wf.Win;
+        const float* p = wf.xin + (((long long)b * wf.Hin + (ok ? ih : 0)) * wf.Win + (ok ? col_in : 0)) * CIN;
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) xw[a][slot][ci] = ok ? __ldg(p + ci) : 0.f;
+      }
+    };
+    if (WG) {
+#pragma unroll
+      for (int bb = 0; bb + 1 < KW; ++bb) load_col(w0 - wf.PL + bb, bb + 1);  // shifted into place by the first iteration
+    }
+    const float *dtw = dt + w0 * g.C, *dbw = db + w0 * g.C;
+    const unsigned *mtw = mt + w0 * C4, *mbw = mb + w0 * C4;
+    float* dxw = dxo + w0 * g.C;
+#pragma unroll 2
+    for (int w = w0; w < w1; ++w) {
+      float4 gt = zero, gb = zero;
+      unsigned wt = 0xffffffffu, wb = 0xffffffffu;
+      if (w <= g.W - 2) {  // windows anchored in column w exist
+        if (top_ok) { gt = ld4(dtw); wt = __ldg(mtw); }
+        if (bot_ok) { gb = ld4(dbw); wb = __ldg(mbw); }
+      }
+      dtw += g.C; dbw += g.C; mtw += C4; mbw += C4;
+      const unsigned e3 = take4(pmt, 3u, relu), e2 = take4(wt, 2u, relu), e1 = take4(pmb, 1u, relu), e0 = take4(wb, 0u, relu);
+      float4 acc = zero;
+#define SB_WIN(c, sh)                                            \
+  if (e3 & (0xffu << sh)) acc.c = __fadd_rn(acc.c, pgt.c);       \
+  if (e2 & (0xffu << sh)) acc.c = __fadd_rn(acc.c, gt.c);        \
+  if (e1 & (0xffu << sh)) acc.c = __fadd_rn(acc.c, pgb.c);       \
+  if (e0 & (0xffu << sh)) acc.c = __fadd_rn(acc.c, gb.c);
+      SB_WIN(x, 0) SB_WIN(y, 8) SB_WIN(z, 16) SB_WIN(w, 24)
+#undef SB_WIN
+      if (!WG || wf.store_dx) st4(dxw, acc);
+      dxw += g.C;
+      if (WG) {
+#pragma unroll
+        for (int a = 0; a < KH; ++a)
+#pragma unroll
+          for (int bb = 0; bb + 1 < KW; ++bb)
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) xw[a][bb][ci] = xw[a][bb + 1][ci];
+        load_col(w - wf.PL + KW - 1, KW - 1);
+#pragma unroll
+        for (int a = 0; a < KH; ++a)
+#pragma unroll
+          for (int bb = 0; bb < KW; ++bb)
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) {
+              const float xv = xw[a][bb][ci];
+              float4& r = dwacc[(a * KW + bb) * CIN + ci];
+              r.x = fmaf(xv, acc.x, r.x); r.y = fmaf(xv, acc.y, r.y); r.z = fmaf(xv, acc.z, r.z); r.w = fmaf(xv, acc.w, r.w);
+            }
+      }
+      pgt = gt; pgb = gb; pmt = wt; pmb = wb;
+    }
+  }
+  if (WG) {
+    // CTA-level sum in a fixed order: lanes with the same channel quad inside a warp (xor C4, 2*C4, ..), then the warps
+    extern __shared__ __align__(16) float4 red[];  // [nwarps][K][C4]
+    const int wl = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int cq = threadIdx.x % C4;  // == c4 when C4 divides the CTA size (checked by the launcher)
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+      for (int o = C4; o < 32; o <<= 1) {
+        dwacc[k].x = __fadd_rn(dwacc[k].x, __shfl_xor_sync(0xffffffffu, dwacc[k].x, o));
+        dwacc[k].y = __fadd_rn(dwacc[k].y, __shfl_xor_sync(0xffffffffu, dwacc[k].y, o));
+        dwacc[k].z = __fadd_rn(dwacc[k].z, __shfl_xor_sync(0xffffffffu, dwacc[k].z, o));
+        dwacc[k].w = __fadd_rn(dwacc[k].w, __shfl_xor_sync(0xffffffffu, dwacc[k].w, o));
+      }
+    if (wl < C4) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) red[(wid * K + k) * C4 + cq] = dwacc[k];
+    }
+    __syncthreads();
+    float* part = wf.partial + (size_t)blockIdx.x * K * g.C;
+    for (int q = threadIdx.x; q < K * C4; q += blockDim.x) {
+      float4 tot = red[q];
+      for (int wq = 1; wq < nwarps; ++wq) {
+        const float4 v = red[wq * K * C4 + q];
+        tot.x = __fadd_rn(tot.x, v.x); tot.y = __fadd_rn(tot.y, v.y); tot.z = __fadd_rn(tot.z, v.z); tot.w = __fadd_rn(tot.w, v.w);
+      }
+      st4(part + (q / C4) * g.C + (q % C4) * 4, tot);
+    }
+  }
+}
 // segments per row: cost ~ whole waves x (columns per thread + prologue columns); a wave = what 148 SMs hold at the kernel's
 // register footprint.  The prologue (index split, pointer setup, the column before the segment) costs ~2.5 columns of the walk
 // (SASS: 315 instructions against 119 per column): LeNet's pool2 backward (23 columns) then takes 2 segments in one wave instead
@@ -342,7 +491,8 @@ static void pool22_segments(const PoolGeom& g, int ctas_per_sm, int* segs_out, i
 static bool pool_is_22s1(const PoolGeom& g);
 // max-pool backward (+ReLU mask) with the filter gradient of the preceding small-K conv: returns false when not covered
 bool pool_bwd_conv_wgrad(const float* x, const float* dy, float* dx, const PoolGeom& g, int relu, float thr, const float* conv_in,
-                         const ConvGeom& cg, float* dw, int store_dx, float* ws, size_t ws_floats, cudaStream_t s) {
+                         const ConvGeom& cg, float* dw, int store_dx, float* ws, size_t ws_floats, cudaStream_t s,
+                         const unsigned char* map) {
   const int C4 = g.C / 4, shape = cg.KH * 100 + cg.KW * 10 + cg.Cin;
   if (!pool_is_22s1(g) || (g.C & 3) || C4 > 32 || (C4 & (C4 - 1)) || cg.SH != 1 || cg.SW != 1) return false;
   if (cg.OH != g.H || cg.OW != g.W || cg.Cout != g.C || cg.N != g.N) return false;
@@ -356,6 +506,15 @@ bool pool_bwd_conv_wgrad(const float* x, const float* dy, float* dx, const PoolG
   if ((size_t)blocks * K * g.C > ws_floats) return false;
   const size_t smem = (size_t)4 * K * C4 * sizeof(float4);
   PoolWgradFuse wf{conv_in, ws, cg.H, cg.W, cg.PT, cg.PL, store_dx};
+  if (map) {  // routed by the forward pass's winner bytes: the activations are not read (and were never written)
+#define SB_POOL_MAP(S) \
+  launch_k(pool22_bwd_map_kernel<S>, blocks, 128, smem, s, (const unsigned*)map, dy, dx, g, relu, seg_len, segs, nt, wf)
+    if (shape == 331) SB_POOL_MAP(331); else if (shape == 333) SB_POOL_MAP(333); else SB_POOL_MAP(551);
+#undef SB_POOL_MAP
+    SB_LAUNCHED();
+    partial_reduce(ws, dw, K * g.C, blocks, s);
+    return true;
+  }
 #define SB_POOL_WG(R, S) \
   launch_k(pool22_bwd_strip_kernel<R, S>, blocks, 128, smem, s, x, dy, dx, g, thr, seg_len, segs, nt, wf)
   if (relu) {
@@ -368,12 +527,21 @@ bool pool_bwd_conv_wgrad(const float* x, const float* dy, float* dx, const PoolG
   partial_reduce(ws, dw, K * g.C, blocks, s);
   return true;
 }
-void pool_max_bwd_v4(const float* x, const float* dy, float* dx, const PoolGeom& g, int relu, float thr, cudaStream_t s) {
+bool pool22_map_ok(const PoolGeom& g) {
+  return pool_is_22s1(g) && (g.C & 3) == 0 && (long long)g.N * g.H * 8 * (g.C / 4) < (1LL << 31);
+}
+void pool_max_bwd_v4(const float* x, const float* dy, float* dx, const PoolGeom& g, int relu, float thr, cudaStream_t s,
+                     const unsigned char* map) {
   if (pool_is_22s1(g) && (long long)g.N * g.H * 8 * (g.C / 4) < (1LL << 31)) {  // <= 8 segments; 32-bit thread index in the kernel
     int segs, seg_len;
     pool22_segments(g, 5, &segs, &seg_len);
     const long long nt = (long long)g.N * g.H * segs * (g.C / 4);
     PoolWgradFuse none{};
+    if (map) {
+      launch_k(pool22_bwd_map_kernel<0>, (int)((nt + 127) / 128), 128, 0, s, (const unsigned*)map, dy, dx, g, relu, seg_len, segs, nt, none);
+      SB_LAUNCHED();
+      return;
+    }
     if (relu) launch_k(pool22_bwd_strip_kernel<true, 0>, (int)((nt + 127) / 128), 128, 0, s, x, dy, dx, g, thr, seg_len, segs, nt, none);
     else launch_k(pool22_bwd_strip_kernel<false, 0>, (int)((nt + 127) / 128), 128, 0, s, x, dy, dx, g, 0.f, seg_len, segs, nt, none);
     SB_LAUNCHED();
@@ -495,11 +663,13 @@ static void launch_smallk_tile(const float* x, const float* w, float* y, const C
 // row pr, i.e. the conv outputs of rows pr, pr+1 and columns ow0 .. ow0+PW.  It stores its own conv row (the backward needs the
 // activations: ReLU mask and pool arg-max) and the pooled row; conv row pr+1 is recomputed by the thread below with the same FMA
 // order, so the stored activation and the pooled maximum are the same bits.  The conv output is never re-read.
-template <int KH, int KW, int CIN, int PW>
+// MAP: instead of the conv activations the kernel stores one winner byte per pool output (win4) -- everything the backward pass
+// needs from them -- so the conv output is never written at all.
+template <int KH, int KW, int CIN, int PW, bool MAP>
 __global__ void __launch_bounds__(256) conv_smallk_pool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                    float* __restrict__ y, float* __restrict__ pooled, ConvGeom g,
                                                                    int relu, float thr, int segs, long long n_threads,
-                                                                   int prewait) {
+                                                                   int prewait, unsigned* __restrict__ map) {
   constexpr int K = KH * KW * CIN;
   const int C4 = g.Cout >> 2;
   extern __shared__ __align__(16) float swt[];  // filter [K][Cout]
@@ -587,6 +757,22 @@ __global__ void __launch_bounds__(256) conv_smallk_pool_fwd_kernel(const float* 
       if (relu) { o.x = fmaxf(thr, o.x); o.y = fmaxf(thr, o.y); o.z = fmaxf(thr, o.z); o.w = fmaxf(thr, o.w); }
       out[r][p] = o;
     }
+  float* po = pooled + (((long long)b * OHp + pr) * OWp + ow0) * g.Cout + c4 * 4;
+  if (MAP) {
+    unsigned* mo = map + (((long long)b * OHp + pr) * OWp + ow0) * C4 + c4;  // one byte per channel: a 32-bit word per quad
+#pragma unroll
+    for (int p = 0; p < PW; ++p) {
+      if (ow0 + p >= OWp) break;
+      float4 m;
+      const unsigned b0 = win4(out[0][p].x, out[0][p + 1].x, out[1][p].x, out[1][p + 1].x, relu, thr, &m.x);
+      const unsigned b1 = win4(out[0][p].y, out[0][p + 1].y, out[1][p].y, out[1][p + 1].y, relu, thr, &m.y);
+      const unsigned b2 = win4(out[0][p].z, out[0][p + 1].z, out[1][p].z, out[1][p + 1].z, relu, thr, &m.z);
+      const unsigned b3 = win4(out[0][p].w, out[0][p + 1].w, out[1][p].w, out[1][p + 1].w, relu, thr, &m.w);
+      st4(po + p * g.Cout, m);
+      mo[p * C4] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+    }
+    return;
+  }
   // the conv activations: own row, and the last conv row from the last pool row
   const int rows_out = pr == OHp - 1 ? 2 : 1;
   for (int r = 0; r < rows_out; ++r) {
@@ -595,7 +781,6 @@ __global__ void __launch_bounds__(256) conv_smallk_pool_fwd_kernel(const float* 
     for (int p = 0; p < PW; ++p)
       if (ow0 + p < g.OW) st4(yo + p * g.Cout, out[r][p]);
   }
-  float* po = pooled + (((long long)b * OHp + pr) * OWp + ow0) * g.Cout + c4 * 4;
 #pragma unroll
   for (int p = 0; p < PW; ++p) {
     if (ow0 + p >= OWp) break;
@@ -609,21 +794,26 @@ __global__ void __launch_bounds__(256) conv_smallk_pool_fwd_kernel(const float* 
 }
 template <int KH, int KW, int CIN>
 static void launch_smallk_pool(const float* x, const float* w, float* y, float* pooled, const ConvGeom& g, int relu, float thr,
-                               cudaStream_t s) {
+                               unsigned char* map, cudaStream_t s) {
   constexpr int PW = 4;
   const int segs = (g.OW + PW - 1) / PW;  // covers the conv columns; the pool columns are one fewer
   const long long nt = (long long)g.N * (g.OH - 1) * segs * (g.Cout / 4);
   const size_t smem = (size_t)KH * KW * CIN * g.Cout * sizeof(float);
-  launch_k(conv_smallk_pool_fwd_kernel<KH, KW, CIN, PW>, (int)((nt + 255) / 256), 256, smem, s, x, w, y, pooled, g, relu, thr, segs, nt,
-           prewait_ok());
+  if (map)
+    launch_k(conv_smallk_pool_fwd_kernel<KH, KW, CIN, PW, true>, (int)((nt + 255) / 256), 256, smem, s, x, w, y, pooled, g, relu, thr,
+             segs, nt, prewait_ok(), (unsigned*)map);
+  else
+    launch_k(conv_smallk_pool_fwd_kernel<KH, KW, CIN, PW, false>, (int)((nt + 255) / 256), 256, smem, s, x, w, y, pooled, g, relu, thr,
+             segs, nt, prewait_ok(), (unsigned*)nullptr);
   SB_LAUNCHED();
 }
-bool conv_smallk_pool_fwd(const float* x, const float* w, float* y, float* pooled, const ConvGeom& g, int relu, float thr, cudaStream_t s) {
+bool conv_smallk_pool_fwd(const float* x, const float* w, float* y, float* pooled, const ConvGeom& g, int relu, float thr,
+                          unsigned char* map, cudaStream_t s) {
   if (g.SH != 1 || g.SW != 1 || g.OH < 2 || g.OW < 2 || g.Cout % 4) return false;
   if ((long long)g.N * g.OH * g.OW * g.Cout >= (1LL << 31)) return false;  // 32-bit thread index and in-row offsets in the kernel
   const int shape = g.KH * 100 + g.KW * 10 + g.Cin;
-  if (shape == 331) { launch_smallk_pool<3, 3, 1>(x, w, y, pooled, g, relu, thr, s); return true; }
-  if (shape == 333) { launch_smallk_pool<3, 3, 3>(x, w, y, pooled, g, relu, thr, s); return true; }
+  if (shape == 331) { launch_smallk_pool<3, 3, 1>(x, w, y, pooled, g, relu, thr, map, s); return true; }
+  if (shape == 333) { launch_smallk_pool<3, 3, 3>(x, w, y, pooled, g, relu, thr, map, s); return true; }
   return false;
 }
 

@@ -30,7 +30,12 @@ __global__ void step_prologue_kernel(StepState* st, const V* __restrict__ ds_x, 
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    if (prev_loss_slot) *prev_loss_slot = st->loss;
+    // the loss of the step BEFORE this one (steps chained on the device): a fixed slot, or -- batches taken by the device-side
+    // cursor -- the slot of the previous batch
+    if (prev_loss_slot) {
+      if (!batch_from_state) *prev_loss_slot = st->loss;
+      else if (b > 0) prev_loss_slot[b - 1] = st->loss;
+    }
     // t = globalIter + localIter + 1, fed as int32 and cast to float (optimizers/Optimizer.scala:143);
     // boost(x, rate, t) = x / (1 - rate^float(t)) (math/alg/AllKernels.scala:546-549).  The power is
     // evaluated in double and rounded once, i.e. the correctly rounded powf TF-CPU (glibc) returns.
@@ -64,12 +69,13 @@ void step_prologue(StepState* st, const float* ds_x, const float* ds_y, float* b
   SB_LAUNCHED();
 }
 
-__global__ void store_loss_kernel(const StepState* __restrict__ st, float* __restrict__ slot) {
+__global__ void store_loss_kernel(const StepState* __restrict__ st, float* __restrict__ slot, int by_cursor) {
   pdl_prologue();
-  *slot = st->loss;
+  if (!by_cursor) *slot = st->loss;
+  else if (st->batch_idx > 0) slot[st->batch_idx - 1] = st->loss;  // the batch the device-side cursor just left
 }
-void store_loss(const StepState* st, float* slot, cudaStream_t s) {
-  launch_k(store_loss_kernel, 1, 1, 0, s, st, slot);
+void store_loss(const StepState* st, float* slot, cudaStream_t s, int by_cursor) {
+  launch_k(store_loss_kernel, 1, 1, 0, s, st, slot, by_cursor);
   SB_LAUNCHED();
 }
 

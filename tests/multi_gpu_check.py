@@ -21,7 +21,7 @@ from scanet3_b200 import _native as N  # noqa: E402
 from scanet3_b200.distributed import RankAverager, init_process_group_from_env  # noqa: E402
 
 
-def run_check(mode, rank, world, local):
+def run_check(mode, rank, world, local, log=None):
     """3 epochs of a small MLP over `world` shards, averaged at every epoch boundary through RankAverager (the very path
     bench.py and the host runtime use); rank 0 compares with the oracle's k-partition run.  -> dict on every rank."""
     spec = [("dense", 16, "sigmoid"), ("dense", 4, "softmax")]
@@ -55,7 +55,7 @@ def run_check(mode, rank, world, local):
             ok = ok and np.allclose(got[k2], v, rtol=1e-3, atol=2e-5)
             max_rel = max(max_rel, float(np.max(np.abs(got[k2] - v) / (np.abs(v) + 1e-3))))
         print(f"MULTI_GPU_CHECK world={world} mode={mode} {'OK' if ok else 'MISMATCH'} max_rel_err={max_rel:.2e} hist={hist} "
-              f"oracle={ohist}", flush=True)
+              f"oracle={ohist}", flush=True, file=log or sys.stdout)
     # every rank must end up with identical parameters
     t = torch.from_numpy(np.concatenate([v.ravel() for v in got.values()])).cuda()
     ref = t.clone()

@@ -653,3 +653,26 @@ def test_avg_pool_goldens_and_trajectory():
             ("conv", 6, "tanh", (2, 2), (1, 1), "Valid", True), ("pool", (2, 2), (1, 1), "Valid", "Avg"), ("flatten",),
             ("dense", 5, "softmax")]
     run_trajectory(spec, "cce", "adam", dict(rate=0.01), batch=6, in_shape=(9, 8, 2), classes=5, steps=8)
+
+
+@pytest.mark.parametrize("prec", [S.PREC_FP32, S.PREC_TF32], ids=["fp32", "tf32"])
+def test_winner_map_path_is_bit_identical_to_the_activation_path(prec, monkeypatch):
+    """conv >> ReLU >> Pool2D(2x2, stride 1) blocks: the forward records one winner byte per pool output instead of the conv
+    activations and the backward routes dy with it (kernels_fast.cu win4 / pool22_bwd_map_kernel; the tensor-core conv's pooled
+    epilogue in TF32 mode).  Loss, every gradient and the updated parameters must be the SAME BITS as with SB_NO_POOL_MAP=1."""
+    _, sm = build_models(LENET)
+    x, y = synth_classification(12, (14, 14, 1), 10, 21)
+    outs = []
+    for off in ("1", "0"):
+        monkeypatch.setenv("SB_NO_POOL_MAP", off)
+        e = make_engine(sm, S.CategoricalCrossentropy, S.Adam(0.001), 12, (14, 14, 1), (10,), precision=prec)
+        e.init_params()
+        loss, grads = e.compute_grads(x, y)
+        l1 = e.train_step(x, y, 1)
+        l2 = e.train_step(x, y, 2)
+        outs.append((loss, l1, l2, {k: v.tobytes() for k, v in grads.items()}, {k: v.tobytes() for k, v in e.get_params().items()}))
+        e.close()
+    assert outs[0][:3] == outs[1][:3]
+    for k in outs[0][3]:
+        assert outs[0][3][k] == outs[1][3][k], f"gradient {k} differs"
+    assert outs[0][4] == outs[1][4]

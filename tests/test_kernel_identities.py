@@ -112,3 +112,63 @@ def test_vector_row_loads_of_the_fused_conv_cover_exactly_the_in_row_columns():
                 lo = [ow0 + j for j in range(4)] if ow0 + 4 <= W else [None] * 4
                 hi = [ow0 + 4 + j for j in range(4)] if ow0 + 8 <= W else [None] * 4
                 assert (lo + hi)[:7] == scalar, (W, pad_right, seg)
+
+
+def win4(p, relu, thr):
+    """kernels_fast.cu `win4`: winner byte of a window = index of the first maximum | (passes the ReLU) << 2"""
+    k = first_max_position(*p)
+    return k | (4 if (not relu or p[k] > thr) else 0)
+
+
+def vcmpeq4(a, b):
+    out = 0
+    for s in (0, 8, 16, 24):
+        if (a >> s) & 0xFF == (b >> s) & 0xFF:
+            out |= 0xFF << s
+    return out
+
+
+def take4(m, idx, relu):
+    """kernels_fast.cu `take4`: per-byte routing test on a packed word of four channels' winner bytes"""
+    return vcmpeq4(m, 0x01010101 * (idx | 4)) if relu else vcmpeq4(m & 0x03030303, 0x01010101 * idx)
+
+
+@pytest.mark.parametrize("relu", [False, True])
+def test_winner_map_routing_matches_the_oracle_pool_and_relu_gradient(relu):
+    """pool22_bwd_map_kernel restated: the forward records win4 per window, the backward routes dy with take4 on packed words
+    (0xffffffff = no window) in the order (h-1,w-1), (h-1,w), (h,w-1), (h,w) -- against the oracle's MaxPoolGrad followed by
+    the ReLU gradient, on a tie-heavy post-ReLU map"""
+    from oracle.layers import pool2d_grad
+    rng = np.random.Generator(np.random.PCG64(11))
+    thr = 0.0
+    z = rng.integers(-3, 4, size=(2, 6, 7, 4)).astype(np.float32)
+    x = np.maximum(z, thr) if relu else z
+    dy = rng.standard_normal((2, 5, 6, 4)).astype(np.float32)
+    ref = pool2d_grad(x, dy, (2, 2), (1, 1), "valid")
+    if relu:
+        ref = ref * (x > thr)
+    N, H, W, C = x.shape
+    words = np.zeros((N, H - 1, W - 1), dtype=np.uint64)
+    for n in range(N):
+        for h in range(H - 1):
+            for w in range(W - 1):
+                word = 0
+                for c in range(4):
+                    p = (x[n, h, w, c], x[n, h, w + 1, c], x[n, h + 1, w, c], x[n, h + 1, w + 1, c])
+                    word |= win4(p, relu, thr) << (8 * c)
+                words[n, h, w] = word
+    got = np.zeros_like(x)
+    for n in range(N):
+        for h in range(H):
+            for w in range(W):
+                acc = [np.float32(0)] * 4
+                for (wh, ww, pos) in ((h - 1, w - 1, 3), (h - 1, w, 2), (h, w - 1, 1), (h, w, 0)):
+                    ok = 0 <= wh < H - 1 and 0 <= ww < W - 1
+                    m = int(words[n, wh, ww]) if ok else 0xFFFFFFFF
+                    g = dy[n, wh, ww] if ok else np.zeros(4, np.float32)
+                    e = take4(m, pos, relu)
+                    for c in range(4):
+                        if e & (0xFF << (8 * c)):
+                            acc[c] = np.float32(acc[c] + g[c])
+                got[n, h, w] = acc
+    np.testing.assert_array_equal(got, ref)
