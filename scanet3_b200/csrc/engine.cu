@@ -536,6 +536,30 @@ static void plan_fusions(sb_engine* e) {
         break;
     }
   }
+  // Second pass (needs fast_skinny of later layers): winner maps for the remaining 2x2 stride-1 pools, and the classifier head's
+  // input gradient folded into the backward of the pool that feeds it (Pool2D >> Flatten >> Dense(N <= 16))
+  const char* nm = getenv("SB_NO_POOL_MAP");
+  const char* nh = getenv("SB_NO_HEAD_DGRAD_FUSION");
+  for (int li = 0; li < nl; ++li) {
+    LayerPlan& L = e->L[li];
+    if (L.d.kind != SB_LAYER_POOL2D || !L.fast_pool || !L.need_dx || !pool22_map_ok(L.pg) || (nm && nm[0] == '1')) continue;
+    if (!L.pool_map && !L.skip_fwd) {  // the standalone forward kernel records the map
+      void* mp = nullptr;
+      SB_CUDA(cudaMalloc(&mp, (size_t)L.pg.N * L.pg.OH * L.pg.OW * L.pg.C));
+      L.pool_map = (unsigned char*)mp;
+    }
+    if (!L.pool_map || L.fuse_conv_wgrad >= 0 || (nh && nh[0] == '1')) continue;
+    if (li + 2 < nl && e->L[li + 1].d.kind == SB_LAYER_FLATTEN && e->L[li + 2].d.kind == SB_LAYER_DENSE && e->L[li + 2].fast_skinny &&
+        !e->L[li + 2].tc_kind && e->L[li + 2].buf_in == L.buf_out && e->L[li + 2].out.d[1] <= 16 &&
+        e->L[li + 2].in.d[1] == (int64_t)L.pg.OH * L.pg.OW * L.pg.C && 2 * L.pg.OW * (L.pg.C / 4) <= 768 && L.pg.W * (L.pg.C / 4) <= 768) {
+      L.fuse_head_dgrad = li + 2;
+      e->L[li + 2].dgrad_in_pool = true;
+      if (!e->ws_side) {
+        e->ws_side_floats = (size_t)e->L[li + 2].in.d[1] * e->L[li + 2].out.d[1] * 8;
+        e->ws_side = dmalloc_floats((int64_t)e->ws_side_floats);
+      }
+    }
+  }
 }
 
 static void allocate(sb_engine* e) {
@@ -717,7 +741,7 @@ static void run_forward(sb_engine* e, int mode) {
       case SB_LAYER_POOL2D: {
         Prof pr(e, "pool_fwd", 4.0 * ((double)L.in.numel() + n_out), 0);
         // the reference layer ignores `reduce` (layer/Pool2D.scala:36-42): always max, unless the descriptor asks to honour it
-        if (L.fast_pool) pool_max_fwd_v4(in, out, L.pg, s);
+        if (L.fast_pool) pool_max_fwd_v4(in, out, L.pg, s, L.pool_map, L.pool_relu_bwd, L.fused_thr);
         else pool_fwd(in, out, L.pg, (L.d.pool_honor_reduce && L.d.pool_reduce == SB_POOL_AVG) ? SB_POOL_AVG : SB_POOL_MAX, s);
         break;
       }
@@ -806,6 +830,18 @@ static void run_backward(sb_engine* e) {
             Prof pr(e, "dense_dgrad_tf32_tcgen05", db, 2.0 * M * N * K);
             ddone = tc_dense_dgrad(e, L, li);
           }
+        }
+        if (L.fast_skinny && !wdone && L.dgrad_in_pool) {
+          // dX is formed inside the backward kernel of the pool that feeds this head (pool_bwd_head_dgrad): only the weight gradient
+          // is left, and nothing but the optimizer waits for it -- side branch (its own workspace: `ws` is in use on the main stream)
+          const bool fork = fork_enabled() && !e->profiling;
+          Prof pr(e, "dense_head_wgrad", db, 2.0 * M * N * K);
+          if (fork) side_branch_begin(e);
+          wdone = ddone = dense_head_bwd(in, dout, P(e, L.p_w), G(e, L.p_w), nullptr, M, N, K, e->ws_side, e->ws_side_floats,
+                                         fork ? e->bstream : s);
+          if (fork) side_branch_end(e);
+          if (!wdone) SB_FAIL(SB_ERR_CUDA, "dense_head_bwd rejected a planned shape");
+          break;
         }
         if (L.fast_skinny && !wdone) {
           const bool dg = L.need_dx && din;
@@ -904,6 +940,13 @@ static void run_backward(sb_engine* e) {
                                   e->ws_floats, s, L.pool_map))
             break;
           SB_FAIL(SB_ERR_CUDA, "pool_bwd_conv_wgrad rejected a planned shape");
+        }
+        if (L.fuse_head_dgrad >= 0) {
+          const LayerPlan& D = e->L[L.fuse_head_dgrad];
+          const int Nc = (int)D.out.d[1];
+          Prof pr(e, "pool_bwd_head_dgrad", 4.0 * ((double)L.in.numel() + (double)D.in.d[1] * Nc) + (double)n_out, 2.0 * (double)n_out * Nc);
+          if (pool_bwd_head_dgrad(L.pool_map, e->dacts[D.buf_out], P(e, D.p_w), din, L.pg, Nc, L.pool_relu_bwd, s)) break;
+          SB_FAIL(SB_ERR_CUDA, "pool_bwd_head_dgrad rejected a planned shape");
         }
         Prof pr(e, L.pool_relu_bwd ? "pool_relu_bwd" : "pool_bwd", 4.0 * (2.0 * L.in.numel() + 2.0 * n_out), 0);
         if (L.fast_pool) pool_max_bwd_v4(in, dout, din, L.pg, L.pool_relu_bwd, L.fused_thr, s, L.pool_map);
@@ -1406,7 +1449,7 @@ extern "C" void sb_engine_destroy(sb_engine* e) {
     for (float* p : e->acts) cudaFree(p);
     for (float* p : e->dacts) cudaFree(p);
     cudaFree(e->arena); cudaFree(e->grads); cudaFree(e->by); cudaFree(e->ds_x); cudaFree(e->ds_y);
-    cudaFree(e->st); cudaFree(e->ws); cudaFree(e->head_scratch); cudaFree(e->est_acc);
+    cudaFree(e->st); cudaFree(e->ws); cudaFree(e->ws_side); cudaFree(e->head_scratch); cudaFree(e->est_acc);
     if (e->st_host) cudaFreeHost(e->st_host);
     if (e->stream) cudaStreamDestroy(e->stream);
   }

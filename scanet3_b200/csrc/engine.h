@@ -67,6 +67,8 @@ struct LayerPlan {
   unsigned char* pool_map = nullptr;  // Pool2D (2x2 stride 1) whose forward is fused into the producing conv: one winner byte per
                                       // output and channel (first-max index | ReLU bit); the backward routes dy with it and the
                                       // conv activations are neither written nor read
+  int fuse_head_dgrad = -1;       // Pool2D: its backward also forms the input gradient of this classifier-head Dense layer
+  bool dgrad_in_pool = false;     // Dense (head): dX is produced by the pool's backward kernel; only dW is computed here
   bool wgrad_in_pool = false;     // Conv2D: the filter gradient is produced by the following pool's backward kernel
   bool fuse_act_bwd = false;      // Bias: also applies the backward of the in-place activation that follows (one pass)
   bool head_skip = false;         // Bias / Softmax of the fused classifier head: executed by the head kernel when training
@@ -121,6 +123,8 @@ struct sb_engine {
   sb::StepState* st = nullptr;
   sb::StepState* st_host = nullptr;  // pinned mirror
   float* ws = nullptr;
+  float* ws_side = nullptr;       // workspace of kernels that run on the backward side branch next to users of `ws`
+  size_t ws_side_floats = 0;
   double* est_acc = nullptr;      // 4 running sums of sb_estimate
   float* head_scratch = nullptr;  // per-CTA partials + completion ticket of the fused classifier-head kernel
   size_t ws_floats = 0;

@@ -118,7 +118,14 @@ void philox_fill(float* p, long long n, unsigned long long seed, int normal, flo
 
 namespace sb {
 // ---- kernels_fast.cu: vectorised / fused variants (return false when the shape is not covered) ----
-void pool_max_fwd_v4(const float* x, float* y, const PoolGeom& g, cudaStream_t s);
+// map != null (2x2 stride-1 pools): also records one winner byte per output and channel -- index of the first maximum | (maximum
+// > thr) << 2 when `relu` (always set otherwise) -- for the map-driven backward kernels
+void pool_max_fwd_v4(const float* x, float* y, const PoolGeom& g, cudaStream_t s, unsigned char* map = nullptr, int relu = 0,
+                     float thr = 0.f);
+// Pool2D(2x2, stride 1) backward fused with the input gradient of the classifier head Dense(N <= 16) that consumes the flattened
+// pool output: dx[b,h,w,c] = sum over the windows won by (h,w) of (G[b,:] . W[f(window,c),:]).  false: shape not covered
+bool pool_bwd_head_dgrad(const unsigned char* map, const float* gmat, const float* w, float* dx, const PoolGeom& g, int N, int relu,
+                         cudaStream_t s);
 // map != null (2x2 stride-1 pools whose forward recorded winner bytes): routed by the map, x is not read
 void pool_max_bwd_v4(const float* x, const float* dy, float* dx, const PoolGeom& g, int relu, float thr, cudaStream_t s,
                      const unsigned char* map = nullptr);

@@ -98,14 +98,57 @@ __global__ void __launch_bounds__(256) pool22_fwd_strip_kernel(const float* __re
     prev = next;
   }
 }
+// the same walk recording the winner byte of every window (win4) next to the maximum: the backward pass then routes dy by the map
+// and never reads x again.  Keeps the previous column's two members in registers: still 2 loads per output.
+__global__ void __launch_bounds__(256) pool22_fwd_map_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                             unsigned* __restrict__ map, PoolGeom g, int relu, float thr,
+                                                             int seg_len, long long n_threads) {
+  pdl_prologue_trigger();
+  const int C4 = g.C >> 2;
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((long long)i >= n_threads) return;
+  const int c4 = (int)(i % (unsigned)C4);
+  unsigned t = i / (unsigned)C4;
+  const int seg = (int)(t % kPoolSegs); t /= kPoolSegs;
+  const int oh = (int)(t % (unsigned)g.OH);
+  const int b = (int)(t / (unsigned)g.OH);
+  const int w0 = seg * seg_len;
+  const int w1 = min(w0 + seg_len, g.OW);
+  if (w0 >= w1) return;
+  const float* r0 = x + (((long long)b * g.H + oh) * g.W) * g.C + c4 * 4;
+  const float* r1 = r0 + (long long)g.W * g.C;
+  float* yo = y + (((long long)b * g.OH + oh) * g.OW) * g.C + c4 * 4;
+  unsigned* mo = map + (((long long)b * g.OH + oh) * g.OW) * C4 + c4;
+  r0 += w0 * g.C; r1 += w0 * g.C; yo += w0 * g.C; mo += w0 * C4;
+  float4 pa = ld4(r0), pc = ld4(r1);  // members 0 (top-left) and 2 (bottom-left) of the window anchored in column w
+#pragma unroll 4
+  for (int w = w0; w < w1; ++w) {
+    r0 += g.C; r1 += g.C;
+    const float4 nb = ld4(r0), nd = ld4(r1);  // members 1 and 3
+    float4 m;
+    const unsigned b0 = win4(pa.x, nb.x, pc.x, nd.x, relu, thr, &m.x);
+    const unsigned b1 = win4(pa.y, nb.y, pc.y, nd.y, relu, thr, &m.y);
+    const unsigned b2 = win4(pa.z, nb.z, pc.z, nd.z, relu, thr, &m.z);
+    const unsigned b3 = win4(pa.w, nb.w, pc.w, nd.w, relu, thr, &m.w);
+    st4(yo, m);
+    *mo = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+    yo += g.C; mo += C4;
+    pa = nb; pc = nd;
+  }
+}
 static bool pool_is_22s1(const PoolGeom& g) {
   return g.KH == 2 && g.KW == 2 && g.SH == 1 && g.SW == 1 && g.PT == 0 && g.PL == 0 && g.OH == g.H - 1 && g.OW == g.W - 1;
 }
-void pool_max_fwd_v4(const float* x, float* y, const PoolGeom& g, cudaStream_t s) {
+void pool_max_fwd_v4(const float* x, float* y, const PoolGeom& g, cudaStream_t s, unsigned char* map, int relu, float thr) {
   const long long nt22 = (long long)g.N * g.OH * kPoolSegs * (g.C / 4);  // 4 segments: 2, 3 and 6 measured 1.3-1.7 % slower on cfg2
   if (pool_is_22s1(g) && nt22 < (1LL << 31)) {  // the strip kernels split a 32-bit thread index
     const long long nt = nt22;
     const int seg_len = (g.OW + kPoolSegs - 1) / kPoolSegs;
+    if (map) {
+      launch_k(pool22_fwd_map_kernel, (int)((nt + 255) / 256), 256, 0, s, x, y, (unsigned*)map, g, relu, thr, seg_len, nt);
+      SB_LAUNCHED();
+      return;
+    }
     launch_k(pool22_fwd_strip_kernel, (int)((nt + 255) / 256), 256, 0, s, x, y, g, seg_len, nt);
     SB_LAUNCHED();
     return;
@@ -470,6 +513,143 @@ __global__ void __launch_bounds__(128, (WG == 331 ? 4 : 1)) pool22_bwd_map_kerne
     }
   }
 }
+// =====================================================================================================================
+// Pool2D(2x2, stride 1) backward fused with the INPUT GRADIENT of the classifier head that consumes the pooled tensor
+// (Pool2D >> Flatten >> Dense(N <= 16), layer/Dense.scala:57-61): dP[b][f] = sum_n G[b][n] W[f][n] is formed on the fly and routed
+// through the winner map, so the head's dX (one write + one read of the whole pooled tensor) never exists and the head's backward
+// kernel shrinks to its weight gradient (off the critical path, on the side branch).
+//   CTA = (output row h of the pool's input, group of images).  Thread (r, pw, c4) owns the pooled position (h-1+r, pw) and four
+//   channels: its 4 x N slab of W stays in REGISTERS for all the images of the group (W-stationary); per image it forms the dP
+//   quad (the FFMA2 pairing and summation order of dense_head_bwd_kernel, so the bits are the same as the unfused path's) into a
+//   double-buffered shared tile [2 rows][OW][C]; after one barrier the threads gather row h: element (h, w) takes dP of windows
+//   (h-1,w-1), (h-1,w), (h,w-1), (h,w) iff their winner byte says so (same order as pool22_bwd_map_kernel).  The winner words of
+//   image b+1 are fetched while image b computes.
+// =====================================================================================================================
+constexpr int kPoolHeadThreads = 768;
+template <int NT>
+__global__ void __launch_bounds__(kPoolHeadThreads, 1) pool22_bwd_head_kernel(const unsigned* __restrict__ map, const float* __restrict__ gmat,
+                                                                            const float* __restrict__ w, float* __restrict__ dx,
+                                                                            PoolGeom g, int N, int relu, int img_per_cta, int prewait) {
+  extern __shared__ __align__(16) float psm[];
+  const int C4 = g.C >> 2, npos = g.OW * C4;
+  float* sg = psm;                                      // [img_per_cta][NT]
+  float* dp = psm + (size_t)img_per_cta * NT;           // [2 buffers][2 rows][OW][C]
+  const int h = blockIdx.x;
+  const int b0 = blockIdx.y * img_per_cta, b1 = min(g.N, b0 + img_per_cta);
+  const int tid = threadIdx.x;
+  const int r = tid / npos, pos = tid - r * npos;       // r: 0 = pooled row h-1, 1 = pooled row h (tid >= 2*npos: gather only)
+  const int pw = pos / C4, c4 = pos - pw * C4;
+  const int ph = h - 1 + r;
+  const bool owns = r < 2 && ph >= 0 && ph < g.OH;
+  // W slab of the position: rows f = (ph*OW + pw)*C + c4*4 + q, q = 0..3, N classes each (zero beyond N)
+  if (!prewait) pdl_wait();
+  float2 wr2[4][NT / 2];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int n = 0; n < NT / 2; ++n) {
+      const float* wp = w + ((size_t)((owns ? ph : 0) * g.OW + pw) * g.C + c4 * 4 + q) * N;
+      wr2[q][n] = make_float2((owns && 2 * n < N) ? __ldg(wp + 2 * n) : 0.f, (owns && 2 * n + 1 < N) ? __ldg(wp + 2 * n + 1) : 0.f);
+    }
+  if (prewait) pdl_wait();
+  pdl_trigger();
+  for (int i = tid; i < (b1 - b0) * NT; i += blockDim.x) {
+    const int m = i / NT, n = i - m * NT;
+    sg[i] = n < N ? __ldg(gmat + (size_t)(b0 + m) * N + n) : 0.f;
+  }
+  // gather item of this thread: output pixel (h, gw), channel quad gc (one item per thread; W*C4 <= blockDim, checked by the launcher)
+  const int gw = tid / C4, gc = tid - gw * C4;
+  const bool gathers = gw < g.W;
+  const bool top_ok = h >= 1, bot_ok = h <= g.H - 2, lft_ok = gw >= 1, rgt_ok = gw <= g.W - 2;
+  auto load_words = [&](int b, unsigned* m4) {
+    const unsigned* mt = map + (((long long)b * g.OH + (top_ok ? h - 1 : 0)) * g.OW) * C4 + gc;
+    const unsigned* mb = map + (((long long)b * g.OH + (bot_ok ? h : 0)) * g.OW) * C4 + gc;
+    m4[0] = (gathers && top_ok && lft_ok) ? __ldg(mt + (gw - 1) * C4) : 0xffffffffu;  // window (h-1, w-1): member 3
+    m4[1] = (gathers && top_ok && rgt_ok) ? __ldg(mt + gw * C4) : 0xffffffffu;        // window (h-1, w)  : member 2
+    m4[2] = (gathers && bot_ok && lft_ok) ? __ldg(mb + (gw - 1) * C4) : 0xffffffffu;  // window (h,   w-1): member 1
+    m4[3] = (gathers && bot_ok && rgt_ok) ? __ldg(mb + gw * C4) : 0xffffffffu;        // window (h,   w)  : member 0
+  };
+  unsigned mcur[4], mnext[4];
+  load_words(b0, mcur);
+  __syncthreads();
+  for (int b = b0; b < b1; ++b) {
+    const int buf = (b - b0) & 1;
+    if (b + 1 < b1) load_words(b + 1, mnext);
+    float* tile = dp + (size_t)buf * 2 * g.OW * g.C;
+    if (r < 2) {
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (owns) {
+        const float* gr = sg + (size_t)(b - b0) * NT;
+        float2 d2[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) d2[q] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int n4 = 0; n4 < NT; n4 += 4) {
+          const float4 gv = *reinterpret_cast<const float4*>(gr + n4);
+          const float2 g0 = make_float2(gv.x, gv.y), g1 = make_float2(gv.z, gv.w);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            d2[q] = __ffma2_rn(g0, wr2[q][n4 / 2], d2[q]);
+            d2[q] = __ffma2_rn(g1, wr2[q][n4 / 2 + 1], d2[q]);
+          }
+        }
+        o = make_float4(__fadd_rn(d2[0].x, d2[0].y), __fadd_rn(d2[1].x, d2[1].y), __fadd_rn(d2[2].x, d2[2].y), __fadd_rn(d2[3].x, d2[3].y));
+      }
+      *reinterpret_cast<float4*>(tile + ((size_t)r * g.OW + pw) * g.C + c4 * 4) = o;
+    }
+    __syncthreads();
+    if (gathers) {
+      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* t0 = tile + gc * 4;                      // pooled row h-1
+      const float* t1 = tile + (size_t)g.OW * g.C + gc * 4; // pooled row h
+      const float4 pgt = (top_ok && lft_ok) ? *reinterpret_cast<const float4*>(t0 + (gw - 1) * g.C) : zero;
+      const float4 gt = (top_ok && rgt_ok) ? *reinterpret_cast<const float4*>(t0 + gw * g.C) : zero;
+      const float4 pgb = (bot_ok && lft_ok) ? *reinterpret_cast<const float4*>(t1 + (gw - 1) * g.C) : zero;
+      const float4 gb = (bot_ok && rgt_ok) ? *reinterpret_cast<const float4*>(t1 + gw * g.C) : zero;
+      const unsigned e3 = take4(mcur[0], 3u, relu), e2 = take4(mcur[1], 2u, relu), e1 = take4(mcur[2], 1u, relu), e0 = take4(mcur[3], 0u, relu);
+      float4 acc = zero;
+#define SB_WIN(c, sh)                                            \
+  if (e3 & (0xffu << sh)) acc.c = __fadd_rn(acc.c, pgt.c);       \
+  if (e2 & (0xffu << sh)) acc.c = __fadd_rn(acc.c, gt.c);        \
+  if (e1 & (0xffu << sh)) acc.c = __fadd_rn(acc.c, pgb.c);       \
+  if (e0 & (0xffu << sh)) acc.c = __fadd_rn(acc.c, gb.c);
+      SB_WIN(x, 0) SB_WIN(y, 8) SB_WIN(z, 16) SB_WIN(w, 24)
+#undef SB_WIN
+      st4(dx + (((long long)b * g.H + h) * g.W + gw) * g.C + gc * 4, acc);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) mcur[q] = mnext[q];
+  }
+}
+// false: shape not covered (the caller runs the head's dgrad and the plain pool backward)
+bool pool_bwd_head_dgrad(const unsigned char* map, const float* gmat, const float* w, float* dx, const PoolGeom& g, int N, int relu,
+                         cudaStream_t s) {
+  if (!map || !pool_is_22s1(g) || (g.C & 3) || N > 16 || N < 1) return false;
+  const int C4 = g.C / 4;
+  if (2 * g.OW * C4 > kPoolHeadThreads || g.W * C4 > kPoolHeadThreads) return false;
+  const int NT = N <= 12 ? 12 : 16;
+  // one wave of CTAs: rows x image groups ~ 148
+  int groups = std::max(1, std::min(g.N, kNumSMs / std::max(1, g.H)));
+  const int img_per_cta = (g.N + groups - 1) / groups;
+  groups = (g.N + img_per_cta - 1) / img_per_cta;
+  const size_t smem = ((size_t)img_per_cta * NT + (size_t)2 * 2 * g.OW * g.C) * sizeof(float);
+  if (smem > 200 * 1024) return false;
+  static bool attr = false;
+  if (!attr) {
+    SB_CUDA(cudaFuncSetAttribute(pool22_bwd_head_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SB_CUDA(cudaFuncSetAttribute(pool22_bwd_head_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  const int thr = std::max(2 * g.OW * C4, g.W * C4);
+  const int threads = (thr + 31) / 32 * 32;
+  const dim3 grid(g.H, groups);
+  const int pw = prewait_ok();
+  if (NT == 12) launch_k(pool22_bwd_head_kernel<12>, grid, threads, smem, s, (const unsigned*)map, gmat, w, dx, g, N, relu, img_per_cta, pw);
+  else launch_k(pool22_bwd_head_kernel<16>, grid, threads, smem, s, (const unsigned*)map, gmat, w, dx, g, N, relu, img_per_cta, pw);
+  SB_LAUNCHED();
+  return true;
+}
+
 // segments per row: cost ~ whole waves x (columns per thread + prologue columns); a wave = what 148 SMs hold at the kernel's
 // register footprint.  The prologue (index split, pointer setup, the column before the segment) costs ~2.5 columns of the walk
 // (SASS: 315 instructions against 119 per column): LeNet's pool2 backward (23 columns) then takes 2 segments in one wave instead

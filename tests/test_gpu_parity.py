@@ -663,8 +663,10 @@ def test_winner_map_path_is_bit_identical_to_the_activation_path(prec, monkeypat
     _, sm = build_models(LENET)
     x, y = synth_classification(12, (14, 14, 1), 10, 21)
     outs = []
-    for off in ("1", "0"):
+    # activation path | winner maps, head dgrad unfused | winner maps + the head's input gradient formed inside pool2's backward
+    for off, nofuse in (("1", "1"), ("0", "1"), ("0", "0")):
         monkeypatch.setenv("SB_NO_POOL_MAP", off)
+        monkeypatch.setenv("SB_NO_HEAD_DGRAD_FUSION", nofuse)
         e = make_engine(sm, S.CategoricalCrossentropy, S.Adam(0.001), 12, (14, 14, 1), (10,), precision=prec)
         e.init_params()
         loss, grads = e.compute_grads(x, y)
@@ -672,7 +674,8 @@ def test_winner_map_path_is_bit_identical_to_the_activation_path(prec, monkeypat
         l2 = e.train_step(x, y, 2)
         outs.append((loss, l1, l2, {k: v.tobytes() for k, v in grads.items()}, {k: v.tobytes() for k, v in e.get_params().items()}))
         e.close()
-    assert outs[0][:3] == outs[1][:3]
-    for k in outs[0][3]:
-        assert outs[0][3][k] == outs[1][3][k], f"gradient {k} differs"
-    assert outs[0][4] == outs[1][4]
+    for o in outs[1:]:
+        assert outs[0][:3] == o[:3]
+        for k in outs[0][3]:
+            assert outs[0][3][k] == o[3][k], f"gradient {k} differs"
+        assert outs[0][4] == o[4]
