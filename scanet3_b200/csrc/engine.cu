@@ -536,13 +536,19 @@ static void plan_fusions(sb_engine* e) {
         break;
     }
   }
-  // Second pass (needs fast_skinny of later layers): winner maps for the remaining 2x2 stride-1 pools, and the classifier head's
-  // input gradient folded into the backward of the pool that feeds it (Pool2D >> Flatten >> Dense(N <= 16))
+  // Second pass (needs fast_skinny of later layers), OFF by default -- SB_POOL_MAP_ALL=1 turns it on: winner maps for 2x2 stride-1
+  // pools whose forward is the standalone kernel, and the classifier head's input gradient folded into the backward of the pool
+  // that feeds it (Pool2D >> Flatten >> Dense(N <= 16)).  Measured on cfg2 (profiles/r2_notes.md): recording the map costs the
+  // standalone pool forward more than the map-driven backward saves (975 k vs 1019 k samples/s), and the fused pool-backward /
+  // head-dgrad kernel is issue-bound at 23 us (985 k): both stay parity-tested (bit-identical to the default path) for the day the
+  // map comes for free out of the tensor-core conv's epilogue.
   const char* nm = getenv("SB_NO_POOL_MAP");
+  const char* all = getenv("SB_POOL_MAP_ALL");
   const char* nh = getenv("SB_NO_HEAD_DGRAD_FUSION");
   for (int li = 0; li < nl; ++li) {
     LayerPlan& L = e->L[li];
     if (L.d.kind != SB_LAYER_POOL2D || !L.fast_pool || !L.need_dx || !pool22_map_ok(L.pg) || (nm && nm[0] == '1')) continue;
+    if (!(all && all[0] == '1')) continue;
     if (!L.pool_map && !L.skip_fwd) {  // the standalone forward kernel records the map
       void* mp = nullptr;
       SB_CUDA(cudaMalloc(&mp, (size_t)L.pg.N * L.pg.OH * L.pg.OW * L.pg.C));
@@ -551,7 +557,7 @@ static void plan_fusions(sb_engine* e) {
     if (!L.pool_map || L.fuse_conv_wgrad >= 0 || (nh && nh[0] == '1')) continue;
     if (li + 2 < nl && e->L[li + 1].d.kind == SB_LAYER_FLATTEN && e->L[li + 2].d.kind == SB_LAYER_DENSE && e->L[li + 2].fast_skinny &&
         !e->L[li + 2].tc_kind && e->L[li + 2].buf_in == L.buf_out && e->L[li + 2].out.d[1] <= 16 &&
-        e->L[li + 2].in.d[1] == (int64_t)L.pg.OH * L.pg.OW * L.pg.C && 2 * L.pg.OW * (L.pg.C / 4) <= 768 && L.pg.W * (L.pg.C / 4) <= 768) {
+        e->L[li + 2].in.d[1] == (int64_t)L.pg.OH * L.pg.OW * L.pg.C && 2 * L.pg.OW * (L.pg.C / 4) <= 704 && L.pg.W * (L.pg.C / 4) <= 704) {
       L.fuse_head_dgrad = li + 2;
       e->L[li + 2].dgrad_in_pool = true;
       if (!e->ws_side) {

@@ -525,8 +525,9 @@ __global__ void __launch_bounds__(128, (WG == 331 ? 4 : 1)) pool22_bwd_map_kerne
 //   (h-1,w-1), (h-1,w), (h,w-1), (h,w) iff their winner byte says so (same order as pool22_bwd_map_kernel).  The winner words of
 //   image b+1 are fetched while image b computes.
 // =====================================================================================================================
-constexpr int kPoolHeadThreads = 768;
-template <int NT>
+constexpr int kPoolHeadThreads = 704;  // 22 warps x 80 registers (warp allocations come in 512-register units: 88 would not launch)
+// NC: compile-time class count (the thread's 4*NC weights are read with 128-bit shared loads), 0 = run-time N (scalar loads)
+template <int NT, int NC>
 __global__ void __launch_bounds__(kPoolHeadThreads, 1) pool22_bwd_head_kernel(const unsigned* __restrict__ map, const float* __restrict__ gmat,
                                                                             const float* __restrict__ w, float* __restrict__ dx,
                                                                             PoolGeom g, int N, int relu, int img_per_cta, int prewait) {
@@ -541,16 +542,49 @@ __global__ void __launch_bounds__(kPoolHeadThreads, 1) pool22_bwd_head_kernel(co
   const int pw = pos / C4, c4 = pos - pw * C4;
   const int ph = h - 1 + r;
   const bool owns = r < 2 && ph >= 0 && ph < g.OH;
-  // W slab of the position: rows f = (ph*OW + pw)*C + c4*4 + q, q = 0..3, N classes each (zero beyond N)
+  // W slab of the position: rows f = (ph*OW + pw)*C + c4*4 + q, q = 0..3, N classes each (zero beyond N) = 4*N contiguous floats.
+  // The CTA's positions cover one contiguous piece of W (pooled rows h-1 and h): it is copied to shared memory with coalesced
+  // 128-bit loads first -- per-thread gathers straight from global memory touch 32 different lines per warp instruction and cost
+  // the LSU ~17 us per CTA (measured: 33 us for the whole kernel).
   if (!prewait) pdl_wait();
   float2 wr2[4][NT / 2];
+  {
+    const int ph_lo = max(h - 1, 0), ph_hi = min(h, g.OH - 1);
+    const long long slab0 = (long long)ph_lo * npos * 4 * N;                    // floats; multiple of 4 (C % 4 == 0)
+    const int slab_n = (ph_hi - ph_lo + 1) * npos * 4 * N;
+    float* wsm = dp + (size_t)2 * 2 * g.OW * g.C;                                // [<= 2 rows][OW][C][N]
+    const float4* src = reinterpret_cast<const float4*>(w + slab0);
+    const int n4 = slab_n / 4;
+    for (int i0 = tid; i0 < n4; i0 += 8 * blockDim.x) {  // 8 independent loads in flight per thread (a load->store chain per
+      float4 t[8];                                        // element would pay the L2 latency ten times over)
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
+      for (int u = 0; u < 8; ++u) t[u] = i0 + u * blockDim.x < n4 ? __ldg(src + i0 + u * blockDim.x) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int n = 0; n < NT / 2; ++n) {
-      const float* wp = w + ((size_t)((owns ? ph : 0) * g.OW + pw) * g.C + c4 * 4 + q) * N;
-      wr2[q][n] = make_float2((owns && 2 * n < N) ? __ldg(wp + 2 * n) : 0.f, (owns && 2 * n + 1 < N) ? __ldg(wp + 2 * n + 1) : 0.f);
+      for (int u = 0; u < 8; ++u)
+        if (i0 + u * blockDim.x < n4) reinterpret_cast<float4*>(wsm)[i0 + u * blockDim.x] = t[u];
     }
+    __syncthreads();
+    const float* wp = wsm + (size_t)((owns ? ph - ph_lo : 0) * npos + pos) * 4 * N;
+    if (NC > 0) {  // 4*NC contiguous floats, 16-byte aligned: NC 128-bit loads (scalar loads at this 160-byte lane stride are 8-way bank conflicts)
+      float wl[4 * (NC > 0 ? NC : 1)];
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+        const float4 t = *reinterpret_cast<const float4*>(wp + 4 * i);
+        wl[4 * i] = t.x; wl[4 * i + 1] = t.y; wl[4 * i + 2] = t.z; wl[4 * i + 3] = t.w;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int n = 0; n < NT / 2; ++n)
+          wr2[q][n] = make_float2((owns && 2 * n < NC) ? wl[q * NC + 2 * n] : 0.f, (owns && 2 * n + 1 < NC) ? wl[q * NC + 2 * n + 1] : 0.f);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int n = 0; n < NT / 2; ++n)
+          wr2[q][n] = make_float2((owns && 2 * n < N) ? wp[q * N + 2 * n] : 0.f, (owns && 2 * n + 1 < N) ? wp[q * N + 2 * n + 1] : 0.f);
+    }
+  }
   if (prewait) pdl_wait();
   pdl_trigger();
   for (int i = tid; i < (b1 - b0) * NT; i += blockDim.x) {
@@ -561,25 +595,47 @@ __global__ void __launch_bounds__(kPoolHeadThreads, 1) pool22_bwd_head_kernel(co
   const int gw = tid / C4, gc = tid - gw * C4;
   const bool gathers = gw < g.W;
   const bool top_ok = h >= 1, bot_ok = h <= g.H - 2, lft_ok = gw >= 1, rgt_ok = gw <= g.W - 2;
-  auto load_words = [&](int b, unsigned* m4) {
-    const unsigned* mt = map + (((long long)b * g.OH + (top_ok ? h - 1 : 0)) * g.OW) * C4 + gc;
-    const unsigned* mb = map + (((long long)b * g.OH + (bot_ok ? h : 0)) * g.OW) * C4 + gc;
-    m4[0] = (gathers && top_ok && lft_ok) ? __ldg(mt + (gw - 1) * C4) : 0xffffffffu;  // window (h-1, w-1): member 3
-    m4[1] = (gathers && top_ok && rgt_ok) ? __ldg(mt + gw * C4) : 0xffffffffu;        // window (h-1, w)  : member 2
-    m4[2] = (gathers && bot_ok && lft_ok) ? __ldg(mb + (gw - 1) * C4) : 0xffffffffu;  // window (h,   w-1): member 1
-    m4[3] = (gathers && bot_ok && rgt_ok) ? __ldg(mb + gw * C4) : 0xffffffffu;        // window (h,   w)  : member 0
-  };
-  unsigned mcur[4], mnext[4];
-  load_words(b0, mcur);
+  // everything that does not depend on the image is hoisted: the four winner words' pointers (advanced by one image per
+  // iteration; a window that does not exist reads a valid dummy address and is masked), the dP tile slots, the output pointer.
+  // (The first version recomputed the 64-bit indices inside the loop: 78 of its ~250 instructions per image, ncu source page.)
+  const bool v3 = gathers && top_ok && lft_ok, v2 = gathers && top_ok && rgt_ok, v1 = gathers && bot_ok && lft_ok, v0 = gathers && bot_ok && rgt_ok;
+  // The winner words of the CTA's images (pooled rows h-1 and h: one contiguous block of <= 2*OW*C4 words per image) are copied
+  // to shared memory up front with independent coalesced loads, so that the per-image loop below touches global memory only to
+  // store dx (a one-image-ahead register prefetch left every iteration waiting for an L2 round trip).
+  const int ph_lo = max(h - 1, 0), ph_hi = min(h, g.OH - 1);
+  const int blk_words = (ph_hi - ph_lo + 1) * npos;         // words per image block
+  const int map_img = g.OH * g.OW * C4;                     // words per image (the launcher keeps the whole map below 2^31 words)
+  unsigned* smap = reinterpret_cast<unsigned*>(dp + (size_t)2 * 2 * g.OW * g.C + (size_t)2 * g.OW * g.C * N);  // [img_per_cta][2*npos]
+  {
+    const unsigned* msrc = map + (long long)b0 * map_img + ph_lo * npos;
+    const int nimg = b1 - b0;
+    if (tid < blk_words) {
+#pragma unroll 4
+      for (int m = 0; m < nimg; ++m) smap[m * 2 * npos + tid] = __ldg(msrc + (long long)m * map_img + tid);
+    }
+  }
+  // word of window (row r in {h-1, h}, column c) of image m: smap[m*2*npos + (r - ph_lo)*npos + c*C4 + gc]
+  const int o3 = v3 ? ((h - 1 - ph_lo) * g.OW + gw - 1) * C4 + gc : 0;  // window (h-1, w-1): member 3
+  const int o2 = v2 ? ((h - 1 - ph_lo) * g.OW + gw) * C4 + gc : 0;      // window (h-1, w)  : member 2
+  const int o1 = v1 ? ((h - ph_lo) * g.OW + gw - 1) * C4 + gc : 0;      // window (h,   w-1): member 1
+  const int o0 = v0 ? ((h - ph_lo) * g.OW + gw) * C4 + gc : 0;          // window (h,   w)  : member 0
+  const unsigned none = 0xffffffffu;
+  const int tile_floats = 2 * g.OW * g.C;
+  float* my_slot = dp + ((size_t)(r < 2 ? r : 0) * g.OW + pw) * g.C + c4 * 4;  // + buf * tile_floats
+  const float* t3 = dp + (v3 ? (gw - 1) * g.C : 0) + gc * 4;                   // pooled row h-1
+  const float* t2 = dp + (v2 ? gw * g.C : 0) + gc * 4;
+  const float* t1 = dp + (size_t)g.OW * g.C + (v1 ? (gw - 1) * g.C : 0) + gc * 4;  // pooled row h
+  const float* t0 = dp + (size_t)g.OW * g.C + (v0 ? gw * g.C : 0) + gc * 4;
+  float* dxo = dx + (((long long)b0 * g.H + h) * g.W + (gathers ? gw : 0)) * g.C + gc * 4;
+  const long long dx_img = (long long)g.H * g.W * g.C;
+  const float* gr = sg;
+  const unsigned* sm_words = smap;
   __syncthreads();
+  int toff = 0;
   for (int b = b0; b < b1; ++b) {
-    const int buf = (b - b0) & 1;
-    if (b + 1 < b1) load_words(b + 1, mnext);
-    float* tile = dp + (size_t)buf * 2 * g.OW * g.C;
     if (r < 2) {
       float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
       if (owns) {
-        const float* gr = sg + (size_t)(b - b0) * NT;
         float2 d2[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) d2[q] = make_float2(0.f, 0.f);
@@ -595,18 +651,19 @@ __global__ void __launch_bounds__(kPoolHeadThreads, 1) pool22_bwd_head_kernel(co
         }
         o = make_float4(__fadd_rn(d2[0].x, d2[0].y), __fadd_rn(d2[1].x, d2[1].y), __fadd_rn(d2[2].x, d2[2].y), __fadd_rn(d2[3].x, d2[3].y));
       }
-      *reinterpret_cast<float4*>(tile + ((size_t)r * g.OW + pw) * g.C + c4 * 4) = o;
+      *reinterpret_cast<float4*>(my_slot + toff) = o;
     }
+    gr += NT;
     __syncthreads();
     if (gathers) {
       const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float* t0 = tile + gc * 4;                      // pooled row h-1
-      const float* t1 = tile + (size_t)g.OW * g.C + gc * 4; // pooled row h
-      const float4 pgt = (top_ok && lft_ok) ? *reinterpret_cast<const float4*>(t0 + (gw - 1) * g.C) : zero;
-      const float4 gt = (top_ok && rgt_ok) ? *reinterpret_cast<const float4*>(t0 + gw * g.C) : zero;
-      const float4 pgb = (bot_ok && lft_ok) ? *reinterpret_cast<const float4*>(t1 + (gw - 1) * g.C) : zero;
-      const float4 gb = (bot_ok && rgt_ok) ? *reinterpret_cast<const float4*>(t1 + gw * g.C) : zero;
-      const unsigned e3 = take4(mcur[0], 3u, relu), e2 = take4(mcur[1], 2u, relu), e1 = take4(mcur[2], 1u, relu), e0 = take4(mcur[3], 0u, relu);
+      const float4 pgt = v3 ? *reinterpret_cast<const float4*>(t3 + toff) : zero;
+      const float4 gt = v2 ? *reinterpret_cast<const float4*>(t2 + toff) : zero;
+      const float4 pgb = v1 ? *reinterpret_cast<const float4*>(t1 + toff) : zero;
+      const float4 gb = v0 ? *reinterpret_cast<const float4*>(t0 + toff) : zero;
+      const unsigned m3 = v3 ? sm_words[o3] : none, m2 = v2 ? sm_words[o2] : none, m1 = v1 ? sm_words[o1] : none,
+                     m0 = v0 ? sm_words[o0] : none;
+      const unsigned e3 = take4(m3, 3u, relu), e2 = take4(m2, 2u, relu), e1 = take4(m1, 1u, relu), e0 = take4(m0, 0u, relu);
       float4 acc = zero;
 #define SB_WIN(c, sh)                                            \
   if (e3 & (0xffu << sh)) acc.c = __fadd_rn(acc.c, pgt.c);       \
@@ -615,10 +672,11 @@ __global__ void __launch_bounds__(kPoolHeadThreads, 1) pool22_bwd_head_kernel(co
   if (e0 & (0xffu << sh)) acc.c = __fadd_rn(acc.c, gb.c);
       SB_WIN(x, 0) SB_WIN(y, 8) SB_WIN(z, 16) SB_WIN(w, 24)
 #undef SB_WIN
-      st4(dx + (((long long)b * g.H + h) * g.W + gw) * g.C + gc * 4, acc);
+      st4(dxo, acc);
+      dxo += dx_img;
     }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) mcur[q] = mnext[q];
+    toff = tile_floats - toff;  // the other buffer
+    sm_words += 2 * npos;
   }
 }
 // false: shape not covered (the caller runs the head's dgrad and the plain pool backward)
@@ -626,26 +684,30 @@ bool pool_bwd_head_dgrad(const unsigned char* map, const float* gmat, const floa
                          cudaStream_t s) {
   if (!map || !pool_is_22s1(g) || (g.C & 3) || N > 16 || N < 1) return false;
   const int C4 = g.C / 4;
+  if ((long long)g.N * g.OH * g.OW * C4 >= (1LL << 31)) return false;
   if (2 * g.OW * C4 > kPoolHeadThreads || g.W * C4 > kPoolHeadThreads) return false;
   const int NT = N <= 12 ? 12 : 16;
   // one wave of CTAs: rows x image groups ~ 148
   int groups = std::max(1, std::min(g.N, kNumSMs / std::max(1, g.H)));
   const int img_per_cta = (g.N + groups - 1) / groups;
   groups = (g.N + img_per_cta - 1) / img_per_cta;
-  const size_t smem = ((size_t)img_per_cta * NT + (size_t)2 * 2 * g.OW * g.C) * sizeof(float);
-  if (smem > 200 * 1024) return false;
+  const size_t smem = ((size_t)img_per_cta * NT + (size_t)2 * 2 * g.OW * g.C + (size_t)2 * g.OW * g.C * N +
+                       (size_t)img_per_cta * 2 * g.OW * C4) * sizeof(float);
+  if (smem > 200 * 1024 || (((size_t)img_per_cta * NT) & 3)) return false;
   static bool attr = false;
   if (!attr) {
-    SB_CUDA(cudaFuncSetAttribute(pool22_bwd_head_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    SB_CUDA(cudaFuncSetAttribute(pool22_bwd_head_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SB_CUDA(cudaFuncSetAttribute(pool22_bwd_head_kernel<12, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SB_CUDA(cudaFuncSetAttribute(pool22_bwd_head_kernel<12, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SB_CUDA(cudaFuncSetAttribute(pool22_bwd_head_kernel<16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
   const int thr = std::max(2 * g.OW * C4, g.W * C4);
   const int threads = (thr + 31) / 32 * 32;
   const dim3 grid(g.H, groups);
   const int pw = prewait_ok();
-  if (NT == 12) launch_k(pool22_bwd_head_kernel<12>, grid, threads, smem, s, (const unsigned*)map, gmat, w, dx, g, N, relu, img_per_cta, pw);
-  else launch_k(pool22_bwd_head_kernel<16>, grid, threads, smem, s, (const unsigned*)map, gmat, w, dx, g, N, relu, img_per_cta, pw);
+  if (N == 10) launch_k(pool22_bwd_head_kernel<12, 10>, grid, threads, smem, s, (const unsigned*)map, gmat, w, dx, g, N, relu, img_per_cta, pw);
+  else if (NT == 12) launch_k(pool22_bwd_head_kernel<12, 0>, grid, threads, smem, s, (const unsigned*)map, gmat, w, dx, g, N, relu, img_per_cta, pw);
+  else launch_k(pool22_bwd_head_kernel<16, 0>, grid, threads, smem, s, (const unsigned*)map, gmat, w, dx, g, N, relu, img_per_cta, pw);
   SB_LAUNCHED();
   return true;
 }

@@ -664,8 +664,10 @@ def test_winner_map_path_is_bit_identical_to_the_activation_path(prec, monkeypat
     x, y = synth_classification(12, (14, 14, 1), 10, 21)
     outs = []
     # activation path | winner maps, head dgrad unfused | winner maps + the head's input gradient formed inside pool2's backward
+    # (conv1's map is the default; the map of the standalone pool kernel and the head fusion are opt-in: SB_POOL_MAP_ALL=1)
     for off, nofuse in (("1", "1"), ("0", "1"), ("0", "0")):
         monkeypatch.setenv("SB_NO_POOL_MAP", off)
+        monkeypatch.setenv("SB_POOL_MAP_ALL", "1")
         monkeypatch.setenv("SB_NO_HEAD_DGRAD_FUSION", nofuse)
         e = make_engine(sm, S.CategoricalCrossentropy, S.Adam(0.001), 12, (14, 14, 1), (10,), precision=prec)
         e.init_params()
