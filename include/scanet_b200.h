@@ -158,7 +158,7 @@ typedef struct {
   float epsilon;
   float init_acc;    /* Adamax/Nadam initial accumulator (Const(initAcc)) */
   int32_t nesterov;  /* SGD */
-  int32_t minimizing; /* Optimizer.minimize (1) / maximize (0 -> SB_ERR_UNSUPPORTED) */
+  int32_t minimizing; /* Optimizer.minimize (1): w - delta ; maximize (0): w + delta (Optimizer.scala:186,326-338) */
   int32_t precision; /* sb_precision */
   int32_t use_graph; /* 1: capture the step into a CUDA graph (default), 0: eager launches */
 } sb_train_desc;

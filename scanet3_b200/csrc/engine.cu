@@ -169,7 +169,6 @@ static void build_plan(sb_engine* e) {
   if (t.batch <= 0) SB_FAIL(SB_ERR_INVALID_ARG, "batch must be positive");
   if (m.input_rank < 0 || m.input_rank > 3 || m.label_rank < 0 || m.label_rank > 3)
     SB_FAIL(SB_ERR_INVALID_ARG, "input/label rank must be in [0,3]");
-  if (!t.minimizing) SB_FAIL(SB_ERR_UNSUPPORTED, "Optimizer.maximize is outside the accelerated path");
   if (t.loss < SB_LOSS_MSE || t.loss > SB_LOSS_CCE) SB_FAIL(SB_ERR_INVALID_ARG, "unknown loss");
   e->n_slots = opt_slots(t.optimizer);
 

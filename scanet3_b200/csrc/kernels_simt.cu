@@ -1045,6 +1045,7 @@ void estimator_accumulate(const float* pred, const float* y, long long rows, int
 struct OptScalars {
   float rate, b1, b2, eps, om_b1, om_b2, bc1, bc2;
   int nesterov;
+  int maximize;  // Optimizer.maximize: w + delta instead of w - delta (optimizers/Optimizer.scala:186)
 };
 __device__ __forceinline__ float decaying_avg(float avg, float nxt, float d, float om_d) {
   return __fadd_rn(__fmul_rn(d, avg), __fmul_rn(om_d, nxt));  // (d*avg) + ((1-d)*next), alg:541-544
@@ -1095,7 +1096,7 @@ __device__ __forceinline__ void opt_update(const OptScalars& o, float& w, float 
     delta = __fdiv_rn(__fmul_rn(o.rate, m), __fadd_rn(sqrtf(vh), o.eps));
     s0 = m; s1 = vc; s2 = vh;
   }
-  w = __fsub_rn(w, delta);
+  w = o.maximize ? __fadd_rn(w, delta) : __fsub_rn(w, delta);  // `if (minimizing) w - del else w + del` (Optimizer.scala:186)
 }
 template <int KIND>
 __global__ void __launch_bounds__(256) optimizer_kernel(OptDesc od, float4* __restrict__ w, const float4* __restrict__ g,
@@ -1105,6 +1106,7 @@ __global__ void __launch_bounds__(256) optimizer_kernel(OptDesc od, float4* __re
   pdl_prologue_trigger_if(early);
   OptScalars o;
   o.rate = od.rate; o.b1 = od.beta1; o.b2 = od.beta2; o.eps = od.epsilon; o.nesterov = od.nesterov;
+  o.maximize = od.minimizing ? 0 : 1;
   o.om_b1 = __fsub_rn(1.f, od.beta1);
   o.om_b2 = __fsub_rn(1.f, od.beta2);
   o.bc1 = st->bc1; o.bc2 = st->bc2;

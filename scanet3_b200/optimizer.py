@@ -323,7 +323,8 @@ def minimize(model: Layer) -> Builder:
 
 
 def maximize(model: Layer) -> Builder:
-    raise N.Unsupported(N.SB_ERR_UNSUPPORTED, "Optimizer.maximize is outside the accelerated path (SURVEY 8b)")
+    """Optimizer.maximize (Optimizer.scala:326-338): the update becomes `w + delta` (Optimizer.scala:186)"""
+    return Builder(_Config(model=model, minimizing=False))
 
 
 class Optimizer:

@@ -1,0 +1,149 @@
+"""BASELINE.json configs 3, 4 and 5 at their FULL sizes through the C ABI against the oracle (these were only
+covered at "pattern" size).  Two train steps each: the first pins forward + gradients + the optimizer from the shared initial
+state, the second pins that the updated state feeds the next step; cost is dominated by the NumPy oracle (seconds).
+
+Tolerances.  fp32 mode (FFMA contractions): loss rtol 1e-4; gradients |err| <= 2e-4 * max|ref| per tensor (reductions of up to
+8192 x 4096 terms in a different order than NumPy's); parameters after Adam steps: an Adam step moves every weight by about `rate`
+whatever the gradient's magnitude, so a gradient whose sign is within rounding noise of zero moves its weight the other way --
+the parameters are therefore checked by max |err| <= 2 * steps * rate and by the FRACTION of elements off by more than
+(rtol 2e-3, atol 3e-5), which must stay below 1e-3.  TF32 mode: loss rtol 3e-3, gradient direction cosine > 0.995 and norm within
+5 % (ReLU masks flip for pre-activations within the tf32 error of zero, tests/test_gpu_tf32.py), parameters max |err| <= 3 * steps
+* rate.  3xTF32 mode: the fp32-mode bounds."""
+import numpy as np
+import pytest
+
+import oracle as O
+import scanet3_b200 as S
+from helpers import build_models, synth_classification
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+
+
+def rel_to_max(got, ref):
+    return float(np.max(np.abs(got.astype(np.float64) - np.asarray(ref, np.float64))) / (np.max(np.abs(ref)) + 1e-30))
+
+
+def check_two_steps(om, sm, oloss, sloss, x, y, batch, in_shape, out_shape, precision, rate=0.001, init=None):
+    steps = 2
+    e = S.Engine(sm, sloss, S.Adam(rate), batch, in_shape, out_shape, device=0, precision=precision)
+    oalg = O.Adam(rate)
+    _, mp, op = O.init_params(om, oalg, (batch,) + tuple(in_shape))
+    if init is not None:
+        mp = init(mp)
+        e.set_params(mp)
+        e.init_opt_params()
+    else:
+        e.init_params()
+    lm = O.LossModel(om, oloss)
+    fp32_class = precision != S.PREC_TF32
+    # ---- gradients from the shared initial state ----
+    gl, gg = e.compute_grads(x[:batch], y[:batch])
+    ol, og, _ = lm.grad_stateful(x[:batch], y[:batch], mp)
+    assert abs(gl - float(ol)) <= (1e-4 if fp32_class else 3e-3) * abs(float(ol)), (gl, float(ol))
+    for k in og:
+        if fp32_class:
+            assert rel_to_max(gg[k], og[k]) < 2e-4, (k, rel_to_max(gg[k], og[k]))
+        else:
+            a, b = gg[k].astype(np.float64).ravel(), np.asarray(og[k], np.float64).ravel()
+            cos = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-300))
+            assert cos > 0.995, (k, cos)
+            assert abs(np.linalg.norm(a) / (np.linalg.norm(b) + 1e-300) - 1) < 0.05, k
+    # ---- two optimizer steps ----
+    for t in range(1, steps + 1):
+        xb, yb = x[(t - 1) * batch:t * batch], y[(t - 1) * batch:t * batch]
+        loss = e.train_step(xb, yb, t)
+        mp, op, oloss_v = O.train_step(lm, oalg, xb, yb, mp, op, t)
+        assert abs(loss - float(oloss_v)) <= (1e-4 if fp32_class else 3e-3) * abs(float(oloss_v)), (t, loss, float(oloss_v))
+    got = e.get_model_params()
+    for k, v in mp.items():
+        err = np.abs(got[k].astype(np.float64) - np.asarray(v, np.float64))
+        assert float(err.max()) <= (2 if fp32_class else 3) * steps * rate + 1e-6, (k, float(err.max()))
+        if fp32_class:
+            off = err > (3e-5 + 2e-3 * np.abs(v))
+            assert float(off.mean()) < 1e-3, (k, float(off.mean()))
+    assert e.launch_count() > 0
+    e.close()
+
+
+@pytest.mark.parametrize("precision", [S.PREC_FP32, S.PREC_TF32, S.PREC_3XTF32], ids=["fp32", "tf32", "3xtf32"])
+def test_config4_wide_mlp_full_size(precision):
+    """BASELINE configs[3]: Dense(4096, ReLU) x 4 >> Dense(10, Softmax), batch 8192, 784 inputs (53.6 M parameters)"""
+    spec = [("dense", 4096, "relu")] * 4 + [("dense", 10, "softmax")]
+    om, sm = build_models(spec)
+    batch = 8192
+    x, y = synth_classification(batch * 2, (784,), 10, 1238)
+    x = (x - 0.5).astype(f32)
+    check_two_steps(om, sm, O.CategoricalCrossentropy, S.CategoricalCrossentropy, x, y, batch, (784,), (10,), precision)
+
+
+CIFAR = lambda mode: [("conv", 64, "relu", (3, 3), (1, 1), "Valid", False), ("bn", 0.99, mode), ("pool", (2, 2), (2, 2), "Valid"),
+                      ("conv", 128, "relu", (3, 3), (1, 1), "Valid", False), ("bn", 0.99, mode), ("pool", (2, 2), (2, 2), "Valid"),
+                      ("conv", 256, "relu", (3, 3), (1, 1), "Valid", False), ("bn", 0.99, mode), ("pool", (2, 2), (2, 2), "Valid"),
+                      ("flatten",), ("dense", 10, "softmax")]
+
+
+@pytest.mark.parametrize("mode", ["reference", "correct"])
+@pytest.mark.parametrize("precision", [S.PREC_FP32, S.PREC_TF32], ids=["fp32", "tf32"])
+def test_config5_cifar_batchnorm_cnn_full_size(precision, mode):
+    """BASELINE configs[4] (SURVEY 8d topology): Conv2D 64/128/256 + fused rank-4 BatchNorm + Pool2D(s2) + Dense, batch 256,
+    32x32x3, both `bn_mode`s (the reference's fused-output wiring quirk, SURVEY App. B-Q5, and the TF op as intended)"""
+    om, sm = build_models(CIFAR(mode))
+    batch = 256
+    x, y = synth_classification(batch * 2, (32, 32, 3), 10, 1239)
+    check_two_steps(om, sm, O.CategoricalCrossentropy, S.CategoricalCrossentropy, x, y, batch, (32, 32, 3), (10,), precision)
+
+
+@pytest.mark.parametrize("precision", [S.PREC_TF32, S.PREC_3XTF32], ids=["tf32", "3xtf32"])
+def test_config3_lstm_full_size_tensor_core_modes_against_the_oracle(precision):
+    """BASELINE configs[2]: LSTM(256) >> Dense(1, Tanh), MSE, seq len 64, batch 1024 -- the tensor-core modes against the ORACLE
+    (round 1 compared them with the repo's own fp32 engine only)"""
+    om, sm = build_models([("lstm", 256), ("dense", 1, "tanh")])
+    batch, t = 1024, 64
+    rng = np.random.Generator(np.random.PCG64(1237))
+    x = rng.uniform(0, 1, size=(batch * 2, t, 1)).astype(f32)
+    y = rng.uniform(0, 1, size=(batch * 2, 1)).astype(f32)
+    e = S.Engine(sm, S.MeanSquaredError, S.Adam(1e-3), batch, (t, 1), (1,), device=0, precision=precision)
+    e.init_params()
+    _, mp, op = O.init_params(om, O.Adam(1e-3), (batch, t, 1))
+    for k, v in e.get_model_params().items():  # the Orthogonal recurrent init runs through the host QR: same values on both sides
+        np.testing.assert_allclose(v, mp[k], rtol=0, atol=1e-6, err_msg=k)
+    lm = O.LossModel(om, O.MeanSquaredError)
+    gl, gg = e.compute_grads(x[:batch], y[:batch])
+    ol, og, _ = lm.grad_stateful(x[:batch], y[:batch], mp)
+    tol_l, tol_g = (4e-3, 1.5e-2) if precision == S.PREC_TF32 else (5e-5, 5e-4)
+    assert abs(gl - float(ol)) <= tol_l * abs(float(ol)), (gl, float(ol))
+    for k in og:
+        assert rel_to_max(gg[k], og[k]) < tol_g, (k, rel_to_max(gg[k], og[k]))
+    oalg = O.Adam(1e-3)
+    for s in (1, 2):
+        xb, yb = x[(s - 1) * batch:s * batch], y[(s - 1) * batch:s * batch]
+        loss = e.train_step(xb, yb, s)
+        mp, op, olv = O.train_step(lm, oalg, xb, yb, mp, op, s)
+        assert abs(loss - float(olv)) <= tol_l * abs(float(olv)), (s, loss, float(olv))
+    got = e.get_model_params()
+    for k, v in mp.items():
+        assert float(np.max(np.abs(got[k] - v))) <= 3 * 2 * 1e-3, k
+    e.close()
+
+
+def test_maximize_walks_up_the_gradient():
+    """Optimizer.maximize (Optimizer.scala:186,326-338): `w + delta` -- the same trajectory as the oracle's `minimizing=False`"""
+    om, sm = build_models([("dense", 8, "sigmoid"), ("dense", 4, "softmax")])
+    x, y = synth_classification(16 * 4, (12,), 4, 2)
+    e = S.Engine(sm, S.CategoricalCrossentropy, S.SGD(0.1), 16, (12,), (4,), device=0, minimizing=False)
+    e.init_params()
+    oalg = O.SGD(0.1)
+    _, mp, op = O.init_params(om, oalg, (16, 12))
+    lm = O.LossModel(om, O.CategoricalCrossentropy)
+    losses = []
+    for t in range(1, 5):
+        xb, yb = x[(t - 1) * 16:t * 16], y[(t - 1) * 16:t * 16]
+        loss = e.train_step(xb, yb, t)
+        mp, op, ol = O.train_step(lm, oalg, xb, yb, mp, op, t, minimizing=False)
+        assert abs(loss - float(ol)) <= 2e-5 * abs(float(ol)) + 1e-7
+        losses.append(loss)
+    got = e.get_model_params()
+    for k, v in mp.items():
+        np.testing.assert_allclose(got[k], v, rtol=1e-3, atol=2e-5, err_msg=k)
+    e.close()

@@ -110,8 +110,7 @@ def test_invalid_models_raise_like_the_reference():
         S.Engine(S.Dense(3), S.MeanSquaredError, S.SGD(), 2, (3,), (2,), device=-1)
     with pytest.raises(S.Unsupported):
         S.Conv2D(4, format="NCHW")
-    with pytest.raises(S.Unsupported):
-        S.maximize(S.Dense(1))
+    assert S.maximize(S.Dense(1))._c.minimizing is False  # Optimizer.maximize (Optimizer.scala:326-338)
     with pytest.raises(ValueError, match="only \\[Same, Valid\\] paddings are supported"):
         S.Pool2D(padding=((1, 0), (1, 0)))
     with pytest.raises(TypeError):  # builder incomplete: run() must not be callable (Optimizer.scala:256-310)
