@@ -10,8 +10,8 @@ whatever the gradient's magnitude, so a gradient whose sign is within rounding n
 the parameters are therefore checked by max |err| <= 2 * steps * rate and by the FRACTION of elements off by more than
 (rtol 2e-3, atol 3e-5), which must stay below 1e-3.  TF32 mode: loss rtol 3e-3, gradient direction cosine > 0.995 and norm within
 5 % (ReLU masks flip for pre-activations within the tf32 error of zero, tests/test_gpu_tf32.py), parameters max |err| <= 3 * steps
-* rate.  3xTF32 mode: the fp32-mode bounds.  LSTM (64 recurrent steps): per-tensor |err| <= tol * max(max|ref|, sqrt(loss)) -- the
-output bias gradient is a cancelling sum of 1024 terms of size ~|p - y| ~ sqrt(loss), so its natural scale is sqrt(loss), not
+* rate.  3xTF32 mode: the fp32-mode bounds.  LSTM (64 recurrent steps): per-tensor |err| <= tol * max|ref|, and tol * max(max|ref|, sqrt(loss)) for the
+output bias gradient, which is a cancelling sum of 1024 terms of size ~|p - y| ~ sqrt(loss), so its natural scale is sqrt(loss), not
 its own (small) value; tol = 1.5e-2 in TF32 and 2e-3 in 3xTF32."""
 import numpy as np
 import pytest
@@ -121,7 +121,9 @@ def test_config3_lstm_full_size_tensor_core_modes_against_the_oracle(precision):
     tol_l, tol_g = (4e-3, 1.5e-2) if precision == S.PREC_TF32 else (5e-5, 2e-3)
     assert abs(gl - float(ol)) <= tol_l * abs(float(ol)), (gl, float(ol))
     for k in og:
-        scale = max(float(np.max(np.abs(og[k]))), float(np.sqrt(ol)))
+        scale = float(np.max(np.abs(og[k])))
+        if np.size(og[k]) <= 16:  # the output layer's bias gradient: a cancelling sum, natural scale sqrt(loss)
+            scale = max(scale, float(np.sqrt(ol)))
         err = float(np.max(np.abs(gg[k].astype(np.float64) - np.asarray(og[k], np.float64))))
         assert err < tol_g * scale, (k, err, scale)
     oalg = O.Adam(1e-3)
