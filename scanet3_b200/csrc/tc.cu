@@ -81,21 +81,40 @@ struct IgemmParams {
   float* out;         // [n_img*Hg*Wg, ldc]: this launch writes columns [n0, n0 + N)
   int ldc, n0;        // output row pitch (all channels) and the first output channel of this launch
   int pt, pl;         // padding before (top, left) of the source grid: taps read (h + sign*kh - pt, w + sign*kw - pl)
+  int x3;             // 3xTF32: converter warps write lo = x - tf32(x) tiles behind the stage's [A | B]; D += A_hi.B_lo + A_lo.B_hi + A_hi.B_hi
 };
 
 constexpr int kIgemmThreads = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..5: epilogue
+constexpr int kIgemmThreadsX3 = 320;  // + warps 6..9: 3xTF32 converters (lo = x - tf32(x) for every word of a stage)
+// lo = x - tf32(x): kind::tf32 ignores the low 13 mantissa bits, so the tile TMA wrote IS the hi operand; the lo tile has the same
+// (swizzled) layout word for word.  128 threads walk `bytes` (multiple of 16).
+__device__ __forceinline__ void split_lo_tile(const uint8_t* hi_p, uint8_t* lo_p, int bytes, int t) {
+  const float4* hi = reinterpret_cast<const float4*>(hi_p);
+  float4* lo = reinterpret_cast<float4*>(lo_p);
+  for (int i = t; i < bytes / 16; i += 128) {
+    const float4 v = hi[i];
+    float4 r;
+    r.x = __fsub_rn(v.x, __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
+    r.y = __fsub_rn(v.y, __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
+    r.z = __fsub_rn(v.z, __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
+    r.w = __fsub_rn(v.w, __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+    lo[i] = r;
+  }
+}
 constexpr int kATileBytes = 128 * 128;
 
-__global__ void __launch_bounds__(kIgemmThreads, 1)
+__global__ void __launch_bounds__(kIgemmThreadsX3, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const IgemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stages x (A 16 KB | B N*128 B)] then barriers
+  // carve: [stages x (A 16 KB | B N*128 B  (| A_lo | B_lo  in 3xTF32 mode))] then barriers
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int b_tile_bytes = p.N * 128;
-  const int stage_bytes = kATileBytes + b_tile_bytes;
+  const int hi_bytes = kATileBytes + b_tile_bytes;
+  const int stage_bytes = p.x3 ? 2 * hi_bytes : hi_bytes;
   uint64_t* full_bar = (uint64_t*)(smem + (size_t)p.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
-  uint64_t* tmem_full = empty_bar + p.stages;
+  uint64_t* conv_bar = empty_bar + p.stages;  // 3xTF32: the stage's low-order tiles are written
+  uint64_t* tmem_full = conv_bar + p.stages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
 
@@ -111,6 +130,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&conv_bar[s], 4);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
@@ -126,7 +146,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   pdl_wait();  // the on-chip setup above overlapped the previous kernel; global memory from here on
   pdl_trigger();  // dependents may start their own on-chip setup now (they still wait for this grid before touching its output)
 
-  if (warp == 0) {
+  if (warp >= 6) {
+    // ================= 3xTF32 converters (launched only in that mode) =================
+    const int t = threadIdx.x - 192;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x)
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        uint8_t* st = smem + (size_t)stage * stage_bytes;
+        split_lo_tile(st, st + hi_bytes, hi_bytes, t);
+        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&conv_bar[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+  } else if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
       int stage = 0;
@@ -169,14 +204,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.N);
         uint32_t accumulate = 0;
         for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait(p.x3 ? &conv_bar[stage] : &full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes) >> 4;
           const uint32_t at = a_lo0 + sa, bt = b_lo0 + sa + (uint32_t)(kATileBytes >> 4);
+          if (p.x3) {
+            const uint32_t lo_off = (uint32_t)(hi_bytes >> 4);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {  // 4 x (K = 8 tf32) per 32-channel chunk
-            umma_tf32_elect(d_tmem, ((uint64_t)a_hi << 32) | (at + ks * 2), ((uint64_t)b_hi << 32) | (bt + ks * b_ks_step), idesc, accumulate);
-            accumulate = 1;
+            for (int ks = 0; ks < 4; ++ks) {  // small terms first: A_hi.B_lo, A_lo.B_hi, then A_hi.B_hi
+              const uint64_t da = ((uint64_t)a_hi << 32) | (at + ks * 2), db = ((uint64_t)b_hi << 32) | (bt + ks * b_ks_step);
+              umma_tf32_elect(d_tmem, da, db + lo_off, idesc, accumulate);
+              umma_tf32_elect(d_tmem, da + lo_off, db, idesc, 1u);
+              umma_tf32_elect(d_tmem, da, db, idesc, 1u);
+              accumulate = 1;
+            }
+          } else {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {  // 4 x (K = 8 tf32) per 32-channel chunk
+              umma_tf32_elect(d_tmem, ((uint64_t)a_hi << 32) | (at + ks * 2), ((uint64_t)b_hi << 32) | (bt + ks * b_ks_step), idesc, accumulate);
+              accumulate = 1;
+            }
           }
           umma_commit_elect(&empty_bar[stage]);  // smem slot is free once these MMAs have read it
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -185,7 +232,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else {
+  } else if (warp < 6) {
     // ================= epilogue: TMEM -> registers -> (ReLU) -> NHWC rows =================
     const int sub = warp & 3;  // TMEM sub-partition this warp may read: lanes [32*sub, 32*sub+32)
     const int row = sub * 32 + lane;
@@ -497,10 +544,11 @@ struct WgradParams {
   int stages;
   float* partial;  // [gridDim.x][taps*Cin*Cout]
   long long* dbg;  // developer timeline (SB_TC_DEBUG=1): 64 clock64 slots per CTA, null in production
+  int x3;          // 3xTF32: converter warps write the low-order tiles behind the stage's [dY | X taps]
 };
 constexpr int kWgradThreads = 192;
 
-__global__ void __launch_bounds__(kWgradThreads, 1)
+__global__ void __launch_bounds__(kIgemmThreadsX3, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, const WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -512,10 +560,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   const int box_bytes = krows * 128;        // one 32-channel box
   const int a_bytes = (p.Mh / 32) * box_bytes;
   const int b_bytes = taps * (p.Cin / 32) * box_bytes;
-  const int stage_bytes = ((a_bytes + b_bytes + 1023) / 1024) * 1024;
+  const int hi_bytes = ((a_bytes + b_bytes + 1023) / 1024) * 1024;
+  const int stage_bytes = p.x3 ? 2 * hi_bytes : hi_bytes;
   uint64_t* full_bar = (uint64_t*)(smem + (size_t)p.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
-  uint64_t* done_bar = empty_bar + p.stages;
+  uint64_t* conv_bar = empty_bar + p.stages;  // 3xTF32: the stage's low-order tiles are written
+  uint64_t* done_bar = conv_bar + p.stages;
   uint32_t* tmem_slot = (uint32_t*)(done_bar + 1);
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // shfl: provably warp-uniform
   const int ncols = taps * p.Cin;
@@ -528,6 +578,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&conv_bar[s], 4);
     }
     mbar_init(done_bar, 1);
     fence_barrier_init();
@@ -543,7 +594,21 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   if (threadIdx.x == 0) WG_T(2);
   const bool has_work = (int)blockIdx.x < p.n_chunks;
 
-  if (warp == 0) {
+  if (warp >= 6) {
+    // 3xTF32 converters (launched only in that mode): lo = x - tf32(x) for the stage's dY and X boxes
+    const int t = threadIdx.x - 192;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int ch = blockIdx.x; ch < p.n_chunks; ch += gridDim.x) {
+      mbar_wait(&full_bar[stage], phase);
+      uint8_t* st = smem + (size_t)stage * stage_bytes;
+      split_lo_tile(st, st + hi_bytes, a_bytes + b_bytes, t);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&conv_bar[stage]);
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -574,16 +639,24 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
       uint32_t accumulate = 0;
       int ti = 0;
       for (int ch = blockIdx.x; ch < p.n_chunks; ch += gridDim.x, ++ti) {
-        mbar_wait(&full_bar[stage], phase);
+        mbar_wait(p.x3 ? &conv_bar[stage] : &full_bar[stage], phase);
         tc_fence_after();
         if (lane == 0 && ti < 12) WG_T(8 + 2 * ti);
         const uint32_t sa = d_lo + (smem_u32(smem + (size_t)stage * stage_bytes) >> 4);
         uint32_t sb = sa + (uint32_t)(a_bytes >> 4);
+        const uint32_t lo_off = (uint32_t)(hi_bytes >> 4);
         for (int t = 0; t < taps; ++t, sb += b_tap) {
           const uint32_t d_tmem = tmem_base + (uint32_t)(t * p.Cin);
           uint32_t acc_t = accumulate;
           for (int ks = 0; ks < nks; ++ks) {
-            umma_tf32_elect(d_tmem, ((uint64_t)d_hi << 32) | (sa + ks * 64), ((uint64_t)d_hi << 32) | (sb + ks * 64), idesc, acc_t);
+            const uint64_t da = ((uint64_t)d_hi << 32) | (sa + ks * 64), db = ((uint64_t)d_hi << 32) | (sb + ks * 64);
+            if (p.x3) {  // small terms first: A_hi.B_lo, A_lo.B_hi, then A_hi.B_hi
+              umma_tf32_elect(d_tmem, da, db + lo_off, idesc, acc_t);
+              umma_tf32_elect(d_tmem, da + lo_off, db, idesc, 1u);
+              umma_tf32_elect(d_tmem, da, db, idesc, 1u);
+            } else {
+              umma_tf32_elect(d_tmem, da, db, idesc, acc_t);
+            }
             acc_t = 1;
           }
         }
@@ -594,7 +667,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
       }
       umma_commit_elect(done_bar);
     }
-  } else {
+  } else if (warp < 6) {
     // epilogue: partial[cta][(t*Cin + ci)*Cout + co] = D_t[co][ci]
     const int sub = warp & 3;
     float* part = p.partial + (size_t)blockIdx.x * p.KH * p.KW * p.Cin * p.Cout + (size_t)p.t0 * p.Cin * p.Cout + p.co0;
@@ -943,12 +1016,14 @@ static bool plan_halo(HaloParams& p, CUtensorMap* map, CUtensorMap* map_out, con
   return true;
 }
 
-static int igemm_smem(const IgemmParams& p) { return p.stages * (kATileBytes + p.N * 128) + 16 * (2 * p.stages + 4) + 16 + 1024; }
+static int igemm_smem(const IgemmParams& p) { return p.stages * (p.x3 ? 2 : 1) * (kATileBytes + p.N * 128) + 16 * (2 * p.stages + 4) + 16 + 1024; }
 
 void tc_plan_layers(sb_engine* e) {
   if (e->train.precision == SB_PREC_FP32) return;
-  // SB_PREC_3XTF32: MatMul contractions run the split-operand 3xTF32 GEMM (fp32-class accuracy on the tensor cores);
-  // convolutions stay on the fp32 FFMA kernels in that mode
+  // SB_PREC_3XTF32: every contraction runs with split operands (hi = tf32(x), lo = x - hi; A_hi.B_lo + A_lo.B_hi + A_hi.B_hi):
+  // fp32-class accuracy on the tensor cores.  MatMul: gemm_tf32_kernel; Conv2D fprop / dgrad / wgrad: the per-tap kernels
+  // (conv_igemm_kernel, conv_wgrad_kernel) with four converter warps -- the halo kernels keep the whole filter resident in
+  // shared memory and have no room for the second copy of every tile.
   const int x3 = e->train.precision == SB_PREC_3XTF32 ? 1 : 0;
   int dev_smem = 0;
   SB_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device));
@@ -995,7 +1070,7 @@ void tc_plan_layers(sb_engine* e) {
       L.tc_plan = D;
       continue;
     }
-    if (x3 || L.d.kind != SB_LAYER_CONV2D || !conv_fits(L.cg)) continue;
+    if (L.d.kind != SB_LAYER_CONV2D || !conv_fits(L.cg)) continue;
     const ConvGeom& g = L.cg;
     ConvTcPlan* P = new ConvTcPlan();
     float* x = e->acts[L.buf_in];
@@ -1020,8 +1095,8 @@ void tc_plan_layers(sb_engine* e) {
       p.relu = P->relu_fused ? 1 : 0;
       p.thr = P->relu_fused ? e->L[li + 1].d.relu_threshold : 0.f;
       p.out = y;
-      p.ldc = g.Cout; p.n0 = 0; p.pt = g.PT; p.pl = g.PL;
-      p.stages = std::max(2, std::min(8, (dev_smem - 2048) / (kATileBytes + p.N * 128)));
+      p.ldc = g.Cout; p.n0 = 0; p.pt = g.PT; p.pl = g.PL; p.x3 = x3;
+      p.stages = std::max(2, std::min(8, (dev_smem - 2048) / ((x3 ? 2 : 1) * (kATileBytes + p.N * 128))));
       uint64_t xd[4] = {(uint64_t)g.Cin, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.N};
       uint32_t xb[4] = {32, (uint32_t)p.Wg, (uint32_t)p.BH, 1};
       P->map_x_fwd = make_map(x, 4, xd, xb);
@@ -1031,7 +1106,7 @@ void tc_plan_layers(sb_engine* e) {
       P->fwd_smem = igemm_smem(p);
       P->fwd_grid = std::min(p.n_tiles, kNumSMs);
       const char* h = getenv("SB_TC_HALO");
-      const bool halo_on = !(h && h[0] == '0');
+      const bool halo_on = !(h && h[0] == '0') && !x3;
       if (halo_on && plan_halo(P->hfwd, &P->map_x_h, &P->map_y_out, x, g.Cin, g.W, g.H, g.N, g.OH, g.OW, g.KH, g.KW, g.Cout, 1, g.Cin, 0, -g.PL,
                                -g.PT, y, dev_smem, &P->hfwd_smem)) {
         P->hfwd.relu = p.relu; P->hfwd.thr = p.thr;
@@ -1050,8 +1125,8 @@ void tc_plan_layers(sb_engine* e) {
       p.b_rows_per_tap = g.Cin;
       p.relu = 0; p.thr = 0.f;
       p.out = dx;
-      p.ldc = g.Cin; p.n0 = 0; p.pt = -g.PT; p.pl = -g.PL;
-      p.stages = std::max(2, std::min(8, (dev_smem - 2048) / (kATileBytes + p.N * 128)));
+      p.ldc = g.Cin; p.n0 = 0; p.pt = -g.PT; p.pl = -g.PL; p.x3 = x3;
+      p.stages = std::max(2, std::min(8, (dev_smem - 2048) / ((x3 ? 2 : 1) * (kATileBytes + p.N * 128))));
       uint64_t yd[4] = {(uint64_t)g.Cout, (uint64_t)g.OW, (uint64_t)g.OH, (uint64_t)g.N};
       uint32_t yb[4] = {32, (uint32_t)p.Wg, (uint32_t)p.BH, 1};
       P->map_dy_dg = make_map(dy, 4, yd, yb);
@@ -1061,7 +1136,7 @@ void tc_plan_layers(sb_engine* e) {
       P->dg_smem = igemm_smem(p);
       P->dg_grid = std::min(p.n_tiles, kNumSMs);
       const char* h = getenv("SB_TC_HALO");
-      const bool halo_on = !(h && h[0] == '0');
+      const bool halo_on = !(h && h[0] == '0') && !x3;
       if (halo_on && plan_halo(P->hdg, &P->map_dy_h, &P->map_dx_out, dy, g.Cout, g.OW, g.OH, g.N, g.H, g.W, g.KH, g.KW, g.Cin, 0, g.Cin, 1,
                                -(g.KW - 1 - g.PL), -(g.KH - 1 - g.PT), dx, dev_smem, &P->hdg_smem)) {
         P->hdg_grid = std::min(P->hdg.n_tiles, kNumSMs);
@@ -1074,10 +1149,10 @@ void tc_plan_layers(sb_engine* e) {
       const int Mh = g.Cout % 128 == 0 ? 128 : 64;
       const int tpp = std::max(1, std::min(taps, 512 / g.Cin));  // taps per launch
       WgradParams p{};
-      p.KH = g.KH; p.KW = g.KW; p.Cin = g.Cin; p.Cout = g.Cout; p.Mh = Mh; p.pt = g.PT; p.pl = g.PL;
+      p.KH = g.KH; p.KW = g.KW; p.Cin = g.Cin; p.Cout = g.Cout; p.Mh = Mh; p.pt = g.PT; p.pl = g.PL; p.x3 = x3;
       p.WK = (g.OW + 7) / 8 * 8;
       const int box_row_bytes = p.WK * 128;  // one grid row of one 32-channel box
-      const int per_bh = (Mh / 32 + tpp * (g.Cin / 32)) * box_row_bytes;
+      const int per_bh = (x3 ? 2 : 1) * (Mh / 32 + tpp * (g.Cin / 32)) * box_row_bytes;
       // deepest chunk that still leaves >= 2 pipeline stages
       p.BH = std::max(1, std::min(g.OH, (dev_smem - 4096) / 2 / per_bh));
       while (p.BH > 1 && 256 / p.WK < p.BH) --p.BH;  // TMA box dims <= 256
@@ -1090,7 +1165,7 @@ void tc_plan_layers(sb_engine* e) {
         for (int co0 = 0; co0 < g.Cout; co0 += Mh) {
           WgradParams q = p;
           q.t0 = t0; q.nt = std::min(tpp, taps - t0); q.co0 = co0;
-          const int stage_bytes = ((p.BH * (Mh / 32 + q.nt * (g.Cin / 32)) * box_row_bytes + 1023) / 1024) * 1024;
+          const int stage_bytes = (x3 ? 2 : 1) * (((p.BH * (Mh / 32 + q.nt * (g.Cin / 32)) * box_row_bytes + 1023) / 1024) * 1024);
           q.stages = std::max(1, std::min(4, (dev_smem - 4096) / stage_bytes));
           const int smem = q.stages * stage_bytes + 16 * (2 * q.stages + 2) + 16 + 1024;
           if (smem > dev_smem) P->wg_ok = false;
@@ -1121,7 +1196,7 @@ void tc_plan_layers(sb_engine* e) {
       // box per chunk instead of one per tap removes the per-tap kernel's 9x redundant L2->SMEM traffic, which is what bounds it
       // (profiles/r1_notes.md item 8).  SB_TC_HALO_WGRAD=0 selects the per-tap kernel.
       const char* h = getenv("SB_TC_HALO_WGRAD");
-      const bool on = !(h && h[0] == '0');
+      const bool on = !(h && h[0] == '0') && !x3;
       WgradHaloParams& p = P->hwg;
       const int n_acc = g.KH * (g.Cin / 32);
       if (on && P->wg_ok && g.KW <= 4 && n_acc * g.Cout <= 512) {
@@ -1270,7 +1345,7 @@ bool tc_conv_fwd(sb_engine* e, LayerPlan& L, int) {
     SB_LAUNCHED();
     return true;
   }
-  launch_k(conv_igemm_kernel, P->fwd_grid, kIgemmThreads, P->fwd_smem, e->stream, P->map_x_fwd, P->map_w_fwd, P->fwd);
+  launch_k(conv_igemm_kernel, P->fwd_grid, P->fwd.x3 ? kIgemmThreadsX3 : kIgemmThreads, P->fwd_smem, e->stream, P->map_x_fwd, P->map_w_fwd, P->fwd);
   SB_LAUNCHED();
   return true;
 }
@@ -1433,7 +1508,8 @@ bool tc_conv_wgrad(sb_engine* e, LayerPlan& L, int, cudaStream_t side) {
     return true;
   }
   for (size_t i = 0; i < P->wg_list.size(); ++i) {
-    launch_k(conv_wgrad_kernel, P->wg_grid, kWgradThreads, P->wg_smem_list[i], st, P->map_dy_wg, P->map_x_wg, P->wg_list[i]);
+    launch_k(conv_wgrad_kernel, P->wg_grid, P->wg_list[i].x3 ? kIgemmThreadsX3 : kWgradThreads, P->wg_smem_list[i], st, P->map_dy_wg,
+             P->map_x_wg, P->wg_list[i]);
     SB_LAUNCHED();
   }
   partial_reduce(P->wg_partial, e->grads + e->params[L.p_w].offset, n, P->wg_grid, st);  // fixed order, 8-way parallel
@@ -1451,7 +1527,7 @@ bool tc_conv_dgrad(sb_engine* e, LayerPlan& L, int) {
     SB_LAUNCHED();
     return true;
   }
-  launch_k(conv_igemm_kernel, P->dg_grid, kIgemmThreads, P->dg_smem, e->stream, P->map_dy_dg, P->map_w_dg, P->dg);
+  launch_k(conv_igemm_kernel, P->dg_grid, P->dg.x3 ? kIgemmThreadsX3 : kIgemmThreads, P->dg_smem, e->stream, P->map_dy_dg, P->map_w_dg, P->dg);
   SB_LAUNCHED();
   return true;
 }

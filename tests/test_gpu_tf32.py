@@ -286,3 +286,50 @@ def test_3xtf32_dense_holds_fp32_tolerance(name, spec, batch, nin):
     assert any(n.startswith("dense_") and "tcgen05" in n for n in names), names  # on the tensor cores, not the FFMA fallback
     for e in (e32, e3x, e1x):
         e.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# 3xTF32 on the convolution kernels (fprop / dgrad / wgrad on tcgen05 with split operands): north-star "a 3xTF32 option to hold
+# fp32 tolerance" for Conv2D as implicit GEMM
+# ---------------------------------------------------------------------------------------------------------------
+X3_CONV_STACKS = [c for c in CONV_STACKS if c[0] in ("lenet28_sigmoid", "tiny_linear", "cout128_tanh", "cifar_tail_tanh", "same_pad_tanh",
+                                                     "explicit_pad_tanh", "ragged_1x3_tanh", "k2x2_no_relu")]
+
+
+@pytest.mark.parametrize("name,spec,batch,in_shape", X3_CONV_STACKS, ids=[c[0] for c in X3_CONV_STACKS])
+def test_3xtf32_conv_holds_fp32_tolerance(name, spec, batch, in_shape):
+    om, sm = build_models(spec)
+    es = [S.Engine(sm, S.CategoricalCrossentropy, S.Adam(0.001), batch, in_shape, (10,), device=0, precision=p)
+          for p in (S.PREC_FP32, S.PREC_3XTF32, S.PREC_TF32)]
+    for e in es:
+        e.init_params()
+    e32, e3x, e1x = es
+    x, y = synth_classification(batch, in_shape, 10, 21)
+    p32, p3x, p1x = e32.predict(x), e3x.predict(x), e1x.predict(x)
+    assert rel_to_max(p3x, p32) < 5e-6
+    assert rel_to_max(p1x, p32) > 10 * rel_to_max(p3x, p32)  # plain TF32 is far outside this band: the split operands do the work
+    l32, g32 = e32.compute_grads(x, y)
+    l3x, g3x = e3x.compute_grads(x, y)
+    assert abs(l3x - l32) <= 2e-6 * abs(l32)
+    _, mp, _ = O.init_params(om, O.Adam(0.001), (batch,) + tuple(in_shape))
+    _, og, _ = O.LossModel(om, O.CategoricalCrossentropy).grad_stateful(x, y, mp)
+    for k in g32:
+        assert rel_to_max(g3x[k], g32[k]) < 2e-5, (k, "vs the fp32 engine")
+        assert rel_to_max(g3x[k], og[k]) < 5e-5, (k, "vs the oracle")
+    e3x.profile_enable(True)
+    e3x.compute_grads(x, y)
+    names = [r["name"] for r in e3x.profile()]
+    e3x.profile_enable(False)
+    assert any(n.startswith("conv2d_fwd") and "tcgen05" in n for n in names), names
+    assert any(n.startswith("conv2d_wgrad") and "tcgen05" in n for n in names), names
+    assert any(n.startswith("conv2d_dgrad") and "tcgen05" in n for n in names), names
+    for e in es:
+        e.close()
+
+
+def test_3xtf32_lenet_config2_full_size_meets_the_fp32_trajectory_tolerances():
+    """BASELINE config 2 at full size with every contraction on the tensor cores in 3xTF32: the SAME tolerances as the fp32 parity run
+    (tests/test_gpu_parity.py::test_lenet_config2_full_size) against the oracle"""
+    from test_gpu_parity import LENET, run_trajectory
+    run_trajectory(LENET, "cce", "adam", dict(rate=0.001), batch=100, in_shape=(28, 28, 1), classes=10, steps=3, rtol=2e-3, atol=3e-5,
+                   loss_rtol=5e-5, precision=S.PREC_3XTF32)
