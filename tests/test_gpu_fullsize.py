@@ -2,16 +2,18 @@
 covered at "pattern" size).  Two train steps each: the first pins forward + gradients + the optimizer from the shared initial
 state, the second pins that the updated state feeds the next step; cost is dominated by the NumPy oracle (seconds).
 
-Tolerances.  fp32 mode (FFMA contractions): loss rtol 1e-4; gradients relative L2 error <= 1e-3 and |err| <= 2e-2 * max|ref| per
-tensor -- reductions of up to 8192 x 4096 terms run in a different order than NumPy's, and at these sizes a few hundred of the 33 M
-ReLU pre-activations per layer sit within fp32 rounding of zero: their masks flip and each flip changes single terms of the
-gradient sums by 100 % (measured: 5e-3 of max on a bias gradient of config 4); parameters after Adam steps: an Adam step moves every weight by about `rate`
+Tolerances.  fp32 mode (FFMA contractions): loss rtol 1e-4; gradients are judged against the oracle run in FLOAT64 -- the engine's
+relative L2 error per tensor must stay within 8x the error the float32 oracle itself makes against that truth (+ 1e-5): reductions
+of up to 8192 x 4096 terms run in a different order than NumPy's, a few hundred of the 33 M ReLU pre-activations per layer sit
+within fp32 rounding of zero (their masks flip and each flip changes single terms of the gradient sums by 100 %), and the
+BatchNorm backward subtracts nearly equal sums -- measured 5e-3 of max on a bias gradient of config 4 and 1e-2 relative L2 on the
+last conv's filter gradient of config 5 between two float32 implementations; parameters after Adam steps: an Adam step moves every weight by about `rate`
 whatever the gradient's magnitude, so a gradient whose sign is within rounding noise of zero moves its weight the other way --
 the parameters are therefore checked by max |err| <= 2 * steps * rate and by the FRACTION of elements off by more than
 (rtol 2e-3, atol 3e-5), which must stay below 1e-3.  TF32 mode: loss rtol 3e-3, gradient direction cosine > 0.995 and norm within
 5 % (ReLU masks flip for pre-activations within the tf32 error of zero, tests/test_gpu_tf32.py), parameters max |err| <= 3 * steps
 * rate.  3xTF32 mode: the fp32-mode bounds.  LSTM (64 recurrent steps): per-tensor |err| <= tol * max|ref|, and tol * max(max|ref|, sqrt(loss)) for the
-output bias gradient, which is a cancelling sum of 1024 terms of size ~|p - y| ~ sqrt(loss), so its natural scale is sqrt(loss), not
+output layer's (Dense(1) >> Bias) gradients, which are cancelling sums of 1024 terms of size ~|p - y| ~ sqrt(loss), so its natural scale is sqrt(loss), not
 its own (small) value; tol = 1.5e-2 in TF32 and 2e-3 in 3xTF32."""
 import numpy as np
 import pytest
@@ -45,12 +47,15 @@ def check_two_steps(om, sm, oloss, sloss, x, y, batch, in_shape, out_shape, prec
     gl, gg = e.compute_grads(x[:batch], y[:batch])
     ol, og, _ = lm.grad_stateful(x[:batch], y[:batch], mp)
     assert abs(gl - float(ol)) <= (1e-4 if fp32_class else 3e-3) * abs(float(ol)), (gl, float(ol))
+    if fp32_class:  # the float64 truth, and how far the float32 oracle itself is from it
+        _, o64, _ = lm.grad_stateful(x[:batch].astype(np.float64), y[:batch].astype(np.float64),
+                                     {k: np.asarray(v, np.float64) for k, v in mp.items()})
     for k in og:
         if fp32_class:
-            a, b = gg[k].astype(np.float64).ravel(), np.asarray(og[k], np.float64).ravel()
-            rel_l2 = float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-300))
-            assert rel_l2 < 1e-3, (k, rel_l2)
-            assert rel_to_max(gg[k], og[k]) < 2e-2, (k, rel_to_max(gg[k], og[k]))
+            t = np.asarray(o64[k], np.float64).ravel()
+            err_engine = float(np.linalg.norm(gg[k].astype(np.float64).ravel() - t) / (np.linalg.norm(t) + 1e-300))
+            err_oracle = float(np.linalg.norm(np.asarray(og[k], np.float64).ravel() - t) / (np.linalg.norm(t) + 1e-300))
+            assert err_engine <= 8 * err_oracle + 1e-5, (k, err_engine, err_oracle)
         else:
             a, b = gg[k].astype(np.float64).ravel(), np.asarray(og[k], np.float64).ravel()
             cos = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-300))
@@ -118,11 +123,11 @@ def test_config3_lstm_full_size_tensor_core_modes_against_the_oracle(precision):
     lm = O.LossModel(om, O.MeanSquaredError)
     gl, gg = e.compute_grads(x[:batch], y[:batch])
     ol, og, _ = lm.grad_stateful(x[:batch], y[:batch], mp)
-    tol_l, tol_g = (4e-3, 1.5e-2) if precision == S.PREC_TF32 else (5e-5, 2e-3)
+    tol_l, tol_g = (4e-3, 1.5e-2) if precision == S.PREC_TF32 else (5e-4, 2e-3)  # (fp32 run of this config: loss_rtol 5e-4)
     assert abs(gl - float(ol)) <= tol_l * abs(float(ol)), (gl, float(ol))
     for k in og:
         scale = float(np.max(np.abs(og[k])))
-        if np.size(og[k]) <= 16:  # the output layer's bias gradient: a cancelling sum, natural scale sqrt(loss)
+        if k.startswith(("1/", "2/")):  # the output layer Dense(1) >> Bias: cancelling sums over the batch, natural scale sqrt(loss)
             scale = max(scale, float(np.sqrt(ol)))
         err = float(np.max(np.abs(gg[k].astype(np.float64) - np.asarray(og[k], np.float64))))
         assert err < tol_g * scale, (k, err, scale)
