@@ -2,15 +2,17 @@
 covered at "pattern" size).  Two train steps each: the first pins forward + gradients + the optimizer from the shared initial
 state, the second pins that the updated state feeds the next step; cost is dominated by the NumPy oracle (seconds).
 
-Tolerances.  fp32 mode (FFMA contractions): loss rtol 1e-4; gradients are judged against the oracle run in FLOAT64 -- the engine's
-relative L2 error per tensor must stay within 8x the error the float32 oracle itself makes against that truth (+ 1e-5): reductions
+Tolerances.  fp32 mode (FFMA contractions): everything is judged against the oracle run in FLOAT64, with the float32 oracle's own
+distance from that truth as the yardstick.  Loss: rtol 1e-4 on the first step, then within 4x the float32 oracle's drift.
+Gradients: the engine's relative L2 error per tensor must stay within 8x the float32 oracle's (+ 2e-4: sequential fp32 column sums
+of 8192 rows against NumPy's pairwise ones): reductions
 of up to 8192 x 4096 terms run in a different order than NumPy's, a few hundred of the 33 M ReLU pre-activations per layer sit
 within fp32 rounding of zero (their masks flip and each flip changes single terms of the gradient sums by 100 %), and the
 BatchNorm backward subtracts nearly equal sums -- measured 5e-3 of max on a bias gradient of config 4 and 1e-2 relative L2 on the
 last conv's filter gradient of config 5 between two float32 implementations; parameters after Adam steps: an Adam step moves every weight by about `rate`
 whatever the gradient's magnitude, so a gradient whose sign is within rounding noise of zero moves its weight the other way --
 the parameters are therefore checked by max |err| <= 2 * steps * rate and by the FRACTION of elements off by more than
-(rtol 2e-3, atol 3e-5), which must stay below 1e-3.  TF32 mode: loss rtol 3e-3, gradient direction cosine > 0.995 and norm within
+(rtol 2e-3, atol 3e-5), which must stay below twice the float32 oracle's own fraction + 1e-3.  TF32 mode: loss rtol 3e-3, gradient direction cosine > 0.995 and norm within
 5 % (ReLU masks flip for pre-activations within the tf32 error of zero, tests/test_gpu_tf32.py), parameters max |err| <= 3 * steps
 * rate.  3xTF32 mode: the fp32-mode bounds.  LSTM (64 recurrent steps): per-tensor |err| <= tol * max|ref|, and tol * max(max|ref|, sqrt(loss)) for the
 output layer's (Dense(1) >> Bias) gradients, which are cancelling sums of 1024 terms of size ~|p - y| ~ sqrt(loss), so its natural scale is sqrt(loss), not
@@ -30,50 +32,56 @@ def rel_to_max(got, ref):
     return float(np.max(np.abs(got.astype(np.float64) - np.asarray(ref, np.float64))) / (np.max(np.abs(ref)) + 1e-30))
 
 
-def check_two_steps(om, sm, oloss, sloss, x, y, batch, in_shape, out_shape, precision, rate=0.001, init=None):
+def rel_l2(a, t):
+    a, t = np.asarray(a, np.float64).ravel(), np.asarray(t, np.float64).ravel()
+    return float(np.linalg.norm(a - t) / (np.linalg.norm(t) + 1e-300))
+
+
+def check_two_steps(om, sm, oloss, sloss, x, y, batch, in_shape, out_shape, precision, rate=0.001):
+    """The oracle runs twice: in float64 (the truth) and in float32 (how far a correct float32 implementation may drift from it --
+    on config 5 the float32 oracle's second-step loss is 9.5e-4 off the float64 one and 32 % of conv1's weights sit outside
+    (rtol 2e-3, atol 3e-5) after two Adam steps, while the engine's loss agrees with the float64 run to 1e-6)."""
     steps = 2
     e = S.Engine(sm, sloss, S.Adam(rate), batch, in_shape, out_shape, device=0, precision=precision)
     oalg = O.Adam(rate)
     _, mp, op = O.init_params(om, oalg, (batch,) + tuple(in_shape))
-    if init is not None:
-        mp = init(mp)
-        e.set_params(mp)
-        e.init_opt_params()
-    else:
-        e.init_params()
+    e.init_params()
     lm = O.LossModel(om, oloss)
     fp32_class = precision != S.PREC_TF32
+    f64 = lambda d: {k: np.asarray(v, np.float64) for k, v in d.items()}
+    x64, y64 = x.astype(np.float64), y.astype(np.float64)
     # ---- gradients from the shared initial state ----
     gl, gg = e.compute_grads(x[:batch], y[:batch])
     ol, og, _ = lm.grad_stateful(x[:batch], y[:batch], mp)
-    assert abs(gl - float(ol)) <= (1e-4 if fp32_class else 3e-3) * abs(float(ol)), (gl, float(ol))
-    if fp32_class:  # the float64 truth, and how far the float32 oracle itself is from it
-        _, o64, _ = lm.grad_stateful(x[:batch].astype(np.float64), y[:batch].astype(np.float64),
-                                     {k: np.asarray(v, np.float64) for k, v in mp.items()})
-    for k in og:
+    tl, tg, _ = lm.grad_stateful(x64[:batch], y64[:batch], f64(mp))
+    assert abs(gl - float(tl)) <= (1e-4 if fp32_class else 3e-3) * abs(float(tl)), (gl, float(tl))
+    for k in tg:
         if fp32_class:
-            t = np.asarray(o64[k], np.float64).ravel()
-            err_engine = float(np.linalg.norm(gg[k].astype(np.float64).ravel() - t) / (np.linalg.norm(t) + 1e-300))
-            err_oracle = float(np.linalg.norm(np.asarray(og[k], np.float64).ravel() - t) / (np.linalg.norm(t) + 1e-300))
-            assert err_engine <= 8 * err_oracle + 1e-5, (k, err_engine, err_oracle)
+            err_engine, err_oracle = rel_l2(gg[k], tg[k]), rel_l2(og[k], tg[k])
+            assert err_engine <= 8 * err_oracle + 2e-4, (k, err_engine, err_oracle)
         else:
-            a, b = gg[k].astype(np.float64).ravel(), np.asarray(og[k], np.float64).ravel()
+            a, b = gg[k].astype(np.float64).ravel(), np.asarray(tg[k], np.float64).ravel()
             cos = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-300))
             assert cos > 0.995, (k, cos)
             assert abs(np.linalg.norm(a) / (np.linalg.norm(b) + 1e-300) - 1) < 0.05, k
     # ---- two optimizer steps ----
+    mp32, op32, mp64, op64 = mp, op, f64(mp), f64(op)
     for t in range(1, steps + 1):
-        xb, yb = x[(t - 1) * batch:t * batch], y[(t - 1) * batch:t * batch]
-        loss = e.train_step(xb, yb, t)
-        mp, op, oloss_v = O.train_step(lm, oalg, xb, yb, mp, op, t)
-        assert abs(loss - float(oloss_v)) <= (1e-4 if fp32_class else 3e-3) * abs(float(oloss_v)), (t, loss, float(oloss_v))
+        sl = slice((t - 1) * batch, t * batch)
+        loss = e.train_step(x[sl], y[sl], t)
+        mp32, op32, l32 = O.train_step(lm, oalg, x[sl], y[sl], mp32, op32, t)
+        mp64, op64, l64 = O.train_step(lm, oalg, x64[sl], y64[sl], mp64, op64, t)
+        drift = abs(float(l32) - float(l64))
+        bound = max(4 * drift, 1e-4 * abs(float(l64))) if fp32_class else 3e-3 * abs(float(l64))
+        assert abs(loss - float(l64)) <= bound, (t, loss, float(l64), float(l32))
     got = e.get_model_params()
-    for k, v in mp.items():
-        err = np.abs(got[k].astype(np.float64) - np.asarray(v, np.float64))
+    for k, v in mp64.items():
+        err = np.abs(got[k].astype(np.float64) - v)
         assert float(err.max()) <= (2 if fp32_class else 3) * steps * rate + 1e-6, (k, float(err.max()))
         if fp32_class:
-            off = err > (3e-5 + 2e-3 * np.abs(v))
-            assert float(off.mean()) < 1e-3, (k, float(off.mean()))
+            off = float((err > (3e-5 + 2e-3 * np.abs(v))).mean())
+            off_oracle = float((np.abs(np.asarray(mp32[k], np.float64) - v) > (3e-5 + 2e-3 * np.abs(v))).mean())
+            assert off <= 2 * off_oracle + 1e-3, (k, off, off_oracle)
     assert e.launch_count() > 0
     e.close()
 
