@@ -38,8 +38,29 @@ static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) 
 // (pdl_prologue); the tensor-core kernels run their on-chip setup (mbarrier init, TMEM allocation, tensor-map prefetch) first.
 // The instruction is a no-op when a kernel is launched without the PDL attribute (SB_PDL=0).
 #ifdef __CUDACC__
+// ---- in-situ step timeline (SB_TRACE=1, developer aid) ----------------------------------------------------------------
+// Every kernel of the engine passes griddepcontrol.wait exactly once; with tracing on, the first thread of its first CTA then
+// appends %globaltimer to a device buffer (slot 0 = running count).  Inside a replayed CUDA graph this gives the start-to-start
+// interval of consecutive kernels -- what each kernel costs the step WITH the overlap programmatic launches buy, which neither
+// ncu (serialised, cold prologues) nor eager event timing (launch gaps) can show.  One __constant__ pointer per translation unit
+// (no relocatable device code in this build); null in production: the cost is one uniform constant load per thread.
+static __constant__ unsigned long long* sb_trace_buf_c = nullptr;
+static inline void sb_trace_set_local(unsigned long long* p) { cudaMemcpyToSymbol(sb_trace_buf_c, &p, sizeof p); }
+constexpr int kTraceSlots = 1 << 16;
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  unsigned long long* tb = sb_trace_buf_c;
+  if (tb != nullptr && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const unsigned long long slot = 2 * atomicAdd(tb, 1ull) + 2;  // two words per event: time, (gridDim.x << 16 | blockDim.x)
+    if (slot + 1 < (unsigned long long)kTraceSlots) {
+      tb[slot] = t;
+      tb[slot + 1] = ((unsigned long long)gridDim.x << 16) | blockDim.x;
+    }
+  }
+}
 __device__ __forceinline__ void pdl_prologue() { pdl_wait(); }
 // Wait, then let the dependents launch: their CTAs fill whatever this grid leaves free and run their own pre-wait setup (a
 // tensor-core kernel's barrier init, TMEM allocation, filter fill) under it; they still block in griddepcontrol.wait until this

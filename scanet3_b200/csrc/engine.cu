@@ -77,6 +77,35 @@ extern "C" int sb_device_count(void) {
   return n;
 }
 
+namespace sb {
+void trace_set_kernels_simt(unsigned long long*); void trace_set_kernels_fast(unsigned long long*); void trace_set_tc(unsigned long long*);
+void trace_set_tc_gemm(unsigned long long*); void trace_set_lstm(unsigned long long*); void trace_set_rnn(unsigned long long*);
+void trace_set_group(unsigned long long*);
+}  // namespace sb
+// SB_TRACE timeline (common.cuh): sb_trace_begin points every translation unit's kernels at a fresh device buffer,
+// sb_trace_read copies the stamps back (count first) and switches tracing off again.
+static unsigned long long* g_trace_dev = nullptr;
+static void trace_point_all(unsigned long long* p) {
+  sb::trace_set_kernels_simt(p); sb::trace_set_kernels_fast(p); sb::trace_set_tc(p); sb::trace_set_tc_gemm(p);
+  sb::trace_set_lstm(p); sb::trace_set_rnn(p); sb::trace_set_group(p);
+}
+extern "C" int sb_internal_trace_begin(void) {
+  SB_API_BEGIN
+  if (!g_trace_dev) SB_CUDA(cudaMalloc((void**)&g_trace_dev, (size_t)sb::kTraceSlots * 8));
+  SB_CUDA(cudaMemset(g_trace_dev, 0, (size_t)sb::kTraceSlots * 8));
+  trace_point_all(g_trace_dev);
+  SB_CUDA(cudaDeviceSynchronize());
+  SB_API_END
+}
+extern "C" int sb_internal_trace_read(unsigned long long* out, int cap) {
+  SB_API_BEGIN
+  if (!g_trace_dev || !out || cap < 1) SB_FAIL(SB_ERR_INVALID_ARG, "no trace in progress");
+  SB_CUDA(cudaDeviceSynchronize());
+  SB_CUDA(cudaMemcpy(out, g_trace_dev, (size_t)std::min(cap, sb::kTraceSlots) * 8, cudaMemcpyDeviceToHost));
+  trace_point_all(nullptr);
+  SB_API_END
+}
+
 static void need_device(const sb_engine* e) {
   if (e == nullptr) SB_FAIL(SB_ERR_INVALID_ARG, "null engine");
   if (e->plan_only)

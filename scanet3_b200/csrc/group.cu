@@ -580,3 +580,7 @@ extern "C" void sb_group_destroy(sb_group* g) {
       if (c) g->nccl.CommDestroy(c);
   delete g;
 }
+
+namespace sb {
+void trace_set_group(unsigned long long* p) { sb_trace_set_local(p); }  // SB_TRACE timeline buffer of this translation unit
+}  // namespace sb

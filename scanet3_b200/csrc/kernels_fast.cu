@@ -1664,3 +1664,7 @@ bool head_bias_softmax_cce(float* z, const float* partial, int chunks, const flo
 }
 
 }  // namespace sb
+
+namespace sb {
+void trace_set_kernels_fast(unsigned long long* p) { sb_trace_set_local(p); }  // SB_TRACE timeline buffer of this translation unit
+}  // namespace sb

@@ -1282,3 +1282,7 @@ void philox_fill(float* p, long long n, unsigned long long seed, int normal, flo
 }
 
 }  // namespace sb
+
+namespace sb {
+void trace_set_kernels_simt(unsigned long long* p) { sb_trace_set_local(p); }  // SB_TRACE timeline buffer of this translation unit
+}  // namespace sb

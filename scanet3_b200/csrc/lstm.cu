@@ -475,3 +475,7 @@ void lstm_free(sb_engine* e) {
 }
 
 }  // namespace sb
+
+namespace sb {
+void trace_set_lstm(unsigned long long* p) { sb_trace_set_local(p); }  // SB_TRACE timeline buffer of this translation unit
+}  // namespace sb

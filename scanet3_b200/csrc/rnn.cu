@@ -194,3 +194,7 @@ void rnn_free(sb_engine* e) {
 }
 
 }  // namespace sb
+
+namespace sb {
+void trace_set_rnn(unsigned long long* p) { sb_trace_set_local(p); }  // SB_TRACE timeline buffer of this translation unit
+}  // namespace sb

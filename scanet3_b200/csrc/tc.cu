@@ -1533,3 +1533,7 @@ bool tc_conv_dgrad(sb_engine* e, LayerPlan& L, int) {
 }
 
 }  // namespace sb
+
+namespace sb {
+void trace_set_tc(unsigned long long* p) { sb_trace_set_local(p); }  // SB_TRACE timeline buffer of this translation unit
+}  // namespace sb

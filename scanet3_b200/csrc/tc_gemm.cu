@@ -519,3 +519,7 @@ void tc_gemm_run_lstm(TcGemm* g, int za, int zb, int zc, const LstmEpi& epi, cud
 void tc_gemm_destroy(TcGemm* g) { delete g; }
 
 }  // namespace sb
+
+namespace sb {
+void trace_set_tc_gemm(unsigned long long* p) { sb_trace_set_local(p); }  // SB_TRACE timeline buffer of this translation unit
+}  // namespace sb
