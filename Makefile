@@ -20,6 +20,20 @@ $(BUILD)/%.o: $(CSRC)/%.cpp $(wildcard $(CSRC)/*.h) include/scanet_b200.h
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -cudart static -ldl -lpthread
 
+# developer variant with the in-situ timeline stamps compiled in (common.cuh SB_TRACE_BUILD): tools/trace_step.py loads it through SB_LIB
+TBUILD    := build/trace
+TOBJS     := $(patsubst $(BUILD)/%,$(TBUILD)/%,$(OBJS))
+TLIB      := scanet3_b200/libscanet_b200_trace.so
+trace: $(TLIB)
+$(TBUILD)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh) include/scanet_b200.h
+	@mkdir -p $(TBUILD)
+	$(NVCC) $(NVFLAGS) -DSB_TRACE_BUILD -c $< -o $@ 2> $(TBUILD)/$*.ptxas.log || (cat $(TBUILD)/$*.ptxas.log; exit 1)
+$(TBUILD)/%.o: $(CSRC)/%.cpp $(wildcard $(CSRC)/*.h) include/scanet_b200.h
+	@mkdir -p $(TBUILD)
+	g++ -O2 -std=c++17 -fPIC -Wall -c $< -o $@
+$(TLIB): $(TOBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(TOBJS) -cudart static -ldl -lpthread
+
 clean:
-	rm -rf $(BUILD) $(LIB)
-.PHONY: all clean
+	rm -rf $(BUILD) $(LIB) $(TLIB)
+.PHONY: all clean trace

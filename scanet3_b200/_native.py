@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libscanet_b200.so")
+LIB_PATH = os.environ.get("SB_LIB") or os.path.join(_HERE, "libscanet_b200.so")  # SB_LIB: a developer variant (`make trace`)
 
 SB_OK, SB_ERR_INVALID_ARG, SB_ERR_UNSUPPORTED, SB_ERR_CUDA, SB_ERR_NCCL, SB_ERR_STATE, SB_ERR_TIMEOUT = range(7)
 ITER_FROM_DEVICE = -1

@@ -38,20 +38,23 @@ static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) 
 // (pdl_prologue); the tensor-core kernels run their on-chip setup (mbarrier init, TMEM allocation, tensor-map prefetch) first.
 // The instruction is a no-op when a kernel is launched without the PDL attribute (SB_PDL=0).
 #ifdef __CUDACC__
-// ---- in-situ step timeline (SB_TRACE=1, developer aid) ----------------------------------------------------------------
+// ---- in-situ step timeline (compiled in only with -DSB_TRACE_BUILD: `make trace`; developer aid) --------------------------
 // Every kernel of the engine passes griddepcontrol.wait exactly once; with tracing on, the first thread of its first CTA then
 // appends %globaltimer to a device buffer (slot 0 = running count).  Inside a replayed CUDA graph this gives the start-to-start
 // interval of consecutive kernels -- what each kernel costs the step WITH the overlap programmatic launches buy, which neither
 // ncu (serialised, cold prologues) nor eager event timing (launch gaps) can show.  One __constant__ pointer per translation unit
-// (no relocatable device code in this build); null in production: the cost is one uniform constant load per thread.
+// (no relocatable device code in this build).  NOT in the production library: even a null check per thread after the wait cost
+// the issue-bound kernels of the LeNet step 2-5 % (1019 k -> 997 k -> 959 k samples/s with a wider predicate), so the product
+// build compiles the stamp out and `make trace` builds scanet3_b200/libscanet_b200_trace.so for tools/trace_step.py.
 static __constant__ unsigned long long* sb_trace_buf_c = nullptr;
 static inline void sb_trace_set_local(unsigned long long* p) { cudaMemcpyToSymbol(sb_trace_buf_c, &p, sizeof p); }
 constexpr int kTraceSlots = 1 << 16;
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
+#ifdef SB_TRACE_BUILD
   unsigned long long* tb = sb_trace_buf_c;
-  if (tb != nullptr && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
+  if (tb != nullptr && (threadIdx.x | threadIdx.y | threadIdx.z | blockIdx.x | blockIdx.y | blockIdx.z) == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     const unsigned long long slot = 2 * atomicAdd(tb, 1ull) + 2;  // two words per event: time, (gridDim.x << 16 | blockDim.x)
@@ -60,6 +63,7 @@ __device__ __forceinline__ void pdl_wait() {
       tb[slot + 1] = ((unsigned long long)gridDim.x << 16) | blockDim.x;
     }
   }
+#endif
 }
 __device__ __forceinline__ void pdl_prologue() { pdl_wait(); }
 // Wait, then let the dependents launch: their CTAs fill whatever this grid leaves free and run their own pre-wait setup (a

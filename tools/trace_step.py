@@ -1,6 +1,7 @@
 """In-situ timeline of the train step inside the replayed CUDA graph (SB_TRACE facility of csrc/common.cuh): every kernel stamps
 %globaltimer right after its programmatic-dependency wait; the start-to-start intervals are what each kernel costs the step with
-the launch overlap included.  usage: python tools/trace_step.py [cfg2] [steps] > profiles/r2_trace_cfg2.txt"""
+the launch overlap included.  Needs the trace build of the library: `make trace`.
+usage: python tools/trace_step.py [cfg2] [steps] > profiles/r2_trace_cfg2.txt"""
 import ctypes as C
 import os
 import sys
@@ -9,6 +10,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("SB_LIB", os.path.join(ROOT, "scanet3_b200", "libscanet_b200_trace.so"))  # built by `make trace`
 import bench  # noqa: E402
 import scanet3_b200 as S  # noqa: E402
 from scanet3_b200 import _native as N  # noqa: E402
