@@ -17,7 +17,8 @@ the parameters are therefore checked by max |err| <= 2 * steps * rate and by the
 5 % (ReLU masks flip for pre-activations within the tf32 error of zero, tests/test_gpu_tf32.py), parameters max |err| <= 3 * steps
 * rate.  3xTF32 mode: the fp32-mode bounds.  LSTM (64 recurrent steps): per-tensor |err| <= tol * max|ref|, and tol * max(max|ref|, sqrt(loss)) for the
 output layer's (Dense(1) >> Bias) gradients, which are cancelling sums of 1024 terms of size ~|p - y| ~ sqrt(loss), so its natural scale is sqrt(loss), not
-its own (small) value; tol = 4e-2 of the model's largest gradient entry in TF32 (measured 2.3e-2 on the F = 1 input kernels) and
+its own (small) value; tol = 8e-2 of the model's largest gradient entry in TF32 (measured 2.3e-2 on the F = 1 input kernels and
+4.5e-2 on the forget-gate bias: sums over 65 536 (row, step) terms of a 64-step tf32 recurrence) and
 2e-3 per tensor in 3xTF32."""
 import numpy as np
 import pytest
@@ -133,7 +134,7 @@ def test_config3_lstm_full_size_tensor_core_modes_against_the_oracle(precision):
     lm = O.LossModel(om, O.MeanSquaredError)
     gl, gg = e.compute_grads(x[:batch], y[:batch])
     ol, og, _ = lm.grad_stateful(x[:batch], y[:batch], mp)
-    tol_l, tol_g = (4e-3, 4e-2) if precision == S.PREC_TF32 else (5e-4, 2e-3)  # (fp32 run of this config: loss_rtol 5e-4)
+    tol_l, tol_g = (4e-3, 8e-2) if precision == S.PREC_TF32 else (5e-4, 2e-3)  # (fp32 run of this config: loss_rtol 5e-4)
     assert abs(gl - float(ol)) <= tol_l * abs(float(ol)), (gl, float(ol))
     gmax = max(float(np.max(np.abs(v))) for v in og.values())
     for k in og:
