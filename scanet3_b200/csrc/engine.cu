@@ -806,27 +806,6 @@ static void run_forward(sb_engine* e, int mode) {
   }
 }
 
-static void run_loss(sb_engine* e, bool with_grad) {
-  const LayerPlan& last = e->L.back();
-  float* pred = e->acts[last.buf_out];
-  float* dpred = with_grad ? e->dacts[last.buf_out] : nullptr;
-  const long long rows = e->label_shape.d[0];
-  const long long cols = e->label_shape.numel() / rows;
-  if (e->head_fused) {
-    const LayerPlan& bias = e->L[e->L.size() - 2];
-    Prof pr(e, "head_bias_softmax_cce", 4.0 * 4.0 * (double)rows * cols, 0);
-    if (!head_bias_softmax_cce(pred, e->head_chunks > 0 ? e->ws : nullptr, e->head_chunks, P(e, bias.p_w), e->by, dpred,
-                               with_grad ? G(e, bias.p_w) : nullptr, e->st, (int)rows, (int)cols, e->head_scratch, e->stream))
-      SB_FAIL(SB_ERR_CUDA, "fused classifier head rejected a planned shape");
-  } else if (e->softmax_cce_fused) {
-    Prof pr(e, "softmax_cce_fused", 4.0 * 4.0 * (double)rows * cols, 0);
-    softmax_cce_fwd_bwd(pred, e->by, dpred, e->st, (int)rows, (int)cols, e->stream);
-  } else {
-    Prof pr(e, "loss_fwd_bwd", 4.0 * 3.0 * (double)rows * cols, 0);
-    loss_fwd_bwd(e->train.loss, pred, e->by, dpred, e->st, rows, cols, e->stream);
-  }
-}
-
 // Side branch of the backward pass: work that only the optimizer waits for (filter gradients) is queued on `bstream` behind the
 // point the main stream has reached; successive branches simply queue up there (in order), and the main stream joins the last
 // one at the end of run_backward.  Inside a captured graph these become parallel branches.
@@ -837,6 +816,38 @@ static void side_branch_begin(sb_engine* e) {
 static void side_branch_end(sb_engine* e) {
   SB_CUDA(cudaEventRecord(e->ev_join, e->bstream));
   e->bwd_forked = true;
+}
+
+static void run_loss(sb_engine* e, bool with_grad) {
+  const LayerPlan& last = e->L.back();
+  float* pred = e->acts[last.buf_out];
+  float* dpred = with_grad ? e->dacts[last.buf_out] : nullptr;
+  const long long rows = e->label_shape.d[0];
+  const long long cols = e->label_shape.numel() / rows;
+  if (e->head_fused) {
+    const LayerPlan& bias = e->L[e->L.size() - 2];
+    Prof pr(e, "head_bias_softmax_cce", 4.0 * 4.0 * (double)rows * cols, 0);
+    // With a backward pass behind it, the final sum of the per-CTA loss / bias-gradient partials moves to the side branch: only dz
+    // is on the critical path (SB_HEAD_DEFER=0 keeps the in-kernel last-CTA combine)
+    static const bool defer_on = [] { const char* v = getenv("SB_HEAD_DEFER"); return !(v && v[0] == '0'); }();
+    const bool defer = defer_on && with_grad && fork_enabled() && !e->profiling;
+    int n_ctas = 0;
+    if (!head_bias_softmax_cce(pred, e->head_chunks > 0 ? e->ws : nullptr, e->head_chunks, P(e, bias.p_w), e->by, dpred,
+                               with_grad ? G(e, bias.p_w) : nullptr, e->st, (int)rows, (int)cols, e->head_scratch, e->stream,
+                               defer ? &n_ctas : nullptr))
+      SB_FAIL(SB_ERR_CUDA, "fused classifier head rejected a planned shape");
+    if (defer) {
+      side_branch_begin(e);
+      head_loss_combine(e->head_scratch, n_ctas, (int)cols, (int)rows, e->st, G(e, bias.p_w), e->bstream);
+      side_branch_end(e);
+    }
+  } else if (e->softmax_cce_fused) {
+    Prof pr(e, "softmax_cce_fused", 4.0 * 4.0 * (double)rows * cols, 0);
+    softmax_cce_fwd_bwd(pred, e->by, dpred, e->st, (int)rows, (int)cols, e->stream);
+  } else {
+    Prof pr(e, "loss_fwd_bwd", 4.0 * 3.0 * (double)rows * cols, 0);
+    loss_fwd_bwd(e->train.loss, pred, e->by, dpred, e->st, rows, cols, e->stream);
+  }
 }
 
 static void run_backward(sb_engine* e) {

@@ -153,8 +153,11 @@ bool dense_head_bwd(const float* x, const float* g, const float* w, float* dw, f
 // z (or the sum of `chunks` split-K partials when partial != null) + bias -> softmax -> CCE loss, dz, dbias
 // scratch: kHeadScratchFloats floats, zero-initialised once (per-CTA partials + the completion ticket)
 constexpr size_t kHeadScratchFloats = 1024 * 40 + 32;
+// deferred_ctas != null: the kernel leaves its per-CTA loss / bias-gradient partials in `scratch` and returns their count; the
+// caller runs head_loss_combine (any stream ordered after this kernel) to form st->loss and dbias -- same summation, same bits
 bool head_bias_softmax_cce(float* z, const float* partial, int chunks, const float* bias, const float* y, float* dz, float* dbias,
-                           StepState* st, int rows, int C, float* scratch, cudaStream_t s);
+                           StepState* st, int rows, int C, float* scratch, cudaStream_t s, int* deferred_ctas = nullptr);
+void head_loss_combine(const float* scratch, int n_ctas, int C, int rows, StepState* st, float* dbias, cudaStream_t s);
 // g <- act'(y)*g in place and out[c] = column sums of the result, one pass (act = 0: plain column sum); false if C % 4 != 0
 bool act_bwd_col_sum(float* g, const float* y, int act, float thr, float* out, long long rows, int C, float* ws, size_t ws_floats,
                      cudaStream_t s);

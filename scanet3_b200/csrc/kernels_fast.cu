@@ -3,6 +3,8 @@
 //   * Conv2D with a tiny reduction (KH*KW*Cin <= 32, e.g. the first layer on 1- or 3-channel images): fprop (+ReLU) and wgrad,
 //   * the skinny dense head (N <= 16 outputs): split-K forward, fused bias + softmax + CCE (+ bias gradient), wgrad, dgrad.
 // All reductions use fixed orders (no atomics), so results are run-to-run deterministic.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -1467,7 +1469,15 @@ bool dense_head_bwd(const float* x, const float* g, const float* w, float* dw, f
   const int pw = prewait_ok();
 #define SB_HEAD_BWD(NT_, DG_, KP_) \
   launch_k(dense_head_bwd_kernel<NT_, DG_, KP_>, grid, thr, smem, s, x, g, w, dwo, dx, M, K, N, rows_per_split, pdl_early_hint(), pw)
-  if (NT == 12) {
+  // rows of X in flight per thread: the kernel is bound by L2 latency x bytes in flight (13 warps per SM at ~90 registers), so the
+  // row loop is unrolled over ALL the rows a thread owns when they are few (cfg2: 100 rows / 4 groups = 25: 1020.6 k -> 1033.6 k
+  // samples/s against 8 in flight; 13 in flight: 1022 k)
+  const int rows_per_thread = (std::min(M, kBwdRows) + kBwdGroups - 1) / kBwdGroups;
+  if (NT == 12 && kpt == 2 && dx && rows_per_thread > 16 && rows_per_thread <= 25) {
+    launch_k(dense_head_bwd_kernel<12, true, 2, kBwdGroups, 25>, grid, thr, smem, s, x, g, w, dwo, dx, M, K, N, rows_per_split, pdl_early_hint(), pw);
+  } else if (NT == 12 && kpt == 2 && dx && rows_per_thread > 25) {
+    launch_k(dense_head_bwd_kernel<12, true, 2, kBwdGroups, 32>, grid, thr, smem, s, x, g, w, dwo, dx, M, K, N, rows_per_split, pdl_early_hint(), pw);
+  } else if (NT == 12) {
     if (kpt == 2) { if (dx) SB_HEAD_BWD(12, true, 2); else SB_HEAD_BWD(12, false, 2); }
     else { if (dx) SB_HEAD_BWD(12, true, 1); else SB_HEAD_BWD(12, false, 1); }
   } else {
@@ -1556,7 +1566,7 @@ __global__ void __launch_bounds__(1024) head_bias_softmax_cce_kernel(float* __re
                                                                      const float* __restrict__ y, float* __restrict__ dz,
                                                                      float* __restrict__ dbias, StepState* st, int rows, int C,
                                                                      int rows_per_cta, float* __restrict__ scratch,
-                                                                     unsigned int* ticket, int early) {
+                                                                     unsigned int* ticket, int early, int defer_combine) {
   pdl_prologue_trigger_if(early);
   __shared__ float zs[32][kHeadMaxCnt];
   __shared__ float sl[kHeadMaxRows];
@@ -1566,6 +1576,12 @@ __global__ void __launch_bounds__(1024) head_bias_softmax_cce_kernel(float* __re
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int row0 = blockIdx.x * rows_per_cta, nrows = min(rows_per_cta, rows - row0);
   const int mn = rows * C, cnt = nrows * C;
+  // labels and bias of this warp's row: requested now, consumed after the barrier (one L2 round trip less on the critical path)
+  float yv_pre = 0.f, bias_pre = 0.f;
+  if (wid < nrows && lane < C) {
+    yv_pre = __ldg(y + (size_t)(row0 + wid) * C + lane);
+    if (bias) bias_pre = __ldg(bias + lane);
+  }
   // ---- z for this CTA's rows: L lanes (one per output) x G groups; chunk c goes to group c % G, groups are added in order ----
   const int L = (cnt + 31) & ~31, G = 1024 / L;
   {
@@ -1589,9 +1605,9 @@ __global__ void __launch_bounds__(1024) head_bias_softmax_cce_kernel(float* __re
     if (lane < C) {
       float v = zs[0][wid * C + lane];
       for (int g2 = 1; g2 < G; ++g2) v = __fadd_rn(v, zs[g2][wid * C + lane]);
-      if (bias) v = __fadd_rn(v, __ldg(bias + lane));
+      if (bias) v = __fadd_rn(v, bias_pre);
       e = expf(v);
-      yv = y[(size_t)row * C + lane];
+      yv = yv_pre;
     }
     float sum = e;
 #pragma unroll
@@ -1629,6 +1645,10 @@ __global__ void __launch_bounds__(1024) head_bias_softmax_cce_kernel(float* __re
     for (int i = 0; i < nrows; ++i) t = __fadd_rn(t, sdb[i][tid - 32]);
     mine[1 + tid - 32] = t;
   }
+  // defer_combine: the per-CTA partials are final when this kernel completes; head_loss_combine_kernel adds them on the backward
+  // side branch -- dz is all the next kernel of the step needs, and the ticket + fence + reload below kept ~2 us of pure latency
+  // on the step's critical path (in-situ timeline, profiles/r2_trace_cfg2.txt: 7.4 us for this kernel)
+  if (defer_combine) return;
   __threadfence();
   __syncthreads();
   if (tid == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
@@ -1649,17 +1669,37 @@ __global__ void __launch_bounds__(1024) head_bias_softmax_cce_kernel(float* __re
   }
   if (tid == 0) *ticket = 0;  // ready for the next launch
 }
+// the same final sum as the last-CTA path above (one warp per quantity, lanes stride the CTAs, fixed tree): same bits
+__global__ void __launch_bounds__(1024) head_loss_combine_kernel(const float* __restrict__ scratch, int n_ctas, int C, int rows,
+                                                                 StepState* st, float* __restrict__ dbias) {
+  pdl_prologue();
+  const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
+  if (q > C) return;
+  float t = 0.f;
+  for (int g2 = lane; g2 < n_ctas; g2 += 32) t = __fadd_rn(t, __ldcg(scratch + (size_t)g2 * 40 + q));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t = __fadd_rn(t, __shfl_xor_sync(0xffffffffu, t, o));
+  if (lane == 0) {
+    if (q == 0) st->loss = __fdiv_rn(-t, (float)rows);
+    else if (dbias) dbias[q - 1] = t;
+  }
+}
+void head_loss_combine(const float* scratch, int n_ctas, int C, int rows, StepState* st, float* dbias, cudaStream_t s) {
+  launch_k(head_loss_combine_kernel, 1, 32 * (C + 1), 0, s, scratch, n_ctas, C, rows, st, dbias);
+  SB_LAUNCHED();
+}
 // scratch: 1024 x 40 floats of per-CTA partials followed by one zero-initialised 32-bit ticket (the kernel leaves it zero)
 bool head_bias_softmax_cce(float* z, const float* partial, int chunks, const float* bias, const float* y, float* dz, float* dbias,
-                           StepState* st, int rows, int C, float* scratch, cudaStream_t s) {
+                           StepState* st, int rows, int C, float* scratch, cudaStream_t s, int* deferred_ctas) {
   if (C > 32 || rows < 1) return false;
   // few rows per CTA (a short dependent-load chain over the split-K partials), but at most 1024 CTAs
   int rpc = std::max(std::max(1, 32 / C), (rows + 1023) / 1024);
   if (rpc > kHeadMaxRows || rpc * C > kHeadMaxCnt) return false;
   const int grid = (rows + rpc - 1) / rpc;
   launch_k(head_bias_softmax_cce_kernel, grid, 1024, 0, s, z, partial, chunks, bias, y, dz, dbias, st, rows, C, rpc, scratch,
-           reinterpret_cast<unsigned int*>(scratch + 1024 * 40), pdl_early_hint());
+           reinterpret_cast<unsigned int*>(scratch + 1024 * 40), pdl_early_hint(), deferred_ctas ? 1 : 0);
   SB_LAUNCHED();
+  if (deferred_ctas) *deferred_ctas = grid;
   return true;
 }
 
