@@ -544,6 +544,26 @@ static void plan_fusions(sb_engine* e) {
             }
           }
         }
+        // tensor-core twin: conv (tcgen05 halo fprop, ReLU in its epilogue) >> pool(2x2, stride 1, VALID): the conv's eight epilogue
+        // warps pool the staged tile and record the winner bytes; the conv activations are never written
+        if (!L.skip_fwd && L.fast_pool) {
+          const int ci = (li >= 1 && e->L[li - 1].d.kind == SB_LAYER_ACTIVATE && e->L[li - 1].skip_fwd) ? li - 2 : li - 1;
+          const PoolGeom& g = L.pg;
+          const bool relu_between = ci == li - 2;
+          const char* nm = getenv("SB_NO_POOL_MAP");  // =1: every pool runs on the activations (A/B and the bit-identity test)
+          if (!(nm && nm[0] == '1') && ci >= 0 && e->L[ci].d.kind == SB_LAYER_CONV2D && e->L[ci].tc_kind == 1 && e->L[ci].buf_out == L.buf_in &&
+              pool22_map_ok(g) && (!relu_between || (L.pool_relu_bwd || !L.need_dx)) && (ci == li - 1 || relu_between)) {
+            unsigned char* mp = nullptr;
+            if (L.need_dx) SB_CUDA(cudaMalloc((void**)&mp, (size_t)g.N * g.OH * g.OW * g.C));
+            if (tc_conv_enable_pool_fusion(e, e->L[ci], e->acts[L.buf_out], mp)) {
+              e->L[ci].fuse_pool_fwd = li;
+              L.skip_fwd = true;
+              L.pool_map = mp;
+            } else {
+              cudaFree(mp);
+            }
+          }
+        }
         break;
       }
       case SB_LAYER_BIAS: {

@@ -314,12 +314,28 @@ struct HaloParams {
   int early_filter;    // load the filter before the programmatic-dependency wait (SB_TC_EARLY_FILTER=0 turns it off)
   long long* dbg;      // developer timeline (SB_TC_DEBUG=1): 64 clock64 slots per CTA, null in production
   int bo_mode;         // debug: 1 = also encode the start row's swizzle phase in the descriptor's base-offset field
+  // Fused Pool2D(2x2, stride 1, VALID) behind the (ReLU) epilogue: consecutive tiles overlap by one conv row (row_stride = BH - 1),
+  // eight epilogue warps drain TMEM into the staging tile and then pool it: `pooled` [n_img, Hg-1, Wg-1, N] and one winner byte
+  // per pooled output (kernels_fast.cu win4; `pmap` may be null) are written INSTEAD of the conv activations.
+  int pool, row_stride;
+  float* pooled;
+  unsigned* pmap;
 };
+// winner byte of a 2x2 window (the same definition as kernels_fast.cu win4): index of the FIRST maximum in row-major order | (max > thr) << 2
+__device__ __forceinline__ unsigned tc_win4(float a, float b, float c, float d, int relu, float thr, float* mx) {
+  float best = a;
+  unsigned idx = 0;
+  if (b > best) { best = b; idx = 1; }
+  if (c > best) { best = c; idx = 2; }
+  if (d > best) { best = d; idx = 3; }
+  *mx = best;
+  return idx | ((!relu || best > thr) ? 4u : 0u);
+}
 
 // TKH/TKW/TKC: compile-time KH, KW and Cin/32 (0 = from the parameters): runtime trip counts in the MMA issue loop cost far more
 // than the MMAs themselves (profiles/r1_notes.md item 11)
 template <int TKH, int TKW, int TKC>
-__global__ void __launch_bounds__(kIgemmThreads, 1)
+__global__ void __launch_bounds__(kIgemmThreadsX3, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_c, const HaloParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -331,7 +347,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint8_t* sm_b = smem;
   uint8_t* sm_a = smem + b_bytes;
   uint8_t* sm_stg = sm_a + (size_t)p.stages * stage_bytes;        // 2 x (N/32) x [128 rows x 128 B], TMA-store staging
-  const int stg_bytes = p.tma_store ? (p.N / 32) * 16384 : 0;
+  const int stg_bytes = (p.tma_store || p.pool) ? (p.N / 32) * 16384 : 0;
   uint64_t* full_bar = (uint64_t*)(sm_stg + 2 * stg_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full = empty_bar + p.stages;
@@ -356,7 +372,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4);
+      mbar_init(&tmem_empty[a], p.pool ? 8 : 4);
     }
     mbar_init(b_bar, 1);
     fence_barrier_init();
@@ -393,7 +409,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const int img = tile / p.tiles_per_img, h0 = (tile - img * p.tiles_per_img) * p.BH;
+        const int img = tile / p.tiles_per_img, h0 = (tile - img * p.tiles_per_img) * p.row_stride;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = sm_a + (size_t)stage * stage_bytes;
         mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(p.kchunks * p.box_bytes));
@@ -457,7 +473,68 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else {
+  } else if (p.pool) {
+    // ================= pooled epilogue (8 warps): TMEM -> (ReLU) -> staging tile -> 2x2/stride-1 max + winner byte =================
+    // warps 2..5 drain the even 32-channel chunks, warps 6..9 the odd ones (a warp may only read the TMEM lanes of sub-partition
+    // warp % 4); after one 256-thread barrier every thread pools channel quads of the staged tile: window (r, c) = staged rows
+    // m, m+1, m+P, m+P+1 (m = r*P + c), members in row-major order.
+    const int sub = warp & 3, grp = (warp - 2) >> 2;
+    const int m = sub * 32 + lane;
+    const int et = threadIdx.x - 64;  // 0..255
+    const int PH = p.Hg - 1, PW = p.Wg - 1, C4 = p.N >> 2, nchunks = p.N >> 5;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
+      const int img = tile / p.tiles_per_img, h0 = (tile - img * p.tiles_per_img) * p.row_stride;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      uint8_t* sbuf = sm_stg + (size_t)(ti & 1) * stg_bytes;
+      for (int ch = grp; ch < nchunks; ch += 2) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * p.N + ch * 32), v);
+        tmem_ld_wait();
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(p.thr, v[j]);
+        }
+        // row m of the chunk tile: 128 B, 16-byte piece j at position j ^ (m & 7) (conflict-free row writes and quad reads)
+        uint8_t* srow = sbuf + (size_t)ch * 16384 + m * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(srow + ((j ^ (m & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      // the accumulator is drained: release it to the MMA warp, then meet the other seven warps
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int rows_pool = min(p.row_stride, PH - h0);
+      const int items = rows_pool * PW * C4;
+      float* pout = p.pooled + ((size_t)(img * PH + h0) * PW) * p.N;
+      unsigned* mout = p.pmap ? p.pmap + ((size_t)(img * PH + h0) * PW) * C4 : nullptr;
+      for (int it = et; it < items; it += 256) {
+        const int cq = it % C4, px = it / C4;          // pooled pixel px = r * PW + c of this tile, channel quad cq
+        const int r = px / PW, c = px - r * PW;
+        const int m0 = r * p.P + c;
+        const uint8_t* base = sbuf + (size_t)(cq >> 3) * 16384;
+        const int j = cq & 7;
+        const float4 a = *reinterpret_cast<const float4*>(base + m0 * 128 + ((j ^ (m0 & 7)) << 4));
+        const float4 b = *reinterpret_cast<const float4*>(base + (m0 + 1) * 128 + ((j ^ ((m0 + 1) & 7)) << 4));
+        const float4 cc = *reinterpret_cast<const float4*>(base + (m0 + p.P) * 128 + ((j ^ ((m0 + p.P) & 7)) << 4));
+        const float4 d = *reinterpret_cast<const float4*>(base + (m0 + p.P + 1) * 128 + ((j ^ ((m0 + p.P + 1) & 7)) << 4));
+        float4 mx;
+        const unsigned b0 = tc_win4(a.x, b.x, cc.x, d.x, p.relu, p.thr, &mx.x);
+        const unsigned b1 = tc_win4(a.y, b.y, cc.y, d.y, p.relu, p.thr, &mx.y);
+        const unsigned b2 = tc_win4(a.z, b.z, cc.z, d.z, p.relu, p.thr, &mx.z);
+        const unsigned b3 = tc_win4(a.w, b.w, cc.w, d.w, p.relu, p.thr, &mx.w);
+        *reinterpret_cast<float4*>(pout + (size_t)px * p.N + cq * 4) = mx;
+        if (mout) mout[(size_t)px * C4 + cq] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+      }
+      // (no second barrier: the staging buffers alternate, and a thread reaches the NEXT tile's barrier only after this loop)
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp < 6) {
     // ================= epilogue: TMEM -> registers -> (ReLU) -> NHWC rows =================
     const int sub = warp & 3;  // TMEM sub-partition this warp may read: lanes [32*sub, 32*sub+32)
     const int m = sub * 32 + lane;
@@ -466,7 +543,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint32_t acc_phase = 0;
     int ti = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
-      const int img = tile / p.tiles_per_img, h0 = (tile - img * p.tiles_per_img) * p.BH;
+      const int img = tile / p.tiles_per_img, h0 = (tile - img * p.tiles_per_img) * p.row_stride;
       const bool valid = r < p.BH && c < p.Wg && h0 + r < p.Hg;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -970,14 +1047,22 @@ static bool conv_fits(const ConvGeom& g) {
 // Fill a HaloParams for an output grid Hg x Wg whose taps read a source tensor [Csrc, Ws, Hs, N] at origin (ox, oy).
 static bool plan_halo(HaloParams& p, CUtensorMap* map, CUtensorMap* map_out, const float* src, int Csrc, int Ws, int Hs, int Nimg, int Hg, int Wg,
                       int KH, int KW, int Nacc, int b_mn_major, int b_rows_per_tap, int flip, int ox, int oy, float* out,
-                      int dev_smem, int* smem_out) {
+                      int dev_smem, int* smem_out, int pool = 0) {
   p.Hg = Hg; p.Wg = Wg; p.KH = KH; p.KW = KW; p.kchunks = Csrc / 32; p.N = Nacc;
   p.P = Wg + KW - 1;
   if (p.P > 128) return false;
   p.BH = std::max(1, std::min(128 / p.P, Hg));
   const int box_h = p.BH + KH - 1;
   if (p.P > 256 || box_h > 256) return false;
-  p.tiles_per_img = (Hg + p.BH - 1) / p.BH;
+  p.pool = pool; p.pooled = nullptr; p.pmap = nullptr;
+  if (pool) {  // tiles overlap by one conv row: tile t pools rows [t*(BH-1), t*(BH-1) + BH-1) out of conv rows [t*(BH-1), t*(BH-1) + BH)
+    if (p.BH < 2 || Hg < 2 || Wg < 2) return false;
+    p.row_stride = p.BH - 1;
+    p.tiles_per_img = (Hg - 1 + p.row_stride - 1) / p.row_stride;
+  } else {
+    p.row_stride = p.BH;
+    p.tiles_per_img = (Hg + p.BH - 1) / p.BH;
+  }
   p.n_tiles = Nimg * p.tiles_per_img;
   p.b_mn_major = b_mn_major; p.b_rows_per_tap = b_rows_per_tap; p.flip = flip; p.ox = ox; p.oy = oy;
   const int rows = std::max(box_h * p.P, 128 + (KH - 1) * p.P + KW - 1);
@@ -996,8 +1081,9 @@ static bool plan_halo(HaloParams& p, CUtensorMap* map, CUtensorMap* map_out, con
   const int b_bytes = KH * KW * p.kchunks * Nacc * 128;
   const int stage_bytes = p.kchunks * p.a_tile_bytes;
   const char* ts = getenv("SB_TC_TMA_STORE");
-  p.tma_store = !(ts && ts[0] == '0') && p.Wg <= 256;
-  int fixed = b_bytes + 16 * 16 + 1024 + 256 + (p.tma_store ? 2 * (Nacc / 32) * 16384 : 0);
+  p.tma_store = !pool && !(ts && ts[0] == '0') && p.Wg <= 256;
+  int fixed = b_bytes + 16 * 16 + 1024 + 256 + ((p.tma_store || pool) ? 2 * (Nacc / 32) * 16384 : 0);
+  if (pool && (dev_smem - fixed) / stage_bytes < 2) return false;  // the pooled epilogue needs its staging tiles
   if (p.tma_store && (dev_smem - fixed) / stage_bytes < 2) {  // staging does not fit: per-thread stores
     p.tma_store = 0;
     fixed = b_bytes + 16 * 16 + 1024 + 256;
@@ -1318,6 +1404,32 @@ void tc_free_layers(sb_engine* e) {
 
 void tc_params_changed(sb_engine*) {}  // the kernels read the filter straight from the arena
 
+// Called by the fusion planner (engine.cu) once it knows that nothing but the following Pool2D(2x2, stride 1, VALID) reads this
+// conv's activations: re-plans the halo fprop with the pooled epilogue.  false: not available (no halo fprop, geometry, shared memory)
+bool tc_conv_enable_pool_fusion(sb_engine* e, LayerPlan& L, float* pooled, unsigned char* map) {
+  ConvTcPlan* P = (ConvTcPlan*)L.tc_plan;
+  const char* off = getenv("SB_NO_TC_POOL_FUSION");
+  if (!P || L.tc_kind != 1 || !P->halo_fwd || (off && off[0] == '1')) return false;
+  const ConvGeom& g = L.cg;
+  int dev_smem = 0;
+  SB_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device));
+  HaloParams hp = P->hfwd;
+  CUtensorMap mx, mo;
+  int smem = 0;
+  if (!plan_halo(hp, &mx, &mo, e->acts[L.buf_in], g.Cin, g.W, g.H, g.N, g.OH, g.OW, g.KH, g.KW, g.Cout, 1, g.Cin, 0, -g.PL, -g.PT,
+                 e->acts[L.buf_out], dev_smem, &smem, 1))
+    return false;
+  hp.relu = P->hfwd.relu; hp.thr = P->hfwd.thr; hp.dbg = P->hfwd.dbg;
+  hp.pooled = pooled;
+  hp.pmap = reinterpret_cast<unsigned*>(map);
+  P->hfwd = hp;
+  P->map_x_h = mx;
+  P->map_y_out = mo;
+  P->hfwd_smem = smem;
+  P->hfwd_grid = std::min(hp.n_tiles, kNumSMs);
+  return true;
+}
+
 bool tc_dense_fwd(sb_engine* e, LayerPlan& L, int) {
   if (L.tc_kind != 2) return false;
   tc_gemm_run(((DenseTcPlan*)L.tc_plan)->fwd, 0, 0, 0, e->stream);
@@ -1341,7 +1453,8 @@ bool tc_conv_fwd(sb_engine* e, LayerPlan& L, int) {
     auto kern = P->hfwd.KH == 3 && P->hfwd.KW == 3 && P->hfwd.kchunks == 1   ? conv_halo_kernel<3, 3, 1>
                 : P->hfwd.KH == 3 && P->hfwd.KW == 3 && P->hfwd.kchunks == 2 ? conv_halo_kernel<3, 3, 2>
                                                                                : conv_halo_kernel<0, 0, 0>;
-    launch_k(kern, P->hfwd_grid, kIgemmThreads, P->hfwd_smem, e->stream, P->map_x_h, P->map_w_fwd, P->map_y_out, P->hfwd);
+    launch_k(kern, P->hfwd_grid, P->hfwd.pool ? kIgemmThreadsX3 : kIgemmThreads, P->hfwd_smem, e->stream, P->map_x_h, P->map_w_fwd,
+             P->map_y_out, P->hfwd);
     SB_LAUNCHED();
     return true;
   }

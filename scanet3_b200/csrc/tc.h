@@ -47,6 +47,9 @@ struct LstmEpi {
 void tc_gemm_run_lstm(TcGemm* g, int za, int zb, int zc, const LstmEpi& epi, cudaStream_t s);
 void tc_gemm_destroy(TcGemm* g);
 
+// halo fprop with the Pool2D(2x2, stride 1, VALID) that follows folded into its epilogue (tc.cu); false: not available
+bool tc_conv_enable_pool_fusion(sb_engine* e, LayerPlan& L, float* pooled, unsigned char* map);
+
 void lstm_plan(sb_engine* e);
 void lstm_forward(sb_engine* e, LayerPlan& L, int li, bool store_state);  // store_state: a train step of a stateful RNN
 void lstm_backward(sb_engine* e, LayerPlan& L, int li);
