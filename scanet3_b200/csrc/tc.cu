@@ -334,8 +334,12 @@ __device__ __forceinline__ unsigned tc_win4(float a, float b, float c, float d, 
 
 // TKH/TKW/TKC: compile-time KH, KW and Cin/32 (0 = from the parameters): runtime trip counts in the MMA issue loop cost far more
 // than the MMAs themselves (profiles/r1_notes.md item 11)
-template <int TKH, int TKW, int TKC>
-__global__ void __launch_bounds__(kIgemmThreadsX3, 1)
+// pooled epilogue: warps 2..9 drain TMEM, warps 2..25 (768 threads) pool -- with only the 8 drain warps pooling, the SM cannot hide
+// the latency of the ~90-instruction item loop and a tile's pooling takes 3x its MMAs (measured: fprop 15 -> 23 us)
+constexpr int kHaloPoolWarps = 24;
+constexpr int kHaloPoolThreads = 64 + 32 * kHaloPoolWarps;
+template <int TKH, int TKW, int TKC, bool POOL = false>
+__global__ void __launch_bounds__(POOL ? kHaloPoolThreads : kIgemmThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_c, const HaloParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -372,7 +376,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], p.pool ? 8 : 4);
+      mbar_init(&tmem_empty[a], POOL ? 8 : 4);
     }
     mbar_init(b_bar, 1);
     fence_barrier_init();
@@ -473,49 +477,59 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (p.pool) {
-    // ================= pooled epilogue (8 warps): TMEM -> (ReLU) -> staging tile -> 2x2/stride-1 max + winner byte =================
+  } else if (POOL) {
+    // ================= pooled epilogue: TMEM -> (ReLU) -> staging tile -> 2x2/stride-1 max + winner byte =================
     // warps 2..5 drain the even 32-channel chunks, warps 6..9 the odd ones (a warp may only read the TMEM lanes of sub-partition
-    // warp % 4); after one 256-thread barrier every thread pools channel quads of the staged tile: window (r, c) = staged rows
-    // m, m+1, m+P, m+P+1 (m = r*P + c), members in row-major order.
+    // warp % 4); after one barrier all kHaloPoolWarps warps pool channel quads of the staged tile: window (r, c) = staged rows
+    // m, m+1, m+P, m+P+1 (m = r*P + c), members in row-major order.  Items advance by a fixed stride, so (r, c) are updated
+    // incrementally (no divisions in the loop).
+    constexpr int NT = 32 * kHaloPoolWarps;
+    const bool drains = warp < 10;
     const int sub = warp & 3, grp = (warp - 2) >> 2;
     const int m = sub * 32 + lane;
-    const int et = threadIdx.x - 64;  // 0..255
+    const int et = threadIdx.x - 64;  // 0 .. NT-1
     const int PH = p.Hg - 1, PW = p.Wg - 1, C4 = p.N >> 2, nchunks = p.N >> 5;
+    // item i = px * C4 + cq ; this thread's items: et, et + NT, ...  ->  px advances by dpx (+1 when cq wraps)
+    const int cq0 = et % C4, px0 = et / C4, dcq = NT % C4, dpx = NT / C4;
     int acc = 0;
     uint32_t acc_phase = 0;
     int ti = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
       const int img = tile / p.tiles_per_img, h0 = (tile - img * p.tiles_per_img) * p.row_stride;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
       uint8_t* sbuf = sm_stg + (size_t)(ti & 1) * stg_bytes;
-      for (int ch = grp; ch < nchunks; ch += 2) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * p.N + ch * 32), v);
-        tmem_ld_wait();
-        if (p.relu) {
+      if (drains) {
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        if (threadIdx.x == 64 && ti < 6) HALO_T(24 + ti * 2);
+        for (int ch = grp; ch < nchunks; ch += 2) {
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * p.N + ch * 32), v);
+          tmem_ld_wait();
+          if (p.relu) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(p.thr, v[j]);
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(p.thr, v[j]);
+          }
+          // row m of the chunk tile: 128 B, 16-byte piece j at position j ^ (m & 7) (conflict-free row writes and quad reads)
+          uint8_t* srow = sbuf + (size_t)ch * 16384 + m * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(srow + ((j ^ (m & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
-        // row m of the chunk tile: 128 B, 16-byte piece j at position j ^ (m & 7) (conflict-free row writes and quad reads)
-        uint8_t* srow = sbuf + (size_t)ch * 16384 + m * 128;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(srow + ((j ^ (m & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        // the accumulator is drained: release it to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       }
-      // the accumulator is drained: release it to the MMA warp, then meet the other seven warps
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x == 64 && ti < 6) HALO_T(36 + ti);
+      asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+      if (threadIdx.x == 64 && ti < 6) HALO_T(42 + ti);
       const int rows_pool = min(p.row_stride, PH - h0);
-      const int items = rows_pool * PW * C4;
+      const int npx = rows_pool * PW;
       float* pout = p.pooled + ((size_t)(img * PH + h0) * PW) * p.N;
       unsigned* mout = p.pmap ? p.pmap + ((size_t)(img * PH + h0) * PW) * C4 : nullptr;
-      for (int it = et; it < items; it += 256) {
-        const int cq = it % C4, px = it / C4;          // pooled pixel px = r * PW + c of this tile, channel quad cq
-        const int r = px / PW, c = px - r * PW;
+      int cq = cq0, px = px0;
+      int r = px / PW, c = px - r * PW;  // once per tile
+      while (px < npx) {
         const int m0 = r * p.P + c;
         const uint8_t* base = sbuf + (size_t)(cq >> 3) * 16384;
         const int j = cq & 7;
@@ -530,8 +544,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const unsigned b3 = tc_win4(a.w, b.w, cc.w, d.w, p.relu, p.thr, &mx.w);
         *reinterpret_cast<float4*>(pout + (size_t)px * p.N + cq * 4) = mx;
         if (mout) mout[(size_t)px * C4 + cq] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+        cq += dcq; px += dpx; c += dpx;
+        if (cq >= C4) { cq -= C4; ++px; ++c; }
+        while (c >= PW) { c -= PW; ++r; }
       }
       // (no second barrier: the staging buffers alternate, and a thread reaches the NEXT tile's barrier only after this loop)
+      if (threadIdx.x == 64 && ti < 6) HALO_T(25 + ti * 2);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp < 6) {
@@ -1348,6 +1366,9 @@ void tc_plan_layers(sb_engine* e) {
     SB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
     SB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<3, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
     SB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<3, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
+    SB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<0, 0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
+    SB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<3, 3, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
+    SB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<3, 3, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
     SB_CUDA(cudaFuncSetAttribute(conv_wgrad_halo_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
     SB_CUDA(cudaFuncSetAttribute(conv_wgrad_halo_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
     SB_CUDA(cudaFuncSetAttribute(conv_wgrad_halo_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
@@ -1375,7 +1396,7 @@ void tc_free_layers(sb_engine* e) {
         FILE* f = fopen(hp == &P->hfwd ? "gpurun_out/halo_fwd_timeline.txt" : "gpurun_out/halo_dgrad_timeline.txt", "w");
         if (f) {
           for (int c = 0; c < kNumSMs; ++c) {
-            for (int j = 0; j < 40; ++j) fprintf(f, "%lld ", h[(size_t)c * 64 + j] ? h[(size_t)c * 64 + j] - h[(size_t)c * 64] : -1);
+            for (int j = 0; j < 48; ++j) fprintf(f, "%lld ", h[(size_t)c * 64 + j] ? h[(size_t)c * 64 + j] - h[(size_t)c * 64] : -1);
             fprintf(f, "\n");
           }
           fclose(f);
@@ -1408,8 +1429,13 @@ void tc_params_changed(sb_engine*) {}  // the kernels read the filter straight f
 // conv's activations: re-plans the halo fprop with the pooled epilogue.  false: not available (no halo fprop, geometry, shared memory)
 bool tc_conv_enable_pool_fusion(sb_engine* e, LayerPlan& L, float* pooled, unsigned char* map) {
   ConvTcPlan* P = (ConvTcPlan*)L.tc_plan;
-  const char* off = getenv("SB_NO_TC_POOL_FUSION");
-  if (!P || L.tc_kind != 1 || !P->halo_fwd || (off && off[0] == '1')) return false;
+  // OFF by default (SB_TC_POOL_FUSION=1 turns it on; parity-tested bit-identical either way).  Measured on cfg2: the pooled
+  // epilogue's shared-memory traffic (32 KB of staging writes + 90 KB of window reads per tile) competes with the MMAs' own
+  // operand fetch, which already saturates shared memory at N = 64 (6 KB per MMA at 128 B/cycle = the 48 cycles an MMA takes): a
+  // tile goes from ~1900 to ~4500 cycles whether 8 or 24 warps pool (SB_TC_DEBUG timeline), fprop 15 -> 23 us, step 1035 k -> 971 k
+  // samples/s -- more than the deleted pool kernel (5 us in the step) gives back.
+  const char* on = getenv("SB_TC_POOL_FUSION");
+  if (!P || L.tc_kind != 1 || !P->halo_fwd || !(on && on[0] == '1')) return false;
   const ConvGeom& g = L.cg;
   int dev_smem = 0;
   SB_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device));
@@ -1450,11 +1476,14 @@ bool tc_conv_fwd(sb_engine* e, LayerPlan& L, int) {
   ConvTcPlan* P = (ConvTcPlan*)L.tc_plan;
   if (!P || L.tc_kind != 1) return false;
   if (P->halo_fwd) {
-    auto kern = P->hfwd.KH == 3 && P->hfwd.KW == 3 && P->hfwd.kchunks == 1   ? conv_halo_kernel<3, 3, 1>
-                : P->hfwd.KH == 3 && P->hfwd.KW == 3 && P->hfwd.kchunks == 2 ? conv_halo_kernel<3, 3, 2>
-                                                                               : conv_halo_kernel<0, 0, 0>;
-    launch_k(kern, P->hfwd_grid, P->hfwd.pool ? kIgemmThreadsX3 : kIgemmThreads, P->hfwd_smem, e->stream, P->map_x_h, P->map_w_fwd,
-             P->map_y_out, P->hfwd);
+    const bool k331 = P->hfwd.KH == 3 && P->hfwd.KW == 3 && P->hfwd.kchunks == 1, k332 = P->hfwd.KH == 3 && P->hfwd.KW == 3 && P->hfwd.kchunks == 2;
+    if (P->hfwd.pool) {
+      auto kern = k331 ? conv_halo_kernel<3, 3, 1, true> : k332 ? conv_halo_kernel<3, 3, 2, true> : conv_halo_kernel<0, 0, 0, true>;
+      launch_k(kern, P->hfwd_grid, kHaloPoolThreads, P->hfwd_smem, e->stream, P->map_x_h, P->map_w_fwd, P->map_y_out, P->hfwd);
+    } else {
+      auto kern = k331 ? conv_halo_kernel<3, 3, 1> : k332 ? conv_halo_kernel<3, 3, 2> : conv_halo_kernel<0, 0, 0>;
+      launch_k(kern, P->hfwd_grid, kIgemmThreads, P->hfwd_smem, e->stream, P->map_x_h, P->map_w_fwd, P->map_y_out, P->hfwd);
+    }
     SB_LAUNCHED();
     return true;
   }

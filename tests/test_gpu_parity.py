@@ -668,6 +668,7 @@ def test_winner_map_path_is_bit_identical_to_the_activation_path(prec, monkeypat
     for off, nofuse in (("1", "1"), ("0", "1"), ("0", "0")):
         monkeypatch.setenv("SB_NO_POOL_MAP", off)
         monkeypatch.setenv("SB_POOL_MAP_ALL", "1")
+        monkeypatch.setenv("SB_TC_POOL_FUSION", "1")  # TF32: conv2's fprop pools in its own epilogue (opt-in as well)
         monkeypatch.setenv("SB_NO_HEAD_DGRAD_FUSION", nofuse)
         e = make_engine(sm, S.CategoricalCrossentropy, S.Adam(0.001), 12, (14, 14, 1), (10,), precision=prec)
         e.init_params()
