@@ -320,6 +320,14 @@ struct HaloParams {
   int pool, row_stride;
   float* pooled;
   unsigned* pmap;
+  // KW-folding (instantiations with a compile-time KW): the KW taps of one kernel row share ONE MMA -- the same A view (row shift of
+  // the kernel row only) against B = [W(kh,0) | W(kh,1) | ...] with N = KW * N accumulator columns; column block j then holds the
+  // tap's contribution displaced by j pixels (rows of the pitch-linear index), and the epilogue re-aligns:
+  //   out[m] = sum_j D[m + d_j][block j],  d_j = j (fprop) or KW-1-j (dgrad, flipped taps).
+  // At N = 64 an MMA is bound by its shared-memory operand fetch (4 KB of A + 32 B x N of B per K = 8 at 128 B/cycle); folding
+  // fetches A once per kernel row instead of once per tap: 36 MMAs x 48 cycles -> 12 x 96 (fprop, N = 192, now math-bound), 72 x 40
+  // -> 24 x 56 (dgrad, N = 96).
+  int fold;
 };
 // winner byte of a 2x2 window (the same definition as kernels_fast.cu win4): index of the FIRST maximum in row-major order | (max > thr) << 2
 __device__ __forceinline__ unsigned tc_win4(float a, float b, float c, float d, int relu, float thr, float* mx) {
@@ -358,10 +366,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* b_bar = tmem_empty + 2;
   uint32_t* tmem_slot = (uint32_t*)(b_bar + 1);
+  // KW-folding: rows a warp needs from the next TMEM sub-partition -- [2 tile parities][N/32 chunks][4 sub-partitions][KW-1 blocks][KW-1 rows][32]
+  float* xch = reinterpret_cast<float*>(((uintptr_t)(tmem_slot + 4) + 15) & ~(uintptr_t)15);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // shfl: provably warp-uniform
+  constexpr bool FOLD_OK = !POOL && TKW >= 2 && TKW <= 4;  // folding needs a compile-time KW (register arrays in the epilogue)
+  const bool fold = FOLD_OK && p.fold;
+  const int NB = fold ? TKW * p.N : p.N;  // accumulator columns per buffer
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < 2 * p.N) tmem_cols <<= 1;
+  while ((int)tmem_cols < 2 * NB) tmem_cols <<= 1;
   long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 64 : nullptr;
 #define HALO_T(slot) do { if (dbg) dbg[slot] = clock64(); } while (0)
 
@@ -393,7 +406,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     mbar_arrive_expect_tx(b_bar, (uint32_t)b_bytes);
     for (int tap = 0; tap < taps; ++tap)
       for (int kc = 0; kc < p.kchunks; ++kc) {
-        uint8_t* sb = sm_b + (size_t)(tap * p.kchunks + kc) * b_tile_bytes;
+        // folded: [chunk][tap] so that the KW taps of a kernel row are adjacent for every channel chunk
+        uint8_t* sb = sm_b + (size_t)(fold ? kc * taps + tap : tap * p.kchunks + kc) * b_tile_bytes;
         if (p.b_mn_major) {
           for (int j = 0; j < p.N / 32; ++j) tma_load_2d(sb + j * 4096, &map_b, b_bar, j * 32, tap * p.b_rows_per_tap + kc * 32);
         } else {
@@ -446,10 +460,36 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (lane == 0 && ti < 6) HALO_T(8 + ti * 2);
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.N);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NB);
         const uint32_t sa0 = a_lo0 + (smem_u32(sm_a + (size_t)stage * stage_bytes) >> 4);
         uint32_t accumulate = 0;
         uint32_t bt = sb0;
+        if (fold) {
+          // one MMA per (kernel row, chunk, k-step): A = the tile shifted by the kernel row only, B = the row's KW taps side by side
+          const uint32_t idesc_f = idesc_tf32(128, NB, 0, p.b_mn_major);
+          uint32_t row_at = sa0 + (p.flip ? (uint32_t)((KH - 1) * P8) : 0u);
+          const int32_t step_h = p.flip ? -P8 : P8;
+          const uint32_t b_row = (uint32_t)KW * b_chunk, b_kc = (uint32_t)(KH * KW) * b_chunk;  // [chunk][tap] layout
+#pragma unroll
+          for (int kh = 0; kh < KH; ++kh, row_at += step_h) {
+            uint32_t at = row_at, btk = sb0 + (uint32_t)kh * b_row;
+#pragma unroll
+            for (int kc = 0; kc < kchunks; ++kc, at += a_chunk, btk += b_kc) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                umma_tf32_elect(d_tmem, ((uint64_t)a_hi << 32) | (at + ks * 2), ((uint64_t)b_hi << 32) | (btk + ks * b_ks_step), idesc_f,
+                                accumulate);
+                accumulate = 1;
+              }
+            }
+          }
+          umma_commit_elect(&empty_bar[stage]);
+          umma_commit_elect(&tmem_full[acc]);
+          if (lane == 0 && ti < 6) HALO_T(9 + ti * 2);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          continue;
+        }
         // tap (kh,kw) reads source rows shifted by (dh*P + dw) pixels = 8 descriptor units (128 B >> 4) each
         uint32_t row_at = sa0 + (p.flip ? (uint32_t)((KH - 1) * P8 + (KW - 1) * 8) : 0u);
         const int32_t step_w = p.flip ? -8 : 8, step_h = p.flip ? -P8 : P8;
@@ -573,10 +613,52 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (threadIdx.x == 64) tma_store_wait_read1();
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
+      const int nch = p.N >> 5;
+      const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * NB);
+      if (FOLD_OK && fold) {
+        // pass 1: the first KW-1 rows of every warp are the rows its predecessor's last lanes will need (displaced blocks only)
+        for (int ch = 0; ch < nch; ++ch)
+#pragma unroll
+          for (int d = 1; d < (FOLD_OK ? TKW : 1); ++d) {
+            const int jb = p.flip ? TKW - 1 - d : d;
+            float t[32];
+            tmem_ld32(t_row + (uint32_t)(jb * p.N + ch * 32), t);
+            tmem_ld_wait();
+            if (lane < d) {
+              float* dst = xch + ((((size_t)((ti & 1) * nch + ch) * 4 + sub) * (TKW - 1) + (d - 1)) * (TKW - 1) + lane) * 32;
+#pragma unroll
+              for (int q = 0; q < 32; q += 4) *reinterpret_cast<float4*>(dst + q) = make_float4(t[q], t[q + 1], t[q + 2], t[q + 3]);
+            }
+          }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+      }
       for (int c0 = 0; c0 < p.N; c0 += 32) {
         float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * p.N + c0), v);
-        tmem_ld_wait();
+        if (FOLD_OK && fold) {
+          // out[m] = D[m][block of displacement 0] + D[m+1][displacement 1] + ... : the other rows live in the next lanes (shuffle)
+          // or, for the last lanes of a warp, in the next sub-partition (pass 1's exchange rows; rows >= 128 only feed dropped outputs)
+          tmem_ld32(t_row + (uint32_t)((p.flip ? TKW - 1 : 0) * p.N + c0), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int d = 1; d < (FOLD_OK ? TKW : 1); ++d) {
+            const int jb = p.flip ? TKW - 1 - d : d;
+            float t[32];
+            tmem_ld32(t_row + (uint32_t)(jb * p.N + c0), t);
+            tmem_ld_wait();
+            const bool over = lane + d >= 32;
+            const float* src = xch + ((((size_t)((ti & 1) * nch + (c0 >> 5)) * 4 + ((sub + 1) & 3)) * (TKW - 1) + (d - 1)) * (TKW - 1) +
+                                      ((lane + d) & 31)) * 32;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+              float up = __shfl_down_sync(0xffffffffu, t[q], d);
+              if (over) up = sub < 3 ? src[q] : 0.f;
+              v[q] = __fadd_rn(v[q], up);
+            }
+          }
+        } else {
+          tmem_ld32(t_row + (uint32_t)c0, v);
+          tmem_ld_wait();
+        }
         if (p.relu) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(p.thr, v[j]);
@@ -1098,13 +1180,17 @@ static bool plan_halo(HaloParams& p, CUtensorMap* map, CUtensorMap* map_out, con
   p.bo_mode = (bo && bo[0] == '1') ? 1 : 0;
   const int b_bytes = KH * KW * p.kchunks * Nacc * 128;
   const int stage_bytes = p.kchunks * p.a_tile_bytes;
+  // KW-folding: the instantiations with compile-time KW = 3 (KH = 3, one or two channel chunks), accumulators 2 x KW*N <= 512 columns
+  { const char* fo = getenv("SB_TC_FOLD");
+    p.fold = (!pool && !(fo && fo[0] == '0') && KH == 3 && KW == 3 && (p.kchunks == 1 || p.kchunks == 2) && KW * Nacc <= 256) ? 1 : 0; }
+  const int xch_bytes = p.fold ? 2 * (Nacc / 32) * 4 * (KW - 1) * (KW - 1) * 128 + 32 : 0;
   const char* ts = getenv("SB_TC_TMA_STORE");
   p.tma_store = !pool && !(ts && ts[0] == '0') && p.Wg <= 256;
-  int fixed = b_bytes + 16 * 16 + 1024 + 256 + ((p.tma_store || pool) ? 2 * (Nacc / 32) * 16384 : 0);
+  int fixed = b_bytes + 16 * 16 + 1024 + 256 + xch_bytes + ((p.tma_store || pool) ? 2 * (Nacc / 32) * 16384 : 0);
   if (pool && (dev_smem - fixed) / stage_bytes < 2) return false;  // the pooled epilogue needs its staging tiles
   if (p.tma_store && (dev_smem - fixed) / stage_bytes < 2) {  // staging does not fit: per-thread stores
     p.tma_store = 0;
-    fixed = b_bytes + 16 * 16 + 1024 + 256;
+    fixed = b_bytes + 16 * 16 + 1024 + 256 + xch_bytes;
   }
   p.stages = std::min(6, (dev_smem - fixed) / stage_bytes);
   if (p.stages < 2) return false;
