@@ -346,8 +346,9 @@ __device__ __forceinline__ unsigned tc_win4(float a, float b, float c, float d, 
 // the latency of the ~90-instruction item loop and a tile's pooling takes 3x its MMAs (measured: fprop 15 -> 23 us)
 constexpr int kHaloPoolWarps = 24;
 constexpr int kHaloPoolThreads = 64 + 32 * kHaloPoolWarps;
-template <int TKH, int TKW, int TKC, bool POOL = false>
-__global__ void __launch_bounds__(POOL ? kHaloPoolThreads : kIgemmThreads, 1)
+// FOLD: compile-time switch of the KW-folded variant (8 epilogue warps, 320 threads); the plain instantiation carries none of its code
+template <int TKH, int TKW, int TKC, bool POOL = false, bool FOLD = false>
+__global__ void __launch_bounds__(POOL ? kHaloPoolThreads : (FOLD ? kIgemmThreadsX3 : kIgemmThreads), 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_c, const HaloParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -370,8 +371,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   float* xch = reinterpret_cast<float*>(((uintptr_t)(tmem_slot + 4) + 15) & ~(uintptr_t)15);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // shfl: provably warp-uniform
-  constexpr bool FOLD_OK = !POOL && TKW >= 2 && TKW <= 4;  // folding needs a compile-time KW (register arrays in the epilogue)
-  const bool fold = FOLD_OK && p.fold;
+  constexpr bool FOLD_OK = FOLD && !POOL && TKW >= 2 && TKW <= 4;  // folding needs a compile-time KW (register arrays in the epilogue)
+  constexpr bool fold = FOLD_OK;
+  constexpr int kEpiWarps = FOLD_OK ? 8 : 4, kEpiThreads = 32 * kEpiWarps;
   const int NB = fold ? TKW * p.N : p.N;  // accumulator columns per buffer
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < 2 * NB) tmem_cols <<= 1;
@@ -389,7 +391,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], POOL ? 8 : 4);
+      mbar_init(&tmem_empty[a], (POOL || FOLD_OK) ? 8 : 4);
     }
     mbar_init(b_bar, 1);
     fence_barrier_init();
@@ -592,8 +594,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       if (threadIdx.x == 64 && ti < 6) HALO_T(25 + ti * 2);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-  } else if (warp < 6) {
+  } else if (warp < 2 + kEpiWarps) {
     // ================= epilogue: TMEM -> registers -> (ReLU) -> NHWC rows =================
+    // (folded variant: eight warps -- warps 2..5 own the even 32-channel chunks, warps 6..9 the odd ones)
+    const int grp = (warp - 2) >> 2;
     const int sub = warp & 3;  // TMEM sub-partition this warp may read: lanes [32*sub, 32*sub+32)
     const int m = sub * 32 + lane;
     const int r = m / p.P, c = m - r * p.P;
@@ -611,13 +615,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       if (p.tma_store) {
         // the staging buffer is free once the stores issued two tiles ago have READ it
         if (threadIdx.x == 64) tma_store_wait_read1();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       }
       const int nch = p.N >> 5;
       const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * NB);
       if (FOLD_OK && fold) {
         // pass 1: the first KW-1 rows of every warp are the rows its predecessor's last lanes will need (displaced blocks only)
-        for (int ch = 0; ch < nch; ++ch)
+        for (int ch = grp; ch < nch; ch += 2)
 #pragma unroll
           for (int d = 1; d < (FOLD_OK ? TKW : 1); ++d) {
             const int jb = p.flip ? TKW - 1 - d : d;
@@ -630,9 +634,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               for (int q = 0; q < 32; q += 4) *reinterpret_cast<float4*>(dst + q) = make_float4(t[q], t[q + 1], t[q + 2], t[q + 3]);
             }
           }
-        asm volatile("bar.sync 2, 128;" ::: "memory");
+        asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads) : "memory");
       }
-      for (int c0 = 0; c0 < p.N; c0 += 32) {
+      for (int c0 = (FOLD_OK ? grp * 32 : 0); c0 < p.N; c0 += (FOLD_OK ? 64 : 32)) {
         float v[32];
         if (FOLD_OK && fold) {
           // out[m] = D[m][block of displacement 0] + D[m+1][displacement 1] + ... : the other rows live in the next lanes (shuffle)
@@ -646,12 +650,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             tmem_ld32(t_row + (uint32_t)(jb * p.N + c0), t);
             tmem_ld_wait();
             const bool over = lane + d >= 32;
-            const float* src = xch + ((((size_t)((ti & 1) * nch + (c0 >> 5)) * 4 + ((sub + 1) & 3)) * (TKW - 1) + (d - 1)) * (TKW - 1) +
-                                      ((lane + d) & 31)) * 32;
+            if (over) {  // the last d lanes: the rows come from the next sub-partition's exchange rows (eight 128-bit loads)
+              const float* src = xch + ((((size_t)((ti & 1) * nch + (c0 >> 5)) * 4 + ((sub + 1) & 3)) * (TKW - 1) + (d - 1)) * (TKW - 1) +
+                                        ((lane + d) & 31)) * 32;
+#pragma unroll
+              for (int q = 0; q < 32; q += 4) {
+                const float4 x4 = sub < 3 ? *reinterpret_cast<const float4*>(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                t[q] = x4.x; t[q + 1] = x4.y; t[q + 2] = x4.z; t[q + 3] = x4.w;
+              }
+            }
+            // lane i takes lane i+d's value; the last d lanes (shuffle source out of range: their own register comes back) hold
+            // the exchange rows loaded above
 #pragma unroll
             for (int q = 0; q < 32; ++q) {
-              float up = __shfl_down_sync(0xffffffffu, t[q], d);
-              if (over) up = sub < 3 ? src[q] : 0.f;
+              const float tq = t[q];
+              const float up = __shfl_down_sync(0xffffffffu, tq, d);
               v[q] = __fadd_rn(v[q], up);
             }
           }
@@ -680,7 +693,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (p.tma_store) {
         fence_proxy_async();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         if (threadIdx.x == 64) {
           const int rows = min(p.BH, p.Hg - h0);
           for (int rr = 0; rr < rows; ++rr)
@@ -1452,6 +1465,8 @@ void tc_plan_layers(sb_engine* e) {
     SB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
     SB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<3, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
     SB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<3, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
+    SB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<3, 3, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
+    SB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<3, 3, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
     SB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<0, 0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
     SB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<3, 3, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
     SB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<3, 3, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
@@ -1566,6 +1581,9 @@ bool tc_conv_fwd(sb_engine* e, LayerPlan& L, int) {
     if (P->hfwd.pool) {
       auto kern = k331 ? conv_halo_kernel<3, 3, 1, true> : k332 ? conv_halo_kernel<3, 3, 2, true> : conv_halo_kernel<0, 0, 0, true>;
       launch_k(kern, P->hfwd_grid, kHaloPoolThreads, P->hfwd_smem, e->stream, P->map_x_h, P->map_w_fwd, P->map_y_out, P->hfwd);
+    } else if (P->hfwd.fold && (k331 || k332)) {
+      auto kern = k331 ? conv_halo_kernel<3, 3, 1, false, true> : conv_halo_kernel<3, 3, 2, false, true>;
+      launch_k(kern, P->hfwd_grid, kIgemmThreadsX3, P->hfwd_smem, e->stream, P->map_x_h, P->map_w_fwd, P->map_y_out, P->hfwd);
     } else {
       auto kern = k331 ? conv_halo_kernel<3, 3, 1> : k332 ? conv_halo_kernel<3, 3, 2> : conv_halo_kernel<0, 0, 0>;
       launch_k(kern, P->hfwd_grid, kIgemmThreads, P->hfwd_smem, e->stream, P->map_x_h, P->map_w_fwd, P->map_y_out, P->hfwd);
@@ -1748,10 +1766,14 @@ bool tc_conv_dgrad(sb_engine* e, LayerPlan& L, int) {
   ConvTcPlan* P = (ConvTcPlan*)L.tc_plan;
   if (!P || L.tc_kind != 1 || !P->has_dgrad) return false;
   if (P->halo_dg) {
-    auto kern = P->hdg.KH == 3 && P->hdg.KW == 3 && P->hdg.kchunks == 1   ? conv_halo_kernel<3, 3, 1>
-                : P->hdg.KH == 3 && P->hdg.KW == 3 && P->hdg.kchunks == 2 ? conv_halo_kernel<3, 3, 2>
-                                                                             : conv_halo_kernel<0, 0, 0>;
-    launch_k(kern, P->hdg_grid, kIgemmThreads, P->hdg_smem, e->stream, P->map_dy_h, P->map_w_dg, P->map_dx_out, P->hdg);
+    const bool k331 = P->hdg.KH == 3 && P->hdg.KW == 3 && P->hdg.kchunks == 1, k332 = P->hdg.KH == 3 && P->hdg.KW == 3 && P->hdg.kchunks == 2;
+    if (P->hdg.fold && (k331 || k332)) {
+      auto kern = k331 ? conv_halo_kernel<3, 3, 1, false, true> : conv_halo_kernel<3, 3, 2, false, true>;
+      launch_k(kern, P->hdg_grid, kIgemmThreadsX3, P->hdg_smem, e->stream, P->map_dy_h, P->map_w_dg, P->map_dx_out, P->hdg);
+    } else {
+      auto kern = k331 ? conv_halo_kernel<3, 3, 1> : k332 ? conv_halo_kernel<3, 3, 2> : conv_halo_kernel<0, 0, 0>;
+      launch_k(kern, P->hdg_grid, kIgemmThreads, P->hdg_smem, e->stream, P->map_dy_h, P->map_w_dg, P->map_dx_out, P->hdg);
+    }
     SB_LAUNCHED();
     return true;
   }
