@@ -650,22 +650,24 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             tmem_ld32(t_row + (uint32_t)(jb * p.N + c0), t);
             tmem_ld_wait();
             const bool over = lane + d >= 32;
-            if (over) {  // the last d lanes: the rows come from the next sub-partition's exchange rows (eight 128-bit loads)
-              const float* src = xch + ((((size_t)((ti & 1) * nch + (c0 >> 5)) * 4 + ((sub + 1) & 3)) * (TKW - 1) + (d - 1)) * (TKW - 1) +
+            // lane i takes lane i+d's row; for the last d lanes that row lives in the next sub-partition: pass 1's exchange rows
+            // (their OWN registers stay untouched -- they are the shuffle sources of the lanes below them)
+            float xr[32];
+#pragma unroll
+            for (int q = 0; q < 32; ++q) xr[q] = 0.f;
+            if (over && sub < 3) {
+              const float* src = xch + ((((size_t)((ti & 1) * nch + (c0 >> 5)) * 4 + (sub + 1)) * (TKW - 1) + (d - 1)) * (TKW - 1) +
                                         ((lane + d) & 31)) * 32;
 #pragma unroll
               for (int q = 0; q < 32; q += 4) {
-                const float4 x4 = sub < 3 ? *reinterpret_cast<const float4*>(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-                t[q] = x4.x; t[q + 1] = x4.y; t[q + 2] = x4.z; t[q + 3] = x4.w;
+                const float4 x4 = *reinterpret_cast<const float4*>(src + q);
+                xr[q] = x4.x; xr[q + 1] = x4.y; xr[q + 2] = x4.z; xr[q + 3] = x4.w;
               }
             }
-            // lane i takes lane i+d's value; the last d lanes (shuffle source out of range: their own register comes back) hold
-            // the exchange rows loaded above
 #pragma unroll
             for (int q = 0; q < 32; ++q) {
-              const float tq = t[q];
-              const float up = __shfl_down_sync(0xffffffffu, tq, d);
-              v[q] = __fadd_rn(v[q], up);
+              const float up = __shfl_down_sync(0xffffffffu, t[q], d);
+              v[q] = __fadd_rn(v[q], over ? xr[q] : up);
             }
           }
         } else {
@@ -1194,8 +1196,13 @@ static bool plan_halo(HaloParams& p, CUtensorMap* map, CUtensorMap* map_out, con
   const int b_bytes = KH * KW * p.kchunks * Nacc * 128;
   const int stage_bytes = p.kchunks * p.a_tile_bytes;
   // KW-folding: the instantiations with compile-time KW = 3 (KH = 3, one or two channel chunks), accumulators 2 x KW*N <= 512 columns
+  // Default: dgrad only (flip) -- there N = Cin is small, the unfolded MMAs are at their worst (40 cycles for N = 32) and the
+  // re-aligning epilogue is light: LeNet conv2 dgrad 20.9 -> 18.7 us eager.  For fprop (N = 64 -> 192) the epilogue's 128 shuffles
+  // per thread and tile outweigh the saved MMA cycles (15.0 -> 18.8 us); SB_TC_FOLD=2 folds both, =0 none.
   { const char* fo = getenv("SB_TC_FOLD");
-    p.fold = (!pool && !(fo && fo[0] == '0') && KH == 3 && KW == 3 && (p.kchunks == 1 || p.kchunks == 2) && KW * Nacc <= 256) ? 1 : 0; }
+    const int mode = fo ? atoi(fo) : 1;
+    const bool geom = !pool && KH == 3 && KW == 3 && (p.kchunks == 1 || p.kchunks == 2) && KW * Nacc <= 256;
+    p.fold = (geom && (mode >= 2 || (mode == 1 && flip))) ? 1 : 0; }
   const int xch_bytes = p.fold ? 2 * (Nacc / 32) * 4 * (KW - 1) * (KW - 1) * 128 + 32 : 0;
   const char* ts = getenv("SB_TC_TMA_STORE");
   p.tma_store = !pool && !(ts && ts[0] == '0') && p.Wg <= 256;
