@@ -966,7 +966,17 @@ static void run_backward(sb_engine* e) {
           // that starts AFTER the dgrad kernel: both want every SM's shared memory, whereas the pool / activation backward
           // kernels that follow dgrad leave room for it (not while per-kernel timing is on).
           const bool fork = fork_enabled() && !e->profiling && L.need_dx && din && !L.wgrad_in_pool;
-          if (!fork) {
+          // SB_FORK_MODE: 1 (default) = the side branch starts BEFORE dgrad, as soon as dY exists; 0 = after dgrad; 2 = no side
+          // branch.  Round 1 measured "after" ahead (both kernels want every SM's shared memory); with the dgrad kernel folded and
+          // the head's combine gone from the main stream the filter gradient + its reduce had become the tail of the step (in-situ
+          // timeline: they finished 9 us after the main stream's last kernel): 1050 k -> 1090 k samples/s, no branch 1022 k.
+          static const int fork_mode = [] { const char* v = getenv("SB_FORK_MODE"); return v ? atoi(v) : 1; }();
+          if (fork && fork_mode == 1) {
+            side_branch_begin(e);
+            wdone = tc_conv_wgrad(e, L, li, e->bstream);
+            side_branch_end(e);
+          }
+          if (!fork || fork_mode == 2) {
             Prof pr(e, "conv2d_wgrad_tf32_tcgen05", cb, fl);
             wdone = tc_conv_wgrad(e, L, li);
           }
@@ -974,7 +984,7 @@ static void run_backward(sb_engine* e) {
             Prof pr(e, "conv2d_dgrad_tf32_tcgen05", cb, fl);
             ddone = tc_conv_dgrad(e, L, li);
           }
-          if (fork) {
+          if (fork && fork_mode == 0) {
             side_branch_begin(e);
             wdone = tc_conv_wgrad(e, L, li, e->bstream);
             side_branch_end(e);
