@@ -870,8 +870,15 @@ static void run_loss(sb_engine* e, bool with_grad) {
   }
 }
 
+// SB_MERGE_REDUCE=0: every filter-gradient reduction right behind its kernel (round-1 behaviour)
+static ReduceBatch* reduce_batch(sb_engine* e) {
+  static const bool on = [] { const char* v = getenv("SB_MERGE_REDUCE"); return !(v && v[0] == '0'); }();
+  return (on && !e->profiling) ? &e->pending_reduce : nullptr;
+}
+
 static void run_backward(sb_engine* e) {
   cudaStream_t s = e->stream;
+  e->pending_reduce.count = 0;
   const int nl = (int)e->L.size();
   for (int li = nl - 1; li >= 0; --li) {
     LayerPlan& L = e->L[li];
@@ -973,7 +980,7 @@ static void run_backward(sb_engine* e) {
           static const int fork_mode = [] { const char* v = getenv("SB_FORK_MODE"); return v ? atoi(v) : 1; }();
           if (fork && fork_mode == 1) {
             side_branch_begin(e);
-            wdone = tc_conv_wgrad(e, L, li, e->bstream);
+            wdone = tc_conv_wgrad(e, L, li, e->bstream, reduce_batch(e));
             side_branch_end(e);
           }
           if (!fork || fork_mode == 2) {
@@ -1012,7 +1019,7 @@ static void run_backward(sb_engine* e) {
           Prof pr(e, "pool_relu_bwd_conv_wgrad", 4.0 * ((double)L.in.numel() + n_out + CL.in.numel()),
                   2.0 * CL.cg.N * CL.cg.OH * CL.cg.OW * (double)CL.cg.Cout * CL.cg.KH * CL.cg.KW * CL.cg.Cin);
           if (pool_bwd_conv_wgrad(in, dout, din, L.pg, L.pool_relu_bwd, L.fused_thr, e->acts[CL.buf_in], CL.cg, G(e, CL.p_w), 0, e->ws,
-                                  e->ws_floats, s, L.pool_map))
+                                  e->ws_floats, s, L.pool_map, reduce_batch(e)))
             break;
           SB_FAIL(SB_ERR_CUDA, "pool_bwd_conv_wgrad rejected a planned shape");
         }
@@ -1053,6 +1060,10 @@ static void run_backward(sb_engine* e) {
     SB_CUDA(cudaStreamWaitEvent(s, e->ev_join, 0));
     e->bwd_forked = false;
   }
+  // the filter-gradient partials collected above (both streams have joined): one launch for all of them
+  const long long before = tl_launch_count;
+  partial_reduce_multi(e->pending_reduce, s);
+  (void)before;
 }
 
 // loss += penalty(theta) and (with_grad) grad += dPenalty/dw, tensors in model order (models/Model.scala:92-119)

@@ -136,6 +136,7 @@ struct sb_engine {
   cudaStream_t bstream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool bwd_forked = false;
+  sb::ReduceBatch pending_reduce;  // filter-gradient partial sums of this backward pass, reduced in one launch before the optimizer
   bool pdl_early = false;   // the shared kernels (prologue, optimizer, head loss, partial reduce) trigger their dependents early
   cudaStream_t cstream = nullptr;
   float* stage_x[2] = {nullptr, nullptr};

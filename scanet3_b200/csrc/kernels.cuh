@@ -132,9 +132,10 @@ void pool_max_bwd_v4(const float* x, const float* dy, float* dx, const PoolGeom&
 bool pool22_map_ok(const PoolGeom& g);  // the winner-map kernels cover this pool geometry
 // 2x2 stride-1 max-pool backward (+ReLU mask) that also accumulates the filter gradient of the small-K Conv2D feeding the pool
 // (conv >> [in-place ReLU] >> pool); dx is written only when store_dx.  false: shape not covered
+struct ReduceBatch;
 bool pool_bwd_conv_wgrad(const float* x, const float* dy, float* dx, const PoolGeom& g, int relu, float thr, const float* conv_in,
                          const ConvGeom& cg, float* dw, int store_dx, float* ws, size_t ws_floats, cudaStream_t s,
-                         const unsigned char* map = nullptr);
+                         const unsigned char* map = nullptr, ReduceBatch* defer = nullptr);
 void conv_smallk_fwd(const float* x, const float* w, float* y, const ConvGeom& g, int relu, float thr, cudaStream_t s);
 // conv (small K, stride 1) >> [ReLU] >> max-pool 2x2 stride 1 VALID: y = the (activated) conv output, pooled = the pool output.
 // false: shape not covered
@@ -163,4 +164,21 @@ bool act_bwd_col_sum(float* g, const float* y, int act, float thr, float* out, l
                      cudaStream_t s);
 // out[i] = sum_c partial[c*n + i], fixed order
 void partial_reduce(const float* partial, float* out, int n, int parts, cudaStream_t s);
+// Reductions that are all due at the same point of the step (the filter-gradient partials of several layers, just before the
+// optimizer) collected into ONE launch: each is summed in the order partial_reduce uses for > 48 parts (32 lane groups), so
+// only reductions with > 48 parts are accepted (same bits as the separate launch).
+struct ReduceBatch {
+  static constexpr int kMax = 4;
+  const float* partial[kMax];
+  float* out[kMax];
+  int n[kMax], parts[kMax], blocks[kMax];
+  int count = 0;
+  bool add(const float* p, float* o, int n_, int parts_) {
+    if (count >= kMax || parts_ <= 48) return false;
+    partial[count] = p; out[count] = o; n[count] = n_; parts[count] = parts_; blocks[count] = 0;
+    ++count;
+    return true;
+  }
+};
+void partial_reduce_multi(ReduceBatch& rb, cudaStream_t s);  // no-op when empty; leaves the batch empty
 }  // namespace sb

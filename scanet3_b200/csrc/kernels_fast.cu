@@ -736,7 +736,7 @@ static bool pool_is_22s1(const PoolGeom& g);
 // max-pool backward (+ReLU mask) with the filter gradient of the preceding small-K conv: returns false when not covered
 bool pool_bwd_conv_wgrad(const float* x, const float* dy, float* dx, const PoolGeom& g, int relu, float thr, const float* conv_in,
                          const ConvGeom& cg, float* dw, int store_dx, float* ws, size_t ws_floats, cudaStream_t s,
-                         const unsigned char* map) {
+                         const unsigned char* map, ReduceBatch* defer) {
   const int C4 = g.C / 4, shape = cg.KH * 100 + cg.KW * 10 + cg.Cin;
   if (!pool_is_22s1(g) || (g.C & 3) || C4 > 32 || (C4 & (C4 - 1)) || cg.SH != 1 || cg.SW != 1) return false;
   if (cg.OH != g.H || cg.OW != g.W || cg.Cout != g.C || cg.N != g.N) return false;
@@ -756,6 +756,7 @@ bool pool_bwd_conv_wgrad(const float* x, const float* dy, float* dx, const PoolG
     if (shape == 331) SB_POOL_MAP(331); else if (shape == 333) SB_POOL_MAP(333); else SB_POOL_MAP(551);
 #undef SB_POOL_MAP
     SB_LAUNCHED();
+    if (defer && defer->add(ws, dw, K * g.C, blocks)) return true;  // summed with the step's other partials in one launch
     partial_reduce(ws, dw, K * g.C, blocks, s);
     return true;
   }
@@ -768,6 +769,7 @@ bool pool_bwd_conv_wgrad(const float* x, const float* dy, float* dx, const PoolG
   }
 #undef SB_POOL_WG
   SB_LAUNCHED();
+  if (defer && defer->add(ws, dw, K * g.C, blocks)) return true;
   partial_reduce(ws, dw, K * g.C, blocks, s);
   return true;
 }
@@ -1208,6 +1210,40 @@ __global__ void __launch_bounds__(32 * YG) partial_reduce_kernel(const float* __
     for (int j = 1; j < YG; ++j) t = __fadd_rn(t, red[j][threadIdx.x]);
     out[i] = t;
   }
+}
+// several reductions in ONE launch (the filter-gradient partials of different layers, all due just before the optimizer): block b
+// belongs to the segment whose block range contains it; each segment is summed exactly as partial_reduce_kernel<32> would
+__global__ void __launch_bounds__(32 * 32) partial_reduce_multi_kernel(ReduceBatch rb, int early) {
+  pdl_prologue_trigger_if(early);
+  __shared__ float red[32][33];
+  int seg = 0, b = blockIdx.x;
+  while (seg + 1 < rb.count && b >= rb.blocks[seg]) { b -= rb.blocks[seg]; ++seg; }
+  const float* __restrict__ partial = rb.partial[seg];
+  float* __restrict__ out = rb.out[seg];
+  const int n = rb.n[seg], parts = rb.parts[seg];
+  const int i = b * 32 + threadIdx.x, y = threadIdx.y;
+  float acc = 0.f;
+  if (i < n)
+    for (int c = y; c < parts; c += 32) acc = __fadd_rn(acc, __ldg(partial + (size_t)c * n + i));
+  red[y][threadIdx.x] = acc;
+  __syncthreads();
+  if (y == 0 && i < n) {
+    float t = red[0][threadIdx.x];
+#pragma unroll
+    for (int j = 1; j < 32; ++j) t = __fadd_rn(t, red[j][threadIdx.x]);
+    out[i] = t;
+  }
+}
+void partial_reduce_multi(ReduceBatch& rb, cudaStream_t s) {
+  if (rb.count == 0) return;
+  int total = 0;
+  for (int i = 0; i < rb.count; ++i) {
+    rb.blocks[i] = (rb.n[i] + 31) / 32;
+    total += rb.blocks[i];
+  }
+  launch_k(partial_reduce_multi_kernel, total, dim3(32, 32), 0, s, rb, pdl_early_hint());
+  SB_LAUNCHED();
+  rb.count = 0;
 }
 // part c goes to lane group c % YG (summed in ascending c inside the group), then the groups in order: a fixed order for a
 // given `parts`.  Many partials -> 32 groups so that no thread walks more than ~parts/32 dependent loads.

@@ -1745,7 +1745,7 @@ bool tc_head_fwd(sb_engine* e, LayerPlan& L, const float* x, const float* w, flo
   return true;
 }
 
-bool tc_conv_wgrad(sb_engine* e, LayerPlan& L, int, cudaStream_t side) {
+bool tc_conv_wgrad(sb_engine* e, LayerPlan& L, int, cudaStream_t side, ReduceBatch* defer) {
   ConvTcPlan* P = (ConvTcPlan*)L.tc_plan;
   cudaStream_t st = side ? side : e->stream;
   if (!P || L.tc_kind != 1 || !P->wg_ok) return false;
@@ -1757,6 +1757,7 @@ bool tc_conv_wgrad(sb_engine* e, LayerPlan& L, int, cudaStream_t side) {
                 : P->hwg.KH == 3 && cis == 2 ? conv_wgrad_halo_kernel<3, 2> : conv_wgrad_halo_kernel<0, 0>;
     launch_k(kern, P->hwg_grid, kWgradThreads, P->hwg_smem, st, P->map_dy_hwg, P->map_x_hwg, P->hwg);
     SB_LAUNCHED();
+    if (defer && defer->add(P->wg_partial, e->grads + e->params[L.p_w].offset, n, P->hwg_grid)) return true;  // summed before the optimizer
     partial_reduce(P->wg_partial, e->grads + e->params[L.p_w].offset, n, P->hwg_grid, st);
     return true;
   }
@@ -1765,6 +1766,7 @@ bool tc_conv_wgrad(sb_engine* e, LayerPlan& L, int, cudaStream_t side) {
              P->map_x_wg, P->wg_list[i]);
     SB_LAUNCHED();
   }
+  if (defer && defer->add(P->wg_partial, e->grads + e->params[L.p_w].offset, n, P->wg_grid)) return true;
   partial_reduce(P->wg_partial, e->grads + e->params[L.p_w].offset, n, P->wg_grid, st);  // fixed order, 8-way parallel
   return true;
 }

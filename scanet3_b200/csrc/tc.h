@@ -5,6 +5,7 @@ typedef struct CUstream_st* cudaStream_t;  // as in driver_types.h (host_init.cp
 struct sb_engine;
 namespace sb {
 struct LayerPlan;
+struct ReduceBatch;  // kernels.cuh
 // decide per layer whether a tcgen05 kernel applies (precision != FP32 and the shape fits); build TMA maps
 void tc_plan_layers(sb_engine* e);
 void tc_free_layers(sb_engine* e);
@@ -16,7 +17,7 @@ bool tc_dense_dgrad(sb_engine* e, LayerPlan& L, int li);
 // skinny classifier head Z[M<=128, N<=16] = X[M,K] . W[K,N] as split-K partials[chunks][M][N] on tcgen05 (TF32 mode, K % 32 == 0)
 bool tc_head_fwd(sb_engine* e, LayerPlan& L, const float* x, const float* w, float* partial, size_t partial_floats, int* chunks_out);
 bool tc_conv_fwd(sb_engine* e, LayerPlan& L, int li);
-bool tc_conv_wgrad(sb_engine* e, LayerPlan& L, int li, cudaStream_t s = nullptr);  // s: side stream (null = the engine's)
+bool tc_conv_wgrad(sb_engine* e, LayerPlan& L, int li, cudaStream_t side = nullptr, ReduceBatch* defer = nullptr);  // s: side stream (null = the engine's)
 bool tc_conv_dgrad(sb_engine* e, LayerPlan& L, int li);
 
 // ---- tc_gemm.cu: tcgen05 TF32 GEMM plans (3-D tensor maps: the outer coordinate picks a slice, e.g. an LSTM time step) ----
