@@ -870,9 +870,11 @@ static void run_loss(sb_engine* e, bool with_grad) {
   }
 }
 
-// SB_MERGE_REDUCE=0: every filter-gradient reduction right behind its kernel (round-1 behaviour)
+// SB_MERGE_REDUCE=1 (experiment, off): the filter-gradient partial sums of the step in ONE launch before the optimizer instead of
+// one reduction right behind each kernel.  Measured on cfg2: 1097 k -> 975 k samples/s -- conv2's reduction (590 k threads, ~8 us
+// in the step) leaves the side branch, where it overlapped pool1's backward, for the serial tail.
 static ReduceBatch* reduce_batch(sb_engine* e) {
-  static const bool on = [] { const char* v = getenv("SB_MERGE_REDUCE"); return !(v && v[0] == '0'); }();
+  static const bool on = [] { const char* v = getenv("SB_MERGE_REDUCE"); return v && v[0] == '1'; }();
   return (on && !e->profiling) ? &e->pending_reduce : nullptr;
 }
 
