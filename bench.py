@@ -502,6 +502,12 @@ def run_ours(args):
             roofline = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": hbm, "unit": "GB/s",
                         "frac": ach / hbm, "traffic": traffic, "share_of_step": top["total_ms"] / tot,
                         "peak_note": f"HBM copy bandwidth {which}"}
+        # every tensor-core class of the step against the same TF32 figure (the north-star's own yardstick for the contractions)
+        roofline["tensor_classes"] = [
+            {"kernel": r["name"], "avg_launch_us": r["total_ms"] * 1e3 / max(r["launches"], 1),
+             "achieved_TFLOPs": r["flops"] / max(r["launches"], 1) / (r["total_ms"] / 1e3 / max(r["launches"], 1)) / 1e12,
+             "frac": r["flops"] / max(r["launches"], 1) / (r["total_ms"] / 1e3 / max(r["launches"], 1)) / 1e12 / tf32_peak}
+            for r in prof_rows if r["flops"] > 0 and "tcgen05" in r["name"] and r["total_ms"] > 0]
         roofline["avg_launch_us"] = per_launch_s * 1e6
         roofline["launches_per_step"] = n_launch / max(psteps, 1)
         roofline["algorithmic_per_launch"] = (top["flops"] if tensor_bound else top["bytes"]) / n_launch

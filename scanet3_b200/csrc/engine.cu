@@ -986,8 +986,16 @@ static void run_backward(sb_engine* e) {
             side_branch_end(e);
           }
           if (!fork || fork_mode == 2) {
-            Prof pr(e, "conv2d_wgrad_tf32_tcgen05", cb, fl);
-            wdone = tc_conv_wgrad(e, L, li);
+            // per-kernel timing: the deterministic reduction of the per-CTA partials is its own class, not half of this one
+            ReduceBatch rb;
+            {
+              Prof pr(e, "conv2d_wgrad_tf32_tcgen05", cb, fl);
+              wdone = tc_conv_wgrad(e, L, li, nullptr, e->profiling ? &rb : nullptr);
+            }
+            if (rb.count) {
+              Prof pr(e, "partial_reduce", 4.0 * ((double)rb.n[0] * rb.parts[0] + rb.n[0]), 0);
+              partial_reduce_multi(rb, s);
+            }
           }
           if (L.need_dx && din) {
             Prof pr(e, "conv2d_dgrad_tf32_tcgen05", cb, fl);
@@ -1018,11 +1026,19 @@ static void run_backward(sb_engine* e) {
         if (!L.need_dx || !din) break;
         if (L.fuse_conv_wgrad >= 0) {
           LayerPlan& CL = e->L[L.fuse_conv_wgrad];
-          Prof pr(e, "pool_relu_bwd_conv_wgrad", 4.0 * ((double)L.in.numel() + n_out + CL.in.numel()),
-                  2.0 * CL.cg.N * CL.cg.OH * CL.cg.OW * (double)CL.cg.Cout * CL.cg.KH * CL.cg.KW * CL.cg.Cin);
-          if (pool_bwd_conv_wgrad(in, dout, din, L.pg, L.pool_relu_bwd, L.fused_thr, e->acts[CL.buf_in], CL.cg, G(e, CL.p_w), 0, e->ws,
-                                  e->ws_floats, s, L.pool_map, reduce_batch(e)))
-            break;
+          ReduceBatch rb;
+          bool ok;
+          {
+            Prof pr(e, "pool_relu_bwd_conv_wgrad", 4.0 * ((double)L.in.numel() + n_out + CL.in.numel()),
+                    2.0 * CL.cg.N * CL.cg.OH * CL.cg.OW * (double)CL.cg.Cout * CL.cg.KH * CL.cg.KW * CL.cg.Cin);
+            ok = pool_bwd_conv_wgrad(in, dout, din, L.pg, L.pool_relu_bwd, L.fused_thr, e->acts[CL.buf_in], CL.cg, G(e, CL.p_w), 0, e->ws,
+                                     e->ws_floats, s, L.pool_map, e->profiling ? &rb : reduce_batch(e));
+          }
+          if (rb.count) {  // per-kernel timing: the reduction of the per-CTA partials is its own class
+            Prof pr(e, "partial_reduce", 4.0 * ((double)rb.n[0] * rb.parts[0] + rb.n[0]), 0);
+            partial_reduce_multi(rb, s);
+          }
+          if (ok) break;
           SB_FAIL(SB_ERR_CUDA, "pool_bwd_conv_wgrad rejected a planned shape");
         }
         if (L.fuse_head_dgrad >= 0) {
