@@ -55,6 +55,7 @@ struct LstmWs {
   // kernels -- the epilogue's row-per-thread TMEM layout makes every c / dc / acts access uncoalesced and concentrates the
   // pointwise work on 128 threads of <= 128 CTAs.  Kept selectable (SB_LSTM_FUSED_EPILOGUE=1) and parity-tested; off by default.
   bool fused_epilogue = false;
+  void* persist = nullptr;   // lstm_persist.cu: one launch for all T forward steps (TF32 mode, F <= 8, B % 128 == 0, <= 148 CTAs)
 };
 
 __device__ __forceinline__ float actf(float x, int act) {
@@ -278,6 +279,8 @@ LstmWs* ws_of(sb_engine* e, LayerPlan& L) {
                               e->device, x3);
     const char* fe = getenv("SB_LSTM_FUSED_EPILOGUE");
     w->fused_epilogue = fe && fe[0] == '1' && w->g_fwd && w->g_bwd && !L.d.return_sequence && !L.d.stateful;
+    if (!x3 && !w->fused_epilogue && !w->xw && w->g_fwd)
+      w->persist = lstm_persist_create((int)B, (int)T, (int)U, (int)F, w->h, w->wr_cat, e->device);
   }
   L.lstm = w;
   return w;
@@ -335,7 +338,11 @@ void lstm_forward(sb_engine* e, LayerPlan& L, int, bool store_state) {
     SB_CUDA(cudaMemcpyAsync(w->h, st_h, (size_t)BU * 4, cudaMemcpyDeviceToDevice, s));
     SB_CUDA(cudaMemcpyAsync(w->c_init, st_c, (size_t)BU * 4, cudaMemcpyDeviceToDevice, s));
   }
-  for (int t = 0; t < T; ++t) {
+  if (w->persist) {  // the whole time loop in one launch
+    lstm_persist_forward(w->persist, w->x_tm, w->wk_cat, w->b_cat, stateful ? w->c_init : nullptr, w->acts, w->c, w->h, act, ract,
+                         L.d.use_bias, stateful ? 0 : 1, s);
+  }
+  for (int t = 0; t < (w->persist ? 0 : T); ++t) {
     float* z = w->acts + (long long)t * B * 4 * U;
     const float* h_prev = w->h + (long long)t * BU;
     float* h_t = w->h + (long long)(t + 1) * BU;
@@ -469,6 +476,7 @@ void lstm_free(sb_engine* e) {
                      w->db_cat, w->dwkb_cat, w->dx_tm, w->dout_tm, w->c_init})
       cudaFree(p);
     tc_gemm_destroy(w->g_fwd); tc_gemm_destroy(w->g_bwd); tc_gemm_destroy(w->g_dwr);
+    lstm_persist_destroy(w->persist);
     delete w;
     L.lstm = nullptr;
   }

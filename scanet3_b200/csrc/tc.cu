@@ -63,6 +63,11 @@ static CUtensorMap make_map(const float* base, int rank, const uint64_t* dims, c
   return m;
 }
 
+// the same helper for the other translation units (lstm_persist.cu)
+CUtensorMap make_tma_map(const float* base, int rank, const uint64_t* dims, const uint32_t* box, bool mn_major) {
+  return make_map(base, rank, dims, box, mn_major);
+}
+
 // =====================================================================================================================
 // implicit-GEMM Conv2D fprop / dgrad
 // =====================================================================================================================

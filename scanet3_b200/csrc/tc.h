@@ -51,6 +51,12 @@ void tc_gemm_destroy(TcGemm* g);
 // halo fprop with the Pool2D(2x2, stride 1, VALID) that follows folded into its epilogue (tc.cu); false: not available
 bool tc_conv_enable_pool_fusion(sb_engine* e, LayerPlan& L, float* pooled, unsigned char* map);
 
+// persistent LSTM time loop (lstm_persist.cu): one launch for all T forward steps; create returns null when the shape is not covered
+void* lstm_persist_create(int B, int T, int U, int F, float* h, const float* wr_cat, int device);
+void lstm_persist_destroy(void* plan);
+void lstm_persist_forward(void* plan, const float* x_tm, const float* wk_cat, const float* b_cat, const float* c_init, float* acts,
+                          float* c, float* h, int act, int ract, int has_bias, int zero_state, cudaStream_t s);
+
 void lstm_plan(sb_engine* e);
 void lstm_forward(sb_engine* e, LayerPlan& L, int li, bool store_state);  // store_state: a train step of a stateful RNN
 void lstm_backward(sb_engine* e, LayerPlan& L, int li);
