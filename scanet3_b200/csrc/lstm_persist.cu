@@ -243,8 +243,12 @@ struct LstmPersistPlan {
 
 // returns an opaque plan or null when the shape is not covered (the caller keeps the per-step path)
 void* lstm_persist_create(int B, int T, int U, int F, float* h, const float* wr_cat, int device) {
-  const char* off = getenv("SB_LSTM_PERSIST");
-  if (off && off[0] == '0') return nullptr;
+  // OPT-IN (SB_LSTM_PERSIST=1).  Measured on cfg3 (B 1024, T 64, U 256; 128 CTAs): 12.1 us per step against 10.6 us for the per-step
+  // GEMM + gate kernels (forward 775 vs 676 us) -- a step is a chain of global-memory round trips (h stores -> fence -> release add
+  // -> acquire poll -> proxy fence -> TMA loads of the 128 KB row block) plus the gate math on only eight warps per SM; what would
+  // pay is a cluster whose CTAs exchange h through distributed shared memory (profiles/r2_notes.md 11).
+  const char* on = getenv("SB_LSTM_PERSIST");
+  if (!(on && on[0] == '1')) return nullptr;
   if (B % 128 || U % 32 || (4 * U) % 64 || U > 256 || F > kLpMaxF || F < 1) return nullptr;
   const int NB = 4 * U / 64, MB = B / 128;
   if (MB * NB > kNumSMs) return nullptr;  // every CTA must be resident: they wait for each other

@@ -354,3 +354,28 @@ def test_3xtf32_lenet_config2_full_size_trajectory():
         assert float(err.max()) <= 2 * rate, (k, float(err.max()))
         assert float((err > 3e-5 + 2e-3 * np.abs(v)).mean()) < 0.08, k
     e.close()
+
+
+def test_persistent_lstm_time_loop_matches_the_per_step_path(monkeypatch):
+    """csrc/lstm_persist.cu (opt-in, SB_LSTM_PERSIST=1): one launch walks all T forward steps with the recurrent weights resident in
+    shared memory and a row-block step barrier.  Same TF32 products, same gate expressions as the per-step GEMM + gate kernels:
+    saved state, output and gradients must agree to 1e-4 of the largest value (K is accumulated in the same order; the two paths
+    differ only in where the x.Wk + b term is added)."""
+    spec = [("lstm", 256), ("dense", 1, "tanh")]
+    _, sm = build_models(spec)
+    batch, t, f = 256, 16, 1
+    rng = np.random.Generator(np.random.PCG64(12))
+    x = rng.uniform(0, 1, size=(batch, t, f)).astype(f32)
+    y = rng.uniform(0, 1, size=(batch, 1)).astype(f32)
+    res = []
+    for on in ("0", "1"):
+        monkeypatch.setenv("SB_LSTM_PERSIST", on)
+        e = S.Engine(sm, S.MeanSquaredError, S.Adam(1e-3), batch, (t, f), (1,), device=0, precision=S.PREC_TF32)
+        e.init_params()
+        res.append((e.predict(x),) + e.compute_grads(x, y))
+        e.close()
+    (p0, l0, g0), (p1, l1, g1) = res
+    assert rel_to_max(p1, p0) < 1e-4
+    assert abs(l1 - l0) <= 1e-4 * abs(l0)
+    for k in g0:
+        assert rel_to_max(g1[k], g0[k]) < 1e-3, k
