@@ -4,7 +4,7 @@ ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v --expt-relaxed-constexpr
 CSRC      := scanet3_b200/csrc
 BUILD     := build
-OBJS      := $(BUILD)/engine.o $(BUILD)/kernels_simt.o $(BUILD)/kernels_fast.o $(BUILD)/tc.o $(BUILD)/tc_gemm.o $(BUILD)/lstm.o $(BUILD)/lstm_persist.o $(BUILD)/rnn.o $(BUILD)/group.o $(BUILD)/host_init.o $(BUILD)/wire.o
+OBJS      := $(BUILD)/engine.o $(BUILD)/kernels_simt.o $(BUILD)/kernels_fast.o $(BUILD)/bn_pool.o $(BUILD)/tc.o $(BUILD)/tc_gemm.o $(BUILD)/lstm.o $(BUILD)/lstm_persist.o $(BUILD)/rnn.o $(BUILD)/group.o $(BUILD)/host_init.o $(BUILD)/wire.o
 LIB       := scanet3_b200/libscanet_b200.so
 
 all: $(LIB)

@@ -493,7 +493,31 @@ static void plan_fusions(sb_engine* e) {
         }
         break;
       }
+      case SB_LAYER_BATCHNORM: {
+        // BatchNorm >> Pool2D(2x2, stride 2, VALID, max): one forward (normalise + pool + winner bytes) and one backward (route by
+        // the bytes, column sums, dx, and the ReLU in front of the BatchNorm) -- the normalised activations and the pool's / ReLU's
+        // gradients never go to memory (SB_NO_BN_POOL=1: the separate kernels)
+        const char* off = getenv("SB_NO_BN_POOL");
+        if ((off && off[0] == '1') || li + 1 >= nl || L.in.rank != 4 || !L.need_dx) break;
+        LayerPlan& PL = e->L[li + 1];
+        if (PL.d.kind != SB_LAYER_POOL2D || (PL.d.pool_honor_reduce && PL.d.pool_reduce == SB_POOL_AVG) || PL.buf_in != L.buf_out ||
+            L.buf_in == L.buf_out || !PL.need_dx || !bn_pool_ok(PL.pg))
+          break;
+        void* mp = nullptr;
+        SB_CUDA(cudaMalloc(&mp, (size_t)PL.pg.N * PL.pg.OH * PL.pg.OW * PL.pg.C));
+        PL.pool_map = (unsigned char*)mp;
+        PL.skip_fwd = PL.skip_bwd = true;
+        PL.in_bn = true;
+        L.bn_pool = li + 1;
+        if (inplace_relu(li - 1) && e->L[li - 1].buf_out == L.buf_in && e->L[li - 1].need_dx && !e->L[li - 1].skip_bwd) {
+          L.bn_relu_bwd = true;
+          L.fused_thr = e->L[li - 1].d.relu_threshold;
+          e->L[li - 1].skip_bwd = true;
+        }
+        break;
+      }
       case SB_LAYER_POOL2D: {
+        if (L.in_bn) break;  // executed by the BatchNorm in front of it
         if (L.d.pool_honor_reduce && L.d.pool_reduce == SB_POOL_AVG) break;  // average pooling: the generic kernels, no fusions
         L.fast_pool = L.pg.C % 4 == 0;
         // dx = [x > thr] * maxpool_grad: the mask of the in-place ReLU that produced this layer's input
@@ -802,6 +826,22 @@ static void run_forward(sb_engine* e, int mode) {
       case SB_LAYER_BATCHNORM: {
         const int C = (int)L.in.d[L.in.rank - 1];
         const long long rows = L.in.numel() / C;
+        if (L.bn_pool >= 0) {
+          LayerPlan& PL = e->L[L.bn_pool];
+          Prof pr(e, "batchnorm_pool_fwd", 4.0 * (2.0 * L.in.numel() + 1.25 * PL.out.numel()), 0);
+          const float *mean = P(e, L.p_aux[2]), *var = P(e, L.p_aux[3]);  // `freeze` / predict: the moving statistics
+          if (mode != FWD_INFER) {
+            if (!bn_stats(in, rows, C, L.bn_save_mean, L.bn_save_var, P(e, L.p_aux[2]), P(e, L.p_aux[3]), L.d.bn_momentum, L.bn_fused, L.d.bn_mode,
+                          mode == FWD_TRAIN, e->ws, e->ws_floats, s))
+              SB_FAIL(SB_ERR_CUDA, "bn_stats rejected a planned shape");
+            mean = L.bn_save_mean;
+            var = L.bn_save_var;
+          }
+          if (!bn_apply_pool_fwd(in, e->acts[PL.buf_out], mode != FWD_INFER ? PL.pool_map : nullptr, P(e, L.p_aux[1]), P(e, L.p_aux[0]), mean, var,
+                                 L.d.bn_epsilon, L.bn_fused, PL.pg, s))
+            SB_FAIL(SB_ERR_CUDA, "bn_apply_pool_fwd rejected a planned shape");
+          break;
+        }
         Prof pr(e, "batchnorm_fwd", 4.0 * (3.0 * L.in.numel()), 0);
         if (mode == FWD_INFER) {
           bn_fwd_infer(in, out, P(e, L.p_aux[1]), P(e, L.p_aux[0]), P(e, L.p_aux[2]), P(e, L.p_aux[3]), rows, C, L.d.bn_epsilon,
@@ -1057,6 +1097,14 @@ static void run_backward(sb_engine* e) {
       case SB_LAYER_BATCHNORM: {
         const int C = (int)L.in.d[L.in.rank - 1];
         const long long rows = L.in.numel() / C;
+        if (L.bn_pool >= 0) {
+          LayerPlan& PL = e->L[L.bn_pool];
+          Prof pr(e, "batchnorm_pool_bwd", 4.0 * (3.0 * L.in.numel() + 2.5 * PL.out.numel()), 0);
+          if (!bn_pool_bwd(in, e->dacts[PL.buf_out], PL.pool_map, din, P(e, L.p_aux[1]), L.bn_save_mean, L.bn_save_var, G(e, L.p_aux[1]),
+                           G(e, L.p_aux[0]), PL.pg, L.d.bn_epsilon, L.bn_fused, L.d.bn_mode, L.bn_relu_bwd, L.fused_thr, e->ws, e->ws_floats, s))
+            SB_FAIL(SB_ERR_CUDA, "bn_pool_bwd rejected a planned shape");
+          break;
+        }
         Prof pr(e, "batchnorm_bwd", 4.0 * (5.0 * L.in.numel()), 0);
         bn_bwd(in, dout, (L.need_dx && din) ? din : nullptr, P(e, L.p_aux[1]), L.bn_save_mean, L.bn_save_var, G(e, L.p_aux[1]),
                G(e, L.p_aux[0]), rows, C, L.d.bn_epsilon, L.bn_fused, L.d.bn_mode, e->ws, e->ws_floats, s);

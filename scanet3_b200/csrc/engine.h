@@ -67,6 +67,9 @@ struct LayerPlan {
   unsigned char* pool_map = nullptr;  // Pool2D (2x2 stride 1) whose forward is fused into the producing conv: one winner byte per
                                       // output and channel (first-max index | ReLU bit); the backward routes dy with it and the
                                       // conv activations are neither written nor read
+  int bn_pool = -1;               // BatchNorm: forward and backward also do this Pool2D(2x2, stride 2) layer (bn_pool.cu); its pool_map holds the winners
+  bool in_bn = false;             // Pool2D: executed by the BatchNorm in front of it
+  bool bn_relu_bwd = false;       // ... and the backward of the in-place ReLU in front of the BatchNorm (fused_thr)
   int fuse_head_dgrad = -1;       // Pool2D: its backward also forms the input gradient of this classifier-head Dense layer
   bool dgrad_in_pool = false;     // Dense (head): dX is produced by the pool's backward kernel; only dW is computed here
   bool wgrad_in_pool = false;     // Conv2D: the filter gradient is produced by the following pool's backward kernel

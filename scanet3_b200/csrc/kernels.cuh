@@ -83,6 +83,16 @@ void pool_bwd_relu(const float* x, const float* dy, float* dx, const PoolGeom& g
 void bn_fwd(const float* x, float* y, const float* gamma, const float* beta, float* mov_mean, float* mov_var,
             float* save_mean, float* save_var, long long rows, int C, float eps, float momentum, int fused, int bn_mode,
             int update_moving, float* ws, size_t ws_floats, cudaStream_t s);
+// bn_pool.cu: one-pass batch statistics, and BatchNorm >> Pool2D(2x2, stride 2, VALID) as one forward / one backward (false: shape not covered)
+bool bn_lean_ok(int C);
+bool bn_pool_ok(const PoolGeom& g);
+bool bn_stats(const float* x, long long rows, int C, float* save_mean, float* save_var, float* mov_mean, float* mov_var, float momentum,
+              int fused, int bn_mode, int update_moving, float* ws, size_t ws_floats, cudaStream_t s);
+bool bn_apply_pool_fwd(const float* x, float* y_pooled, unsigned char* map, const float* gamma, const float* beta, const float* mean,
+                       const float* var, float eps, int fused, const PoolGeom& g, cudaStream_t s);
+bool bn_pool_bwd(const float* x, const float* dy_pooled, const unsigned char* map, float* dx, const float* gamma, const float* save_mean,
+                 const float* save_var, float* dgamma, float* dbeta, const PoolGeom& g, float eps, int fused, int bn_mode, int relu, float thr,
+                 float* ws, size_t ws_floats, cudaStream_t s);
 void bn_fwd_infer(const float* x, float* y, const float* gamma, const float* beta, const float* mov_mean, const float* mov_var,
                   long long rows, int C, float eps, int fused, cudaStream_t s);
 void bn_bwd(const float* x, const float* dy, float* dx, const float* gamma, const float* save_mean, const float* save_var,

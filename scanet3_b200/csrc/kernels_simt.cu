@@ -858,15 +858,20 @@ void bn_fwd(const float* x, float* y, const float* gamma, const float* beta, flo
             float* save_mean, float* save_var, long long rows, int C, float eps, float momentum, int fused, int bn_mode,
             int update_moving, float* ws, size_t wsf, cudaStream_t s) {
   const bool v4 = (C % 4 == 0) && ((((uintptr_t)x) | ((uintptr_t)y)) % 16 == 0);
-  ColChunks cc = v4 ? launch_bn_reduce4<0>(x, nullptr, nullptr, nullptr, ws, wsf, rows, C, 0, s)
-                    : launch_col_reduce(FBnSum{x, C}, ws, wsf, rows, C, s);
-  launch_k(bn_mean_kernel, ceil_div(C, 128), 128, 0, s, ws, save_mean, cc.chunks, C, (float)rows);
-  SB_LAUNCHED();
-  cc = v4 ? launch_bn_reduce4<1>(x, nullptr, save_mean, nullptr, ws, wsf, rows, C, 0, s)
-          : launch_col_reduce(FBnSqDev2{x, save_mean, C}, ws, wsf, rows, C, s);
-  launch_k(bn_finalize_kernel, ceil_div(C, 128), 128, 0, s, ws, cc.chunks, C, (float)rows, gamma, beta, save_mean, save_var, mov_mean,
-                                                      mov_var, eps, momentum, fused, bn_mode, update_moving);
-  SB_LAUNCHED();
+  const char* two_pass = getenv("SB_BN_TWO_PASS");
+  const bool lean = !(two_pass && two_pass[0] == '1');
+  // one pass over x (bn_pool.cu) where the layout allows; else the two-pass moments: mean, then mean of squared deviations
+  if (!(lean && v4 && bn_stats(x, rows, C, save_mean, save_var, mov_mean, mov_var, momentum, fused, bn_mode, update_moving, ws, wsf, s))) {
+    ColChunks cc = v4 ? launch_bn_reduce4<0>(x, nullptr, nullptr, nullptr, ws, wsf, rows, C, 0, s)
+                      : launch_col_reduce(FBnSum{x, C}, ws, wsf, rows, C, s);
+    launch_k(bn_mean_kernel, ceil_div(C, 128), 128, 0, s, ws, save_mean, cc.chunks, C, (float)rows);
+    SB_LAUNCHED();
+    cc = v4 ? launch_bn_reduce4<1>(x, nullptr, save_mean, nullptr, ws, wsf, rows, C, 0, s)
+            : launch_col_reduce(FBnSqDev2{x, save_mean, C}, ws, wsf, rows, C, s);
+    launch_k(bn_finalize_kernel, ceil_div(C, 128), 128, 0, s, ws, cc.chunks, C, (float)rows, gamma, beta, save_mean, save_var, mov_mean,
+                                                        mov_var, eps, momentum, fused, bn_mode, update_moving);
+    SB_LAUNCHED();
+  }
   long long n = rows * C;
   if (v4) {
     int blocks = (int)fmin((double)ceil_div(n / 4, 256), (double)kNumSMs * 16);

@@ -735,29 +735,35 @@ struct WgradParams {
   int n_chunks, chunks_per_img;
   int BH, WK;
   int KH, KW, Cin, Cout;
-  int t0, nt;      // this launch accumulates taps [t0, t0 + nt)  (nt * Cin <= 512 TMEM columns)
-  int co0, Mh;     // ... for output channels [co0, co0 + Mh), Mh = 64 or 128 (the UMMA M)
+  // blockIdx.y picks a slice of the filter: taps [t0, t0 + nt) (nt * Cin <= 512 TMEM columns) x output channels [co0, co0 + Mh);
+  // blockIdx.x is the K split (the chunks ch = blockIdx.x, + gridDim.x, ...).  One launch covers every slice, so the number of
+  // partial filter gradients is the K split (148 / slices), not 148 per slice.
+  int n_slices, nt_max;
+  unsigned char s_t0[16], s_nt[16];
+  unsigned short s_co0[16];
+  int Mh;          // 64 or 128 (the UMMA M)
   int pt, pl;      // padding before: tap (kh,kw) pairs dY(oh,ow) with X(oh + kh - pt, ow + kw - pl); OOB pixels are zero-filled
   int stages;
-  float* partial;  // [gridDim.x][taps*Cin*Cout]
+  float* partial;  // [gridDim.x][KH*KW*Cin*Cout]
   long long* dbg;  // developer timeline (SB_TC_DEBUG=1): 64 clock64 slots per CTA, null in production
   int x3;          // 3xTF32: converter warps write the low-order tiles behind the stage's [dY | X taps]
 };
 constexpr int kWgradThreads = 192;
+constexpr int kWgradMaxSlices = 16;
 
 __global__ void __launch_bounds__(kIgemmThreadsX3, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, const WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 64 : nullptr;
+  long long* dbg = p.dbg && blockIdx.y == 0 ? p.dbg + (size_t)blockIdx.x * 64 : nullptr;
 #define WG_T(slot) do { if (dbg) dbg[slot] = clock64(); } while (0)
   if (threadIdx.x == 0) WG_T(0);
-  const int taps = p.nt;  // taps of this launch
+  const int taps = p.s_nt[blockIdx.y], t0 = p.s_t0[blockIdx.y], co0 = p.s_co0[blockIdx.y];  // this CTA's slice of the filter
   const int krows = p.BH * p.WK;            // K rows per chunk (multiple of 8)
   const int box_bytes = krows * 128;        // one 32-channel box
   const int a_bytes = (p.Mh / 32) * box_bytes;
   const int b_bytes = taps * (p.Cin / 32) * box_bytes;
-  const int hi_bytes = ((a_bytes + b_bytes + 1023) / 1024) * 1024;
+  const int hi_bytes = ((a_bytes + p.nt_max * (p.Cin / 32) * box_bytes + 1023) / 1024) * 1024;  // stage layout of the widest slice
   const int stage_bytes = p.x3 ? 2 * hi_bytes : hi_bytes;
   uint64_t* full_bar = (uint64_t*)(smem + (size_t)p.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
@@ -815,11 +821,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
         uint8_t* sa = smem + (size_t)stage * stage_bytes;
         uint8_t* sb = sa + a_bytes;
         mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(a_bytes + b_bytes));
-        for (int j = 0; j < p.Mh / 32; ++j) tma_load_4d(sa + j * box_bytes, &map_dy, &full_bar[stage], p.co0 + j * 32, 0, h0, img);
+        for (int j = 0; j < p.Mh / 32; ++j) tma_load_4d(sa + j * box_bytes, &map_dy, &full_bar[stage], co0 + j * 32, 0, h0, img);
         for (int t = 0; t < taps; ++t)
           for (int j = 0; j < p.Cin / 32; ++j)
-            tma_load_4d(sb + (t * (p.Cin / 32) + j) * box_bytes, &map_x, &full_bar[stage], j * 32, (p.t0 + t) % p.KW - p.pl,
-                        h0 + (p.t0 + t) / p.KW - p.pt, img);
+            tma_load_4d(sb + (t * (p.Cin / 32) + j) * box_bytes, &map_x, &full_bar[stage], j * 32, (t0 + t) % p.KW - p.pl,
+                        h0 + (t0 + t) / p.KW - p.pt, img);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -867,7 +873,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   } else if (warp < 6) {
     // epilogue: partial[cta][(t*Cin + ci)*Cout + co] = D_t[co][ci]
     const int sub = warp & 3;
-    float* part = p.partial + (size_t)blockIdx.x * p.KH * p.KW * p.Cin * p.Cout + (size_t)p.t0 * p.Cin * p.Cout + p.co0;
+    float* part = p.partial + (size_t)blockIdx.x * p.KH * p.KW * p.Cin * p.Cout + (size_t)t0 * p.Cin * p.Cout + co0;
     int co = -1;
     if (p.Mh == 128) co = sub * 32 + lane;                    // M = 128: TMEM lane == row
     else if (lane < 16) co = sub * 16 + lane;                 // M = 64: row m sits in lane (m % 16) + 32 * (m / 16)
@@ -1140,7 +1146,6 @@ struct ConvTcPlan {
   int hfwd_smem = 0, hdg_smem = 0, hfwd_grid = 0, hdg_grid = 0;
   WgradParams wg{};
   std::vector<WgradParams> wg_list;   // launches of the per-tap wgrad kernel (tap groups x channel halves)
-  std::vector<int> wg_smem_list;
   bool wg_ok = false;
   WgradHaloParams hwg{};
   CUtensorMap map_dy_hwg, map_x_hwg;
@@ -1373,21 +1378,28 @@ void tc_plan_layers(sb_engine* e) {
       while (p.BH > 1 && 256 / p.WK < p.BH) --p.BH;  // TMA box dims <= 256
       p.chunks_per_img = (g.OH + p.BH - 1) / p.BH;
       p.n_chunks = g.N * p.chunks_per_img;
-      P->wg_grid = std::min(p.n_chunks, kNumSMs);
-      SB_CUDA(cudaMalloc((void**)&P->wg_partial, (size_t)P->wg_grid * taps * g.Cin * g.Cout * sizeof(float)));
+      const int n_slices = ((taps + tpp - 1) / tpp) * (g.Cout / Mh);
+      const int full_grid = std::min(p.n_chunks, kNumSMs);  // what the halo kernel below would use
+      P->wg_grid = n_slices <= kWgradMaxSlices ? std::max(1, std::min(p.n_chunks, kNumSMs / n_slices)) : full_grid;  // the K split
+      SB_CUDA(cudaMalloc((void**)&P->wg_partial, (size_t)full_grid * taps * g.Cin * g.Cout * sizeof(float)));
       p.partial = P->wg_partial;
+      p.nt_max = tpp;
+      {
+        const int stage_bytes = (x3 ? 2 : 1) * (((p.BH * (Mh / 32 + tpp * (g.Cin / 32)) * box_row_bytes + 1023) / 1024) * 1024);
+        p.stages = std::max(1, std::min(4, (dev_smem - 4096) / stage_bytes));
+        P->wg_smem = p.stages * stage_bytes + 16 * (3 * p.stages + 2) + 16 + 1024;
+        if (P->wg_smem > dev_smem) P->wg_ok = false;
+      }
+      // every (tap group, channel half) slice in ONE launch (gridDim.y); more than 16 slices: one launch per 16
+      WgradParams q = p;
       for (int t0 = 0; t0 < taps; t0 += tpp)
         for (int co0 = 0; co0 < g.Cout; co0 += Mh) {
-          WgradParams q = p;
-          q.t0 = t0; q.nt = std::min(tpp, taps - t0); q.co0 = co0;
-          const int stage_bytes = (x3 ? 2 : 1) * (((p.BH * (Mh / 32 + q.nt * (g.Cin / 32)) * box_row_bytes + 1023) / 1024) * 1024);
-          q.stages = std::max(1, std::min(4, (dev_smem - 4096) / stage_bytes));
-          const int smem = q.stages * stage_bytes + 16 * (2 * q.stages + 2) + 16 + 1024;
-          if (smem > dev_smem) P->wg_ok = false;
-          P->wg_list.push_back(q);
-          P->wg_smem_list.push_back(smem);
-          P->wg_smem = std::max(P->wg_smem, smem);
+          q.s_t0[q.n_slices] = (unsigned char)t0;
+          q.s_nt[q.n_slices] = (unsigned char)std::min(tpp, taps - t0);
+          q.s_co0[q.n_slices] = (unsigned short)co0;
+          if (++q.n_slices == kWgradMaxSlices) { P->wg_list.push_back(q); q = p; }
         }
+      if (q.n_slices) P->wg_list.push_back(q);
       {
         const char* dbg = getenv("SB_TC_DEBUG");
         if (dbg && dbg[0] == '1') {
@@ -1446,7 +1458,7 @@ void tc_plan_layers(sb_engine* e) {
           p.stages = std::max(2, std::min(6, (dev_smem - 4096) / stage_bytes));
           P->hwg_grid = (int)std::min<long long>(p.n_chunks, kNumSMs);
           P->hwg_smem = p.stages * stage_bytes + 16 * (2 * p.stages + 2) + 16 + 1024;
-          if (P->hwg_smem <= dev_smem && P->hwg_grid <= P->wg_grid) {  // the partial buffer is sized for wg_grid CTAs
+          if (P->hwg_smem <= dev_smem) {  // the partial buffer is sized for min(n_chunks, SMs) CTAs
             p.partial = P->wg_partial;
             uint64_t yd[4] = {(uint64_t)g.Cout, (uint64_t)g.OW, (uint64_t)g.OH, (uint64_t)g.N};
             uint32_t yb[4] = {32, (uint32_t)p.P, (uint32_t)p.BH, 1};
@@ -1767,8 +1779,8 @@ bool tc_conv_wgrad(sb_engine* e, LayerPlan& L, int, cudaStream_t side, ReduceBat
     return true;
   }
   for (size_t i = 0; i < P->wg_list.size(); ++i) {
-    launch_k(conv_wgrad_kernel, P->wg_grid, P->wg_list[i].x3 ? kIgemmThreadsX3 : kWgradThreads, P->wg_smem_list[i], st, P->map_dy_wg,
-             P->map_x_wg, P->wg_list[i]);
+    launch_k(conv_wgrad_kernel, dim3(P->wg_grid, P->wg_list[i].n_slices), P->wg_list[i].x3 ? kIgemmThreadsX3 : kWgradThreads, P->wg_smem, st,
+             P->map_dy_wg, P->map_x_wg, P->wg_list[i]);
     SB_LAUNCHED();
   }
   if (defer && defer->add(P->wg_partial, e->grads + e->params[L.p_w].offset, n, P->wg_grid)) return true;

@@ -262,6 +262,48 @@ def test_batchnorm_cnn_trajectory(mode):  # BASELINE config 5 pattern (fused ran
                    atol=5e-5, loss_rtol=1e-4)
 
 
+BN_POOL = [("conv", 16, "relu", (3, 3), (1, 1), "Valid", False), ("bn", 0.99, "correct"), ("pool", (2, 2), (2, 2), "Valid"),
+           ("conv", 32, "relu", (3, 3), (1, 1), "Same", True), ("bn", 0.9, "correct"), ("pool", (2, 2), (2, 2), "Valid"),
+           ("flatten",), ("dense", 10, "softmax")]
+
+
+@pytest.mark.parametrize("mode", ["reference", "correct"])
+def test_batchnorm_pool_block_with_odd_extents(mode):
+    """Conv2D(ReLU) >> BatchNorm >> Pool2D(2x2, stride 2) runs as one forward and one backward (csrc/bn_pool.cu).  13x11 images:
+    the first block pools 11x9 -> 5x4 and the second 5x4 -> 2x2, so both have a last row / column outside every window (their dy is
+    zero, their BatchNorm dx is not)."""
+    spec = [(it[0], it[1], mode) if it[0] == "bn" else it for it in BN_POOL]
+    run_trajectory(spec, "cce", "adam", dict(rate=0.001), batch=12, in_shape=(13, 11, 3), classes=10, steps=5, rtol=3e-3, atol=5e-5,
+                   loss_rtol=1e-4)
+
+
+def test_batchnorm_pool_block_matches_the_separate_kernels(monkeypatch):
+    """The same model with SB_NO_BN_POOL=1 SB_BN_TWO_PASS=1 (two-pass moments, BatchNorm / Pool2D / ReLU backward as separate
+    kernels): loss and gradients agree to fp32 rounding of the sums (the one-pass moments merge partial (n, mean, M2) triples, so the
+    bits differ), and so does predict(), which normalises with the moving statistics."""
+    _, sm = build_models(BN_POOL)
+    x, y = synth_classification(24, (13, 11, 3), 10, 5)
+    outs = []
+    for off in ("1", "0"):
+        monkeypatch.setenv("SB_NO_BN_POOL", off)
+        monkeypatch.setenv("SB_BN_TWO_PASS", off)
+        e = make_engine(sm, S.CategoricalCrossentropy, S.Adam(0.001), 24, (13, 11, 3), (10,))
+        e.init_params()
+        loss, grads = e.compute_grads(x, y)
+        l1 = e.train_step(x, y, 1)
+        outs.append((loss, l1, grads, e.get_params(), e.predict(x), e.eval_loss(x, y)))
+        e.close()
+    a, b = outs
+    assert abs(a[0] - b[0]) <= 2e-6 * abs(a[0]) and abs(a[1] - b[1]) <= 2e-6 * abs(a[1]) and abs(a[5] - b[5]) <= 2e-6 * abs(a[5])
+    for k in a[2]:
+        scale = float(np.max(np.abs(a[2][k]))) + 1e-12
+        assert float(np.max(np.abs(a[2][k] - b[2][k]))) <= 2e-4 * scale, k
+    for k in a[3]:
+        if "moving" in k:
+            np.testing.assert_allclose(b[3][k], a[3][k], rtol=1e-5, atol=1e-7, err_msg=k)
+    np.testing.assert_allclose(b[4], a[4], rtol=1e-4, atol=1e-6)
+
+
 def test_graph_and_eager_are_bit_identical():
     om, sm = build_models(MLP)
     x, y = synth_classification(400, (784,), 10, 11)
