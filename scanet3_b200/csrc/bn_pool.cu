@@ -20,7 +20,7 @@ namespace {
 
 constexpr int kBnThreads = 256;
 constexpr int kBnUnroll = 8;   // rows folded per update (and loads in flight per thread)
-constexpr int kBnSegments = 8; // the finalize kernels merge the chunks in 8 consecutive segments, then the segments
+constexpr int kBnSegments = 32; // the finalize kernels sum the chunks in 32 interleaved segments, then the segments in order
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
@@ -107,33 +107,50 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const float* __res
   }
 }
 
-// merges the chunk moments (segments of consecutive chunks in parallel, then the segments in order), writes the batch statistics and
-// updates the moving ones exactly as bn_finalize_kernel (kernels_simt.cu) does
+// merges the chunk moments and writes the batch statistics; updates the moving ones exactly as bn_finalize_kernel (kernels_simt.cu).
+// With n_j rows, mean m_j and M2_j per chunk:  mean = sum n_j m_j / N,  M2 = sum (M2_j + n_j (m_j - mean)^2)  (the pairwise-merge
+// identity summed over all chunks at once, so no serial chain of divisions).  Thread (channel, segment): chunks segment, segment + 32, ..
+// in ascending order, then the 32 segments in order.
 __global__ void __launch_bounds__(32 * kBnSegments) bn_stats_finalize_kernel(const float* __restrict__ partial, int chunks, int C, long long rows,
                                                                              long long rows_per_chunk, float* __restrict__ mean_out,
                                                                              float* __restrict__ var_out, float* __restrict__ mov_mean,
                                                                              float* __restrict__ mov_var, float momentum, int fused, int bn_mode,
                                                                              int update_moving) {
   pdl_prologue();
-  __shared__ float sn[kBnSegments][33], smn[kBnSegments][33], ss[kBnSegments][33];
+  __shared__ float red[kBnSegments][33];
+  __shared__ float mean_s[32];
   const int c = blockIdx.x * 32 + threadIdx.x, seg = threadIdx.y;
-  const int per = (chunks + kBnSegments - 1) / kBnSegments;
-  float n = 0.f, m = 0.f, s = 0.f;
-  if (c < C) {
-    const int j1 = min(chunks, (seg + 1) * per);
-    for (int j = seg * per; j < j1; ++j) {
+  const bool ok = c < C;
+  const float frows = (float)rows;
+  float a = 0.f;
+  if (ok)
+    for (int j = seg; j < chunks; j += kBnSegments) {
       const long long ra = (long long)j * rows_per_chunk;
       const float nb = (float)(ra + rows_per_chunk < rows ? rows_per_chunk : rows - ra);
-      chan_merge(n, m, s, nb, partial[((long long)j * 2 + 0) * C + c], partial[((long long)j * 2 + 1) * C + c]);
+      a = __fadd_rn(a, __fmul_rn(nb, partial[((long long)j * 2 + 0) * C + c]));
     }
-  }
-  sn[seg][threadIdx.x] = n; smn[seg][threadIdx.x] = m; ss[seg][threadIdx.x] = s;
+  red[seg][threadIdx.x] = a;
   __syncthreads();
-  if (seg != 0 || c >= C) return;
-  for (int g = 1; g < kBnSegments; ++g)
-    if (sn[g][threadIdx.x] > 0.f) chan_merge(n, m, s, sn[g][threadIdx.x], smn[g][threadIdx.x], ss[g][threadIdx.x]);
-  const float frows = (float)rows;
-  const float v = __fdiv_rn(s, frows);  // biased
+  if (seg == 0) {
+    for (int g = 1; g < kBnSegments; ++g) a = __fadd_rn(a, red[g][threadIdx.x]);
+    mean_s[threadIdx.x] = __fdiv_rn(a, frows);
+  }
+  __syncthreads();
+  const float m = mean_s[threadIdx.x];
+  float q = 0.f;
+  if (ok)
+    for (int j = seg; j < chunks; j += kBnSegments) {
+      const long long ra = (long long)j * rows_per_chunk;
+      const float nb = (float)(ra + rows_per_chunk < rows ? rows_per_chunk : rows - ra);
+      const float d = __fsub_rn(partial[((long long)j * 2 + 0) * C + c], m);
+      q = __fadd_rn(q, __fadd_rn(partial[((long long)j * 2 + 1) * C + c], __fmul_rn(nb, __fmul_rn(d, d))));
+    }
+  __syncthreads();
+  red[seg][threadIdx.x] = q;
+  __syncthreads();
+  if (seg != 0 || !ok) return;
+  for (int g = 1; g < kBnSegments; ++g) q = __fadd_rn(q, red[g][threadIdx.x]);
+  const float v = __fdiv_rn(q, frows);  // biased
   mean_out[c] = m;
   var_out[c] = v;
   if (update_moving) {
@@ -279,30 +296,27 @@ __global__ void __launch_bounds__(kBnThreads) bn_pool_bwd_reduce_kernel(const fl
   }
 }
 
-// sums of the chunk partials (segments in parallel, then in order) -> dbeta, dgamma and the two sums the apply kernel needs
+// sums of the chunk partials (32 interleaved segments, then the segments in order) -> dbeta, dgamma and the two sums the apply kernel needs
 __global__ void __launch_bounds__(32 * kBnSegments) bn_bwd_sums_kernel(const float* __restrict__ partial, int chunks, int C,
                                                                        const float* __restrict__ save_mean, const float* __restrict__ save_var,
                                                                        float eps, int quirk, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                                        float* __restrict__ sums) {
   pdl_prologue();
-  __shared__ float sa[kBnSegments][33], sb_[kBnSegments][33];
+  __shared__ float sa[kBnSegments][33], sc[kBnSegments][33];
   const int c = blockIdx.x * 32 + threadIdx.x, seg = threadIdx.y;
-  const int per = (chunks + kBnSegments - 1) / kBnSegments;
   float a0 = 0.f, a1 = 0.f;
-  if (c < C) {
-    const int j1 = min(chunks, (seg + 1) * per);
-    for (int j = seg * per; j < j1; ++j) {
+  if (c < C)
+    for (int j = seg; j < chunks; j += kBnSegments) {
       a0 = __fadd_rn(a0, partial[((long long)j * 2 + 0) * C + c]);
       a1 = __fadd_rn(a1, partial[((long long)j * 2 + 1) * C + c]);
     }
-  }
   sa[seg][threadIdx.x] = a0;
-  sb_[seg][threadIdx.x] = a1;
+  sc[seg][threadIdx.x] = a1;
   __syncthreads();
   if (seg != 0 || c >= C) return;
   for (int g = 1; g < kBnSegments; ++g) {
     a0 = __fadd_rn(a0, sa[g][threadIdx.x]);
-    a1 = __fadd_rn(a1, sb_[g][threadIdx.x]);
+    a1 = __fadd_rn(a1, sc[g][threadIdx.x]);
   }
   const float var_in = quirk ? save_mean[c] : save_var[c];
   const float istd = __fdiv_rn(1.f, sqrtf(__fadd_rn(var_in, eps)));
@@ -337,7 +351,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_pool_bwd_apply_kernel(const flo
       ve[k] = __fadd_rn(quirk ? m[k] : v[k], eps);
       gi[k] = __fmul_rn(g[k], __fdiv_rn(1.f, sqrtf(ve[k])));
       mg[k] = __fdiv_rn(a[k], rows);
-      mgx[k] = __fdiv_rn(b[k], rows);
+      mgx[k] = __fdiv_rn(__fdiv_rn(b[k], rows), ve[k]);  // mean(dy * xc) / (var_in + eps), folded once per channel
     }
   }
   const float4* xp = reinterpret_cast<const float4*>(x) + c4;
@@ -373,7 +387,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_pool_bwd_apply_kernel(const flo
         for (int k = 0; k < 4; ++k) {
           const float dy = ((mp >> (8 * k)) & 0xffu) == (unsigned)(a * 2 + b) ? g[k] : 0.f;
           const float xc = __fsub_rn(xv[k], mean_in[k]);
-          const float tt = __fsub_rn(__fsub_rn(dy, mg[k]), __fdiv_rn(__fmul_rn(xc, mgx[k]), ve[k]));
+          const float tt = __fsub_rn(__fsub_rn(dy, mg[k]), __fmul_rn(xc, mgx[k]));
           const float r = __fmul_rn(gi[k], tt);
           o[k] = (!relu || xv[k] > thr) ? r : 0.f;
         }

@@ -1153,12 +1153,145 @@ __global__ void __launch_bounds__(256) conv_smallk_wgrad_kernel(const float* __r
   }
 }
 void partial_reduce(const float* partial, float* out, int n, int parts, cudaStream_t s);
+// wgrad through shared memory (Cout >= 32): a block walks tiles of 64 consecutive output pixels.  Per tile the dY rows [64][Cout] and
+// the tile's im2col matrix [64][K padded to 32] are staged once; thread (phase, k group of 8, channel group of 4) then accumulates
+// 8 x 4 products per pixel from three 128-bit shared loads (the two X loads are broadcasts), i.e. 32 FMAs per 3 loads instead of
+// 108 FMAs per 28 global loads above -- and 32 accumulators instead of 108, so three blocks fit an SM.  The phases (pixels
+// p % phases) are summed in phase order, one partial per block, blocks reduced in block order (deterministic).
+constexpr int kWgP = 64;        // pixels per tile
+constexpr int kWgKP = 32;       // K padded
+constexpr int kWgColStride = 36;  // floats per im2col row: 16-byte aligned rows, 4-way (not 32-way) conflicts on the scalar fill
+template <int KH, int KW, int CIN, int Q>
+__device__ __forceinline__ void wg_fill_cols(float* __restrict__ col, const float* __restrict__ x, const ConvGeom& g, int b, int oh, int ow, bool live) {
+  constexpr int K = KH * KW * CIN;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    constexpr int dummy = 0;
+    (void)dummy;
+    const int k = Q * 8 + j;
+    float v = 0.f;
+    if (k < K) {
+      const int tap = k / CIN, ci = k % CIN, a = tap / KW, bb = tap % KW;
+      const int ih = oh * g.SH + a - g.PT, iw = ow * g.SW + bb - g.PL;
+      if (live && ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) v = __ldg(x + (((long long)b * g.H + ih) * g.W + iw) * CIN + ci);
+    }
+    col[k] = v;
+  }
+}
+template <int KH, int KW, int CIN>
+__global__ void __launch_bounds__(256, 3) conv_smallk_wgrad_tile_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                        float* __restrict__ partial, ConvGeom g, long long pixels, int tiles) {
+  pdl_prologue();
+  constexpr int K = KH * KW * CIN;
+  static_assert(K <= kWgKP, "K must fit the padded im2col row");
+  extern __shared__ __align__(16) float wg_sm[];
+  const int Cout = g.Cout, CO4 = Cout >> 2;
+  float* dys = wg_sm;                        // [kWgP][Cout]
+  float* cols = wg_sm + kWgP * Cout;         // [kWgP][kWgColStride]
+  const int tid = threadIdx.x;
+  const int tpp = CO4 * (kWgKP / 8);         // threads per phase
+  const int phases = 256 / tpp;
+  const int ph = tid / tpp, r = tid % tpp, kg = r / CO4, c4 = r % CO4;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
+  const int fp = tid % kWgP, fq = tid / kWgP;  // im2col fill: pixel of the tile, quarter of the padded K (warp-uniform)
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long p0 = (long long)tile * kWgP;
+    // dY rows of the tile: one contiguous run of kWgP * Cout floats
+    for (int i = tid; i < kWgP * CO4; i += 256) {
+      const long long p = p0 + i / CO4;
+      const float4 v = p < pixels ? ld4(dy + p0 * Cout + (long long)i * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(dys + i * 4) = v;
+    }
+    {
+      const long long p = p0 + fp;
+      const bool live = p < pixels;
+      const int ow = (int)(p % g.OW), oh = (int)((p / g.OW) % g.OH), b = (int)(p / ((long long)g.OW * g.OH));
+      float* col = cols + fp * kWgColStride;
+      if (fq == 0) wg_fill_cols<KH, KW, CIN, 0>(col, x, g, b, oh, ow, live);
+      else if (fq == 1) wg_fill_cols<KH, KW, CIN, 1>(col, x, g, b, oh, ow, live);
+      else if (fq == 2) wg_fill_cols<KH, KW, CIN, 2>(col, x, g, b, oh, ow, live);
+      else wg_fill_cols<KH, KW, CIN, 3>(col, x, g, b, oh, ow, live);
+    }
+    __syncthreads();
+    if (ph < phases) {
+#pragma unroll 4
+      for (int p = ph; p < kWgP; p += phases) {
+        const float4 xa = *reinterpret_cast<const float4*>(cols + p * kWgColStride + kg * 8);
+        const float4 xb = *reinterpret_cast<const float4*>(cols + p * kWgColStride + kg * 8 + 4);
+        const float4 gv = *reinterpret_cast<const float4*>(dys + p * Cout + c4 * 4);
+        const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc[i][0] = fmaf(xv[i], gv.x, acc[i][0]); acc[i][1] = fmaf(xv[i], gv.y, acc[i][1]);
+          acc[i][2] = fmaf(xv[i], gv.z, acc[i][2]); acc[i][3] = fmaf(xv[i], gv.w, acc[i][3]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // the phases, in phase order: red[phase][k][Cout] reuses the tile buffers (phases * 32 * Cout floats <= the dY tile + im2col tile)
+  float* red = wg_sm;
+  if (ph < phases) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      *reinterpret_cast<float4*>(red + ((size_t)ph * kWgKP + kg * 8 + i) * Cout + c4 * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+  }
+  __syncthreads();
+  float* part = partial + (long long)blockIdx.x * K * Cout;
+  for (int i = tid; i < K * CO4; i += 256) {
+    const int k = i / CO4, cc = i % CO4;
+    float4 tot = *reinterpret_cast<const float4*>(red + (size_t)k * Cout + cc * 4);
+    for (int q = 1; q < phases; ++q) {
+      const float4 v = *reinterpret_cast<const float4*>(red + ((size_t)q * kWgKP + k) * Cout + cc * 4);
+      tot.x = __fadd_rn(tot.x, v.x); tot.y = __fadd_rn(tot.y, v.y); tot.z = __fadd_rn(tot.z, v.z); tot.w = __fadd_rn(tot.w, v.w);
+    }
+    st4(part + (size_t)k * Cout + cc * 4, tot);
+  }
+}
+template <int KH, int KW, int CIN>
+static bool launch_smallk_wgrad_tile(const float* x, const float* dy, float* dw, const ConvGeom& g, float* ws, size_t ws_floats, cudaStream_t s) {
+  const int K = KH * KW * CIN, CO4 = g.Cout / 4;
+  const int tpp = CO4 * (kWgKP / 8);
+  if (CO4 < 8 || (CO4 & (CO4 - 1)) || tpp > 256) return false;  // Cout = 32, 64, 128, 256
+  const int phases = 256 / tpp;
+  const size_t tile_floats = (size_t)kWgP * g.Cout + (size_t)kWgP * kWgColStride;
+  const size_t red_floats = (size_t)phases * kWgKP * g.Cout;
+  const size_t smem = std::max(tile_floats, red_floats) * sizeof(float);
+  if (smem > 200 * 1024) return false;
+  const long long pixels = (long long)g.N * g.OH * g.OW;
+  const int tiles = (int)((pixels + kWgP - 1) / kWgP);
+  int blocks = std::min(tiles, 3 * kNumSMs);
+  if ((size_t)blocks * K * g.Cout > ws_floats) blocks = (int)(ws_floats / ((size_t)K * g.Cout));
+  if (blocks < 1) return false;
+  static bool attr = false;
+  if (!attr) {
+    SB_CUDA(cudaFuncSetAttribute(conv_smallk_wgrad_tile_kernel<KH, KW, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  launch_k(conv_smallk_wgrad_tile_kernel<KH, KW, CIN>, blocks, 256, smem, s, x, dy, ws, g, pixels, tiles);
+  SB_LAUNCHED();
+  partial_reduce(ws, dw, K * g.Cout, blocks, s);
+  return true;
+}
+
 // filter shapes 3x3x1, 3x3x3, 5x5x1 (fully unrolled accumulators); ws must hold blocks*K*Cout floats
 bool conv_smallk_wgrad(const float* x, const float* dy, float* dw, const ConvGeom& g, float* ws, size_t ws_floats, cudaStream_t s) {
   const int K = g.KH * g.KW * g.Cin;
   const int C4 = g.Cout / 4;
   const int shape = g.KH * 100 + g.KW * 10 + g.Cin;
   if ((shape != 331 && shape != 333 && shape != 551) || C4 > 32 || (C4 & (C4 - 1))) return false;
+  {
+    const char* old = getenv("SB_SMALLK_WGRAD_REG");  // =1: the register-accumulator kernel for every shape (A/B)
+    if (!(old && old[0] == '1') && g.Cout >= 32) {
+      if (shape == 331 && launch_smallk_wgrad_tile<3, 3, 1>(x, dy, dw, g, ws, ws_floats, s)) return true;
+      if (shape == 333 && launch_smallk_wgrad_tile<3, 3, 3>(x, dy, dw, g, ws, ws_floats, s)) return true;
+      if (shape == 551 && launch_smallk_wgrad_tile<5, 5, 1>(x, dy, dw, g, ws, ws_floats, s)) return true;
+    }
+  }
   const long long pixels = (long long)g.N * g.OH * g.OW;
   const size_t smem = (size_t)8 * K * C4 * sizeof(float4);
   if (smem > 160 * 1024) return false;
@@ -1211,6 +1344,35 @@ __global__ void __launch_bounds__(32 * YG) partial_reduce_kernel(const float* __
     out[i] = t;
   }
 }
+// the same sums (same order per element, so the same bits) four elements per thread: the big filter gradients (n >= 16 K floats) are
+// bound by reading the partials, and 128-bit loads of 512 contiguous bytes per warp do that at several times the scalar kernel's rate
+template <int YG>
+__global__ void __launch_bounds__(32 * YG) partial_reduce4_kernel(const float* __restrict__ partial, float* __restrict__ out, int n4,
+                                                                 int parts, int early) {
+  pdl_prologue_trigger_if(early);
+  __shared__ float4 red[YG][33];
+  const int i = blockIdx.x * 32 + threadIdx.x, y = threadIdx.y;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < n4) {
+    const float4* p4 = reinterpret_cast<const float4*>(partial) + i;
+#pragma unroll 4
+    for (int c = y; c < parts; c += YG) {
+      const float4 v = __ldg(p4 + (size_t)c * n4);
+      acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y); acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
+    }
+  }
+  red[y][threadIdx.x] = acc;
+  __syncthreads();
+  if (y == 0 && i < n4) {
+    float4 t = red[0][threadIdx.x];
+#pragma unroll
+    for (int j = 1; j < YG; ++j) {
+      const float4 v = red[j][threadIdx.x];
+      t.x = __fadd_rn(t.x, v.x); t.y = __fadd_rn(t.y, v.y); t.z = __fadd_rn(t.z, v.z); t.w = __fadd_rn(t.w, v.w);
+    }
+    reinterpret_cast<float4*>(out)[i] = t;
+  }
+}
 // several reductions in ONE launch (the filter-gradient partials of different layers, all due just before the optimizer): block b
 // belongs to the segment whose block range contains it; each segment is summed exactly as partial_reduce_kernel<32> would
 __global__ void __launch_bounds__(32 * 32) partial_reduce_multi_kernel(ReduceBatch rb, int early) {
@@ -1248,6 +1410,13 @@ void partial_reduce_multi(ReduceBatch& rb, cudaStream_t s) {
 // part c goes to lane group c % YG (summed in ascending c inside the group), then the groups in order: a fixed order for a
 // given `parts`.  Many partials -> 32 groups so that no thread walks more than ~parts/32 dependent loads.
 void partial_reduce(const float* partial, float* out, int n, int parts, cudaStream_t s) {
+  if (n >= 16384 && n % 4 == 0 && (((uintptr_t)partial | (uintptr_t)out) & 15) == 0) {
+    const int n4 = n / 4;
+    if (parts > 48) launch_k(partial_reduce4_kernel<32>, (n4 + 31) / 32, dim3(32, 32), 0, s, partial, out, n4, parts, pdl_early_hint());
+    else launch_k(partial_reduce4_kernel<8>, (n4 + 31) / 32, dim3(32, 8), 0, s, partial, out, n4, parts, pdl_early_hint());
+    SB_LAUNCHED();
+    return;
+  }
   if (parts > 48) launch_k(partial_reduce_kernel<32>, (n + 31) / 32, dim3(32, 32), 0, s, partial, out, n, parts, pdl_early_hint());
   else launch_k(partial_reduce_kernel<8>, (n + 31) / 32, dim3(32, 8), 0, s, partial, out, n, parts, pdl_early_hint());
   SB_LAUNCHED();

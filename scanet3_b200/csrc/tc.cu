@@ -922,6 +922,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
 struct WgradHaloParams {
   int n_chunks, chunks_per_img;
   int BH, P, KH, KW, Cin, Cout, OH;
+  int Ns;               // output channels per CTA (the MMA N): blockIdx.y picks the slice [blockIdx.y * Ns, + Ns); KH * Cin/32 * Ns <= 512 TMEM columns
   int ox, oy;           // X box origin relative to the chunk's first output pixel: (-PL, -PT)
   int dy_tile_bytes;    // one 32-co slice of the dY chunk (multiple of 1024)
   int x_tile_bytes;     // one 32-ci slice of the X halo chunk, incl. the KW-1 zeroed tail rows (multiple of 1024)
@@ -938,11 +939,12 @@ __global__ void __launch_bounds__(kWgradThreads, 1)
 conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, const WgradHaloParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 64 : nullptr;
+  long long* dbg = p.dbg && blockIdx.y == 0 ? p.dbg + (size_t)blockIdx.x * 64 : nullptr;
 #define WG_T(slot) do { if (dbg) dbg[slot] = clock64(); } while (0)
   if (threadIdx.x == 0) WG_T(0);
   const int KH = TKH ? TKH : p.KH;
-  const int co_slices = p.Cout / 32, ci_slices = TCIS ? TCIS : p.Cin / 32;
+  const int Ns = p.Ns, co0 = (int)blockIdx.y * Ns;
+  const int co_slices = Ns / 32, ci_slices = TCIS ? TCIS : p.Cin / 32;
   const int a_bytes = ci_slices * p.x_tile_bytes, b_bytes = co_slices * p.dy_tile_bytes;
   const int stage_bytes = a_bytes + b_bytes;
   uint64_t* full_bar = (uint64_t*)(smem + (size_t)p.stages * stage_bytes);
@@ -952,7 +954,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const int n_acc = KH * ci_slices;
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < n_acc * p.Cout) tmem_cols <<= 1;
+  while ((int)tmem_cols < n_acc * Ns) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_dy);
@@ -996,14 +998,14 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
         } else {
           mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(ci_slices * p.x_box_bytes + co_slices * p.dy_box_bytes));
           for (int j = 0; j < ci_slices; ++j) tma_load_4d(sa + (size_t)j * p.x_tile_bytes, &map_x, &full_bar[stage], j * 32, p.ox, h0 + p.oy, img);
-          for (int j = 0; j < co_slices; ++j) tma_load_4d(sb + (size_t)j * p.dy_tile_bytes, &map_dy, &full_bar[stage], j * 32, 0, h0, img);
+          for (int j = 0; j < co_slices; ++j) tma_load_4d(sb + (size_t)j * p.dy_tile_bytes, &map_dy, &full_bar[stage], co0 + j * 32, 0, h0, img);
         }
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (has_work) {  // warp-uniform loop, one elected lane issues
-      const uint32_t idesc = idesc_tf32(128, p.Cout, 1, 1);
+      const uint32_t idesc = idesc_tf32(128, Ns, 1, 1);
       // MN-major SW128 (32-byte atoms): 8 K-rows (1024 B) per instruction; A: 32-element M groups 128 B apart (the KW taps);
       // B: 32-element N groups one dY slice apart
       const uint64_t a_d = smem_desc(0, 128, 512, 1), b_d = smem_desc(0, (uint32_t)p.dy_tile_bytes, 512, 1);
@@ -1030,7 +1032,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
           for (int kh = 0; kh < KH; ++kh, at_kh += kh_step) {
             uint32_t at = at_kh;
 #pragma unroll
-            for (int j = 0; j < ci_slices; ++j, at += x_tile, d_tmem += p.Cout)
+            for (int j = 0; j < ci_slices; ++j, at += x_tile, d_tmem += Ns)
               umma_tf32_elect(d_tmem, ((uint64_t)a_hi << 32) | at, ((uint64_t)b_hi << 32) | (sb + ks * 64), idesc, accumulate);
           }
           accumulate = 1;
@@ -1053,17 +1055,17 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_
     // This warp's 32 rows (one kw, 32 ci) of accumulator a are ONE contiguous 32 x Cout block of the partial.  Each lane holds a
     // row: transpose through a padded scratch (the pipeline stages are idle once done_bar fired; row pitch Cout + 4 floats keeps
     // both the 128-bit row writes and the 128-bit line reads conflict-free) and store whole 512-byte pieces.
-    const int pitch = p.Cout + 4;
+    const int pitch = Ns + 4;
     const uint32_t scratch = smem_u32(smem) + (uint32_t)(sub * 32 * pitch * 4);
-    const int f4_per_row = p.Cout / 4;            // Cout % 32 == 0
+    const int f4_per_row = Ns / 4;                // Ns % 32 == 0
     const int rows_per_it = 32 / f4_per_row > 0 ? 32 / f4_per_row : 1;
     for (int a = 0; a < n_acc; ++a) {
       const int kh = a / ci_slices, j = a - kh * ci_slices;
-      float* blk = part + ((size_t)((kh * p.KW + sub) * p.Cin + j * 32)) * p.Cout;
-      for (int c0 = 0; c0 < p.Cout; c0 += 32) {
+      float* blk = part + ((size_t)((kh * p.KW + sub) * p.Cin + j * 32)) * p.Cout + co0;
+      for (int c0 = 0; c0 < Ns; c0 += 32) {
         float v[32];
         if (has_work) {
-          tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(a * p.Cout + c0), v);
+          tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(a * Ns + c0), v);
           tmem_ld_wait();
         } else {
 #pragma unroll
@@ -1150,7 +1152,7 @@ struct ConvTcPlan {
   WgradHaloParams hwg{};
   CUtensorMap map_dy_hwg, map_x_hwg;
   bool halo_wg = false;
-  int hwg_smem = 0, hwg_grid = 0;
+  int hwg_smem = 0, hwg_grid = 0, hwg_slices = 1;
   int fwd_smem = 0, dg_smem = 0, wg_smem = 0;
   int fwd_grid = 0, dg_grid = 0, wg_grid = 0;
   float* wg_partial = nullptr;
@@ -1426,7 +1428,14 @@ void tc_plan_layers(sb_engine* e) {
       const bool on = !(h && h[0] == '0') && !x3;
       WgradHaloParams& p = P->hwg;
       const int n_acc = g.KH * (g.Cin / 32);
-      if (on && P->wg_ok && g.KW <= 4 && n_acc * g.Cout <= 512) {
+      // output-channel slices (gridDim.y): the widest Ns (multiple of 32 dividing Cout) whose accumulators fit TMEM; below 64 the MMA
+      // is bound by its operand fetch and X would be re-read once per slice, so the per-tap kernel keeps those shapes
+      int Ns = 0;
+      for (int c = g.Cout; c >= 32; c -= 32)
+        if (g.Cout % c == 0 && n_acc * c <= 512) { Ns = c; break; }
+      const int n_slices = Ns ? g.Cout / Ns : 0;
+      const int slice_ctas = Ns ? std::max(1, kNumSMs / n_slices) : 0;
+      if (on && P->wg_ok && g.KW <= 4 && Ns && (Ns == g.Cout || Ns >= 64)) {
         // pitch P >= OW + KW - 1 and rows per chunk BH: BH*P % 8 == 0, boxes <= 256 rows; minimise rounds x k-steps per chunk
         double best = 1e30;
         int bP = 0, bBH = 0;
@@ -1434,19 +1443,19 @@ void tc_plan_layers(sb_engine* e) {
           for (int BH = 1; BH <= g.OH; ++BH) {
             if ((BH * Pc) % 8 || (BH + g.KH - 1) > 256) continue;
             const int rows_x = (BH + g.KH - 1) * Pc + g.KW - 1;
-            const int stage = (g.Cin / 32) * ((rows_x + 7) / 8) * 1024 + (g.Cout / 32) * BH * Pc * 128;
+            const int stage = (g.Cin / 32) * ((rows_x + 7) / 8) * 1024 + (Ns / 32) * BH * Pc * 128;
             if (2 * stage + 4096 > dev_smem) continue;
-            if (4 * 32 * (g.Cout + 4) * 4 > 2 * stage) continue;  // the epilogue's transpose scratch reuses the idle stages
+            if (4 * 32 * (Ns + 4) * 4 > 2 * stage) continue;  // the epilogue's transpose scratch reuses the idle stages
             const long long chunks = (long long)g.N * ((g.OH + BH - 1) / BH);
             // cycles per CTA: rounds x max(MMA issue, TMA fill at ~25 B/cycle/SM with every SM pulling) + the first fill
             // (MMA rates and the fill rate: profiles/r1_notes.md items 8)
-            const double mma = g.Cout <= 32 ? 40 : g.Cout <= 64 ? 48 : g.Cout / 2;
+            const double mma = Ns <= 32 ? 40 : Ns <= 64 ? 48 : Ns / 2;
             const double fill = stage / 25.0;
-            const double cost = (double)((chunks + kNumSMs - 1) / kNumSMs) * std::max((BH * Pc / 8) * n_acc * mma + 150.0, fill) + fill;
+            const double cost = (double)((chunks + slice_ctas - 1) / slice_ctas) * std::max((BH * Pc / 8) * n_acc * mma + 150.0, fill) + fill;
             if (cost < best) { best = cost; bP = Pc; bBH = BH; }
           }
         if (bP) {
-          p.BH = bBH; p.P = bP; p.KH = g.KH; p.KW = g.KW; p.Cin = g.Cin; p.Cout = g.Cout; p.OH = g.OH;
+          p.BH = bBH; p.P = bP; p.KH = g.KH; p.KW = g.KW; p.Cin = g.Cin; p.Cout = g.Cout; p.OH = g.OH; p.Ns = Ns;
           p.ox = -g.PL; p.oy = -g.PT;
           p.chunks_per_img = (g.OH + p.BH - 1) / p.BH;
           p.n_chunks = g.N * p.chunks_per_img;
@@ -1454,9 +1463,10 @@ void tc_plan_layers(sb_engine* e) {
           p.dy_tile_bytes = p.dy_box_bytes;  // BH*P % 8 == 0 => multiple of 1024
           p.x_box_bytes = (p.BH + g.KH - 1) * p.P * 128;
           p.x_tile_bytes = (((p.BH + g.KH - 1) * p.P + g.KW - 1 + 7) / 8) * 1024;
-          const int stage_bytes = (g.Cin / 32) * p.x_tile_bytes + (g.Cout / 32) * p.dy_tile_bytes;
+          const int stage_bytes = (g.Cin / 32) * p.x_tile_bytes + (Ns / 32) * p.dy_tile_bytes;
           p.stages = std::max(2, std::min(6, (dev_smem - 4096) / stage_bytes));
-          P->hwg_grid = (int)std::min<long long>(p.n_chunks, kNumSMs);
+          P->hwg_grid = (int)std::min<long long>(p.n_chunks, slice_ctas);
+          P->hwg_slices = n_slices;
           P->hwg_smem = p.stages * stage_bytes + 16 * (2 * p.stages + 2) + 16 + 1024;
           if (P->hwg_smem <= dev_smem) {  // the partial buffer is sized for min(n_chunks, SMs) CTAs
             p.partial = P->wg_partial;
@@ -1772,7 +1782,7 @@ bool tc_conv_wgrad(sb_engine* e, LayerPlan& L, int, cudaStream_t side, ReduceBat
     const int cis = P->hwg.Cin / 32;
     auto kern = P->hwg.KH == 3 && cis == 1 ? conv_wgrad_halo_kernel<3, 1>
                 : P->hwg.KH == 3 && cis == 2 ? conv_wgrad_halo_kernel<3, 2> : conv_wgrad_halo_kernel<0, 0>;
-    launch_k(kern, P->hwg_grid, kWgradThreads, P->hwg_smem, st, P->map_dy_hwg, P->map_x_hwg, P->hwg);
+    launch_k(kern, dim3(P->hwg_grid, P->hwg_slices), kWgradThreads, P->hwg_smem, st, P->map_dy_hwg, P->map_x_hwg, P->hwg);
     SB_LAUNCHED();
     if (defer && defer->add(P->wg_partial, e->grads + e->params[L.p_w].offset, n, P->hwg_grid)) return true;  // summed before the optimizer
     partial_reduce(P->wg_partial, e->grads + e->params[L.p_w].offset, n, P->hwg_grid, st);
