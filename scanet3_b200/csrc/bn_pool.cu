@@ -123,12 +123,12 @@ __global__ void __launch_bounds__(32 * kBnSegments) bn_stats_finalize_kernel(con
   const bool ok = c < C;
   const float frows = (float)rows;
   float a = 0.f;
-  if (ok)
-    for (int j = seg; j < chunks; j += kBnSegments) {
-      const long long ra = (long long)j * rows_per_chunk;
-      const float nb = (float)(ra + rows_per_chunk < rows ? rows_per_chunk : rows - ra);
-      a = __fadd_rn(a, __fmul_rn(nb, partial[((long long)j * 2 + 0) * C + c]));
-    }
+  const float n_full = (float)rows_per_chunk, n_last = (float)(rows - (long long)(chunks - 1) * rows_per_chunk);
+  if (ok) {
+#pragma unroll 4
+    for (int j = seg; j < chunks; j += kBnSegments)
+      a = __fadd_rn(a, __fmul_rn(j == chunks - 1 ? n_last : n_full, __ldg(partial + ((long long)j * 2 + 0) * C + c)));
+  }
   red[seg][threadIdx.x] = a;
   __syncthreads();
   if (seg == 0) {
@@ -138,13 +138,13 @@ __global__ void __launch_bounds__(32 * kBnSegments) bn_stats_finalize_kernel(con
   __syncthreads();
   const float m = mean_s[threadIdx.x];
   float q = 0.f;
-  if (ok)
+  if (ok) {
+#pragma unroll 4
     for (int j = seg; j < chunks; j += kBnSegments) {
-      const long long ra = (long long)j * rows_per_chunk;
-      const float nb = (float)(ra + rows_per_chunk < rows ? rows_per_chunk : rows - ra);
-      const float d = __fsub_rn(partial[((long long)j * 2 + 0) * C + c], m);
-      q = __fadd_rn(q, __fadd_rn(partial[((long long)j * 2 + 1) * C + c], __fmul_rn(nb, __fmul_rn(d, d))));
+      const float d = __fsub_rn(__ldg(partial + ((long long)j * 2 + 0) * C + c), m);
+      q = __fadd_rn(q, __fadd_rn(__ldg(partial + ((long long)j * 2 + 1) * C + c), __fmul_rn(j == chunks - 1 ? n_last : n_full, __fmul_rn(d, d))));
     }
+  }
   __syncthreads();
   red[seg][threadIdx.x] = q;
   __syncthreads();
@@ -305,11 +305,13 @@ __global__ void __launch_bounds__(32 * kBnSegments) bn_bwd_sums_kernel(const flo
   __shared__ float sa[kBnSegments][33], sc[kBnSegments][33];
   const int c = blockIdx.x * 32 + threadIdx.x, seg = threadIdx.y;
   float a0 = 0.f, a1 = 0.f;
-  if (c < C)
+  if (c < C) {
+#pragma unroll 4
     for (int j = seg; j < chunks; j += kBnSegments) {
-      a0 = __fadd_rn(a0, partial[((long long)j * 2 + 0) * C + c]);
-      a1 = __fadd_rn(a1, partial[((long long)j * 2 + 1) * C + c]);
+      a0 = __fadd_rn(a0, __ldg(partial + ((long long)j * 2 + 0) * C + c));
+      a1 = __fadd_rn(a1, __ldg(partial + ((long long)j * 2 + 1) * C + c));
     }
+  }
   sa[seg][threadIdx.x] = a0;
   sc[seg][threadIdx.x] = a1;
   __syncthreads();

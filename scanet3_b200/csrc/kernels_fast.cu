@@ -850,8 +850,8 @@ __global__ void __launch_bounds__(256) conv_smallk_fwd_tile_kernel(const float* 
   extern __shared__ __align__(16) float swt[];  // filter [K][Cout]
   for (int i = threadIdx.x; i < K * g.Cout; i += blockDim.x) swt[i] = w[i];
   __syncthreads();
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_threads) return;
+  // persistent: the filter is staged once per block, the items advance by the grid's thread count
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_threads; i += (long long)gridDim.x * blockDim.x) {
   const int c4 = (int)(i % C4);
   long long t = i / C4;
   const int seg = (int)(t % segs); t /= segs;
@@ -895,6 +895,7 @@ __global__ void __launch_bounds__(256) conv_smallk_fwd_tile_kernel(const float* 
     if (relu) { o.x = fmaxf(thr, o.x); o.y = fmaxf(thr, o.y); o.z = fmaxf(thr, o.z); o.w = fmaxf(thr, o.w); }
     st4(yo + (long long)p * g.Cout, o);
   }
+  }
 }
 template <int KH, int KW, int CIN>
 static void launch_smallk_tile(const float* x, const float* w, float* y, const ConvGeom& g, int relu, float thr, cudaStream_t s) {
@@ -902,7 +903,8 @@ static void launch_smallk_tile(const float* x, const float* w, float* y, const C
   const int segs = (g.OW + PW - 1) / PW;
   const long long nt = (long long)g.N * g.OH * segs * (g.Cout / 4);
   const size_t smem = (size_t)KH * KW * CIN * g.Cout * sizeof(float);
-  launch_k(conv_smallk_fwd_tile_kernel<KH, KW, CIN, PW>, (int)((nt + 255) / 256), 256, smem, s, x, w, y, g, relu, thr, segs, nt);
+  const int blocks = (int)std::min<long long>((nt + 255) / 256, (long long)kNumSMs * 8);
+  launch_k(conv_smallk_fwd_tile_kernel<KH, KW, CIN, PW>, blocks, 256, smem, s, x, w, y, g, relu, thr, segs, nt);
   SB_LAUNCHED();
 }
 // Small-K conv (stride 1) >> [ReLU] >> max-pool 2x2 stride 1 VALID in ONE pass: a thread owns 4 channels x PW pool outputs of pool
@@ -1161,33 +1163,37 @@ void partial_reduce(const float* partial, float* out, int n, int parts, cudaStre
 constexpr int kWgP = 64;        // pixels per tile
 constexpr int kWgKP = 32;       // K padded
 constexpr int kWgColStride = 36;  // floats per im2col row: 16-byte aligned rows, 4-way (not 32-way) conflicts on the scalar fill
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool live) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int bytes = live ? 16 : 0;  // 0: the 16 bytes are zero-filled, nothing is read
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 template <int KH, int KW, int CIN, int Q>
-__device__ __forceinline__ void wg_fill_cols(float* __restrict__ col, const float* __restrict__ x, const ConvGeom& g, int b, int oh, int ow, bool live) {
+__device__ __forceinline__ void wg_load_cols(float (&v)[8], const float* __restrict__ x, const ConvGeom& g, int b, int oh, int ow, bool live) {
   constexpr int K = KH * KW * CIN;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    constexpr int dummy = 0;
-    (void)dummy;
     const int k = Q * 8 + j;
-    float v = 0.f;
+    v[j] = 0.f;
     if (k < K) {
       const int tap = k / CIN, ci = k % CIN, a = tap / KW, bb = tap % KW;
       const int ih = oh * g.SH + a - g.PT, iw = ow * g.SW + bb - g.PL;
-      if (live && ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) v = __ldg(x + (((long long)b * g.H + ih) * g.W + iw) * CIN + ci);
+      if (live && ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) v[j] = __ldg(x + (((long long)b * g.H + ih) * g.W + iw) * CIN + ci);
     }
-    col[k] = v;
   }
 }
+// Two tile buffers: while the block accumulates tile t, the dY rows of tile t+1 arrive through cp.async and its im2col values sit in
+// registers (loaded before the FMAs, stored after them) -- one barrier per tile, no exposed global latency.
 template <int KH, int KW, int CIN>
-__global__ void __launch_bounds__(256, 3) conv_smallk_wgrad_tile_kernel(const float* __restrict__ x, const float* __restrict__ dy,
-                                                                        float* __restrict__ partial, ConvGeom g, long long pixels, int tiles) {
+__global__ void __launch_bounds__(256, 2) conv_smallk_wgrad_tile_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                        float* __restrict__ partial, ConvGeom g, long long pixels, int tiles,
+                                                                        int buf_floats) {
   pdl_prologue();
   constexpr int K = KH * KW * CIN;
   static_assert(K <= kWgKP, "K must fit the padded im2col row");
   extern __shared__ __align__(16) float wg_sm[];
   const int Cout = g.Cout, CO4 = Cout >> 2;
-  float* dys = wg_sm;                        // [kWgP][Cout]
-  float* cols = wg_sm + kWgP * Cout;         // [kWgP][kWgColStride]
   const int tid = threadIdx.x;
   const int tpp = CO4 * (kWgKP / 8);         // threads per phase
   const int phases = 256 / tpp;
@@ -1198,25 +1204,47 @@ __global__ void __launch_bounds__(256, 3) conv_smallk_wgrad_tile_kernel(const fl
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
   const int fp = tid % kWgP, fq = tid / kWgP;  // im2col fill: pixel of the tile, quarter of the padded K (warp-uniform)
-  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+  // buffer b: dY rows [kWgP][Cout] then im2col rows [kWgP][kWgColStride]
+  auto issue_dy = [&](int tile, float* dys) {
     const long long p0 = (long long)tile * kWgP;
-    // dY rows of the tile: one contiguous run of kWgP * Cout floats
     for (int i = tid; i < kWgP * CO4; i += 256) {
-      const long long p = p0 + i / CO4;
-      const float4 v = p < pixels ? ld4(dy + p0 * Cout + (long long)i * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(dys + i * 4) = v;
+      const bool live = p0 + i / CO4 < pixels;
+      cp_async16(dys + i * 4, dy + (live ? p0 * Cout + (long long)i * 4 : 0), live);
     }
-    {
-      const long long p = p0 + fp;
-      const bool live = p < pixels;
-      const int ow = (int)(p % g.OW), oh = (int)((p / g.OW) % g.OH), b = (int)(p / ((long long)g.OW * g.OH));
-      float* col = cols + fp * kWgColStride;
-      if (fq == 0) wg_fill_cols<KH, KW, CIN, 0>(col, x, g, b, oh, ow, live);
-      else if (fq == 1) wg_fill_cols<KH, KW, CIN, 1>(col, x, g, b, oh, ow, live);
-      else if (fq == 2) wg_fill_cols<KH, KW, CIN, 2>(col, x, g, b, oh, ow, live);
-      else wg_fill_cols<KH, KW, CIN, 3>(col, x, g, b, oh, ow, live);
+  };
+  auto load_cols = [&](int tile, float (&v)[8]) {
+    const long long p = (long long)tile * kWgP + fp;
+    const bool live = p < pixels;
+    const int ow = (int)(p % g.OW), oh = (int)((p / g.OW) % g.OH), b = (int)(p / ((long long)g.OW * g.OH));
+    if (fq == 0) wg_load_cols<KH, KW, CIN, 0>(v, x, g, b, oh, ow, live);
+    else if (fq == 1) wg_load_cols<KH, KW, CIN, 1>(v, x, g, b, oh, ow, live);
+    else if (fq == 2) wg_load_cols<KH, KW, CIN, 2>(v, x, g, b, oh, ow, live);
+    else wg_load_cols<KH, KW, CIN, 3>(v, x, g, b, oh, ow, live);
+  };
+  auto store_cols = [&](float* cols, const float (&v)[8]) {
+    float* col = cols + fp * kWgColStride + fq * 8;
+    *reinterpret_cast<float4*>(col) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(col + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  };
+  int tile = blockIdx.x, cur = 0;
+  if (tile < tiles) {
+    float v[8];
+    issue_dy(tile, wg_sm);
+    load_cols(tile, v);
+    store_cols(wg_sm + kWgP * Cout, v);
+  }
+  for (; tile < tiles; tile += gridDim.x, cur ^= 1) {
+    float* dys = wg_sm + (size_t)cur * buf_floats;
+    float* cols = dys + kWgP * Cout;
+    float* ndys = wg_sm + (size_t)(cur ^ 1) * buf_floats;
+    cp_async_wait_all();
+    __syncthreads();  // tile `cur` is complete; everyone has left the other buffer (read during the previous iteration)
+    const int next = tile + gridDim.x;
+    float v[8];
+    if (next < tiles) {
+      issue_dy(next, ndys);
+      load_cols(next, v);
     }
-    __syncthreads();
     if (ph < phases) {
 #pragma unroll 4
       for (int p = ph; p < kWgP; p += phases) {
@@ -1231,9 +1259,11 @@ __global__ void __launch_bounds__(256, 3) conv_smallk_wgrad_tile_kernel(const fl
         }
       }
     }
-    __syncthreads();
+    if (next < tiles) store_cols(ndys + kWgP * Cout, v);
   }
-  // the phases, in phase order: red[phase][k][Cout] reuses the tile buffers (phases * 32 * Cout floats <= the dY tile + im2col tile)
+  cp_async_wait_all();
+  __syncthreads();
+  // the phases, in phase order: red[phase][k][Cout] reuses the tile buffers
   float* red = wg_sm;
   if (ph < phases) {
 #pragma unroll
@@ -1260,11 +1290,11 @@ static bool launch_smallk_wgrad_tile(const float* x, const float* dy, float* dw,
   const int phases = 256 / tpp;
   const size_t tile_floats = (size_t)kWgP * g.Cout + (size_t)kWgP * kWgColStride;
   const size_t red_floats = (size_t)phases * kWgKP * g.Cout;
-  const size_t smem = std::max(tile_floats, red_floats) * sizeof(float);
+  const size_t smem = std::max(2 * tile_floats, red_floats) * sizeof(float);
   if (smem > 200 * 1024) return false;
   const long long pixels = (long long)g.N * g.OH * g.OW;
   const int tiles = (int)((pixels + kWgP - 1) / kWgP);
-  int blocks = std::min(tiles, 3 * kNumSMs);
+  int blocks = std::min(tiles, 2 * kNumSMs);
   if ((size_t)blocks * K * g.Cout > ws_floats) blocks = (int)(ws_floats / ((size_t)K * g.Cout));
   if (blocks < 1) return false;
   static bool attr = false;
@@ -1272,7 +1302,7 @@ static bool launch_smallk_wgrad_tile(const float* x, const float* dy, float* dw,
     SB_CUDA(cudaFuncSetAttribute(conv_smallk_wgrad_tile_kernel<KH, KW, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
-  launch_k(conv_smallk_wgrad_tile_kernel<KH, KW, CIN>, blocks, 256, smem, s, x, dy, ws, g, pixels, tiles);
+  launch_k(conv_smallk_wgrad_tile_kernel<KH, KW, CIN>, blocks, 256, smem, s, x, dy, ws, g, pixels, tiles, (int)tile_floats);
   SB_LAUNCHED();
   partial_reduce(ws, dw, K * g.Cout, blocks, s);
   return true;

@@ -87,6 +87,10 @@ struct IgemmParams {
   int ldc, n0;        // output row pitch (all channels) and the first output channel of this launch
   int pt, pl;         // padding before (top, left) of the source grid: taps read (h + sign*kh - pt, w + sign*kw - pl)
   int x3;             // 3xTF32: converter warps write lo = x - tf32(x) tiles behind the stage's [A | B]; D += A_hi.B_lo + A_lo.B_hi + A_hi.B_hi
+  // Small grids (Hg*Wg <= 64): a tile is `ipt` whole images (BH == Hg; the TMA box spans ipt images), so the M = 128 rows of the MMA
+  // are filled instead of holding one 4x4 or 6x6 image.  nsplit > 1 (fprop): work unit = (tile, slice of N output channels), N is the
+  // slice width -- more CTAs busy when there are few tiles, and every CTA streams only its slice of the filter.
+  int ipt, nsplit, n_img;
 };
 
 constexpr int kIgemmThreads = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..5: epilogue
@@ -124,8 +128,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // shfl: provably warp-uniform
-  const int a_box_bytes = p.BH * p.Wg * 128;
+  const int a_box_bytes = p.BH * p.Wg * 128 * p.ipt;
   const int kblocks = p.KH * p.KW * p.kchunks;
+  const int n_units = p.n_tiles * p.nsplit;  // unit = tile * nsplit + slice: the slices of a tile run back to back (A stays in L2)
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < 2 * p.N) tmem_cols <<= 1;
 
@@ -156,7 +161,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int t = threadIdx.x - 192;
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x)
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x)
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         uint8_t* st = smem + (size_t)stage * stage_bytes;
@@ -171,8 +176,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const int img = tile / p.tiles_per_img, h0 = (tile % p.tiles_per_img) * p.BH;
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int tile = unit / p.nsplit, n0 = p.n0 + (unit - tile * p.nsplit) * p.N;
+        const int img = p.ipt > 1 ? tile * p.ipt : tile / p.tiles_per_img, h0 = p.ipt > 1 ? 0 : (tile % p.tiles_per_img) * p.BH;
         int tap = 0;
         for (int kh = 0; kh < p.KH; ++kh)
           for (int kw = 0; kw < p.KW; ++kw, ++tap)
@@ -184,9 +190,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               tma_load_4d(sa, &map_a, &full_bar[stage], kc * 32, p.sign * kw - p.pl, h0 + p.sign * kh - p.pt, img);
               if (p.b_mn_major) {
                 for (int j = 0; j < p.N / 32; ++j)
-                  tma_load_2d(sb + j * 4096, &map_b, &full_bar[stage], p.n0 + j * 32, tap * p.b_rows_per_tap + kc * 32);
+                  tma_load_2d(sb + j * 4096, &map_b, &full_bar[stage], n0 + j * 32, tap * p.b_rows_per_tap + kc * 32);
               } else {
-                tma_load_2d(sb, &map_b, &full_bar[stage], kc * 32, tap * p.b_rows_per_tap + p.n0);
+                tma_load_2d(sb, &map_b, &full_bar[stage], kc * 32, tap * p.b_rows_per_tap + n0);
               }
               if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
@@ -203,7 +209,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.N);
@@ -243,12 +249,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int row = sub * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      const int img = tile / p.tiles_per_img, h0 = (tile % p.tiles_per_img) * p.BH;
-      const int rows_valid = min(p.BH, p.Hg - h0) * p.Wg;
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+      const int tile = unit / p.nsplit, n0 = p.n0 + (unit - tile * p.nsplit) * p.N;
+      const int img = p.ipt > 1 ? tile * p.ipt : tile / p.tiles_per_img, h0 = p.ipt > 1 ? 0 : (tile % p.tiles_per_img) * p.BH;
+      const int rows_valid = p.ipt > 1 ? min(p.ipt, p.n_img - img) * p.Hg * p.Wg : min(p.BH, p.Hg - h0) * p.Wg;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      float* orow = p.out + ((size_t)(img * p.Hg + h0) * p.Wg + row) * p.ldc + p.n0;
+      float* orow = p.out + ((size_t)(img * p.Hg + h0) * p.Wg + row) * p.ldc + n0;
       for (int c0 = 0; c0 < p.N; c0 += 32) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * p.N + c0), v);
@@ -1238,6 +1245,32 @@ static bool plan_halo(HaloParams& p, CUtensorMap* map, CUtensorMap* map_out, con
   return true;
 }
 
+// tiles of whole images when an image fills less than half of the MMA's 128 rows
+static void igemm_small_grid(IgemmParams& p, int n_img) {
+  p.n_img = n_img;
+  p.ipt = 1;
+  const int px = p.Hg * p.Wg;
+  if (p.BH == p.Hg && px <= 64) {
+    p.ipt = std::max(1, std::min(128 / px, n_img));
+    p.n_tiles = (n_img + p.ipt - 1) / p.ipt;
+  }
+}
+// N slices per tile (fprop): the cheaper of {1, 2, 4} under  max(per-CTA time, aggregate L2 -> shared-memory time), with a CTA pulling
+// ~55 B/cycle, the L2 delivering ~3400 B/cycle to all SMs, and an M = 128 MMA of K = 8 taking max(N/2, 40) cycles (profiles/r1_notes.md item 8)
+static int igemm_pick_nsplit(int n_tiles, int kblocks, int a_box_bytes, int n_full) {
+  int best = 1;
+  double best_cost = 1e30;
+  for (int ns = 1; ns <= 4; ns *= 2) {
+    if (n_full % (32 * ns) || n_full / ns < 64) break;
+    const int n = n_full / ns;
+    const double units = (double)n_tiles * ns, rounds = std::ceil(units / kNumSMs);
+    const double bytes = (double)kblocks * (a_box_bytes + n * 128.0);
+    const double mma = kblocks * 4.0 * std::max(n / 2.0, 40.0);
+    const double cost = std::max(rounds * std::max(bytes / 55.0, mma), units * bytes / 3400.0);
+    if (cost < best_cost * 0.95) { best_cost = cost; best = ns; }
+  }
+  return best;
+}
 static int igemm_smem(const IgemmParams& p) { return p.stages * (p.x3 ? 2 : 1) * (kATileBytes + p.N * 128) + 16 * (2 * p.stages + 4) + 16 + 1024; }
 
 void tc_plan_layers(sb_engine* e) {
@@ -1312,7 +1345,10 @@ void tc_plan_layers(sb_engine* e) {
       p.Hg = g.OH; p.Wg = g.OW; p.BH = std::max(1, std::min(128 / g.OW, g.OH));
       p.tiles_per_img = (g.OH + p.BH - 1) / p.BH;
       p.n_tiles = g.N * p.tiles_per_img;
+      igemm_small_grid(p, g.N);
       p.KH = g.KH; p.KW = g.KW; p.kchunks = g.Cin / 32; p.sign = +1; p.N = g.Cout; p.b_mn_major = 1;
+      p.nsplit = igemm_pick_nsplit(p.n_tiles, taps * p.kchunks, p.BH * p.Wg * 128 * p.ipt, g.Cout);
+      p.N = g.Cout / p.nsplit;
       p.b_rows_per_tap = g.Cin;
       p.relu = P->relu_fused ? 1 : 0;
       p.thr = P->relu_fused ? e->L[li + 1].d.relu_threshold : 0.f;
@@ -1320,13 +1356,13 @@ void tc_plan_layers(sb_engine* e) {
       p.ldc = g.Cout; p.n0 = 0; p.pt = g.PT; p.pl = g.PL; p.x3 = x3;
       p.stages = std::max(2, std::min(8, (dev_smem - 2048) / ((x3 ? 2 : 1) * (kATileBytes + p.N * 128))));
       uint64_t xd[4] = {(uint64_t)g.Cin, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.N};
-      uint32_t xb[4] = {32, (uint32_t)p.Wg, (uint32_t)p.BH, 1};
+      uint32_t xb[4] = {32, (uint32_t)p.Wg, (uint32_t)p.BH, (uint32_t)p.ipt};
       P->map_x_fwd = make_map(x, 4, xd, xb);
       uint64_t wd[2] = {(uint64_t)g.Cout, (uint64_t)taps * g.Cin};
       uint32_t wb[2] = {32, 32};
       P->map_w_fwd = make_map(w, 2, wd, wb, true);
       P->fwd_smem = igemm_smem(p);
-      P->fwd_grid = std::min(p.n_tiles, kNumSMs);
+      P->fwd_grid = std::min(p.n_tiles * p.nsplit, kNumSMs);
       const char* h = getenv("SB_TC_HALO");
       const bool halo_on = !(h && h[0] == '0') && !x3;
       if (halo_on && plan_halo(P->hfwd, &P->map_x_h, &P->map_y_out, x, g.Cin, g.W, g.H, g.N, g.OH, g.OW, g.KH, g.KW, g.Cout, 1, g.Cin, 0, -g.PL,
@@ -1343,6 +1379,8 @@ void tc_plan_layers(sb_engine* e) {
       p.Hg = g.H; p.Wg = g.W; p.BH = std::max(1, std::min(128 / g.W, g.H));
       p.tiles_per_img = (g.H + p.BH - 1) / p.BH;
       p.n_tiles = g.N * p.tiles_per_img;
+      igemm_small_grid(p, g.N);
+      p.nsplit = 1;
       p.KH = g.KH; p.KW = g.KW; p.kchunks = g.Cout / 32; p.sign = -1; p.N = g.Cin; p.b_mn_major = 0;
       p.b_rows_per_tap = g.Cin;
       p.relu = 0; p.thr = 0.f;
@@ -1350,7 +1388,7 @@ void tc_plan_layers(sb_engine* e) {
       p.ldc = g.Cin; p.n0 = 0; p.pt = -g.PT; p.pl = -g.PL; p.x3 = x3;
       p.stages = std::max(2, std::min(8, (dev_smem - 2048) / ((x3 ? 2 : 1) * (kATileBytes + p.N * 128))));
       uint64_t yd[4] = {(uint64_t)g.Cout, (uint64_t)g.OW, (uint64_t)g.OH, (uint64_t)g.N};
-      uint32_t yb[4] = {32, (uint32_t)p.Wg, (uint32_t)p.BH, 1};
+      uint32_t yb[4] = {32, (uint32_t)p.Wg, (uint32_t)p.BH, (uint32_t)p.ipt};
       P->map_dy_dg = make_map(dy, 4, yd, yb);
       uint64_t wd[2] = {(uint64_t)g.Cout, (uint64_t)taps * g.Cin};
       uint32_t wb[2] = {32, (uint32_t)g.Cin};
