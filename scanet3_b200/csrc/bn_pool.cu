@@ -463,4 +463,6 @@ bool bn_pool_bwd(const float* x, const float* dyp, const unsigned char* map, flo
   return true;
 }
 
+void trace_set_bn_pool(unsigned long long* p) { sb_trace_set_local(p); }  // SB_TRACE timeline buffer of this translation unit
+
 }  // namespace sb

@@ -80,14 +80,14 @@ extern "C" int sb_device_count(void) {
 namespace sb {
 void trace_set_kernels_simt(unsigned long long*); void trace_set_kernels_fast(unsigned long long*); void trace_set_tc(unsigned long long*);
 void trace_set_tc_gemm(unsigned long long*); void trace_set_lstm(unsigned long long*); void trace_set_rnn(unsigned long long*);
-void trace_set_group(unsigned long long*); void trace_set_lstm_persist(unsigned long long*);
+void trace_set_group(unsigned long long*); void trace_set_lstm_persist(unsigned long long*); void trace_set_bn_pool(unsigned long long*);
 }  // namespace sb
 // SB_TRACE timeline (common.cuh): sb_trace_begin points every translation unit's kernels at a fresh device buffer,
 // sb_trace_read copies the stamps back (count first) and switches tracing off again.
 static unsigned long long* g_trace_dev = nullptr;
 static void trace_point_all(unsigned long long* p) {
   sb::trace_set_kernels_simt(p); sb::trace_set_kernels_fast(p); sb::trace_set_tc(p); sb::trace_set_tc_gemm(p);
-  sb::trace_set_lstm(p); sb::trace_set_rnn(p); sb::trace_set_group(p); sb::trace_set_lstm_persist(p);
+  sb::trace_set_lstm(p); sb::trace_set_rnn(p); sb::trace_set_group(p); sb::trace_set_lstm_persist(p); sb::trace_set_bn_pool(p);
 }
 extern "C" int sb_internal_trace_begin(void) {
   SB_API_BEGIN

@@ -850,62 +850,70 @@ __global__ void __launch_bounds__(256) conv_smallk_fwd_tile_kernel(const float* 
   extern __shared__ __align__(16) float swt[];  // filter [K][Cout]
   for (int i = threadIdx.x; i < K * g.Cout; i += blockDim.x) swt[i] = w[i];
   __syncthreads();
-  // persistent: the filter is staged once per block, the items advance by the grid's thread count
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_threads; i += (long long)gridDim.x * blockDim.x) {
-  const int c4 = (int)(i % C4);
-  long long t = i / C4;
-  const int seg = (int)(t % segs); t /= segs;
-  const int oh = (int)(t % g.OH);
-  const int b = (int)(t / g.OH);
-  const int ow0 = seg * PW;
-  float4 acc[PW];
+  // persistent: the filter is staged once per block, the items advance by the grid's thread count (32-bit index split: the launcher
+  // keeps n_threads < 2^31).  Packed fp32x2 FMAs (two independent IEEE FMAs, the same bits as the scalar form): channel pairs
+  // (0,1) and (2,3), as in conv_smallk_pool_fwd_kernel below.
+  const unsigned nthr = (unsigned)n_threads, step = gridDim.x * blockDim.x;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nthr; i += step) {
+    const int c4 = (int)(i % (unsigned)C4);
+    unsigned t = i / (unsigned)C4;
+    const int seg = (int)(t % (unsigned)segs); t /= (unsigned)segs;
+    const int oh = (int)(t % (unsigned)g.OH);
+    const int b = (int)(t / (unsigned)g.OH);
+    const int ow0 = seg * PW;
+    float2 acc[PW][2];
 #pragma unroll
-  for (int p = 0; p < PW; ++p) acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = 0; p < PW; ++p) acc[p][0] = acc[p][1] = make_float2(0.f, 0.f);
+    const float* wq = swt + c4 * 4;
 #pragma unroll
-  for (int a = 0; a < KH; ++a) {
-    const int ih = oh + a - g.PT;
-    const bool row_ok = ih >= 0 && ih < g.H;
-    const float* xr = x + ((long long)b * g.H + (row_ok ? ih : 0)) * g.W * CIN;
-    float xv[(PW + KW - 1) * CIN];
+    for (int a = 0; a < KH; ++a) {
+      const int ih = oh + a - g.PT;
+      const bool row_ok = ih >= 0 && ih < g.H;
+      const float* xr = x + ((long long)b * g.H + (row_ok ? ih : 0)) * g.W * CIN;
+      float xv[(PW + KW - 1) * CIN];
 #pragma unroll
-    for (int q = 0; q < PW + KW - 1; ++q) {
-      const int iw = ow0 + q - g.PL;
-      const bool ok = row_ok && iw >= 0 && iw < g.W;
+      for (int q = 0; q < PW + KW - 1; ++q) {
+        const int iw = ow0 + q - g.PL;
+        const bool ok = row_ok && iw >= 0 && iw < g.W;
 #pragma unroll
-      for (int ci = 0; ci < CIN; ++ci) xv[q * CIN + ci] = ok ? __ldg(xr + (long long)iw * CIN + ci) : 0.f;
-    }
-#pragma unroll
-    for (int bb = 0; bb < KW; ++bb)
-#pragma unroll
-      for (int ci = 0; ci < CIN; ++ci) {
-        const float4 wv = *reinterpret_cast<const float4*>(&swt[((a * KW + bb) * CIN + ci) * g.Cout + c4 * 4]);
-#pragma unroll
-        for (int p = 0; p < PW; ++p) {
-          const float v = xv[(p + bb) * CIN + ci];
-          acc[p].x = fmaf(v, wv.x, acc[p].x); acc[p].y = fmaf(v, wv.y, acc[p].y);
-          acc[p].z = fmaf(v, wv.z, acc[p].z); acc[p].w = fmaf(v, wv.w, acc[p].w);
-        }
+        for (int ci = 0; ci < CIN; ++ci) xv[q * CIN + ci] = ok ? __ldg(xr + iw * CIN + ci) : 0.f;
       }
-  }
-  float* yo = y + (((long long)b * g.OH + oh) * g.OW + ow0) * g.Cout + c4 * 4;
 #pragma unroll
-  for (int p = 0; p < PW; ++p) {
-    if (ow0 + p >= g.OW) break;
-    float4 o = acc[p];
-    if (relu) { o.x = fmaxf(thr, o.x); o.y = fmaxf(thr, o.y); o.z = fmaxf(thr, o.z); o.w = fmaxf(thr, o.w); }
-    st4(yo + (long long)p * g.Cout, o);
-  }
+      for (int bb = 0; bb < KW; ++bb)
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+          const float4 wv = *reinterpret_cast<const float4*>(wq + ((a * KW + bb) * CIN + ci) * g.Cout);
+          const float2 w01 = make_float2(wv.x, wv.y), w23 = make_float2(wv.z, wv.w);
+#pragma unroll
+          for (int p = 0; p < PW; ++p) {
+            const float v = xv[(p + bb) * CIN + ci];
+            const float2 vv = make_float2(v, v);
+            acc[p][0] = __ffma2_rn(vv, w01, acc[p][0]);
+            acc[p][1] = __ffma2_rn(vv, w23, acc[p][1]);
+          }
+        }
+    }
+    float* yo = y + (((long long)b * g.OH + oh) * g.OW + ow0) * g.Cout + c4 * 4;
+#pragma unroll
+    for (int p = 0; p < PW; ++p) {
+      if (ow0 + p >= g.OW) break;
+      float4 o = make_float4(acc[p][0].x, acc[p][0].y, acc[p][1].x, acc[p][1].y);
+      if (relu) { o.x = fmaxf(thr, o.x); o.y = fmaxf(thr, o.y); o.z = fmaxf(thr, o.z); o.w = fmaxf(thr, o.w); }
+      st4(yo + (long long)p * g.Cout, o);
+    }
   }
 }
 template <int KH, int KW, int CIN>
-static void launch_smallk_tile(const float* x, const float* w, float* y, const ConvGeom& g, int relu, float thr, cudaStream_t s) {
+static bool launch_smallk_tile(const float* x, const float* w, float* y, const ConvGeom& g, int relu, float thr, cudaStream_t s) {
   constexpr int PW = 4;
   const int segs = (g.OW + PW - 1) / PW;
   const long long nt = (long long)g.N * g.OH * segs * (g.Cout / 4);
+  if (nt >= (1ll << 31) || (long long)g.H * g.W * CIN >= (1ll << 31)) return false;  // 32-bit item index in the kernel
   const size_t smem = (size_t)KH * KW * CIN * g.Cout * sizeof(float);
   const int blocks = (int)std::min<long long>((nt + 255) / 256, (long long)kNumSMs * 8);
   launch_k(conv_smallk_fwd_tile_kernel<KH, KW, CIN, PW>, blocks, 256, smem, s, x, w, y, g, relu, thr, segs, nt);
   SB_LAUNCHED();
+  return true;
 }
 // Small-K conv (stride 1) >> [ReLU] >> max-pool 2x2 stride 1 VALID in ONE pass: a thread owns 4 channels x PW pool outputs of pool
 // row pr, i.e. the conv outputs of rows pr, pr+1 and columns ow0 .. ow0+PW.  It stores its own conv row (the backward needs the
@@ -1068,9 +1076,9 @@ bool conv_smallk_pool_fwd(const float* x, const float* w, float* y, float* poole
 void conv_smallk_fwd(const float* x, const float* w, float* y, const ConvGeom& g, int relu, float thr, cudaStream_t s) {
   if (g.SH == 1 && g.SW == 1) {
     const int shape = g.KH * 100 + g.KW * 10 + g.Cin;
-    if (shape == 331) return launch_smallk_tile<3, 3, 1>(x, w, y, g, relu, thr, s);
-    if (shape == 333) return launch_smallk_tile<3, 3, 3>(x, w, y, g, relu, thr, s);
-    if (shape == 551) return launch_smallk_tile<5, 5, 1>(x, w, y, g, relu, thr, s);
+    if (shape == 331 && launch_smallk_tile<3, 3, 1>(x, w, y, g, relu, thr, s)) return;
+    if (shape == 333 && launch_smallk_tile<3, 3, 3>(x, w, y, g, relu, thr, s)) return;
+    if (shape == 551 && launch_smallk_tile<5, 5, 1>(x, w, y, g, relu, thr, s)) return;
   }
   const long long n4 = (long long)g.N * g.OH * g.OW * (g.Cout / 4);
   launch_k(conv_smallk_fwd_kernel, grid_for(n4, 256), 256, 0, s, x, w, y, g, relu, thr, n4);
@@ -1198,11 +1206,9 @@ __global__ void __launch_bounds__(256, 2) conv_smallk_wgrad_tile_kernel(const fl
   const int tpp = CO4 * (kWgKP / 8);         // threads per phase
   const int phases = 256 / tpp;
   const int ph = tid / tpp, r = tid % tpp, kg = r / CO4, c4 = r % CO4;
-  float acc[8][4];
+  float2 acc[8][2];  // packed fp32x2 FMAs (two independent IEEE FMAs): channel pairs (0,1) and (2,3)
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
+  for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = make_float2(0.f, 0.f);
   const int fp = tid % kWgP, fq = tid / kWgP;  // im2col fill: pixel of the tile, quarter of the padded K (warp-uniform)
   // buffer b: dY rows [kWgP][Cout] then im2col rows [kWgP][kWgColStride]
   auto issue_dy = [&](int tile, float* dys) {
@@ -1213,9 +1219,10 @@ __global__ void __launch_bounds__(256, 2) conv_smallk_wgrad_tile_kernel(const fl
     }
   };
   auto load_cols = [&](int tile, float (&v)[8]) {
-    const long long p = (long long)tile * kWgP + fp;
-    const bool live = p < pixels;
-    const int ow = (int)(p % g.OW), oh = (int)((p / g.OW) % g.OH), b = (int)(p / ((long long)g.OW * g.OH));
+    const unsigned p = (unsigned)tile * kWgP + fp;  // the launcher keeps pixels < 2^31
+    const bool live = p < (unsigned)pixels;
+    const unsigned pr = p / (unsigned)g.OW;
+    const int ow = (int)(p - pr * (unsigned)g.OW), b = (int)(pr / (unsigned)g.OH), oh = (int)(pr - (unsigned)b * (unsigned)g.OH);
     if (fq == 0) wg_load_cols<KH, KW, CIN, 0>(v, x, g, b, oh, ow, live);
     else if (fq == 1) wg_load_cols<KH, KW, CIN, 1>(v, x, g, b, oh, ow, live);
     else if (fq == 2) wg_load_cols<KH, KW, CIN, 2>(v, x, g, b, oh, ow, live);
@@ -1252,10 +1259,12 @@ __global__ void __launch_bounds__(256, 2) conv_smallk_wgrad_tile_kernel(const fl
         const float4 xb = *reinterpret_cast<const float4*>(cols + p * kWgColStride + kg * 8 + 4);
         const float4 gv = *reinterpret_cast<const float4*>(dys + p * Cout + c4 * 4);
         const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+        const float2 g01 = make_float2(gv.x, gv.y), g23 = make_float2(gv.z, gv.w);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          acc[i][0] = fmaf(xv[i], gv.x, acc[i][0]); acc[i][1] = fmaf(xv[i], gv.y, acc[i][1]);
-          acc[i][2] = fmaf(xv[i], gv.z, acc[i][2]); acc[i][3] = fmaf(xv[i], gv.w, acc[i][3]);
+          const float2 vv = make_float2(xv[i], xv[i]);
+          acc[i][0] = __ffma2_rn(vv, g01, acc[i][0]);
+          acc[i][1] = __ffma2_rn(vv, g23, acc[i][1]);
         }
       }
     }
@@ -1268,7 +1277,7 @@ __global__ void __launch_bounds__(256, 2) conv_smallk_wgrad_tile_kernel(const fl
   if (ph < phases) {
 #pragma unroll
     for (int i = 0; i < 8; ++i)
-      *reinterpret_cast<float4*>(red + ((size_t)ph * kWgKP + kg * 8 + i) * Cout + c4 * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      *reinterpret_cast<float4*>(red + ((size_t)ph * kWgKP + kg * 8 + i) * Cout + c4 * 4) = make_float4(acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y);
   }
   __syncthreads();
   float* part = partial + (long long)blockIdx.x * K * Cout;
@@ -1293,6 +1302,7 @@ static bool launch_smallk_wgrad_tile(const float* x, const float* dy, float* dw,
   const size_t smem = std::max(2 * tile_floats, red_floats) * sizeof(float);
   if (smem > 200 * 1024) return false;
   const long long pixels = (long long)g.N * g.OH * g.OW;
+  if (pixels + kWgP >= (1ll << 31)) return false;  // 32-bit pixel index in the kernel
   const int tiles = (int)((pixels + kWgP - 1) / kWgP);
   int blocks = std::min(tiles, 2 * kNumSMs);
   if ((size_t)blocks * K * g.Cout > ws_floats) blocks = (int)(ws_floats / ((size_t)K * g.Cout));
