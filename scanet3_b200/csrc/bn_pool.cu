@@ -169,10 +169,10 @@ struct BnChunks {
   long long rows_per_chunk;
 };
 // chunks of whole block-rows x unroll, about three blocks per SM; bounded by the workspace ([chunk][2][C] floats)
-BnChunks bn_chunks(long long rows, int C, size_t wsf) {
+BnChunks bn_chunks(long long rows, int C, size_t wsf, int unroll = kBnUnroll, int per_sm = 3) {
   const int R = kBnThreads / (C / 4);
-  const long long unit = (long long)R * kBnUnroll;
-  long long want = 3 * kNumSMs;
+  const long long unit = (long long)R * unroll;
+  long long want = (long long)per_sm * kNumSMs;
   const long long by_ws = (long long)(wsf / ((size_t)2 * C));
   if (want > by_ws) want = by_ws;
   if (want < 1) want = 1;
@@ -216,22 +216,21 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_pool_kernel(const float* 
                                                                   const float* __restrict__ mean, const float* __restrict__ var, float eps, int fused,
                                                                   int H, int W, int C4, int OH, int OW, long long n4) {
   pdl_prologue();
-  const long long stride = (long long)gridDim.x * kBnThreads;  // a multiple of C4: the channel group of a thread is fixed
-  long long i = (long long)blockIdx.x * kBnThreads + threadIdx.x;
-  if (i >= n4) return;
-  const int c4 = (int)(i % C4);
+  // 32-bit index math (bn_pool_ok keeps every element count below 2^31: a 64-bit division costs more than the item's arithmetic)
+  const unsigned stride = gridDim.x * kBnThreads;  // a multiple of C4: the channel group of a thread is fixed
+  unsigned i = blockIdx.x * kBnThreads + threadIdx.x;
+  const unsigned n = (unsigned)n4;
+  if (i >= n) return;
+  const int c4 = (int)(i % (unsigned)C4);
   BnScale bn;
   bn.load(gamma, beta, mean, var, eps, c4 * 4, fused);
   const float4* xp = reinterpret_cast<const float4*>(x) + c4;
-  for (; i < n4; i += stride) {
-    long long p = i / C4;
-    const int pw = (int)(p % OW);
-    p /= OW;
-    const int ph = (int)(p % OH);
-    const long long img = p / OH;
-    const long long base = ((img * H + 2 * ph) * W + 2 * pw) * C4;
-    const float4 qa = __ldg(xp + base), qb = __ldg(xp + base + C4), qc = __ldg(xp + base + (long long)W * C4),
-                 qd = __ldg(xp + base + (long long)W * C4 + C4);
+  for (; i < n; i += stride) {
+    unsigned p = i / (unsigned)C4;
+    const unsigned t1 = p / (unsigned)OW, pw = p - t1 * (unsigned)OW;
+    const unsigned img = t1 / (unsigned)OH, ph = t1 - img * (unsigned)OH;
+    const unsigned base = ((img * H + 2 * ph) * W + 2 * pw) * C4;
+    const float4 qa = __ldg(xp + base), qb = __ldg(xp + base + C4), qc = __ldg(xp + base + W * C4), qd = __ldg(xp + base + W * C4 + C4);
     float4 o;
     const unsigned b0 = first_max4(bn.apply(qa.x, 0), bn.apply(qb.x, 0), bn.apply(qc.x, 0), bn.apply(qd.x, 0), &o.x);
     const unsigned b1 = first_max4(bn.apply(qa.y, 1), bn.apply(qb.y, 1), bn.apply(qc.y, 1), bn.apply(qd.y, 1), &o.y);
@@ -263,17 +262,13 @@ __global__ void __launch_bounds__(kBnThreads) bn_pool_bwd_reduce_kernel(const fl
   float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
   const float4* xp = reinterpret_cast<const float4*>(x) + c4;
 #pragma unroll 2
-  for (long long r = r0 + j; r < r1; r += R) {
-    long long p = r;
-    const int pw = (int)(p % OW);
-    p /= OW;
-    const int ph = (int)(p % OH);
-    const long long img = p / OH;
-    const long long base = ((img * H + 2 * ph) * W + 2 * pw) * C4;
+  for (unsigned r = (unsigned)r0 + j; r < (unsigned)r1; r += R) {
+    const unsigned t1 = r / (unsigned)OW, pw = r - t1 * (unsigned)OW;
+    const unsigned img = t1 / (unsigned)OH, ph = t1 - img * (unsigned)OH;
+    const unsigned base = ((img * H + 2 * ph) * W + 2 * pw) * C4;
     const float4 g = __ldg(reinterpret_cast<const float4*>(dyp) + r * C4 + c4);
     const unsigned mp = __ldg(reinterpret_cast<const unsigned*>(map) + r * C4 + c4);
-    const float4 qa = __ldg(xp + base), qb = __ldg(xp + base + C4), qc = __ldg(xp + base + (long long)W * C4),
-                 qd = __ldg(xp + base + (long long)W * C4 + C4);
+    const float4 qa = __ldg(xp + base), qb = __ldg(xp + base + C4), qc = __ldg(xp + base + W * C4), qd = __ldg(xp + base + W * C4 + C4);
 #define SB_PICK(f, sh) ((((mp >> (sh)) & 2u) ? (((mp >> (sh)) & 1u) ? qd.f : qc.f) : (((mp >> (sh)) & 1u) ? qb.f : qa.f)))
     const float xw0 = SB_PICK(x, 0), xw1 = SB_PICK(y, 8), xw2 = SB_PICK(z, 16), xw3 = SB_PICK(w, 24);
 #undef SB_PICK
@@ -338,10 +333,11 @@ __global__ void __launch_bounds__(kBnThreads) bn_pool_bwd_apply_kernel(const flo
                                                                       float rows, int quirk, int relu, float thr, int H, int W, int C4, int OH, int OW,
                                                                       int BH, int BW, long long n4) {
   pdl_prologue();
-  const long long stride = (long long)gridDim.x * kBnThreads;
-  long long i = (long long)blockIdx.x * kBnThreads + threadIdx.x;
-  if (i >= n4) return;
-  const int c4 = (int)(i % C4), c = c4 * 4, C = C4 * 4;
+  const unsigned stride = gridDim.x * kBnThreads;
+  unsigned i = blockIdx.x * kBnThreads + threadIdx.x;
+  const unsigned n = (unsigned)n4;
+  if (i >= n) return;
+  const int c4 = (int)(i % (unsigned)C4), c = c4 * 4, C = C4 * 4;
   float mean_in[4], ve[4], gi[4], mg[4], mgx[4];
   {
     const float4 m4 = ldg4(save_mean + c), v4 = ldg4(save_var + c), s0 = ldg4(sums + c), s1 = ldg4(sums + C + c), gm = ldg4(gamma + c);
@@ -358,17 +354,16 @@ __global__ void __launch_bounds__(kBnThreads) bn_pool_bwd_apply_kernel(const flo
   }
   const float4* xp = reinterpret_cast<const float4*>(x) + c4;
   float4* dxp = reinterpret_cast<float4*>(dx) + c4;
-  for (; i < n4; i += stride) {
-    long long p = i / C4;
-    const int bw = (int)(p % BW);
-    p /= BW;
-    const int bh = (int)(p % BH);
-    const long long img = p / BH;
+  for (; i < n; i += stride) {
+    const unsigned p = i / (unsigned)C4;
+    const unsigned t1 = p / (unsigned)BW, ubw = p - t1 * (unsigned)BW;
+    const unsigned img = t1 / (unsigned)BH, ubh = t1 - img * (unsigned)BH;
+    const int bw = (int)ubw, bh = (int)ubh;
     const bool inwin = bh < OH && bw < OW;
     float g[4] = {0.f, 0.f, 0.f, 0.f};
     unsigned mp = 0;
     if (inwin) {
-      const long long pi = ((img * OH + bh) * OW + bw) * C4 + c4;
+      const unsigned pi = ((img * OH + bh) * OW + bw) * C4 + c4;
       const float4 q = __ldg(reinterpret_cast<const float4*>(dyp) + pi);
       g[0] = q.x; g[1] = q.y; g[2] = q.z; g[3] = q.w;
       mp = __ldg(reinterpret_cast<const unsigned*>(map) + pi) & 0x03030303u;
@@ -381,7 +376,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_pool_bwd_apply_kernel(const flo
 #pragma unroll
       for (int b = 0; b < 2; ++b) {
         if (2 * bw + b >= W) continue;
-        const long long off = ((img * H + 2 * bh + a) * W + 2 * bw + b) * C4;
+        const unsigned off = ((img * H + 2 * bh + a) * W + 2 * bw + b) * C4;
         const float4 q = __ldg(xp + off);
         const float xv[4] = {q.x, q.y, q.z, q.w};
         float o[4];
@@ -425,7 +420,7 @@ bool bn_stats(const float* x, long long rows, int C, float* save_mean, float* sa
 
 bool bn_pool_ok(const PoolGeom& g) {
   return bn_lean_ok(g.C) && g.KH == 2 && g.KW == 2 && g.SH == 2 && g.SW == 2 && g.PT == 0 && g.PL == 0 && g.OH == g.H / 2 && g.OW == g.W / 2 &&
-         g.OH >= 1 && g.OW >= 1;
+         g.OH >= 1 && g.OW >= 1 && (long long)g.N * (g.H + 1) * (g.W + 1) * g.C < (1ll << 31);  // 32-bit element indices in the kernels
 }
 
 bool bn_apply_pool_fwd(const float* x, float* yp, unsigned char* map, const float* gamma, const float* beta, const float* mean, const float* var,
@@ -447,7 +442,7 @@ bool bn_pool_bwd(const float* x, const float* dyp, const unsigned char* map, flo
   const long long rows = (long long)g.N * g.H * g.W, prow = (long long)g.N * g.OH * g.OW;
   float* sums = ws;  // [2*C sums][partials...]
   float* part = ws + 2 * (size_t)C;
-  BnChunks cc = bn_chunks(prow, C, wsf - 2 * (size_t)C);
+  BnChunks cc = bn_chunks(prow, C, wsf - 2 * (size_t)C, 1, 4);  // whole block-rows per chunk, four blocks per SM
   launch_k(bn_pool_bwd_reduce_kernel, cc.chunks, kBnThreads, 0, s, x, dyp, map, save_mean, save_var, part, g.H, g.W, C4, g.OH, g.OW, prow,
            cc.rows_per_chunk, (float)rows, quirk);
   SB_LAUNCHED();
