@@ -745,6 +745,12 @@ static float* G(sb_engine* e, int pi) { return e->grads + e->params[pi].offset; 
 
 enum FwdMode { FWD_TRAIN = 0, FWD_LOSS_ONLY = 1, FWD_INFER = 2 };
 
+// per-kernel timing collects a layer's deferred reduction so that it is its own class; it must then run what the product path runs
+static void reduce_each(ReduceBatch& rb, cudaStream_t s) {
+  for (int i = 0; i < rb.count; ++i) partial_reduce(rb.partial[i], rb.out[i], rb.n[i], rb.parts[i], s);
+  rb.count = 0;
+}
+
 static void run_forward(sb_engine* e, int mode) {
   cudaStream_t s = e->stream;
   const int nl = (int)e->L.size();
@@ -1034,7 +1040,7 @@ static void run_backward(sb_engine* e) {
             }
             if (rb.count) {
               Prof pr(e, "partial_reduce", 4.0 * ((double)rb.n[0] * rb.parts[0] + rb.n[0]), 0);
-              partial_reduce_multi(rb, s);
+              reduce_each(rb, s);  // the launches the product path makes, not the merged variant
             }
           }
           if (L.need_dx && din) {
@@ -1076,7 +1082,7 @@ static void run_backward(sb_engine* e) {
           }
           if (rb.count) {  // per-kernel timing: the reduction of the per-CTA partials is its own class
             Prof pr(e, "partial_reduce", 4.0 * ((double)rb.n[0] * rb.parts[0] + rb.n[0]), 0);
-            partial_reduce_multi(rb, s);
+            reduce_each(rb, s);  // the launches the product path makes, not the merged variant
           }
           if (ok) break;
           SB_FAIL(SB_ERR_CUDA, "pool_bwd_conv_wgrad rejected a planned shape");

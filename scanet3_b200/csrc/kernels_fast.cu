@@ -1373,8 +1373,10 @@ __global__ void __launch_bounds__(32 * YG) partial_reduce_kernel(const float* __
   __shared__ float red[YG][33];
   const int i = blockIdx.x * 32 + threadIdx.x, y = threadIdx.y;
   float acc = 0.f;
-  if (i < n)
+  if (i < n) {
+#pragma unroll 4
     for (int c = y; c < parts; c += YG) acc = __fadd_rn(acc, __ldg(partial + (size_t)c * n + i));
+  }
   red[y][threadIdx.x] = acc;
   __syncthreads();
   if (y == 0 && i < n) {
