@@ -55,6 +55,9 @@ struct LstmWs {
   // kernels -- the epilogue's row-per-thread TMEM layout makes every c / dc / acts access uncoalesced and concentrates the
   // pointwise work on 128 threads of <= 128 CTAs.  Kept selectable (SB_LSTM_FUSED_EPILOGUE=1) and parity-tested; off by default.
   bool fused_epilogue = false;
+  float* bwd_ws = nullptr;   // split-K partials of the dH product
+  size_t bwd_ws_floats = 0;
+  bool fast_math = false;    // TF32 mode: approximate exp / reciprocal in the gate activations (actf_t); SB_LSTM_EXACT_GATES=1 turns it off
   void* persist = nullptr;   // lstm_persist.cu: one launch for all T forward steps (TF32 mode, F <= 8, B % 128 == 0, <= 148 CTAs)
 };
 
@@ -62,6 +65,19 @@ __device__ __forceinline__ float actf(float x, int act) {
   switch (act) {
     case 1: return __fdiv_rn(1.f, __fadd_rn(1.f, expf(-x)));
     case 2: return tanhf(x);
+    case 4: return fmaxf(0.f, x);
+    default: return x;
+  }
+}
+// TF32 mode only (FAST): sigmoid and tanh through ex2.approx / rcp.approx -- relative error ~1e-6 (absolute ~1e-7 for tanh near
+// zero), three orders below the tf32 products they are applied to, and 4-5x fewer instructions than expf + IEEE division / tanhf:
+// the gate kernels of a time step are instruction-bound, not memory-bound (profiles/r2_notes.md 13).  FP32 and 3xTF32 keep the exact forms.
+template <bool FAST>
+__device__ __forceinline__ float actf_t(float x, int act) {
+  if (!FAST) return actf(x, act);
+  switch (act) {
+    case 1: return __fdividef(1.f, 1.f + __expf(-x));
+    case 2: return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x));  // tanh x = 1 - 2 / (1 + e^{2x}); saturates cleanly (e^{2x} -> inf: 1, -> 0: -1)
     case 4: return fmaxf(0.f, x);
     default: return x;
   }
@@ -111,19 +127,19 @@ __global__ void lstm_transpose_kernel(const float* __restrict__ in, float* __res
 }
 
 // Forward gates of one time step.  z (in/out): recurrent product (ignored when first), becomes the activations.
-template <int FI>  // FI > 0: inline input projection with F = FI features ; FI == 0: xw holds X_t . Wk_cat
+template <int FI, bool FAST>  // FI > 0: inline input projection with F = FI features ; FI == 0: xw holds X_t . Wk_cat
 __global__ void __launch_bounds__(256) lstm_gates_fwd_kernel(float* __restrict__ z, const float* __restrict__ x_t,
                                                              const float* __restrict__ wk_cat, const float* __restrict__ b_cat,
                                                              const float* __restrict__ xw_t, const float* __restrict__ c_prev,
                                                              float* __restrict__ c_out, float* __restrict__ h_out, int B, int U,
                                                              int first, int act, int ract, int has_bias) {
   pdl_prologue_trigger();
-  const long long n = (long long)B * U;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int j = (int)(i % U);
-    const long long b = i / U;
+  const unsigned n = (unsigned)B * (unsigned)U;  // the launcher keeps B * 4U below 2^31: 32-bit index math
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned b = i / (unsigned)U;
+    const int j = (int)(i - b * (unsigned)U);
     float a[4];
-    float4* zq = reinterpret_cast<float4*>(z + b * 4 * U + 4 * j);  // the unit's four gates are adjacent
+    float4* zq = reinterpret_cast<float4*>(z + (size_t)b * 4 * U + 4 * j);  // the unit's four gates are adjacent
     const float4 zr = first ? make_float4(0.f, 0.f, 0.f, 0.f) : *zq;
     const float zin[4] = {zr.x, zr.y, zr.z, zr.w};
 #pragma unroll
@@ -133,37 +149,38 @@ __global__ void __launch_bounds__(256) lstm_gates_fwd_kernel(float* __restrict__
       if (FI > 0) {
         xp = 0.f;
 #pragma unroll
-        for (int f = 0; f < FI; ++f) xp = fmaf(__ldg(x_t + b * FI + f), __ldg(wk_cat + (long long)f * 4 * U + col), xp);
+        for (int f = 0; f < FI; ++f) xp = fmaf(__ldg(x_t + (size_t)b * FI + f), __ldg(wk_cat + (size_t)f * 4 * U + col), xp);
       } else {
-        xp = xw_t[b * 4 * U + col];
+        xp = xw_t[(size_t)b * 4 * U + col];
       }
       float v = first ? xp : __fadd_rn(xp, zin[g]);           // (x.Wk + h.Wr)
       if (has_bias) v = __fadd_rn(v, __ldg(b_cat + col));       // + b
-      a[g] = actf(v, g == 2 ? act : ract);
+      a[g] = actf_t<FAST>(v, g == 2 ? act : ract);
     }
     *zq = make_float4(a[0], a[1], a[2], a[3]);
     const float cp = first ? 0.f : c_prev[i];
     const float c = __fadd_rn(__fmul_rn(cp, a[0]), __fmul_rn(a[1], a[2]));  // c_prev*f + i*g
     c_out[i] = c;
-    h_out[i] = __fmul_rn(a[3], actf(c, act));                                // o * act(c)
+    h_out[i] = __fmul_rn(a[3], actf_t<FAST>(c, act));                        // o * act(c)
   }
 }
 
 // Backward gates of one time step (oracle/layers.py LSTMCell.step_bwd):
 //   do = dh*ac ; dc = act'(dh*o ; ac) + dc_next ; df = dc*c_prev ; di = dc*g ; dg = dc*i ; dz_G = act_G'(d_G ; a_G) ; dc_prev = dc*f
+template <bool FAST>
 __global__ void __launch_bounds__(256) lstm_gates_bwd_kernel(float* __restrict__ acts_dz, const float* __restrict__ c_t,
                                                              const float* __restrict__ c_prev, const float* __restrict__ dh,
                                                              const float* __restrict__ dh_seq, float* __restrict__ dc_io, int B, int U,
                                                              int first, int last, int act, int ract) {
   pdl_prologue_trigger();
-  const long long n = (long long)B * U;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int j = (int)(i % U);
-    const long long b = i / U;
-    float4* q = reinterpret_cast<float4*>(acts_dz + b * 4 * U + 4 * j);
+  const unsigned n = (unsigned)B * (unsigned)U;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned b = i / (unsigned)U;
+    const int j = (int)(i - b * (unsigned)U);
+    float4* q = reinterpret_cast<float4*>(acts_dz + (size_t)b * 4 * U + 4 * j);
     const float4 a4 = *q;
     const float f = a4.x, ig = a4.y, g = a4.z, o = a4.w;
-    const float ac = actf(c_t[i], act);
+    const float ac = actf_t<FAST>(c_t[i], act);
     // returnSequence: this step's own output gradient joins the recurrent one (`dout + dstate`, oracle RNN.backward)
     const float dhv = dh_seq ? __fadd_rn(dh_seq[i], dh[i]) : dh[i];
     const float d_o = __fmul_rn(dhv, ac);
@@ -253,6 +270,7 @@ LstmWs* ws_of(sb_engine* e, LayerPlan& L) {
   LstmWs* w = new LstmWs();
   w->B = (int)L.in.d[0]; w->T = (int)L.in.d[1]; w->F = (int)L.in.d[2]; w->U = L.d.units;
   const long long B = w->B, T = w->T, F = w->F, U = w->U;
+  if (B * 4 * U >= (1ll << 31)) { delete w; throw CudaError("LSTM: batch x 4 x units must stay below 2^31 (32-bit element indices in the gate kernels)"); }
   w->wr_cat = dalloc(U * 4 * U);
   w->wk_cat = dalloc(F * 4 * U);
   w->b_cat = dalloc(4 * U);
@@ -274,9 +292,21 @@ LstmWs* ws_of(sb_engine* e, LayerPlan& L) {
   if (e->train.precision != SB_PREC_FP32 && B * U * 4 * U >= (1 << 22) && U % 32 == 0) {
     const int x3 = e->train.precision == SB_PREC_3XTF32 ? 1 : 0;
     w->g_fwd = tc_gemm_create(0, 1, w->h, (int)T + 1, w->wr_cat, 1, w->acts, (int)T, (int)B, (int)(4 * U), (int)U, 0, nullptr, 0, e->device, x3);
-    w->g_bwd = tc_gemm_create(0, 0, w->acts, (int)T, w->wr_cat, 1, w->dh, 1, (int)B, (int)U, (int)(4 * U), 0, nullptr, 0, e->device, x3);
+    // dH_{t-1} = dZ_t . Wr_cat^T sits on the serial path of BPTT and has few output tiles (cfg3: 16) over a long K (4U): deterministic
+    // split-K over a private workspace (SB_LSTM_BWD_SPLITK=0: one CTA per tile, 32-column tiles -- 13 us per step instead of ~5)
+    {
+      const char* sk = getenv("SB_LSTM_BWD_SPLITK");
+      const char* fe0 = getenv("SB_LSTM_FUSED_EPILOGUE");  // the fused-epilogue variant cannot split
+      if (!(sk && sk[0] == '0') && !(fe0 && fe0[0] == '1') && !x3) {
+        w->bwd_ws_floats = (size_t)8 * B * U;
+        w->bwd_ws = dalloc((long long)w->bwd_ws_floats);
+      }
+    }
+    w->g_bwd = tc_gemm_create(0, 0, w->acts, (int)T, w->wr_cat, 1, w->dh, 1, (int)B, (int)U, (int)(4 * U), w->bwd_ws ? 2 : 0, w->bwd_ws,
+                              w->bwd_ws_floats, e->device, x3);
     w->g_dwr = tc_gemm_create(1, 1, w->h, 1, w->acts, 1, w->dwr_cat, 1, (int)U, (int)(4 * U), (int)(T * B), 1, e->ws, e->ws_floats,
                               e->device, x3);
+    { const char* ex = getenv("SB_LSTM_EXACT_GATES"); w->fast_math = !x3 && w->g_fwd && !(ex && ex[0] == '1'); }
     const char* fe = getenv("SB_LSTM_FUSED_EPILOGUE");
     w->fused_epilogue = fe && fe[0] == '1' && w->g_fwd && w->g_bwd && !L.d.return_sequence && !L.d.stateful;
     if (!x3 && !w->fused_epilogue && !w->xw && w->g_fwd)
@@ -299,8 +329,12 @@ template <int FI>
 void launch_gates_fwd(LstmWs* w, float* z, const float* x_t, const float* xw_t, const float* c_prev, float* c_out, float* h_out,
                       int first, int act, int ract, int has_bias, cudaStream_t s) {
   const long long n = (long long)w->B * w->U;
-  launch_k(lstm_gates_fwd_kernel<FI>, ew_grid(n), 256, 0, s, z, x_t, w->wk_cat, w->b_cat, xw_t, c_prev, c_out, h_out, w->B, w->U, first,
-                                                       act, ract, has_bias);
+  if (w->fast_math)
+    launch_k(lstm_gates_fwd_kernel<FI, true>, ew_grid(n), 256, 0, s, z, x_t, w->wk_cat, w->b_cat, xw_t, c_prev, c_out, h_out, w->B, w->U, first,
+             act, ract, has_bias);
+  else
+    launch_k(lstm_gates_fwd_kernel<FI, false>, ew_grid(n), 256, 0, s, z, x_t, w->wk_cat, w->b_cat, xw_t, c_prev, c_out, h_out, w->B, w->U, first,
+             act, ract, has_bias);
   SB_LAUNCHED();
 }
 
@@ -409,8 +443,12 @@ void lstm_backward(sb_engine* e, LayerPlan& L, int) {
     const float* c_prev = t ? w->c + (long long)(t - 1) * BU : (stateful ? w->c_init : nullptr);
     if (t == T - 1 || !w->fused_epilogue) {  // fused mode: the gate backward of step t < T-1 ran in the epilogue of step t+1
       const float* dh_seq = (seq && t < T - 1) ? w->dout_tm + (long long)t * BU : nullptr;
-      launch_k(lstm_gates_bwd_kernel, ew_grid(BU), 256, 0, s, a, c_t, c_prev, dh, dh_seq, w->dc, B, U, t == 0 && !stateful, t == T - 1, act,
-               ract);
+      if (w->fast_math)
+        launch_k(lstm_gates_bwd_kernel<true>, ew_grid(BU), 256, 0, s, a, c_t, c_prev, dh, dh_seq, w->dc, B, U, t == 0 && !stateful, t == T - 1,
+                 act, ract);
+      else
+        launch_k(lstm_gates_bwd_kernel<false>, ew_grid(BU), 256, 0, s, a, c_t, c_prev, dh, dh_seq, w->dc, B, U, t == 0 && !stateful, t == T - 1,
+                 act, ract);
       SB_LAUNCHED();
     }
     if (t > 0) {
@@ -473,7 +511,7 @@ void lstm_free(sb_engine* e) {
     if (!L.lstm || L.d.kind != SB_LAYER_LSTM) continue;
     LstmWs* w = (LstmWs*)L.lstm;
     for (float* p : {w->wr_cat, w->wk_cat, w->b_cat, w->x_tm, w->acts, w->c, w->h, w->xw, w->dh, w->dc, w->dwr_cat, w->dwk_cat,
-                     w->db_cat, w->dwkb_cat, w->dx_tm, w->dout_tm, w->c_init})
+                     w->db_cat, w->dwkb_cat, w->dx_tm, w->dout_tm, w->c_init, w->bwd_ws})
       cudaFree(p);
     tc_gemm_destroy(w->g_fwd); tc_gemm_destroy(w->g_bwd); tc_gemm_destroy(w->g_dwr);
     lstm_persist_destroy(w->persist);

@@ -448,8 +448,11 @@ TcGemm* tc_gemm_create(int a_mn_major, int b_mn_major, const float* A, int a_sli
     const int BNc = std::min(bn, n_cap);
     const int tiles = p.m_tiles * ((N + BNc - 1) / BNc);
     int splits = 1;
-    if (allow_split && ws && tiles * 2 <= kNumSMs && p.kb_total >= 64)
-      splits = std::max(1, std::min({kNumSMs / tiles, p.kb_total / 16, (int)(ws_floats / ((size_t)M * N))}));
+    // allow_split == 2: a latency-critical small-output product on the serial path of a recurrence (LSTM dH = dZ . Wr^T: 16 tiles
+    // of K = 1024) -- split down to 4 k-blocks per CTA so that every SM streams a share of the operands
+    const int min_kb = allow_split == 2 ? 4 : 16;
+    if (allow_split && ws && tiles * 2 <= kNumSMs && p.kb_total >= 4 * min_kb)
+      splits = std::max(1, std::min({kNumSMs / tiles, p.kb_total / min_kb, (int)(ws_floats / ((size_t)M * N))}));
     const int work = tiles * splits, waves = (work + kNumSMs - 1) / kNumSMs;
     const double eff = BNc >= 256 ? 1.0 : BNc >= 128 ? 0.9 : BNc >= 64 ? 0.7 : 0.45;
     const double score = (double)work / (waves * (double)kNumSMs) * eff;
