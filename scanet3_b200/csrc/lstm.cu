@@ -55,8 +55,10 @@ struct LstmWs {
   // kernels -- the epilogue's row-per-thread TMEM layout makes every c / dc / acts access uncoalesced and concentrates the
   // pointwise work on 128 threads of <= 128 CTAs.  Kept selectable (SB_LSTM_FUSED_EPILOGUE=1) and parity-tested; off by default.
   bool fused_epilogue = false;
+  bool fused_fwd = false;
   float* bwd_ws = nullptr;   // split-K partials of the dH product
   size_t bwd_ws_floats = 0;
+  bool bwd_fold = true;      // the gate backward kernel sums the split-K partials itself (SB_LSTM_BWD_FOLD=0: a separate partial_reduce launch)
   bool fast_math = false;    // TF32 mode: approximate exp / reciprocal in the gate activations (actf_t); SB_LSTM_EXACT_GATES=1 turns it off
   void* persist = nullptr;   // lstm_persist.cu: one launch for all T forward steps (TF32 mode, F <= 8, B % 128 == 0, <= 148 CTAs)
 };
@@ -171,7 +173,7 @@ template <bool FAST>
 __global__ void __launch_bounds__(256) lstm_gates_bwd_kernel(float* __restrict__ acts_dz, const float* __restrict__ c_t,
                                                              const float* __restrict__ c_prev, const float* __restrict__ dh,
                                                              const float* __restrict__ dh_seq, float* __restrict__ dc_io, int B, int U,
-                                                             int first, int last, int act, int ract) {
+                                                             int first, int last, int act, int ract, int dh_parts) {
   pdl_prologue_trigger();
   const unsigned n = (unsigned)B * (unsigned)U;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -182,7 +184,15 @@ __global__ void __launch_bounds__(256) lstm_gates_bwd_kernel(float* __restrict__
     const float f = a4.x, ig = a4.y, g = a4.z, o = a4.w;
     const float ac = actf_t<FAST>(c_t[i], act);
     // returnSequence: this step's own output gradient joins the recurrent one (`dout + dstate`, oracle RNN.backward)
-    const float dhv = dh_seq ? __fadd_rn(dh_seq[i], dh[i]) : dh[i];
+    // dh_parts > 1: dh is the split-K partials [dh_parts][B*U] of the dH product, summed here in split order (the order partial_reduce uses)
+    float dhp[8];  // all loads in flight first (the plan keeps dh_parts <= 8), then the ordered sum
+#pragma unroll
+    for (int sp = 0; sp < 8; ++sp) dhp[sp] = sp < dh_parts ? __ldg(dh + (size_t)sp * n + i) : 0.f;
+    float dhr = dhp[0];
+#pragma unroll
+    for (int sp = 1; sp < 8; ++sp)
+      if (sp < dh_parts) dhr = __fadd_rn(dhr, dhp[sp]);
+    const float dhv = dh_seq ? __fadd_rn(dh_seq[i], dhr) : dhr;
     const float d_o = __fmul_rn(dhv, ac);
     float dc = actg(__fmul_rn(dhv, o), ac, act);
     if (!last) dc = __fadd_rn(dc, dc_io[i]);
@@ -298,6 +308,7 @@ LstmWs* ws_of(sb_engine* e, LayerPlan& L) {
       const char* sk = getenv("SB_LSTM_BWD_SPLITK");
       const char* fe0 = getenv("SB_LSTM_FUSED_EPILOGUE");  // the fused-epilogue variant cannot split
       if (!(sk && sk[0] == '0') && !(fe0 && fe0[0] == '1') && !x3) {
+        { const char* bf = getenv("SB_LSTM_BWD_FOLD"); w->bwd_fold = !(bf && bf[0] == '0'); }
         w->bwd_ws_floats = (size_t)8 * B * U;
         w->bwd_ws = dalloc((long long)w->bwd_ws_floats);
       }
@@ -309,7 +320,9 @@ LstmWs* ws_of(sb_engine* e, LayerPlan& L) {
     { const char* ex = getenv("SB_LSTM_EXACT_GATES"); w->fast_math = !x3 && w->g_fwd && !(ex && ex[0] == '1'); }
     const char* fe = getenv("SB_LSTM_FUSED_EPILOGUE");
     w->fused_epilogue = fe && fe[0] == '1' && w->g_fwd && w->g_bwd && !L.d.return_sequence && !L.d.stateful;
-    if (!x3 && !w->fused_epilogue && !w->xw && w->g_fwd)
+    // =2: the forward gates in the GEMM epilogue, the backward as separate kernels (keeps the split-K dH product)
+    w->fused_fwd = w->fused_epilogue || (fe && fe[0] == '2' && w->g_fwd && !L.d.return_sequence && !L.d.stateful);
+    if (!x3 && !w->fused_fwd && !w->xw && w->g_fwd)
       w->persist = lstm_persist_create((int)B, (int)T, (int)U, (int)F, w->h, w->wr_cat, e->device);
   }
   L.lstm = w;
@@ -382,10 +395,10 @@ void lstm_forward(sb_engine* e, LayerPlan& L, int, bool store_state) {
     float* h_t = w->h + (long long)(t + 1) * BU;
     float* c_t = w->c + (long long)t * BU;
     const float* c_prev = t ? w->c + (long long)(t - 1) * BU : (stateful ? w->c_init : nullptr);
-    if (t > 0 && w->fused_epilogue && !w->xw) {
+    if (t > 0 && w->fused_fwd && !w->xw) {
       // Z_t = H_{t-1} . Wr_cat with the gate math in the GEMM epilogue: activations -> acts[t], c_t, h_t (no separate kernel)
       LstmEpi ep{};
-      ep.mode = 1; ep.F = F; ep.U = U; ep.act = act; ep.ract = ract; ep.has_bias = L.d.use_bias;
+      ep.mode = 1; ep.F = F; ep.U = U; ep.act = act; ep.ract = ract; ep.has_bias = L.d.use_bias; ep.fast = w->fast_math ? 1 : 0;
       ep.x_t = w->x_tm + (long long)t * B * F; ep.wk_cat = w->wk_cat; ep.b_cat = w->b_cat;
       ep.c_prev = c_prev; ep.c_out = c_t; ep.h_out = h_t;
       tc_gemm_run_lstm(w->g_fwd, t, 0, t, ep, s);
@@ -436,6 +449,7 @@ void lstm_backward(sb_engine* e, LayerPlan& L, int) {
     SB_LAUNCHED();
     dh = w->dout_tm + (long long)(T - 1) * BU;
   }
+  int dh_parts = 1;
   for (int t = T - 1; t >= 0; --t) {
     float* a = w->acts + (long long)t * B * 4 * U;
     const float* c_t = w->c + (long long)t * BU;
@@ -445,26 +459,28 @@ void lstm_backward(sb_engine* e, LayerPlan& L, int) {
       const float* dh_seq = (seq && t < T - 1) ? w->dout_tm + (long long)t * BU : nullptr;
       if (w->fast_math)
         launch_k(lstm_gates_bwd_kernel<true>, ew_grid(BU), 256, 0, s, a, c_t, c_prev, dh, dh_seq, w->dc, B, U, t == 0 && !stateful, t == T - 1,
-                 act, ract);
+                 act, ract, dh_parts);
       else
         launch_k(lstm_gates_bwd_kernel<false>, ew_grid(BU), 256, 0, s, a, c_t, c_prev, dh, dh_seq, w->dc, B, U, t == 0 && !stateful, t == T - 1,
-                 act, ract);
+                 act, ract, dh_parts);
       SB_LAUNCHED();
     }
     if (t > 0) {
       if (w->fused_epilogue) {
         // dH_{t-1} = dZ_t . Wr_cat^T, consumed in the epilogue: gate backward of step t-1 (acts[t-1] -> dZ_{t-1}, dc -> dc_{t-2})
         LstmEpi ep{};
-        ep.mode = 2; ep.F = F; ep.U = U; ep.act = act; ep.ract = ract; ep.has_bias = L.d.use_bias;
+        ep.mode = 2; ep.F = F; ep.U = U; ep.act = act; ep.ract = ract; ep.has_bias = L.d.use_bias; ep.fast = w->fast_math ? 1 : 0;
         ep.acts_dz = w->acts + (long long)(t - 1) * B * 4 * U;
         ep.c_cur = w->c + (long long)(t - 1) * BU;
         ep.c_prev = t - 1 > 0 ? w->c + (long long)(t - 2) * BU : nullptr;
         ep.dc_io = w->dc;
         tc_gemm_run_lstm(w->g_bwd, t, 0, 0, ep, s);
       } else {
-        if (w->g_bwd) tc_gemm_run(w->g_bwd, t, 0, 0, s);  // dH_{t-1} = dZ_t . Wr_cat^T
-        else gemm_nt(a, w->wr_cat, w->dh, B, U, 4 * U, e->ws, e->ws_floats, s);
         dh = w->dh;
+        dh_parts = 1;
+        if (w->g_bwd && tc_gemm_is_split(w->g_bwd) && w->bwd_fold) dh_parts = tc_gemm_run_partials(w->g_bwd, t, 0, s, &dh);  // summed by the gate kernel
+        else if (w->g_bwd) tc_gemm_run(w->g_bwd, t, 0, 0, s);  // dH_{t-1} = dZ_t . Wr_cat^T
+        else gemm_nt(a, w->wr_cat, w->dh, B, U, 4 * U, e->ws, e->ws_floats, s);
       }
     }
   }

@@ -29,12 +29,15 @@ TcGemm* tc_gemm_create(int a_mn_major, int b_mn_major, const float* A, int a_sli
 void tc_gemm_set_epilogue(TcGemm* g, const float* bias, int act, float thr);
 bool tc_gemm_is_split(const TcGemm* g);
 void tc_gemm_run(TcGemm* g, int za, int zb, int zc, cudaStream_t s);
+// split-K plans (tc_gemm_is_split): launch without the reduction; returns the number of partials [splits][M*N] left in the workspace
+int tc_gemm_run_partials(TcGemm* g, int za, int zb, cudaStream_t s, const float** partial);
 // LSTM pointwise work fused into the GEMM epilogue (columns are unit-interleaved: col = 4*unit + gate, csrc/lstm.cu):
 //  mode 1 (forward, C = Z_t = H_{t-1}.Wr_cat): z += x_t.Wk_cat + b ; activations written to C in place of z ; c_t, h_t stored
 //  mode 2 (backward, C = dH_{t-1} = dZ_t.Wr_cat^T, not stored): the gate backward of step t-1 -> dZ_{t-1} in place of acts_{t-1}
 struct LstmEpi {
   int mode;
   int F, U, act, ract, has_bias;
+  int fast;             // approximate exp / reciprocal in the activations (TF32 mode; the same forms as lstm.cu actf_t)
   const float* x_t;     // [B, F]   (mode 1)
   const float* wk_cat;  // [F, 4U]
   const float* b_cat;   // [4U]

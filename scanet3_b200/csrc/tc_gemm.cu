@@ -109,6 +109,15 @@ __device__ __forceinline__ float lstm_actg(float g, float y, int act) {
     default: return g;
   }
 }
+// TF32 mode: the approximate forms of lstm.cu actf_t (ex2.approx / rcp.approx)
+__device__ __forceinline__ float lstm_actf_fast(float x, int act) {
+  switch (act) {
+    case 1: return __fdividef(1.f, 1.f + __expf(-x));
+    case 2: return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x));
+    case 4: return fmaxf(0.f, x);
+    default: return x;
+  }
+}
 // v[32] = z of row b, columns col0..col0+31 = units col0/4 .. col0/4+7 (4 gates each): becomes the activations
 __device__ __forceinline__ void lstm_epi_fwd(float* v, long long b, int col0, const LstmEpi& le) {
   const int j0 = col0 >> 2;
@@ -125,11 +134,11 @@ __device__ __forceinline__ void lstm_epi_fwd(float* v, long long b, int col0, co
       for (int f = 0; f < le.F; ++f) xp = fmaf(__ldg(le.x_t + b * le.F + f), __ldg(le.wk_cat + (long long)f * 4 * le.U + col), xp);
       float z = __fadd_rn(xp, v[4 * u + g]);                    // (x.Wk + h.Wr)
       if (le.has_bias) z = __fadd_rn(z, __ldg(le.b_cat + col));  // + b
-      a[g] = lstm_actf(z, g == 2 ? le.act : le.ract);
+      a[g] = le.fast ? lstm_actf_fast(z, g == 2 ? le.act : le.ract) : lstm_actf(z, g == 2 ? le.act : le.ract);
       v[4 * u + g] = a[g];
     }
     cn[u] = __fadd_rn(__fmul_rn(cp[u], a[0]), __fmul_rn(a[1], a[2]));  // c_prev*f + i*g
-    hn[u] = __fmul_rn(a[3], lstm_actf(cn[u], le.act));                   // o * act(c)
+    hn[u] = __fmul_rn(a[3], le.fast ? lstm_actf_fast(cn[u], le.act) : lstm_actf(cn[u], le.act));  // o * act(c)
   }
   *reinterpret_cast<float4*>(le.c_out + b * le.U + j0) = *reinterpret_cast<float4*>(cn);
   *reinterpret_cast<float4*>(le.c_out + b * le.U + j0 + 4) = *reinterpret_cast<float4*>(cn + 4);
@@ -144,7 +153,7 @@ __device__ __forceinline__ void lstm_epi_bwd(const float* v, long long b, int j0
     float4* q = reinterpret_cast<float4*>(le.acts_dz + b * 4 * le.U + 4 * (j0 + u));
     const float4 a4 = *q;
     const float f = a4.x, ig = a4.y, g = a4.z, o = a4.w;
-    const float ac = lstm_actf(le.c_cur[i], le.act);
+    const float ac = le.fast ? lstm_actf_fast(le.c_cur[i], le.act) : lstm_actf(le.c_cur[i], le.act);
     const float dhv = v[u];
     const float d_o = __fmul_rn(dhv, ac);
     const float dc = __fadd_rn(lstm_actg(__fmul_rn(dhv, o), ac, le.act), le.dc_io[i]);
@@ -506,6 +515,16 @@ void tc_gemm_run(TcGemm* g, int za, int zb, int zc, cudaStream_t s) {
   launch_k(gemm_tf32_kernel, g->grid, p.x3 ? kGemmThreadsX3 : kGemmThreads, g->smem, s, g->map_a, g->map_b, g->map_c, p);
   SB_LAUNCHED();
   if (p.splits > 1) partial_reduce(g->partial, g->c + (long long)zc * g->c_slice, p.M * p.N, p.splits, s);
+}
+
+// split-K plans only: the partial products stay in the workspace ([splits][M*N], to be summed in split order by the consumer)
+int tc_gemm_run_partials(TcGemm* g, int za, int zb, cudaStream_t s, const float** partial) {
+  GemmParams p = g->p;
+  p.za = za; p.zb = zb; p.zc = 0;
+  launch_k(gemm_tf32_kernel, g->grid, p.x3 ? kGemmThreadsX3 : kGemmThreads, g->smem, s, g->map_a, g->map_b, g->map_c, p);
+  SB_LAUNCHED();
+  *partial = g->partial;
+  return p.splits;
 }
 
 void tc_gemm_run_lstm(TcGemm* g, int za, int zb, int zc, const LstmEpi& epi, cudaStream_t s) {
