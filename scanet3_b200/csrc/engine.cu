@@ -957,7 +957,8 @@ static void run_backward(sb_engine* e) {
           const bool fork = fork_enabled() && !e->profiling;
           Prof pr(e, "dense_head_wgrad", db, 2.0 * M * N * K);
           if (fork) side_branch_begin(e);
-          wdone = ddone = dense_head_bwd(in, dout, P(e, L.p_w), G(e, L.p_w), nullptr, M, N, K, e->ws_side, e->ws_side_floats,
+          wdone = ddone = tc_head_bwd(e, L, in, dout, P(e, L.p_w), G(e, L.p_w), nullptr, fork ? e->bstream : s) ||
+                          dense_head_bwd(in, dout, P(e, L.p_w), G(e, L.p_w), nullptr, M, N, K, e->ws_side, e->ws_side_floats,
                                          fork ? e->bstream : s);
           if (fork) side_branch_end(e);
           if (!wdone) SB_FAIL(SB_ERR_CUDA, "dense_head_bwd rejected a planned shape");
@@ -966,7 +967,8 @@ static void run_backward(sb_engine* e) {
         if (L.fast_skinny && !wdone) {
           const bool dg = L.need_dx && din;
           Prof pr(e, "dense_head_bwd", db + (dg ? 4.0 * M * K : 0.0), (dg ? 4.0 : 2.0) * M * N * K);
-          wdone = ddone = dense_head_bwd(in, dout, P(e, L.p_w), G(e, L.p_w), dg ? din : nullptr, M, N, K, e->ws, e->ws_floats, s);
+          wdone = ddone = tc_head_bwd(e, L, in, dout, P(e, L.p_w), G(e, L.p_w), dg ? din : nullptr, s) ||
+                          dense_head_bwd(in, dout, P(e, L.p_w), G(e, L.p_w), dg ? din : nullptr, M, N, K, e->ws, e->ws_floats, s);
         }
         if (!wdone) {
           Prof pr(e, "dense_wgrad_f32", db, 2.0 * M * N * K);

@@ -81,6 +81,7 @@ struct LayerPlan {
   int tc_kind = 0;                // 0 none, otherwise a tcgen05 kernel variant
   void* tc_plan = nullptr;        // opaque plan of the tensor-core path (TMA descriptors, buffers)
   void* head_tc = nullptr;        // opaque plan of the tensor-core classifier-head forward (tc.cu)
+  void* head_bwd_tc = nullptr;    // ... and of its backward (dW and dX in one kernel)
   void* lstm = nullptr;           // opaque LSTM workspace
 };
 

@@ -10,7 +10,7 @@
 //   (release add after the h stores; the TMA producer polls it with acquire loads and a generic->async proxy fence before it
 //   issues the loads).  All B/128 x 4U/64 CTAs (128 for cfg3) are co-resident (one per SM; the launcher refuses grids > 148),
 //   every wait is bounded (trap instead of a hang).
-//   Numerics: the same expressions, in the same order, as lstm_gates_fwd_kernel; the recurrent product in TF32.
+//   Numerics: the same expressions, in the same order, as lstm_gates_fwd_kernel<.., true> (TF32 mode); the recurrent product in TF32.
 #include <stdlib.h>
 #include <string.h>
 
@@ -46,13 +46,20 @@ struct LstmPersistParams {
   unsigned long long* dbg; // developer timeline of the cluster form (SB_LC_TIMELINE=1): [T][8] %globaltimer stamps of CTA 0, else null
 };
 
+// the TF32-mode forms of lstm.cu actf_t<true> (ex2.approx / rcp.approx): these kernels run in TF32 mode only
 __device__ __forceinline__ float lp_act(float x, int act) {
   switch (act) {
-    case 1: return __fdiv_rn(1.f, __fadd_rn(1.f, expf(-x)));
-    case 2: return tanhf(x);
+    case 1: return __fdividef(1.f, 1.f + __expf(-x));
+    case 2: return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x));
     case 4: return fmaxf(0.f, x);
     default: return x;
   }
+}
+// h is stored rounded to the nearest tf32 value, as lstm_gates_fwd_kernel<.., true> does (lstm.cu tf32_rn): these kernels run in TF32 mode only
+__device__ __forceinline__ float lp_tf32_rn(float x) {
+  unsigned u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
 }
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   unsigned int v;
@@ -212,7 +219,7 @@ lstm_persist_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_
         *reinterpret_cast<float4*>(arow + 4 * j) = make_float4(a[0], a[1], a[2], a[3]);
         const float cn = __fadd_rn(__fmul_rn(cst[j], a[0]), __fmul_rn(a[1], a[2]));   // c_prev*f + i*g
         cst[j] = cn;
-        hq[j] = __fmul_rn(a[3], lp_act(cn, p.act));                                    // o * act(c)
+        hq[j] = lp_tf32_rn(__fmul_rn(a[3], lp_act(cn, p.act)));                                    // o * act(c)
       }
       float* crow = p.c + ((size_t)t * p.B + row) * p.U + u0;
       float* hrow = p.h + ((size_t)(t + 1) * p.B + row) * p.U + u0;
@@ -443,7 +450,7 @@ lstm_cluster_fwd_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_
           *reinterpret_cast<float4*>(arow + 4 * j) = make_float4(a[0], a[1], a[2], a[3]);
           const float cn = __fadd_rn(__fmul_rn(cst[j], a[0]), __fmul_rn(a[1], a[2]));   // c_prev*f + i*g
           cst[j] = cn;
-          hq[j] = __fmul_rn(a[3], lp_act(cn, p.act));                                    // o * act(c)
+          hq[j] = lp_tf32_rn(__fmul_rn(a[3], lp_act(cn, p.act)));                                    // o * act(c)
         }
         float* crow = p.c + ((size_t)t * p.B + row) * p.U + u0;
         float* hrow = p.h + ((size_t)(t + 1) * p.B + row) * p.U + u0;

@@ -1550,9 +1550,11 @@ void tc_plan_layers(sb_engine* e) {
 }
 
 static void head_tc_free(LayerPlan& L);  // defined with the kernel below
+static void head_bwd_tc_free(LayerPlan& L);
 void tc_free_layers(sb_engine* e) {
   for (auto& L : e->L) {
     head_tc_free(L);
+    head_bwd_tc_free(L);
     if (L.tc_plan && L.tc_kind == 2) {
       DenseTcPlan* D = (DenseTcPlan*)L.tc_plan;
       tc_gemm_destroy(D->fwd); tc_gemm_destroy(D->wgrad); tc_gemm_destroy(D->dgrad);
@@ -1807,6 +1809,175 @@ bool tc_head_fwd(sb_engine* e, LayerPlan& L, const float* x, const float* w, flo
   launch_k(head_fwd_tc_kernel, P->p.chunks, kHeadTcThreads, P->smem, e->stream, P->map_x, P->p);
   SB_LAUNCHED();
   *chunks_out = P->p.chunks;
+  return true;
+}
+
+// =====================================================================================================================
+// Skinny classifier head BACKWARD on the tensor cores (TF32 mode, M <= 128 rows, N <= 16 outputs, K % 128 == 0):
+//     dW[k][n] = sum_m X[m][k] G[m][n]          dX[m][k] = sum_n G[m][n] W[k][n]
+// CTA c owns the 128 k columns [128c, 128c + 128).  The FFMA kernel (kernels_fast.cu dense_head_bwd_kernel) issues ~40 instructions
+// per (row, two columns) on 13 warps per SM (18.8 us on cfg2: issue-bound at 20 % occupancy); here
+//   * dW tile D1[M = 128 k, N = 16] : A = the X tile straight from memory, MN-major (k contiguous), four TMA boxes [32 k x MP rows]
+//     (MP = M rounded up to 8; rows >= M are TMA zero fill), K dimension = the batch rows; B = G^T written by the threads in the
+//     K-major SWIZZLE_128B layout (row n, 16-byte chunk ((m % 32) / 4) ^ (n % 8));  MP/8 MMAs.
+//   * dX tile D2[M = 128 rows, N = 128 k] : A = G, B = the W slab [128 k x 16 n], both K-major and written by the threads
+//     (row pitches of N * 4 bytes are not TMA-able);  two MMAs -- issued first, they do not wait for the X tile.
+//   X is read once by TMA, dX written once as 512-byte row pieces, dW as one contiguous slab: the kernel is bound by those bytes.
+// =====================================================================================================================
+struct HeadBwdParams {
+  int M, MP, K, N;
+  int prewait;
+  const float* g;   // [M, N]
+  const float* w;   // [K, N]
+  float* dw;        // [K, N]
+  float* dx;        // [M, K] or null
+};
+constexpr int kHeadBwdThreads = 192;
+
+__global__ void __launch_bounds__(kHeadBwdThreads, 2) head_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const HeadBwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int box_bytes = p.MP * 128;                       // one [32 k x MP rows] box of X
+  const int a_bytes = ((4 * box_bytes + 1023) / 1024) * 1024;
+  uint8_t* sm_x = smem;                                   // 4 boxes, MN-major (SWIZZLE_128B_ATOM_32B)
+  uint8_t* sm_gt = sm_x + a_bytes;                        // G^T : 4 tiles of [16 rows n x 128 B (32 m)]
+  uint8_t* sm_g = sm_gt + 4 * 2048;                       // G   : [128 rows m x 128 B (n)]
+  uint8_t* sm_w = sm_g + 16384;                           // W   : [128 rows k x 128 B (n)]
+  uint64_t* x_bar = (uint64_t*)(sm_w + 16384);
+  uint64_t* done_bar = x_bar + 1;
+  uint32_t* tmem_slot = (uint32_t*)(done_bar + 1);
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * 128;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_x);
+    mbar_init(x_bar, 1);
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {  // two allocations (128 + 32 columns, not one of 256): two CTAs per SM leave TMEM for an overlapping dependent kernel
+    tmem_alloc_keep_permit(tmem_slot, 128);  // dX tile
+    tmem_alloc(tmem_slot + 1, 32);   // dW tile
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot[0], tmem_dw = tmem_slot[1];
+  // the W slab may be staged before the dependency wait when the kernel launched just before does not write weights
+  auto stage_w = [&]() {
+    for (int i = threadIdx.x; i < 128 * 16; i += blockDim.x) {
+      const int n = i & 15, k = i >> 4;
+      const float v = n < p.N ? __ldg(p.w + (size_t)(k0 + k) * p.N + n) : 0.f;
+      *reinterpret_cast<float*>(sm_w + k * 128 + ((((n >> 2) ^ (k & 7)) << 4) | ((n & 3) << 2))) = v;
+    }
+  };
+  if (p.prewait) stage_w();
+  pdl_wait();
+  pdl_trigger();
+  if (threadIdx.x == 0) {  // the X tile: rows >= M of every box are zero fill
+    mbar_arrive_expect_tx(x_bar, (uint32_t)(4 * box_bytes));
+    for (int j = 0; j < 4; ++j) tma_load_2d(sm_x + (size_t)j * box_bytes, &map_x, x_bar, k0 + j * 32, 0);
+  }
+  if (!p.prewait) stage_w();
+  for (int i = threadIdx.x; i < 128 * 16; i += blockDim.x) {
+    const int n = i & 15, m = i >> 4;
+    const float v = (m < p.M && n < p.N) ? __ldg(p.g + (size_t)m * p.N + n) : 0.f;
+    *reinterpret_cast<float*>(sm_g + m * 128 + ((((n >> 2) ^ (m & 7)) << 4) | ((n & 3) << 2))) = v;                 // G   (row m, n along K)
+    const int t = m >> 5, mm = m & 31;
+    *reinterpret_cast<float*>(sm_gt + (size_t)t * 2048 + n * 128 + ((((mm >> 2) ^ (n & 7)) << 4) | ((mm & 3) << 2))) = v;  // G^T (row n, m along K)
+  }
+  fence_proxy_async();
+  __syncthreads();
+  if (warp == 1) {
+    const uint64_t kd = smem_desc_sw128(0, 16, 1024);                      // K-major operands
+    const uint32_t k_hi = (uint32_t)(kd >> 32), k_lo = (uint32_t)kd;
+    const uint64_t xd = smem_desc(0, (uint32_t)box_bytes, 512, 1);         // MN-major X: 32-column groups one box apart
+    const uint32_t x_hi = (uint32_t)(xd >> 32), x_lo = (uint32_t)xd;
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0), tmem_w = __shfl_sync(0xffffffffu, tmem_dw, 0);
+    const uint32_t g0 = k_lo + ((smem_u32(sm_g) >> 4) & 0x3FFFu), w0 = k_lo + ((smem_u32(sm_w) >> 4) & 0x3FFFu);
+    const uint32_t gt0 = k_lo + ((smem_u32(sm_gt) >> 4) & 0x3FFFu), x0 = x_lo + ((smem_u32(sm_x) >> 4) & 0x3FFFu);
+    if (p.dx) {  // dX tile: D2[128 m, 128 k] = G[128, 16] . W_tile^T -- operands staged by the threads, no wait for TMA
+      const uint32_t idesc2 = idesc_tf32(128, 128, 0, 0);
+      umma_tf32_elect(tmem_u, ((uint64_t)k_hi << 32) | g0, ((uint64_t)k_hi << 32) | w0, idesc2, 0u);
+      umma_tf32_elect(tmem_u, ((uint64_t)k_hi << 32) | (g0 + 2), ((uint64_t)k_hi << 32) | (w0 + 2), idesc2, 1u);
+    }
+    mbar_wait(x_bar, 0);
+    tc_fence_after();
+    const uint32_t idesc1 = idesc_tf32(128, 16, 1, 0);
+    const int steps = p.MP / 8;
+    for (int sidx = 0; sidx < steps; ++sidx)  // 8 batch rows per MMA: A rows are 128 B apart inside a box, B tiles hold 32 rows each
+      umma_tf32_elect(tmem_w, ((uint64_t)x_hi << 32) | (x0 + sidx * 64),
+                      ((uint64_t)k_hi << 32) | (gt0 + (sidx >> 2) * 128 + (sidx & 3) * 2), idesc1, sidx ? 1u : 0u);
+    umma_commit_elect(done_bar);
+  } else if (warp >= 2) {
+    const int sub = warp & 3, row = sub * 32 + lane;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    float v[32];
+    // dW: TMEM lane = k column of the tile
+    tmem_ld32(tmem_dw + ((uint32_t)(sub * 32) << 16), v);
+    tmem_ld_wait();
+    {
+      float* o = p.dw + (size_t)(k0 + row) * p.N;
+#pragma unroll
+      for (int n = 0; n < 16; ++n)
+        if (n < p.N) o[n] = v[n];
+    }
+    if (p.dx) {  // dX: TMEM lane = batch row
+      float* o = p.dx + (size_t)row * p.K + k0;
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (row < p.M) {
+#pragma unroll
+          for (int q = 0; q < 32; q += 4) *reinterpret_cast<float4*>(o + c0 + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 128);
+    tmem_dealloc(tmem_dw, 32);
+  }
+}
+
+struct HeadBwdTcPlan {
+  CUtensorMap map_x;
+  HeadBwdParams p;
+  const float* x;
+  int smem;
+};
+
+static void head_bwd_tc_free(LayerPlan& L) {
+  delete (HeadBwdTcPlan*)L.head_bwd_tc;
+  L.head_bwd_tc = nullptr;
+}
+
+// false: shape / mode not covered (the caller runs dense_head_bwd)
+bool tc_head_bwd(sb_engine* e, LayerPlan& L, const float* x, const float* g, const float* w, float* dw, float* dx, cudaStream_t st) {
+  const char* off = getenv("SB_TC_HEAD_BWD");  // =0: the FFMA kernel (read per call: the A/B test flips it inside one process)
+  if ((off && off[0] == '0') || e->train.precision != SB_PREC_TF32) return false;
+  const int M = (int)L.in.d[0], K = (int)L.in.d[1], N = (int)L.out.d[1];
+  if (M > 128 || N > 16 || (K % 128) || K < 128 * kNumSMs || (((uintptr_t)x) & 127) || (dx && (((uintptr_t)dx) & 15))) return false;
+  HeadBwdTcPlan* P = (HeadBwdTcPlan*)L.head_bwd_tc;
+  if (!P || P->x != x) {
+    delete P;
+    P = new HeadBwdTcPlan();
+    P->p.M = M; P->p.MP = (M + 7) / 8 * 8; P->p.K = K; P->p.N = N;
+    uint64_t xd[2] = {(uint64_t)K, (uint64_t)M};
+    uint32_t xb[2] = {32, (uint32_t)P->p.MP};
+    P->map_x = make_map(x, 2, xd, xb, true);
+    P->x = x;
+    P->smem = ((4 * P->p.MP * 128 + 1023) / 1024) * 1024 + 4 * 2048 + 2 * 16384 + 64 + 1024;
+    SB_CUDA(cudaFuncSetAttribute(head_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P->smem));
+    L.head_bwd_tc = P;
+  }
+  P->p.g = g; P->p.w = w; P->p.dw = dw; P->p.dx = dx;
+  P->p.prewait = prewait_ok();
+  launch_k(head_bwd_tc_kernel, K / 128, kHeadBwdThreads, P->smem, st, P->map_x, P->p);
+  SB_LAUNCHED();
   return true;
 }
 

@@ -16,6 +16,8 @@ bool tc_dense_wgrad(sb_engine* e, LayerPlan& L, int li);
 bool tc_dense_dgrad(sb_engine* e, LayerPlan& L, int li);
 // skinny classifier head Z[M<=128, N<=16] = X[M,K] . W[K,N] as split-K partials[chunks][M][N] on tcgen05 (TF32 mode, K % 32 == 0)
 bool tc_head_fwd(sb_engine* e, LayerPlan& L, const float* x, const float* w, float* partial, size_t partial_floats, int* chunks_out);
+// its backward: dW[K,N] = X^T . G and (dx != null) dX[M,K] = G . W^T in one kernel (TF32 mode, M <= 128, K % 128 == 0)
+bool tc_head_bwd(sb_engine* e, LayerPlan& L, const float* x, const float* g, const float* w, float* dw, float* dx, cudaStream_t st);
 bool tc_conv_fwd(sb_engine* e, LayerPlan& L, int li);
 bool tc_conv_wgrad(sb_engine* e, LayerPlan& L, int li, cudaStream_t side = nullptr, ReduceBatch* defer = nullptr);  // s: side stream (null = the engine's)
 bool tc_conv_dgrad(sb_engine* e, LayerPlan& L, int li);

@@ -139,6 +139,7 @@ __device__ __forceinline__ void lstm_epi_fwd(float* v, long long b, int col0, co
     }
     cn[u] = __fadd_rn(__fmul_rn(cp[u], a[0]), __fmul_rn(a[1], a[2]));  // c_prev*f + i*g
     hn[u] = __fmul_rn(a[3], le.fast ? lstm_actf_fast(cn[u], le.act) : lstm_actf(cn[u], le.act));  // o * act(c)
+    if (le.fast) { unsigned r_; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r_) : "f"(hn[u])); hn[u] = __uint_as_float(r_); }  // lstm.cu tf32_rn
   }
   *reinterpret_cast<float4*>(le.c_out + b * le.U + j0) = *reinterpret_cast<float4*>(cn);
   *reinterpret_cast<float4*>(le.c_out + b * le.U + j0 + 4) = *reinterpret_cast<float4*>(cn + 4);

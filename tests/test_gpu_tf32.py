@@ -356,6 +356,29 @@ def test_3xtf32_lenet_config2_full_size_trajectory():
     e.close()
 
 
+@pytest.mark.parametrize("batch", [100, 37, 128])
+def test_tensor_core_head_backward_matches_the_ffma_kernel(batch, monkeypatch):
+    """csrc/tc.cu head_bwd_tc_kernel (TF32 mode, the config-2 head: 36864 -> 10): dW = X^T . G and dX = G . W^T on tcgen05, X tile by
+    TMA as an MN-major operand (batch rows = the K dimension, rows past the batch are TMA zero fill), G / G^T / W written by the
+    threads in the K-major swizzled layout.  Against SB_TC_HEAD_BWD=0 (the FFMA kernel): same forward, so the same loss; every
+    gradient within tf32 rounding of the FFMA one (the head's inputs are post-ReLU pool outputs, its gradient feeds conv2/conv1)."""
+    spec = [("conv", 32, "relu", (3, 3), (1, 1), "Valid", False), ("pool", (2, 2), (1, 1), "Valid"),
+            ("conv", 64, "relu", (3, 3), (1, 1), "Valid", False), ("pool", (2, 2), (1, 1), "Valid"), ("flatten",), ("dense", 10, "softmax")]
+    _, sm = build_models(spec)
+    x, y = synth_classification(batch, (28, 28, 1), 10, 5)
+    res = []
+    for on in ("0", "1"):
+        monkeypatch.setenv("SB_TC_HEAD_BWD", on)
+        e = S.Engine(sm, S.CategoricalCrossentropy, S.Adam(1e-3), batch, (28, 28, 1), (10,), device=0, precision=S.PREC_TF32)
+        e.init_params()
+        res.append(e.compute_grads(x, y))
+        e.close()
+    (l0, g0), (l1, g1) = res
+    assert l0 == l1
+    for k in g0:
+        assert rel_to_max(g1[k], g0[k]) < 3e-3, (k, rel_to_max(g1[k], g0[k]))
+
+
 def test_persistent_lstm_time_loop_matches_the_per_step_path(monkeypatch):
     """csrc/lstm_persist.cu (opt-in, SB_LSTM_PERSIST=1): one launch walks all T forward steps with the recurrent weights resident in
     shared memory and a row-block step barrier.  Same TF32 products, same gate expressions as the per-step GEMM + gate kernels:

@@ -25,5 +25,3 @@ for s in range(t):
     ds = d[:, s, :]
     print(f"step {s}: max {ds.max():.3e}; bad rows {np.nonzero(ds.max(axis=1) > 1e-5)[0].tolist()[:70]}")
     print(f"         bad units by chunk of 32: {[int((ds[:, c*32:(c+1)*32].max() > 1e-5)) for c in range(8)]}  per-unit-in-chunk: {np.nonzero(ds.max(axis=0) > 1e-5)[0].tolist()[:40]}")
-# how does the cluster result relate to the reference: h1 computed from a PARTIAL h0?  (regress p2[:,1] onto p0)
-np.save(os.path.join(ROOT, "gpurun_out", "lc_p0.npy"), p0); np.save(os.path.join(ROOT, "gpurun_out", "lc_p2.npy"), p2)
