@@ -106,6 +106,17 @@ inline void launch_k(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t 
   cfg.numAttrs = 1;
   SB_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<A&&>(args)...));
   set_prewait_ok(1);
+  // developer aid (SB_SYNC_DEBUG=1, eager mode only): wait for every kernel and name the one that faults
+  static const bool sync_debug = [] { const char* v = getenv("SB_SYNC_DEBUG"); return v && v[0] == '1'; }();
+  if (sync_debug) {
+    const cudaError_t err = cudaStreamSynchronize(s);
+    if (err != cudaSuccess) {
+      const char* name = "?";
+      cudaFuncGetName(&name, (const void*)kernel);
+      fprintf(stderr, "[sb] SB_SYNC_DEBUG: %s after kernel %s grid (%u,%u,%u) block (%u,%u,%u) smem %zu\n", cudaGetErrorString(err), name, grid.x,
+              grid.y, grid.z, block.x, block.y, block.z, smem);
+    }
+  }
 }
 #endif
 

@@ -1421,8 +1421,7 @@ void tc_plan_layers(sb_engine* e) {
       const int n_slices = ((taps + tpp - 1) / tpp) * (g.Cout / Mh);
       const int full_grid = std::min(p.n_chunks, kNumSMs);  // what the halo kernel below would use
       P->wg_grid = n_slices <= kWgradMaxSlices ? std::max(1, std::min(p.n_chunks, kNumSMs / n_slices)) : full_grid;  // the K split
-      SB_CUDA(cudaMalloc((void**)&P->wg_partial, (size_t)full_grid * taps * g.Cin * g.Cout * sizeof(float)));
-      p.partial = P->wg_partial;
+      (void)full_grid;  // the partial buffer is allocated below, once the halo form's grid is known too
       p.nt_max = tpp;
       {
         const int stage_bytes = (x3 ? 2 : 1) * (((p.BH * (Mh / 32 + tpp * (g.Cin / 32)) * box_row_bytes + 1023) / 1024) * 1024);
@@ -1507,7 +1506,6 @@ void tc_plan_layers(sb_engine* e) {
           P->hwg_slices = n_slices;
           P->hwg_smem = p.stages * stage_bytes + 16 * (2 * p.stages + 2) + 16 + 1024;
           if (P->hwg_smem <= dev_smem) {  // the partial buffer is sized for min(n_chunks, SMs) CTAs
-            p.partial = P->wg_partial;
             uint64_t yd[4] = {(uint64_t)g.Cout, (uint64_t)g.OW, (uint64_t)g.OH, (uint64_t)g.N};
             uint32_t yb[4] = {32, (uint32_t)p.P, (uint32_t)p.BH, 1};
             P->map_dy_hwg = make_map(dy, 4, yd, yb, true);
@@ -1522,9 +1520,17 @@ void tc_plan_layers(sb_engine* e) {
       }
     }
     if (P->fwd_smem > dev_smem || P->dg_smem > dev_smem) {
-      cudaFree(P->wg_partial);
       delete P;
       continue;
+    }
+    if (P->wg_ok) {
+      // one partial filter gradient per K split: the per-tap kernel writes wg_grid of them, the halo form hwg_grid (its chunks are cut
+      // differently, so it can have MORE of them than the per-tap kernel)
+      const int parts = std::max(P->wg_grid, P->halo_wg ? P->hwg_grid : 0);
+      SB_CUDA(cudaMalloc((void**)&P->wg_partial, (size_t)parts * taps * g.Cin * g.Cout * sizeof(float)));
+      for (WgradParams& q : P->wg_list) q.partial = P->wg_partial;
+      P->wg.partial = P->wg_partial;
+      P->hwg.partial = P->wg_partial;
     }
     L.tc_kind = 1;
     L.tc_plan = P;
@@ -1862,14 +1868,33 @@ __global__ void __launch_bounds__(kHeadBwdThreads, 2) head_bwd_tc_kernel(const _
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot[0], tmem_dw = tmem_slot[1];
-  // the W slab may be staged before the dependency wait when the kernel launched just before does not write weights
-  auto stage_w = [&]() {
-    for (int i = threadIdx.x; i < 128 * 16; i += blockDim.x) {
-      const int n = i & 15, k = i >> 4;
-      const float v = n < p.N ? __ldg(p.w + (size_t)(k0 + k) * p.N + n) : 0.f;
-      *reinterpret_cast<float*>(sm_w + k * 128 + ((((n >> 2) ^ (k & 7)) << 4) | ((n & 3) << 2))) = v;
+  // Staging of the thread-written operands.  The sources are CONTIGUOUS in memory (128 rows of W, M rows of G, N floats each), so
+  // the threads walk them linearly with every load in flight (fixed trip counts, unrolled) and scatter into the swizzled layouts;
+  // the padding (n >= N, m >= M) comes from zero-filling the three areas first.
+  const unsigned div_n = (65536u + p.N - 1) / p.N;  // i / N == (i * div_n) >> 16 for i < 128 * 16
+  {
+    float4* z = reinterpret_cast<float4*>(sm_gt);
+    for (int i = threadIdx.x; i < (4 * 2048 + 2 * 16384) / 16; i += blockDim.x) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  auto stage_w = [&]() {  // element (k, n) -> row k, 16-byte chunk (n / 4) ^ (k % 8), word n % 4
+    const int total = 128 * p.N;
+    float v[11];
+#pragma unroll
+    for (int it = 0; it < 11; ++it) {
+      const int i = threadIdx.x + it * kHeadBwdThreads;
+      v[it] = i < total ? __ldg(p.w + (size_t)k0 * p.N + i) : 0.f;
+    }
+#pragma unroll
+    for (int it = 0; it < 11; ++it) {
+      const int i = threadIdx.x + it * kHeadBwdThreads;
+      if (i < total) {
+        const int k = (int)(((unsigned)i * div_n) >> 16), n = i - k * p.N;
+        *reinterpret_cast<float*>(sm_w + k * 128 + ((((n >> 2) ^ (k & 7)) << 4) | ((n & 3) << 2))) = v[it];
+      }
     }
   };
+  // the W slab may be staged before the dependency wait when the kernel launched just before does not write weights
   if (p.prewait) stage_w();
   pdl_wait();
   pdl_trigger();
@@ -1878,12 +1903,24 @@ __global__ void __launch_bounds__(kHeadBwdThreads, 2) head_bwd_tc_kernel(const _
     for (int j = 0; j < 4; ++j) tma_load_2d(sm_x + (size_t)j * box_bytes, &map_x, x_bar, k0 + j * 32, 0);
   }
   if (!p.prewait) stage_w();
-  for (int i = threadIdx.x; i < 128 * 16; i += blockDim.x) {
-    const int n = i & 15, m = i >> 4;
-    const float v = (m < p.M && n < p.N) ? __ldg(p.g + (size_t)m * p.N + n) : 0.f;
-    *reinterpret_cast<float*>(sm_g + m * 128 + ((((n >> 2) ^ (m & 7)) << 4) | ((n & 3) << 2))) = v;                 // G   (row m, n along K)
-    const int t = m >> 5, mm = m & 31;
-    *reinterpret_cast<float*>(sm_gt + (size_t)t * 2048 + n * 128 + ((((mm >> 2) ^ (n & 7)) << 4) | ((mm & 3) << 2))) = v;  // G^T (row n, m along K)
+  {
+    const int total = p.M * p.N;
+    float v[11];
+#pragma unroll
+    for (int it = 0; it < 11; ++it) {
+      const int i = threadIdx.x + it * kHeadBwdThreads;
+      v[it] = i < total ? __ldg(p.g + i) : 0.f;
+    }
+#pragma unroll
+    for (int it = 0; it < 11; ++it) {
+      const int i = threadIdx.x + it * kHeadBwdThreads;
+      if (i < total) {
+        const int m = (int)(((unsigned)i * div_n) >> 16), n = i - m * p.N;
+        *reinterpret_cast<float*>(sm_g + m * 128 + ((((n >> 2) ^ (m & 7)) << 4) | ((n & 3) << 2))) = v[it];                 // G   (row m, n along K)
+        const int t = m >> 5, mm = m & 31;
+        *reinterpret_cast<float*>(sm_gt + (size_t)t * 2048 + n * 128 + ((((mm >> 2) ^ (n & 7)) << 4) | ((mm & 3) << 2))) = v[it];  // G^T (row n, m along K)
+      }
+    }
   }
   fence_proxy_async();
   __syncthreads();
