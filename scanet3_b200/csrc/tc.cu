@@ -1994,8 +1994,13 @@ static void head_bwd_tc_free(LayerPlan& L) {
 
 // false: shape / mode not covered (the caller runs dense_head_bwd)
 bool tc_head_bwd(sb_engine* e, LayerPlan& L, const float* x, const float* g, const float* w, float* dw, float* dx, cudaStream_t st) {
-  const char* off = getenv("SB_TC_HEAD_BWD");  // =0: the FFMA kernel (read per call: the A/B test flips it inside one process)
-  if ((off && off[0] == '0') || e->train.precision != SB_PREC_TF32) return false;
+  // OPT-IN (SB_TC_HEAD_BWD=1; read per call: the A/B test flips it inside one process).  Measured on cfg2 (batch 100, K = 30976): the
+  // same ~10.5 us from this kernel's start to the next kernel's start as the FFMA kernel inside the replayed step (91.86 vs 91.89 us
+  // per step), 16.4 vs 19.6 us under ncu with a cold L2 -- its lifetime is a chain of latencies (operand staging, the X tile, 32
+  // row-strided 16-byte stores per thread), not the 40 instructions per element it removes, and it adds tf32 rounding to the head's
+  // gradients; so the FFMA kernel stays the default (profiles/r2_notes.md 14).
+  const char* on = getenv("SB_TC_HEAD_BWD");
+  if (!(on && on[0] == '1') || e->train.precision != SB_PREC_TF32) return false;
   const int M = (int)L.in.d[0], K = (int)L.in.d[1], N = (int)L.out.d[1];
   if (M > 128 || N > 16 || (K % 128) || K < 128 * kNumSMs || (((uintptr_t)x) & 127) || (dx && (((uintptr_t)dx) & 15))) return false;
   HeadBwdTcPlan* P = (HeadBwdTcPlan*)L.head_bwd_tc;
