@@ -340,6 +340,9 @@ struct HaloParams {
   // fetches A once per kernel row instead of once per tap: 36 MMAs x 48 cycles -> 12 x 96 (fprop, N = 192, now math-bound), 72 x 40
   // -> 24 x 56 (dgrad, N = 96).
   int fold;
+  // Output-channel slices (fprop, filters too large to stay resident whole): gridDim.y slices of N accumulator columns each; the CTA
+  // keeps ITS slice of the filter resident and walks every tile.  ldc = channels of the output tensor (= N without slicing).
+  int ldc;
 };
 // winner byte of a 2x2 window (the same definition as kernels_fast.cu win4): index of the FIRST maximum in row-major order | (max > thr) << 2
 __device__ __forceinline__ unsigned tc_win4(float a, float b, float c, float d, int relu, float thr, float* mx) {
@@ -389,8 +392,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int NB = fold ? TKW * p.N : p.N;  // accumulator columns per buffer
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < 2 * NB) tmem_cols <<= 1;
-  long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 64 : nullptr;
+  long long* dbg = p.dbg && blockIdx.y == 0 ? p.dbg + (size_t)blockIdx.x * 64 : nullptr;
 #define HALO_T(slot) do { if (dbg) dbg[slot] = clock64(); } while (0)
+  const int n0 = (int)blockIdx.y * p.N;  // first output channel of this CTA's slice
 
   if (threadIdx.x == 0) {
     HALO_T(0);
@@ -423,7 +427,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // folded: [chunk][tap] so that the KW taps of a kernel row are adjacent for every channel chunk
         uint8_t* sb = sm_b + (size_t)(fold ? kc * taps + tap : tap * p.kchunks + kc) * b_tile_bytes;
         if (p.b_mn_major) {
-          for (int j = 0; j < p.N / 32; ++j) tma_load_2d(sb + j * 4096, &map_b, b_bar, j * 32, tap * p.b_rows_per_tap + kc * 32);
+          for (int j = 0; j < p.N / 32; ++j) tma_load_2d(sb + j * 4096, &map_b, b_bar, n0 + j * 32, tap * p.b_rows_per_tap + kc * 32);
         } else {
           tma_load_2d(sb, &map_b, b_bar, kc * 32, tap * p.b_rows_per_tap);
         }
@@ -622,7 +626,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       if (threadIdx.x == 64 && ti < 6) HALO_T(24 + ti * 2);
-      float* orow = p.out + ((size_t)(img * p.Hg + h0 + r) * p.Wg + c) * p.N;
+      float* orow = p.out + ((size_t)(img * p.Hg + h0 + r) * p.Wg + c) * p.ldc + n0;
       uint8_t* sbuf = sm_stg + (size_t)(ti & 1) * stg_bytes;
       if (p.tma_store) {
         // the staging buffer is free once the stores issued two tiles ago have READ it
@@ -712,7 +716,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const int rows = min(p.BH, p.Hg - h0);
           for (int rr = 0; rr < rows; ++rr)
             for (int cc = 0; cc < p.N / 32; ++cc)
-              tma_store_4d(&map_c, sbuf + (size_t)cc * 16384 + (size_t)rr * p.P * 128, cc * 32, 0, h0 + rr, img);
+              tma_store_4d(&map_c, sbuf + (size_t)cc * 16384 + (size_t)rr * p.P * 128, n0 + cc * 32, 0, h0 + rr, img);
           tma_store_commit_group();
         }
       }
@@ -1152,7 +1156,7 @@ struct ConvTcPlan {
   CUtensorMap map_x_h, map_dy_h;       // halo kernels: source boxes [32 ch, P, BH+KH-1, 1]
   CUtensorMap map_y_out, map_dx_out;   // halo kernels: TMA-store boxes [32 ch, Wg, 1, 1]
   bool halo_fwd = false, halo_dg = false;
-  int hfwd_smem = 0, hdg_smem = 0, hfwd_grid = 0, hdg_grid = 0;
+  int hfwd_smem = 0, hdg_smem = 0, hfwd_grid = 0, hdg_grid = 0, hfwd_slices = 1;
   WgradParams wg{};
   std::vector<WgradParams> wg_list;   // launches of the per-tap wgrad kernel (tap groups x channel halves)
   bool wg_ok = false;
@@ -1180,9 +1184,11 @@ static bool conv_fits(const ConvGeom& g) {
 
 // Fill a HaloParams for an output grid Hg x Wg whose taps read a source tensor [Csrc, Ws, Hs, N] at origin (ox, oy).
 static bool plan_halo(HaloParams& p, CUtensorMap* map, CUtensorMap* map_out, const float* src, int Csrc, int Ws, int Hs, int Nimg, int Hg, int Wg,
-                      int KH, int KW, int Nacc, int b_mn_major, int b_rows_per_tap, int flip, int ox, int oy, float* out,
-                      int dev_smem, int* smem_out, int pool = 0) {
-  p.Hg = Hg; p.Wg = Wg; p.KH = KH; p.KW = KW; p.kchunks = Csrc / 32; p.N = Nacc;
+                      int KH, int KW, int Nfull, int b_mn_major, int b_rows_per_tap, int flip, int ox, int oy, float* out,
+                      int dev_smem, int* smem_out, int pool = 0, int n_slices = 1) {
+  if (n_slices < 1 || Nfull % (32 * n_slices) || (n_slices > 1 && (pool || !b_mn_major))) return false;  // slices: fprop only
+  const int Nacc = Nfull / n_slices;
+  p.Hg = Hg; p.Wg = Wg; p.KH = KH; p.KW = KW; p.kchunks = Csrc / 32; p.N = Nacc; p.ldc = Nfull;
   p.P = Wg + KW - 1;
   if (p.P > 128) return false;
   p.BH = std::max(1, std::min(128 / p.P, Hg));
@@ -1234,7 +1240,7 @@ static bool plan_halo(HaloParams& p, CUtensorMap* map, CUtensorMap* map_out, con
   p.stages = std::min(6, (dev_smem - fixed) / stage_bytes);
   if (p.stages < 2) return false;
   {
-    uint64_t od[4] = {(uint64_t)Nacc, (uint64_t)Wg, (uint64_t)Hg, (uint64_t)Nimg};
+    uint64_t od[4] = {(uint64_t)Nfull, (uint64_t)Wg, (uint64_t)Hg, (uint64_t)Nimg};
     uint32_t ob[4] = {32, (uint32_t)Wg, 1, 1};
     *map_out = make_map(out, 4, od, ob);
   }
@@ -1365,11 +1371,19 @@ void tc_plan_layers(sb_engine* e) {
       P->fwd_grid = std::min(p.n_tiles * p.nsplit, kNumSMs);
       const char* h = getenv("SB_TC_HALO");
       const bool halo_on = !(h && h[0] == '0') && !x3;
-      if (halo_on && plan_halo(P->hfwd, &P->map_x_h, &P->map_y_out, x, g.Cin, g.W, g.H, g.N, g.OH, g.OW, g.KH, g.KW, g.Cout, 1, g.Cin, 0, -g.PL,
-                               -g.PT, y, dev_smem, &P->hfwd_smem)) {
-        P->hfwd.relu = p.relu; P->hfwd.thr = p.thr;
-        P->hfwd_grid = std::min(P->hfwd.n_tiles, kNumSMs);
-        P->halo_fwd = true;
+      // the whole filter resident, or -- when it does not fit shared memory (cfg5 conv2: 295 KB) -- output-channel slices of >= 64
+      // columns, each CTA keeping its slice resident and walking every tile (SB_TC_HALO_SLICES=0: the per-tap kernel for those)
+      const char* hs = getenv("SB_TC_HALO_SLICES");
+      const int max_slices = (hs && hs[0] == '0') ? 1 : 4;
+      for (int ns = 1; halo_on && ns <= max_slices && !P->halo_fwd; ns *= 2) {
+        if (g.Cout % (32 * ns) || (ns > 1 && g.Cout / ns < 64)) break;
+        if (plan_halo(P->hfwd, &P->map_x_h, &P->map_y_out, x, g.Cin, g.W, g.H, g.N, g.OH, g.OW, g.KH, g.KW, g.Cout, 1, g.Cin, 0, -g.PL, -g.PT, y,
+                      dev_smem, &P->hfwd_smem, 0, ns)) {
+          P->hfwd.relu = p.relu; P->hfwd.thr = p.thr;
+          P->hfwd_slices = ns;
+          P->hfwd_grid = std::max(1, std::min(P->hfwd.n_tiles, kNumSMs / ns));
+          P->halo_fwd = true;
+        }
       }
     }
     // ---- dgrad: tile = BH rows of the H x W input grid; source dY shifted by -tap with zero fill ----
@@ -1616,7 +1630,7 @@ bool tc_conv_enable_pool_fusion(sb_engine* e, LayerPlan& L, float* pooled, unsig
   // tile goes from ~1900 to ~4500 cycles whether 8 or 24 warps pool (SB_TC_DEBUG timeline), fprop 15 -> 23 us, step 1035 k -> 971 k
   // samples/s -- more than the deleted pool kernel (5 us in the step) gives back.
   const char* on = getenv("SB_TC_POOL_FUSION");
-  if (!P || L.tc_kind != 1 || !P->halo_fwd || !(on && on[0] == '1')) return false;
+  if (!P || L.tc_kind != 1 || !P->halo_fwd || P->hfwd_slices != 1 || !(on && on[0] == '1')) return false;
   const ConvGeom& g = L.cg;
   int dev_smem = 0;
   SB_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device));
@@ -1663,10 +1677,10 @@ bool tc_conv_fwd(sb_engine* e, LayerPlan& L, int) {
       launch_k(kern, P->hfwd_grid, kHaloPoolThreads, P->hfwd_smem, e->stream, P->map_x_h, P->map_w_fwd, P->map_y_out, P->hfwd);
     } else if (P->hfwd.fold && (k331 || k332)) {
       auto kern = k331 ? conv_halo_kernel<3, 3, 1, false, true> : conv_halo_kernel<3, 3, 2, false, true>;
-      launch_k(kern, P->hfwd_grid, kIgemmThreadsX3, P->hfwd_smem, e->stream, P->map_x_h, P->map_w_fwd, P->map_y_out, P->hfwd);
+      launch_k(kern, dim3(P->hfwd_grid, P->hfwd_slices), kIgemmThreadsX3, P->hfwd_smem, e->stream, P->map_x_h, P->map_w_fwd, P->map_y_out, P->hfwd);
     } else {
       auto kern = k331 ? conv_halo_kernel<3, 3, 1> : k332 ? conv_halo_kernel<3, 3, 2> : conv_halo_kernel<0, 0, 0>;
-      launch_k(kern, P->hfwd_grid, kIgemmThreads, P->hfwd_smem, e->stream, P->map_x_h, P->map_w_fwd, P->map_y_out, P->hfwd);
+      launch_k(kern, dim3(P->hfwd_grid, P->hfwd_slices), kIgemmThreads, P->hfwd_smem, e->stream, P->map_x_h, P->map_w_fwd, P->map_y_out, P->hfwd);
     }
     SB_LAUNCHED();
     return true;
