@@ -1707,9 +1707,13 @@ bool dense_head_bwd(const float* x, const float* g, const float* w, float* dw, f
   if (smem > 48 * 1024) return false;
   const int kblocks = (K + KB - 1) / KB, thr = kBwdK * GRr;
   // enough CTAs for ~2 waves at 7 CTAs/SM: split the rows when K alone does not give them
-  int splits = std::max(1, std::min({(2 * 7 * kNumSMs + kblocks - 1) / kblocks, (M + kBwdRows - 1) / kBwdRows,
+  // Few column blocks (a short K, e.g. config 5's 1024 -> 10 head: 16 blocks): split the rows finer than the 128-row staging chunk so
+  // that ~one CTA per SM exists (config 5: 32 -> 128 CTAs); with many column blocks (config 2: 484) the 128-row granularity stays
+  const int row_gran = kblocks < kNumSMs ? 32 : kBwdRows;
+  int splits = std::max(1, std::min({(2 * 7 * kNumSMs + kblocks - 1) / kblocks, (M + row_gran - 1) / row_gran,
                                      (int)(ws_floats / ((size_t)K * N))}));
-  const int rows_per_split = ((M + splits - 1) / splits + kBwdRows - 1) / kBwdRows * kBwdRows;
+  if (kblocks < kNumSMs) splits = std::min(splits, std::max(1, kNumSMs / kblocks));
+  const int rows_per_split = ((M + splits - 1) / splits + row_gran - 1) / row_gran * row_gran;
   splits = (M + rows_per_split - 1) / rows_per_split;
   float* dwo = splits > 1 ? ws : dw;
   const dim3 grid(kblocks, splits);
@@ -1719,7 +1723,7 @@ bool dense_head_bwd(const float* x, const float* g, const float* w, float* dw, f
   // rows of X in flight per thread: the kernel is bound by L2 latency x bytes in flight (13 warps per SM at ~90 registers), so the
   // row loop is unrolled over ALL the rows a thread owns when they are few (cfg2: 100 rows / 4 groups = 25: 1020.6 k -> 1033.6 k
   // samples/s against 8 in flight; 13 in flight: 1022 k)
-  const int rows_per_thread = (std::min(M, kBwdRows) + kBwdGroups - 1) / kBwdGroups;
+  const int rows_per_thread = (std::min({M, kBwdRows, rows_per_split}) + kBwdGroups - 1) / kBwdGroups;
   if (NT == 12 && kpt == 2 && dx && rows_per_thread > 16 && rows_per_thread <= 25) {
     launch_k(dense_head_bwd_kernel<12, true, 2, kBwdGroups, 25>, grid, thr, smem, s, x, g, w, dwo, dx, M, K, N, rows_per_split, pdl_early_hint(), pw);
   } else if (NT == 12 && kpt == 2 && dx && rows_per_thread > 25) {
