@@ -267,6 +267,25 @@ BN_POOL = [("conv", 16, "relu", (3, 3), (1, 1), "Valid", False), ("bn", 0.99, "c
            ("flatten",), ("dense", 10, "softmax")]
 
 
+@pytest.mark.parametrize("kernel,cin,cout", [((5, 5), 1, 32), ((3, 3), 3, 128), ((3, 3), 1, 64), ((3, 3), 3, 24)])
+def test_first_layer_filter_gradient_kernels(kernel, cin, cout):
+    """Conv2D with KH*KW*Cin <= 32 as the FIRST layer and no 2x2/1 pool behind it: the filter gradient runs in
+    conv_smallk_wgrad_tile_kernel (Cout >= 32: pixel tiles + im2col rows in shared memory) or the register-accumulator kernel
+    (Cout = 24), the forward in the persistent small-K kernel -- trajectories against the oracle in fp32."""
+    spec = [("conv", cout, "tanh", kernel, (1, 1), "Valid", False), ("flatten",), ("dense", 6, "softmax")]
+    run_trajectory(spec, "cce", "adam", dict(rate=0.003), batch=9, in_shape=(11, 13, cin), classes=6, steps=5, rtol=2e-3, atol=3e-5,
+                   loss_rtol=5e-5)
+
+
+def test_batchnorm_pool_block_falls_back_when_the_layout_does_not_fit():
+    """24 channels: 256 is not a multiple of C/4 = 6, so bn_pool.cu's kernels do not apply and the two-pass BatchNorm, the generic
+    pool and the ReLU backward run as separate kernels -- same trajectory against the oracle."""
+    spec = [("conv", 24, "relu", (3, 3), (1, 1), "Valid", False), ("bn", 0.9, "correct"), ("pool", (2, 2), (2, 2), "Valid"),
+            ("flatten",), ("dense", 10, "softmax")]
+    run_trajectory(spec, "cce", "adam", dict(rate=0.001), batch=10, in_shape=(9, 9, 3), classes=10, steps=5, rtol=3e-3, atol=5e-5,
+                   loss_rtol=1e-4)
+
+
 @pytest.mark.parametrize("mode", ["reference", "correct"])
 def test_batchnorm_pool_block_with_odd_extents(mode):
     """Conv2D(ReLU) >> BatchNorm >> Pool2D(2x2, stride 2) runs as one forward and one backward (csrc/bn_pool.cu).  13x11 images:
