@@ -1706,13 +1706,16 @@ bool dense_head_bwd(const float* x, const float* g, const float* w, float* dw, f
   const size_t smem = ((size_t)kBwdRows * NT + KB * (NT + 1) + (size_t)GRr * KB * (NT + 1)) * 4;
   if (smem > 48 * 1024) return false;
   const int kblocks = (K + KB - 1) / KB, thr = kBwdK * GRr;
-  // enough CTAs for ~2 waves at 7 CTAs/SM: split the rows when K alone does not give them
-  // Few column blocks (a short K, e.g. config 5's 1024 -> 10 head: 16 blocks): split the rows finer than the 128-row staging chunk so
-  // that ~one CTA per SM exists (config 5: 32 -> 128 CTAs); with many column blocks (config 2: 484) the 128-row granularity stays
-  const int row_gran = kblocks < kNumSMs ? 32 : kBwdRows;
-  int splits = std::max(1, std::min({(2 * 7 * kNumSMs + kblocks - 1) / kblocks, (M + row_gran - 1) / row_gran,
+  // enough CTAs for ~2 waves at 7 CTAs/SM: split the rows (in whole 128-row staging chunks) when K alone does not give them
+  int row_gran = kBwdRows;
+  int splits = std::max(1, std::min({(2 * 7 * kNumSMs + kblocks - 1) / kblocks, (M + kBwdRows - 1) / kBwdRows,
                                      (int)(ws_floats / ((size_t)K * N))}));
-  if (kblocks < kNumSMs) splits = std::min(splits, std::max(1, kNumSMs / kblocks));
+  // still fewer CTAs than SMs (a short K and a small batch, e.g. config 5's 1024 -> 10 head at batch 256: 16 x 2): split the rows
+  // finer than the staging chunk, up to about one CTA per SM (config 5: 32 -> 128 CTAs)
+  if (kblocks * splits < kNumSMs && M > 32) {
+    row_gran = 32;
+    splits = std::max(1, std::min({kNumSMs / kblocks, (M + 31) / 32, (int)(ws_floats / ((size_t)K * N))}));
+  }
   const int rows_per_split = ((M + splits - 1) / splits + row_gran - 1) / row_gran * row_gran;
   splits = (M + rows_per_split - 1) / rows_per_split;
   float* dwo = splits > 1 ? ws : dw;
