@@ -303,6 +303,11 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
                "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem)), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all_groups() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -1851,10 +1856,12 @@ struct HeadBwdParams {
   const float* w;   // [K, N]
   float* dw;        // [K, N]
   float* dx;        // [M, K] or null
+  int dbg_mode;     // developer experiment (SB_HB_EXPERIMENT): 1 = no dX stores, 2 = no X tile / dW product (wrong results)
 };
 constexpr int kHeadBwdThreads = 192;
 
-__global__ void __launch_bounds__(kHeadBwdThreads, 2) head_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const HeadBwdParams p) {
+__global__ void __launch_bounds__(kHeadBwdThreads, 2) head_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dx,
+                                                                         const HeadBwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int box_bytes = p.MP * 128;                       // one [32 k x MP rows] box of X
@@ -1863,7 +1870,8 @@ __global__ void __launch_bounds__(kHeadBwdThreads, 2) head_bwd_tc_kernel(const _
   uint8_t* sm_gt = sm_x + a_bytes;                        // G^T : 4 tiles of [16 rows n x 128 B (32 m)]
   uint8_t* sm_g = sm_gt + 4 * 2048;                       // G   : [128 rows m x 128 B (n)]
   uint8_t* sm_w = sm_g + 16384;                           // W   : [128 rows k x 128 B (n)]
-  uint64_t* x_bar = (uint64_t*)(sm_w + 16384);
+  // barriers behind the operands AND behind the 64 KB the dX staging reuses once the MMAs are done
+  uint64_t* x_bar = (uint64_t*)(smem + max(a_bytes + 4 * 2048 + 2 * 16384, 4 * 16384));
   uint64_t* done_bar = x_bar + 1;
   uint32_t* tmem_slot = (uint32_t*)(done_bar + 1);
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
@@ -1912,7 +1920,7 @@ __global__ void __launch_bounds__(kHeadBwdThreads, 2) head_bwd_tc_kernel(const _
   if (p.prewait) stage_w();
   pdl_wait();
   pdl_trigger();
-  if (threadIdx.x == 0) {  // the X tile: rows >= M of every box are zero fill
+  if (threadIdx.x == 0 && p.dbg_mode != 2) {  // the X tile: rows >= M of every box are zero fill
     mbar_arrive_expect_tx(x_bar, (uint32_t)(4 * box_bytes));
     for (int j = 0; j < 4; ++j) tma_load_2d(sm_x + (size_t)j * box_bytes, &map_x, x_bar, k0 + j * 32, 0);
   }
@@ -1951,10 +1959,10 @@ __global__ void __launch_bounds__(kHeadBwdThreads, 2) head_bwd_tc_kernel(const _
       umma_tf32_elect(tmem_u, ((uint64_t)k_hi << 32) | g0, ((uint64_t)k_hi << 32) | w0, idesc2, 0u);
       umma_tf32_elect(tmem_u, ((uint64_t)k_hi << 32) | (g0 + 2), ((uint64_t)k_hi << 32) | (w0 + 2), idesc2, 1u);
     }
-    mbar_wait(x_bar, 0);
+    if (p.dbg_mode != 2) mbar_wait(x_bar, 0);
     tc_fence_after();
     const uint32_t idesc1 = idesc_tf32(128, 16, 1, 0);
-    const int steps = p.MP / 8;
+    const int steps = p.dbg_mode == 2 ? 0 : p.MP / 8;
     for (int sidx = 0; sidx < steps; ++sidx)  // 8 batch rows per MMA: A rows are 128 B apart inside a box, B tiles hold 32 rows each
       umma_tf32_elect(tmem_w, ((uint64_t)x_hi << 32) | (x0 + sidx * 64),
                       ((uint64_t)k_hi << 32) | (gt0 + (sidx >> 2) * 128 + (sidx & 3) * 2), idesc1, sidx ? 1u : 0u);
@@ -1973,15 +1981,23 @@ __global__ void __launch_bounds__(kHeadBwdThreads, 2) head_bwd_tc_kernel(const _
       for (int n = 0; n < 16; ++n)
         if (n < p.N) o[n] = v[n];
     }
-    if (p.dx) {  // dX: TMEM lane = batch row
-      float* o = p.dx + (size_t)row * p.K + k0;
+    if (p.dx) {  // dX: TMEM lane = batch row.  Per-thread stores would be 32 row-strided 16-byte pieces per thread (measured: 5.5 of the
+      // kernel's 10.4 us); instead the tile goes through the swizzled layout of four [128 rows x 32 k] TMA boxes in the (now dead)
+      // operand memory and leaves as four bulk stores -- rows past the batch are clipped by the tensor map
       for (int c0 = 0; c0 < 128; c0 += 32) {
         tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)c0, v);
         tmem_ld_wait();
-        if (row < p.M) {
+        uint8_t* srow = smem + (size_t)(c0 >> 5) * 16384 + row * 128;
 #pragma unroll
-          for (int q = 0; q < 32; q += 4) *reinterpret_cast<float4*>(o + c0 + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
-        }
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(srow + ((j ^ (row & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      fence_proxy_async();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64 && p.dbg_mode != 1) {
+        for (int c = 0; c < 4; ++c) tma_store_2d(&map_dx, smem + (size_t)c * 16384, k0 + c * 32, 0);
+        tma_store_commit_group();
+        tma_store_wait_all_groups();  // the staging memory is read (and the global writes are done) before the CTA exits
       }
     }
   }
@@ -1995,9 +2011,10 @@ __global__ void __launch_bounds__(kHeadBwdThreads, 2) head_bwd_tc_kernel(const _
 }
 
 struct HeadBwdTcPlan {
-  CUtensorMap map_x;
+  CUtensorMap map_x, map_dx;
   HeadBwdParams p;
   const float* x;
+  const float* dx;
   int smem;
 };
 
@@ -2008,17 +2025,16 @@ static void head_bwd_tc_free(LayerPlan& L) {
 
 // false: shape / mode not covered (the caller runs dense_head_bwd)
 bool tc_head_bwd(sb_engine* e, LayerPlan& L, const float* x, const float* g, const float* w, float* dw, float* dx, cudaStream_t st) {
-  // OPT-IN (SB_TC_HEAD_BWD=1; read per call: the A/B test flips it inside one process).  Measured on cfg2 (batch 100, K = 30976): the
-  // same ~10.5 us from this kernel's start to the next kernel's start as the FFMA kernel inside the replayed step (91.86 vs 91.89 us
-  // per step), 16.4 vs 19.6 us under ncu with a cold L2 -- its lifetime is a chain of latencies (operand staging, the X tile, 32
-  // row-strided 16-byte stores per thread), not the 40 instructions per element it removes, and it adds tf32 rounding to the head's
-  // gradients; so the FFMA kernel stays the default (profiles/r2_notes.md 14).
-  const char* on = getenv("SB_TC_HEAD_BWD");
-  if (!(on && on[0] == '1') || e->train.precision != SB_PREC_TF32) return false;
+  // Default in TF32 mode (SB_TC_HEAD_BWD=0: the FFMA kernel; read per call: the A/B test flips it inside one process).  Measured on
+  // cfg2 (batch 100, K = 30976), in-situ timeline of the replayed step: 7.8 us from this kernel's start to the next kernel's start
+  // against 10.5 us for the FFMA kernel; step 91.9 -> 89.5 us (1.088 M -> 1.117 M samples/s).  With per-thread dX stores it was no
+  // faster than the FFMA kernel (10.4 us, 5.5 of them in the row-strided stores): profiles/r2_notes.md 14.
+  const char* off = getenv("SB_TC_HEAD_BWD");
+  if ((off && off[0] == '0') || e->train.precision != SB_PREC_TF32) return false;
   const int M = (int)L.in.d[0], K = (int)L.in.d[1], N = (int)L.out.d[1];
   if (M > 128 || N > 16 || (K % 128) || K < 128 * kNumSMs || (((uintptr_t)x) & 127) || (dx && (((uintptr_t)dx) & 15))) return false;
   HeadBwdTcPlan* P = (HeadBwdTcPlan*)L.head_bwd_tc;
-  if (!P || P->x != x) {
+  if (!P || P->x != x || P->dx != dx) {
     delete P;
     P = new HeadBwdTcPlan();
     P->p.M = M; P->p.MP = (M + 7) / 8 * 8; P->p.K = K; P->p.N = N;
@@ -2026,13 +2042,18 @@ bool tc_head_bwd(sb_engine* e, LayerPlan& L, const float* x, const float* g, con
     uint32_t xb[2] = {32, (uint32_t)P->p.MP};
     P->map_x = make_map(x, 2, xd, xb, true);
     P->x = x;
-    P->smem = ((4 * P->p.MP * 128 + 1023) / 1024) * 1024 + 4 * 2048 + 2 * 16384 + 64 + 1024;
+    P->dx = dx;
+    uint32_t db[2] = {32, 128};
+    P->map_dx = make_map(dx ? dx : x, 2, xd, db);  // dX tile stores: K-major boxes of 32 k x 128 rows (rows >= M clipped)
+    // operands, and at least the 64 KB the dX staging reuses
+    P->smem = std::max(((4 * P->p.MP * 128 + 1023) / 1024) * 1024 + 4 * 2048 + 2 * 16384, 4 * 16384) + 64 + 1024;
     SB_CUDA(cudaFuncSetAttribute(head_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P->smem));
     L.head_bwd_tc = P;
   }
   P->p.g = g; P->p.w = w; P->p.dw = dw; P->p.dx = dx;
   P->p.prewait = prewait_ok();
-  launch_k(head_bwd_tc_kernel, K / 128, kHeadBwdThreads, P->smem, st, P->map_x, P->p);
+  { const char* ex = getenv("SB_HB_EXPERIMENT"); P->p.dbg_mode = ex ? atoi(ex) : 0; }
+  launch_k(head_bwd_tc_kernel, K / 128, kHeadBwdThreads, P->smem, st, P->map_x, P->map_dx, P->p);
   SB_LAUNCHED();
   return true;
 }

@@ -364,7 +364,7 @@ def test_3xtf32_lenet_config2_full_size_trajectory():
 def test_tensor_core_head_backward_matches_the_ffma_kernel(batch, monkeypatch):
     """csrc/tc.cu head_bwd_tc_kernel (TF32 mode, the config-2 head: 36864 -> 10): dW = X^T . G and dX = G . W^T on tcgen05, X tile by
     TMA as an MN-major operand (batch rows = the K dimension, rows past the batch are TMA zero fill), G / G^T / W written by the
-    threads in the K-major swizzled layout; opt-in, SB_TC_HEAD_BWD=1.  Against the default FFMA kernel: same forward, so the same loss; every
+    threads in the K-major swizzled layout, dX through swizzled staging + TMA stores.  Against SB_TC_HEAD_BWD=0 (the FFMA kernel): same forward, so the same loss; every
     gradient within tf32 rounding of the FFMA one (the head's inputs are post-ReLU pool outputs, its gradient feeds conv2/conv1)."""
     spec = [("conv", 32, "relu", (3, 3), (1, 1), "Valid", False), ("pool", (2, 2), (1, 1), "Valid"),
             ("conv", 64, "relu", (3, 3), (1, 1), "Valid", False), ("pool", (2, 2), (1, 1), "Valid"), ("flatten",), ("dense", 10, "softmax")]
