@@ -105,6 +105,46 @@ def test_tf32_conv_forward_and_gradients(name, spec, batch, in_shape, wgrad, mon
     etc.close()
 
 
+def _tf32_trunc(a):
+    """what kind::tf32 keeps of an fp32 operand: the low 13 mantissa bits are ignored (truncation, not rounding)"""
+    return (np.ascontiguousarray(a, np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def test_tf32_lenet_gradients_match_an_oracle_with_truncated_operands(monkeypatch):
+    """BASELINE config 2 at full size, TF32 mode, pinned TIGHTLY: the oracle is run with the operands of exactly the contractions the
+    engine puts on tcgen05 (conv2 fprop / dgrad / wgrad: Cin = 32; the head 30976 -> 10 forward and backward) truncated to tf32 and
+    accumulated in float64.  What is left between the two is accumulation order (and the handful of ReLU masks it flips), so the
+    loss must agree to 2e-6 and every gradient to 5e-4 of its largest entry -- measured 4e-6 (head bias), 2.8e-4 (head weights),
+    6.7e-5 (conv2), 4.1e-5 (conv1) -- not the 4e-3 / cosine 0.995 bounds the plain-fp32 oracle allows."""
+    import oracle.layers as Lm
+    spec = CONV_STACKS[0][1]
+    om, sm = build_models(spec)
+    batch = 100
+    x, y = synth_classification(batch, (28, 28, 1), 10, 21)
+    e = S.Engine(sm, S.CategoricalCrossentropy, S.Adam(0.001), batch, (28, 28, 1), (10,), device=0, precision=S.PREC_TF32)
+    e.init_params()
+    gl, gg = e.compute_grads(x, y)
+    e.close()
+    f64 = np.float64
+    conv2d0, wgrad0, dgrad0 = Lm.conv2d, Lm.conv2d_wgrad, Lm.conv2d_dgrad
+    on_tc = lambda cin: cin % 32 == 0  # the engine's rule for the tcgen05 conv kernels (tc.cu conv_fits)
+    monkeypatch.setattr(Lm, "conv2d", lambda x_, w_, *a, **k: conv2d0(_tf32_trunc(x_).astype(f64), _tf32_trunc(w_).astype(f64), *a, **k).astype(np.float32)
+                        if on_tc(x_.shape[-1]) else conv2d0(x_, w_, *a, **k))
+    monkeypatch.setattr(Lm, "conv2d_wgrad", lambda x_, ws, g_, *a, **k: wgrad0(_tf32_trunc(x_).astype(f64), ws, _tf32_trunc(g_).astype(f64), *a, **k).astype(np.float32)
+                        if on_tc(x_.shape[-1]) else wgrad0(x_, ws, g_, *a, **k))
+    monkeypatch.setattr(Lm, "conv2d_dgrad", lambda xs, w_, g_, *a, **k: dgrad0(xs, _tf32_trunc(w_).astype(f64), _tf32_trunc(g_).astype(f64), *a, **k).astype(np.float32)
+                        if on_tc(xs[-1]) else dgrad0(xs, w_, g_, *a, **k))
+    t = lambda a_: _tf32_trunc(a_).astype(f64)
+    monkeypatch.setattr(Lm.DenseKernel, "forward", lambda self, x_, p, training: ((t(x_) @ t(p["weights"])).astype(np.float32), x_, {}))
+    monkeypatch.setattr(Lm.DenseKernel, "backward", lambda self, g_, x_, p, need_dx: (
+        (t(g_) @ t(p["weights"]).T).astype(np.float32) if need_dx else None, {"weights": (t(x_).T @ t(g_)).astype(np.float32)}))
+    _, mp, _ = O.init_params(om, O.Adam(0.001), (batch, 28, 28, 1))
+    ol, og, _ = O.LossModel(om, O.CategoricalCrossentropy).grad_stateful(x, y, mp)
+    assert abs(gl - float(ol)) <= 2e-6 * abs(float(ol)), (gl, float(ol))
+    worst = {k: rel_to_max(gg[k], og[k]) for k in og}
+    assert max(worst.values()) < 5e-4, worst
+
+
 def test_tf32_lenet_trajectory_config2():
     spec = CONV_STACKS[0][1]
     om, sm = build_models(spec)
