@@ -173,6 +173,74 @@ def test_config3_lstm_full_size_tensor_core_modes_against_the_oracle(precision):
     assert not bad, bad  # every violated bound at once
 
 
+def _tf32_rn(a):
+    """cvt.rna.tf32.f32: round to the nearest tf32 value, ties away from zero (sign-magnitude: add half an ulp, drop 13 bits)"""
+    u = np.ascontiguousarray(a, np.float32).view(np.uint32)
+    return ((u + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def test_config3_lstm_tf32_matches_an_oracle_that_rounds_where_the_engine_rounds(monkeypatch):
+    """BASELINE configs[2] at full size in TF32 mode, pinned TIGHTLY.  In TF32 mode the engine stores h_t, dZ_t and the packed
+    recurrent weights rounded to the nearest tf32 value (csrc/lstm.cu tf32_rn), so the operands of its tcgen05 products are exact
+    tf32 numbers and the products exact in fp32.  The oracle cell below rounds at the same three places and accumulates in float64:
+    what is left is accumulation order, the approximate exp of the TF32-mode gate kernels (~1e-6) and the rare rounding decision
+    either of them flips.  Loss 1e-5 (measured 4e-6), every gradient 1e-3 of the model's largest entry (measured 3.8e-4, a gate bias) --
+    against the direction-only bounds (cosine 0.98) the plain oracle allows in the test above."""
+    import oracle.layers as Lm
+    om, sm = build_models([("lstm", 256), ("dense", 1, "tanh")])
+    batch, t = 1024, 64
+    rng = np.random.Generator(np.random.PCG64(1237))
+    x = rng.uniform(0, 1, size=(batch, t, 1)).astype(f32)
+    y = rng.uniform(0, 1, size=(batch, 1)).astype(f32)
+    e = S.Engine(sm, S.MeanSquaredError, S.Adam(1e-3), batch, (t, 1), (1,), device=0, precision=S.PREC_TF32)
+    e.init_params()
+    gl, gg = e.compute_grads(x, y)
+    e.close()
+    f64 = np.float64
+
+    def step(self, x_, c_prev, h_prev, p):
+        zs, acts = {}, {}
+        for gname in self.GATES:
+            z = (x_ @ p[f"{gname}/0/kernel_weights"]) + (h_prev.astype(f64) @ _tf32_rn(p[f"{gname}/0/recurrent_weights"]).astype(f64)).astype(f32)
+            if self.bias:
+                z = z + p[f"{gname}/1/weights"]
+            zs[gname] = z
+            acts[gname] = self._act(gname).fwd(z)
+        f, i, g, o = (acts[n] for n in self.GATES)
+        c = c_prev * f + i * g
+        ac = self.activation.fwd(c)
+        h = _tf32_rn(o * ac)
+        return h, c, (x_, c_prev, h_prev, zs, acts, c, ac)
+
+    def step_bwd(self, dh, dc_next, cache, p):
+        x_, c_prev, h_prev, zs, acts, c, ac = cache
+        f, i, g, o = (acts[n] for n in self.GATES)
+        do = dh * ac
+        dc = self.activation.bwd(dh * o, c, ac) + dc_next
+        dacts = {"forget": dc * c_prev, "input": dc * g, "gate": dc * i, "output": do}
+        dc_prev = dc * f
+        dh_prev = np.zeros(h_prev.shape, f64)
+        grads = {}
+        for gname in self.GATES:
+            dz = _tf32_rn(self._act(gname).bwd(dacts[gname], zs[gname], acts[gname]))
+            grads[f"{gname}/0/kernel_weights"] = (x_.astype(f64).T @ dz.astype(f64)).astype(f32)
+            grads[f"{gname}/0/recurrent_weights"] = (h_prev.astype(f64).T @ dz.astype(f64)).astype(f32)
+            if self.bias:
+                grads[f"{gname}/1/weights"] = np.sum(dz, axis=0, dtype=f64).astype(f32)
+            dh_prev = dh_prev + dz.astype(f64) @ _tf32_rn(p[f"{gname}/0/recurrent_weights"]).astype(f64).T
+        self._last_dx = np.zeros_like(x_)
+        return dh_prev.astype(f32), dc_prev, grads
+
+    monkeypatch.setattr(Lm.LSTMCell, "step", step)
+    monkeypatch.setattr(Lm.LSTMCell, "step_bwd", step_bwd)
+    _, mp, _ = O.init_params(om, O.Adam(1e-3), (batch, t, 1))
+    ol, og, _ = O.LossModel(om, O.MeanSquaredError).grad_stateful(x, y, mp)
+    assert abs(gl - float(ol)) <= 1e-5 * abs(float(ol)), (gl, float(ol))
+    gmax = max(float(np.max(np.abs(v))) for v in og.values())
+    worst = {k: float(np.max(np.abs(gg[k].astype(f64) - np.asarray(og[k], f64)))) / gmax for k in og}
+    assert max(worst.values()) < 1e-3, worst
+
+
 def test_maximize_walks_up_the_gradient():
     """Optimizer.maximize (Optimizer.scala:186,326-338): `w + delta` -- the same trajectory as the oracle's `minimizing=False`"""
     om, sm = build_models([("dense", 8, "sigmoid"), ("dense", 4, "softmax")])
