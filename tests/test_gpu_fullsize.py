@@ -116,6 +116,53 @@ def test_config5_cifar_batchnorm_cnn_full_size(precision, mode):
     check_two_steps(om, sm, O.CategoricalCrossentropy, S.CategoricalCrossentropy, x, y, batch, (32, 32, 3), (10,), precision)
 
 
+def _tf32_trunc(a):
+    """what kind::tf32 keeps of an fp32 operand: the low 13 mantissa bits are ignored"""
+    return (np.ascontiguousarray(a, np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def cfg5_tf32_emulation_report(batch, setattr_):
+    """engine (TF32 mode) vs the oracle whose Conv2D contractions truncate their operands to tf32 where the engine runs tcgen05 kernels"""
+    import oracle.layers as Lm
+    om, sm = build_models(CIFAR("correct"))
+    x, y = synth_classification(batch, (32, 32, 3), 10, 1239)
+    e = S.Engine(sm, S.CategoricalCrossentropy, S.Adam(1e-3), batch, (32, 32, 3), (10,), device=0, precision=S.PREC_TF32)
+    e.init_params()
+    gl, gg = e.compute_grads(x, y)
+    e.close()
+    f64 = np.float64
+    conv2d0, wgrad0, dgrad0 = Lm.conv2d, Lm.conv2d_wgrad, Lm.conv2d_dgrad
+    on_tc = lambda cin: cin % 32 == 0
+    t = lambda a_: _tf32_trunc(a_).astype(f64)
+    setattr_(Lm, "conv2d", lambda x_, w_, *a, **k: conv2d0(t(x_), t(w_), *a, **k).astype(f32) if on_tc(x_.shape[-1]) else conv2d0(x_, w_, *a, **k))
+    setattr_(Lm, "conv2d_wgrad", lambda x_, ws, g_, *a, **k: wgrad0(t(x_), ws, t(g_), *a, **k).astype(f32) if on_tc(x_.shape[-1]) else wgrad0(x_, ws, g_, *a, **k))
+    setattr_(Lm, "conv2d_dgrad", lambda xs, w_, g_, *a, **k: dgrad0(xs, t(w_), t(g_), *a, **k).astype(f32) if on_tc(xs[-1]) else dgrad0(xs, w_, g_, *a, **k))
+    _, mp, _ = O.init_params(om, O.Adam(1e-3), (batch, 32, 32, 3))
+    ol, og, _ = O.LossModel(om, O.CategoricalCrossentropy).grad_stateful(x, y, mp)
+    report = {"loss": (gl, float(ol))}
+    for k in og:
+        a_, b_ = gg[k].astype(f64).ravel(), np.asarray(og[k], f64).ravel()
+        cos = float(a_ @ b_ / (np.linalg.norm(a_) * np.linalg.norm(b_) + 1e-300))
+        rmax = float(np.max(np.abs(a_ - b_)) / (np.max(np.abs(b_)) + 1e-300))
+        report[k] = (round(cos, 7), round(rmax, 6))
+    return report
+
+
+def test_config5_tf32_gradients_match_an_oracle_with_truncated_operands(monkeypatch):
+    """BASELINE configs[4] at full size, TF32 mode, pinned through the contractions themselves: the oracle's Conv2D fprop / dgrad /
+    wgrad truncate their operands to tf32 wherever the engine runs the tcgen05 kernels (Cin % 32 == 0: conv2, conv3; conv1 and the
+    1024 -> 10 head stay fp32 on both sides) and accumulate in float64.  Loss 1e-4 (measured 4.6e-5); everything behind the last
+    BatchNorm (its gamma / beta, the head) within 2e-3 of the largest entry (measured <= 5.5e-4); every tensor's direction cosine
+    > 0.999 (measured >= 0.99944; the plain oracle allows 0.995).  In front of a BatchNorm no oracle pins single entries tighter: its
+    backward subtracts nearly equal sums, which amplifies accumulation-order differences to per-cent level -- the same 1e-2 relative
+    L2 on conv3's filter gradient separates two float32 implementations (module docstring)."""
+    report = cfg5_tf32_emulation_report(256, monkeypatch.setattr)
+    gl, ol = report.pop("loss")
+    ok = abs(gl - ol) <= 1e-4 * abs(ol) and all(c > 0.999 for c, _ in report.values())
+    ok = ok and all(report[k][1] < 2e-3 for k in ("10/gamma", "10/beta", "13/weights", "14/weights"))
+    assert ok, "\n" + "\n".join(f"{k}: {v}" for k, v in report.items())
+
+
 @pytest.mark.parametrize("precision", [S.PREC_TF32, S.PREC_3XTF32], ids=["tf32", "3xtf32"])
 def test_config3_lstm_full_size_tensor_core_modes_against_the_oracle(precision):
     """BASELINE configs[2]: LSTM(256) >> Dense(1, Tanh), MSE, seq len 64, batch 1024 -- the tensor-core modes against the ORACLE
