@@ -1856,7 +1856,6 @@ struct HeadBwdParams {
   const float* w;   // [K, N]
   float* dw;        // [K, N]
   float* dx;        // [M, K] or null
-  int dbg_mode;     // developer experiment (SB_HB_EXPERIMENT): 1 = no dX stores, 2 = no X tile / dW product (wrong results)
 };
 constexpr int kHeadBwdThreads = 192;
 
@@ -1920,7 +1919,7 @@ __global__ void __launch_bounds__(kHeadBwdThreads, 2) head_bwd_tc_kernel(const _
   if (p.prewait) stage_w();
   pdl_wait();
   pdl_trigger();
-  if (threadIdx.x == 0 && p.dbg_mode != 2) {  // the X tile: rows >= M of every box are zero fill
+  if (threadIdx.x == 0) {  // the X tile: rows >= M of every box are zero fill
     mbar_arrive_expect_tx(x_bar, (uint32_t)(4 * box_bytes));
     for (int j = 0; j < 4; ++j) tma_load_2d(sm_x + (size_t)j * box_bytes, &map_x, x_bar, k0 + j * 32, 0);
   }
@@ -1959,10 +1958,10 @@ __global__ void __launch_bounds__(kHeadBwdThreads, 2) head_bwd_tc_kernel(const _
       umma_tf32_elect(tmem_u, ((uint64_t)k_hi << 32) | g0, ((uint64_t)k_hi << 32) | w0, idesc2, 0u);
       umma_tf32_elect(tmem_u, ((uint64_t)k_hi << 32) | (g0 + 2), ((uint64_t)k_hi << 32) | (w0 + 2), idesc2, 1u);
     }
-    if (p.dbg_mode != 2) mbar_wait(x_bar, 0);
+    mbar_wait(x_bar, 0);
     tc_fence_after();
     const uint32_t idesc1 = idesc_tf32(128, 16, 1, 0);
-    const int steps = p.dbg_mode == 2 ? 0 : p.MP / 8;
+    const int steps = p.MP / 8;
     for (int sidx = 0; sidx < steps; ++sidx)  // 8 batch rows per MMA: A rows are 128 B apart inside a box, B tiles hold 32 rows each
       umma_tf32_elect(tmem_w, ((uint64_t)x_hi << 32) | (x0 + sidx * 64),
                       ((uint64_t)k_hi << 32) | (gt0 + (sidx >> 2) * 128 + (sidx & 3) * 2), idesc1, sidx ? 1u : 0u);
@@ -1994,7 +1993,7 @@ __global__ void __launch_bounds__(kHeadBwdThreads, 2) head_bwd_tc_kernel(const _
       }
       fence_proxy_async();
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 64 && p.dbg_mode != 1) {
+      if (threadIdx.x == 64) {
         for (int c = 0; c < 4; ++c) tma_store_2d(&map_dx, smem + (size_t)c * 16384, k0 + c * 32, 0);
         tma_store_commit_group();
         tma_store_wait_all_groups();  // the staging memory is read (and the global writes are done) before the CTA exits
@@ -2052,7 +2051,6 @@ bool tc_head_bwd(sb_engine* e, LayerPlan& L, const float* x, const float* g, con
   }
   P->p.g = g; P->p.w = w; P->p.dw = dw; P->p.dx = dx;
   P->p.prewait = prewait_ok();
-  { const char* ex = getenv("SB_HB_EXPERIMENT"); P->p.dbg_mode = ex ? atoi(ex) : 0; }
   launch_k(head_bwd_tc_kernel, K / 128, kHeadBwdThreads, P->smem, st, P->map_x, P->map_dx, P->p);
   SB_LAUNCHED();
   return true;
