@@ -458,6 +458,39 @@ static float* dmalloc_floats(int64_t n) {
 
 // Decide which layers run on the vectorised / fused kernels of kernels_fast.cu.  Runs after tc_plan_layers, which owns
 // the contractions that fit tcgen05 (and already folded the ReLU that follows them into its epilogue).
+// Early optimizer (cfg2: 89.3 -> 87.8 us per step, bit-identical; profiles/r2_notes.md 17): eligible when the tensor-core conv layer closest to the input that forks a side branch
+// has only parameter-free layers between itself and the FIRST trainable layer -- then every gradient but the first layer's is complete
+// when that side branch has reduced its filter gradient, and the arena from that layer's first parameter on can be updated there.
+static void plan_early_optimizer(sb_engine* e) {
+  e->early_opt_layer = -1;
+  const char* off_ = getenv("SB_EARLY_OPT");  // =0: one optimizer launch at the end of the step
+  if ((off_ && off_[0] == '0') || e->has_reg || !fork_enabled()) return;
+  const int nl = (int)e->L.size();
+  int first_tr = -1;
+  for (const Param& p : e->params)
+    if (p.role == SB_ROLE_WEIGHT && (first_tr < 0 || p.layer < first_tr)) first_tr = p.layer;
+  if (first_tr < 0) return;
+  int cand = -1;
+  for (int li = first_tr + 1; li < nl; ++li) {
+    const LayerPlan& L = e->L[li];
+    bool has_params = false;
+    for (const Param& p : e->params)
+      if (p.role == SB_ROLE_WEIGHT && p.layer == li) has_params = true;
+    if (!has_params) continue;
+    if (L.d.kind == SB_LAYER_CONV2D && L.tc_kind == 1 && L.need_dx && !L.wgrad_in_pool) cand = li;
+    break;  // the first parameterised layer behind the first trainable one decides
+  }
+  if (cand < 0) return;
+  int64_t off = -1;
+  for (const Param& p : e->params)
+    if (p.role == SB_ROLE_WEIGHT && p.layer >= cand && (off < 0 || p.offset < off)) off = p.offset;
+  for (const Param& p : e->params)  // arena order must be model order: nothing of the first layer behind `off`
+    if (p.role == SB_ROLE_WEIGHT && p.layer < cand && p.offset >= off) return;
+  if (off <= 0 || off % 4) return;
+  e->early_opt_layer = cand;
+  e->early_opt_off = off;
+}
+
 static void plan_fusions(sb_engine* e) {
   const char* off = getenv("SB_DISABLE_FAST");
   e->fast = !(off && off[0] == '1');
@@ -650,6 +683,7 @@ static void allocate(sb_engine* e) {
   SB_CUDA(cudaStreamCreateWithPriority(&e->bstream, cudaStreamNonBlocking, prio_lo));  // created outside any capture
   SB_CUDA(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
   SB_CUDA(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+  SB_CUDA(cudaEventCreateWithFlags(&e->ev_mid, cudaEventDisableTiming));
   // the arena allocation carries a tail of cross-GPU flags / scalars behind the tensors (one IPC handle maps both)
   e->arena = dmalloc_floats(e->arena_floats + sb::kArenaTailFloats);
   SB_CUDA(cudaMemsetAsync(e->arena, 0, (size_t)(e->arena_floats + sb::kArenaTailFloats) * 4, e->stream));
@@ -683,6 +717,7 @@ static void allocate(sb_engine* e) {
   }
   tc_plan_layers(e);  // tensor-core fast paths (TMA descriptors, padded-grid buffers)
   plan_fusions(e);    // vectorised / fused bandwidth kernels
+  plan_early_optimizer(e);
   lstm_plan(e);       // LSTM workspaces (saved gate activations for BPTT)
   rnn_plan(e);        // SimpleRNN workspaces
   SB_CUDA(cudaStreamSynchronize(e->stream));
@@ -924,6 +959,8 @@ static ReduceBatch* reduce_batch(sb_engine* e) {
   return (on && !e->profiling) ? &e->pending_reduce : nullptr;
 }
 
+static void optimizer_range(sb_engine* e, int64_t off, int64_t n, int advance_batch, cudaStream_t s);
+
 static void run_backward(sb_engine* e) {
   cudaStream_t s = e->stream;
   e->pending_reduce.count = 0;
@@ -1028,7 +1065,22 @@ static void run_backward(sb_engine* e) {
           // the head's combine gone from the main stream the filter gradient + its reduce had become the tail of the step (in-situ
           // timeline: they finished 9 us after the main stream's last kernel): 1050 k -> 1090 k samples/s, no branch 1022 k.
           static const int fork_mode = [] { const char* v = getenv("SB_FORK_MODE"); return v ? atoi(v) : 1; }();
-          if (fork && fork_mode == 1) {
+          const bool early_opt = fork && fork_mode == 1 && e->early_opt_now && li == e->early_opt_layer;
+          if (early_opt) {
+            // filter gradient + reduction on the side branch, dgrad on the main stream, and -- once dgrad has read this layer's
+            // weights -- the optimizer update of every parameter from this layer on, still on the side branch
+            side_branch_begin(e);
+            wdone = tc_conv_wgrad(e, L, li, e->bstream, nullptr);
+            {
+              Prof pr(e, "conv2d_dgrad_tf32_tcgen05", cb, fl);
+              ddone = tc_conv_dgrad(e, L, li);
+            }
+            SB_CUDA(cudaEventRecord(e->ev_mid, e->stream));
+            SB_CUDA(cudaStreamWaitEvent(e->bstream, e->ev_mid, 0));
+            optimizer_range(e, e->early_opt_off, e->nW - e->early_opt_off, 0, e->bstream);
+            e->early_opt_done = true;
+            side_branch_end(e);
+          } else if (fork && fork_mode == 1) {
             side_branch_begin(e);
             wdone = tc_conv_wgrad(e, L, li, e->bstream, reduce_batch(e));
             side_branch_end(e);
@@ -1045,7 +1097,7 @@ static void run_backward(sb_engine* e) {
               reduce_each(rb, s);  // the launches the product path makes, not the merged variant
             }
           }
-          if (L.need_dx && din) {
+          if (L.need_dx && din && !ddone) {
             Prof pr(e, "conv2d_dgrad_tf32_tcgen05", cb, fl);
             ddone = tc_conv_dgrad(e, L, li);
           }
@@ -1167,14 +1219,23 @@ static OptDesc opt_desc(const sb_engine* e) {
   return o;
 }
 
+// the update of arena floats [off, off + n) on stream s
+static void optimizer_range(sb_engine* e, int64_t off, int64_t n, int advance_batch, cudaStream_t s) {
+  float* w = e->arena + off;
+  float* s0 = e->arena + e->nW + e->nS + off;
+  float* s1 = e->n_slots >= 2 ? s0 + e->nW : nullptr;
+  float* s2 = e->n_slots >= 3 ? s0 + 2 * e->nW : nullptr;
+  optimizer_step(opt_desc(e), w, e->grads + off, s0, s1, s2, n, e->st, advance_batch, s);
+}
 static void run_optimizer(sb_engine* e, int advance_batch) {
   static const double bytes_per_param[8] = {20, 28, 20, 20, 28, 28, 28, 36};
   Prof pr(e, "optimizer_fused", bytes_per_param[e->train.optimizer] * (double)e->nW, 0);
-  float* w = e->arena;
-  float* s0 = e->arena + e->nW + e->nS;
-  float* s1 = e->n_slots >= 2 ? s0 + e->nW : nullptr;
-  float* s2 = e->n_slots >= 3 ? s0 + 2 * e->nW : nullptr;
-  optimizer_step(opt_desc(e), w, e->grads, s0, s1, s2, e->nW, e->st, advance_batch, e->stream);
+  if (e->early_opt_done) {  // everything from early_opt_off on was updated on the side branch of this step's backward pass
+    e->early_opt_done = false;
+    optimizer_range(e, 0, e->early_opt_off, advance_batch, e->stream);
+    return;
+  }
+  optimizer_range(e, 0, e->nW, advance_batch, e->stream);
 }
 
 static void run_prologue(sb_engine* e, bool resident) {
@@ -1190,11 +1251,20 @@ static void run_prologue_staged(sb_engine* e, int parity, int j = 0) {
                 j > 0 ? e->loss_hist[parity] + (j - 1) : nullptr);
 }
 
+// backward pass of a TRAIN step (an optimizer update follows): the side branch may already update the parameters whose gradients
+// are complete (early optimizer, engine.h)
+static void run_backward_train(sb_engine* e) {
+  e->early_opt_done = false;
+  e->early_opt_now = e->early_opt_layer >= 0 && !e->profiling;
+  run_backward(e);
+  e->early_opt_now = false;
+}
+
 static void run_train_step_body(sb_engine* e, bool resident) {
   run_prologue(e, resident);
   run_forward(e, FWD_TRAIN);
   run_loss(e, true);
-  run_backward(e);
+  run_backward_train(e);
   run_reg(e, true);
   run_optimizer(e, resident ? 1 : 0);
 }
@@ -1204,7 +1274,7 @@ static void run_train_step_body_staged(sb_engine* e, bool parity) {
   run_prologue_staged(e, parity ? 1 : 0);
   run_forward(e, FWD_TRAIN);
   run_loss(e, true);
-  run_backward(e);
+  run_backward_train(e);
   run_reg(e, true);
   run_optimizer(e, 0);
 }
@@ -1221,7 +1291,7 @@ static void run_train_step_body_cursor(sb_engine* e, bool parity) {
   }
   run_forward(e, FWD_TRAIN);
   run_loss(e, true);
-  run_backward(e);
+  run_backward_train(e);
   run_reg(e, true);
   run_optimizer(e, 1);
 }
@@ -1232,7 +1302,7 @@ static void run_train_group_body_staged(sb_engine* e, bool parity) {
     run_prologue_staged(e, parity ? 1 : 0, j);
     run_forward(e, FWD_TRAIN);
     run_loss(e, true);
-    run_backward(e);
+    run_backward_train(e);
     run_reg(e, true);
     run_optimizer(e, 0);
   }
@@ -1601,7 +1671,7 @@ extern "C" void sb_engine_destroy(sb_engine* e) {
       if (e->ev_free[i]) cudaEventDestroy(e->ev_free[i]);
     }
     if (e->cstream) { cudaStreamSynchronize(e->cstream); cudaStreamDestroy(e->cstream); }
-    if (e->bstream) { cudaStreamSynchronize(e->bstream); cudaStreamDestroy(e->bstream); cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join); }
+    if (e->bstream) { cudaStreamSynchronize(e->bstream); cudaStreamDestroy(e->bstream); cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join); cudaEventDestroy(e->ev_mid); }
     tc_free_layers(e);
     rnn_free(e);
     lstm_free(e);
@@ -1956,7 +2026,7 @@ extern "C" int sb_compute_grads(sb_engine* e, const float* x, const float* y, fl
   const long long before = tl_launch_count;
   run_forward(e, FWD_LOSS_ONLY);
   run_loss(e, true);
-  run_backward(e);
+  run_backward(e);  // gradients only: no optimizer follows, every gradient must be left complete
   run_reg(e, true);
   e->launches += tl_launch_count - before;
   float loss = read_loss(e);

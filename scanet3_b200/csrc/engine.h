@@ -138,7 +138,13 @@ struct sb_engine {
   // backward fork: a conv layer's filter gradient (tensor-core kernel + reduce) runs on `bstream` next to the input-gradient
   // chain (dgrad -> pool backward ...), joined before the penalties / optimizer; inside a captured graph this is a parallel branch
   cudaStream_t bstream = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_mid = nullptr;
+  // Early optimizer (SB_EARLY_OPT=0 turns it off): the side branch of layer `early_opt_layer` also updates every parameter from arena
+  // offset `early_opt_off` on (all their gradients exist by then), once that layer's dgrad has read the weights; the tail of the step
+  // then only updates the first layer's parameters [0, early_opt_off)
+  int early_opt_layer = -1;
+  int64_t early_opt_off = 0;
+  bool early_opt_now = false, early_opt_done = false;
   bool bwd_forked = false;
   sb::ReduceBatch pending_reduce;  // filter-gradient partial sums of this backward pass, reduced in one launch before the optimizer
   bool pdl_early = false;   // the shared kernels (prologue, optimizer, head loss, partial reduce) trigger their dependents early

@@ -323,6 +323,25 @@ def test_batchnorm_pool_block_matches_the_separate_kernels(monkeypatch):
     np.testing.assert_allclose(b[4], a[4], rtol=1e-4, atol=1e-6)
 
 
+@pytest.mark.parametrize("alg", ["adam", "amsgrad"])
+def test_early_optimizer_on_the_side_branch_is_bit_identical(alg, monkeypatch):
+    """Default; SB_EARLY_OPT=0 turns it off: conv2's side branch (filter gradient + reduction) also runs the optimizer update of every parameter from conv2
+    on, once conv2's dgrad has read the weights; the tail of the step only updates conv1.  Same arithmetic on the same gradients:
+    losses, parameters and optimizer state must be the same bits (TF32 mode: the tensor-core conv path is the one that forks)."""
+    _, sm = build_models(LENET)
+    x, y = synth_classification(24 * 4, (14, 14, 1), 10, 9)
+    outs = []
+    for on in ("0", "1"):
+        monkeypatch.setenv("SB_EARLY_OPT", on)
+        e = make_engine(sm, S.CategoricalCrossentropy, SALG[alg](rate=0.01), 24, (14, 14, 1), (10,), precision=S.PREC_TF32)
+        e.init_params()
+        losses = [e.train_step(x[i * 24:(i + 1) * 24], y[i * 24:(i + 1) * 24], i + 1) for i in range(4)]
+        outs.append((losses, {k: v.tobytes() for k, v in e.get_params().items()}))
+        e.close()
+    assert outs[0][0] == outs[1][0]
+    assert outs[0][1] == outs[1][1]
+
+
 def test_graph_and_eager_are_bit_identical():
     om, sm = build_models(MLP)
     x, y = synth_classification(400, (784,), 10, 11)
